@@ -1,0 +1,210 @@
+/* mavi.h — C ABI of libmavi_cuda.so, the B200 device backend for Mavi.jl's per-step hot path.
+ *
+ * The reference (Mavi.jl) has no FFI: its seam is Julia multiple dispatch on
+ * IntCfg.device::DeviceMode (src/configs.jl:471-487) -> calc_forces!(system, chunks, device)
+ * (src/integration.jl:112,159,197,226) and get_step_function (src/integration.jl:537-548,
+ * src/rings/integration.jl:545).  A `CUDADevice <: DeviceMode` on the Julia side `ccall`s the
+ * entry points below (binding shown in INTEGRATION.md).  Every entry point:
+ *   - is extern "C", takes plain pointers/sizes, never retains host pointers after returning,
+ *   - returns an int32 status (0 = MAVI_OK); mavi_last_error() gives the message.
+ *
+ * Memory contract: positions / velocities / forces are `Vector{SVector{2,T}}` on the Julia side
+ * (src/states.jl:75-125) == contiguous T[2*N] (x0,y0,x1,y1,...).  All ids crossing the ABI are the
+ * caller's ORIGINAL 0-based slot ids; the device reorders particles internally and un-permutes on
+ * download.  Cell ids are 0-based linear ids  cell = (col-1)*num_rows + (row-1)  of the reference's
+ * 1-based (row, col) (row 1 = TOP row, src/chunks.jl:129-130; row index fastest, src/chunks.jl:35-36).
+ */
+#ifndef MAVI_H
+#define MAVI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAVI_ABI_VERSION 1
+#define MAVI_MAX_SPACES 8
+
+/* status codes (reference: Julia exceptions, see INTEGRATION.md "Error conventions") */
+enum {
+  MAVI_OK = 0,
+  MAVI_ERR_BAD_PARAMS = 1,   /* error(...) in constructors, src/rings/rings.jl:233-262 */
+  MAVI_ERR_OUT_OF_GRID = 2,  /* BoundsError from chunk_particles[...], src/chunks.jl:144-146 */
+  MAVI_ERR_NAN = 3,
+  MAVI_ERR_CUDA = 4,
+  MAVI_ERR_NCCL = 5,
+  MAVI_ERR_OUTSIDE_SPACE = 6, /* throw("Particles with ids=... outside space."), src/systems.jl:76-79 */
+  MAVI_ERR_CAPACITY = 7,      /* halo / migration buffer overflow (multi-GPU only) */
+  MAVI_ERR_UNSUPPORTED = 8
+};
+
+enum { MAVI_F64 = 0, MAVI_F32 = 1 };
+
+/* WallType subtypes, src/configs.jl:235-279 */
+enum { MAVI_WALL_RIGID = 0, MAVI_WALL_PERIODIC = 1, MAVI_WALL_SLIPPERY = 2, MAVI_WALL_POTENTIAL = 3 };
+/* GeometryCfg subtypes, src/configs.jl:28-152 */
+enum { MAVI_GEOM_RECT = 0, MAVI_GEOM_CIRCLE = 1, MAVI_GEOM_LINES = 2 };
+/* PotentialCfg used by PotentialWalls, src/configs.jl:341-397 */
+enum { MAVI_POT_HARMTRUNC = 0, MAVI_POT_LJ = 1 };
+/* PotentialWallMode, src/configs.jl:252-261 */
+enum { MAVI_WALLMODE_OUTSIDE = 0, MAVI_WALLMODE_INSIDE = 1, MAVI_WALLMODE_REPULSION = 2 };
+/* DynamicCfg subtypes, src/configs.jl:341-415, src/rings/configs.jl:95-107 */
+enum { MAVI_DYN_LJ = 0, MAVI_DYN_HARMTRUNC = 1, MAVI_DYN_SZABO = 2, MAVI_DYN_RTP = 3, MAVI_DYN_RINGS = 4 };
+/* stochastic terms: caller-supplied noise (exact parity) or device Philox4x32-10 (production) */
+enum { MAVI_RNG_HOST_NOISE = 0, MAVI_RNG_PHILOX = 1 };
+
+/* Line2D (src/configs.jl:95-117): normal/tangent/length are derived exactly as the ctor does. */
+typedef struct MaviLine {
+  double p1[2];
+  double p2[2];
+} MaviLine;
+
+/* One (wall_type, geometry_cfg) pair of a SpaceCfg (src/configs.jl:285-302).  spaces[0] is the
+ * main wall/geometry (get_main_wall / get_main_geometry, src/configs.jl:304-312). */
+typedef struct MaviSpace {
+  int32_t wall;          /* MAVI_WALL_* */
+  int32_t geom;          /* MAVI_GEOM_* */
+  double rect_bl[2];     /* RectangleCfg.bottom_left */
+  double rect_len;       /* RectangleCfg.length */
+  double rect_h;         /* RectangleCfg.height */
+  double circ_center[2]; /* CircleCfg.center */
+  double circ_radius;    /* CircleCfg.radius */
+  const MaviLine *lines; /* LinesCfg.lines (copied at create) */
+  int32_t n_lines;
+  int32_t pot_kind;      /* PotentialWalls.potential: MAVI_POT_* */
+  double pot[4];         /* HarmTrunc: k_rep,k_atr,dist_eq,dist_max; LJ: sigma,epsilon */
+  int32_t pot_mode;      /* MAVI_WALLMODE_* */
+  int32_t _pad;
+} MaviSpace;
+
+/* RingsCfg + RingsState layout (src/rings/configs.jl:95-107, src/rings/states.jl:74-124).
+ * Scalar idx of particle p (0-based) of ring r (0-based) = r*n_max + p (src/rings/states.jl:137-139). */
+typedef struct MaviRingsParams {
+  int32_t num_types;
+  int32_t n_max;             /* num_max_particles = size(rings_pos, 1) */
+  int64_t num_rings;
+  const double *p0, *relax_time, *vo, *mobility, *rot_diff, *k_area, *k_spring, *l_spring; /* [num_types] */
+  const int32_t *num_particles; /* [num_types] */
+  const double *interaction;    /* [num_types][num_types][4] = k_rep,k_atr,dist_eq,dist_max (InteractionMatrix, src/rings/configs.jl:59-89) */
+  const int32_t *types;         /* [num_rings], 1-based ring types, or NULL when the state has no types */
+} MaviRingsParams;
+
+typedef struct MaviParams {
+  uint32_t struct_size; /* sizeof(MaviParams), ABI check */
+  int32_t dtype;        /* MAVI_F64 (default) / MAVI_F32 */
+  int64_t n;            /* number of particle slots = length(state.pos) */
+
+  int32_t n_spaces;
+  int32_t _pad0;
+  MaviSpace spaces[MAVI_MAX_SPACES];
+
+  /* Chunks (src/chunks.jl:26-40): grid over the bounding box of the geometry (src/systems.jl:14-28).
+   * num_cols == 0 -> chunks === nothing -> all-pairs path (src/integration.jl:197-224). */
+  double grid_bl[2];
+  double grid_len;
+  double grid_h;
+  int32_t num_cols;
+  int32_t num_rows;
+
+  int32_t dynamics; /* MAVI_DYN_* */
+  int32_t _pad1;
+  /* LJ: sigma,epsilon | HarmTrunc: k_rep,k_atr,dist_eq,dist_max |
+   * Szabo: vo,mobility,relax_time,k_rep,k_adh,r_eq,r_max,rot_diff | RTP: vo,sigma,epsilon,tumble_rate */
+  double dyn[8];
+  double particle_radius; /* particle_radius(dynamic_cfg) as computed by the host (src/configs.jl:418-421); Rings: minimum over types */
+  const MaviRingsParams *rings; /* MAVI_DYN_RINGS only */
+
+  double dt; /* IntCfg.dt */
+
+  int32_t rng_mode; /* MAVI_RNG_* */
+  int32_t _pad2;
+  uint64_t seed;
+
+  int32_t device; /* CUDA device ordinal */
+  int32_t flags;  /* MAVI_FLAG_* */
+  void *stream;   /* cudaStream_t to enqueue on, or NULL for the legacy default stream */
+
+  /* x-slab domain decomposition, one process per GPU.  world<=1 -> single GPU. */
+  int32_t rank;
+  int32_t world;
+  const void *nccl_unique_id; /* ncclUniqueId bytes (128), same on every rank */
+  int64_t n_global;           /* total particle count over all ranks (0 -> n) */
+} MaviParams;
+
+/* flags */
+#define MAVI_FLAG_RESORT_EVERY_STEP 1 /* disable the "nobody changed cell -> keep order" fast path (A/B testing) */
+
+typedef struct MaviHandle MaviHandle;
+
+/* ---- lifetime -------------------------------------------------------------------------------
+ * replaces: System(...) ctor, src/systems.jl:73-114 (force buffers, Chunks build, first update_chunks!)
+ *           RingsSystem(...) ctor, src/rings/rings.jl:231-291 */
+int32_t mavi_create(const MaviParams *params, MaviHandle **out);
+int32_t mavi_destroy(MaviHandle *h);
+int32_t mavi_abi_version(void);
+
+/* ---- state movement (the only host<->device copies) -------------------------------------------
+ * replaces direct reads/writes of system.state.{pos,vel,pol_angle,pol}.
+ * `second` is vel (SecondLawState, T[2n]) or pol_angle (SelfPropelledState, T[n]) or pol
+ * (RingsState, T[num_rings]).  active_mask (n bytes, may be NULL = all active) is the ParticleIds mask
+ * (src/states.jl:27-52).  The constructor-time inside check (src/space_checks.jl:9-37) runs here. */
+int32_t mavi_upload_state(MaviHandle *h, const void *pos, const void *second, const uint8_t *active_mask, int64_t n);
+int32_t mavi_download_state(MaviHandle *h, void *pos, void *second);
+/* get_forces(system), src/systems.jl:117 */
+int32_t mavi_download_forces(MaviHandle *h, void *forces);
+/* multi-GPU only: original ids of the particles this rank currently owns, and their count */
+int32_t mavi_local_count(MaviHandle *h, int64_t *n_local);
+int32_t mavi_download_local(MaviHandle *h, int64_t *ids, void *pos, void *second, void *forces);
+
+/* ---- the hot path ---------------------------------------------------------------------------
+ * mavi_step: nsteps x (newton_step! | szabo_step! | rtp_step!  src/integration.jl:507-535 |
+ *                      Rings step!  src/rings/integration.jl:522-543), chosen like get_step_function.
+ * host_noise (MAVI_RNG_HOST_NOISE): per step  Szabo T[n] (randn, src/integration.jl:460) |
+ *   RTP T[2n] (u, u2 pairs, src/integration.jl:493-495) | Rings T[num_rings] (randn, src/rings/integration.jl:348);
+ *   may be NULL when the stochastic amplitude is zero or for Newton dynamics. */
+int32_t mavi_step(MaviHandle *h, int64_t nsteps, const void *host_noise);
+/* clean_forces! + update_chunks! + calc_forces! (+ Rings: springs, area forces) + calc_walls_forces!:
+ * the force state a reference system holds right after these calls (src/integration.jl:508-511) */
+int32_t mavi_calc_forces(MaviHandle *h);
+/* update_chunks!(system.chunks), src/chunks.jl:150-163, src/integration.jl:54-59 */
+int32_t mavi_bin(MaviHandle *h);
+/* cell_of_particle[n] (0-based linear cell id, -1 for inactive), counts[num_rows*num_cols]
+ * (== num_particles_in_chunk, row fastest).  Either pointer may be NULL. */
+int32_t mavi_download_cells(MaviHandle *h, int32_t *cell_of_particle, int32_t *counts);
+/* chunk_particles as CSR: start[num_cells+1], ids[n_active] ascending ids inside each cell
+ * (== the reference's fill order, src/chunks.jl:153-155).  Either pointer may be NULL. */
+int32_t mavi_download_cell_lists(MaviHandle *h, int32_t *start, int32_t *ids);
+/* neighbour stencil actually used by the pair kernels for cell `cell`: up to 8 neighbour cell ids
+ * (the reference's half stencil src/chunks.jl:61-118 united with its mirror image); returns count in *n. */
+int32_t mavi_cell_neighbors(MaviHandle *h, int32_t cell, int32_t *out8, int32_t *n);
+
+/* ---- quantities, src/quantities.jl ----------------------------------------------------------
+ * ke = kinetic_energy (:12-18; NaN for states without vel).  pe_mode 0: exact all-pairs LJ
+ * potential_energy (:46-66, O(N^2)); 1: sum over the cell-stencil pair set (labelled deviation). */
+int32_t mavi_energies(MaviHandle *h, int32_t pe_mode, double *ke, double *pe);
+
+/* ---- Rings info, src/rings/rings.jl:118-217 -------------------------------------------------
+ * areas[num_rings], cms[2*num_rings], cont_pos[2*n] (continuos_pos).  Any pointer may be NULL. */
+int32_t mavi_rings_download_info(MaviHandle *h, void *areas, void *cms, void *cont_pos);
+
+/* TimeInfo, src/systems.jl:30-33 (time += dt accumulated in Float64, src/integration.jl:500-503) */
+int32_t mavi_get_time(MaviHandle *h, int64_t *num_steps, double *time);
+int32_t mavi_set_time(MaviHandle *h, int64_t num_steps, double time);
+
+/* blocks until all enqueued work is done and returns the deferred device error word as status */
+int32_t mavi_sync(MaviHandle *h);
+int32_t mavi_last_error(MaviHandle *h, char *buf, int32_t n);
+
+/* ---- instrumentation (bench.py / tests) ------------------------------------------------------ */
+/* number of kernels this handle has launched since creation */
+int32_t mavi_launch_count(MaviHandle *h, int64_t *n);
+/* device time of the last mavi_step call per phase, CUDA events on the launching stream:
+ * ms[0]=bin+sort ms[1]=pass A ms[2]=pass B (or the single fused pass) ms[3]=exchange ms[4]=total */
+int32_t mavi_last_step_ms(MaviHandle *h, float *ms5);
+int32_t mavi_set_profiling(MaviHandle *h, int32_t on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAVI_H */

@@ -1,0 +1,189 @@
+"""Host-side mirror of `Mavi.Systems.System` (reference: src/systems.jl:45-114) bound to a device handle.
+
+`System(...)` keeps the reference's keyword signature.  Construction lowers the configs, creates the device
+context (`mavi_create`) and uploads the state (`mavi_upload_state`) — the points where the reference allocates
+force buffers, builds `Chunks` and runs the first `update_chunks!`.  Particle state then stays device-resident;
+`sync_to_host!` (here `sync_to_host`) is the copy-back hook for GUI / experiment / checkpoint code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .configs import CUDADevice, SpaceCfg
+from .params import lower
+
+
+class TimeInfo:
+    """src/systems.jl:30-33."""
+
+    def __init__(self, num_steps=0, time=0.0):
+        self.num_steps = num_steps
+        self.time = time
+
+
+class StandardSys:
+    pass
+
+
+class RingsSys:
+    pass
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class System:
+    def __init__(self, *, state, space_cfg: SpaceCfg, dynamic_cfg, int_cfg, info=None, debug_info=None,
+                 time_info=None, sys_type="standard", rng=None):
+        self.state = state
+        self.space_cfg = space_cfg
+        self.dynamic_cfg = dynamic_cfg
+        self.int_cfg = int_cfg
+        self.info = info
+        self.debug_info = debug_info
+        self.time_info = time_info or TimeInfo(0, 0.0)
+        self.type = StandardSys() if sys_type == "standard" else sys_type
+        self.rng = rng
+        if not isinstance(int_cfg.device, CUDADevice):
+            raise TypeError("this backend implements IntCfg(device=CUDADevice()); Sequencial/Threaded are the "
+                            "reference's own CPU paths and are not reimplemented here (no CPU fallback)")
+        self._lib = capi.load_library()
+        self._lowered = lower(state, space_cfg, dynamic_cfg, int_cfg)
+        self._dtype = np.float32 if self._lowered.params.dtype == capi.F32 else np.float64
+        self._h = C.c_void_p()
+        self._n = len(state.pos)
+        self._forces = None
+        self._check(self._lib.mavi_create(C.byref(self._lowered.params), C.byref(self._h)))
+        self._check(self._lib.mavi_set_time(self._h, self.time_info.num_steps, self.time_info.time))
+        self.upload_state()
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, status):
+        if status != capi.OK:
+            buf = C.create_string_buffer(512)
+            if self._h:
+                self._lib.mavi_last_error(self._h, buf, 512)
+            raise capi.MaviError(status, buf.value.decode(errors="replace"))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mavi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ state movement
+    def upload_state(self):
+        """Host state -> device (after construction or after the host edited `system.state`)."""
+        st = self.state
+        pos = np.ascontiguousarray(st.pos, dtype=self._dtype)
+        second = np.ascontiguousarray(st.second, dtype=self._dtype)
+        mask = st.active_mask()
+        self._check(self._lib.mavi_upload_state(self._h, _ptr(pos), _ptr(second), _ptr(mask), self._n))
+
+    def sync_to_host(self):
+        """`sync_to_host!(system)`: device state -> `system.state` arrays, and TimeInfo."""
+        st = self.state
+        pos = np.empty((self._n, 2), dtype=self._dtype)
+        second = np.empty(st.second.shape, dtype=self._dtype)
+        self._check(self._lib.mavi_download_state(self._h, _ptr(pos), _ptr(second)))
+        st.pos[...] = pos
+        st.second[...] = second
+        ns, t = C.c_int64(), C.c_double()
+        self._check(self._lib.mavi_get_time(self._h, C.byref(ns), C.byref(t)))
+        self.time_info.num_steps, self.time_info.time = ns.value, t.value
+        return self
+
+    def sync(self):
+        self._check(self._lib.mavi_sync(self._h))
+
+    # ------------------------------------------------------------------ hot path
+    def step(self, nsteps=1, host_noise=None):
+        """nsteps x the step function `get_step_function(system)` selects (src/integration.jl:537-548)."""
+        noise = None if host_noise is None else np.ascontiguousarray(host_noise, dtype=self._dtype)
+        self._check(self._lib.mavi_step(self._h, nsteps, _ptr(noise)))
+        # time_info advances on the host exactly like update_time! (time += dt per step, Float64)
+        dt = float(self.int_cfg.dt)
+        for _ in range(nsteps):
+            self.time_info.time += dt
+            self.time_info.num_steps += 1
+
+    def calc_forces(self):
+        self._check(self._lib.mavi_calc_forces(self._h))
+
+    def update_chunks(self):
+        self._check(self._lib.mavi_bin(self._h))
+
+    def get_forces(self):
+        """`get_forces(system)`, src/systems.jl:117 (downloads; (N, 2))."""
+        f = np.empty((self._n, 2), dtype=self._dtype)
+        self._check(self._lib.mavi_download_forces(self._h, _ptr(f)))
+        return f
+
+    # ------------------------------------------------------------------ chunks inspection (parity checks)
+    @property
+    def num_cells(self):
+        p = self._lowered.params
+        return p.num_cols * p.num_rows
+
+    def download_cells(self):
+        cell = np.empty(self._n, dtype=np.int32)
+        counts = np.empty(self.num_cells, dtype=np.int32)
+        self._check(self._lib.mavi_download_cells(self._h, _ptr(cell), _ptr(counts)))
+        return cell, counts
+
+    def download_cell_lists(self):
+        start = np.empty(self.num_cells + 1, dtype=np.int32)
+        ids = np.full(self._n, -1, dtype=np.int32)
+        self._check(self._lib.mavi_download_cell_lists(self._h, _ptr(start), _ptr(ids)))
+        return start, ids[: start[-1]]
+
+    def cell_neighbors(self, cell):
+        out = (C.c_int32 * 8)()
+        n = C.c_int32()
+        self._check(self._lib.mavi_cell_neighbors(self._h, cell, out, C.byref(n)))
+        return [out[i] for i in range(n.value)]
+
+    # ------------------------------------------------------------------ quantities / instrumentation
+    def energies(self, pe_mode=0):
+        ke, pe = C.c_double(), C.c_double()
+        self._check(self._lib.mavi_energies(self._h, pe_mode, C.byref(ke), C.byref(pe)))
+        return ke.value, pe.value
+
+    def launch_count(self):
+        n = C.c_int64()
+        self._check(self._lib.mavi_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def set_profiling(self, on=True):
+        self._check(self._lib.mavi_set_profiling(self._h, int(on)))
+
+    def last_step_ms(self):
+        ms = (C.c_float * 5)()
+        self._check(self._lib.mavi_last_step_ms(self._h, ms))
+        return list(ms)
+
+    def rings_info(self):
+        nr = self.state.num_rings
+        areas = np.empty(nr, dtype=self._dtype)
+        cms = np.empty((nr, 2), dtype=self._dtype)
+        cont = np.empty((self._n, 2), dtype=self._dtype)
+        self._check(self._lib.mavi_rings_download_info(self._h, _ptr(areas), _ptr(cms), _ptr(cont)))
+        return areas, cms, cont
+
+
+def get_forces(system):
+    return system.get_forces()
+
+
+def get_num_total_particles(system):
+    from .states import get_num_total_particles as g
+    return g(system.state)

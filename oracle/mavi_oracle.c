@@ -1,0 +1,1117 @@
+/* mavi_oracle.c — CPU oracle (plain C) for the Mavi.jl per-step hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * PARITY UNPINNED (see mavi_oracle.h): Julia cannot run in this image and the reference's tests hold
+ * no portable golden vectors for this path; every function below cites the reference lines it restates.
+ * All `file:line` citations are relative to /root/reference/.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fopenmp -fPIC -shared   (no FMA contraction: Julia does not contract)
+ */
+#include "mavi_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+struct OrSystem {
+  MaviParams p;
+  MaviLine *lines[MAVI_MAX_SPACES];
+  MaviRingsParams rp; /* deep copy */
+  int64_t n;
+  double *pos;    /* [2n] */
+  double *second; /* vel [2n] | pol_angle [n] | ring pol [num_rings] */
+  uint8_t *mask;
+  int64_t *ids;   /* active particle ids, 0-based, ascending (get_particles_ids) */
+  int64_t n_ids;
+  int32_t nthreads;
+  double **forces; /* forces[t][2n]  (src/systems.jl:89-97) */
+  /* Chunks (src/chunks.jl:10-25) */
+  int has_chunks;
+  int64_t num_cols, num_rows, nc;
+  double cl, ch;
+  int64_t *chunk_particles; /* [nc][rows][cols], first index fastest */
+  int64_t *num_in_chunk;    /* [rows][cols], row fastest */
+  int32_t *neigh;           /* [cells][4] linear cell ids (row + rows*col) */
+  int8_t *neigh_n;
+  /* RingsInfo (src/rings/rings.jl:118-128) */
+  double *cont_pos, *areas, *cms;
+  int64_t num_steps;
+  double time;
+  char err[256];
+};
+
+/* ------------------------------------------------------------------ helpers */
+
+static double *dup_d(const double *src, int64_t n) {
+  double *d = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  if (src) memcpy(d, src, sizeof(double) * (size_t)n);
+  return d;
+}
+
+static int is_periodic(const OrSystem *s) {
+  /* calc_diff dispatch: SpaceCfg{PeriodicWalls, RectangleCfg}; ManyWalls -> first pair (src/integration.jl:43-52) */
+  return s->p.spaces[0].wall == MAVI_WALL_PERIODIC && s->p.spaces[0].geom == MAVI_GEOM_RECT;
+}
+
+/* Base.div(x::Float64, y::Float64) = round((x - rem(x, y)) / y)  (Julia Base, not under /root/reference;
+ * call sites src/chunks.jl:129-130).  rem == C fmod, round == rint (ties to even). */
+double mor_julia_div(double x, double y) { return rint((x - fmod(x, y)) / y); }
+
+/* calc_diff, src/integration.jl:38-52 */
+void mor_calc_diff(const OrSystem *s, const double *r1, const double *r2, double *dr) {
+  dr[0] = r1[0] - r2[0];
+  dr[1] = r1[1] - r2[1];
+  if (is_periodic(s)) {
+    const double sz[2] = {s->p.spaces[0].rect_len, s->p.spaces[0].rect_h};
+    for (int d = 0; d < 2; d++) {
+      /* dr - (abs(dr) > size/2) * copysign(size, dr) */
+      double flag = fabs(dr[d]) > (sz[d] / 2) ? 1.0 : 0.0;
+      dr[d] = dr[d] - flag * copysign(sz[d], dr[d]);
+    }
+  }
+}
+
+/* potential_force(dr, dist, potential): HarmTrunc src/configs.jl:354-368, LenJones :389-397 */
+void mor_potential_force(int32_t kind, const double *par, const double *dr, double dist, double *f) {
+  if (kind == MAVI_POT_HARMTRUNC) {
+    const double k_rep = par[0], k_atr = par[1], dist_eq = par[2], dist_max = par[3];
+    if (dist > dist_max) {
+      f[0] = 0.0; f[1] = 0.0;
+      return;
+    }
+    double fmod_;
+    if (dist < dist_eq) fmod_ = -k_rep * (dist / dist_eq - 1);
+    else fmod_ = -k_atr * (dist / dist_eq - 1);
+    double c = fmod_ / dist;
+    f[0] = c * dr[0]; f[1] = c * dr[1];
+  } else {
+    const double sigma = par[0], epsilon = par[1];
+    double fmod_ = 4 * epsilon * (12 * pow(sigma, 12) / pow(dist, 13) - 6 * pow(sigma, 6) / pow(dist, 7));
+    double c = fmod_ / dist;
+    f[0] = c * dr[0]; f[1] = c * dr[1];
+  }
+}
+
+/* calc_interaction(::SzaboCfg), src/integration.jl:68-87.  dr is NOT normalised (sic). */
+void mor_szabo_interaction(const double *par, const double *dr, double *f) {
+  const double k_rep = par[3], k_adh = par[4], r_eq = par[5], r_max = par[6];
+  double dist = sqrt(dr[0] * dr[0] + dr[1] * dr[1]);
+  if (dist > r_max) {
+    f[0] = 0.0; f[1] = 0.0;
+    return;
+  }
+  double f_mod;
+  if (dist > r_eq) f_mod = k_adh / r_eq;
+  else f_mod = k_rep / (r_max - r_eq);
+  double r = dist - r_eq;
+  double c = -f_mod * r;
+  f[0] = c * dr[0]; f[1] = c * dr[1];
+}
+
+/* calc_interaction(::RunTumbleCfg), src/integration.jl:89-109 (WCA) */
+void mor_rtp_interaction(const double *par, const double *dr, double *f) {
+  const double sigma = par[1], epsilon = par[2];
+  double dist = sqrt(dr[0] * dr[0] + dr[1] * dr[1]);
+  double cutoff = pow(2.0, 1.0 / 6.0) * sigma;
+  if (dist > cutoff) {
+    f[0] = 0.0; f[1] = 0.0;
+    return;
+  }
+  double fmod_ = -4 * epsilon * (-12 * pow(sigma, 12) / pow(dist, 13) + 6 * pow(sigma, 6) / pow(dist, 7));
+  double c = fmod_ / dist;
+  f[0] = c * dr[0]; f[1] = c * dr[1];
+}
+
+/* ring helpers, src/rings/states.jl:137-146, :195-198 */
+static inline int64_t ring_of(const OrSystem *s, int64_t idx0) { return idx0 / s->rp.n_max; }
+static inline int32_t ring_type(const OrSystem *s, int64_t ring0) { return s->rp.types ? s->rp.types[ring0] - 1 : 0; }
+static inline int32_t ring_np(const OrSystem *s, int64_t ring0) { return s->rp.num_particles[ring_type(s, ring0)]; }
+
+/* Rings calc_interaction + calc_interaction_force, src/rings/integration.jl:32-77 */
+static void rings_interaction(const OrSystem *s, int64_t i, int64_t j, double *f) {
+  int64_t ri = ring_of(s, i), rj = ring_of(s, j);
+  const double *ic = s->rp.interaction + 4 * ((int64_t)ring_type(s, ri) * s->rp.num_types + ring_type(s, rj));
+  double dr[2];
+  mor_calc_diff(s, s->pos + 2 * i, s->pos + 2 * j, dr);
+  double dist = sqrt(dr[0] * dr[0] + dr[1] * dr[1]);
+  const double k_rep = ic[0], k_atr = ic[1], dist_eq = ic[2], dist_max = ic[3];
+  f[0] = 0.0; f[1] = 0.0;
+  if (dist > dist_max) return;
+  if (ri == rj) {
+    int64_t diff = i > j ? i - j : j - i;
+    int64_t num_p = ring_np(s, ri);
+    if (diff == 1 || diff == num_p - 1) return;
+  }
+  double fmod_;
+  if (dist < dist_eq) fmod_ = -k_rep * (dist / dist_eq - 1);
+  else {
+    if (ri == rj) fmod_ = 0.0;
+    else fmod_ = -k_atr * (dist / dist_eq - 1);
+  }
+  double c = fmod_ / dist;
+  f[0] = c * dr[0]; f[1] = c * dr[1];
+}
+
+/* calc_interaction dispatch, src/integration.jl:62-109, src/rings/integration.jl:32-45 */
+static inline void interaction(const OrSystem *s, int64_t i, int64_t j, double *f) {
+  double dr[2];
+  switch (s->p.dynamics) {
+    case MAVI_DYN_LJ:
+      mor_calc_diff(s, s->pos + 2 * i, s->pos + 2 * j, dr);
+      mor_potential_force(MAVI_POT_LJ, s->p.dyn, dr, sqrt(dr[0] * dr[0] + dr[1] * dr[1]), f);
+      break;
+    case MAVI_DYN_HARMTRUNC:
+      mor_calc_diff(s, s->pos + 2 * i, s->pos + 2 * j, dr);
+      mor_potential_force(MAVI_POT_HARMTRUNC, s->p.dyn, dr, sqrt(dr[0] * dr[0] + dr[1] * dr[1]), f);
+      break;
+    case MAVI_DYN_SZABO:
+      mor_calc_diff(s, s->pos + 2 * i, s->pos + 2 * j, dr);
+      mor_szabo_interaction(s->p.dyn, dr, f);
+      break;
+    case MAVI_DYN_RTP:
+      mor_calc_diff(s, s->pos + 2 * i, s->pos + 2 * j, dr);
+      mor_rtp_interaction(s->p.dyn, dr, f);
+      break;
+    default:
+      rings_interaction(s, i, j, f);
+  }
+}
+
+/* ------------------------------------------------------------------ chunks */
+
+/* get_neighbors periodic, src/chunks.jl:61-87 */
+static int64_t wrap_id(int64_t x, int64_t num_t) {
+  if (x == 0) return num_t;
+  if (x % (num_t + 1) == 0) return 1;
+  return x;
+}
+
+static void build_neighbors(OrSystem *s) {
+  const int64_t nr = s->num_rows, ncl = s->num_cols;
+  s->neigh = (int32_t *)malloc(sizeof(int32_t) * 4 * (size_t)(nr * ncl));
+  s->neigh_n = (int8_t *)calloc((size_t)(nr * ncl), 1);
+#define CELL(i, j) ((int32_t)(((i)-1) + nr * ((j)-1)))
+#define PUSH(i, j, ii, jj)                                          \
+  do {                                                              \
+    int32_t c_ = CELL(i, j);                                        \
+    s->neigh[4 * c_ + s->neigh_n[c_]] = CELL(ii, jj);               \
+    s->neigh_n[c_]++;                                               \
+  } while (0)
+  if (s->p.spaces[0].wall == MAVI_WALL_PERIODIC) {
+    for (int64_t i = 1; i <= nr; i++)
+      for (int64_t j = 1; j <= ncl; j++) {
+        PUSH(i, j, wrap_id(i + 1, nr), wrap_id(j, ncl));
+        PUSH(i, j, wrap_id(i + 1, nr), wrap_id(j + 1, ncl));
+        PUSH(i, j, wrap_id(i, nr), wrap_id(j + 1, ncl));
+        PUSH(i, j, wrap_id(i - 1, nr), wrap_id(j + 1, ncl));
+      }
+  } else {
+    /* get_neighbors walled, src/chunks.jl:89-118.  Later assignments overwrite earlier ones. */
+    for (int64_t i = 1; i <= nr - 1; i++) {
+      s->neigh_n[CELL(i, 1)] = 0;
+      PUSH(i, 1, i + 1, 1);
+      PUSH(i, 1, i + 1, 2);
+      PUSH(i, 1, i, 2);
+      for (int64_t j = 2; j <= ncl - 1; j++) {
+        s->neigh_n[CELL(i, j)] = 0;
+        PUSH(i, j, i + 1, j - 1);
+        PUSH(i, j, i + 1, j);
+        PUSH(i, j, i + 1, j + 1);
+        PUSH(i, j, i, j + 1);
+      }
+      s->neigh_n[CELL(i, ncl)] = 0;
+      PUSH(i, ncl, i + 1, ncl - 1);
+      PUSH(i, ncl, i + 1, ncl);
+    }
+    for (int64_t j = 1; j <= ncl - 1; j++) {
+      s->neigh_n[CELL(nr, j)] = 0;
+      PUSH(nr, j, nr, j + 1);
+    }
+    s->neigh_n[CELL(nr, ncl)] = 0;
+  }
+#undef PUSH
+#undef CELL
+}
+
+/* Chunks ctor, src/chunks.jl:26-40 (+ get_chunks, src/systems.jl:14-28) */
+static int32_t chunks_init(OrSystem *s) {
+  s->has_chunks = s->p.num_cols > 0;
+  if (!s->has_chunks) return MAVI_OK;
+  s->num_cols = s->p.num_cols;
+  s->num_rows = s->p.num_rows;
+  if (s->num_rows < 1) return MAVI_ERR_BAD_PARAMS;
+  if (s->p.spaces[0].wall != MAVI_WALL_PERIODIC && s->num_cols < 2) {
+    snprintf(s->err, sizeof s->err, "walled neighbour table needs num_cols >= 2 (reference indexes column 0)");
+    return MAVI_ERR_BAD_PARAMS;
+  }
+  s->cl = s->p.grid_len / (double)s->num_cols;
+  s->ch = s->p.grid_h / (double)s->num_rows;
+  double r = s->p.particle_radius;
+  double ncf = (ceil(0.5 * s->cl / r) + 1) * (ceil(0.5 * s->ch / r) + 1);
+  s->nc = (int64_t)ceil(ncf * 2);
+  size_t cells = (size_t)(s->num_rows * s->num_cols);
+  s->chunk_particles = (int64_t *)malloc(sizeof(int64_t) * cells * (size_t)s->nc);
+  s->num_in_chunk = (int64_t *)calloc(cells, sizeof(int64_t));
+  build_neighbors(s);
+  return MAVI_OK;
+}
+
+/* update_particle_chunk!, src/chunks.jl:120-147.  i is 0-based here; the table stores 0-based ids. */
+static int32_t update_particle_chunk(OrSystem *s, int64_t i) {
+  const double space_h = s->p.grid_h;
+  const double *bl = s->p.grid_bl;
+  const double x = s->pos[2 * i], y = s->pos[2 * i + 1];
+  double rowf = mor_julia_div(-y + bl[1] + space_h, s->ch);
+  double colf = mor_julia_div(x - bl[0], s->cl);
+  if (!(fabs(rowf) < 9.0e15) || !(fabs(colf) < 9.0e15)) { /* trunc(Int, NaN/Inf) -> InexactError */
+    snprintf(s->err, sizeof s->err, "particle %lld: non-finite cell index", (long long)i);
+    return MAVI_ERR_OUT_OF_GRID;
+  }
+  int64_t row_id = (int64_t)rowf + 1;
+  int64_t col_id = (int64_t)colf + 1;
+  row_id -= row_id == (s->num_rows + 1) ? 1 : 0;
+  col_id -= col_id == (s->num_cols + 1) ? 1 : 0;
+  if (row_id < 1 || row_id > s->num_rows || col_id < 1 || col_id > s->num_cols) {
+    snprintf(s->err, sizeof s->err, "particle %lld out of grid (row %lld col %lld): BoundsError in the reference",
+             (long long)i, (long long)row_id, (long long)col_id);
+    return MAVI_ERR_OUT_OF_GRID;
+  }
+  int64_t cell = (row_id - 1) + s->num_rows * (col_id - 1);
+  int64_t p_i = s->num_in_chunk[cell];
+  if (p_i >= s->nc) {
+    snprintf(s->err, sizeof s->err, "cell %lld over capacity nc=%lld: BoundsError in the reference", (long long)cell,
+             (long long)s->nc);
+    return MAVI_ERR_CAPACITY;
+  }
+  s->chunk_particles[cell * s->nc + p_i] = i;
+  s->num_in_chunk[cell] += 1;
+  return MAVI_OK;
+}
+
+/* update_chunks!, State-aware: active ids only.  src/integration.jl:54-59, src/rings/integration.jl:18-23 */
+int32_t mor_update_chunks(OrSystem *s) {
+  if (!s->has_chunks) return MAVI_OK; /* update_chunks!(::Nothing), src/chunks.jl:165 */
+  memset(s->num_in_chunk, 0, sizeof(int64_t) * (size_t)(s->num_rows * s->num_cols));
+  for (int64_t k = 0; k < s->n_ids; k++) {
+    int32_t st = update_particle_chunk(s, s->ids[k]);
+    if (st) return st;
+  }
+  return MAVI_OK;
+}
+
+/* ------------------------------------------------------------------ forces */
+
+/* clean_forces!, src/systems.jl:119-123 */
+void mor_clean_forces(OrSystem *s) {
+  for (int t = 0; t < s->nthreads; t++) memset(s->forces[t], 0, sizeof(double) * 2 * (size_t)s->n);
+}
+
+static inline void pair_scatter(const OrSystem *s, double *forces, int64_t p1, int64_t p2) {
+  double f[2];
+  interaction(s, p1, p2, f);
+  forces[2 * p1] += f[0];
+  forces[2 * p1 + 1] += f[1];
+  forces[2 * p2] -= f[0];
+  forces[2 * p2 + 1] -= f[1];
+}
+
+/* one cell column of calc_forces!(system, chunks, device), src/integration.jl:116-156 / :160-190 */
+static void forces_column(const OrSystem *s, double *forces, int64_t col /*0-based*/) {
+  for (int64_t row = 0; row < s->num_rows; row++) {
+    int64_t cell = row + s->num_rows * col;
+    int64_t np = s->num_in_chunk[cell];
+    const int64_t *chunk = s->chunk_particles + cell * s->nc;
+    for (int64_t i = 0; i < np; i++) {
+      int64_t p1 = chunk[i];
+      for (int64_t j = i + 1; j < np; j++) pair_scatter(s, forces, p1, chunk[j]);
+      for (int k = 0; k < s->neigh_n[cell]; k++) {
+        int64_t ncell = s->neigh[4 * cell + k];
+        int64_t nei_np = s->num_in_chunk[ncell];
+        const int64_t *nei_chunk = s->chunk_particles + ncell * s->nc;
+        for (int64_t j = 0; j < nei_np; j++) pair_scatter(s, forces, p1, nei_chunk[j]);
+      }
+    }
+  }
+}
+
+/* calc_forces!(system): dispatch of src/integration.jl:226 */
+void mor_pair_forces(OrSystem *s) {
+  if (!s->has_chunks) {
+    /* all pairs over active ids, src/integration.jl:197-224 */
+    double *forces = s->forces[0];
+    for (int64_t i = 0; i < s->n_ids; i++)
+      for (int64_t j = i + 1; j < s->n_ids; j++) pair_scatter(s, forces, s->ids[i], s->ids[j]);
+    return;
+  }
+  if (s->nthreads <= 1) {
+    /* Sequencial, src/integration.jl:112-157: for col, for row */
+    for (int64_t col = 0; col < s->num_cols; col++) forces_column(s, s->forces[0], col);
+    return;
+  }
+  /* Threaded, src/integration.jl:159-194: @threads :static over columns (contiguous blocks, the first
+   * `rem` threads get one extra), private slices, then get_forces .= sum(system.forces). */
+  const int T = s->nthreads;
+  const int64_t len = s->num_cols / T, rem = s->num_cols % T;
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+  for (int t = 0; t < T; t++) {
+    int64_t lo = t * len + (t < rem ? t : rem);
+    int64_t hi = lo + len + (t < rem ? 1 : 0);
+    for (int64_t col = lo; col < hi; col++) forces_column(s, s->forces[t], col);
+  }
+  double *f0 = s->forces[0];
+#pragma omp parallel for schedule(static) num_threads(T)
+  for (int64_t k = 0; k < 2 * s->n; k++) {
+    double acc = f0[k];
+    for (int t = 1; t < T; t++) acc += s->forces[t][k];
+    f0[k] = acc;
+  }
+}
+
+/* signed_pos(point, ::CircleCfg), src/configs.jl:154-163 */
+static void signed_pos_circle(const double *pt, const MaviSpace *sp, double *dr, double *dist, double *flag) {
+  double d0 = pt[0] - sp->circ_center[0], d1 = pt[1] - sp->circ_center[1];
+  double dd = sqrt(d0 * d0 + d1 * d1); /* sum(dr.^2)^.5 */
+  double h0 = d0 / dd, h1 = d1 / dd;
+  dr[0] = d0 - h0 * sp->circ_radius;
+  dr[1] = d1 - h1 * sp->circ_radius;
+  double sd = dd - sp->circ_radius;
+  *dist = fabs(sd);
+  *flag = sd > 0 ? 1.0 : (sd < 0 ? -1.0 : sd); /* sign() */
+}
+
+/* Line2D ctor, src/configs.jl:102-117 */
+static void line_frame(const MaviLine *l, double *normal, double *tangent, double *length) {
+  double d0 = l->p2[0] - l->p1[0], d1 = l->p2[1] - l->p1[1];
+  double norm = sqrt(d0 * d0 + d1 * d1);
+  normal[0] = -d1 / norm; normal[1] = d0 / norm;
+  tangent[0] = d0 / norm; tangent[1] = d1 / norm;
+  *length = norm;
+}
+
+/* signed_pos(point, ::Line2D), src/configs.jl:119-135 */
+static void signed_pos_line(const double *pt, const MaviLine *l, double *dr, double *dist) {
+  double nrm[2], tan[2], len;
+  line_frame(l, nrm, tan, &len);
+  dr[0] = pt[0] - l->p1[0];
+  dr[1] = pt[1] - l->p1[1];
+  double delta_t = dr[0] * tan[0] + dr[1] * tan[1];
+  if (delta_t > 0) {
+    if (delta_t < len) {
+      double b0 = l->p1[0] + tan[0] * delta_t, b1 = l->p1[1] + tan[1] * delta_t;
+      dr[0] = pt[0] - b0; dr[1] = pt[1] - b1;
+    } else {
+      dr[0] = pt[0] - l->p2[0]; dr[1] = pt[1] - l->p2[1];
+    }
+  }
+  *dist = sqrt(dr[0] * dr[0] + dr[1] * dr[1]);
+}
+
+/* process_dist, src/configs.jl:259-261 */
+static double process_dist(int32_t mode, double dist, double flag) {
+  if (mode == MAVI_WALLMODE_OUTSIDE) return flag * dist;
+  if (mode == MAVI_WALLMODE_INSIDE) return -flag * dist;
+  return dist;
+}
+
+/* calc_walls_forces!, src/integration.jl:228-266 (ManyWalls: only ForceWalls sub-spaces act) */
+void mor_walls_forces(OrSystem *s) {
+  double *forces = s->forces[0];
+  for (int k = 0; k < s->p.n_spaces; k++) {
+    const MaviSpace *sp = &s->p.spaces[k];
+    if (sp->wall != MAVI_WALL_POTENTIAL) continue;
+    for (int64_t q = 0; q < s->n_ids; q++) {
+      int64_t i = s->ids[q];
+      const double *pt = s->pos + 2 * i;
+      double dr[2], dist, flag, f[2];
+      if (sp->geom == MAVI_GEOM_CIRCLE) {
+        signed_pos_circle(pt, sp, dr, &dist, &flag);
+        dist = process_dist(sp->pot_mode, dist, flag);
+        mor_potential_force(sp->pot_kind, sp->pot, dr, dist, f);
+        forces[2 * i] += f[0]; forces[2 * i + 1] += f[1];
+      } else if (sp->geom == MAVI_GEOM_LINES) {
+        for (int l = 0; l < sp->n_lines; l++) {
+          signed_pos_line(pt, &s->lines[k][l], dr, &dist);
+          dist = process_dist(sp->pot_mode, dist, 1.0);
+          mor_potential_force(sp->pot_kind, sp->pot, dr, dist, f);
+          forces[2 * i] += f[0]; forces[2 * i + 1] += f[1];
+        }
+      }
+      /* PotentialWalls on a RectangleCfg: no signed_pos method exists in the reference -> MethodError;
+       * rejected at create. */
+    }
+  }
+}
+
+/* per-particle radius: get_particle_radius, src/systems.jl:132-133, src/rings/rings.jl:47-56 */
+static double particle_radius_of(const OrSystem *s, int64_t idx) {
+  if (s->p.dynamics != MAVI_DYN_RINGS) return s->p.particle_radius;
+  int32_t t = ring_type(s, ring_of(s, idx));
+  return s->rp.interaction[4 * ((int64_t)t * s->rp.num_types + t) + 2] / 2.0;
+}
+
+/* walls!(system, SpaceCfg{W,G}) for one (wall, geometry) pair, src/integration.jl:268-401 */
+static void walls_one(OrSystem *s, const MaviSpace *sp, const MaviLine *lines) {
+  double *pos = s->pos;
+  if (sp->wall == MAVI_WALL_RIGID && sp->geom == MAVI_GEOM_RECT) {
+    /* :271-285 — velocity flip only, uses particle_radius(dynamic_cfg) */
+    double *vel = s->second;
+    const double r = s->p.particle_radius;
+    const double size[2] = {sp->rect_len, sp->rect_h};
+    for (int64_t q = 0; q < s->n_ids; q++) {
+      int64_t i = s->ids[q];
+      int out[2];
+      for (int d = 0; d < 2; d++) {
+        double rel = pos[2 * i + d] - sp->rect_bl[d];
+        out[d] = ((rel + r) > size[d]) || ((rel - r) < 0);
+      }
+      if (out[0] || out[1])
+        for (int d = 0; d < 2; d++) vel[2 * i + d] = vel[2 * i + d] * (double)(-2 * out[d] + 1);
+    }
+  } else if (sp->wall == MAVI_WALL_RIGID && sp->geom == MAVI_GEOM_CIRCLE) {
+    /* :287-306 — cross terms use raw pos (exact only for centre 0; kept) */
+    double *vel = s->second;
+    double mr = sp->circ_radius - s->p.particle_radius;
+    double max_r2 = mr * mr;
+    for (int64_t q = 0; q < s->n_ids; q++) {
+      int64_t i = s->ids[q];
+      double px = pos[2 * i], py = pos[2 * i + 1];
+      double ex = px - sp->circ_center[0], ey = py - sp->circ_center[1];
+      double dr2x = ex * ex, dr2y = ey * ey;
+      double r2 = dr2x + dr2y;
+      if (r2 <= max_r2) continue;
+      double vx = vel[2 * i], vy = vel[2 * i + 1];
+      double nvx = (vx * (dr2y - dr2x) - 2 * vy * px * py) / r2;
+      double nvy = (-vy * (dr2y - dr2x) - 2 * vx * px * py) / r2;
+      vel[2 * i] = nvx; vel[2 * i + 1] = nvy;
+    }
+  } else if (sp->wall == MAVI_WALL_PERIODIC && sp->geom == MAVI_GEOM_RECT) {
+    /* :309-324 */
+    const double size[2] = {sp->rect_len, sp->rect_h};
+    for (int64_t q = 0; q < s->n_ids; q++) {
+      int64_t i = s->ids[q];
+      int out[2], any = 0;
+      double diff[2], half[2];
+      for (int d = 0; d < 2; d++) {
+        half[d] = size[d] / 2;
+        double center = sp->rect_bl[d] + size[d] / 2;
+        diff[d] = pos[2 * i + d] - center;
+        out[d] = fabs(diff[d]) > half[d];
+        any |= out[d];
+      }
+      if (any)
+        for (int d = 0; d < 2; d++) {
+          double sg = diff[d] > 0 ? 1.0 : (diff[d] < 0 ? -1.0 : diff[d]);
+          pos[2 * i + d] = pos[2 * i + d] - sg * (half[d] * 2) * (double)out[d];
+        }
+    }
+  } else if (sp->wall == MAVI_WALL_SLIPPERY && sp->geom == MAVI_GEOM_LINES) {
+    /* :327-378 — pos_i is read once per particle, corrections accumulate into state.pos */
+    for (int64_t q = 0; q < s->n_ids; q++) {
+      int64_t pid = s->ids[q];
+      double pr = particle_radius_of(s, pid);
+      const double pi0 = pos[2 * pid], pi1 = pos[2 * pid + 1];
+      for (int l = 0; l < sp->n_lines; l++) {
+        double nrm[2], tan[2], len;
+        line_frame(&lines[l], nrm, tan, &len);
+        double dr0 = pi0 - lines[l].p1[0], dr1 = pi1 - lines[l].p1[1];
+        double delta_s = dr0 * nrm[0] + dr1 * nrm[1];
+        if (fabs(delta_s) > pr) continue;
+        double delta_t = dr0 * tan[0] + dr1 * tan[1];
+        int is_corner = 0;
+        const double *corner = NULL;
+        if (delta_t > 0) {
+          if (delta_t > len) {
+            if (delta_t > (len + pr)) continue;
+            is_corner = 1;
+            corner = lines[l].p2;
+          }
+        } else if (delta_t > -pr) {
+          is_corner = 1;
+          corner = lines[l].p1;
+        } else {
+          continue;
+        }
+        if (is_corner) {
+          dr0 = pi0 - corner[0]; dr1 = pi1 - corner[1];
+          double norm = sqrt(dr0 * dr0 + dr1 * dr1);
+          if (norm > pr) continue;
+          double alpha = pr / norm - 1;
+          pos[2 * pid] += alpha * dr0;
+          pos[2 * pid + 1] += alpha * dr1;
+        } else {
+          double sgn = delta_s > 0 ? 1.0 : (delta_s < 0 ? -1.0 : delta_s);
+          double alpha = sgn * (pr - sgn * delta_s);
+          pos[2 * pid] += alpha * nrm[0];
+          pos[2 * pid + 1] += alpha * nrm[1];
+        }
+      }
+    }
+  } else if (sp->wall == MAVI_WALL_SLIPPERY && sp->geom == MAVI_GEOM_CIRCLE) {
+    /* :380-401 — calc_diff uses the SYSTEM space_cfg (min image if the main space is periodic) */
+    for (int64_t q = 0; q < s->n_ids; q++) {
+      int64_t pid = s->ids[q];
+      double pr = particle_radius_of(s, pid);
+      double mr = sp->circ_radius + pr;
+      double max_r_2 = mr * mr;
+      double dr[2];
+      mor_calc_diff(s, pos + 2 * pid, sp->circ_center, dr);
+      double dr_2 = dr[0] * dr[0] + dr[1] * dr[1];
+      if (dr_2 > max_r_2) continue;
+      double dr_norm = sqrt(dr_2);
+      double k = sp->circ_radius + pr - dr_norm;
+      pos[2 * pid] = pos[2 * pid] + k * dr[0] / dr_norm;
+      pos[2 * pid + 1] = pos[2 * pid + 1] + k * dr[1] / dr_norm;
+    }
+  }
+  /* every other (wall, geometry) pair: generic no-op method walls!(system, ::SpaceCfg), :268 */
+}
+
+/* walls!(system): single space or ManyWalls loop, src/integration.jl:404-412 */
+void mor_walls(OrSystem *s) {
+  for (int k = 0; k < s->p.n_spaces; k++) walls_one(s, &s->p.spaces[k], s->lines[k]);
+}
+
+/* ------------------------------------------------------------------ integrators */
+
+/* update_verlet!, src/integration.jl:415-431.  Pass 2 runs on the stale chunks and without wall forces;
+ * the broadcasts cover every slot of pos/vel, active or not. */
+void mor_update_verlet(OrSystem *s) {
+  const int64_t m = 2 * s->n;
+  double *forces = s->forces[0];
+  double *old = dup_d(forces, m);
+  const double dt = s->p.dt;
+  const double term = dt * dt / 2; /* dt^2/2 */
+  double *pos = s->pos, *vel = s->second;
+  for (int64_t k = 0; k < m; k++) pos[k] = pos[k] + (vel[k] * dt + forces[k] * term);
+  mor_clean_forces(s);
+  mor_pair_forces(s);
+  const double hdt = dt / 2;
+  for (int64_t k = 0; k < m; k++) vel[k] = vel[k] + hdt * (forces[k] + old[k]);
+  free(old);
+}
+
+static inline double sign_d(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : x); }
+
+/* update_szabo!, src/integration.jl:433-465.  Loops 1:get_num_total_particles (slots, not ids);
+ * "speed" is sqrt(|vx|+|vy|) (sic).  noise[i] stands for the reference's global randn(). */
+static void update_szabo(OrSystem *s, const double *noise) {
+  const double *par = s->p.dyn;
+  const double vo = par[0], mu = par[1], relax_time = par[2], drot = par[7];
+  const double dt = s->p.dt;
+  double *forces = s->forces[0], *pos = s->pos, *ang = s->second;
+  for (int64_t i = 0; i < s->n_ids; i++) {
+    double theta = ang[i];
+    double polx = cos(theta), poly = sin(theta);
+    double velx = vo * polx + mu * forces[2 * i], vely = vo * poly + mu * forces[2 * i + 1];
+    double speed = sqrt(fabs(velx) + fabs(vely));
+    double cross_prod;
+    if (speed > 0) cross_prod = (polx * vely - poly * velx) / speed;
+    else cross_prod = 0;
+    if (fabs(cross_prod) > 1) cross_prod = sign_d(cross_prod);
+    double nz = noise ? noise[i] : 0.0;
+    double d_theta = 1 / relax_time * asin(cross_prod) * dt + sqrt(2 * drot * dt) * nz;
+    pos[2 * i] += velx * dt;
+    pos[2 * i + 1] += vely * dt;
+    ang[i] += d_theta;
+  }
+}
+
+/* update_rtp!, src/integration.jl:467-498.  noise[2i] = u, noise[2i+1] = the second rand() (used on tumble). */
+static void update_rtp(OrSystem *s, const double *noise) {
+  const double *par = s->p.dyn;
+  const double vo = par[0], tumble_rate = par[3];
+  const double dt = s->p.dt;
+  const double two_pi = 2 * M_PI;
+  double *forces = s->forces[0], *pos = s->pos, *ang = s->second;
+  for (int64_t i = 0; i < s->n_ids; i++) {
+    double theta = ang[i];
+    double polx = cos(theta), poly = sin(theta);
+    double velx = vo * polx + forces[2 * i], vely = vo * poly + forces[2 * i + 1];
+    pos[2 * i] += velx * dt;
+    pos[2 * i + 1] += vely * dt;
+    double u = noise ? noise[2 * i] : 1.0;
+    if (u < tumble_rate * dt) ang[i] = two_pi * (noise ? noise[2 * i + 1] : 0.0);
+  }
+}
+
+/* update_time!, src/integration.jl:500-503 */
+static void update_time(OrSystem *s) {
+  s->time += s->p.dt;
+  s->num_steps += 1;
+}
+
+/* ------------------------------------------------------------------ rings */
+
+/* update_continuos_pos!, src/rings/integration.jl:118-138 (periodic main wall only; otherwise the
+ * "continuous" positions are rings_pos itself, src/rings/rings.jl:31-43) */
+static void update_continuos_pos(OrSystem *s) {
+  if (s->p.spaces[0].wall != MAVI_WALL_PERIODIC) return;
+  const int64_t nm = s->rp.n_max;
+  for (int64_t ring = 0; ring < s->rp.num_rings; ring++) {
+    memcpy(s->cont_pos + 2 * ring * nm, s->pos + 2 * ring * nm, sizeof(double) * 2 * (size_t)nm);
+    int32_t np = ring_np(s, ring);
+    for (int32_t i = 1; i < np; i++) {
+      int64_t a = ring * nm + i, b = a - 1;
+      double dr[2];
+      mor_calc_diff(s, s->pos + 2 * a, s->pos + 2 * b, dr);
+      s->cont_pos[2 * a] = s->cont_pos[2 * b] + dr[0];
+      s->cont_pos[2 * a + 1] = s->cont_pos[2 * b + 1] + dr[1];
+    }
+  }
+}
+
+static const double *ring_points(const OrSystem *s, int64_t ring) {
+  const double *base = s->p.spaces[0].wall == MAVI_WALL_PERIODIC ? s->cont_pos : s->pos;
+  return base + 2 * ring * s->rp.n_max;
+}
+
+/* update_cms!, src/rings/integration.jl:366-372 */
+static void update_cms(OrSystem *s) {
+  for (int64_t ring = 0; ring < s->rp.num_rings; ring++) {
+    const double *pts = ring_points(s, ring);
+    int32_t np = ring_np(s, ring);
+    double sx = pts[0], sy = pts[1];
+    for (int32_t i = 1; i < np; i++) { sx += pts[2 * i]; sy += pts[2 * i + 1]; }
+    s->cms[2 * ring] = sx / np;
+    s->cms[2 * ring + 1] = sy / np;
+  }
+}
+
+/* calc_area, src/rings/integration.jl:103-116 (shoelace) */
+static double calc_area(const double *pts, int32_t np) {
+  double area = 0.0;
+  for (int32_t i = 0; i < np - 1; i++) area += pts[2 * i] * pts[2 * (i + 1) + 1] - pts[2 * i + 1] * pts[2 * (i + 1)];
+  area += pts[2 * (np - 1)] * pts[1] - pts[2 * (np - 1) + 1] * pts[0];
+  return area / 2.0;
+}
+
+/* forces!, src/rings/integration.jl:197-226 = calc_forces! + springs (:79-97) + area_forces! (:140-195) */
+static void rings_forces(OrSystem *s) {
+  mor_pair_forces(s);
+  double *forces = s->forces[0];
+  const int64_t nm = s->rp.n_max;
+  for (int64_t ring = 0; ring < s->rp.num_rings; ring++) {
+    int32_t np = ring_np(s, ring);
+    int32_t t = ring_type(s, ring);
+    double k = s->rp.k_spring[t], l = s->rp.l_spring[t];
+    for (int32_t sp = 0; sp < np; sp++) {
+      int64_t p1 = ring * nm + sp, p2 = ring * nm + (sp == np - 1 ? 0 : sp + 1);
+      double dr[2];
+      mor_calc_diff(s, s->pos + 2 * p1, s->pos + 2 * p2, dr);
+      double dist = sqrt(dr[0] * dr[0] + dr[1] * dr[1]);
+      double fmod_ = -k * (dist - l);
+      double c = fmod_ / dist;
+      double f0 = c * dr[0], f1 = c * dr[1];
+      forces[2 * p1] += f0; forces[2 * p1 + 1] += f1;
+      forces[2 * p2] -= f0; forces[2 * p2 + 1] -= f1;
+    }
+  }
+  for (int64_t ring = 0; ring < s->rp.num_rings; ring++) {
+    int32_t np = ring_np(s, ring);
+    int32_t t = ring_type(s, ring);
+    double area = calc_area(ring_points(s, ring), np);
+    s->areas[ring] = area;
+    double k_area = s->rp.k_area[t], p0 = s->rp.p0[t], l0 = s->rp.l_spring[t];
+    double a0s = np * l0 / p0;
+    double area0 = a0s * a0s;
+    for (int32_t i = 0; i < np; i++) {
+      double fmod_ = k_area * (area - area0);
+      int32_t id1 = i == 0 ? np - 1 : i - 1;
+      int32_t id2 = i == np - 1 ? 0 : i + 1;
+      double dr[2];
+      mor_calc_diff(s, s->pos + 2 * (ring * nm + id2), s->pos + 2 * (ring * nm + id1), dr);
+      double ax = dr[1] / 2, ay = -dr[0] / 2;
+      forces[2 * (ring * nm + i)] -= fmod_ * ax;
+      forces[2 * (ring * nm + i) + 1] -= fmod_ * ay;
+    }
+  }
+}
+
+/* update!, src/rings/integration.jl:300-351.  noise[ring] stands for randn(system.rng). */
+static void rings_update(OrSystem *s, const double *noise) {
+  const double dt = s->p.dt;
+  double *forces = s->forces[0], *pos = s->pos, *pol_a = s->second;
+  const int64_t nm = s->rp.n_max;
+  for (int64_t ring = 0; ring < s->rp.num_rings; ring++) {
+    int32_t np = ring_np(s, ring);
+    int32_t t = ring_type(s, ring);
+    double vo = s->rp.vo[t], relax_time = s->rp.relax_time[t], mu = s->rp.mobility[t], drot = s->rp.rot_diff[t];
+    double theta = pol_a[ring];
+    double polx = cos(theta), poly = sin(theta);
+    double vcx = 0.0, vcy = 0.0;
+    for (int32_t i = 0; i < np; i++) {
+      int64_t pid = ring * nm + i;
+      double velx = vo * polx + mu * forces[2 * pid], vely = vo * poly + mu * forces[2 * pid + 1];
+      vcx += velx; vcy += vely;
+      pos[2 * pid] += velx * dt;
+      pos[2 * pid + 1] += vely * dt;
+    }
+    vcx /= np; vcy /= np;
+    double speed = sqrt(vcx * vcx + vcy * vcy);
+    double cross_prod;
+    if (speed == 0) cross_prod = 0;
+    else {
+      cross_prod = (polx * vcy - poly * vcx) / speed;
+      if (fabs(cross_prod) > 1) cross_prod = sign_d(cross_prod);
+    }
+    double nz = noise ? noise[ring] : 0.0;
+    double d_theta = 1 / relax_time * asin(cross_prod) * dt + sqrt(2 * drot * dt) * nz;
+    pol_a[ring] += d_theta;
+  }
+}
+
+/* ------------------------------------------------------------------ steps */
+
+static int64_t noise_stride(const OrSystem *s) {
+  switch (s->p.dynamics) {
+    case MAVI_DYN_SZABO: return s->n;
+    case MAVI_DYN_RTP: return 2 * s->n;
+    case MAVI_DYN_RINGS: return s->rp.num_rings;
+    default: return 0;
+  }
+}
+
+/* newton_step! / szabo_step! / rtp_step!, src/integration.jl:507-535; Rings step!, src/rings/integration.jl:522-543 */
+static int32_t step_once(OrSystem *s, const double *noise) {
+  int32_t st;
+  if (s->p.dynamics == MAVI_DYN_RINGS) {
+    update_cms(s);
+    /* update_sources! / update_ids!: fixed ring set here */
+    if ((st = mor_update_chunks(s))) return st;
+    update_continuos_pos(s);
+    mor_clean_forces(s);
+    rings_forces(s);
+    mor_walls_forces(s);
+    rings_update(s, noise);
+    mor_walls(s);
+    s->num_steps += 1;
+    s->time += s->p.dt;
+    return MAVI_OK;
+  }
+  mor_clean_forces(s);
+  if ((st = mor_update_chunks(s))) return st;
+  mor_pair_forces(s);
+  mor_walls_forces(s);
+  if (s->p.dynamics == MAVI_DYN_SZABO) update_szabo(s, noise);
+  else if (s->p.dynamics == MAVI_DYN_RTP) update_rtp(s, noise);
+  else mor_update_verlet(s);
+  mor_walls(s);
+  update_time(s);
+  return MAVI_OK;
+}
+
+int32_t mor_step(OrSystem *s, int64_t nsteps, const double *noise) {
+  int64_t stride = noise_stride(s);
+  for (int64_t k = 0; k < nsteps; k++) {
+    int32_t st = step_once(s, noise ? noise + k * stride : NULL);
+    if (st) return st;
+  }
+  return MAVI_OK;
+}
+
+int32_t mor_calc_forces(OrSystem *s) {
+  mor_clean_forces(s);
+  int32_t st = mor_update_chunks(s);
+  if (st) return st;
+  if (s->p.dynamics == MAVI_DYN_RINGS) {
+    update_continuos_pos(s);
+    rings_forces(s);
+  } else {
+    mor_pair_forces(s);
+  }
+  mor_walls_forces(s);
+  return MAVI_OK;
+}
+
+int32_t mor_bin(OrSystem *s) { return mor_update_chunks(s); }
+
+/* ------------------------------------------------------------------ quantities */
+
+/* kinetic_energy src/quantities.jl:12-18 (all slots, mass 1); potential_energy LJ :46-66 (all pairs over
+ * 1:N_active_count, no cutoff).  pe_mode 1: 4eps*sum over the cell-stencil pair set (not in the reference). */
+int32_t mor_energies(OrSystem *s, int32_t pe_mode, double *ke, double *pe) {
+  if (ke) {
+    if (s->p.dynamics == MAVI_DYN_LJ || s->p.dynamics == MAVI_DYN_HARMTRUNC) {
+      double acc = 0;
+      for (int64_t i = 0; i < s->n; i++) acc += s->second[2 * i] * s->second[2 * i] + s->second[2 * i + 1] * s->second[2 * i + 1];
+      *ke = acc / 2;
+    } else *ke = NAN;
+  }
+  if (pe) {
+    if (s->p.dynamics != MAVI_DYN_LJ) { *pe = NAN; return MAVI_OK; }
+    const double sigma = s->p.dyn[0], epsilon = s->p.dyn[1];
+    double pot = 0.0;
+    if (pe_mode == 0) {
+      const int64_t N = s->n_ids;
+      for (int64_t i = 0; i < N; i++)
+        for (int64_t j = i + 1; j < N; j++) {
+          double dr[2];
+          mor_calc_diff(s, s->pos + 2 * i, s->pos + 2 * j, dr);
+          double dist = sqrt(dr[0] * dr[0] + dr[1] * dr[1]);
+          pot += (pow(sigma / dist, 12) - pow(sigma / dist, 6));
+        }
+    } else {
+      if (!s->has_chunks) return MAVI_ERR_BAD_PARAMS;
+      for (int64_t cell = 0; cell < s->num_rows * s->num_cols; cell++) {
+        int64_t np = s->num_in_chunk[cell];
+        const int64_t *chunk = s->chunk_particles + cell * s->nc;
+        for (int64_t i = 0; i < np; i++) {
+          for (int64_t j = i + 1; j < np; j++) {
+            double dr[2];
+            mor_calc_diff(s, s->pos + 2 * chunk[i], s->pos + 2 * chunk[j], dr);
+            double dist = sqrt(dr[0] * dr[0] + dr[1] * dr[1]);
+            pot += (pow(sigma / dist, 12) - pow(sigma / dist, 6));
+          }
+          for (int k = 0; k < s->neigh_n[cell]; k++) {
+            int64_t ncell = s->neigh[4 * cell + k];
+            const int64_t *nch = s->chunk_particles + ncell * s->nc;
+            for (int64_t j = 0; j < s->num_in_chunk[ncell]; j++) {
+              double dr[2];
+              mor_calc_diff(s, s->pos + 2 * chunk[i], s->pos + 2 * nch[j], dr);
+              double dist = sqrt(dr[0] * dr[0] + dr[1] * dr[1]);
+              pot += (pow(sigma / dist, 12) - pow(sigma / dist, 6));
+            }
+          }
+        }
+      }
+    }
+    *pe = pot * (4 * epsilon);
+  }
+  return MAVI_OK;
+}
+
+/* ------------------------------------------------------------------ lifetime / IO */
+
+static int32_t validate(OrSystem *s) {
+  const MaviParams *p = &s->p;
+  if (p->struct_size != sizeof(MaviParams)) {
+    snprintf(s->err, sizeof s->err, "MaviParams.struct_size %u != %zu", p->struct_size, sizeof(MaviParams));
+    return MAVI_ERR_BAD_PARAMS;
+  }
+  if (p->dtype != MAVI_F64) {
+    snprintf(s->err, sizeof s->err, "oracle is Float64 only");
+    return MAVI_ERR_UNSUPPORTED;
+  }
+  if (p->n < 0 || p->n_spaces < 1 || p->n_spaces > MAVI_MAX_SPACES) return MAVI_ERR_BAD_PARAMS;
+  for (int k = 0; k < p->n_spaces; k++)
+    if (p->spaces[k].wall == MAVI_WALL_POTENTIAL && p->spaces[k].geom == MAVI_GEOM_RECT) {
+      snprintf(s->err, sizeof s->err, "PotentialWalls on RectangleCfg: no signed_pos method in the reference");
+      return MAVI_ERR_UNSUPPORTED;
+    }
+  if (p->dynamics == MAVI_DYN_RINGS) {
+    if (!p->rings) return MAVI_ERR_BAD_PARAMS;
+    if (p->rings->num_rings * p->rings->n_max != p->n) {
+      snprintf(s->err, sizeof s->err, "n != num_rings*n_max");
+      return MAVI_ERR_BAD_PARAMS;
+    }
+  }
+  return MAVI_OK;
+}
+
+int32_t mor_create(const MaviParams *p, OrSystem **out) {
+  OrSystem *s = (OrSystem *)calloc(1, sizeof(OrSystem));
+  s->p = *p;
+  *out = s;
+  int32_t st = validate(s);
+  if (st) return st;
+  for (int k = 0; k < p->n_spaces; k++) {
+    int nl = p->spaces[k].n_lines;
+    if (p->spaces[k].geom == MAVI_GEOM_LINES && nl > 0) {
+      s->lines[k] = (MaviLine *)malloc(sizeof(MaviLine) * (size_t)nl);
+      memcpy(s->lines[k], p->spaces[k].lines, sizeof(MaviLine) * (size_t)nl);
+      s->p.spaces[k].lines = s->lines[k];
+    }
+  }
+  s->n = p->n;
+  int64_t n_second = 2 * s->n;
+  if (p->dynamics == MAVI_DYN_RINGS) {
+    const MaviRingsParams *r = p->rings;
+    s->rp = *r;
+    int nt = r->num_types;
+    s->rp.p0 = dup_d(r->p0, nt); s->rp.relax_time = dup_d(r->relax_time, nt); s->rp.vo = dup_d(r->vo, nt);
+    s->rp.mobility = dup_d(r->mobility, nt); s->rp.rot_diff = dup_d(r->rot_diff, nt); s->rp.k_area = dup_d(r->k_area, nt);
+    s->rp.k_spring = dup_d(r->k_spring, nt); s->rp.l_spring = dup_d(r->l_spring, nt);
+    int32_t *np = (int32_t *)malloc(sizeof(int32_t) * (size_t)nt);
+    memcpy(np, r->num_particles, sizeof(int32_t) * (size_t)nt);
+    s->rp.num_particles = np;
+    s->rp.interaction = dup_d(r->interaction, 4 * nt * nt);
+    if (r->types) {
+      int32_t *ty = (int32_t *)malloc(sizeof(int32_t) * (size_t)r->num_rings);
+      memcpy(ty, r->types, sizeof(int32_t) * (size_t)r->num_rings);
+      s->rp.types = ty;
+    }
+    s->p.rings = &s->rp;
+    n_second = r->num_rings;
+    s->cont_pos = (double *)calloc((size_t)(2 * s->n + 2), sizeof(double));
+    s->areas = (double *)calloc((size_t)r->num_rings + 1, sizeof(double));
+    s->cms = (double *)calloc((size_t)(2 * r->num_rings) + 2, sizeof(double));
+  } else if (p->dynamics == MAVI_DYN_SZABO || p->dynamics == MAVI_DYN_RTP) {
+    n_second = s->n;
+  }
+  s->pos = (double *)calloc((size_t)(2 * s->n + 2), sizeof(double));
+  s->second = (double *)calloc((size_t)n_second + 2, sizeof(double));
+  s->mask = (uint8_t *)malloc((size_t)s->n + 1);
+  s->ids = (int64_t *)malloc(sizeof(int64_t) * ((size_t)s->n + 1));
+  s->nthreads = 1;
+  s->forces = (double **)malloc(sizeof(double *));
+  s->forces[0] = (double *)calloc((size_t)(2 * s->n + 2), sizeof(double));
+  return chunks_init(s);
+}
+
+void mor_set_threads(OrSystem *s, int32_t nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  for (int t = 1; t < s->nthreads; t++) free(s->forces[t]);
+  s->forces = (double **)realloc(s->forces, sizeof(double *) * (size_t)nthreads);
+  for (int t = 1; t < nthreads; t++) s->forces[t] = (double *)calloc((size_t)(2 * s->n + 2), sizeof(double));
+  s->nthreads = nthreads;
+}
+
+void mor_destroy(OrSystem *s) {
+  if (!s) return;
+  for (int k = 0; k < MAVI_MAX_SPACES; k++) free(s->lines[k]);
+  if (s->p.dynamics == MAVI_DYN_RINGS && s->p.rings == &s->rp) {
+    free((void *)s->rp.p0); free((void *)s->rp.relax_time); free((void *)s->rp.vo); free((void *)s->rp.mobility);
+    free((void *)s->rp.rot_diff); free((void *)s->rp.k_area); free((void *)s->rp.k_spring); free((void *)s->rp.l_spring);
+    free((void *)s->rp.num_particles); free((void *)s->rp.interaction); free((void *)s->rp.types);
+  }
+  free(s->pos); free(s->second); free(s->mask); free(s->ids);
+  if (s->forces) {
+    for (int t = 0; t < s->nthreads; t++) free(s->forces[t]);
+    free(s->forces);
+  }
+  free(s->chunk_particles); free(s->num_in_chunk); free(s->neigh); free(s->neigh_n);
+  free(s->cont_pos); free(s->areas); free(s->cms);
+  free(s);
+}
+
+const char *mor_last_error(OrSystem *s) { return s->err; }
+
+/* check_inside, src/space_checks.jl:9-61 — only Rectangle / Circle geometries have a real check;
+ * ManyGeometries falls to the generic method that returns [] (no check). */
+static int32_t check_inside(OrSystem *s) {
+  if (s->p.n_spaces != 1) return MAVI_OK;
+  const MaviSpace *sp = &s->p.spaces[0];
+  for (int64_t q = 0; q < s->n_ids; q++) {
+    int64_t i = s->ids[q];
+    double x = s->pos[2 * i], y = s->pos[2 * i + 1];
+    int out = 0;
+    if (sp->geom == MAVI_GEOM_RECT) {
+      double trx = sp->rect_bl[0] + sp->rect_len, try_ = sp->rect_bl[1] + sp->rect_h;
+      out = (x < sp->rect_bl[0]) || (y < sp->rect_bl[1]) || (x > trx) || (y > try_);
+    } else if (sp->geom == MAVI_GEOM_CIRCLE) {
+      out = (x * x + y * y) > sp->circ_radius * sp->circ_radius; /* ignores the centre (sic) */
+    }
+    if (out) {
+      snprintf(s->err, sizeof s->err, "Particles with ids=[%lld, ...] outside space.", (long long)(i + 1));
+      return MAVI_ERR_OUTSIDE_SPACE;
+    }
+  }
+  return MAVI_OK;
+}
+
+/* System ctor tail (src/systems.jl:73-114): ids, inside check, first update_chunks!;
+ * RingsSystem ctor tail (src/rings/rings.jl:280-288): prime continuos_pos, cms, chunks, forces!. */
+int32_t mor_upload_state(OrSystem *s, const double *pos, const double *second, const uint8_t *mask, int64_t n) {
+  if (n != s->n) return MAVI_ERR_BAD_PARAMS;
+  memcpy(s->pos, pos, sizeof(double) * 2 * (size_t)n);
+  int64_t n_second = 2 * n;
+  if (s->p.dynamics == MAVI_DYN_RINGS) n_second = s->rp.num_rings;
+  else if (s->p.dynamics == MAVI_DYN_SZABO || s->p.dynamics == MAVI_DYN_RTP) n_second = n;
+  if (second) memcpy(s->second, second, sizeof(double) * (size_t)n_second);
+  s->n_ids = 0;
+  if (s->p.dynamics == MAVI_DYN_RINGS) {
+    /* FixRingsIds, src/rings/states.jl:45-61 */
+    for (int64_t ring = 0; ring < s->rp.num_rings; ring++) {
+      int32_t np = ring_np(s, ring);
+      for (int64_t q = 0; q < s->rp.n_max; q++) {
+        s->mask[ring * s->rp.n_max + q] = q < np;
+        if (q < np) s->ids[s->n_ids++] = ring * s->rp.n_max + q;
+      }
+    }
+  } else {
+    /* ParticleIds / eachindex(pos), src/states.jl:27-70 */
+    for (int64_t i = 0; i < n; i++) {
+      s->mask[i] = mask ? (mask[i] != 0) : 1;
+      if (s->mask[i]) s->ids[s->n_ids++] = i;
+    }
+  }
+  int32_t st = check_inside(s);
+  if (st) return st;
+  if (s->p.dynamics == MAVI_DYN_RINGS) {
+    update_continuos_pos(s);
+    update_cms(s);
+    if ((st = mor_update_chunks(s))) return st;
+    mor_clean_forces(s);
+    rings_forces(s);
+    return MAVI_OK;
+  }
+  return mor_update_chunks(s);
+}
+
+int32_t mor_download_state(OrSystem *s, double *pos, double *second) {
+  if (pos) memcpy(pos, s->pos, sizeof(double) * 2 * (size_t)s->n);
+  if (second) {
+    int64_t n_second = 2 * s->n;
+    if (s->p.dynamics == MAVI_DYN_RINGS) n_second = s->rp.num_rings;
+    else if (s->p.dynamics == MAVI_DYN_SZABO || s->p.dynamics == MAVI_DYN_RTP) n_second = s->n;
+    memcpy(second, s->second, sizeof(double) * (size_t)n_second);
+  }
+  return MAVI_OK;
+}
+
+int32_t mor_download_forces(OrSystem *s, double *f) {
+  memcpy(f, s->forces[0], sizeof(double) * 2 * (size_t)s->n);
+  return MAVI_OK;
+}
+
+int32_t mor_download_cells(OrSystem *s, int32_t *cell_of_particle, int32_t *counts) {
+  if (!s->has_chunks) return MAVI_ERR_BAD_PARAMS;
+  int64_t cells = s->num_rows * s->num_cols;
+  if (counts)
+    for (int64_t c = 0; c < cells; c++) counts[c] = (int32_t)s->num_in_chunk[c];
+  if (cell_of_particle) {
+    for (int64_t i = 0; i < s->n; i++) cell_of_particle[i] = -1;
+    for (int64_t c = 0; c < cells; c++)
+      for (int64_t k = 0; k < s->num_in_chunk[c]; k++) cell_of_particle[s->chunk_particles[c * s->nc + k]] = (int32_t)c;
+  }
+  return MAVI_OK;
+}
+
+int32_t mor_download_cell_lists(OrSystem *s, int32_t *start, int32_t *ids) {
+  if (!s->has_chunks) return MAVI_ERR_BAD_PARAMS;
+  int64_t cells = s->num_rows * s->num_cols, acc = 0;
+  for (int64_t c = 0; c < cells; c++) {
+    if (start) start[c] = (int32_t)acc;
+    if (ids)
+      for (int64_t k = 0; k < s->num_in_chunk[c]; k++) ids[acc + k] = (int32_t)s->chunk_particles[c * s->nc + k];
+    acc += s->num_in_chunk[c];
+  }
+  if (start) start[cells] = (int32_t)acc;
+  return MAVI_OK;
+}
+
+int32_t mor_cell_neighbors(OrSystem *s, int32_t cell, int32_t *out4, int32_t *n) {
+  if (!s->has_chunks || cell < 0 || cell >= s->num_rows * s->num_cols) return MAVI_ERR_BAD_PARAMS;
+  *n = s->neigh_n[cell];
+  for (int k = 0; k < *n; k++) out4[k] = s->neigh[4 * cell + k];
+  return MAVI_OK;
+}
+
+int64_t mor_chunk_capacity(OrSystem *s) { return s->nc; }
+
+int32_t mor_rings_download_info(OrSystem *s, double *areas, double *cms, double *cont_pos) {
+  if (s->p.dynamics != MAVI_DYN_RINGS) return MAVI_ERR_BAD_PARAMS;
+  if (areas) memcpy(areas, s->areas, sizeof(double) * (size_t)s->rp.num_rings);
+  if (cms) memcpy(cms, s->cms, sizeof(double) * 2 * (size_t)s->rp.num_rings);
+  if (cont_pos) memcpy(cont_pos, s->cont_pos, sizeof(double) * 2 * (size_t)s->n);
+  return MAVI_OK;
+}
+
+int32_t mor_get_time(OrSystem *s, int64_t *num_steps, double *time) {
+  if (num_steps) *num_steps = s->num_steps;
+  if (time) *time = s->time;
+  return MAVI_OK;
+}
