@@ -1,0 +1,659 @@
+// api.cu — the C ABI of libmavi_cuda.so (include/mavi.h): handle lifetime, state movement, step orchestration.
+// Reference citations are relative to /root/reference/.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <utility>
+#include <vector>
+
+#include "handle.cuh"
+
+using namespace mavi;
+
+namespace mavi {
+
+void Handle::set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err, sizeof err, fmt, ap);
+  va_end(ap);
+}
+
+#define CUDA_TRY(h, expr)                                                                       \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      (h)->set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #expr); \
+      return MAVI_ERR_CUDA;                                                                     \
+    }                                                                                           \
+  } while (0)
+
+// largest x with fl(sqrt(x)) <= d  ->  (sqrt(r2) > d)  <=>  (r2 > x), exactly
+static double sqrt_le_threshold(double d) {
+  double x = d * d;
+  while (std::sqrt(x) <= d) x = std::nextafter(x, INFINITY);
+  while (std::sqrt(x) > d) x = std::nextafter(x, -INFINITY);
+  return x;
+}
+// smallest x with fl(sqrt(x)) >= d  ->  (sqrt(r2) < d)  <=>  (r2 < x), exactly
+static double sqrt_ge_threshold(double d) {
+  double x = d * d;
+  while (std::sqrt(x) >= d && x > 0) x = std::nextafter(x, -INFINITY);
+  while (std::sqrt(x) < d) x = std::nextafter(x, INFINITY);
+  return x;
+}
+
+template <typename T>
+static int dev_alloc(Handle *h, T **ptr, size_t count) {
+  *ptr = nullptr;
+  if (count == 0) count = 1;
+  CUDA_TRY(h, cudaMalloc((void **)ptr, count * sizeof(T)));
+  h->allocs.push_back((void *)*ptr);
+  return MAVI_OK;
+}
+
+template <typename T>
+static int dev_upload(Handle *h, const T **dst, const T *src, size_t count) {
+  T *d;
+  int st = dev_alloc(h, &d, count);
+  if (st) return st;
+  CUDA_TRY(h, cudaMemcpy(d, src, count * sizeof(T), cudaMemcpyHostToDevice));
+  *dst = d;
+  return MAVI_OK;
+}
+
+static int validate_and_lower(Handle *h, const MaviParams *mp) {
+  DevParams &p = h->p;
+  if (mp->struct_size != sizeof(MaviParams)) {
+    h->set_error("MaviParams.struct_size %u != %zu (ABI mismatch)", mp->struct_size, sizeof(MaviParams));
+    return MAVI_ERR_BAD_PARAMS;
+  }
+  if (mp->dtype != MAVI_F64) {
+    h->set_error("Float32 mode is not built in this version of libmavi_cuda.so");
+    return MAVI_ERR_UNSUPPORTED;
+  }
+  if (mp->n < 0 || mp->n > 0x7fffffff || mp->n_spaces < 1 || mp->n_spaces > MAVI_MAX_SPACES) {
+    h->set_error("bad n / n_spaces");
+    return MAVI_ERR_BAD_PARAMS;
+  }
+  if (mp->world > 1) {
+    h->set_error("multi-GPU slabs are not built in this version");
+    return MAVI_ERR_UNSUPPORTED;
+  }
+  memset(&p, 0, sizeof p);
+  p.n = (int)mp->n;
+  p.n_count = p.n;
+  p.dynamics = mp->dynamics;
+  for (int i = 0; i < 8; i++) p.dyn[i] = mp->dyn[i];
+  p.particle_radius = mp->particle_radius;
+  p.dt = mp->dt;
+  p.term = mp->dt * mp->dt / 2;  // dt^2/2
+  p.hdt = mp->dt / 2;
+  p.rng_mode = mp->rng_mode;
+  p.seed = mp->seed;
+
+  // spaces
+  p.n_spaces = mp->n_spaces;
+  for (int k = 0; k < mp->n_spaces; k++) {
+    const MaviSpace &s = mp->spaces[k];
+    DevSpace &d = p.spaces[k];
+    d.wall = s.wall;
+    d.geom = s.geom;
+    d.rect_bl[0] = s.rect_bl[0]; d.rect_bl[1] = s.rect_bl[1];
+    d.rect_sz[0] = s.rect_len; d.rect_sz[1] = s.rect_h;
+    d.cc[0] = s.circ_center[0]; d.cc[1] = s.circ_center[1];
+    d.cr = s.circ_radius;
+    d.pot_kind = s.pot_kind;
+    for (int i = 0; i < 4; i++) d.pot[i] = s.pot[i];
+    d.pot_mode = s.pot_mode;
+    d.n_lines = 0;
+    d.lines = nullptr;
+    if (s.wall == MAVI_WALL_POTENTIAL) {
+      if (s.geom == MAVI_GEOM_RECT) {
+        h->set_error("PotentialWalls on a RectangleCfg: the reference has no signed_pos method for it");
+        return MAVI_ERR_UNSUPPORTED;
+      }
+      p.has_force_walls = 1;
+    }
+    if (s.geom == MAVI_GEOM_LINES && s.n_lines > 0) {
+      std::vector<DevLine> lines(s.n_lines);
+      for (int l = 0; l < s.n_lines; l++) {
+        // Line2D ctor, src/configs.jl:102-117
+        const MaviLine &ml = s.lines[l];
+        DevLine &dl = lines[l];
+        double d0 = ml.p2[0] - ml.p1[0], d1 = ml.p2[1] - ml.p1[1];
+        double norm = std::sqrt(d0 * d0 + d1 * d1);
+        dl.p1[0] = ml.p1[0]; dl.p1[1] = ml.p1[1];
+        dl.p2[0] = ml.p2[0]; dl.p2[1] = ml.p2[1];
+        dl.normal[0] = -d1 / norm; dl.normal[1] = d0 / norm;
+        dl.tangent[0] = d0 / norm; dl.tangent[1] = d1 / norm;
+        dl.length = norm;
+      }
+      int st = dev_upload(h, &d.lines, lines.data(), lines.size());
+      if (st) return st;
+      d.n_lines = s.n_lines;
+    }
+  }
+  const MaviSpace &m0 = mp->spaces[0];
+  p.periodic = (m0.wall == MAVI_WALL_PERIODIC && m0.geom == MAVI_GEOM_RECT) ? 1 : 0;
+  p.size[0] = m0.rect_len; p.size[1] = m0.rect_h;
+  p.half[0] = m0.rect_len / 2; p.half[1] = m0.rect_h / 2;
+
+  // Chunks ctor, src/chunks.jl:26-40
+  if (mp->num_cols > 0) {
+    if (mp->num_rows < 1) {
+      h->set_error("num_rows must be >= 1");
+      return MAVI_ERR_BAD_PARAMS;
+    }
+    const bool per_wall = m0.wall == MAVI_WALL_PERIODIC;
+    if (per_wall && (mp->num_cols < 2 || mp->num_rows < 2)) {
+      h->set_error("periodic cell grid needs >= 2 rows and columns (a 1-wide periodic grid lists a cell as its own "
+                   "neighbour in the reference and yields NaN self-pairs)");
+      return MAVI_ERR_BAD_PARAMS;
+    }
+    if (!per_wall && mp->num_cols < 2) {
+      h->set_error("walled cell grid needs num_cols >= 2 (the reference indexes column 0 otherwise)");
+      return MAVI_ERR_BAD_PARAMS;
+    }
+    long long cells = (long long)mp->num_cols * mp->num_rows;
+    if (cells > 0x7ffffff0LL) {
+      h->set_error("too many cells");
+      return MAVI_ERR_BAD_PARAMS;
+    }
+    p.num_cols = mp->num_cols;
+    p.num_rows = mp->num_rows;
+    p.num_cells = (int)cells;
+    p.wrap_cols = p.wrap_rows = per_wall ? 1 : 0;
+    p.grid_bl[0] = mp->grid_bl[0]; p.grid_bl[1] = mp->grid_bl[1];
+    p.grid_h = mp->grid_h;
+    p.cl = mp->grid_len / (double)mp->num_cols;
+    p.ch = mp->grid_h / (double)mp->num_rows;
+  }
+
+  switch (mp->dynamics) {
+    case MAVI_DYN_LJ:
+      p.lj_sig2 = mp->dyn[0] * mp->dyn[0];
+      p.lj_24eps = 24.0 * mp->dyn[1];
+      break;
+    case MAVI_DYN_HARMTRUNC:
+      p.cut2 = sqrt_le_threshold(mp->dyn[3]);
+      p.eq2_lo = sqrt_ge_threshold(mp->dyn[2]);
+      p.harm_inv_deq = 1.0 / mp->dyn[2];
+      break;
+    case MAVI_DYN_SZABO:
+      p.cut2 = sqrt_le_threshold(mp->dyn[6]);
+      p.szabo_eq2_hi = sqrt_le_threshold(mp->dyn[5]);
+      p.szabo_fadh = mp->dyn[4] / mp->dyn[5];
+      p.szabo_frep = mp->dyn[3] / (mp->dyn[6] - mp->dyn[5]);
+      break;
+    case MAVI_DYN_RTP:
+      p.lj_sig2 = mp->dyn[1] * mp->dyn[1];
+      p.lj_24eps = 24.0 * mp->dyn[2];
+      p.cut2 = sqrt_le_threshold(std::pow(2.0, 1.0 / 6.0) * mp->dyn[1]);
+      break;
+    case MAVI_DYN_RINGS:
+      return rings_lower(h, mp);
+    default:
+      h->set_error("unknown dynamics %d", mp->dynamics);
+      return MAVI_ERR_BAD_PARAMS;
+  }
+  return MAVI_OK;
+}
+
+static int allocate(Handle *h) {
+  const DevParams &p = h->p;
+  DevArrays &a = h->a;
+  const size_t n = (size_t)p.n;
+  int st;
+  for (int b = 0; b < 2; b++) {
+    if ((st = dev_alloc(h, &a.pos[b], n))) return st;
+    if ((st = dev_alloc(h, &a.idflag[b], n))) return st;
+    if ((st = dev_alloc(h, &a.cell[b], n))) return st;
+    if (h->second_kind == SECOND_VEL) {
+      if ((st = dev_alloc(h, &a.vel[b], n))) return st;
+    } else {
+      if ((st = dev_alloc(h, &a.ang[b], h->second_kind == SECOND_RING_POL ? (size_t)p.rings.num_rings : n))) return st;
+    }
+  }
+  if ((st = dev_alloc(h, &a.force, n))) return st;
+  if ((st = dev_alloc(h, &a.force_old, n))) return st;
+  if ((st = dev_alloc(h, &a.cell_new, n))) return st;
+  if ((st = dev_alloc(h, &a.perm, n))) return st;
+  const size_t nc = (size_t)p.num_cells + 2;
+  if ((st = dev_alloc(h, &a.count, nc))) return st;
+  if ((st = dev_alloc(h, &a.start, nc))) return st;
+  if ((st = dev_alloc(h, &a.scan_partials, nc / 4096 + 2))) return st;
+  if ((st = dev_alloc(h, &a.flags, 8))) return st;
+  if ((st = dev_alloc(h, &a.reduce_buf, 4096))) return st;
+  CUDA_TRY(h, cudaMemsetAsync(a.flags, 0, 8 * sizeof(int), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(a.count, 0, nc * sizeof(int), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(a.start, 0, nc * sizeof(int), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(a.force, 0, n * sizeof(double2), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(a.force_old, 0, n * sizeof(double2), h->stream));
+  if (h->second_kind == SECOND_RING_POL) return rings_allocate(h);
+  return MAVI_OK;
+}
+
+// Reads the device error word; called at every synchronisation point.
+int Handle::check_device_flags() {
+  int f[2] = {0, 0};
+  cudaError_t e = cudaMemcpyAsync(f, a.flags, sizeof f, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e != cudaSuccess) {
+    set_error("CUDA error %s while reading the device error word", cudaGetErrorString(e));
+    return MAVI_ERR_CUDA;
+  }
+  if (f[0] & 4) {
+    set_error("Particles outside space (check_inside, src/space_checks.jl)");
+    return MAVI_ERR_OUTSIDE_SPACE;
+  }
+  if (f[0] & ERRBIT_OUT_OF_GRID) {
+    set_error("a particle left the chunk grid (BoundsError in the reference, src/chunks.jl:144-146)");
+    return MAVI_ERR_OUT_OF_GRID;
+  }
+  if (f[0] & ERRBIT_NAN) {
+    set_error("non-finite state");
+    return MAVI_ERR_NAN;
+  }
+  return MAVI_OK;
+}
+
+// update_chunks!: cell ids, histogram, scan, stable scatter, physical re-order of the state arrays.
+int Handle::bin_and_sort(bool with_forces) {
+  if (p.num_cells == 0) return MAVI_OK;  // update_chunks!(::Nothing)
+  LaunchCtx c = ctx();
+  const size_t nc = (size_t)p.num_cells + 2;
+  CUDA_TRY(this, cudaMemsetAsync(a.count, 0, nc * sizeof(int), stream));
+  CUDA_TRY(this, cudaMemsetAsync(a.flags + 1, 0, sizeof(int), stream));
+  launch_cell_index(c, p, a.pos[0], a.idflag[0], a.cell[0], a.cell_new, a.count, a.flags);
+  launch_exclusive_scan(c, a.count, a.start, a.scan_partials, (int)nc);
+  launch_scatter(c, p, a.cell_new, a.start, a.count, a.perm);
+  launch_gather(c, p, a.perm, a.cell_new, a.start, a, 0, 1, second_kind == SECOND_VEL, second_kind != SECOND_RING_POL,
+                with_forces);
+  std::swap(a.pos[0], a.pos[1]);
+  std::swap(a.idflag[0], a.idflag[1]);
+  std::swap(a.cell[0], a.cell[1]);
+  if (second_kind == SECOND_VEL) std::swap(a.vel[0], a.vel[1]);
+  else if (second_kind == SECOND_ANGLE) std::swap(a.ang[0], a.ang[1]);
+  if (with_forces) std::swap(a.force, a.force_old);
+  cells_valid = true;
+  CUDA_TRY(this, cudaGetLastError());
+  return MAVI_OK;
+}
+
+int Handle::step_once(const double *noise_dev) {
+  int st;
+  LaunchCtx c = ctx();
+  if (p.dynamics == MAVI_DYN_RINGS) return rings_step(this, noise_dev);
+  if (prof) cudaEventRecord(ev[0], stream);
+  if ((st = bin_and_sort(false))) return st;
+  if (prof) cudaEventRecord(ev[1], stream);
+  if (p.dynamics == MAVI_DYN_LJ || p.dynamics == MAVI_DYN_HARMTRUNC) {
+    launch_newton_a(c, p, a, 0);  // pos[0] -> pos[1] (drift), F1 -> force_old
+    if (prof) cudaEventRecord(ev[2], stream);
+    launch_newton_b(c, p, a, 0);  // pos[1] -> pos[0], vel, F2 -> force
+    if (prof) cudaEventRecord(ev[3], stream);
+  } else {
+    if (prof) cudaEventRecord(ev[2], stream);
+    launch_self_propelled(c, p, a, 0, noise_dev, (unsigned long long)num_steps);
+    std::swap(a.pos[0], a.pos[1]);
+    if (prof) cudaEventRecord(ev[3], stream);
+  }
+  time += p.dt;  // update_time!, src/integration.jl:500-503
+  num_steps += 1;
+  return MAVI_OK;
+}
+
+}  // namespace mavi
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+extern "C" {
+
+int32_t mavi_abi_version(void) { return MAVI_ABI_VERSION; }
+
+int32_t mavi_create(const MaviParams *params, MaviHandle **out) {
+  if (!params || !out) return MAVI_ERR_BAD_PARAMS;
+  Handle *h = new Handle();
+  *out = reinterpret_cast<MaviHandle *>(h);
+  h->device = params->device;
+  h->flags_cfg = params->flags;
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) {
+    h->set_error("cudaSetDevice(%d): %s — libmavi_cuda.so needs a CUDA device; there is no CPU fallback", h->device,
+                 cudaGetErrorString(e));
+    return MAVI_ERR_CUDA;
+  }
+  h->stream = (cudaStream_t)params->stream;
+  switch (params->dynamics) {
+    case MAVI_DYN_LJ:
+    case MAVI_DYN_HARMTRUNC: h->second_kind = SECOND_VEL; break;
+    case MAVI_DYN_SZABO:
+    case MAVI_DYN_RTP: h->second_kind = SECOND_ANGLE; break;
+    default: h->second_kind = SECOND_RING_POL;
+  }
+  int st = validate_and_lower(h, params);
+  if (st) return st;
+  if ((st = allocate(h))) return st;
+  for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev[i]);
+  cudaEventCreate(&h->ev_call[0]);
+  cudaEventCreate(&h->ev_call[1]);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return MAVI_OK;
+}
+
+int32_t mavi_destroy(MaviHandle *hh) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return MAVI_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (void *ptr : h->allocs) cudaFree(ptr);
+  for (int i = 0; i < 4; i++)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 2; i++)
+    if (h->ev_call[i]) cudaEventDestroy(h->ev_call[i]);
+  delete h;
+  return MAVI_OK;
+}
+
+int32_t mavi_last_error(MaviHandle *hh, char *buf, int32_t n) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || !buf || n <= 0) return MAVI_ERR_BAD_PARAMS;
+  snprintf(buf, (size_t)n, "%s", h->err);
+  return MAVI_OK;
+}
+
+// System ctor tail (src/systems.jl:73-114): ids, inside check, first update_chunks!.
+int32_t mavi_upload_state(MaviHandle *hh, const void *pos, const void *second, const uint8_t *active_mask, int64_t n) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || !pos || n != h->p.n) return MAVI_ERR_BAD_PARAMS;
+  cudaSetDevice(h->device);
+  DevArrays &a = h->a;
+  LaunchCtx c = h->ctx();
+  const size_t sn = (size_t)n;
+  CUDA_TRY(h, cudaMemcpyAsync(a.pos[0], pos, sn * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  if (second) {
+    if (h->second_kind == SECOND_VEL)
+      CUDA_TRY(h, cudaMemcpyAsync(a.vel[0], second, sn * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+    else if (h->second_kind == SECOND_ANGLE)
+      CUDA_TRY(h, cudaMemcpyAsync(a.ang[0], second, sn * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    else
+      CUDA_TRY(h, cudaMemcpyAsync(a.ang[0], second, (size_t)h->p.rings.num_rings * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  CUDA_TRY(h, cudaMemsetAsync(a.flags, 0, 8 * sizeof(int), h->stream));
+  if (h->second_kind == SECOND_RING_POL) return rings_upload_finish(h);
+  unsigned char *mask_dev = nullptr;
+  h->p.n_count = h->p.n;
+  if (active_mask) {
+    // ParticleIds (src/states.jl:27-52): count = number of active ids
+    mask_dev = reinterpret_cast<unsigned char *>(a.perm);
+    CUDA_TRY(h, cudaMemcpyAsync(mask_dev, active_mask, sn, cudaMemcpyHostToDevice, h->stream));
+    int cnt = 0;
+    for (size_t i = 0; i < sn; i++) cnt += active_mask[i] != 0;
+    h->p.n_count = cnt;
+  }
+  launch_init_ids(c, h->p.n, mask_dev, a.idflag[0], a.cell[0], h->p.num_cells);
+  if (h->p.n_spaces == 1) launch_check_inside(c, h->p, a.pos[0], a.idflag[0], a.flags);
+  CUDA_TRY(h, cudaMemsetAsync(a.force, 0, sn * sizeof(double2), h->stream));
+  h->cells_valid = false;
+  int st = h->check_device_flags();
+  if (st) return st;
+  if ((st = h->bin_and_sort(false))) return st;
+  return h->check_device_flags();
+}
+
+int32_t mavi_download_state(MaviHandle *hh, void *pos, void *second) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return MAVI_ERR_BAD_PARAMS;
+  cudaSetDevice(h->device);
+  DevArrays &a = h->a;
+  LaunchCtx c = h->ctx();
+  const size_t sn = (size_t)h->p.n;
+  if (pos) {
+    launch_unpermute2(c, h->p.n, a.idflag[0], a.pos[0], a.pos[1]);
+    CUDA_TRY(h, cudaMemcpyAsync(pos, a.pos[1], sn * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (second) {
+    if (h->second_kind == SECOND_VEL) {
+      launch_unpermute2(c, h->p.n, a.idflag[0], a.vel[0], a.vel[1]);
+      CUDA_TRY(h, cudaMemcpyAsync(second, a.vel[1], sn * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+    } else if (h->second_kind == SECOND_ANGLE) {
+      launch_unpermute1(c, h->p.n, a.idflag[0], a.ang[0], a.ang[1]);
+      CUDA_TRY(h, cudaMemcpyAsync(second, a.ang[1], sn * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    } else {
+      CUDA_TRY(h, cudaMemcpyAsync(second, a.ang[0], (size_t)h->p.rings.num_rings * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+  }
+  return h->check_device_flags();
+}
+
+int32_t mavi_download_forces(MaviHandle *hh, void *forces) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || !forces) return MAVI_ERR_BAD_PARAMS;
+  cudaSetDevice(h->device);
+  DevArrays &a = h->a;
+  launch_unpermute2(h->ctx(), h->p.n, a.idflag[0], a.force, a.force_old);
+  CUDA_TRY(h, cudaMemcpyAsync(forces, a.force_old, (size_t)h->p.n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  return h->check_device_flags();
+}
+
+int32_t mavi_local_count(MaviHandle *hh, int64_t *n_local) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || !n_local) return MAVI_ERR_BAD_PARAMS;
+  *n_local = h->p.n;
+  return MAVI_OK;
+}
+
+int32_t mavi_download_local(MaviHandle *hh, int64_t *ids, void *pos, void *second, void *forces) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return MAVI_ERR_BAD_PARAMS;
+  // single GPU: the local set is everything, in original-id order
+  if (ids)
+    for (int64_t i = 0; i < h->p.n; i++) ids[i] = i;
+  int st = mavi_download_state(hh, pos, second);
+  if (st) return st;
+  if (forces) return mavi_download_forces(hh, forces);
+  return MAVI_OK;
+}
+
+int32_t mavi_step(MaviHandle *hh, int64_t nsteps, const void *host_noise) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || nsteps < 0) return MAVI_ERR_BAD_PARAMS;
+  cudaSetDevice(h->device);
+  const double *noise_dev = nullptr;
+  size_t stride = 0;
+  if (host_noise && h->p.rng_mode == MAVI_RNG_HOST_NOISE) {
+    switch (h->p.dynamics) {
+      case MAVI_DYN_SZABO: stride = (size_t)h->p.n; break;
+      case MAVI_DYN_RTP: stride = 2 * (size_t)h->p.n; break;
+      case MAVI_DYN_RINGS: stride = (size_t)h->p.rings.num_rings; break;
+      default: stride = 0;
+    }
+    size_t total = stride * (size_t)nsteps;
+    if (total > 0) {
+      if (total > h->noise_cap) {
+        if (h->noise_dev) cudaFree(h->noise_dev);
+        CUDA_TRY(h, cudaMalloc((void **)&h->noise_dev, total * sizeof(double)));
+        h->noise_cap = total;
+      }
+      CUDA_TRY(h, cudaMemcpyAsync(h->noise_dev, host_noise, total * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      noise_dev = h->noise_dev;
+    }
+  }
+  if (h->prof) cudaEventRecord(h->ev_call[0], h->stream);
+  for (int64_t s = 0; s < nsteps; s++) {
+    int st = h->step_once(noise_dev ? noise_dev + (size_t)s * stride : nullptr);
+    if (st) return st;
+  }
+  if (h->prof) cudaEventRecord(h->ev_call[1], h->stream);
+  CUDA_TRY(h, cudaGetLastError());
+  return h->check_device_flags();
+}
+
+int32_t mavi_calc_forces(MaviHandle *hh) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return MAVI_ERR_BAD_PARAMS;
+  cudaSetDevice(h->device);
+  if (h->p.dynamics == MAVI_DYN_RINGS) return rings_calc_forces(h);
+  int st = h->bin_and_sort(false);
+  if (st) return st;
+  launch_force_only(h->ctx(), h->p, h->a, 0, true);
+  return h->check_device_flags();
+}
+
+int32_t mavi_bin(MaviHandle *hh) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return MAVI_ERR_BAD_PARAMS;
+  cudaSetDevice(h->device);
+  int st = h->bin_and_sort(true);
+  if (st) return st;
+  return h->check_device_flags();
+}
+
+int32_t mavi_download_cells(MaviHandle *hh, int32_t *cell_of_particle, int32_t *counts) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || h->p.num_cells == 0) return MAVI_ERR_BAD_PARAMS;
+  cudaSetDevice(h->device);
+  DevArrays &a = h->a;
+  if (cell_of_particle) {
+    launch_unpermute_cells(h->ctx(), h->p.n, h->p.num_cells, a.idflag[0], a.cell[0], a.perm);
+    CUDA_TRY(h, cudaMemcpyAsync(cell_of_particle, a.perm, (size_t)h->p.n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (counts) {
+    std::vector<int> start((size_t)h->p.num_cells + 1);
+    CUDA_TRY(h, cudaMemcpyAsync(start.data(), a.start, start.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int c = 0; c < h->p.num_cells; c++) counts[c] = start[c + 1] - start[c];
+  }
+  return h->check_device_flags();
+}
+
+int32_t mavi_download_cell_lists(MaviHandle *hh, int32_t *start, int32_t *ids) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || h->p.num_cells == 0) return MAVI_ERR_BAD_PARAMS;
+  cudaSetDevice(h->device);
+  DevArrays &a = h->a;
+  std::vector<int> st((size_t)h->p.num_cells + 1);
+  CUDA_TRY(h, cudaMemcpyAsync(st.data(), a.start, st.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (start) memcpy(start, st.data(), st.size() * sizeof(int));
+  if (ids) {
+    launch_ids(h->ctx(), h->p.n, a.idflag[0], a.perm);
+    CUDA_TRY(h, cudaMemcpyAsync(ids, a.perm, (size_t)st.back() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  }
+  return h->check_device_flags();
+}
+
+// The neighbour cells the stencil walker visits for `cell`, in visiting order (no de-duplication: 2-wide periodic
+// grids list a cell twice exactly where the reference double counts).  Mirrors for_each_neighbor (common.cuh).
+int32_t mavi_cell_neighbors(MaviHandle *hh, int32_t cell, int32_t *out8, int32_t *n) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || !out8 || !n || h->p.num_cells == 0 || cell < 0 || cell >= h->p.num_cells) return MAVI_ERR_BAD_PARAMS;
+  const DevParams &p = h->p;
+  const int R = p.num_rows, Cn = p.num_cols;
+  const int col = cell / R, row = cell - col * R;
+  int cnt = 0;
+  for (int dc = -1; dc <= 1; dc++) {
+    int c2 = col + dc;
+    if (c2 < 0) { if (!p.wrap_cols) continue; c2 = Cn - 1; }
+    else if (c2 >= Cn) { if (!p.wrap_cols) continue; c2 = 0; }
+    for (int dr = -1; dr <= 1; dr++) {
+      int r2 = row + dr;
+      if (r2 < 0) { if (!p.wrap_rows) continue; r2 = R - 1; }
+      else if (r2 >= R) { if (!p.wrap_rows) continue; r2 = 0; }
+      if (dc == 0 && dr == 0) continue;
+      out8[cnt++] = c2 * R + r2;
+    }
+  }
+  *n = cnt;
+  return MAVI_OK;
+}
+
+int32_t mavi_energies(MaviHandle *hh, int32_t pe_mode, double *ke, double *pe) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return MAVI_ERR_BAD_PARAMS;
+  cudaSetDevice(h->device);
+  DevArrays &a = h->a;
+  LaunchCtx c = h->ctx();
+  double *out = a.reduce_buf + 2048;
+  double host[2] = {NAN, NAN};
+  if (ke && h->second_kind == SECOND_VEL) {
+    launch_kinetic_energy(c, h->p, a.vel[0], a.reduce_buf, out);
+    CUDA_TRY(h, cudaMemcpyAsync(&host[0], out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (pe && h->p.dynamics == MAVI_DYN_LJ) {
+    if (pe_mode == 1 && h->p.num_cells == 0) {
+      h->set_error("pe_mode 1 needs chunks");
+      return MAVI_ERR_BAD_PARAMS;
+    }
+    launch_potential_energy(c, h->p, a, 0, pe_mode, out + 1);
+    CUDA_TRY(h, cudaMemcpyAsync(&host[1], out + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  int st = h->check_device_flags();
+  if (ke) *ke = host[0];
+  if (pe) *pe = host[1];
+  return st;
+}
+
+int32_t mavi_rings_download_info(MaviHandle *hh, void *areas, void *cms, void *cont_pos) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || h->p.dynamics != MAVI_DYN_RINGS) return MAVI_ERR_BAD_PARAMS;
+  cudaSetDevice(h->device);
+  return rings_download_info(h, areas, cms, cont_pos);
+}
+
+int32_t mavi_get_time(MaviHandle *hh, int64_t *num_steps, double *time) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return MAVI_ERR_BAD_PARAMS;
+  if (num_steps) *num_steps = h->num_steps;
+  if (time) *time = h->time;
+  return MAVI_OK;
+}
+
+int32_t mavi_set_time(MaviHandle *hh, int64_t num_steps, double time) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return MAVI_ERR_BAD_PARAMS;
+  h->num_steps = num_steps;
+  h->time = time;
+  return MAVI_OK;
+}
+
+int32_t mavi_sync(MaviHandle *hh) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return MAVI_ERR_BAD_PARAMS;
+  cudaSetDevice(h->device);
+  return h->check_device_flags();
+}
+
+int32_t mavi_launch_count(MaviHandle *hh, int64_t *n) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || !n) return MAVI_ERR_BAD_PARAMS;
+  *n = h->launches;
+  return MAVI_OK;
+}
+
+int32_t mavi_set_profiling(MaviHandle *hh, int32_t on) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return MAVI_ERR_BAD_PARAMS;
+  h->prof = on != 0;
+  return MAVI_OK;
+}
+
+int32_t mavi_last_step_ms(MaviHandle *hh, float *ms5) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || !ms5) return MAVI_ERR_BAD_PARAMS;
+  cudaSetDevice(h->device);
+  for (int i = 0; i < 5; i++) ms5[i] = 0.f;
+  if (!h->prof) return MAVI_OK;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&ms5[0], h->ev[0], h->ev[1]);
+  cudaEventElapsedTime(&ms5[1], h->ev[1], h->ev[2]);
+  cudaEventElapsedTime(&ms5[2], h->ev[2], h->ev[3]);
+  cudaEventElapsedTime(&ms5[4], h->ev_call[0], h->ev_call[1]);
+  cudaGetLastError();
+  return MAVI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,248 @@
+// common.cuh — device parameter block, exact cell arithmetic, pair laws and the stencil walker shared by all
+// kernels of libmavi_cuda.so.  sm_100a only.  Reference citations are relative to /root/reference/.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mavi.h"
+
+namespace mavi {
+
+// One Line2D (src/configs.jl:95-117) with the frame the ctor derives, laid out as 9 doubles on the device.
+struct DevLine {
+  double p1[2], p2[2], normal[2], tangent[2], length;
+};
+
+struct DevSpace {
+  int wall, geom;
+  double rect_bl[2], rect_sz[2];
+  double cc[2], cr;
+  const DevLine *lines;
+  int n_lines;
+  int pot_kind;
+  double pot[4];
+  double pot_cut2;  // largest r2 with sqrt(r2) <= dist_max (exact cutoff test without sqrt)
+  int pot_mode;
+};
+
+struct DevRings {
+  int num_types, n_max;
+  int num_rings;
+  const double *p0, *relax_time, *vo, *mobility, *rot_diff, *k_area, *k_spring, *l_spring;
+  const int *num_particles;
+  const double *interaction;  // [t1][t2][6]: k_rep,k_atr,dist_eq,dist_max, cut2 (exact r2 threshold), 1/dist_eq
+  const int *types;           // 0-based per ring, or nullptr
+};
+
+// Kernel parameter block (passed by value as __grid_constant__).
+struct DevParams {
+  int n;               // particle slots held by this device
+  int n_count;         // get_num_total_particles(state): number of active ids
+  int num_cols, num_rows, num_cells;
+  int wrap_cols, wrap_rows;  // stencil index wrap (periodic main wall)
+  int periodic;              // calc_diff applies the minimum image (src/integration.jl:43-48)
+  double grid_bl[2], grid_h, cl, ch;
+  double size[2], half[2];   // main rectangle size and size/2
+  int dynamics;
+  double dyn[8];
+  // derived pair-law constants
+  double lj_sig2, lj_24eps;        // LJ / RTP:  F/d = 24 eps s6 (2 s6 - 1) / r2,  s6 = (sig^2/r2)^3
+  double cut2;                     // exact r2 threshold of the law's cutoff (HarmTrunc dist_max, Szabo r_max, RTP 2^(1/6) sigma)
+  double eq2_lo;                   // HarmTrunc: smallest r2 with sqrt(r2) >= dist_eq  (d < dist_eq  <=>  r2 < eq2_lo)
+  double szabo_eq2_hi;             // Szabo: largest r2 with sqrt(r2) <= r_eq          (d > r_eq     <=>  r2 > szabo_eq2_hi)
+  double harm_inv_deq;             // HarmTrunc: 1/dist_eq
+  double szabo_fadh, szabo_frep;   // Szabo: k_adh/r_eq, k_rep/(r_max-r_eq)  (src/integration.jl:79-83)
+  double particle_radius;
+  double dt, term, hdt;            // dt, dt^2/2, dt/2  (src/integration.jl:420-430)
+  int n_spaces;
+  int has_force_walls;
+  DevSpace spaces[MAVI_MAX_SPACES];
+  int rng_mode;
+  unsigned long long seed;
+  DevRings rings;
+};
+
+enum { ERRBIT_OUT_OF_GRID = 1, ERRBIT_NAN = 2 };
+
+#define MAVI_INACTIVE_BIT 0x80000000u
+
+// ---------------------------------------------------------------------------------------------------------
+// Exact Base.div(x::Float64, y::Float64) = round((x - rem(x,y))/y) for y > 0 (call sites src/chunks.jl:129-130).
+// rem is exact, so the reference value is trunc(x/y) of the REAL quotient.  fl(x/y) can be off by one unit when x
+// is a rounded multiple of y; one FMA gives the sign of the exact remainder and fixes it.  Verified against the
+// fmod formulation (oracle mor_julia_div) in tests/test_oracle_kat.py and tests/test_gpu_binning.py.
+__device__ __forceinline__ double julia_div_pos(double x, double y) {
+  double ax = fabs(x);
+  double q = trunc(ax / y);
+  double rem = fma(-q, y, ax);  // sign (and zero-ness) of ax - q*y is exact
+  if (rem < 0.0) q -= 1.0;
+  else if (rem >= y) q += 1.0;
+  return copysign(q, x);
+}
+
+// update_particle_chunk! (src/chunks.jl:120-147): 0-based linear cell id (row fastest), or -1 if out of grid.
+__device__ __forceinline__ int cell_of_point(const DevParams &p, double x, double y) {
+  double rowf = julia_div_pos(-y + p.grid_bl[1] + p.grid_h, p.ch);
+  double colf = julia_div_pos(x - p.grid_bl[0], p.cl);
+  if (!(fabs(rowf) < 2.0e9) || !(fabs(colf) < 2.0e9)) return -1;  // NaN/Inf -> InexactError in the reference
+  int row = (int)rowf + 1, col = (int)colf + 1;
+  row -= (row == p.num_rows + 1) ? 1 : 0;
+  col -= (col == p.num_cols + 1) ? 1 : 0;
+  if (row < 1 || row > p.num_rows || col < 1 || col > p.num_cols) return -1;
+  return (row - 1) + p.num_rows * (col - 1);
+}
+
+// calc_diff component (src/integration.jl:38-48): strict '>', one image.
+template <bool PERIODIC>
+__device__ __forceinline__ double min_image(double d, double half, double size) {
+  if (PERIODIC) {
+    if (fabs(d) > half) d -= copysign(size, d);
+  }
+  return d;
+}
+
+// 1/x to ~1 ulp without the special-case slow path of the IEEE division (x is a finite positive r^2 here).
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));  // MUFU.RCP64H, ~20 bits
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+// r2 exactly as the reference rounds it: sum(dr.^2) = fl(fl(dx*dx) + fl(dy*dy)), no contraction.
+__device__ __forceinline__ double dist2_exact(double dx, double dy) {
+  return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Pair laws: coefficient c with force_on_i = c * dr  (dr = r_i - r_j, minimum image applied).
+template <int DYN>
+__device__ __forceinline__ double pair_coef(const DevParams &p, double r2);
+
+// LenJonesCfg, src/configs.jl:389-397: fmod/d = 4 eps (12 sig^12/d^14 - 6 sig^6/d^8); no cutoff.
+template <>
+__device__ __forceinline__ double pair_coef<MAVI_DYN_LJ>(const DevParams &p, double r2) {
+  double inv = fast_rcp(r2);
+  double s2 = p.lj_sig2 * inv;
+  double s6 = s2 * s2 * s2;
+  return (p.lj_24eps * s6) * fma(2.0, s6, -1.0) * inv;
+}
+
+// HarmTruncCfg, src/configs.jl:354-368: 0 beyond dist_max; fmod/d = -k (d/d_eq - 1)/d = k (1/d - 1/d_eq).
+template <>
+__device__ __forceinline__ double pair_coef<MAVI_DYN_HARMTRUNC>(const DevParams &p, double r2) {
+  if (r2 > p.cut2) return 0.0;
+  double k = (r2 < p.eq2_lo) ? p.dyn[0] : p.dyn[1];
+  double inv_d = rsqrt(r2);
+  return k * (inv_d - p.harm_inv_deq);
+}
+
+// SzaboCfg, src/integration.jl:68-87: -f_mod (d - r_eq) * dr with dr NOT normalised (kept).
+template <>
+__device__ __forceinline__ double pair_coef<MAVI_DYN_SZABO>(const DevParams &p, double r2) {
+  if (r2 > p.cut2) return 0.0;
+  double d = sqrt(r2);
+  double f_mod = (r2 > p.szabo_eq2_hi) ? p.szabo_fadh : p.szabo_frep;
+  return -f_mod * (d - p.dyn[5]);
+}
+
+// RunTumbleCfg, src/integration.jl:89-109: WCA, cutoff 2^(1/6) sigma.
+template <>
+__device__ __forceinline__ double pair_coef<MAVI_DYN_RTP>(const DevParams &p, double r2) {
+  if (r2 > p.cut2) return 0.0;
+  double inv = fast_rcp(r2);
+  double s2 = p.lj_sig2 * inv;
+  double s6 = s2 * s2 * s2;
+  return (p.lj_24eps * s6) * fma(2.0, s6, -1.0) * inv;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Stencil walker.  The reference enumerates same-cell pairs (j > i) plus the half stencil of each cell
+// (src/chunks.jl:61-118, src/integration.jl:116-156) and scatters +f/-f.  As a gather, particle i sees every
+// particle of its own cell and of the half stencil UNITED WITH ITS MIRROR IMAGE = the 8 surrounding cells
+// (wrapped when the main wall is periodic, clipped otherwise).  Visiting wrapped rows/columns individually keeps
+// the reference's double counting on 2-row / 2-column periodic grids.  Cells of one column are contiguous in the
+// sorted order (row fastest), so the walk is at most 3 contiguous runs of `start`.
+//   f(j) is called for every neighbour slot j != self.
+template <typename F>
+__device__ __forceinline__ void for_each_neighbor(const DevParams &p, const int *__restrict__ start, int cell, int self,
+                                                  F &&f) {
+  const int R = p.num_rows, Cn = p.num_cols;
+  const int col = cell / R, row = cell - col * R;
+#pragma unroll 1
+  for (int dc = -1; dc <= 1; dc++) {
+    int c2 = col + dc;
+    if (c2 < 0) {
+      if (!p.wrap_cols) continue;
+      c2 = Cn - 1;
+    } else if (c2 >= Cn) {
+      if (!p.wrap_cols) continue;
+      c2 = 0;
+    }
+    const int base = c2 * R;
+    if (row > 0 && row < R - 1) {
+      int jb = __ldg(start + base + row - 1), je = __ldg(start + base + row + 2);
+      for (int j = jb; j < je; j++)
+        if (j != self) f(j);
+    } else {
+#pragma unroll 1
+      for (int dr = -1; dr <= 1; dr++) {
+        int r2 = row + dr;
+        if (r2 < 0) {
+          if (!p.wrap_rows) continue;
+          r2 = R - 1;
+        } else if (r2 >= R) {
+          if (!p.wrap_rows) continue;
+          r2 = 0;
+        }
+        int jb = __ldg(start + base + r2), je = __ldg(start + base + r2 + 1);
+        for (int j = jb; j < je; j++)
+          if (j != self) f(j);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG (production mode; the reference's Julia RNG streams are not reproducible,
+// SURVEY.md 7 "RNG parity").  key = seed, counter = (particle/ring id, step, stream).
+__device__ __forceinline__ void philox4x32(unsigned int c[4], unsigned int k0, unsigned int k1) {
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    unsigned int hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    unsigned int hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    unsigned int n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+__device__ __forceinline__ double u01_from_bits(unsigned int hi, unsigned int lo) {
+  unsigned long long v = ((unsigned long long)hi << 32) | lo;
+  return (double)(v >> 11) * (1.0 / 9007199254740992.0);  // [0,1)
+}
+
+// two uniforms in [0,1) for (id, step)
+__device__ __forceinline__ void philox_uniform2(unsigned long long seed, unsigned int id, unsigned long long step,
+                                                double &u0, double &u1) {
+  unsigned int c[4] = {id, (unsigned int)step, (unsigned int)(step >> 32), 0x4d415649u};
+  philox4x32(c, (unsigned int)seed, (unsigned int)(seed >> 32));
+  u0 = u01_from_bits(c[0], c[1]);
+  u1 = u01_from_bits(c[2], c[3]);
+}
+
+// one standard normal (Box-Muller) for (id, step)
+__device__ __forceinline__ double philox_normal(unsigned long long seed, unsigned int id, unsigned long long step) {
+  double u0, u1;
+  philox_uniform2(seed, id, step, u0, u1);
+  double r = sqrt(-2.0 * log(1.0 - u0));  // 1-u0 in (0,1]
+  return r * cospi(2.0 * u1);
+}
+
+__device__ __forceinline__ double sign_d(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : x); }
+
+}  // namespace mavi

@@ -1,0 +1,56 @@
+// handle.cuh — host-side state of one MaviHandle (one device, one stream).
+#pragma once
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace mavi {
+
+enum SecondKind { SECOND_VEL = 0, SECOND_ANGLE = 1, SECOND_RING_POL = 2 };
+
+// Rings scratch (RingsInfo, src/rings/rings.jl:118-128)
+struct RingsArrays {
+  double2 *cont_pos = nullptr;  // continuos_pos as of the last unwrap
+  double *areas = nullptr;
+  double2 *cms = nullptr;       // info.cms (lags one step, src/rings/integration.jl:523)
+  double2 *cms_next = nullptr;  // centre of mass of the last unwrap -> becomes cms at the next update_cms!
+  int *types0 = nullptr;        // 0-based ring types
+  double *inter6 = nullptr;
+};
+
+struct Handle {
+  DevParams p;
+  DevArrays a;
+  RingsArrays r;
+  int device = 0;
+  int flags_cfg = 0;
+  cudaStream_t stream = nullptr;
+  SecondKind second_kind = SECOND_VEL;
+  bool cells_valid = false;
+  bool prof = false;
+  long long launches = 0;
+  long long num_steps = 0;
+  double time = 0.0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_call[2] = {nullptr, nullptr};
+  std::vector<void *> allocs;
+  double *noise_dev = nullptr;
+  size_t noise_cap = 0;
+  char err[512] = {0};
+
+  LaunchCtx ctx() { return LaunchCtx{stream, &launches}; }
+  void set_error(const char *fmt, ...);
+  int check_device_flags();
+  int bin_and_sort(bool with_forces);
+  int step_once(const double *noise_dev);
+};
+
+// rings.cu
+int rings_lower(Handle *h, const MaviParams *mp);
+int rings_allocate(Handle *h);
+int rings_upload_finish(Handle *h);
+int rings_step(Handle *h, const double *noise_dev);
+int rings_calc_forces(Handle *h);
+int rings_download_info(Handle *h, void *areas, void *cms, void *cont_pos);
+
+}  // namespace mavi
