@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of the Mavi.jl per-step hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this framework (libmavi_cuda.so through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference ALGORITHM on the host cores (CPU oracle,
+                                                            # Threaded mode: the reference is Julia and cannot run here)
+
+Workload (N=1): the configuration the metric is quoted on — LJ lattice gas, 4000x4000 = 16M particles, periodic
+rectangle, 3600x3600 Chunks, Float64, dt = 0.001, velocities uniform in [-0.2,0.2]^2 (seed 24042001), SURVEY.md 8d.
+A "step" is one newton_step! (bin -> force pass 1 + drift -> force pass 2 + kick + walls) over all particles.
+With N>1 ranks every rank owns an x-slab of 16M particles of a box N times as long (weak scaling).
+
+One JSON line on stdout (rank 0).  `value`: state resident in HBM.  `e2e`: every step uploads pos+vel from pinned host
+memory, steps once and downloads pos+vel (the stateless drop-in call a host-side caller makes).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+SEED = 24042001
+B_ALG_NEWTON = 168.0  # algorithmic bytes per particle-step, Float64 Newton/LJ
+B_ALG_PASS_B = 80.0   # pass B: read pos', vel, F1 (48) + write vel', F2 (32)
+B_ALG_PASS_A = 64.0   # pass A: read pos, vel (32) + write pos', F1 (32)
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def lj_workload(pkg, nx, ny, cuda_device=None, chunks=True):
+    """LJ lattice gas of SURVEY.md 8d (examples/chunks.jl geometry with README sigma=eps=1)."""
+    dyn = pkg.LenJonesCfg(sigma=1.0, epsilon=1.0)
+    pos, geom = pkg.rectangular_grid(nx, ny, 0.4, pkg.particle_radius(dyn))
+    rng = np.random.default_rng(SEED)
+    vel = pkg.random_vel(nx * ny, 1 / 5, rng=rng)
+    space = pkg.SpaceCfg(wall_type=pkg.PeriodicWalls(), geometry_cfg=geom)
+    ccfg = pkg.ChunksCfg(num_cols=int(nx * 0.9), num_rows=int(ny * 0.9)) if chunks else None
+    int_cfg = pkg.IntCfg(dt=0.001, chunks_cfg=ccfg, device=cuda_device or pkg.CUDADevice())
+    return dict(pos=pos, vel=vel, space=space, dyn=dyn, int_cfg=int_cfg, geom=geom)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_rate(pkg, steps, warmup, sample_n=1000, threads=None):
+    """The reference algorithm on the host cores: CPU oracle in Threaded mode (column-partitioned pair loop with private
+    force slices, src/integration.jl:159-194; serial re-bin; two force passes) on a bounded sample of the workload."""
+    oracle = entry.load_oracle()
+    from mavi_jl_b200.params import lower
+    threads = threads or os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    w = lj_workload(pkg, sample_n, sample_n)
+    st = pkg.SecondLawState(pos=w["pos"], vel=w["vel"])
+    o = oracle.OracleSystem(state=st, space_cfg=w["space"], dynamic_cfg=w["dyn"], int_cfg=w["int_cfg"], lower=lower,
+                            threads=threads)
+    if warmup:
+        o.step(warmup)
+    t0 = time.perf_counter()
+    o.step(steps)
+    dt = time.perf_counter() - t0
+    n = sample_n * sample_n
+    return n * steps / dt, dt, threads, f"LJ lattice {sample_n}x{sample_n} = {n} particles (same density/cell ratio as the 16M workload), {steps} steps"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pkg = entry.load_package()
+    rate, secs, threads, sample = cpu_reference_rate(pkg, args.steps, args.warmup, sample_n=args.cpu_sample)
+    line = {
+        "impl": "reference", "metric": "particle-steps/s", "value": rate, "unit": "particle-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "LJ lattice gas 4000x4000=16M, periodic, 3600x3600 chunks, f64, dt=0.001 (bounded sample on CPU)"},
+        "cpu_baseline": {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference algorithm restated in C (oracle, Threaded mode); Julia is not installed, parity unpinned",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libmavi_cuda.so has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = entry.load_package()
+    pkg.load_library()
+
+    nx, ny = args.nx, args.ny
+    stream = torch.cuda.current_stream().cuda_stream
+    dev = pkg.CUDADevice(device=local_rank, stream=stream, flags=args.flags)
+    w = lj_workload(pkg, nx, ny, cuda_device=dev)
+    n = nx * ny
+    state = pkg.SecondLawState(pos=w["pos"], vel=w["vel"])
+    system = pkg.System(state=state, space_cfg=w["space"], dynamic_cfg=w["dyn"], int_cfg=w["int_cfg"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident throughput (`value`) ---------------------------------------------------------------
+    system.step(args.warmup)
+    system.set_profiling(True)
+    launches0 = system.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    system.step(args.steps)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.summary()
+    launches = system.launch_count() - launches0
+    phase_ms = system.last_step_ms()  # bin+sort, pass A, pass B of the last step (CUDA events on the launching stream)
+    system.set_profiling(False)
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * n * args.steps / (ms * 1e-3)
+
+    # ---- end to end through host buffers (`e2e`) -------------------------------------------------------
+    e2e_steps = max(3, min(args.steps, args.e2e_steps))
+    pin_pos = torch.empty((n, 2), dtype=torch.float64).pin_memory()
+    pin_vel = torch.empty((n, 2), dtype=torch.float64).pin_memory()
+    system.sync_to_host()
+    pin_pos.numpy()[...] = system.state.pos
+    pin_vel.numpy()[...] = system.state.vel
+    system.state.pos, system.state.vel = pin_pos.numpy(), pin_vel.numpy()
+
+    def e2e_step():
+        system.upload_state()   # H2D pos+vel from pinned memory (+ constructor-time checks and binning)
+        system.step(1)
+        system.sync_to_host()   # D2H pos+vel into pinned memory
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_kind = measured_peak_hbm()
+    dom = "pass_b" if phase_ms[2] >= phase_ms[1] else "pass_a"
+    dom_ms = phase_ms[2] if dom == "pass_b" else phase_ms[1]
+    dom_bytes = (B_ALG_PASS_B if dom == "pass_b" else B_ALG_PASS_A) * n
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    step_achieved = B_ALG_NEWTON * n * world / (ms * 1e-3 / args.steps) / 1e9
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        rate, secs, threads, sample = cpu_reference_rate(pkg, args.cpu_steps, 1, sample_n=args.cpu_sample)
+        cpu = {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample}
+    line = {
+        "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"LJ lattice gas {nx}x{ny}={n} particles per GPU, periodic rectangle, {int(nx * 0.9)}x{int(ny * 0.9)} chunks, "
+                               f"f64, dt=0.001, newton_step! (2 force passes)", "l2": "state arrays (>=1.5 GB) exceed the 126 MB L2; no flush needed",
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent x-slabs"},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_kind": peak_kind, "kernel_ms": dom_ms,
+                     "step": {"achieved": step_achieved / world, "frac": step_achieved / world / peak, "bytes_per_particle_step": B_ALG_NEWTON},
+                     "phase_ms": {"bin_sort": phase_ms[0], "pass_a": phase_ms[1], "pass_b": phase_ms[2]}},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 32 * n,
+                "steps": e2e_steps, "what": "per step: mavi_upload_state(pos,vel from pinned host) + mavi_step(1) + mavi_download_state(pos,vel)"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=4000)
+    ap.add_argument("--ny", type=int, default=4000)
+    ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-sample", type=int, default=1000, help="CPU baseline sample: an n x n lattice")
+    ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
