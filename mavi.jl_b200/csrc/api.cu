@@ -169,12 +169,17 @@ static int validate_and_lower(Handle *h, const MaviParams *mp) {
     p.grid_h = mp->grid_h;
     p.cl = mp->grid_len / (double)mp->num_cols;
     p.ch = mp->grid_h / (double)mp->num_rows;
+    // interior cells may skip the minimum image when two cell widths + two guarded drifts stay below size/2
+    p.fast_interior = (p.periodic && mp->num_cols >= 8 && mp->num_rows >= 8 && 4.0 * p.cl <= p.half[0] &&
+                       4.0 * p.ch <= p.half[1]) ? 1 : 0;
   }
 
   switch (mp->dynamics) {
     case MAVI_DYN_LJ:
       p.lj_sig2 = mp->dyn[0] * mp->dyn[0];
       p.lj_24eps = 24.0 * mp->dyn[1];
+      p.lj_c48 = 48.0 * mp->dyn[1] / p.lj_sig2;
+      p.lj_c24 = 24.0 * mp->dyn[1] / p.lj_sig2;
       break;
     case MAVI_DYN_HARMTRUNC:
       p.cut2 = sqrt_le_threshold(mp->dyn[3]);
@@ -190,6 +195,8 @@ static int validate_and_lower(Handle *h, const MaviParams *mp) {
     case MAVI_DYN_RTP:
       p.lj_sig2 = mp->dyn[1] * mp->dyn[1];
       p.lj_24eps = 24.0 * mp->dyn[2];
+      p.lj_c48 = 48.0 * mp->dyn[2] / p.lj_sig2;
+      p.lj_c24 = 24.0 * mp->dyn[2] / p.lj_sig2;
       p.cut2 = sqrt_le_threshold(std::pow(2.0, 1.0 / 6.0) * mp->dyn[1]);
       break;
     case MAVI_DYN_RINGS:
@@ -225,6 +232,9 @@ static int allocate(Handle *h) {
   if ((st = dev_alloc(h, &a.start, nc))) return st;
   if ((st = dev_alloc(h, &a.scan_partials, nc / 4096 + 2))) return st;
   if ((st = dev_alloc(h, &a.flags, 8))) return st;
+  if ((st = dev_alloc(h, &a.fix_idx, n))) return st;
+  if ((st = dev_alloc(h, &a.fix_pos, n))) return st;
+  CUDA_TRY(h, cudaMallocHost((void **)&h->flags_host, 8 * sizeof(int)));
   if ((st = dev_alloc(h, &a.reduce_buf, 4096))) return st;
   CUDA_TRY(h, cudaMemsetAsync(a.flags, 0, 8 * sizeof(int), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(a.count, 0, nc * sizeof(int), h->stream));
@@ -237,8 +247,8 @@ static int allocate(Handle *h) {
 
 // Reads the device error word; called at every synchronisation point.
 int Handle::check_device_flags() {
-  int f[2] = {0, 0};
-  cudaError_t e = cudaMemcpyAsync(f, a.flags, sizeof f, cudaMemcpyDeviceToHost, stream);
+  int *f = flags_host;
+  cudaError_t e = cudaMemcpyAsync(f, a.flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   if (e != cudaSuccess) {
     set_error("CUDA error %s while reading the device error word", cudaGetErrorString(e));
@@ -265,7 +275,7 @@ int Handle::bin_and_sort(bool with_forces) {
   LaunchCtx c = ctx();
   const size_t nc = (size_t)p.num_cells + 2;
   CUDA_TRY(this, cudaMemsetAsync(a.count, 0, nc * sizeof(int), stream));
-  CUDA_TRY(this, cudaMemsetAsync(a.flags + 1, 0, sizeof(int), stream));
+  CUDA_TRY(this, cudaMemsetAsync(a.flags + 1, 0, 3 * sizeof(int), stream));
   launch_cell_index(c, p, a.pos[0], a.idflag[0], a.cell[0], a.cell_new, a.count, a.flags);
   launch_exclusive_scan(c, a.count, a.start, a.scan_partials, (int)nc);
   launch_scatter(c, p, a.cell_new, a.start, a.count, a.perm);
@@ -278,6 +288,7 @@ int Handle::bin_and_sort(bool with_forces) {
   else if (second_kind == SECOND_ANGLE) std::swap(a.ang[0], a.ang[1]);
   if (with_forces) std::swap(a.force, a.force_old);
   cells_valid = true;
+  need_sort = false;
   CUDA_TRY(this, cudaGetLastError());
   return MAVI_OK;
 }
@@ -287,12 +298,18 @@ int Handle::step_once(const double *noise_dev) {
   LaunchCtx c = ctx();
   if (p.dynamics == MAVI_DYN_RINGS) return rings_step(this, noise_dev);
   if (prof) cudaEventRecord(ev[0], stream);
-  if ((st = bin_and_sort(false))) return st;
+  // update_chunks!: the previous step proved (exactly, still_in_cell) whether any particle would be binned into another
+  // cell; if none would, the sorted order and cell_start ARE the fresh binning and the counting sort is skipped.
+  if (need_sort || (flags_cfg & MAVI_FLAG_RESORT_EVERY_STEP)) {
+    if ((st = bin_and_sort(false))) return st;
+  }
+  CUDA_TRY(this, cudaMemsetAsync(a.flags + 1, 0, 3 * sizeof(int), stream));
   if (prof) cudaEventRecord(ev[1], stream);
   if (p.dynamics == MAVI_DYN_LJ || p.dynamics == MAVI_DYN_HARMTRUNC) {
     launch_newton_a(c, p, a, 0);  // pos[0] -> pos[1] (drift), F1 -> force_old
     if (prof) cudaEventRecord(ev[2], stream);
-    launch_newton_b(c, p, a, 0);  // pos[1] -> pos[0], vel, F2 -> force
+    launch_newton_b(c, p, a, 0);  // F2 from pos[1]; vel, force; sparse wall fix-ups applied to pos[1]
+    std::swap(a.pos[0], a.pos[1]);
     if (prof) cudaEventRecord(ev[3], stream);
   } else {
     if (prof) cudaEventRecord(ev[2], stream);
@@ -302,6 +319,9 @@ int Handle::step_once(const double *noise_dev) {
   }
   time += p.dt;  // update_time!, src/integration.jl:500-503
   num_steps += 1;
+  // one 16-byte read-back per step: error word + "somebody changed cell" -> decides the next step's re-sort
+  if ((st = check_device_flags())) return st;
+  need_sort = p.num_cells > 0 && flags_host[1] > 0;
   return MAVI_OK;
 }
 
@@ -350,6 +370,8 @@ int32_t mavi_destroy(MaviHandle *hh) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   for (void *ptr : h->allocs) cudaFree(ptr);
+  if (h->flags_host) cudaFreeHost(h->flags_host);
+  if (h->noise_dev) cudaFree(h->noise_dev);
   for (int i = 0; i < 4; i++)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (int i = 0; i < 2; i++)

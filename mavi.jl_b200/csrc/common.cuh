@@ -48,6 +48,8 @@ struct DevParams {
   double dyn[8];
   // derived pair-law constants
   double lj_sig2, lj_24eps;        // LJ / RTP:  F/d = 24 eps s6 (2 s6 - 1) / r2,  s6 = (sig^2/r2)^3
+  double lj_c48, lj_c24;           // 48 eps / sig^2, 24 eps / sig^2:  F/d = u^4 (c48 u^3 - c24),  u = sig^2 / r2
+  int fast_interior;               // grid >= 8x8: interior cells may skip the minimum image (guarded, see kernels.cu)
   double cut2;                     // exact r2 threshold of the law's cutoff (HarmTrunc dist_max, Szabo r_max, RTP 2^(1/6) sigma)
   double eq2_lo;                   // HarmTrunc: smallest r2 with sqrt(r2) >= dist_eq  (d < dist_eq  <=>  r2 < eq2_lo)
   double szabo_eq2_hi;             // Szabo: largest r2 with sqrt(r2) <= r_eq          (d > r_eq     <=>  r2 > szabo_eq2_hi)
@@ -93,6 +95,21 @@ __device__ __forceinline__ int cell_of_point(const DevParams &p, double x, doubl
   return (row - 1) + p.num_rows * (col - 1);
 }
 
+// Exact test "update_particle_chunk! would put (x, y) into `cell` again" without a division: the reference index is
+// trunc of the REAL quotient t/c, so index == k  <=>  k*c <= t < (k+1)*c with the products taken exactly; for a double t
+// that is  RU(k*c) <= t < RU((k+1)*c)  (RU = round-up multiply).  Edge conventions of src/chunks.jl:129-142: index -0
+// (t in (-c, 0)) maps to the first cell, index n (t in [n*c, (n+1)*c)) is clamped to the last cell.
+__device__ __forceinline__ bool axis_in_cell(double t, int k, int n, double c) {
+  bool lo = (k == 0) ? (t > -c) : (t >= __dmul_ru((double)k, c));
+  bool hi = t < __dmul_ru((double)((k == n - 1) ? n + 1 : k + 1), c);
+  return lo && hi;
+}
+__device__ __forceinline__ bool still_in_cell(const DevParams &p, double x, double y, int cell) {
+  const int col = cell / p.num_rows, row = cell - col * p.num_rows;
+  return axis_in_cell(-y + p.grid_bl[1] + p.grid_h, row, p.num_rows, p.ch) &&
+         axis_in_cell(x - p.grid_bl[0], col, p.num_cols, p.cl);
+}
+
 // calc_diff component (src/integration.jl:38-48): strict '>', one image.
 template <bool PERIODIC>
 __device__ __forceinline__ double min_image(double d, double half, double size) {
@@ -106,11 +123,9 @@ __device__ __forceinline__ double min_image(double d, double half, double size) 
 __device__ __forceinline__ double fast_rcp(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));  // MUFU.RCP64H, ~20 bits
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  return r;
+  double e = fma(-x, r, 1.0);   // |e| ~ 2^-20
+  double t = fma(e, e, e);      // r (1 + e + e^2) = (1/x)(1 - e^3): one cubic step instead of two Newton steps
+  return fma(r, t, r);
 }
 
 // r2 exactly as the reference rounds it: sum(dr.^2) = fl(fl(dx*dx) + fl(dy*dy)), no contraction.
@@ -126,10 +141,11 @@ __device__ __forceinline__ double pair_coef(const DevParams &p, double r2);
 // LenJonesCfg, src/configs.jl:389-397: fmod/d = 4 eps (12 sig^12/d^14 - 6 sig^6/d^8); no cutoff.
 template <>
 __device__ __forceinline__ double pair_coef<MAVI_DYN_LJ>(const DevParams &p, double r2) {
-  double inv = fast_rcp(r2);
-  double s2 = p.lj_sig2 * inv;
-  double s6 = s2 * s2 * s2;
-  return (p.lj_24eps * s6) * fma(2.0, s6, -1.0) * inv;
+  double u = p.lj_sig2 * fast_rcp(r2);
+  double u2 = u * u;
+  double u3 = u2 * u;
+  double u4 = u2 * u2;
+  return u4 * fma(u3, p.lj_c48, -p.lj_c24);  // 6 FP64 ops + 3 for the reciprocal
 }
 
 // HarmTruncCfg, src/configs.jl:354-368: 0 beyond dist_max; fmod/d = -k (d/d_eq - 1)/d = k (1/d - 1/d_eq).
@@ -154,10 +170,11 @@ __device__ __forceinline__ double pair_coef<MAVI_DYN_SZABO>(const DevParams &p, 
 template <>
 __device__ __forceinline__ double pair_coef<MAVI_DYN_RTP>(const DevParams &p, double r2) {
   if (r2 > p.cut2) return 0.0;
-  double inv = fast_rcp(r2);
-  double s2 = p.lj_sig2 * inv;
-  double s6 = s2 * s2 * s2;
-  return (p.lj_24eps * s6) * fma(2.0, s6, -1.0) * inv;
+  double u = p.lj_sig2 * fast_rcp(r2);
+  double u2 = u * u;
+  double u3 = u2 * u;
+  double u4 = u2 * u2;
+  return u4 * fma(u3, p.lj_c48, -p.lj_c24);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -27,6 +27,8 @@ struct Handle {
   cudaStream_t stream = nullptr;
   SecondKind second_kind = SECOND_VEL;
   bool cells_valid = false;
+  bool need_sort = true;   // the sorted order is not known to equal the fresh binning
+  int *flags_host = nullptr;  // pinned mirror of a.flags[0..3]
   bool prof = false;
   long long launches = 0;
   long long num_steps = 0;

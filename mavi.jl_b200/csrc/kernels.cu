@@ -201,21 +201,63 @@ void launch_gather(const LaunchCtx &c, const DevParams &p, const int *perm, cons
 // Pair forces (calc_forces!, src/integration.jl:112-224) as a per-particle gather, fused with the integrators.
 // =========================================================================================================
 
-template <int DYN, bool PER>
+// flags[] layout (device error / control word)
+enum { FLAG_ERR = 0, FLAG_CHANGED = 1, FLAG_BIGMOVE = 2, FLAG_NFIX = 3 };
+
+template <int DYN, bool MINIMG>
 __device__ __forceinline__ void accumulate_pair(const DevParams &p, double2 ri, double2 rj, double &fx, double &fy) {
-  double dx = min_image<PER>(ri.x - rj.x, p.half[0], p.size[0]);
-  double dy = min_image<PER>(ri.y - rj.y, p.half[1], p.size[1]);
-  double r2 = dist2_exact(dx, dy);
+  double dx = min_image<MINIMG>(ri.x - rj.x, p.half[0], p.size[0]);
+  double dy = min_image<MINIMG>(ri.y - rj.y, p.half[1], p.size[1]);
+  // laws with a cutoff need r2 rounded exactly like the reference (bit-exact neighbour decisions); LJ has no cutoff
+  double r2 = (DYN == MAVI_DYN_LJ) ? fma(dx, dx, dy * dy) : dist2_exact(dx, dy);
   double c = pair_coef<DYN>(p, r2);
   fx = fma(c, dx, fx);
   fy = fma(c, dy, fy);
 }
 
+// Interior cell (no stencil wrap / clipping): the neighbours are 4 contiguous runs of the sorted order
+//   column-1: [a0,b0)   own column: [a1,k) and (k,b1)   column+1: [a2,b2)
+// walked by ONE flat, branch-free loop: neighbour t lives at slot t + offset(t) (three compares select the offset), so
+// a warp waits for the max over lanes of the neighbour COUNT instead of the sum of per-column maxima, and the next
+// position is prefetched while the current pair is evaluated.
+template <int DYN, bool MINIMG>
+__device__ __forceinline__ void interior_force(const DevParams &p, const int *__restrict__ start,
+                                               const double2 *__restrict__ pos, int cell, int k, double2 ri, double &fx,
+                                               double &fy) {
+  const int R = p.num_rows;
+  const int *s = start + cell;
+  const int a0 = __ldg(s - R - 1), b0 = __ldg(s - R + 2);
+  const int a1 = __ldg(s - 1), b1 = __ldg(s + 2);
+  const int a2 = __ldg(s + R - 1), b2 = __ldg(s + R + 2);
+  const int c1 = b0 - a0;            // neighbours t <  c1          -> slot a0 + t
+  const int c2 = c1 + (k - a1);      //            c1 <= t < c2    -> slot a1 + (t - c1)
+  const int c3 = c2 + (b1 - k - 1);  //            c2 <= t < c3    -> slot k + 1 + (t - c2)   (skips self)
+  const int total = c3 + (b2 - a2);  //            c3 <= t         -> slot a2 + (t - c3)
+  if (total <= 0) return;
+  const int d1 = (a1 - c1) - a0, d3 = (a2 - c3) - (a1 - c1) - 1;
+  // slot(t) = t + a0 + [t>=c1] d1 + [t>=c2] + [t>=c3] d3   (predicated adds, no branches)
+  auto slot = [&](int t) { return t + a0 + (t >= c1 ? d1 : 0) + (t >= c2 ? 1 : 0) + (t >= c3 ? d3 : 0); };
+  // two neighbours per trip: independent FP64 chains, and the loads of the next pair are in flight meanwhile
+  double2 r0 = __ldg(pos + slot(0));
+  double2 r1 = (total > 1) ? __ldg(pos + slot(1)) : r0;
+  int t = 0;
+#pragma unroll 1
+  for (; t + 2 <= total; t += 2) {
+    const double2 q0 = r0, q1 = r1;
+    if (t + 2 < total) r0 = __ldg(pos + slot(t + 2));
+    if (t + 3 < total) r1 = __ldg(pos + slot(t + 3));
+    accumulate_pair<DYN, MINIMG>(p, ri, q0, fx, fy);
+    accumulate_pair<DYN, MINIMG>(p, ri, q1, fx, fy);
+  }
+  if (t < total) accumulate_pair<DYN, MINIMG>(p, ri, r0, fx, fy);
+}
+
 // ALLP: chunks === nothing -> all pairs over active ids (src/integration.jl:197-224); physical order = id order.
+// exact_minimg: force the minimum image on interior cells too (pass B after an abnormally large drift).
 template <int DYN, bool PER, bool ALLP>
 __device__ __forceinline__ double2 pair_force(const DevParams &p, const int *__restrict__ start,
                                               const double2 *__restrict__ pos, const unsigned int *__restrict__ idflag,
-                                              int cell, int k, double2 ri) {
+                                              int cell, int k, double2 ri, bool exact_minimg) {
   double fx = 0.0, fy = 0.0;
   if (ALLP) {
     for (int j = 0; j < p.n; j++) {
@@ -223,14 +265,25 @@ __device__ __forceinline__ double2 pair_force(const DevParams &p, const int *__r
       accumulate_pair<DYN, PER>(p, ri, __ldg(pos + j), fx, fy);
     }
   } else {
-    for_each_neighbor(p, start, cell, k, [&](int j) { accumulate_pair<DYN, PER>(p, ri, __ldg(pos + j), fx, fy); });
+    const int R = p.num_rows;
+    const int col = cell / R, row = cell - col * R;
+    const bool interior = row >= 1 && row <= R - 2 && col >= 1 && col <= p.num_cols - 2;
+    if (interior) {
+      // Fresh cells: both particles of a pair lie inside 8-adjacent cells, so |dr| < 2 cell widths <= size/4 on a grid
+      // of >= 8 cells per axis and the reference's `abs(dr) > size/2` test is false: min image skipped EXACTLY.
+      // Stale cells (Verlet pass 2) are covered by the per-step displacement guard (FLAG_BIGMOVE).
+      if (PER && (exact_minimg || !p.fast_interior)) interior_force<DYN, true>(p, start, pos, cell, k, ri, fx, fy);
+      else interior_force<DYN, false>(p, start, pos, cell, k, ri, fx, fy);
+    } else {
+      for_each_neighbor(p, start, cell, k, [&](int j) { accumulate_pair<DYN, PER>(p, ri, __ldg(pos + j), fx, fy); });
+    }
   }
   return make_double2(fx, fy);
 }
 
 // clean_forces! + calc_forces! (+ calc_walls_forces!): the force state after src/integration.jl:508-511.
 template <int DYN, bool PER, bool ALLP>
-__global__ void k_force_only(const __grid_constant__ DevParams p, const int *__restrict__ start,
+__global__ void __launch_bounds__(TPB) k_force_only(const __grid_constant__ DevParams p, const int *__restrict__ start,
                              const int *__restrict__ cell, const unsigned int *__restrict__ idflag,
                              const double2 *__restrict__ pos, double2 *__restrict__ force, int with_walls) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -238,7 +291,7 @@ __global__ void k_force_only(const __grid_constant__ DevParams p, const int *__r
   double2 F = make_double2(0.0, 0.0);
   if (!(idflag[k] & MAVI_INACTIVE_BIT)) {
     double2 r = pos[k];
-    F = pair_force<DYN, PER, ALLP>(p, start, pos, idflag, ALLP ? 0 : cell[k], k, r);
+    F = pair_force<DYN, PER, ALLP>(p, start, pos, idflag, ALLP ? 0 : cell[k], k, r, false);
     if (with_walls && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
   }
   force[k] = F;
@@ -247,104 +300,137 @@ __global__ void k_force_only(const __grid_constant__ DevParams p, const int *__r
 // newton_step! first half (src/integration.jl:507-512 + update_verlet! :418-424):
 //   F1 = pair forces + wall forces;  pos' = pos + vel dt + F1 dt^2/2  (every slot, active or not).
 template <int DYN, bool PER, bool ALLP>
-__global__ void k_newton_a(const __grid_constant__ DevParams p, const int *__restrict__ start,
+__global__ void __launch_bounds__(TPB) k_newton_a(const __grid_constant__ DevParams p, const int *__restrict__ start,
                            const int *__restrict__ cell, const unsigned int *__restrict__ idflag,
                            const double2 *__restrict__ pos_in, const double2 *__restrict__ vel,
-                           double2 *__restrict__ pos_out, double2 *__restrict__ f1) {
+                           double2 *__restrict__ pos_out, double2 *__restrict__ f1, int *__restrict__ flags) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= p.n) return;
   double2 r = pos_in[k];
   double2 F = make_double2(0.0, 0.0);
   if (!(idflag[k] & MAVI_INACTIVE_BIT)) {
-    F = pair_force<DYN, PER, ALLP>(p, start, pos_in, idflag, ALLP ? 0 : cell[k], k, r);
+    F = pair_force<DYN, PER, ALLP>(p, start, pos_in, idflag, ALLP ? 0 : cell[k], k, r, false);
     if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
   }
   double2 v = vel[k];
-  r.x = r.x + (v.x * p.dt + F.x * p.term);
-  r.y = r.y + (v.y * p.dt + F.y * p.term);
+  double mx = v.x * p.dt + F.x * p.term, my = v.y * p.dt + F.y * p.term;
+  r.x = r.x + mx;
+  r.y = r.y + my;
+  // displacement guard of the interior fast path: a drift beyond one cell in one step makes pass B take the exact
+  // (minimum-image everywhere) path.  Never happens in a stable run; keeps the fast path assumption-free.
+  if (!ALLP && PER && !(fabs(mx) <= p.cl && fabs(my) <= p.ch)) flags[FLAG_BIGMOVE] = 1;
   pos_out[k] = r;
   f1[k] = F;
 }
 
 // newton_step! second half (update_verlet! :426-430, walls! :513): F2 on the drifted positions with the STALE cell
-// lists and WITHOUT wall forces; vel += dt/2 (F2 + F1); walls!(active ids).
+// lists and WITHOUT wall forces; vel += dt/2 (F2 + F1); walls!(active ids).  Also decides, exactly, whether the next
+// update_chunks! would put the particle into the cell it is sorted under (-> the re-sort can be skipped), and defers
+// position changes made by walls! (periodic wrap, slippery projection) to a sparse fix-up list because neighbours
+// still read the unmodified drifted positions in this launch.
 template <int DYN, bool PER, bool ALLP>
-__global__ void k_newton_b(const __grid_constant__ DevParams p, const int *__restrict__ start,
+__global__ void __launch_bounds__(TPB) k_newton_b(const __grid_constant__ DevParams p, const int *__restrict__ start,
                            const int *__restrict__ cell, const unsigned int *__restrict__ idflag,
                            const double2 *__restrict__ pos_in, double2 *__restrict__ vel,
-                           const double2 *__restrict__ f1, double2 *__restrict__ f2, double2 *__restrict__ pos_out) {
+                           const double2 *__restrict__ f1, double2 *__restrict__ f2, int *__restrict__ flags,
+                           int *__restrict__ fix_idx, double2 *__restrict__ fix_pos) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= p.n) return;
-  double2 r = pos_in[k];
-  double2 F = make_double2(0.0, 0.0);
-  const bool active = !(idflag[k] & MAVI_INACTIVE_BIT);
-  if (active) F = pair_force<DYN, PER, ALLP>(p, start, pos_in, idflag, ALLP ? 0 : cell[k], k, r);
-  double2 v = vel[k];
-  double2 Fo = f1[k];
-  v.x = v.x + p.hdt * (F.x + Fo.x);
-  v.y = v.y + p.hdt * (F.y + Fo.y);
-  if (active) apply_walls<true>(p, r.x, r.y, v.x, v.y, p.particle_radius);
-  vel[k] = v;
-  f2[k] = F;
-  pos_out[k] = r;
+  bool changed = false;
+  if (k < p.n) {
+    double2 r = pos_in[k];
+    double2 F = make_double2(0.0, 0.0);
+    const bool active = !(idflag[k] & MAVI_INACTIVE_BIT);
+    const int c = ALLP ? 0 : cell[k];
+    if (active) F = pair_force<DYN, PER, ALLP>(p, start, pos_in, idflag, c, k, r, !ALLP && flags[FLAG_BIGMOVE] != 0);
+    double2 v = vel[k];
+    double2 Fo = f1[k];
+    v.x = v.x + p.hdt * (F.x + Fo.x);
+    v.y = v.y + p.hdt * (F.y + Fo.y);
+    if (active) {
+      const double x0 = r.x, y0 = r.y;
+      apply_walls<true>(p, r.x, r.y, v.x, v.y, p.particle_radius);
+      if (r.x != x0 || r.y != y0) {
+        int m = atomicAdd(&flags[FLAG_NFIX], 1);
+        fix_idx[m] = k;
+        fix_pos[m] = r;
+      }
+      if (!ALLP) changed = !still_in_cell(p, r.x, r.y, c);
+    }
+    vel[k] = v;
+    f2[k] = F;
+  }
+  unsigned int m = __ballot_sync(0xffffffffu, changed);
+  if (m && (threadIdx.x & 31) == 0) atomicAdd(&flags[FLAG_CHANGED], __popc(m));
+}
+
+__global__ void k_apply_pos_fixes(const int *__restrict__ flags, const int *__restrict__ fix_idx,
+                                  const double2 *__restrict__ fix_pos, double2 *__restrict__ pos) {
+  const int n = flags[FLAG_NFIX];
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) pos[fix_idx[m]] = fix_pos[m];
 }
 
 // szabo_step! / rtp_step! (src/integration.jl:517-535): forces + update_szabo! (:433-465) / update_rtp! (:467-498)
 // + walls! in ONE pass.  The update loops slots 1:count (not ids) like the reference.
 template <int DYN, bool PER, bool ALLP>
-__global__ void k_self_propelled(const __grid_constant__ DevParams p, const int *__restrict__ start,
+__global__ void __launch_bounds__(TPB) k_self_propelled(const __grid_constant__ DevParams p, const int *__restrict__ start,
                                  const int *__restrict__ cell, const unsigned int *__restrict__ idflag,
                                  const double2 *__restrict__ pos_in, double *__restrict__ ang,
                                  double2 *__restrict__ pos_out, double2 *__restrict__ force,
-                                 const double *__restrict__ noise, unsigned long long step) {
+                                 const double *__restrict__ noise, unsigned long long step, int *__restrict__ flags) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= p.n) return;
-  const unsigned int idf = idflag[k];
-  const bool active = !(idf & MAVI_INACTIVE_BIT);
-  const unsigned int id = idf & ~MAVI_INACTIVE_BIT;
-  double2 r = pos_in[k];
-  double2 F = make_double2(0.0, 0.0);
-  if (active) {
-    F = pair_force<DYN, PER, ALLP>(p, start, pos_in, idflag, ALLP ? 0 : cell[k], k, r);
-    if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
-  }
-  force[k] = F;
-  if ((int)id < p.n_count) {
-    double theta = ang[k];
-    double sn, cs;
-    sincos(theta, &sn, &cs);
-    if (DYN == MAVI_DYN_SZABO) {
-      const double vo = p.dyn[0], mu = p.dyn[1], relax_time = p.dyn[2], drot = p.dyn[7];
-      double velx = vo * cs + mu * F.x, vely = vo * sn + mu * F.y;
-      double speed = sqrt(fabs(velx) + fabs(vely));  // sqrt(sum(abs, vel)) (sic), :448
-      double cross_prod = speed > 0.0 ? (cs * vely - sn * velx) / speed : 0.0;
-      if (fabs(cross_prod) > 1.0) cross_prod = sign_d(cross_prod);
-      double nz = 0.0;
-      if (drot != 0.0) nz = (p.rng_mode == MAVI_RNG_HOST_NOISE) ? (noise ? noise[id] : 0.0) : philox_normal(p.seed, id, step);
-      double d_theta = 1.0 / relax_time * asin(cross_prod) * p.dt + sqrt(2.0 * drot * p.dt) * nz;
-      r.x += velx * p.dt;
-      r.y += vely * p.dt;
-      ang[k] = theta + d_theta;
-    } else {
-      const double vo = p.dyn[0], tumble_rate = p.dyn[3];
-      double velx = vo * cs + F.x, vely = vo * sn + F.y;
-      r.x += velx * p.dt;
-      r.y += vely * p.dt;
-      double u, u2;
-      if (p.rng_mode == MAVI_RNG_HOST_NOISE) {
-        u = noise ? noise[2 * (size_t)id] : 1.0;
-        u2 = noise ? noise[2 * (size_t)id + 1] : 0.0;
-      } else {
-        philox_uniform2(p.seed, id, step, u, u2);
-      }
-      if (u < tumble_rate * p.dt) ang[k] = 6.283185307179586 * u2;  // 2*pi*rand(), :495
+  bool changed = false;
+  if (k < p.n) {
+    const unsigned int idf = idflag[k];
+    const bool active = !(idf & MAVI_INACTIVE_BIT);
+    const unsigned int id = idf & ~MAVI_INACTIVE_BIT;
+    const int c = ALLP ? 0 : cell[k];
+    double2 r = pos_in[k];
+    double2 F = make_double2(0.0, 0.0);
+    if (active) {
+      F = pair_force<DYN, PER, ALLP>(p, start, pos_in, idflag, c, k, r, false);
+      if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
     }
+    force[k] = F;
+    if ((int)id < p.n_count) {
+      double theta = ang[k];
+      double sn, cs;
+      sincos(theta, &sn, &cs);
+      if (DYN == MAVI_DYN_SZABO) {
+        const double vo = p.dyn[0], mu = p.dyn[1], relax_time = p.dyn[2], drot = p.dyn[7];
+        double velx = vo * cs + mu * F.x, vely = vo * sn + mu * F.y;
+        double speed = sqrt(fabs(velx) + fabs(vely));  // sqrt(sum(abs, vel)) (sic), :448
+        double cross_prod = speed > 0.0 ? (cs * vely - sn * velx) / speed : 0.0;
+        if (fabs(cross_prod) > 1.0) cross_prod = sign_d(cross_prod);
+        double nz = 0.0;
+        if (drot != 0.0) nz = (p.rng_mode == MAVI_RNG_HOST_NOISE) ? (noise ? noise[id] : 0.0) : philox_normal(p.seed, id, step);
+        double d_theta = 1.0 / relax_time * asin(cross_prod) * p.dt + sqrt(2.0 * drot * p.dt) * nz;
+        r.x += velx * p.dt;
+        r.y += vely * p.dt;
+        ang[k] = theta + d_theta;
+      } else {
+        const double vo = p.dyn[0], tumble_rate = p.dyn[3];
+        double velx = vo * cs + F.x, vely = vo * sn + F.y;
+        r.x += velx * p.dt;
+        r.y += vely * p.dt;
+        double u, u2;
+        if (p.rng_mode == MAVI_RNG_HOST_NOISE) {
+          u = noise ? noise[2 * (size_t)id] : 1.0;
+          u2 = noise ? noise[2 * (size_t)id + 1] : 0.0;
+        } else {
+          philox_uniform2(p.seed, id, step, u, u2);
+        }
+        if (u < tumble_rate * p.dt) ang[k] = 6.283185307179586 * u2;  // 2*pi*rand(), :495
+      }
+    }
+    if (active) {
+      double vx = 0.0, vy = 0.0;
+      apply_walls<false>(p, r.x, r.y, vx, vy, p.particle_radius);
+      if (!ALLP) changed = !still_in_cell(p, r.x, r.y, c);
+    }
+    pos_out[k] = r;
   }
-  if (active) {
-    double vx = 0.0, vy = 0.0;
-    apply_walls<false>(p, r.x, r.y, vx, vy, p.particle_radius);
-  }
-  pos_out[k] = r;
+  unsigned int m = __ballot_sync(0xffffffffu, changed);
+  if (m && (threadIdx.x & 31) == 0) atomicAdd(&flags[FLAG_CHANGED], __popc(m));
 }
 
 // ---- dispatch over (dynamics, periodic, all-pairs) ----------------------------------------------------------
@@ -373,7 +459,7 @@ void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &
 void launch_newton_a(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int cur) {
   const bool allp = p.num_cells == 0;
 #define CALL(D, P, A) \
-  MAVI_LAUNCH(c, (k_newton_a<D, P, A>), nblk(p.n), TPB, p, a.start, a.cell[cur], a.idflag[cur], a.pos[cur], a.vel[cur], a.pos[cur ^ 1], a.force_old)
+  MAVI_LAUNCH(c, (k_newton_a<D, P, A>), nblk(p.n), TPB, p, a.start, a.cell[cur], a.idflag[cur], a.pos[cur], a.vel[cur], a.pos[cur ^ 1], a.force_old, a.flags)
   if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, allp, CALL);
   else MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, allp, CALL);
 #undef CALL
@@ -381,19 +467,20 @@ void launch_newton_a(const LaunchCtx &c, const DevParams &p, const DevArrays &a,
 
 void launch_newton_b(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int cur) {
   const bool allp = p.num_cells == 0;
-  // reads the drifted positions pos[cur^1], writes the final positions back into pos[cur]
+  // reads the drifted positions pos[cur^1] (which become the current positions after the sparse wall fix-ups)
 #define CALL(D, P, A) \
-  MAVI_LAUNCH(c, (k_newton_b<D, P, A>), nblk(p.n), TPB, p, a.start, a.cell[cur], a.idflag[cur], a.pos[cur ^ 1], a.vel[cur], a.force_old, a.force, a.pos[cur])
+  MAVI_LAUNCH(c, (k_newton_b<D, P, A>), nblk(p.n), TPB, p, a.start, a.cell[cur], a.idflag[cur], a.pos[cur ^ 1], a.vel[cur], a.force_old, a.force, a.flags, a.fix_idx, a.fix_pos)
   if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, allp, CALL);
   else MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, allp, CALL);
 #undef CALL
+  MAVI_LAUNCH(c, k_apply_pos_fixes, 64, TPB, a.flags, a.fix_idx, a.fix_pos, a.pos[cur ^ 1]);
 }
 
 void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int cur, const double *noise,
                            unsigned long long step) {
   const bool allp = p.num_cells == 0;
 #define CALL(D, P, A) \
-  MAVI_LAUNCH(c, (k_self_propelled<D, P, A>), nblk(p.n), TPB, p, a.start, a.cell[cur], a.idflag[cur], a.pos[cur], a.ang[cur], a.pos[cur ^ 1], a.force, noise, step)
+  MAVI_LAUNCH(c, (k_self_propelled<D, P, A>), nblk(p.n), TPB, p, a.start, a.cell[cur], a.idflag[cur], a.pos[cur], a.ang[cur], a.pos[cur ^ 1], a.force, noise, step, a.flags)
   if (p.dynamics == MAVI_DYN_SZABO) MAVI_DISPATCH_DYN(MAVI_DYN_SZABO, p.periodic, allp, CALL);
   else MAVI_DISPATCH_DYN(MAVI_DYN_RTP, p.periodic, allp, CALL);
 #undef CALL

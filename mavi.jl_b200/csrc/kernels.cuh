@@ -20,7 +20,9 @@ struct DevArrays {
   int *count;           // [num_cells+2] histogram / scatter cursors
   int *start;           // [num_cells+2] exclusive scan of count
   int *scan_partials;   // block sums of the scan
-  int *flags;           // [0] error bits, [1] number of particles whose cell changed
+  int *flags;           // [0] error bits, [1] #particles that left their sorted cell, [2] big-drift guard, [3] #position fix-ups
+  int *fix_idx;         // sparse list of slots whose position walls! changed in pass B
+  double2 *fix_pos;
   double *reduce_buf;   // block partials of the energy reductions
 };
 
