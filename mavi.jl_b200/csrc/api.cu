@@ -208,53 +208,185 @@ static int validate_and_lower(Handle *h, const MaviParams *mp) {
   return MAVI_OK;
 }
 
+// magic number for x / d, valid for 0 <= x < 2^31 (round-up method with a 32-bit multiplier)
+static void magic_div(unsigned int d, unsigned int *mul, unsigned int *shr) {
+  if (d <= 1) { *mul = 0; *shr = 0; return; }  // d == 1: identity (fastdiv special-cases mul == 0)
+  unsigned int l = 0;
+  while ((1ull << l) < d) ++l;  // l = ceil(log2 d)
+  unsigned long long m = ((1ull << (31 + l)) + d - 1) / d;  // ceil(2^(31+l) / d) fits in 32 bits
+  *mul = (unsigned int)m;
+  *shr = l - 1;
+}
+
+static void dev_free(Handle *h, void *ptr) {
+  if (!ptr) return;
+  for (auto &q : h->allocs)
+    if (q == ptr) q = nullptr;
+  cudaFree(ptr);
+}
+
+// handle-lifetime arrays: staging (dense, n entries), control words, scratch that does not depend on the tile capacity
 static int allocate(Handle *h) {
   const DevParams &p = h->p;
   DevArrays &a = h->a;
   const size_t n = (size_t)p.n;
   int st;
-  for (int b = 0; b < 2; b++) {
-    if ((st = dev_alloc(h, &a.pos[b], n))) return st;
-    if ((st = dev_alloc(h, &a.idflag[b], n))) return st;
-    if ((st = dev_alloc(h, &a.cell[b], n))) return st;
-    if (h->second_kind == SECOND_VEL) {
-      if ((st = dev_alloc(h, &a.vel[b], n))) return st;
-    } else {
-      if ((st = dev_alloc(h, &a.ang[b], h->second_kind == SECOND_RING_POL ? (size_t)p.rings.num_rings : n))) return st;
-    }
+  memset(&a, 0, sizeof a);
+  if ((st = dev_alloc(h, &a.st_pos, n))) return st;
+  if ((st = dev_alloc(h, &a.st_force, n))) return st;
+  if ((st = dev_alloc(h, &a.st_id, n))) return st;
+  if ((st = dev_alloc(h, &a.st_cell, n))) return st;
+  if (h->second_kind == SECOND_VEL) {
+    if ((st = dev_alloc(h, &a.st_vel, n))) return st;
+  } else {
+    if ((st = dev_alloc(h, &a.st_ang, h->second_kind == SECOND_RING_POL ? (size_t)p.rings.num_rings : n))) return st;
   }
-  if ((st = dev_alloc(h, &a.force, n))) return st;
-  if ((st = dev_alloc(h, &a.force_old, n))) return st;
-  if ((st = dev_alloc(h, &a.cell_new, n))) return st;
-  if ((st = dev_alloc(h, &a.perm, n))) return st;
   const size_t nc = (size_t)p.num_cells + 2;
   if ((st = dev_alloc(h, &a.count, nc))) return st;
-  if ((st = dev_alloc(h, &a.start, nc))) return st;
-  if ((st = dev_alloc(h, &a.scan_partials, nc / 4096 + 2))) return st;
-  if ((st = dev_alloc(h, &a.flags, 8))) return st;
+  if ((st = dev_alloc(h, &a.flags, FLAG_COUNT))) return st;
   if ((st = dev_alloc(h, &a.fix_idx, n))) return st;
   if ((st = dev_alloc(h, &a.fix_pos, n))) return st;
-  CUDA_TRY(h, cudaMallocHost((void **)&h->flags_host, 8 * sizeof(int)));
   if ((st = dev_alloc(h, &a.reduce_buf, 4096))) return st;
-  CUDA_TRY(h, cudaMemsetAsync(a.flags, 0, 8 * sizeof(int), h->stream));
+  if ((st = dev_alloc(h, &a.cta_first, n / TPB + 2))) return st;
+  CUDA_TRY(h, cudaMallocHost((void **)&h->flags_host, FLAG_COUNT * sizeof(int)));
+  CUDA_TRY(h, cudaMemsetAsync(a.flags, 0, FLAG_COUNT * sizeof(int), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(a.count, 0, nc * sizeof(int), h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(a.start, 0, nc * sizeof(int), h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(a.force, 0, n * sizeof(double2), h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(a.force_old, 0, n * sizeof(double2), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(a.st_force, 0, n * sizeof(double2), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(a.cta_first, 0, (n / TPB + 2) * sizeof(int), h->stream));
   if (h->second_kind == SECOND_RING_POL) return rings_allocate(h);
+  return MAVI_OK;
+}
+
+// slot-indexed state for a given tile capacity (re-done when a tile overflows)
+int Handle::alloc_state(int n_active, int cap) {
+  DevArrays &A = a;
+  void *old[] = {A.pos[0], A.pos[1], A.vel, A.ang, A.idflag, A.cell, A.force, A.force_old, A.tstart, A.tile_prefix,
+                 A.perm, A.scan_partials, A.tile_dirty, A.dirty_list, A.inbox_cnt, A.inbox, A.mv_src, A.mv_pos,
+                 A.mv_second, A.mv_force, A.mv_id, A.mv_cell};
+  for (void *q : old) dev_free(this, q);
+  p.n_active = p.num_cells > 0 ? n_active : 0;
+  p.n_count = n_active;
+  if (p.num_cells > 0) {
+    p.tpc = (p.num_rows + MAVI_TR - 1) / MAVI_TR;
+    p.nt = p.num_cols * p.tpc;
+    p.cap = cap;
+    long long slots = (long long)p.nt * cap + (p.n - n_active);
+    if (slots > 0x7ffffff0LL) {
+      set_error("tile layout needs %lld slots (> 2^31)", slots);
+      return MAVI_ERR_BAD_PARAMS;
+    }
+    p.tail_base = p.nt * cap;
+    magic_div((unsigned int)p.num_rows, &p.rows_mul, &p.rows_shr);
+    magic_div((unsigned int)p.tpc, &p.tpc_mul, &p.tpc_shr);
+    magic_div((unsigned int)p.num_cols, &p.cols_mul, &p.cols_shr);
+    p.inbox_cap = 16;
+    p.mv_cap = p.n / 4 > 4096 ? p.n / 4 : 4096;
+  } else {
+    p.tpc = p.nt = p.cap = 0;
+    p.tail_base = 0;
+    p.inbox_cap = p.mv_cap = 0;
+  }
+  ns = (size_t)p.tail_base + (size_t)(p.n - p.n_active);
+  int st;
+  for (int b = 0; b < 2; b++)
+    if ((st = dev_alloc(this, &A.pos[b], ns))) return st;
+  if (second_kind == SECOND_VEL) {
+    if ((st = dev_alloc(this, &A.vel, ns))) return st;
+  } else if (second_kind == SECOND_ANGLE) {
+    if ((st = dev_alloc(this, &A.ang, ns))) return st;
+  }
+  if ((st = dev_alloc(this, &A.idflag, ns))) return st;
+  if ((st = dev_alloc(this, &A.cell, ns))) return st;
+  if ((st = dev_alloc(this, &A.force, ns))) return st;
+  if ((st = dev_alloc(this, &A.force_old, ns))) return st;
+  const size_t nt = (size_t)p.nt;
+  if ((st = dev_alloc(this, &A.tstart, nt * (MAVI_TR + 1) + 1))) return st;
+  if ((st = dev_alloc(this, &A.tile_prefix, nt + 2))) return st;
+  if ((st = dev_alloc(this, &A.perm, ns + nt + 2))) return st;
+  if ((st = dev_alloc(this, &A.scan_partials, (nt + 2) / 4096 + 2))) return st;
+  if ((st = dev_alloc(this, &A.tile_dirty, nt + 1))) return st;
+  if ((st = dev_alloc(this, &A.dirty_list, nt + 1))) return st;
+  if ((st = dev_alloc(this, &A.inbox_cnt, nt + 1))) return st;
+  if ((st = dev_alloc(this, &A.inbox, nt * (size_t)p.inbox_cap + 1))) return st;
+  const size_t mv = (size_t)p.mv_cap + 1;
+  if ((st = dev_alloc(this, &A.mv_src, mv))) return st;
+  if ((st = dev_alloc(this, &A.mv_pos, mv))) return st;
+  if ((st = dev_alloc(this, &A.mv_second, mv))) return st;
+  if ((st = dev_alloc(this, &A.mv_force, mv))) return st;
+  if ((st = dev_alloc(this, &A.mv_id, mv))) return st;
+  if ((st = dev_alloc(this, &A.mv_cell, mv))) return st;
+  CUDA_TRY(this, cudaMemsetAsync(A.force_old, 0, ns * sizeof(double2), stream));
+  CUDA_TRY(this, cudaMemsetAsync(A.pos[1], 0, ns * sizeof(double2), stream));
+  return MAVI_OK;
+}
+
+static int round_up16(double x) { return ((int)std::ceil(x) + 15) / 16 * 16; }
+
+// update_chunks! from scratch: staging arrays -> tile layout.  Grows the tile capacity until every tile fits.
+int Handle::rebuild_from_staging(int n_active) {
+  const bool second_is_vel = second_kind == SECOND_VEL;
+  int cap = p.cap;
+  if (p.num_cells > 0 && (a.pos[0] == nullptr || n_active != p.n_active || cap <= 0)) {
+    const long long ntiles = (long long)p.num_cols * ((p.num_rows + MAVI_TR - 1) / MAVI_TR);
+    cap = round_up16(2.0 * (double)n_active / (double)ntiles + 16.0);
+    int st = alloc_state(n_active, cap);
+    if (st) return st;
+  } else if (a.pos[0] == nullptr || n_active != p.n_count) {
+    int st = alloc_state(n_active, 0);
+    if (st) return st;
+  }
+  for (int attempt = 0; attempt < 8; attempt++) {
+    if (p.num_cells == 0) {
+      // chunks === nothing: slots are the original order; plain copies
+      const size_t n = (size_t)p.n;
+      CUDA_TRY(this, cudaMemcpyAsync(a.pos[0], a.st_pos, n * sizeof(double2), cudaMemcpyDeviceToDevice, stream));
+      if (second_is_vel) CUDA_TRY(this, cudaMemcpyAsync(a.vel, a.st_vel, n * sizeof(double2), cudaMemcpyDeviceToDevice, stream));
+      else if (second_kind == SECOND_ANGLE) CUDA_TRY(this, cudaMemcpyAsync(a.ang, a.st_ang, n * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+      CUDA_TRY(this, cudaMemcpyAsync(a.force, a.st_force, n * sizeof(double2), cudaMemcpyDeviceToDevice, stream));
+      CUDA_TRY(this, cudaMemcpyAsync(a.idflag, a.st_id, n * sizeof(unsigned int), cudaMemcpyDeviceToDevice, stream));
+      return MAVI_OK;
+    }
+    CUDA_TRY(this, cudaMemsetAsync(a.count, 0, ((size_t)p.num_cells + 2) * sizeof(int), stream));
+    CUDA_TRY(this, cudaMemsetAsync(a.flags + 1, 0, (FLAG_COUNT - 1) * sizeof(int), stream));
+    CUDA_TRY(this, cudaMemsetAsync(a.tile_dirty, 0, ((size_t)p.nt + 1) * sizeof(int), stream));
+    CUDA_TRY(this, cudaMemsetAsync(a.inbox_cnt, 0, ((size_t)p.nt + 1) * sizeof(int), stream));
+    launch_build_tiles(ctx(), p, a, second_is_vel);
+    int st = check_device_flags();
+    if (st) return st;
+    if (!flags_host[FLAG_OVERFLOW]) return MAVI_OK;
+    cap = round_up16(flags_host[FLAG_MAXCOUNT] * 1.25 + 8.0);
+    if ((st = alloc_state(n_active, cap))) return st;
+  }
+  set_error("tile capacity did not converge");
+  return MAVI_ERR_CAPACITY;
+}
+
+// update_chunks! of the current device state (mavi_bin, overflow fallback)
+int Handle::rebuild_from_current() {
+  launch_compact_to_staging(ctx(), p, a, second_kind == SECOND_VEL);
+  return rebuild_from_staging(p.num_cells > 0 ? p.n_active : p.n_count);
+}
+
+// A particle left the chunk grid during the previous step: the reference notices at its next update_chunks!
+// (BoundsError, src/chunks.jl:144-146), i.e. when the next step / calc_forces! / update_chunks! is requested.
+int Handle::pending_out_of_grid() {
+  if (flags_host && (flags_host[FLAG_ERR] & ERRBIT_OOG_PENDING)) {
+    set_error("a particle left the chunk grid (BoundsError in the reference, src/chunks.jl:144-146)");
+    return MAVI_ERR_OUT_OF_GRID;
+  }
   return MAVI_OK;
 }
 
 // Reads the device error word; called at every synchronisation point.
 int Handle::check_device_flags() {
   int *f = flags_host;
-  cudaError_t e = cudaMemcpyAsync(f, a.flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream);
+  cudaError_t e = cudaMemcpyAsync(f, a.flags, FLAG_COUNT * sizeof(int), cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   if (e != cudaSuccess) {
     set_error("CUDA error %s while reading the device error word", cudaGetErrorString(e));
     return MAVI_ERR_CUDA;
   }
-  if (f[0] & 4) {
+  if (f[0] & ERRBIT_OUTSIDE_SPACE) {
     set_error("Particles outside space (check_inside, src/space_checks.jl)");
     return MAVI_ERR_OUTSIDE_SPACE;
   }
@@ -269,59 +401,44 @@ int Handle::check_device_flags() {
   return MAVI_OK;
 }
 
-// update_chunks!: cell ids, histogram, scan, stable scatter, physical re-order of the state arrays.
-int Handle::bin_and_sort(bool with_forces) {
-  if (p.num_cells == 0) return MAVI_OK;  // update_chunks!(::Nothing)
-  LaunchCtx c = ctx();
-  const size_t nc = (size_t)p.num_cells + 2;
-  CUDA_TRY(this, cudaMemsetAsync(a.count, 0, nc * sizeof(int), stream));
-  CUDA_TRY(this, cudaMemsetAsync(a.flags + 1, 0, 3 * sizeof(int), stream));
-  launch_cell_index(c, p, a.pos[0], a.idflag[0], a.cell[0], a.cell_new, a.count, a.flags);
-  launch_exclusive_scan(c, a.count, a.start, a.scan_partials, (int)nc);
-  launch_scatter(c, p, a.cell_new, a.start, a.count, a.perm);
-  launch_gather(c, p, a.perm, a.cell_new, a.start, a, 0, 1, second_kind == SECOND_VEL, second_kind != SECOND_RING_POL,
-                with_forces);
-  std::swap(a.pos[0], a.pos[1]);
-  std::swap(a.idflag[0], a.idflag[1]);
-  std::swap(a.cell[0], a.cell[1]);
-  if (second_kind == SECOND_VEL) std::swap(a.vel[0], a.vel[1]);
-  else if (second_kind == SECOND_ANGLE) std::swap(a.ang[0], a.ang[1]);
-  if (with_forces) std::swap(a.force, a.force_old);
-  cells_valid = true;
-  need_sort = false;
-  CUDA_TRY(this, cudaGetLastError());
-  return MAVI_OK;
-}
-
 int Handle::step_once(const double *noise_dev) {
   int st;
   LaunchCtx c = ctx();
   if (p.dynamics == MAVI_DYN_RINGS) return rings_step(this, noise_dev);
+  if (int st0 = pending_out_of_grid()) return st0;
+  const bool second_is_vel = second_kind == SECOND_VEL;
   if (prof) cudaEventRecord(ev[0], stream);
-  // update_chunks!: the previous step proved (exactly, still_in_cell) whether any particle would be binned into another
-  // cell; if none would, the sorted order and cell_start ARE the fresh binning and the counting sort is skipped.
-  if (need_sort || (flags_cfg & MAVI_FLAG_RESORT_EVERY_STEP)) {
-    if ((st = bin_and_sort(false))) return st;
+  if ((flags_cfg & MAVI_FLAG_RESORT_EVERY_STEP) && p.num_cells > 0) {
+    if ((st = rebuild_from_current())) return st;  // A/B switch: global rebuild instead of the incremental repair
   }
-  CUDA_TRY(this, cudaMemsetAsync(a.flags + 1, 0, 3 * sizeof(int), stream));
+  // per-step control words: #dirty tiles, big-drift guard, #position fix-ups, #inter-tile movers
+  CUDA_TRY(this, cudaMemsetAsync(a.flags + 1, 0, 4 * sizeof(int), stream));
   if (prof) cudaEventRecord(ev[1], stream);
-  if (p.dynamics == MAVI_DYN_LJ || p.dynamics == MAVI_DYN_HARMTRUNC) {
-    launch_newton_a(c, p, a, 0);  // pos[0] -> pos[1] (drift), F1 -> force_old
+  if (second_is_vel) {
+    launch_newton_a(c, p, a);  // pos[0] -> pos[1] (drift), F1 -> force_old
     if (prof) cudaEventRecord(ev[2], stream);
-    launch_newton_b(c, p, a, 0);  // F2 from pos[1]; vel, force; sparse wall fix-ups applied to pos[1]
-    std::swap(a.pos[0], a.pos[1]);
-    if (prof) cudaEventRecord(ev[3], stream);
+    launch_newton_b(c, p, a);  // F2 from pos[1]; vel, force; sparse wall fix-ups applied to pos[1]
   } else {
     if (prof) cudaEventRecord(ev[2], stream);
-    launch_self_propelled(c, p, a, 0, noise_dev, (unsigned long long)num_steps);
-    std::swap(a.pos[0], a.pos[1]);
-    if (prof) cudaEventRecord(ev[3], stream);
+    launch_self_propelled(c, p, a, noise_dev, (unsigned long long)num_steps);
   }
+  std::swap(a.pos[0], a.pos[1]);
+  if (prof) cudaEventRecord(ev[3], stream);
+  // update_chunks! for the NEXT step, incrementally: only tiles a particle left or entered are rewritten
+  if (!(flags_cfg & MAVI_FLAG_RESORT_EVERY_STEP)) launch_repair_tiles(c, p, a, second_is_vel);
+  if (prof) cudaEventRecord(ev[4], stream);
   time += p.dt;  // update_time!, src/integration.jl:500-503
   num_steps += 1;
-  // one 16-byte read-back per step: error word + "somebody changed cell" -> decides the next step's re-sort
+  // one small read-back per step: error word + tile overflow
   if ((st = check_device_flags())) return st;
-  need_sort = p.num_cells > 0 && flags_host[1] > 0;
+  if (flags_host[FLAG_OVERFLOW]) {
+    // a tile or inbox ran out of slots: nothing was modified by the repair; rebuild with a larger capacity
+    int cap = round_up16((flags_host[FLAG_MAXCOUNT] > p.cap ? flags_host[FLAG_MAXCOUNT] : p.cap) * 1.25 + 8.0);
+    launch_compact_to_staging(c, p, a, second_is_vel);
+    const int n_active = p.n_active;
+    if ((st = alloc_state(n_active, cap))) return st;
+    if ((st = rebuild_from_staging(n_active))) return st;
+  }
   return MAVI_OK;
 }
 
@@ -357,7 +474,7 @@ int32_t mavi_create(const MaviParams *params, MaviHandle **out) {
   int st = validate_and_lower(h, params);
   if (st) return st;
   if ((st = allocate(h))) return st;
-  for (int i = 0; i < 4; i++) cudaEventCreate(&h->ev[i]);
+  for (int i = 0; i < 5; i++) cudaEventCreate(&h->ev[i]);
   cudaEventCreate(&h->ev_call[0]);
   cudaEventCreate(&h->ev_call[1]);
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -369,10 +486,11 @@ int32_t mavi_destroy(MaviHandle *hh) {
   if (!h) return MAVI_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  for (void *ptr : h->allocs) cudaFree(ptr);
+  for (void *ptr : h->allocs)
+    if (ptr) cudaFree(ptr);
   if (h->flags_host) cudaFreeHost(h->flags_host);
   if (h->noise_dev) cudaFree(h->noise_dev);
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < 5; i++)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (int i = 0; i < 2; i++)
     if (h->ev_call[i]) cudaEventDestroy(h->ev_call[i]);
@@ -395,34 +513,32 @@ int32_t mavi_upload_state(MaviHandle *hh, const void *pos, const void *second, c
   DevArrays &a = h->a;
   LaunchCtx c = h->ctx();
   const size_t sn = (size_t)n;
-  CUDA_TRY(h, cudaMemcpyAsync(a.pos[0], pos, sn * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(a.st_pos, pos, sn * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
   if (second) {
     if (h->second_kind == SECOND_VEL)
-      CUDA_TRY(h, cudaMemcpyAsync(a.vel[0], second, sn * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(a.st_vel, second, sn * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
     else if (h->second_kind == SECOND_ANGLE)
-      CUDA_TRY(h, cudaMemcpyAsync(a.ang[0], second, sn * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(a.st_ang, second, sn * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     else
-      CUDA_TRY(h, cudaMemcpyAsync(a.ang[0], second, (size_t)h->p.rings.num_rings * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(a.st_ang, second, (size_t)h->p.rings.num_rings * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   }
-  CUDA_TRY(h, cudaMemsetAsync(a.flags, 0, 8 * sizeof(int), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(a.flags, 0, FLAG_COUNT * sizeof(int), h->stream));
   if (h->second_kind == SECOND_RING_POL) return rings_upload_finish(h);
   unsigned char *mask_dev = nullptr;
-  h->p.n_count = h->p.n;
+  int n_active = h->p.n;
   if (active_mask) {
     // ParticleIds (src/states.jl:27-52): count = number of active ids
-    mask_dev = reinterpret_cast<unsigned char *>(a.perm);
+    mask_dev = reinterpret_cast<unsigned char *>(a.st_cell);
     CUDA_TRY(h, cudaMemcpyAsync(mask_dev, active_mask, sn, cudaMemcpyHostToDevice, h->stream));
-    int cnt = 0;
-    for (size_t i = 0; i < sn; i++) cnt += active_mask[i] != 0;
-    h->p.n_count = cnt;
+    n_active = 0;
+    for (size_t i = 0; i < sn; i++) n_active += active_mask[i] != 0;
   }
-  launch_init_ids(c, h->p.n, mask_dev, a.idflag[0], a.cell[0], h->p.num_cells);
-  if (h->p.n_spaces == 1) launch_check_inside(c, h->p, a.pos[0], a.idflag[0], a.flags);
-  CUDA_TRY(h, cudaMemsetAsync(a.force, 0, sn * sizeof(double2), h->stream));
-  h->cells_valid = false;
+  launch_init_staging_ids(c, h->p.n, mask_dev, a.st_id);
+  CUDA_TRY(h, cudaMemsetAsync(a.st_force, 0, sn * sizeof(double2), h->stream));
+  if (h->p.n_spaces == 1) launch_check_inside(c, h->p, a);
   int st = h->check_device_flags();
   if (st) return st;
-  if ((st = h->bin_and_sort(false))) return st;
+  if ((st = h->rebuild_from_staging(n_active))) return st;
   return h->check_device_flags();
 }
 
@@ -433,19 +549,18 @@ int32_t mavi_download_state(MaviHandle *hh, void *pos, void *second) {
   DevArrays &a = h->a;
   LaunchCtx c = h->ctx();
   const size_t sn = (size_t)h->p.n;
+  if (h->second_kind == SECOND_RING_POL) return rings_download_state(h, pos, second);
   if (pos) {
-    launch_unpermute2(c, h->p.n, a.idflag[0], a.pos[0], a.pos[1]);
-    CUDA_TRY(h, cudaMemcpyAsync(pos, a.pos[1], sn * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+    launch_unpermute2(c, h->p, a, a.pos[0], a.st_pos);
+    CUDA_TRY(h, cudaMemcpyAsync(pos, a.st_pos, sn * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
   }
   if (second) {
     if (h->second_kind == SECOND_VEL) {
-      launch_unpermute2(c, h->p.n, a.idflag[0], a.vel[0], a.vel[1]);
-      CUDA_TRY(h, cudaMemcpyAsync(second, a.vel[1], sn * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
-    } else if (h->second_kind == SECOND_ANGLE) {
-      launch_unpermute1(c, h->p.n, a.idflag[0], a.ang[0], a.ang[1]);
-      CUDA_TRY(h, cudaMemcpyAsync(second, a.ang[1], sn * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      launch_unpermute2(c, h->p, a, a.vel, a.st_vel);
+      CUDA_TRY(h, cudaMemcpyAsync(second, a.st_vel, sn * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
     } else {
-      CUDA_TRY(h, cudaMemcpyAsync(second, a.ang[0], (size_t)h->p.rings.num_rings * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      launch_unpermute1(c, h->p, a, a.ang, a.st_ang);
+      CUDA_TRY(h, cudaMemcpyAsync(second, a.st_ang, sn * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     }
   }
   return h->check_device_flags();
@@ -456,8 +571,9 @@ int32_t mavi_download_forces(MaviHandle *hh, void *forces) {
   if (!h || !forces) return MAVI_ERR_BAD_PARAMS;
   cudaSetDevice(h->device);
   DevArrays &a = h->a;
-  launch_unpermute2(h->ctx(), h->p.n, a.idflag[0], a.force, a.force_old);
-  CUDA_TRY(h, cudaMemcpyAsync(forces, a.force_old, (size_t)h->p.n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  if (h->second_kind == SECOND_RING_POL) return rings_download_forces(h, forces);
+  launch_unpermute2(h->ctx(), h->p, a, a.force, a.st_force);
+  CUDA_TRY(h, cudaMemcpyAsync(forces, a.st_force, (size_t)h->p.n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
   return h->check_device_flags();
 }
 
@@ -519,9 +635,9 @@ int32_t mavi_calc_forces(MaviHandle *hh) {
   if (!h) return MAVI_ERR_BAD_PARAMS;
   cudaSetDevice(h->device);
   if (h->p.dynamics == MAVI_DYN_RINGS) return rings_calc_forces(h);
-  int st = h->bin_and_sort(false);
-  if (st) return st;
-  launch_force_only(h->ctx(), h->p, h->a, 0, true);
+  if (int st0 = h->pending_out_of_grid()) return st0;
+  // the tile layout always equals the fresh binning of the current positions (repaired at the end of every step)
+  launch_force_only(h->ctx(), h->p, h->a, true);
   return h->check_device_flags();
 }
 
@@ -529,7 +645,10 @@ int32_t mavi_bin(MaviHandle *hh) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h) return MAVI_ERR_BAD_PARAMS;
   cudaSetDevice(h->device);
-  int st = h->bin_and_sort(true);
+  if (h->p.dynamics == MAVI_DYN_RINGS) return rings_bin(h);
+  if (h->p.num_cells == 0) return MAVI_OK;  // update_chunks!(::Nothing)
+  if (int st0 = h->pending_out_of_grid()) return st0;
+  int st = h->rebuild_from_current();
   if (st) return st;
   return h->check_device_flags();
 }
@@ -539,15 +658,14 @@ int32_t mavi_download_cells(MaviHandle *hh, int32_t *cell_of_particle, int32_t *
   if (!h || h->p.num_cells == 0) return MAVI_ERR_BAD_PARAMS;
   cudaSetDevice(h->device);
   DevArrays &a = h->a;
+  if (h->p.dynamics == MAVI_DYN_RINGS) return rings_download_cells(h, cell_of_particle, counts, nullptr, nullptr);
   if (cell_of_particle) {
-    launch_unpermute_cells(h->ctx(), h->p.n, h->p.num_cells, a.idflag[0], a.cell[0], a.perm);
-    CUDA_TRY(h, cudaMemcpyAsync(cell_of_particle, a.perm, (size_t)h->p.n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    launch_unpermute_cells(h->ctx(), h->p, a, a.st_cell);
+    CUDA_TRY(h, cudaMemcpyAsync(cell_of_particle, a.st_cell, (size_t)h->p.n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   }
   if (counts) {
-    std::vector<int> start((size_t)h->p.num_cells + 1);
-    CUDA_TRY(h, cudaMemcpyAsync(start.data(), a.start, start.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    for (int c = 0; c < h->p.num_cells; c++) counts[c] = start[c + 1] - start[c];
+    launch_cell_counts(h->ctx(), h->p, a, a.perm);
+    CUDA_TRY(h, cudaMemcpyAsync(counts, a.perm, (size_t)h->p.num_cells * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   }
   return h->check_device_flags();
 }
@@ -557,13 +675,22 @@ int32_t mavi_download_cell_lists(MaviHandle *hh, int32_t *start, int32_t *ids) {
   if (!h || h->p.num_cells == 0) return MAVI_ERR_BAD_PARAMS;
   cudaSetDevice(h->device);
   DevArrays &a = h->a;
-  std::vector<int> st((size_t)h->p.num_cells + 1);
-  CUDA_TRY(h, cudaMemcpyAsync(st.data(), a.start, st.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  if (start) memcpy(start, st.data(), st.size() * sizeof(int));
+  if (h->p.dynamics == MAVI_DYN_RINGS) return rings_download_cells(h, nullptr, nullptr, start, ids);
+  if (start) {
+    std::vector<int> counts((size_t)h->p.num_cells);
+    launch_cell_counts(h->ctx(), h->p, a, a.perm);
+    CUDA_TRY(h, cudaMemcpyAsync(counts.data(), a.perm, counts.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    int acc = 0;
+    for (int cix = 0; cix < h->p.num_cells; cix++) {
+      start[cix] = acc;
+      acc += counts[cix];
+    }
+    start[h->p.num_cells] = acc;
+  }
   if (ids) {
-    launch_ids(h->ctx(), h->p.n, a.idflag[0], a.perm);
-    CUDA_TRY(h, cudaMemcpyAsync(ids, a.perm, (size_t)st.back() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    launch_ids_in_cell_order(h->ctx(), h->p, a, a.st_cell);
+    CUDA_TRY(h, cudaMemcpyAsync(ids, a.st_cell, (size_t)h->p.n_active * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   }
   return h->check_device_flags();
 }
@@ -602,7 +729,7 @@ int32_t mavi_energies(MaviHandle *hh, int32_t pe_mode, double *ke, double *pe) {
   double *out = a.reduce_buf + 2048;
   double host[2] = {NAN, NAN};
   if (ke && h->second_kind == SECOND_VEL) {
-    launch_kinetic_energy(c, h->p, a.vel[0], a.reduce_buf, out);
+    launch_kinetic_energy(c, h->p, a, out);
     CUDA_TRY(h, cudaMemcpyAsync(&host[0], out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   }
   if (pe && h->p.dynamics == MAVI_DYN_LJ) {
@@ -610,7 +737,8 @@ int32_t mavi_energies(MaviHandle *hh, int32_t pe_mode, double *ke, double *pe) {
       h->set_error("pe_mode 1 needs chunks");
       return MAVI_ERR_BAD_PARAMS;
     }
-    launch_potential_energy(c, h->p, a, 0, pe_mode, out + 1);
+    if (pe_mode == 0) launch_compact_to_staging(c, h->p, a, true);
+    launch_potential_energy(c, h->p, a, pe_mode, out + 1);
     CUDA_TRY(h, cudaMemcpyAsync(&host[1], out + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   }
   int st = h->check_device_flags();
@@ -673,6 +801,7 @@ int32_t mavi_last_step_ms(MaviHandle *hh, float *ms5) {
   cudaEventElapsedTime(&ms5[0], h->ev[0], h->ev[1]);
   cudaEventElapsedTime(&ms5[1], h->ev[1], h->ev[2]);
   cudaEventElapsedTime(&ms5[2], h->ev[2], h->ev[3]);
+  cudaEventElapsedTime(&ms5[3], h->ev[3], h->ev[4]);
   cudaEventElapsedTime(&ms5[4], h->ev_call[0], h->ev_call[1]);
   cudaGetLastError();
   return MAVI_OK;

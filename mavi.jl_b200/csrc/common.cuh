@@ -41,6 +41,18 @@ struct DevParams {
   int n_count;         // get_num_total_particles(state): number of active ids
   int num_cols, num_rows, num_cells;
   int wrap_cols, wrap_rows;  // stencil index wrap (periodic main wall)
+  // Padded tile layout: a tile = MAVI_TR consecutive cell rows of ONE cell column with `cap` particle slots; tile t owns
+  // slots [t*cap, (t+1)*cap), particles sorted by (cell, id) in its prefix.  Inactive slots live in a tail region.
+  int tpc;        // tiles per column = ceil(num_rows / MAVI_TR)
+  int nt;         // number of tiles = num_cols * tpc
+  int cap;        // slots per tile
+  int n_active;   // particles living in tiles; ranks >= n_active are the inactive tail
+  int tail_base;  // first slot of the inactive tail = nt * cap
+  int inbox_cap;  // per-tile capacity for particles arriving from other tiles in one step
+  int mv_cap;     // capacity of the per-step inter-tile mover list
+  unsigned int rows_mul, rows_shr;  // magic number division by num_rows
+  unsigned int tpc_mul, tpc_shr;    // ... by tpc
+  unsigned int cols_mul, cols_shr;  // ... by num_cols
   int periodic;              // calc_diff applies the minimum image (src/integration.jl:43-48)
   double grid_bl[2], grid_h, cl, ch;
   double size[2], half[2];   // main rectangle size and size/2
@@ -65,7 +77,37 @@ struct DevParams {
   DevRings rings;
 };
 
-enum { ERRBIT_OUT_OF_GRID = 1, ERRBIT_NAN = 2 };
+enum { ERRBIT_OUT_OF_GRID = 1, ERRBIT_NAN = 2, ERRBIT_OUTSIDE_SPACE = 4, ERRBIT_OOG_PENDING = 8 };
+
+// flags[] layout (device control word, mirrored to pinned host memory once per step)
+enum { FLAG_ERR = 0, FLAG_CHANGED = 1, FLAG_BIGMOVE = 2, FLAG_NFIX = 3, FLAG_NMV = 4, FLAG_OVERFLOW = 5, FLAG_MAXCOUNT = 6, FLAG_COUNT = 8 };
+
+#define MAVI_TR 32  // cell rows per tile
+
+// index of (tile, local row) in tstart[]: tstart[tile*(MAVI_TR+1) + lr] = first slot of that cell's particles,
+// entry MAVI_TR = end of the tile's particles.
+// x / d for 0 <= x < 2^31 with a host-computed (mul, shr) pair: q = umulhi(x, mul) >> shr  (Granlund-Montgomery)
+__device__ __forceinline__ int fastdiv(int x, unsigned int mul, unsigned int shr) {
+  return mul ? (int)(__umulhi((unsigned int)x, mul) >> shr) : x;  // mul == 0 encodes d == 1
+}
+__device__ __forceinline__ int div_rows(const DevParams &p, int x) { return fastdiv(x, p.rows_mul, p.rows_shr); }
+__device__ __forceinline__ int div_tpc(const DevParams &p, int x) { return fastdiv(x, p.tpc_mul, p.tpc_shr); }
+__device__ __forceinline__ int div_cols(const DevParams &p, int x) { return fastdiv(x, p.cols_mul, p.cols_shr); }
+
+__device__ __forceinline__ int tile_of_cell(const DevParams &p, int cell) {
+  const int col = div_rows(p, cell), row = cell - col * p.num_rows;
+  return col * p.tpc + row / MAVI_TR;
+}
+// Kernels enumerate tiles TILE-ROW-MAJOR (order index o = tile_row * num_cols + col): 256 consecutive ranks are then a
+// block of ~6 adjacent columns x 32 rows whose neighbours are mostly the block's own particles (L1 hits).
+__device__ __forceinline__ int tile_of_order(const DevParams &p, int o) {
+  const int tr = div_cols(p, o), col = o - tr * p.num_cols;
+  return col * p.tpc + tr;
+}
+__device__ __forceinline__ int tq_of(const DevParams &p, int col, int row) {
+  const int tr = row / MAVI_TR;
+  return (col * p.tpc + tr) * (MAVI_TR + 1) + (row - tr * MAVI_TR);
+}
 
 #define MAVI_INACTIVE_BIT 0x80000000u
 
@@ -105,7 +147,7 @@ __device__ __forceinline__ bool axis_in_cell(double t, int k, int n, double c) {
   return lo && hi;
 }
 __device__ __forceinline__ bool still_in_cell(const DevParams &p, double x, double y, int cell) {
-  const int col = cell / p.num_rows, row = cell - col * p.num_rows;
+  const int col = div_rows(p, cell), row = cell - col * p.num_rows;
   return axis_in_cell(-y + p.grid_bl[1] + p.grid_h, row, p.num_rows, p.ch) &&
          axis_in_cell(x - p.grid_bl[0], col, p.num_cols, p.cl);
 }
@@ -182,11 +224,11 @@ __device__ __forceinline__ double pair_coef<MAVI_DYN_RTP>(const DevParams &p, do
 // (src/chunks.jl:61-118, src/integration.jl:116-156) and scatters +f/-f.  As a gather, particle i sees every
 // particle of its own cell and of the half stencil UNITED WITH ITS MIRROR IMAGE = the 8 surrounding cells
 // (wrapped when the main wall is periodic, clipped otherwise).  Visiting wrapped rows/columns individually keeps
-// the reference's double counting on 2-row / 2-column periodic grids.  Cells of one column are contiguous in the
-// sorted order (row fastest), so the walk is at most 3 contiguous runs of `start`.
+// the reference's double counting on 2-row / 2-column periodic grids.  This generic walker visits the 9 cells one by
+// one through tstart[]; interior cells away from tile edges use the flat 3-run fast path in kernels.cu instead.
 //   f(j) is called for every neighbour slot j != self.
 template <typename F>
-__device__ __forceinline__ void for_each_neighbor(const DevParams &p, const int *__restrict__ start, int cell, int self,
+__device__ __forceinline__ void for_each_neighbor(const DevParams &p, const int *__restrict__ tstart, int cell, int self,
                                                   F &&f) {
   const int R = p.num_rows, Cn = p.num_cols;
   const int col = cell / R, row = cell - col * R;
@@ -200,26 +242,20 @@ __device__ __forceinline__ void for_each_neighbor(const DevParams &p, const int 
       if (!p.wrap_cols) continue;
       c2 = 0;
     }
-    const int base = c2 * R;
-    if (row > 0 && row < R - 1) {
-      int jb = __ldg(start + base + row - 1), je = __ldg(start + base + row + 2);
+#pragma unroll 1
+    for (int dr = -1; dr <= 1; dr++) {
+      int r2 = row + dr;
+      if (r2 < 0) {
+        if (!p.wrap_rows) continue;
+        r2 = R - 1;
+      } else if (r2 >= R) {
+        if (!p.wrap_rows) continue;
+        r2 = 0;
+      }
+      const int q = tq_of(p, c2, r2);
+      int jb = __ldg(tstart + q), je = __ldg(tstart + q + 1);
       for (int j = jb; j < je; j++)
         if (j != self) f(j);
-    } else {
-#pragma unroll 1
-      for (int dr = -1; dr <= 1; dr++) {
-        int r2 = row + dr;
-        if (r2 < 0) {
-          if (!p.wrap_rows) continue;
-          r2 = R - 1;
-        } else if (r2 >= R) {
-          if (!p.wrap_rows) continue;
-          r2 = 0;
-        }
-        int jb = __ldg(start + base + r2), je = __ldg(start + base + r2 + 1);
-        for (int j = jb; j < je; j++)
-          if (j != self) f(j);
-      }
     }
   }
 }

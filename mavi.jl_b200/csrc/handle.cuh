@@ -26,14 +26,13 @@ struct Handle {
   int flags_cfg = 0;
   cudaStream_t stream = nullptr;
   SecondKind second_kind = SECOND_VEL;
-  bool cells_valid = false;
-  bool need_sort = true;   // the sorted order is not known to equal the fresh binning
+  size_t ns = 0;  // number of particle slots (tiles * cap + inactive tail)
   int *flags_host = nullptr;  // pinned mirror of a.flags[0..3]
   bool prof = false;
   long long launches = 0;
   long long num_steps = 0;
   double time = 0.0;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_call[2] = {nullptr, nullptr};
   std::vector<void *> allocs;
   double *noise_dev = nullptr;
@@ -43,7 +42,10 @@ struct Handle {
   LaunchCtx ctx() { return LaunchCtx{stream, &launches}; }
   void set_error(const char *fmt, ...);
   int check_device_flags();
-  int bin_and_sort(bool with_forces);
+  int pending_out_of_grid();
+  int alloc_state(int n_active, int cap);
+  int rebuild_from_staging(int n_active);
+  int rebuild_from_current();
   int step_once(const double *noise_dev);
 };
 
@@ -54,5 +56,9 @@ int rings_upload_finish(Handle *h);
 int rings_step(Handle *h, const double *noise_dev);
 int rings_calc_forces(Handle *h);
 int rings_download_info(Handle *h, void *areas, void *cms, void *cont_pos);
+int rings_download_state(Handle *h, void *pos, void *second);
+int rings_download_forces(Handle *h, void *forces);
+int rings_bin(Handle *h);
+int rings_download_cells(Handle *h, int *cell_of_particle, int *counts, int *start, int *ids);
 
 }  // namespace mavi

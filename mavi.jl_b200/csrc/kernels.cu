@@ -1,55 +1,195 @@
-// kernels.cu — cell binning (counting sort + prefix scan + stable physical re-order), fused force+integrate
-// passes, energy reductions.  sm_100a.  No tensor cores: the path is FP64 vector math over HBM-resident SoA arrays
-// (double2 loads), not a dense contraction.  Reference citations are relative to /root/reference/.
+// kernels.cu — padded-tile cell lists (full build + O(#movers) incremental repair), fused force+integrate passes and
+// energy reductions.  sm_100a.  No tensor cores: the path is FP64 vector math over HBM-resident SoA arrays (double2
+// loads), not a dense contraction.  Reference citations are relative to /root/reference/.
 #include "kernels.cuh"
 #include "walls.cuh"
 
 namespace mavi {
 
-constexpr int TPB = 256;
 static inline int nblk(long long n, int tpb = TPB) { return (int)((n + tpb - 1) / tpb); }
 
-#define MAVI_LAUNCH(ctx, kernel, grid, block, ...)              \
-  do {                                                          \
-    kernel<<<(grid), (block), 0, (ctx).stream>>>(__VA_ARGS__);  \
-    (*(ctx).launches)++;                                        \
+#define MAVI_LAUNCH(ctx, kernel, grid, block, smem, ...)             \
+  do {                                                               \
+    kernel<<<(grid), (block), (smem), (ctx).stream>>>(__VA_ARGS__);  \
+    (*(ctx).launches)++;                                             \
   } while (0)
 
-enum { ERRBIT_OUTSIDE_SPACE = 4 };
-
-// =========================================================================================================
-// Binning: update_chunks! (src/chunks.jl:150-163, src/integration.jl:54-59) as a counting sort.
-// =========================================================================================================
-
-// cell id per slot + histogram; also counts how many particles left the cell they are currently sorted under.
-__global__ void k_cell_index(const __grid_constant__ DevParams p, const double2 *__restrict__ pos,
-                             const unsigned int *__restrict__ idflag, const int *__restrict__ cell_old,
-                             int *__restrict__ cell_new, int *__restrict__ count, int *__restrict__ flags) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  bool changed = false;
-  if (k < p.n) {
-    int c;
-    if (idflag[k] & MAVI_INACTIVE_BIT) {
-      c = p.num_cells;  // pseudo-cell of inactive slots (never binned by the reference: active ids only)
-    } else {
-      double2 r = pos[k];
-      c = cell_of_point(p, r.x, r.y);
-      if (c < 0) {  // BoundsError in the reference (src/chunks.jl:144-146)
-        atomicOr(&flags[0], ERRBIT_OUT_OF_GRID);
-        c = 0;
-      }
-    }
-    cell_new[k] = c;
-    atomicAdd(&count[c], 1);
-    changed = (c != cell_old[k]);
-  }
-  unsigned int m = __ballot_sync(0xffffffffu, changed);
-  if (m && (threadIdx.x & 31) == 0) atomicAdd(&flags[1], __popc(m));
+// rank (dense particle index) -> slot.  Ranks < n_active enumerate the tile populations in TILE-ROW-MAJOR order
+// (tile_prefix is the exclusive scan in that order); cta_first[b] is the order index of the tile holding rank b*TPB.
+// Ranks >= n_active are the inactive tail.  The CTA-level version stages the ~8 prefix entries a block needs in shared
+// memory so that threads do not chase dependent global loads.
+__device__ __forceinline__ int slot_of_rank(const DevParams &p, const int *__restrict__ tile_prefix,
+                                            const int *__restrict__ cta_first, int rank) {
+  if (rank >= p.n_active) return p.tail_base + (rank - p.n_active);
+  int o = __ldg(cta_first + rank / TPB);
+  while (rank >= __ldg(tile_prefix + o + 1)) ++o;
+  return tile_of_order(p, o) * p.cap + (rank - __ldg(tile_prefix + o));
 }
 
-void launch_cell_index(const LaunchCtx &c, const DevParams &p, const double2 *pos, const unsigned int *idflag,
-                       const int *cell_old, int *cell_new, int *count, int *flags) {
-  MAVI_LAUNCH(c, k_cell_index, nblk(p.n), TPB, p, pos, idflag, cell_old, cell_new, count, flags);
+constexpr int RANK_WIN = 32;  // prefix entries staged per CTA (a block of 256 ranks rarely spans more tiles)
+__device__ __forceinline__ int slot_of_rank_cta(const DevParams &p, const int *__restrict__ tile_prefix,
+                                                const int *__restrict__ cta_first, int rank, int *s_win) {
+  // all threads of the block must call this (it synchronises); rank may be >= p.n
+  const int o0 = (blockIdx.x * TPB < p.n_active) ? __ldg(cta_first + blockIdx.x) : 0;
+  if (threadIdx.x <= RANK_WIN) {
+    const int o = o0 + threadIdx.x;
+    s_win[threadIdx.x] = (blockIdx.x * TPB < p.n_active && o <= p.nt) ? __ldg(tile_prefix + o) : 0x7fffffff;
+  }
+  __syncthreads();
+  if (rank >= p.n_active) return p.tail_base + (rank - p.n_active);
+  // number of window entries (beyond the first) that are <= rank = tile offset inside the window
+  int lo = 0;
+#pragma unroll
+  for (int step = RANK_WIN / 2; step >= 1; step >>= 1)
+    if (s_win[lo + step] <= rank) lo += step;
+  int o = o0 + lo;
+  if (lo == RANK_WIN - 1)  // window exhausted (very sparse tiles): finish with the global walk
+    while (rank >= __ldg(tile_prefix + o + 1)) ++o;
+  return tile_of_order(p, o) * p.cap + (rank - ((lo == RANK_WIN - 1) ? __ldg(tile_prefix + o) : s_win[lo]));
+}
+
+// =========================================================================================================
+// Full build: update_chunks! (src/chunks.jl:150-163, src/integration.jl:54-59) from the dense staging arrays.
+// =========================================================================================================
+
+// check_inside, src/space_checks.jl:9-61 (Rectangle: any coordinate < bottom_left or > top_right; Circle: |pos|^2 > R^2,
+// centre ignored (sic)); only single-geometry spaces are checked (ManyGeometries hits the generic no-op method).
+__global__ void k_check_inside(const __grid_constant__ DevParams p, const double2 *__restrict__ pos,
+                               const unsigned int *__restrict__ idflag, int *__restrict__ flags) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= p.n || (idflag[k] & MAVI_INACTIVE_BIT)) return;
+  const DevSpace &sp = p.spaces[0];
+  double2 r = pos[k];
+  bool out = false;
+  if (sp.geom == MAVI_GEOM_RECT) {
+    double trx = sp.rect_bl[0] + sp.rect_sz[0], try_ = sp.rect_bl[1] + sp.rect_sz[1];
+    out = (r.x < sp.rect_bl[0]) || (r.y < sp.rect_bl[1]) || (r.x > trx) || (r.y > try_);
+  } else if (sp.geom == MAVI_GEOM_CIRCLE) {
+    out = (r.x * r.x + r.y * r.y) > sp.cr * sp.cr;
+  }
+  if (out) atomicOr(&flags[FLAG_ERR], ERRBIT_OUTSIDE_SPACE);
+}
+
+void launch_check_inside(const LaunchCtx &c, const DevParams &p, const DevArrays &a) {
+  MAVI_LAUNCH(c, k_check_inside, nblk(p.n), TPB, 0, p, a.st_pos, a.st_id, a.flags);
+}
+
+__global__ void k_init_staging_ids(int n, const unsigned char *__restrict__ mask, unsigned int *__restrict__ st_id) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) st_id[k] = (unsigned int)k | ((mask && mask[k] == 0) ? MAVI_INACTIVE_BIT : 0u);
+}
+
+void launch_init_staging_ids(const LaunchCtx &c, int n, const unsigned char *mask, unsigned int *st_id) {
+  MAVI_LAUNCH(c, k_init_staging_ids, nblk(n), TPB, 0, n, mask, st_id);
+}
+
+// cell id of every staged particle (update_particle_chunk!, src/chunks.jl:120-147) + per-cell histogram
+__global__ void k_build_cell_index(const __grid_constant__ DevParams p, const double2 *__restrict__ st_pos,
+                                   const unsigned int *__restrict__ st_id, int *__restrict__ st_cell,
+                                   int *__restrict__ count, int *__restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  int c = -1;  // inactive: never binned (active ids only)
+  if (!(st_id[i] & MAVI_INACTIVE_BIT)) {
+    double2 r = st_pos[i];
+    c = cell_of_point(p, r.x, r.y);
+    if (c < 0) {  // BoundsError in the reference (src/chunks.jl:144-146)
+      atomicOr(&flags[FLAG_ERR], ERRBIT_OUT_OF_GRID);
+      c = 0;
+    }
+    atomicAdd(&count[c], 1);
+  }
+  st_cell[i] = c;
+}
+
+// per tile: exclusive scan of its cells' populations -> tstart; capacity check
+__global__ void k_build_layout(const __grid_constant__ DevParams p, const int *__restrict__ count,
+                               int *__restrict__ tstart, int *__restrict__ flags) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.nt) return;
+  const int col = t / p.tpc, tr = t - col * p.tpc;
+  const int base = t * p.cap;
+  int run = base;
+  int *ts = tstart + (size_t)t * (MAVI_TR + 1);
+  for (int lr = 0; lr < MAVI_TR; lr++) {
+    ts[lr] = run;
+    const int row = tr * MAVI_TR + lr;
+    if (row < p.num_rows) run += count[col * p.num_rows + row];
+  }
+  ts[MAVI_TR] = run;
+  const int cnt = run - base;
+  atomicMax(&flags[FLAG_MAXCOUNT], cnt);
+  if (cnt > p.cap) flags[FLAG_OVERFLOW] = 1;
+}
+
+// scatter staged particle indices into their cell range (cursor = count, consumed down to zero)
+__global__ void k_build_scatter(const __grid_constant__ DevParams p, const int *__restrict__ st_cell,
+                                const int *__restrict__ tstart, int *__restrict__ count, int *__restrict__ perm,
+                                const int *__restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n || flags[FLAG_OVERFLOW]) return;
+  int c = st_cell[i];
+  if (c < 0) return;
+  const int col = c / p.num_rows, row = c - col * p.num_rows;
+  int slot = tstart[tq_of(p, col, row)] + atomicSub(&count[c], 1) - 1;
+  perm[slot] = i;
+}
+
+// Stable placement: staged particle i goes to (start of its cell) + (rank of its original id inside the cell), i.e.
+// ascending ids per cell like the reference's fill loop (src/chunks.jl:153-155).  Makes the layout (and every force
+// summation order) independent of atomic scheduling -> bit-reproducible runs.  Inactive particles go to the tail.
+__global__ void k_build_place(const __grid_constant__ DevParams p, const int *__restrict__ st_cell,
+                              const int *__restrict__ tstart, const int *__restrict__ perm,
+                              const double2 *__restrict__ st_pos, const double2 *__restrict__ st_vel,
+                              const double *__restrict__ st_ang, const double2 *__restrict__ st_force,
+                              const unsigned int *__restrict__ st_id, double2 *__restrict__ pos,
+                              double2 *__restrict__ vel, double *__restrict__ ang, double2 *__restrict__ force,
+                              unsigned int *__restrict__ idflag, int *__restrict__ cell, int *__restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n || flags[FLAG_OVERFLOW]) return;
+  const int c = st_cell[i];
+  const unsigned int idf = st_id[i];
+  int d;
+  if (c < 0) {
+    d = p.tail_base + atomicAdd(&flags[7], 1);
+  } else {
+    const int col = c / p.num_rows, row = c - col * p.num_rows;
+    const int q = tq_of(p, col, row);
+    const int b = tstart[q], e = tstart[q + 1];
+    const unsigned int myid = idf & ~MAVI_INACTIVE_BIT;
+    int rank = 0;
+    for (int t = b; t < e; t++) {
+      const int o = perm[t];
+      if (o != i) rank += (st_id[o] & ~MAVI_INACTIVE_BIT) < myid;
+    }
+    d = b + rank;
+  }
+  pos[d] = st_pos[i];
+  if (vel) vel[d] = st_vel[i];
+  if (ang) ang[d] = st_ang[i];
+  force[d] = st_force[i];
+  idflag[d] = idf;
+  cell[d] = c;
+}
+
+// tile populations -> (scan) -> tile_prefix, then the first tile of every 256-rank block
+__global__ void k_tile_counts(const __grid_constant__ DevParams p, const int *__restrict__ tstart, int *__restrict__ out) {
+  int o = blockIdx.x * blockDim.x + threadIdx.x;  // tile-row-major order index
+  if (o > p.nt) return;
+  int cnt = 0;
+  if (o < p.nt) {
+    const int t = tile_of_order(p, o);
+    cnt = tstart[(size_t)t * (MAVI_TR + 1) + MAVI_TR] - t * p.cap;
+  }
+  out[o] = cnt;
+}
+
+__global__ void k_cta_first(const __grid_constant__ DevParams p, const int *__restrict__ tile_prefix,
+                            int *__restrict__ cta_first) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.nt) return;
+  const int lo = tile_prefix[t], hi = tile_prefix[t + 1];
+  for (int b = (lo + TPB - 1) / TPB; b * TPB < hi; b++) cta_first[b] = t;
 }
 
 // ---- exclusive prefix scan (reduce / top / final), 4096 items per block ------------------------------------
@@ -134,75 +274,211 @@ __global__ void k_scan_final(const int *__restrict__ in, int *__restrict__ out, 
 
 void launch_exclusive_scan(const LaunchCtx &c, const int *in, int *out, int *partials, int n) {
   int nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-  MAVI_LAUNCH(c, k_scan_reduce, nb, SCAN_TPB, in, partials, n);
-  MAVI_LAUNCH(c, k_scan_top, 1, SCAN_TPB, partials, nb);
-  MAVI_LAUNCH(c, k_scan_final, nb, SCAN_TPB, in, out, partials, n);
+  MAVI_LAUNCH(c, k_scan_reduce, nb, SCAN_TPB, 0, in, partials, n);
+  MAVI_LAUNCH(c, k_scan_top, 1, SCAN_TPB, 0, partials, nb);
+  MAVI_LAUNCH(c, k_scan_final, nb, SCAN_TPB, 0, in, out, partials, n);
 }
 
-// scatter slot ids into their cell range (cursor = count, consumed down to zero)
-__global__ void k_scatter(const __grid_constant__ DevParams p, const int *__restrict__ cell_new,
-                          const int *__restrict__ start, int *__restrict__ count, int *__restrict__ perm) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= p.n) return;
-  int c = cell_new[k];
-  int slot = start[c] + atomicSub(&count[c], 1) - 1;
-  perm[slot] = k;
+static void refresh_rank_maps(const LaunchCtx &c, const DevParams &p, const DevArrays &a) {
+  if (p.nt == 0) return;
+  int *tmp = a.perm;  // nt+1 ints of scratch
+  MAVI_LAUNCH(c, k_tile_counts, nblk(p.nt + 1), TPB, 0, p, a.tstart, tmp);
+  launch_exclusive_scan(c, tmp, a.tile_prefix, a.scan_partials, p.nt + 1);
+  MAVI_LAUNCH(c, k_cta_first, nblk(p.nt), TPB, 0, p, a.tile_prefix, a.cta_first);
 }
 
-void launch_scatter(const LaunchCtx &c, const DevParams &p, const int *cell_new, const int *start, int *count, int *perm) {
-  MAVI_LAUNCH(c, k_scatter, nblk(p.n), TPB, p, cell_new, start, count, perm);
+void launch_build_tiles(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel) {
+  // caller has zeroed count[], flags[FLAG_OVERFLOW], flags[FLAG_MAXCOUNT], flags[7]
+  MAVI_LAUNCH(c, k_build_cell_index, nblk(p.n), TPB, 0, p, a.st_pos, a.st_id, a.st_cell, a.count, a.flags);
+  MAVI_LAUNCH(c, k_build_layout, nblk(p.nt), TPB, 0, p, a.count, a.tstart, a.flags);
+  MAVI_LAUNCH(c, k_build_scatter, nblk(p.n), TPB, 0, p, a.st_cell, a.tstart, a.count, a.perm, a.flags);
+  MAVI_LAUNCH(c, k_build_place, nblk(p.n), TPB, 0, p, a.st_cell, a.tstart, a.perm, a.st_pos,
+              second_is_vel ? a.st_vel : nullptr, second_is_vel ? nullptr : a.st_ang, a.st_force, a.st_id, a.pos[0],
+              second_is_vel ? a.vel : nullptr, second_is_vel ? nullptr : a.ang, a.force, a.idflag, a.cell, a.flags);
+  refresh_rank_maps(c, p, a);
 }
 
-// Stable placement + physical re-order: the particle scattered to slot s goes to start[cell] + (rank of its original
-// id inside the cell), i.e. ascending ids per cell like the reference's fill loop (src/chunks.jl:153-155).  Makes the
-// layout (and every force summation order) independent of atomic scheduling -> bit-reproducible runs.
-__global__ void k_gather(const __grid_constant__ DevParams p, const int *__restrict__ perm,
-                         const int *__restrict__ cell_new, const int *__restrict__ start,
-                         const double2 *__restrict__ pos_s, double2 *__restrict__ pos_d,
-                         const double2 *__restrict__ vel_s, double2 *__restrict__ vel_d,
-                         const double *__restrict__ ang_s, double *__restrict__ ang_d,
-                         const unsigned int *__restrict__ id_s, unsigned int *__restrict__ id_d,
-                         int *__restrict__ cell_d, const double2 *__restrict__ f_s, double2 *__restrict__ f_d) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= p.n) return;
-  int src = perm[s];
-  int c = cell_new[src];
-  unsigned int idf = id_s[src];
-  int d = s;
-  if (c < p.num_cells) {
-    int b = start[c], e = start[c + 1];
-    unsigned int myid = idf & ~MAVI_INACTIVE_BIT;
-    int rank = 0;
-    for (int t = b; t < e; t++) {
-      if (t == s) continue;
-      unsigned int other = id_s[perm[t]] & ~MAVI_INACTIVE_BIT;
-      rank += other < myid;
-    }
-    d = b + rank;
+// dense copy of the current state into the staging arrays, in rank order
+__global__ void k_compact(const __grid_constant__ DevParams p, const int *__restrict__ tile_prefix,
+                          const int *__restrict__ cta_first, const double2 *__restrict__ pos,
+                          const double2 *__restrict__ vel, const double *__restrict__ ang,
+                          const double2 *__restrict__ force, const unsigned int *__restrict__ idflag,
+                          double2 *__restrict__ st_pos, double2 *__restrict__ st_vel, double *__restrict__ st_ang,
+                          double2 *__restrict__ st_force, unsigned int *__restrict__ st_id) {
+  int rank = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rank >= p.n) return;
+  const int k = slot_of_rank(p, tile_prefix, cta_first, rank);
+  st_pos[rank] = pos[k];
+  if (vel) st_vel[rank] = vel[k];
+  if (ang) st_ang[rank] = ang[k];
+  st_force[rank] = force[k];
+  st_id[rank] = idflag[k];
+}
+
+void launch_compact_to_staging(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel) {
+  MAVI_LAUNCH(c, k_compact, nblk(p.n), TPB, 0, p, a.tile_prefix, a.cta_first, a.pos[0], second_is_vel ? a.vel : nullptr,
+              second_is_vel ? nullptr : a.ang, a.force, a.idflag, a.st_pos, second_is_vel ? a.st_vel : nullptr,
+              second_is_vel ? nullptr : a.st_ang, a.st_force, a.st_id);
+}
+
+// =========================================================================================================
+// Incremental update_chunks!: the integrate kernels have already written the fresh cell of every particle that
+// left its cell (cell[k]), marked its tile dirty and queued inter-tile movers in the destination tile's inbox.
+// =========================================================================================================
+
+// copy the records of inter-tile movers aside so that source tiles can be rewritten independently
+__global__ void k_repair_collect(const int *__restrict__ flags, const int *__restrict__ mv_src,
+                                 const double2 *__restrict__ pos, const double2 *__restrict__ vel,
+                                 const double *__restrict__ ang, const double2 *__restrict__ force,
+                                 const unsigned int *__restrict__ idflag, const int *__restrict__ cell,
+                                 double2 *__restrict__ mv_pos, double2 *__restrict__ mv_second,
+                                 double2 *__restrict__ mv_force, unsigned int *__restrict__ mv_id,
+                                 int *__restrict__ mv_cell, int mv_cap) {
+  if (flags[FLAG_OVERFLOW]) return;
+  const int n = min(flags[FLAG_NMV], mv_cap);
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
+    const int k = mv_src[m];
+    mv_pos[m] = pos[k];
+    mv_second[m] = vel ? vel[k] : make_double2(ang[k], 0.0);
+    mv_force[m] = force[k];
+    mv_id[m] = idflag[k];
+    mv_cell[m] = cell[k];
   }
-  pos_d[d] = pos_s[src];
-  if (vel_s) vel_d[d] = vel_s[src];
-  if (ang_s) ang_d[d] = ang_s[src];
-  id_d[d] = idf;
-  cell_d[d] = c;
-  if (f_s) f_d[d] = f_s[src];
 }
 
-void launch_gather(const LaunchCtx &c, const DevParams &p, const int *perm, const int *cell_new, const int *start,
-                   const DevArrays &a, int src, int dst, bool second_is_vel, bool has_second, bool with_forces) {
-  MAVI_LAUNCH(c, k_gather, nblk(p.n), TPB, p, perm, cell_new, start, a.pos[src], a.pos[dst],
-              (has_second && second_is_vel) ? a.vel[src] : nullptr, (has_second && second_is_vel) ? a.vel[dst] : nullptr,
-              (has_second && !second_is_vel) ? a.ang[src] : nullptr, (has_second && !second_is_vel) ? a.ang[dst] : nullptr,
-              a.idflag[src], a.idflag[dst], a.cell[dst], with_forces ? a.force : nullptr,
-              with_forces ? a.force_old : nullptr);
+// One warp per dirty tile.  CHECK pass: population after the repair must fit (else FLAG_OVERFLOW -> the host rebuilds
+// with a larger capacity; nothing has been modified).  WRITE pass: stayers + arrivals are sorted by (cell, id) and
+// the tile and its tstart[] row are rewritten in place (all reads are staged in shared memory first).
+constexpr int REPAIR_WARPS = 4;
+struct RepairRec {
+  double2 pos, second, force;
+  unsigned long long key;  // (cell << 32) | id  -> ascending cells, ascending ids inside a cell
+  unsigned int idflag;
+  int cell;
+};
+
+template <bool WRITE>
+__global__ void __launch_bounds__(REPAIR_WARPS * 32) k_repair_tiles(
+    const __grid_constant__ DevParams p, int *__restrict__ flags, const int *__restrict__ dirty_list,
+    int *__restrict__ tile_dirty, int *__restrict__ inbox_cnt, const int *__restrict__ inbox, int *__restrict__ tstart,
+    double2 *__restrict__ pos, double2 *__restrict__ vel, double *__restrict__ ang, double2 *__restrict__ force,
+    unsigned int *__restrict__ idflag, int *__restrict__ cell, const double2 *__restrict__ mv_pos,
+    const double2 *__restrict__ mv_second, const double2 *__restrict__ mv_force, const unsigned int *__restrict__ mv_id,
+    const int *__restrict__ mv_cell) {
+  extern __shared__ unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  RepairRec *rec = reinterpret_cast<RepairRec *>(smem_raw) + (size_t)w * p.cap;
+  const int ndirty = flags[FLAG_CHANGED];
+  if (WRITE && flags[FLAG_OVERFLOW]) return;
+  for (int d = blockIdx.x * REPAIR_WARPS + w; d < ndirty; d += gridDim.x * REPAIR_WARPS) {
+    const int t = dirty_list[d];
+    const int base = t * p.cap;
+    int *ts = tstart + (size_t)t * (MAVI_TR + 1);
+    const int cnt_old = ts[MAVI_TR] - base;
+    const int nin = inbox_cnt[t];
+    // ---- gather: stayers of this tile ...
+    int m = 0;
+    for (int l0 = 0; l0 < cnt_old; l0 += 32) {
+      const int l = l0 + lane;
+      bool stay = false;
+      int c = 0;
+      if (l < cnt_old) {
+        c = cell[base + l];
+        stay = tile_of_cell(p, c) == t;
+      }
+      const unsigned int bal = __ballot_sync(0xffffffffu, stay);
+      if (WRITE && stay) {
+        const int e = m + __popc(bal & ((1u << lane) - 1));
+        RepairRec &r = rec[e];
+        const int k = base + l;
+        r.pos = pos[k];
+        r.second = vel ? vel[k] : make_double2(ang[k], 0.0);
+        r.force = force[k];
+        r.idflag = idflag[k];
+        r.cell = c;
+        r.key = ((unsigned long long)(unsigned int)c << 32) | (r.idflag & ~MAVI_INACTIVE_BIT);
+      }
+      m += __popc(bal);
+    }
+    const int total = m + nin;
+    if (!WRITE) {
+      if (lane == 0) {
+        atomicMax(&flags[FLAG_MAXCOUNT], total);
+        if (total > p.cap || nin > p.inbox_cap) flags[FLAG_OVERFLOW] = 1;
+      }
+      continue;
+    }
+    if (!WRITE) continue;  // (keeps the compiler from warning about the unreachable tail in the CHECK instantiation)
+    // ---- ... plus arrivals from other tiles
+    for (int i = lane; i < nin; i += 32) {
+      const int mi = inbox[(size_t)t * p.inbox_cap + i];
+      RepairRec &r = rec[m + i];
+      r.pos = mv_pos[mi];
+      r.second = mv_second[mi];
+      r.force = mv_force[mi];
+      r.idflag = mv_id[mi];
+      r.cell = mv_cell[mi];
+      r.key = ((unsigned long long)(unsigned int)r.cell << 32) | (r.idflag & ~MAVI_INACTIVE_BIT);
+    }
+    __syncwarp();
+    // ---- rank sort (keys are unique) and in-place rewrite
+    for (int e = lane; e < total; e += 32) {
+      const unsigned long long key = rec[e].key;
+      int rank = 0;
+      for (int o = 0; o < total; o++) rank += rec[o].key < key;
+      const int k = base + rank;
+      const RepairRec &r = rec[e];
+      pos[k] = r.pos;
+      if (vel) vel[k] = r.second;
+      else ang[k] = r.second.x;
+      force[k] = r.force;
+      idflag[k] = r.idflag;
+      cell[k] = r.cell;
+    }
+    // ---- tstart row of the tile: lane lr counts the particles of local row lr, warp scan
+    {
+      const int col = t / p.tpc, tr = t - col * p.tpc;
+      const int mycell = col * p.num_rows + tr * MAVI_TR + lane;
+      int cnt = 0;
+      for (int o = 0; o < total; o++) cnt += rec[o].cell == mycell;
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      ts[lane] = base + incl - cnt;
+      if (lane == 31) ts[MAVI_TR] = base + incl;
+    }
+    if (lane == 0) {
+      tile_dirty[t] = 0;
+      inbox_cnt[t] = 0;
+    }
+    __syncwarp();
+  }
+}
+
+void launch_repair_tiles(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel) {
+  if (p.nt == 0) return;
+  double2 *vel = second_is_vel ? a.vel : nullptr;
+  double *ang = second_is_vel ? nullptr : a.ang;
+  const size_t smem = (size_t)REPAIR_WARPS * p.cap * sizeof(RepairRec);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k_repair_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int grid = 148 * 4;
+  MAVI_LAUNCH(c, (k_repair_tiles<false>), grid, REPAIR_WARPS * 32, 0, p, a.flags, a.dirty_list, a.tile_dirty, a.inbox_cnt,
+              a.inbox, a.tstart, a.pos[0], vel, ang, a.force, a.idflag, a.cell, a.mv_pos, a.mv_second, a.mv_force, a.mv_id,
+              a.mv_cell);
+  MAVI_LAUNCH(c, k_repair_collect, 64, TPB, 0, a.flags, a.mv_src, a.pos[0], vel, ang, a.force, a.idflag, a.cell, a.mv_pos,
+              a.mv_second, a.mv_force, a.mv_id, a.mv_cell, p.mv_cap);
+  MAVI_LAUNCH(c, (k_repair_tiles<true>), grid, REPAIR_WARPS * 32, smem, p, a.flags, a.dirty_list, a.tile_dirty, a.inbox_cnt,
+              a.inbox, a.tstart, a.pos[0], vel, ang, a.force, a.idflag, a.cell, a.mv_pos, a.mv_second, a.mv_force, a.mv_id,
+              a.mv_cell);
+  refresh_rank_maps(c, p, a);
 }
 
 // =========================================================================================================
 // Pair forces (calc_forces!, src/integration.jl:112-224) as a per-particle gather, fused with the integrators.
 // =========================================================================================================
-
-// flags[] layout (device error / control word)
-enum { FLAG_ERR = 0, FLAG_CHANGED = 1, FLAG_BIGMOVE = 2, FLAG_NFIX = 3 };
 
 template <int DYN, bool MINIMG>
 __device__ __forceinline__ void accumulate_pair(const DevParams &p, double2 ri, double2 rj, double &fx, double &fy) {
@@ -215,83 +491,208 @@ __device__ __forceinline__ void accumulate_pair(const DevParams &p, double2 ri, 
   fy = fma(c, dy, fy);
 }
 
-// Interior cell (no stencil wrap / clipping): the neighbours are 4 contiguous runs of the sorted order
-//   column-1: [a0,b0)   own column: [a1,k) and (k,b1)   column+1: [a2,b2)
-// walked by ONE flat, branch-free loop: neighbour t lives at slot t + offset(t) (three compares select the offset), so
-// a warp waits for the max over lanes of the neighbour COUNT instead of the sum of per-column maxima, and the next
-// position is prefetched while the current pair is evaluated.
+// Neighbour enumeration through a per-thread SEGMENT TABLE in shared memory.  The neighbours of a particle (own cell
+// + the 8 surrounding cells) are at most 7 contiguous runs of slots: rows row-1..row+1 of each of the 3 columns, each
+// split in two where a tile edge (the slack of the upper tile = a hole in slot space) lies in between, and the own
+// column split once more around the particle itself.  Each thread writes its runs as (slot offset, virtual end) pairs
+// and then walks ONE flat virtual index 0..total-1: slot = index + offset, and the table is consulted only when the
+// index crosses a run boundary.  A warp therefore waits for the max over lanes of the neighbour COUNT (not a sum of
+// per-run maxima), every lane executes the same loop body, and positions are fetched two neighbours ahead.
+constexpr int SEG_MAX = 8;
+
+struct SegWalker {
+  const int *tbl;  // [2*SEG_MAX][TPB] column of this thread: ends at [2s], offsets at [2s+1]
+  int s, brk, off, u, total;
+  __device__ __forceinline__ void init(const int *t, int total_) {
+    tbl = t;
+    s = 0;
+    u = 0;
+    total = total_;
+    brk = tbl[0];
+    off = tbl[TPB];
+  }
+  // slot of the next neighbour (call at most `total` times)
+  __device__ __forceinline__ int next() {
+    if (u >= brk) {
+      ++s;
+      brk = tbl[(2 * s) * TPB];
+      off = tbl[(2 * s + 1) * TPB];
+    }
+    return (u++) + off;
+  }
+};
+
 template <int DYN, bool MINIMG>
-__device__ __forceinline__ void interior_force(const DevParams &p, const int *__restrict__ start,
-                                               const double2 *__restrict__ pos, int cell, int k, double2 ri, double &fx,
-                                               double &fy) {
-  const int R = p.num_rows;
-  const int *s = start + cell;
-  const int a0 = __ldg(s - R - 1), b0 = __ldg(s - R + 2);
-  const int a1 = __ldg(s - 1), b1 = __ldg(s + 2);
-  const int a2 = __ldg(s + R - 1), b2 = __ldg(s + R + 2);
-  const int c1 = b0 - a0;            // neighbours t <  c1          -> slot a0 + t
-  const int c2 = c1 + (k - a1);      //            c1 <= t < c2    -> slot a1 + (t - c1)
-  const int c3 = c2 + (b1 - k - 1);  //            c2 <= t < c3    -> slot k + 1 + (t - c2)   (skips self)
-  const int total = c3 + (b2 - a2);  //            c3 <= t         -> slot a2 + (t - c3)
-  if (total <= 0) return;
-  const int d1 = (a1 - c1) - a0, d3 = (a2 - c3) - (a1 - c1) - 1;
-  // slot(t) = t + a0 + [t>=c1] d1 + [t>=c2] + [t>=c3] d3   (predicated adds, no branches)
-  auto slot = [&](int t) { return t + a0 + (t >= c1 ? d1 : 0) + (t >= c2 ? 1 : 0) + (t >= c3 ? d3 : 0); };
-  // two neighbours per trip: independent FP64 chains, and the loads of the next pair are in flight meanwhile
-  double2 r0 = __ldg(pos + slot(0));
-  double2 r1 = (total > 1) ? __ldg(pos + slot(1)) : r0;
+__device__ __forceinline__ void walk_pairs(const DevParams &p, const double2 *__restrict__ pos, const int *tbl,
+                                           int total, double2 ri, double &fx, double &fy) {
+  SegWalker w;
+  w.init(tbl, total);
+  double2 r0 = __ldg(pos + w.next());
+  double2 r1 = (total > 1) ? __ldg(pos + w.next()) : r0;
   int t = 0;
 #pragma unroll 1
   for (; t + 2 <= total; t += 2) {
     const double2 q0 = r0, q1 = r1;
-    if (t + 2 < total) r0 = __ldg(pos + slot(t + 2));
-    if (t + 3 < total) r1 = __ldg(pos + slot(t + 3));
+    if (t + 2 < total) r0 = __ldg(pos + w.next());
+    if (t + 3 < total) r1 = __ldg(pos + w.next());
     accumulate_pair<DYN, MINIMG>(p, ri, q0, fx, fy);
     accumulate_pair<DYN, MINIMG>(p, ri, q1, fx, fy);
   }
   if (t < total) accumulate_pair<DYN, MINIMG>(p, ri, r0, fx, fy);
 }
 
-// ALLP: chunks === nothing -> all pairs over active ids (src/integration.jl:197-224); physical order = id order.
-// exact_minimg: force the minimum image on interior cells too (pass B after an abnormally large drift).
-template <int DYN, bool PER, bool ALLP>
-__device__ __forceinline__ double2 pair_force(const DevParams &p, const int *__restrict__ start,
-                                              const double2 *__restrict__ pos, const unsigned int *__restrict__ idflag,
-                                              int cell, int k, double2 ri, bool exact_minimg) {
+template <int DYN, bool PER>
+__device__ __forceinline__ double2 cell_pair_force(const DevParams &p, const int *__restrict__ tstart,
+                                                   const double2 *__restrict__ pos, int *__restrict__ tbl, int cell,
+                                                   int k, double2 ri, bool exact_minimg) {
+  const int R = p.num_rows, Cn = p.num_cols;
+  const int col = div_rows(p, cell), row = cell - col * R;
   double fx = 0.0, fy = 0.0;
-  if (ALLP) {
-    for (int j = 0; j < p.n; j++) {
-      if (j == k || (idflag[j] & MAVI_INACTIVE_BIT)) continue;
-      accumulate_pair<DYN, PER>(p, ri, __ldg(pos + j), fx, fy);
+  bool use_mi = PER && (exact_minimg || !p.fast_interior);
+  // Rows row-1..row+1 as two row intervals [r1a,r1b] and [r2a,r2b], each inside ONE tile (second may be empty):
+  // a tile edge between two of the rows splits them, a periodic wrap puts one interval at the far end of the column,
+  // a clipped (walled) edge just shortens the first interval.
+  int r1a = row - 1, r1b = row + 1, r2a = 0, r2b = -1;
+  if (row == 0) {
+    r1a = 0;
+    if (p.wrap_rows) { r2a = 0; r2b = (R > 1) ? 1 : 0; r1a = r1b = R - 1; use_mi = PER; }
+    else r1b = (R > 1) ? 1 : 0;
+  } else if (row == R - 1) {
+    r1b = R - 1;
+    if (p.wrap_rows) { r2a = r2b = 0; use_mi = PER; }
+  }
+  if (r2b < r2a && (r1a / MAVI_TR) != (r1b / MAVI_TR)) {  // tile edge inside the interval: split it
+    const int edge = (r1b / MAVI_TR) * MAVI_TR;           // first row of the lower tile
+    r2a = edge; r2b = r1b; r1b = edge - 1;
+  }
+  if ((r1a / MAVI_TR) != (r1b / MAVI_TR) || (r2b >= r2a && (r2a / MAVI_TR) != (r2b / MAVI_TR))) {
+    // wrap AND tile edge at once (only when (R-1) % 32 == 0): generic per-cell walk
+    for_each_neighbor(p, tstart, cell, k, [&](int j) { accumulate_pair<DYN, PER>(p, ri, __ldg(pos + j), fx, fy); });
+    return make_double2(fx, fy);
+  }
+  const bool two = r2b >= r2a;
+  const int t1 = r1a / MAVI_TR, t2 = r2a / MAVI_TR;
+  const int o1a = t1 * (MAVI_TR + 1) + (r1a - t1 * MAVI_TR), o1b = t1 * (MAVI_TR + 1) + (r1b - t1 * MAVI_TR) + 1;
+  const int o2a = t2 * (MAVI_TR + 1) + (r2a - t2 * MAVI_TR), o2b = t2 * (MAVI_TR + 1) + (r2b - t2 * MAVI_TR) + 1;
+  int S = 0, vtotal = 0;
+  auto add_seg = [&](int first, int len) {
+    if (len > 0) {
+      tbl[(2 * S + 1) * TPB] = first - vtotal;
+      vtotal += len;
+      tbl[(2 * S) * TPB] = vtotal;
+      ++S;
     }
-  } else {
-    const int R = p.num_rows;
-    const int col = cell / R, row = cell - col * R;
-    const bool interior = row >= 1 && row <= R - 2 && col >= 1 && col <= p.num_cols - 2;
-    if (interior) {
-      // Fresh cells: both particles of a pair lie inside 8-adjacent cells, so |dr| < 2 cell widths <= size/4 on a grid
-      // of >= 8 cells per axis and the reference's `abs(dr) > size/2` test is false: min image skipped EXACTLY.
-      // Stale cells (Verlet pass 2) are covered by the per-step displacement guard (FLAG_BIGMOVE).
-      if (PER && (exact_minimg || !p.fast_interior)) interior_force<DYN, true>(p, start, pos, cell, k, ri, fx, fy);
-      else interior_force<DYN, false>(p, start, pos, cell, k, ri, fx, fy);
+  };
+#pragma unroll
+  for (int dc = -1; dc <= 1; dc++) {
+    int c2 = col + dc;
+    if (c2 < 0) {
+      if (!p.wrap_cols) continue;
+      c2 = Cn - 1;
+      use_mi = PER;
+    } else if (c2 >= Cn) {
+      if (!p.wrap_cols) continue;
+      c2 = 0;
+      use_mi = PER;
+    }
+    const int *tc = tstart + (size_t)c2 * p.tpc * (MAVI_TR + 1);
+    const int a = __ldg(tc + o1a), ea = __ldg(tc + o1b);
+    const int b = two ? __ldg(tc + o2a) : ea, eb = two ? __ldg(tc + o2b) : ea;
+    if (dc != 0) {
+      add_seg(a, ea - a);
+      add_seg(b, eb - b);
+    } else if (k < ea && k >= a) {  // own column: split around self
+      add_seg(a, k - a);
+      add_seg(k + 1, ea - k - 1);
+      add_seg(b, eb - b);
     } else {
-      for_each_neighbor(p, start, cell, k, [&](int j) { accumulate_pair<DYN, PER>(p, ri, __ldg(pos + j), fx, fy); });
+      add_seg(a, ea - a);
+      add_seg(b, k - b);
+      add_seg(k + 1, eb - k - 1);
     }
+  }
+  if (vtotal > 0) {
+    // Minimum image: needed only for neighbours reached through a wrapped row/column (or always, in exact mode);
+    // applying it to the other neighbours of such a particle is an exact no-op, so the choice is per particle.
+    if (use_mi) walk_pairs<DYN, true>(p, pos, tbl, vtotal, ri, fx, fy);
+    else walk_pairs<DYN, false>(p, pos, tbl, vtotal, ri, fx, fy);
   }
   return make_double2(fx, fy);
 }
 
+// ALLP: chunks === nothing -> all pairs over active ids (src/integration.jl:197-224); slots = original order.
+// exact_minimg: force the minimum image everywhere (pass B after an abnormally large drift).
+//
+// Minimum-image shortcut (exactness argument): with fresh cells both particles of a non-wrapped pair lie inside
+// 8-adjacent cells, so |dr| < 2 cell widths <= size/4 on a grid of >= 8 cells per axis and the reference's
+// `abs(dr) > size/2` test is false -> skipped EXACTLY.  Stale cells (Verlet pass 2) are covered by the per-step
+// displacement guard (FLAG_BIGMOVE) which switches pass B to the exact path.
+template <int DYN, bool PER, bool ALLP>
+__device__ __forceinline__ double2 pair_force(const DevParams &p, const int *__restrict__ tstart,
+                                              const double2 *__restrict__ pos, const unsigned int *__restrict__ idflag,
+                                              int *__restrict__ lst, int cell, int k, double2 ri, bool exact_minimg) {
+  if (ALLP) {
+    double fx = 0.0, fy = 0.0;
+    for (int j = 0; j < p.n; j++) {
+      if (j == k || (idflag[j] & MAVI_INACTIVE_BIT)) continue;
+      accumulate_pair<DYN, PER>(p, ri, __ldg(pos + j), fx, fy);
+    }
+    return make_double2(fx, fy);
+  }
+  return cell_pair_force<DYN, PER>(p, tstart, pos, lst, cell, k, ri, exact_minimg);
+}
+
+// The particle in slot k (sorted under cell c_old) now sits at (x, y).  If update_particle_chunk! would bin it
+// elsewhere, record its fresh cell, mark the tiles involved for the incremental repair and queue it in the
+// destination tile's inbox when it changes tile.
+struct MoverSink {
+  int *cell, *tile_dirty, *dirty_list, *inbox_cnt, *inbox, *mv_src, *flags;
+};
+
+__device__ __forceinline__ void mark_dirty(const MoverSink &ms, int t) {
+  if (atomicExch(&ms.tile_dirty[t], 1) == 0) ms.dirty_list[atomicAdd(&ms.flags[FLAG_CHANGED], 1)] = t;
+}
+
+__device__ __forceinline__ void note_if_moved(const DevParams &p, const MoverSink &ms, int k, int c_old, double x,
+                                              double y) {
+  if (still_in_cell(p, x, y, c_old)) return;
+  int c_new = cell_of_point(p, x, y);
+  if (c_new < 0) {  // left the grid: the reference throws BoundsError at its NEXT update_chunks! -> reported then
+    atomicOr(&ms.flags[FLAG_ERR], ERRBIT_OOG_PENDING);
+    return;
+  }
+  if (c_new == c_old) return;
+  ms.cell[k] = c_new;
+  const int t_old = tile_of_cell(p, c_old), t_new = tile_of_cell(p, c_new);
+  mark_dirty(ms, t_old);
+  if (t_new != t_old) {
+    mark_dirty(ms, t_new);
+    const int m = atomicAdd(&ms.flags[FLAG_NMV], 1);
+    const int i = atomicAdd(&ms.inbox_cnt[t_new], 1);
+    if (m < p.mv_cap && i < p.inbox_cap) {
+      ms.mv_src[m] = k;
+      ms.inbox[(size_t)t_new * p.inbox_cap + i] = m;
+    } else {
+      ms.flags[FLAG_OVERFLOW] = 1;
+    }
+  }
+}
+
 // clean_forces! + calc_forces! (+ calc_walls_forces!): the force state after src/integration.jl:508-511.
 template <int DYN, bool PER, bool ALLP>
-__global__ void __launch_bounds__(TPB) k_force_only(const __grid_constant__ DevParams p, const int *__restrict__ start,
+__global__ void __launch_bounds__(TPB) k_force_only(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
+                             const int *__restrict__ tile_prefix, const int *__restrict__ cta_first,
                              const int *__restrict__ cell, const unsigned int *__restrict__ idflag,
                              const double2 *__restrict__ pos, double2 *__restrict__ force, int with_walls) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= p.n) return;
+  __shared__ int s_lst[ALLP ? 1 : 2 * SEG_MAX * TPB];
+  __shared__ int s_win[RANK_WIN + 1];
+  int rank = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = ALLP ? rank : slot_of_rank_cta(p, tile_prefix, cta_first, rank, s_win);
+  if (rank >= p.n) return;
   double2 F = make_double2(0.0, 0.0);
   if (!(idflag[k] & MAVI_INACTIVE_BIT)) {
     double2 r = pos[k];
-    F = pair_force<DYN, PER, ALLP>(p, start, pos, idflag, ALLP ? 0 : cell[k], k, r, false);
+    F = pair_force<DYN, PER, ALLP>(p, tstart, pos, idflag, s_lst + threadIdx.x, ALLP ? 0 : cell[k], k, r, false);
     if (with_walls && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
   }
   force[k] = F;
@@ -300,16 +701,20 @@ __global__ void __launch_bounds__(TPB) k_force_only(const __grid_constant__ DevP
 // newton_step! first half (src/integration.jl:507-512 + update_verlet! :418-424):
 //   F1 = pair forces + wall forces;  pos' = pos + vel dt + F1 dt^2/2  (every slot, active or not).
 template <int DYN, bool PER, bool ALLP>
-__global__ void __launch_bounds__(TPB) k_newton_a(const __grid_constant__ DevParams p, const int *__restrict__ start,
+__global__ void __launch_bounds__(TPB) k_newton_a(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
+                           const int *__restrict__ tile_prefix, const int *__restrict__ cta_first,
                            const int *__restrict__ cell, const unsigned int *__restrict__ idflag,
                            const double2 *__restrict__ pos_in, const double2 *__restrict__ vel,
                            double2 *__restrict__ pos_out, double2 *__restrict__ f1, int *__restrict__ flags) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= p.n) return;
+  __shared__ int s_lst[ALLP ? 1 : 2 * SEG_MAX * TPB];
+  __shared__ int s_win[RANK_WIN + 1];
+  int rank = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = ALLP ? rank : slot_of_rank_cta(p, tile_prefix, cta_first, rank, s_win);
+  if (rank >= p.n) return;
   double2 r = pos_in[k];
   double2 F = make_double2(0.0, 0.0);
   if (!(idflag[k] & MAVI_INACTIVE_BIT)) {
-    F = pair_force<DYN, PER, ALLP>(p, start, pos_in, idflag, ALLP ? 0 : cell[k], k, r, false);
+    F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, s_lst + threadIdx.x, ALLP ? 0 : cell[k], k, r, false);
     if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
   }
   double2 v = vel[k];
@@ -324,43 +729,41 @@ __global__ void __launch_bounds__(TPB) k_newton_a(const __grid_constant__ DevPar
 }
 
 // newton_step! second half (update_verlet! :426-430, walls! :513): F2 on the drifted positions with the STALE cell
-// lists and WITHOUT wall forces; vel += dt/2 (F2 + F1); walls!(active ids).  Also decides, exactly, whether the next
-// update_chunks! would put the particle into the cell it is sorted under (-> the re-sort can be skipped), and defers
-// position changes made by walls! (periodic wrap, slippery projection) to a sparse fix-up list because neighbours
-// still read the unmodified drifted positions in this launch.
+// lists and WITHOUT wall forces; vel += dt/2 (F2 + F1); walls!(active ids).  Position changes made by walls!
+// (periodic wrap, slippery projection) are deferred to a sparse fix-up list because neighbours still read the
+// unmodified drifted positions in this launch; the fresh cell of the FINAL position feeds the incremental repair.
 template <int DYN, bool PER, bool ALLP>
-__global__ void __launch_bounds__(TPB) k_newton_b(const __grid_constant__ DevParams p, const int *__restrict__ start,
-                           const int *__restrict__ cell, const unsigned int *__restrict__ idflag,
-                           const double2 *__restrict__ pos_in, double2 *__restrict__ vel,
-                           const double2 *__restrict__ f1, double2 *__restrict__ f2, int *__restrict__ flags,
-                           int *__restrict__ fix_idx, double2 *__restrict__ fix_pos) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  bool changed = false;
-  if (k < p.n) {
-    double2 r = pos_in[k];
-    double2 F = make_double2(0.0, 0.0);
-    const bool active = !(idflag[k] & MAVI_INACTIVE_BIT);
-    const int c = ALLP ? 0 : cell[k];
-    if (active) F = pair_force<DYN, PER, ALLP>(p, start, pos_in, idflag, c, k, r, !ALLP && flags[FLAG_BIGMOVE] != 0);
-    double2 v = vel[k];
-    double2 Fo = f1[k];
-    v.x = v.x + p.hdt * (F.x + Fo.x);
-    v.y = v.y + p.hdt * (F.y + Fo.y);
-    if (active) {
-      const double x0 = r.x, y0 = r.y;
-      apply_walls<true>(p, r.x, r.y, v.x, v.y, p.particle_radius);
-      if (r.x != x0 || r.y != y0) {
-        int m = atomicAdd(&flags[FLAG_NFIX], 1);
-        fix_idx[m] = k;
-        fix_pos[m] = r;
-      }
-      if (!ALLP) changed = !still_in_cell(p, r.x, r.y, c);
+__global__ void __launch_bounds__(TPB) k_newton_b(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
+                           const int *__restrict__ tile_prefix, const int *__restrict__ cta_first,
+                           const unsigned int *__restrict__ idflag, const double2 *__restrict__ pos_in,
+                           double2 *__restrict__ vel, const double2 *__restrict__ f1, double2 *__restrict__ f2,
+                           int *__restrict__ fix_idx, double2 *__restrict__ fix_pos, const MoverSink ms) {
+  __shared__ int s_lst[ALLP ? 1 : 2 * SEG_MAX * TPB];
+  __shared__ int s_win[RANK_WIN + 1];
+  int rank = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = ALLP ? rank : slot_of_rank_cta(p, tile_prefix, cta_first, rank, s_win);
+  if (rank >= p.n) return;
+  double2 r = pos_in[k];
+  double2 F = make_double2(0.0, 0.0);
+  const bool active = !(idflag[k] & MAVI_INACTIVE_BIT);
+  const int c = ALLP ? 0 : ms.cell[k];
+  if (active) F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, s_lst + threadIdx.x, c, k, r, !ALLP && ms.flags[FLAG_BIGMOVE] != 0);
+  double2 v = vel[k];
+  double2 Fo = f1[k];
+  v.x = v.x + p.hdt * (F.x + Fo.x);
+  v.y = v.y + p.hdt * (F.y + Fo.y);
+  if (active) {
+    const double x0 = r.x, y0 = r.y;
+    apply_walls<true>(p, r.x, r.y, v.x, v.y, p.particle_radius);
+    if (r.x != x0 || r.y != y0) {
+      int m = atomicAdd(&ms.flags[FLAG_NFIX], 1);
+      fix_idx[m] = k;
+      fix_pos[m] = r;
     }
-    vel[k] = v;
-    f2[k] = F;
+    if (!ALLP) note_if_moved(p, ms, k, c, r.x, r.y);
   }
-  unsigned int m = __ballot_sync(0xffffffffu, changed);
-  if (m && (threadIdx.x & 31) == 0) atomicAdd(&flags[FLAG_CHANGED], __popc(m));
+  vel[k] = v;
+  f2[k] = F;
 }
 
 __global__ void k_apply_pos_fixes(const int *__restrict__ flags, const int *__restrict__ fix_idx,
@@ -372,65 +775,64 @@ __global__ void k_apply_pos_fixes(const int *__restrict__ flags, const int *__re
 // szabo_step! / rtp_step! (src/integration.jl:517-535): forces + update_szabo! (:433-465) / update_rtp! (:467-498)
 // + walls! in ONE pass.  The update loops slots 1:count (not ids) like the reference.
 template <int DYN, bool PER, bool ALLP>
-__global__ void __launch_bounds__(TPB) k_self_propelled(const __grid_constant__ DevParams p, const int *__restrict__ start,
-                                 const int *__restrict__ cell, const unsigned int *__restrict__ idflag,
-                                 const double2 *__restrict__ pos_in, double *__restrict__ ang,
-                                 double2 *__restrict__ pos_out, double2 *__restrict__ force,
-                                 const double *__restrict__ noise, unsigned long long step, int *__restrict__ flags) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  bool changed = false;
-  if (k < p.n) {
-    const unsigned int idf = idflag[k];
-    const bool active = !(idf & MAVI_INACTIVE_BIT);
-    const unsigned int id = idf & ~MAVI_INACTIVE_BIT;
-    const int c = ALLP ? 0 : cell[k];
-    double2 r = pos_in[k];
-    double2 F = make_double2(0.0, 0.0);
-    if (active) {
-      F = pair_force<DYN, PER, ALLP>(p, start, pos_in, idflag, c, k, r, false);
-      if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
-    }
-    force[k] = F;
-    if ((int)id < p.n_count) {
-      double theta = ang[k];
-      double sn, cs;
-      sincos(theta, &sn, &cs);
-      if (DYN == MAVI_DYN_SZABO) {
-        const double vo = p.dyn[0], mu = p.dyn[1], relax_time = p.dyn[2], drot = p.dyn[7];
-        double velx = vo * cs + mu * F.x, vely = vo * sn + mu * F.y;
-        double speed = sqrt(fabs(velx) + fabs(vely));  // sqrt(sum(abs, vel)) (sic), :448
-        double cross_prod = speed > 0.0 ? (cs * vely - sn * velx) / speed : 0.0;
-        if (fabs(cross_prod) > 1.0) cross_prod = sign_d(cross_prod);
-        double nz = 0.0;
-        if (drot != 0.0) nz = (p.rng_mode == MAVI_RNG_HOST_NOISE) ? (noise ? noise[id] : 0.0) : philox_normal(p.seed, id, step);
-        double d_theta = 1.0 / relax_time * asin(cross_prod) * p.dt + sqrt(2.0 * drot * p.dt) * nz;
-        r.x += velx * p.dt;
-        r.y += vely * p.dt;
-        ang[k] = theta + d_theta;
-      } else {
-        const double vo = p.dyn[0], tumble_rate = p.dyn[3];
-        double velx = vo * cs + F.x, vely = vo * sn + F.y;
-        r.x += velx * p.dt;
-        r.y += vely * p.dt;
-        double u, u2;
-        if (p.rng_mode == MAVI_RNG_HOST_NOISE) {
-          u = noise ? noise[2 * (size_t)id] : 1.0;
-          u2 = noise ? noise[2 * (size_t)id + 1] : 0.0;
-        } else {
-          philox_uniform2(p.seed, id, step, u, u2);
-        }
-        if (u < tumble_rate * p.dt) ang[k] = 6.283185307179586 * u2;  // 2*pi*rand(), :495
-      }
-    }
-    if (active) {
-      double vx = 0.0, vy = 0.0;
-      apply_walls<false>(p, r.x, r.y, vx, vy, p.particle_radius);
-      if (!ALLP) changed = !still_in_cell(p, r.x, r.y, c);
-    }
-    pos_out[k] = r;
+__global__ void __launch_bounds__(TPB) k_self_propelled(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
+                                 const int *__restrict__ tile_prefix, const int *__restrict__ cta_first,
+                                 const unsigned int *__restrict__ idflag, const double2 *__restrict__ pos_in,
+                                 double *__restrict__ ang, double2 *__restrict__ pos_out, double2 *__restrict__ force,
+                                 const double *__restrict__ noise, unsigned long long step, const MoverSink ms) {
+  __shared__ int s_lst[ALLP ? 1 : 2 * SEG_MAX * TPB];
+  __shared__ int s_win[RANK_WIN + 1];
+  int rank = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = ALLP ? rank : slot_of_rank_cta(p, tile_prefix, cta_first, rank, s_win);
+  if (rank >= p.n) return;
+  const unsigned int idf = idflag[k];
+  const bool active = !(idf & MAVI_INACTIVE_BIT);
+  const unsigned int id = idf & ~MAVI_INACTIVE_BIT;
+  const int c = ALLP ? 0 : ms.cell[k];
+  double2 r = pos_in[k];
+  double2 F = make_double2(0.0, 0.0);
+  if (active) {
+    F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, s_lst + threadIdx.x, c, k, r, false);
+    if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
   }
-  unsigned int m = __ballot_sync(0xffffffffu, changed);
-  if (m && (threadIdx.x & 31) == 0) atomicAdd(&flags[FLAG_CHANGED], __popc(m));
+  force[k] = F;
+  if ((int)id < p.n_count) {
+    double theta = ang[k];
+    double sn, cs;
+    sincos(theta, &sn, &cs);
+    if (DYN == MAVI_DYN_SZABO) {
+      const double vo = p.dyn[0], mu = p.dyn[1], relax_time = p.dyn[2], drot = p.dyn[7];
+      double velx = vo * cs + mu * F.x, vely = vo * sn + mu * F.y;
+      double speed = sqrt(fabs(velx) + fabs(vely));  // sqrt(sum(abs, vel)) (sic), :448
+      double cross_prod = speed > 0.0 ? (cs * vely - sn * velx) / speed : 0.0;
+      if (fabs(cross_prod) > 1.0) cross_prod = sign_d(cross_prod);
+      double nz = 0.0;
+      if (drot != 0.0) nz = (p.rng_mode == MAVI_RNG_HOST_NOISE) ? (noise ? noise[id] : 0.0) : philox_normal(p.seed, id, step);
+      double d_theta = 1.0 / relax_time * asin(cross_prod) * p.dt + sqrt(2.0 * drot * p.dt) * nz;
+      r.x += velx * p.dt;
+      r.y += vely * p.dt;
+      ang[k] = theta + d_theta;
+    } else {
+      const double vo = p.dyn[0], tumble_rate = p.dyn[3];
+      double velx = vo * cs + F.x, vely = vo * sn + F.y;
+      r.x += velx * p.dt;
+      r.y += vely * p.dt;
+      double u, u2;
+      if (p.rng_mode == MAVI_RNG_HOST_NOISE) {
+        u = noise ? noise[2 * (size_t)id] : 1.0;
+        u2 = noise ? noise[2 * (size_t)id + 1] : 0.0;
+      } else {
+        philox_uniform2(p.seed, id, step, u, u2);
+      }
+      if (u < tumble_rate * p.dt) ang[k] = 6.283185307179586 * u2;  // 2*pi*rand(), :495
+    }
+  }
+  if (active) {
+    double vx = 0.0, vy = 0.0;
+    apply_walls<false>(p, r.x, r.y, vx, vy, p.particle_radius);
+    if (!ALLP) note_if_moved(p, ms, k, c, r.x, r.y);
+  }
+  pos_out[k] = r;
 }
 
 // ---- dispatch over (dynamics, periodic, all-pairs) ----------------------------------------------------------
@@ -443,10 +845,14 @@ __global__ void __launch_bounds__(TPB) k_self_propelled(const __grid_constant__ 
     }                                                                                 \
   } while (0)
 
-void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int cur, bool with_wall_forces) {
+static MoverSink mover_sink(const DevArrays &a) {
+  return MoverSink{a.cell, a.tile_dirty, a.dirty_list, a.inbox_cnt, a.inbox, a.mv_src, a.flags};
+}
+
+void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool with_wall_forces) {
   const bool allp = p.num_cells == 0;
 #define CALL(D, P, A) \
-  MAVI_LAUNCH(c, (k_force_only<D, P, A>), nblk(p.n), TPB, p, a.start, a.cell[cur], a.idflag[cur], a.pos[cur], a.force, (int)with_wall_forces)
+  MAVI_LAUNCH(c, (k_force_only<D, P, A>), nblk(p.n), TPB, 0, p, a.tstart, a.tile_prefix, a.cta_first, a.cell, a.idflag, a.pos[0], a.force, (int)with_wall_forces)
   switch (p.dynamics) {
     case MAVI_DYN_LJ: MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, allp, CALL); break;
     case MAVI_DYN_HARMTRUNC: MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, allp, CALL); break;
@@ -456,31 +862,33 @@ void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &
 #undef CALL
 }
 
-void launch_newton_a(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int cur) {
+void launch_newton_a(const LaunchCtx &c, const DevParams &p, const DevArrays &a) {
   const bool allp = p.num_cells == 0;
 #define CALL(D, P, A) \
-  MAVI_LAUNCH(c, (k_newton_a<D, P, A>), nblk(p.n), TPB, p, a.start, a.cell[cur], a.idflag[cur], a.pos[cur], a.vel[cur], a.pos[cur ^ 1], a.force_old, a.flags)
+  MAVI_LAUNCH(c, (k_newton_a<D, P, A>), nblk(p.n), TPB, 0, p, a.tstart, a.tile_prefix, a.cta_first, a.cell, a.idflag, a.pos[0], a.vel, a.pos[1], a.force_old, a.flags)
   if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, allp, CALL);
   else MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, allp, CALL);
 #undef CALL
 }
 
-void launch_newton_b(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int cur) {
+void launch_newton_b(const LaunchCtx &c, const DevParams &p, const DevArrays &a) {
   const bool allp = p.num_cells == 0;
-  // reads the drifted positions pos[cur^1] (which become the current positions after the sparse wall fix-ups)
+  const MoverSink ms = mover_sink(a);
+  // reads the drifted positions pos[1] (which become the current positions after the sparse wall fix-ups)
 #define CALL(D, P, A) \
-  MAVI_LAUNCH(c, (k_newton_b<D, P, A>), nblk(p.n), TPB, p, a.start, a.cell[cur], a.idflag[cur], a.pos[cur ^ 1], a.vel[cur], a.force_old, a.force, a.flags, a.fix_idx, a.fix_pos)
+  MAVI_LAUNCH(c, (k_newton_b<D, P, A>), nblk(p.n), TPB, 0, p, a.tstart, a.tile_prefix, a.cta_first, a.idflag, a.pos[1], a.vel, a.force_old, a.force, a.fix_idx, a.fix_pos, ms)
   if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, allp, CALL);
   else MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, allp, CALL);
 #undef CALL
-  MAVI_LAUNCH(c, k_apply_pos_fixes, 64, TPB, a.flags, a.fix_idx, a.fix_pos, a.pos[cur ^ 1]);
+  MAVI_LAUNCH(c, k_apply_pos_fixes, 64, TPB, 0, a.flags, a.fix_idx, a.fix_pos, a.pos[1]);
 }
 
-void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int cur, const double *noise,
+void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const double *noise,
                            unsigned long long step) {
   const bool allp = p.num_cells == 0;
+  const MoverSink ms = mover_sink(a);
 #define CALL(D, P, A) \
-  MAVI_LAUNCH(c, (k_self_propelled<D, P, A>), nblk(p.n), TPB, p, a.start, a.cell[cur], a.idflag[cur], a.pos[cur], a.ang[cur], a.pos[cur ^ 1], a.force, noise, step, a.flags)
+  MAVI_LAUNCH(c, (k_self_propelled<D, P, A>), nblk(p.n), TPB, 0, p, a.tstart, a.tile_prefix, a.cta_first, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms)
   if (p.dynamics == MAVI_DYN_SZABO) MAVI_DISPATCH_DYN(MAVI_DYN_SZABO, p.periodic, allp, CALL);
   else MAVI_DISPATCH_DYN(MAVI_DYN_RTP, p.periodic, allp, CALL);
 #undef CALL
@@ -515,138 +923,158 @@ __global__ void k_reduce_final(const double *__restrict__ partials, int nb, doub
 }
 
 // kinetic_energy, src/quantities.jl:12-18: sum over ALL slots of |v|^2, /2 (mass 1)
-__global__ void k_kinetic(int n, const double2 *__restrict__ vel, double *__restrict__ partials) {
+__global__ void k_kinetic(const __grid_constant__ DevParams p, const int *__restrict__ tile_prefix,
+                          const int *__restrict__ cta_first, const double2 *__restrict__ vel,
+                          double *__restrict__ partials) {
   double s = 0.0;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    double2 v = vel[k];
-    s += v.x * v.x + v.y * v.y;
-  }
-  s = block_sum(s);
-  if (threadIdx.x == 0) partials[blockIdx.x] = s;
-}
-
-void launch_kinetic_energy(const LaunchCtx &c, const DevParams &p, const double2 *vel, double *partials, double *out) {
-  int nb = min(nblk(p.n, RED_TPB), RED_MAX_BLOCKS);
-  if (nb < 1) nb = 1;
-  MAVI_LAUNCH(c, k_kinetic, nb, RED_TPB, p.n, vel, partials);
-  MAVI_LAUNCH(c, k_reduce_final, 1, RED_TPB, partials, nb, 0.5, out);
-}
-
-// potential_energy(::LenJonesCfg), src/quantities.jl:46-66.  MODE 0: every pair i<j of slots 1:count (exact, O(N^2));
-// MODE 1: the cell-stencil pair set (each pair seen from both ends -> halved).
-template <bool PER, int MODE>
-__global__ void k_potential(const __grid_constant__ DevParams p, const int *__restrict__ start,
-                            const int *__restrict__ cell, const unsigned int *__restrict__ idflag,
-                            const double2 *__restrict__ pos, double *__restrict__ partials) {
-  double s = 0.0;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < p.n; k += gridDim.x * blockDim.x) {
-    const unsigned int idf = idflag[k];
-    double2 ri = pos[k];
-    auto term = [&](int j) {
-      double2 rj = __ldg(pos + j);
-      double dx = min_image<PER>(ri.x - rj.x, p.half[0], p.size[0]);
-      double dy = min_image<PER>(ri.y - rj.y, p.half[1], p.size[1]);
-      double s2 = p.lj_sig2 / (dx * dx + dy * dy);
-      double s6 = s2 * s2 * s2;
-      s += s6 * s6 - s6;
-    };
-    if (MODE == 0) {
-      if ((int)(idf & ~MAVI_INACTIVE_BIT) >= p.n_count) continue;
-      for (int j = k + 1; j < p.n; j++)
-        if ((int)(idflag[j] & ~MAVI_INACTIVE_BIT) < p.n_count) term(j);
-    } else {
-      if (idf & MAVI_INACTIVE_BIT) continue;
-      for_each_neighbor(p, start, cell[k], k, term);
+  // whole 256-rank blocks per CTA so that cta_first[rank / TPB] stays valid
+  for (int base = blockIdx.x * TPB; base < p.n; base += gridDim.x * TPB) {
+    int rank = base + threadIdx.x;
+    if (rank < p.n) {
+      double2 v = vel[slot_of_rank(p, tile_prefix, cta_first, rank)];
+      s += v.x * v.x + v.y * v.y;
     }
   }
   s = block_sum(s);
   if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
 
-void launch_potential_energy(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int cur, int mode, double *out) {
+void launch_kinetic_energy(const LaunchCtx &c, const DevParams &p, const DevArrays &a, double *out) {
+  int nb = min(nblk(p.n, RED_TPB), RED_MAX_BLOCKS);
+  if (nb < 1) nb = 1;
+  MAVI_LAUNCH(c, k_kinetic, nb, RED_TPB, 0, p, a.tile_prefix, a.cta_first, a.vel, a.reduce_buf);
+  MAVI_LAUNCH(c, k_reduce_final, 1, RED_TPB, 0, a.reduce_buf, nb, 0.5, out);
+}
+
+// potential_energy(::LenJonesCfg), src/quantities.jl:46-66.
+// exact mode: every pair i<j of slots 1:count, O(N^2), on the dense staging copy (no cutoff, min image)
+template <bool PER>
+__global__ void k_potential_exact(const __grid_constant__ DevParams p, const unsigned int *__restrict__ st_id,
+                                  const double2 *__restrict__ st_pos, double *__restrict__ partials) {
+  double s = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
+    if ((int)(st_id[i] & ~MAVI_INACTIVE_BIT) >= p.n_count) continue;
+    const double2 ri = st_pos[i];
+    for (int j = i + 1; j < p.n; j++) {
+      if ((int)(st_id[j] & ~MAVI_INACTIVE_BIT) >= p.n_count) continue;
+      const double2 rj = __ldg(st_pos + j);
+      double dx = min_image<PER>(ri.x - rj.x, p.half[0], p.size[0]);
+      double dy = min_image<PER>(ri.y - rj.y, p.half[1], p.size[1]);
+      double s2 = p.lj_sig2 / (dx * dx + dy * dy);
+      double s6 = s2 * s2 * s2;
+      s += s6 * s6 - s6;
+    }
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+// stencil mode: the cell-stencil pair set (each pair seen from both ends -> halved by the caller)
+template <bool PER>
+__global__ void k_potential_stencil(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
+                                    const int *__restrict__ tile_prefix, const int *__restrict__ cta_first,
+                                    const int *__restrict__ cell, const unsigned int *__restrict__ idflag,
+                                    const double2 *__restrict__ pos, double *__restrict__ partials) {
+  double s = 0.0;
+  for (int base = blockIdx.x * TPB; base < p.n; base += gridDim.x * TPB) {
+    int rank = base + threadIdx.x;
+    if (rank >= p.n) continue;
+    const int k = slot_of_rank(p, tile_prefix, cta_first, rank);
+    if (idflag[k] & MAVI_INACTIVE_BIT) continue;
+    const double2 ri = pos[k];
+    for_each_neighbor(p, tstart, cell[k], k, [&](int j) {
+      const double2 rj = __ldg(pos + j);
+      double dx = min_image<PER>(ri.x - rj.x, p.half[0], p.size[0]);
+      double dy = min_image<PER>(ri.y - rj.y, p.half[1], p.size[1]);
+      double s2 = p.lj_sig2 / (dx * dx + dy * dy);
+      double s6 = s2 * s2 * s2;
+      s += s6 * s6 - s6;
+    });
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+void launch_potential_energy(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int mode, double *out) {
   int nb = min(nblk(p.n, RED_TPB), RED_MAX_BLOCKS);
   if (nb < 1) nb = 1;
   const double eps4 = 4.0 * p.dyn[1];
-  if (mode == 0) {
-    if (p.periodic) MAVI_LAUNCH(c, (k_potential<true, 0>), nb, RED_TPB, p, a.start, a.cell[cur], a.idflag[cur], a.pos[cur], a.reduce_buf);
-    else MAVI_LAUNCH(c, (k_potential<false, 0>), nb, RED_TPB, p, a.start, a.cell[cur], a.idflag[cur], a.pos[cur], a.reduce_buf);
-    MAVI_LAUNCH(c, k_reduce_final, 1, RED_TPB, a.reduce_buf, nb, eps4, out);
+  if (mode == 0) {  // caller has refreshed the staging copy
+    if (p.periodic) MAVI_LAUNCH(c, (k_potential_exact<true>), nb, RED_TPB, 0, p, a.st_id, a.st_pos, a.reduce_buf);
+    else MAVI_LAUNCH(c, (k_potential_exact<false>), nb, RED_TPB, 0, p, a.st_id, a.st_pos, a.reduce_buf);
+    MAVI_LAUNCH(c, k_reduce_final, 1, RED_TPB, 0, a.reduce_buf, nb, eps4, out);
   } else {
-    if (p.periodic) MAVI_LAUNCH(c, (k_potential<true, 1>), nb, RED_TPB, p, a.start, a.cell[cur], a.idflag[cur], a.pos[cur], a.reduce_buf);
-    else MAVI_LAUNCH(c, (k_potential<false, 1>), nb, RED_TPB, p, a.start, a.cell[cur], a.idflag[cur], a.pos[cur], a.reduce_buf);
-    MAVI_LAUNCH(c, k_reduce_final, 1, RED_TPB, a.reduce_buf, nb, 0.5 * eps4, out);
+    if (p.periodic) MAVI_LAUNCH(c, (k_potential_stencil<true>), nb, RED_TPB, 0, p, a.tstart, a.tile_prefix, a.cta_first, a.cell, a.idflag, a.pos[0], a.reduce_buf);
+    else MAVI_LAUNCH(c, (k_potential_stencil<false>), nb, RED_TPB, 0, p, a.tstart, a.tile_prefix, a.cta_first, a.cell, a.idflag, a.pos[0], a.reduce_buf);
+    MAVI_LAUNCH(c, k_reduce_final, 1, RED_TPB, 0, a.reduce_buf, nb, 0.5 * eps4, out);
   }
 }
 
 // =========================================================================================================
-// Upload / download helpers
+// Download helpers: un-permute slot order to original ids
 // =========================================================================================================
-__global__ void k_unpermute2(int n, const unsigned int *__restrict__ idflag, const double2 *__restrict__ in,
-                             double2 *__restrict__ out) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < n) out[idflag[k] & ~MAVI_INACTIVE_BIT] = in[k];
+__global__ void k_unpermute2(const __grid_constant__ DevParams p, const int *__restrict__ tile_prefix,
+                             const int *__restrict__ cta_first, const unsigned int *__restrict__ idflag,
+                             const double2 *__restrict__ in, double2 *__restrict__ out) {
+  int rank = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rank >= p.n) return;
+  const int k = slot_of_rank(p, tile_prefix, cta_first, rank);
+  out[idflag[k] & ~MAVI_INACTIVE_BIT] = in[k];
 }
-__global__ void k_unpermute1(int n, const unsigned int *__restrict__ idflag, const double *__restrict__ in,
-                             double *__restrict__ out) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < n) out[idflag[k] & ~MAVI_INACTIVE_BIT] = in[k];
+__global__ void k_unpermute1(const __grid_constant__ DevParams p, const int *__restrict__ tile_prefix,
+                             const int *__restrict__ cta_first, const unsigned int *__restrict__ idflag,
+                             const double *__restrict__ in, double *__restrict__ out) {
+  int rank = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rank >= p.n) return;
+  const int k = slot_of_rank(p, tile_prefix, cta_first, rank);
+  out[idflag[k] & ~MAVI_INACTIVE_BIT] = in[k];
 }
-__global__ void k_unpermute_cells(int n, int num_cells, const unsigned int *__restrict__ idflag,
+__global__ void k_unpermute_cells(const __grid_constant__ DevParams p, const int *__restrict__ tile_prefix,
+                                  const int *__restrict__ cta_first, const unsigned int *__restrict__ idflag,
                                   const int *__restrict__ cell, int *__restrict__ out) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < n) {
-    int c = cell[k];
-    out[idflag[k] & ~MAVI_INACTIVE_BIT] = c < num_cells ? c : -1;
-  }
+  int rank = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rank >= p.n) return;
+  const int k = slot_of_rank(p, tile_prefix, cta_first, rank);
+  out[idflag[k] & ~MAVI_INACTIVE_BIT] = rank < p.n_active ? cell[k] : -1;
 }
-__global__ void k_ids(int n, const unsigned int *__restrict__ idflag, int *__restrict__ out) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < n) out[k] = (int)(idflag[k] & ~MAVI_INACTIVE_BIT);
+// num_particles_in_chunk (row fastest) from tstart
+__global__ void k_cell_counts(const __grid_constant__ DevParams p, const int *__restrict__ tstart, int *__restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.num_cells) return;
+  const int col = c / p.num_rows, row = c - col * p.num_rows;
+  const int q = tq_of(p, col, row);
+  out[c] = tstart[q + 1] - tstart[q];
 }
-__global__ void k_init_ids(int n, const unsigned char *__restrict__ mask, unsigned int *__restrict__ idflag,
-                           int *__restrict__ cell, int num_cells) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < n) {
-    bool act = mask ? mask[k] != 0 : true;
-    idflag[k] = (unsigned int)k | (act ? 0u : MAVI_INACTIVE_BIT);
-    cell[k] = -2;  // "not sorted yet": forces the first re-sort
-  }
-}
-// check_inside, src/space_checks.jl:9-61 (Rectangle: any coordinate < bottom_left or > top_right; Circle: |pos|^2 > R^2,
-// centre ignored (sic)); only single-geometry spaces are checked (ManyGeometries hits the generic no-op method).
-__global__ void k_check_inside(const __grid_constant__ DevParams p, const double2 *__restrict__ pos,
-                               const unsigned int *__restrict__ idflag, int *__restrict__ flags) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= p.n || (idflag[k] & MAVI_INACTIVE_BIT)) return;
-  const DevSpace &sp = p.spaces[0];
-  double2 r = pos[k];
-  bool out = false;
-  if (sp.geom == MAVI_GEOM_RECT) {
-    double trx = sp.rect_bl[0] + sp.rect_sz[0], try_ = sp.rect_bl[1] + sp.rect_sz[1];
-    out = (r.x < sp.rect_bl[0]) || (r.y < sp.rect_bl[1]) || (r.x > trx) || (r.y > try_);
-  } else if (sp.geom == MAVI_GEOM_CIRCLE) {
-    out = (r.x * r.x + r.y * r.y) > sp.cr * sp.cr;
-  }
-  if (out) atomicOr(&flags[0], ERRBIT_OUTSIDE_SPACE);
+// ids of the active particles in (cell, id) order, i.e. as the reference's chunk_particles lists them:
+// out[cell_start[c] + i] = id of the i-th particle of cell c   (cell_start = exclusive scan of the cell populations)
+__global__ void k_ids_in_cell_order(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
+                                    const int *__restrict__ cell_start, const unsigned int *__restrict__ idflag,
+                                    int *__restrict__ out) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.num_cells) return;
+  const int col = div_rows(p, c), row = c - col * p.num_rows;
+  const int q = tq_of(p, col, row);
+  const int b = tstart[q], e = tstart[q + 1], d = cell_start[c];
+  for (int j = b; j < e; j++) out[d + (j - b)] = (int)(idflag[j] & ~MAVI_INACTIVE_BIT);
 }
 
-void launch_unpermute2(const LaunchCtx &c, int n, const unsigned int *idflag, const double2 *in, double2 *out) {
-  MAVI_LAUNCH(c, k_unpermute2, nblk(n), TPB, n, idflag, in, out);
+void launch_unpermute2(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const double2 *in, double2 *out) {
+  MAVI_LAUNCH(c, k_unpermute2, nblk(p.n), TPB, 0, p, a.tile_prefix, a.cta_first, a.idflag, in, out);
 }
-void launch_unpermute1(const LaunchCtx &c, int n, const unsigned int *idflag, const double *in, double *out) {
-  MAVI_LAUNCH(c, k_unpermute1, nblk(n), TPB, n, idflag, in, out);
+void launch_unpermute1(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const double *in, double *out) {
+  MAVI_LAUNCH(c, k_unpermute1, nblk(p.n), TPB, 0, p, a.tile_prefix, a.cta_first, a.idflag, in, out);
 }
-void launch_unpermute_cells(const LaunchCtx &c, int n, int num_cells, const unsigned int *idflag, const int *cell, int *out) {
-  MAVI_LAUNCH(c, k_unpermute_cells, nblk(n), TPB, n, num_cells, idflag, cell, out);
+void launch_unpermute_cells(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int *out) {
+  MAVI_LAUNCH(c, k_unpermute_cells, nblk(p.n), TPB, 0, p, a.tile_prefix, a.cta_first, a.idflag, a.cell, out);
 }
-void launch_ids(const LaunchCtx &c, int n, const unsigned int *idflag, int *out) {
-  MAVI_LAUNCH(c, k_ids, nblk(n), TPB, n, idflag, out);
+void launch_cell_counts(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int *out) {
+  MAVI_LAUNCH(c, k_cell_counts, nblk(p.num_cells), TPB, 0, p, a.tstart, out);
 }
-void launch_init_ids(const LaunchCtx &c, int n, const unsigned char *mask, unsigned int *idflag, int *cell, int num_cells) {
-  MAVI_LAUNCH(c, k_init_ids, nblk(n), TPB, n, mask, idflag, cell, num_cells);
-}
-void launch_check_inside(const LaunchCtx &c, const DevParams &p, const double2 *pos, const unsigned int *idflag, int *flags) {
-  MAVI_LAUNCH(c, k_check_inside, nblk(p.n), TPB, p, pos, idflag, flags);
+void launch_ids_in_cell_order(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int *out) {
+  // cell populations -> exclusive scan (count[] is free between builds; re-zeroed by the next build)
+  MAVI_LAUNCH(c, k_cell_counts, nblk(p.num_cells), TPB, 0, p, a.tstart, a.perm);
+  launch_exclusive_scan(c, a.perm, a.count, a.scan_partials, p.num_cells);
+  MAVI_LAUNCH(c, k_ids_in_cell_order, nblk(p.num_cells), TPB, 0, p, a.tstart, a.count, a.idflag, out);
 }
 
 }  // namespace mavi

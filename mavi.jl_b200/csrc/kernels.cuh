@@ -4,26 +4,50 @@
 
 namespace mavi {
 
-// Device arrays of one handle.  Physical order is "sorted by cell, ascending original id inside a cell"
-// (the reference's chunk fill order, src/chunks.jl:153-155); `idflag[k]` is the original id of slot k
-// (bit 31 set for inactive particles, which live in the pseudo-cell `num_cells` at the tail).
+constexpr int TPB = 256;  // threads per block of every rank-mapped kernel (cta_first[] is indexed by rank / TPB)
+
+// Device arrays of one handle.
+//
+// Particle state lives in SLOTS.  With chunks, slots are grouped in padded tiles (see DevParams): tile t owns slots
+// [t*cap, (t+1)*cap) and keeps its particles sorted by (cell, original id) in the prefix — the reference's chunk fill
+// order (src/chunks.jl:153-155) — so update_chunks! is an O(#movers) repair of the few tiles a particle left or
+// entered instead of a global re-sort.  Inactive particles (never binned by the reference) live in a tail region.
+// Kernels run over RANKS 0..n-1 (dense) and map rank -> slot through tile_prefix[] / cta_first[].
 struct DevArrays {
-  double2 *pos[2];      // ping-pong: pos[cur] is the current state
-  double2 *vel[2];      // SecondLawState velocities (ping-pong for the re-sort)
-  double *ang[2];       // SelfPropelledState pol_angle (ping-pong for the re-sort)
-  unsigned int *idflag[2];
-  int *cell[2];         // cell of each sorted slot
+  // slot-indexed state
+  double2 *pos[2];      // ping-pong: pos[0] is the current state
+  double2 *vel;         // SecondLawState velocities
+  double *ang;          // SelfPropelledState pol_angle
+  unsigned int *idflag; // original id of the particle in the slot (bit 31: inactive)
+  int *cell;            // cell the particle is binned in
   double2 *force;       // F (get_forces)
-  double2 *force_old;   // F1 of the Verlet step / re-sort scratch for forces
-  int *cell_new;        // fresh cell ids before the re-sort
-  int *perm;            // scatter result: slot -> source slot
-  int *count;           // [num_cells+2] histogram / scatter cursors
-  int *start;           // [num_cells+2] exclusive scan of count
-  int *scan_partials;   // block sums of the scan
-  int *flags;           // [0] error bits, [1] #particles that left their sorted cell, [2] big-drift guard, [3] #position fix-ups
+  double2 *force_old;   // F1 of the Verlet step
+  // staging in dense rank order (upload, downloads, full rebuilds)
+  double2 *st_pos, *st_vel, *st_force;
+  double *st_ang;
+  unsigned int *st_id;
+  int *st_cell;
+  // tile bookkeeping
+  int *tstart;          // [nt*(MAVI_TR+1)]
+  int *tile_prefix;     // [nt+2] exclusive scan of the tile populations
+  int *cta_first;       // [n/TPB+2] tile holding rank b*TPB
+  int *count;           // [num_cells+2] histogram scratch of full builds
+  int *perm;            // [ns+nt+2] scatter scratch / int scratch
+  int *scan_partials;
+  // incremental repair
+  int *tile_dirty;      // [nt] 0/1
+  int *dirty_list;      // [nt] tiles to repair this step
+  int *inbox_cnt;       // [nt] particles arriving from other tiles
+  int *inbox;           // [nt*inbox_cap] -> index into the mover list
+  int *mv_src;          // [mv_cap] source slot of an inter-tile mover
+  double2 *mv_pos, *mv_second, *mv_force;
+  unsigned int *mv_id;
+  int *mv_cell;
+  // control
+  int *flags;           // see FLAG_* in common.cuh
   int *fix_idx;         // sparse list of slots whose position walls! changed in pass B
   double2 *fix_pos;
-  double *reduce_buf;   // block partials of the energy reductions
+  double *reduce_buf;
 };
 
 struct LaunchCtx {
@@ -31,31 +55,32 @@ struct LaunchCtx {
   long long *launches;  // incremented per kernel launch
 };
 
-// binning / counting sort
-void launch_cell_index(const LaunchCtx &c, const DevParams &p, const double2 *pos, const unsigned int *idflag,
-                       const int *cell_old, int *cell_new, int *count, int *flags);
+// full build of the tile layout from the staging arrays (upload, mavi_bin, overflow fallback)
+void launch_check_inside(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
+void launch_build_tiles(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel);
+// dense copy of the current state into staging (rank order)
+void launch_compact_to_staging(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel);
+void launch_init_staging_ids(const LaunchCtx &c, int n, const unsigned char *mask, unsigned int *st_id);
+// incremental update_chunks!: repair the tiles touched by this step's movers, then refresh the rank maps
+void launch_repair_tiles(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel);
 void launch_exclusive_scan(const LaunchCtx &c, const int *in, int *out, int *partials, int n);
-void launch_scatter(const LaunchCtx &c, const DevParams &p, const int *cell_new, const int *start, int *count, int *perm);
-void launch_gather(const LaunchCtx &c, const DevParams &p, const int *perm, const int *cell_new, const int *start,
-                   const DevArrays &a, int src, int dst, bool second_is_vel, bool has_second, bool with_forces);
 
-// force + integrate passes (cell list)
-void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int cur, bool with_wall_forces);
-void launch_newton_a(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int cur);
-void launch_newton_b(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int cur);
-void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int cur, const double *noise,
+// force + integrate passes
+void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool with_wall_forces);
+void launch_newton_a(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
+void launch_newton_b(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
+void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const double *noise,
                            unsigned long long step);
 
 // quantities
-void launch_kinetic_energy(const LaunchCtx &c, const DevParams &p, const double2 *vel, double *partials, double *out);
-void launch_potential_energy(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int cur, int mode, double *out);
+void launch_kinetic_energy(const LaunchCtx &c, const DevParams &p, const DevArrays &a, double *out);
+void launch_potential_energy(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int mode, double *out);
 
-// un-permute helpers for downloads: out[id[k]] = in[k]
-void launch_unpermute2(const LaunchCtx &c, int n, const unsigned int *idflag, const double2 *in, double2 *out);
-void launch_unpermute1(const LaunchCtx &c, int n, const unsigned int *idflag, const double *in, double *out);
-void launch_unpermute_cells(const LaunchCtx &c, int n, int num_cells, const unsigned int *idflag, const int *cell, int *out);
-void launch_ids(const LaunchCtx &c, int n, const unsigned int *idflag, int *out);
-void launch_init_ids(const LaunchCtx &c, int n, const unsigned char *mask, unsigned int *idflag, int *cell, int num_cells);
-void launch_check_inside(const LaunchCtx &c, const DevParams &p, const double2 *pos, const unsigned int *idflag, int *flags);
+// downloads (un-permute to original ids)
+void launch_unpermute2(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const double2 *in, double2 *out);
+void launch_unpermute1(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const double *in, double *out);
+void launch_unpermute_cells(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int *out);
+void launch_cell_counts(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int *out);
+void launch_ids_in_cell_order(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int *out);
 
 }  // namespace mavi

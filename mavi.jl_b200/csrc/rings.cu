@@ -12,4 +12,8 @@ int rings_upload_finish(Handle *h) { return unsupported(h); }
 int rings_step(Handle *h, const double *) { return unsupported(h); }
 int rings_calc_forces(Handle *h) { return unsupported(h); }
 int rings_download_info(Handle *h, void *, void *, void *) { return unsupported(h); }
+int rings_download_state(Handle *h, void *, void *) { return unsupported(h); }
+int rings_download_forces(Handle *h, void *) { return unsupported(h); }
+int rings_bin(Handle *h) { return unsupported(h); }
+int rings_download_cells(Handle *h, int *, int *, int *, int *) { return unsupported(h); }
 }  // namespace mavi
