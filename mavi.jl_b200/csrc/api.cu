@@ -209,6 +209,8 @@ static int validate_and_lower(Handle *h, const MaviParams *mp) {
 }
 
 // magic number for x / d, valid for 0 <= x < 2^31 (round-up method with a 32-bit multiplier)
+static void magic_div(unsigned int d, unsigned int *mul, unsigned int *shr);
+void mavi_magic_div(unsigned int d, unsigned int *mul, unsigned int *shr) { magic_div(d, mul, shr); }
 static void magic_div(unsigned int d, unsigned int *mul, unsigned int *shr) {
   if (d <= 1) { *mul = 0; *shr = 0; return; }  // d == 1: identity (fastdiv special-cases mul == 0)
   unsigned int l = 0;

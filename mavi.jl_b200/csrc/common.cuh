@@ -31,7 +31,7 @@ struct DevRings {
   int num_rings;
   const double *p0, *relax_time, *vo, *mobility, *rot_diff, *k_area, *k_spring, *l_spring;
   const int *num_particles;
-  const double *interaction;  // [t1][t2][6]: k_rep,k_atr,dist_eq,dist_max, cut2 (exact r2 threshold), 1/dist_eq
+  const double *interaction;  // [t1][t2][7]: k_rep,k_atr,dist_eq,dist_max, cut2, eq2_lo (exact r2 thresholds), 1/dist_eq
   const int *types;           // 0-based per ring, or nullptr
 };
 

@@ -13,9 +13,7 @@ struct RingsArrays {
   double2 *cont_pos = nullptr;  // continuos_pos as of the last unwrap
   double *areas = nullptr;
   double2 *cms = nullptr;       // info.cms (lags one step, src/rings/integration.jl:523)
-  double2 *cms_next = nullptr;  // centre of mass of the last unwrap -> becomes cms at the next update_cms!
-  int *types0 = nullptr;        // 0-based ring types
-  double *inter6 = nullptr;
+  double *pol = nullptr;        // state.pol, one angle per ring
 };
 
 struct Handle {
@@ -26,6 +24,7 @@ struct Handle {
   int flags_cfg = 0;
   cudaStream_t stream = nullptr;
   SecondKind second_kind = SECOND_VEL;
+  int rings_n_active = 0;  // active particle slots of a RingsState
   size_t ns = 0;  // number of particle slots (tiles * cap + inactive tail)
   int *flags_host = nullptr;  // pinned mirror of a.flags[0..3]
   bool prof = false;
@@ -48,6 +47,9 @@ struct Handle {
   int rebuild_from_current();
   int step_once(const double *noise_dev);
 };
+
+// api.cu
+void mavi_magic_div(unsigned int d, unsigned int *mul, unsigned int *shr);
 
 // rings.cu
 int rings_lower(Handle *h, const MaviParams *mp);

@@ -298,6 +298,35 @@ void launch_build_tiles(const LaunchCtx &c, const DevParams &p, const DevArrays 
   refresh_rank_maps(c, p, a);
 }
 
+
+// ---- index-only tiles (Mavi.Rings): the state stays ring-ordered; only particle INDICES are binned -----------------
+// after the scatter every cell's slot range of perm[] is sorted ascending (= ascending ids, src/chunks.jl:153-155)
+__global__ void k_sort_perm_cells(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
+                                  int *__restrict__ perm, const int *__restrict__ flags) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.num_cells || flags[FLAG_OVERFLOW]) return;
+  const int col = div_rows(p, c), row = c - col * p.num_rows;
+  const int q = tq_of(p, col, row);
+  const int b = tstart[q], e = tstart[q + 1];
+  for (int i = b + 1; i < e; i++) {
+    const int v = perm[i];
+    int j = i - 1;
+    while (j >= b && perm[j] > v) {
+      perm[j + 1] = perm[j];
+      --j;
+    }
+    perm[j + 1] = v;
+  }
+}
+
+void launch_build_index_tiles(const LaunchCtx &c, const DevParams &p, const double2 *pos, const unsigned int *idflag,
+                              int *cell_out, int *count, int *tstart, int *perm, int *flags) {
+  MAVI_LAUNCH(c, k_build_cell_index, nblk(p.n), TPB, 0, p, pos, idflag, cell_out, count, flags);
+  MAVI_LAUNCH(c, k_build_layout, nblk(p.nt), TPB, 0, p, count, tstart, flags);
+  MAVI_LAUNCH(c, k_build_scatter, nblk(p.n), TPB, 0, p, cell_out, tstart, count, perm, flags);
+  MAVI_LAUNCH(c, k_sort_perm_cells, nblk(p.num_cells), TPB, 0, p, tstart, perm, flags);
+}
+
 // dense copy of the current state into the staging arrays, in rank order
 __global__ void k_compact(const __grid_constant__ DevParams p, const int *__restrict__ tile_prefix,
                           const int *__restrict__ cta_first, const double2 *__restrict__ pos,

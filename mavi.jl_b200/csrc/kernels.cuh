@@ -58,6 +58,9 @@ struct LaunchCtx {
 // full build of the tile layout from the staging arrays (upload, mavi_bin, overflow fallback)
 void launch_check_inside(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
 void launch_build_tiles(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel);
+// Mavi.Rings: bin particle indices only (perm[slot] = particle index, ascending inside every cell)
+void launch_build_index_tiles(const LaunchCtx &c, const DevParams &p, const double2 *pos, const unsigned int *idflag,
+                              int *cell_out, int *count, int *tstart, int *perm, int *flags);
 // dense copy of the current state into staging (rank order)
 void launch_compact_to_staging(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel);
 void launch_init_staging_ids(const LaunchCtx &c, int n, const unsigned char *mask, unsigned int *st_id);

@@ -1,19 +1,536 @@
-// rings.cu — Mavi.Rings on the device (placeholder until the ring kernels land).
+// rings.cu — Mavi.Rings on the device (reference: src/rings/integration.jl, src/rings/rings.jl, src/rings/states.jl).
+//
+// The ring state stays RING-ORDERED (scalar idx = ring*n_max + p, src/rings/states.jl:137-139) so that one warp owns one
+// ring; only particle indices are binned (index tiles) for the pair pass.  Per step (src/rings/integration.jl:522-543):
+//   k_rings_pair : calc_forces! with the Rings pair law (:32-77) + calc_walls_forces!          (thread per particle)
+//   k_rings_ring : update_cms! -> update_continuos_pos! -> calc_area -> springs -> area_forces! -> update! -> walls!
+//                                                                                              (warp per ring)
+#include <cmath>
+#include <cstring>
+#include <vector>
+
 #include "handle.cuh"
+#include "walls.cuh"
 
 namespace mavi {
-static int unsupported(Handle *h) {
-  h->set_error("Mavi.Rings kernels are not built in this version");
-  return MAVI_ERR_UNSUPPORTED;
+
+#define RINGS_TRY(h, expr)                                                                              \
+  do {                                                                                                  \
+    cudaError_t e_ = (expr);                                                                            \
+    if (e_ != cudaSuccess) {                                                                            \
+      (h)->set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, __LINE__, #expr); \
+      return MAVI_ERR_CUDA;                                                                             \
+    }                                                                                                   \
+  } while (0)
+
+#define RINGS_LAUNCH(h, kernel, grid, block, ...)                 \
+  do {                                                            \
+    kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);     \
+    (h)->launches++;                                              \
+  } while (0)
+
+constexpr int RING_NMAX = 128;  // particles per ring the warp kernel stages in shared memory
+constexpr int RING_WARPS = 4;
+
+__device__ __forceinline__ int ring_type(const DevRings &r, int ring) { return r.types ? r.types[ring] : 0; }
+
+// idflag for ring-ordered slots: padding slots of shorter ring types are inactive (FixRingsIds, src/rings/states.jl:45-61)
+__global__ void k_rings_ids(const __grid_constant__ DevParams p, unsigned int *__restrict__ idflag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  const int ring = i / p.rings.n_max, q = i - ring * p.rings.n_max;
+  const int np = p.rings.num_particles[ring_type(p.rings, ring)];
+  idflag[i] = (unsigned int)i | (q < np ? 0u : MAVI_INACTIVE_BIT);
 }
-int rings_lower(Handle *h, const MaviParams *) { return unsupported(h); }
-int rings_allocate(Handle *h) { return unsupported(h); }
-int rings_upload_finish(Handle *h) { return unsupported(h); }
-int rings_step(Handle *h, const double *) { return unsupported(h); }
-int rings_calc_forces(Handle *h) { return unsupported(h); }
-int rings_download_info(Handle *h, void *, void *, void *) { return unsupported(h); }
-int rings_download_state(Handle *h, void *, void *) { return unsupported(h); }
-int rings_download_forces(Handle *h, void *) { return unsupported(h); }
-int rings_bin(Handle *h) { return unsupported(h); }
-int rings_download_cells(Handle *h, int *, int *, int *, int *) { return unsupported(h); }
+
+// calc_interaction + calc_interaction_force (src/rings/integration.jl:32-77) summed over the stencil, + wall forces
+template <bool PER>
+__global__ void __launch_bounds__(TPB) k_rings_pair(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
+                                                    const int *__restrict__ perm, const int *__restrict__ cell,
+                                                    const unsigned int *__restrict__ idflag,
+                                                    const double2 *__restrict__ pos, double2 *__restrict__ fpair,
+                                                    int with_walls) {
+  extern __shared__ double s_inter[];  // [num_types^2][7]
+  const DevRings &R = p.rings;
+  for (int t = threadIdx.x; t < R.num_types * R.num_types * 7; t += blockDim.x) s_inter[t] = R.interaction[t];
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  double fx = 0.0, fy = 0.0;
+  if (!(idflag[i] & MAVI_INACTIVE_BIT)) {
+    const int ring = i / R.n_max;
+    const int ti = ring_type(R, ring);
+    const int np = R.num_particles[ti];
+    const double2 ri = pos[i];
+    auto visit = [&](int j) {
+      const double2 rj = __ldg(pos + j);
+      const double dx = min_image<PER>(ri.x - rj.x, p.half[0], p.size[0]);
+      const double dy = min_image<PER>(ri.y - rj.y, p.half[1], p.size[1]);
+      const double r2 = dist2_exact(dx, dy);
+      const int rj_ring = j / R.n_max;
+      const double *ic = s_inter + 7 * (ti * R.num_types + ring_type(R, rj_ring));
+      if (r2 > ic[4]) return;  // dist > dist_max
+      const bool same = rj_ring == ring;
+      if (same) {
+        const int diff = i > j ? i - j : j - i;
+        if (diff == 1 || diff == np - 1) return;  // bonded neighbours inside the ring
+      }
+      const double k = (r2 < ic[5]) ? ic[0] : (same ? 0.0 : ic[1]);  // no intra-ring attraction
+      const double c = k * (rsqrt(r2) - ic[6]);
+      fx = fma(c, dx, fx);
+      fy = fma(c, dy, fy);
+    };
+    if (p.num_cells == 0) {
+      // chunks === nothing: all pairs over the active ids (src/integration.jl:197-224)
+      for (int j = 0; j < p.n; j++)
+        if (j != i && !(idflag[j] & MAVI_INACTIVE_BIT)) visit(j);
+    } else {
+      for_each_neighbor(p, tstart, cell[i], -1, [&](int s) {
+        const int j = __ldg(perm + s);
+        if (j != i) visit(j);
+      });
+    }
+    if (with_walls && p.has_force_walls) wall_forces(p, ri.x, ri.y, fx, fy);
+  }
+  fpair[i] = make_double2(fx, fy);
+}
+
+// One warp per ring.  MODE 0: forces! only (constructor priming / mavi_calc_forces); MODE 1: full step.
+template <bool PER, int MODE>
+__global__ void __launch_bounds__(RING_WARPS * 32) k_rings_ring(
+    const __grid_constant__ DevParams p, double2 *__restrict__ pos, double *__restrict__ pol,
+    const double2 *__restrict__ fpair, double2 *__restrict__ force, double2 *__restrict__ cont_pos,
+    double *__restrict__ areas, double2 *__restrict__ cms, const double *__restrict__ noise, unsigned long long step,
+    int prime_cms) {
+  __shared__ double2 s_pos[RING_WARPS][RING_NMAX];
+  __shared__ double2 s_cont[RING_WARPS][RING_NMAX];
+  __shared__ double2 s_vel[RING_WARPS][RING_NMAX];
+  const DevRings &R = p.rings;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int ring = blockIdx.x * RING_WARPS + w;
+  if (ring >= R.num_rings) return;
+  const int t = ring_type(R, ring);
+  const int np = R.num_particles[t];
+  const int base = ring * R.n_max;
+  double2 *sp = s_pos[w], *sc = s_cont[w], *sv = s_vel[w];
+  for (int i = lane; i < R.n_max; i += 32) sp[i] = pos[base + i];
+  __syncwarp();
+  // ---- update_cms! (src/rings/integration.jl:366-372) runs FIRST in step!: it still sees last step's continuos_pos
+  if (MODE == 1 && lane == 0) {
+    double sx, sy;
+    if (PER) { sx = cont_pos[base].x; sy = cont_pos[base].y; }
+    else { sx = sp[0].x; sy = sp[0].y; }
+    for (int i = 1; i < np; i++) {
+      const double2 c = PER ? cont_pos[base + i] : sp[i];
+      sx += c.x;
+      sy += c.y;
+    }
+    cms[ring] = make_double2(sx / np, sy / np);
+  }
+  __syncwarp();
+  // ---- update_continuos_pos! (:118-138): sequential unwrap, same accumulation order as the reference
+  if (PER) {
+    if (lane == 0) {
+      sc[0] = sp[0];
+      for (int i = 1; i < np; i++) {
+        const double dx = min_image<true>(sp[i].x - sp[i - 1].x, p.half[0], p.size[0]);
+        const double dy = min_image<true>(sp[i].y - sp[i - 1].y, p.half[1], p.size[1]);
+        sc[i] = make_double2(sc[i - 1].x + dx, sc[i - 1].y + dy);
+      }
+      for (int i = np; i < R.n_max; i++) sc[i] = sp[i];  // continuos_pos[:, ring] .= rings_pos[:, ring] first
+    }
+    __syncwarp();
+    for (int i = lane; i < R.n_max; i += 32) cont_pos[base + i] = sc[i];
+  } else {
+    for (int i = lane; i < R.n_max; i += 32) sc[i] = sp[i];
+    __syncwarp();
+  }
+  // ---- calc_area (:103-116), shoelace, sequential
+  double area = 0.0;
+  if (lane == 0) {
+    for (int i = 0; i < np - 1; i++) area += sc[i].x * sc[i + 1].y - sc[i].y * sc[i + 1].x;
+    area += sc[np - 1].x * sc[0].y - sc[np - 1].y * sc[0].x;
+    area = area / 2.0;
+    areas[ring] = area;
+    if (MODE == 0 && prime_cms) {  // constructor: update_cms! right after the first unwrap (src/rings/rings.jl:280-283)
+      double sx = sc[0].x, sy = sc[0].y;
+      for (int i = 1; i < np; i++) { sx += sc[i].x; sy += sc[i].y; }
+      cms[ring] = make_double2(sx / np, sy / np);
+    }
+  }
+  area = __shfl_sync(0xffffffffu, area, 0);
+  // ---- forces! (:197-226): pair forces + springs (:79-97) + area_forces! (:140-195)
+  const double k_spring = R.k_spring[t], l_spring = R.l_spring[t];
+  const double k_area = R.k_area[t], p0 = R.p0[t];
+  const double a0s = np * l_spring / p0;
+  const double fmod_area = k_area * (area - a0s * a0s);
+  const double vo = R.vo[t], mu = R.mobility[t];
+  const double theta = pol[ring];
+  double sn, cs;
+  sincos(theta, &sn, &cs);
+  auto spring = [&](int a, int b, double &ox, double &oy) {  // springs_force(p1 = a, p2 = b)
+    const double dx = min_image<PER>(sp[a].x - sp[b].x, p.half[0], p.size[0]);
+    const double dy = min_image<PER>(sp[a].y - sp[b].y, p.half[1], p.size[1]);
+    const double dist = sqrt(dx * dx + dy * dy);
+    const double c = (-k_spring * (dist - l_spring)) / dist;
+    ox = c * dx;
+    oy = c * dy;
+  };
+  for (int i = lane; i < np; i += 32) {
+    const int nxt = (i == np - 1) ? 0 : i + 1, prv = (i == 0) ? np - 1 : i - 1;
+    double2 F = fpair[base + i];
+    double ax, ay, bx, by;
+    spring(i, nxt, ax, ay);  // spring i: +f on its first particle
+    spring(prv, i, bx, by);  // spring i-1: -f on its second particle
+    F.x += ax; F.y += ay;
+    F.x -= bx; F.y -= by;
+    const double dx = min_image<PER>(sp[nxt].x - sp[prv].x, p.half[0], p.size[0]);
+    const double dy = min_image<PER>(sp[nxt].y - sp[prv].y, p.half[1], p.size[1]);
+    F.x -= fmod_area * (dy / 2);
+    F.y -= fmod_area * (-dx / 2);
+    force[base + i] = F;
+    if (MODE == 1) {
+      // update! (:300-351): overdamped active motion
+      const double vx = vo * cs + mu * F.x, vy = vo * sn + mu * F.y;
+      sv[i] = make_double2(vx, vy);
+      double x = sp[i].x + vx * p.dt, y = sp[i].y + vy * p.dt;
+      double dummy_vx = 0.0, dummy_vy = 0.0;
+      const double pr = R.interaction[7 * (t * R.num_types + t) + 2] / 2.0;  // get_particle_radius of the ring type
+      apply_walls<false>(p, x, y, dummy_vx, dummy_vy, pr);  // walls!(system), generic walls over the active ids
+      pos[base + i] = make_double2(x, y);
+    }
+  }
+  for (int i = np + lane; i < R.n_max; i += 32) force[base + i] = make_double2(0.0, 0.0);
+  if (MODE == 1) {
+    __syncwarp();
+    if (lane == 0) {
+      double vcx = 0.0, vcy = 0.0;
+      for (int i = 0; i < np; i++) { vcx += sv[i].x; vcy += sv[i].y; }
+      vcx /= np;
+      vcy /= np;
+      const double speed = sqrt(vcx * vcx + vcy * vcy);
+      double cross_prod = 0.0;
+      if (speed != 0.0) {
+        cross_prod = (cs * vcy - sn * vcx) / speed;
+        if (fabs(cross_prod) > 1.0) cross_prod = sign_d(cross_prod);
+      }
+      const double drot = R.rot_diff[t];
+      double nz = 0.0;
+      if (drot != 0.0)
+        nz = (p.rng_mode == MAVI_RNG_HOST_NOISE) ? (noise ? noise[ring] : 0.0) : philox_normal(p.seed, (unsigned int)ring, step);
+      pol[ring] = theta + (1.0 / R.relax_time[t] * asin(cross_prod) * p.dt + sqrt(2.0 * drot * p.dt) * nz);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+static int up(Handle *h, const T **dst, const T *src, size_t n) {
+  T *d = nullptr;
+  if (cudaMalloc((void **)&d, (n ? n : 1) * sizeof(T)) != cudaSuccess) {
+    h->set_error("cudaMalloc failed (rings parameters)");
+    return MAVI_ERR_CUDA;
+  }
+  h->allocs.push_back((void *)d);
+  if (n && cudaMemcpy(d, src, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+    h->set_error("cudaMemcpy failed (rings parameters)");
+    return MAVI_ERR_CUDA;
+  }
+  *dst = d;
+  return MAVI_OK;
+}
+
+static double sqrt_le_thr(double d) {
+  double x = d * d;
+  while (std::sqrt(x) <= d) x = std::nextafter(x, INFINITY);
+  while (std::sqrt(x) > d) x = std::nextafter(x, -INFINITY);
+  return x;
+}
+static double sqrt_ge_thr(double d) {
+  double x = d * d;
+  while (std::sqrt(x) >= d && x > 0) x = std::nextafter(x, -INFINITY);
+  while (std::sqrt(x) < d) x = std::nextafter(x, INFINITY);
+  return x;
+}
+
+int rings_lower(Handle *h, const MaviParams *mp) {
+  const MaviRingsParams *r = mp->rings;
+  if (!r || r->num_types < 1 || r->n_max < 1 || r->num_rings < 0 || r->num_rings * r->n_max != mp->n) {
+    h->set_error("bad MaviRingsParams (n must equal num_rings * n_max)");
+    return MAVI_ERR_BAD_PARAMS;
+  }
+  if (r->n_max > RING_NMAX) {
+    h->set_error("rings with more than %d particles are not supported by the warp kernel", RING_NMAX);
+    return MAVI_ERR_UNSUPPORTED;
+  }
+  const int nt = r->num_types;
+  for (int t = 0; t < nt; t++)
+    if (r->num_particles[t] < 3 || r->num_particles[t] > r->n_max) {
+      h->set_error("ring type %d: num_particles must be in [3, n_max]", t + 1);
+      return MAVI_ERR_BAD_PARAMS;
+    }
+  std::vector<double> inter((size_t)nt * nt * 7);
+  for (int a = 0; a < nt; a++)
+    for (int b = 0; b < nt; b++) {
+      const double *s = r->interaction + 4 * (a * nt + b), *st = r->interaction + 4 * (b * nt + a);
+      for (int q = 0; q < 4; q++)
+        if (s[q] != st[q]) {
+          h->set_error("InteractionMatrix must be symmetric: the reference applies +f/-f of ONE evaluation to both particles");
+          return MAVI_ERR_UNSUPPORTED;
+        }
+      double *d = inter.data() + 7 * (a * nt + b);
+      d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+      d[4] = sqrt_le_thr(s[3]);  // dist > dist_max  <=>  r2 > d[4]
+      d[5] = sqrt_ge_thr(s[2]);  // dist < dist_eq   <=>  r2 < d[5]
+      d[6] = 1.0 / s[2];
+    }
+  DevRings &R = h->p.rings;
+  R.num_types = nt;
+  R.n_max = r->n_max;
+  R.num_rings = (int)r->num_rings;
+  int st;
+  if ((st = up(h, &R.p0, r->p0, nt)) || (st = up(h, &R.relax_time, r->relax_time, nt)) || (st = up(h, &R.vo, r->vo, nt)) ||
+      (st = up(h, &R.mobility, r->mobility, nt)) || (st = up(h, &R.rot_diff, r->rot_diff, nt)) ||
+      (st = up(h, &R.k_area, r->k_area, nt)) || (st = up(h, &R.k_spring, r->k_spring, nt)) ||
+      (st = up(h, &R.l_spring, r->l_spring, nt)) || (st = up(h, &R.num_particles, r->num_particles, nt)) ||
+      (st = up(h, &R.interaction, inter.data(), inter.size())))
+    return st;
+  R.types = nullptr;
+  long long n_active = 0;
+  if (r->types) {
+    std::vector<int> t0((size_t)r->num_rings);
+    for (long long i = 0; i < r->num_rings; i++) {
+      if (r->types[i] < 1 || r->types[i] > nt) {
+        h->set_error("ring %lld has type %d outside 1..%d", i + 1, r->types[i], nt);
+        return MAVI_ERR_BAD_PARAMS;
+      }
+      t0[i] = r->types[i] - 1;
+      n_active += r->num_particles[t0[i]];
+    }
+    if ((st = up(h, &R.types, t0.data(), t0.size()))) return st;
+  } else {
+    n_active = r->num_rings * (long long)r->num_particles[0];
+  }
+  h->rings_n_active = (int)n_active;
+  return MAVI_OK;
+}
+
+static int rings_alloc_tiles(Handle *h, int cap);
+
+int rings_allocate(Handle *h) {
+  DevArrays &a = h->a;
+  RingsArrays &r = h->r;
+  const size_t n = (size_t)h->p.n, nr = (size_t)h->p.rings.num_rings;
+  auto al = [&](void **ptr, size_t bytes) -> int {
+    if (cudaMalloc(ptr, bytes ? bytes : 16) != cudaSuccess) {
+      h->set_error("cudaMalloc failed (rings state)");
+      return MAVI_ERR_CUDA;
+    }
+    h->allocs.push_back(*ptr);
+    return MAVI_OK;
+  };
+  int st;
+  if ((st = al((void **)&a.pos[0], n * sizeof(double2))) || (st = al((void **)&a.force, n * sizeof(double2))) ||
+      (st = al((void **)&a.force_old, n * sizeof(double2))) || (st = al((void **)&a.idflag, n * sizeof(unsigned int))) ||
+      (st = al((void **)&a.cell, n * sizeof(int))) || (st = al((void **)&r.cont_pos, n * sizeof(double2))) ||
+      (st = al((void **)&r.areas, nr * sizeof(double))) || (st = al((void **)&r.cms, nr * sizeof(double2))) ||
+      (st = al((void **)&r.pol, nr * sizeof(double))))
+    return st;
+  h->p.n_count = h->rings_n_active;
+  h->ns = n;
+  RINGS_TRY(h, cudaMemsetAsync(a.force, 0, n * sizeof(double2), h->stream));
+  RINGS_TRY(h, cudaMemsetAsync(r.cont_pos, 0, n * sizeof(double2), h->stream));
+  if (h->p.num_cells > 0) {
+    const long long ntiles = (long long)h->p.num_cols * ((h->p.num_rows + MAVI_TR - 1) / MAVI_TR);
+    int cap = ((int)std::ceil(2.0 * h->rings_n_active / (double)ntiles + 16.0) + 15) / 16 * 16;
+    return rings_alloc_tiles(h, cap);
+  }
+  return MAVI_OK;
+}
+
+static int rings_alloc_tiles(Handle *h, int cap) {
+  DevParams &p = h->p;
+  DevArrays &a = h->a;
+  void *old[] = {a.tstart, a.perm};
+  for (void *q : old)
+    if (q) {
+      for (auto &x : h->allocs)
+        if (x == q) x = nullptr;
+      cudaFree(q);
+    }
+  p.tpc = (p.num_rows + MAVI_TR - 1) / MAVI_TR;
+  p.nt = p.num_cols * p.tpc;
+  p.cap = cap;
+  p.n_active = 0;
+  p.tail_base = 0;
+  mavi_magic_div((unsigned int)p.num_rows, &p.rows_mul, &p.rows_shr);
+  mavi_magic_div((unsigned int)p.tpc, &p.tpc_mul, &p.tpc_shr);
+  mavi_magic_div((unsigned int)p.num_cols, &p.cols_mul, &p.cols_shr);
+  const size_t slots = (size_t)p.nt * cap;
+  if (slots > 0x7ffffff0ull) {
+    h->set_error("index tiles need too many slots");
+    return MAVI_ERR_BAD_PARAMS;
+  }
+  a.tstart = nullptr;
+  a.perm = nullptr;
+  if (cudaMalloc((void **)&a.tstart, ((size_t)p.nt * (MAVI_TR + 1) + 1) * sizeof(int)) != cudaSuccess ||
+      cudaMalloc((void **)&a.perm, (slots + 2) * sizeof(int)) != cudaSuccess) {
+    h->set_error("cudaMalloc failed (index tiles)");
+    return MAVI_ERR_CUDA;
+  }
+  h->allocs.push_back(a.tstart);
+  h->allocs.push_back(a.perm);
+  return MAVI_OK;
+}
+
+// update_chunks! for Rings (src/rings/integration.jl:18-23): bin the active particle indices
+int rings_bin(Handle *h) {
+  DevParams &p = h->p;
+  DevArrays &a = h->a;
+  if (p.num_cells == 0) return MAVI_OK;
+  if (int st0 = h->pending_out_of_grid()) return st0;
+  for (int attempt = 0; attempt < 8; attempt++) {
+    RINGS_TRY(h, cudaMemsetAsync(a.count, 0, ((size_t)p.num_cells + 2) * sizeof(int), h->stream));
+    RINGS_TRY(h, cudaMemsetAsync(a.flags + 1, 0, (FLAG_COUNT - 1) * sizeof(int), h->stream));
+    launch_build_index_tiles(h->ctx(), p, a.pos[0], a.idflag, a.cell, a.count, a.tstart, a.perm, a.flags);
+    int st = h->check_device_flags();
+    if (st) return st;
+    if (!h->flags_host[FLAG_OVERFLOW]) return MAVI_OK;
+    int cap = ((int)std::ceil(h->flags_host[FLAG_MAXCOUNT] * 1.25 + 8.0) + 15) / 16 * 16;
+    if ((st = rings_alloc_tiles(h, cap))) return st;
+  }
+  h->set_error("index tile capacity did not converge");
+  return MAVI_ERR_CAPACITY;
+}
+
+static void launch_pair(Handle *h, bool with_walls) {
+  const DevParams &p = h->p;
+  DevArrays &a = h->a;
+  const size_t smem = (size_t)p.rings.num_types * p.rings.num_types * 7 * sizeof(double);
+  const int grid = (p.n + TPB - 1) / TPB;
+  if (p.periodic) {
+    k_rings_pair<true><<<grid, TPB, smem, h->stream>>>(p, a.tstart, a.perm, a.cell, a.idflag, a.pos[0], a.force_old, (int)with_walls);
+  } else {
+    k_rings_pair<false><<<grid, TPB, smem, h->stream>>>(p, a.tstart, a.perm, a.cell, a.idflag, a.pos[0], a.force_old, (int)with_walls);
+  }
+  h->launches++;
+}
+
+static void launch_ring(Handle *h, int mode, const double *noise, int prime_cms) {
+  const DevParams &p = h->p;
+  DevArrays &a = h->a;
+  RingsArrays &r = h->r;
+  const int grid = (p.rings.num_rings + RING_WARPS - 1) / RING_WARPS;
+  if (grid == 0) return;
+  const unsigned long long step = (unsigned long long)h->num_steps;
+#define RING_CALL(PER, MODE) \
+  RINGS_LAUNCH(h, (k_rings_ring<PER, MODE>), grid, RING_WARPS * 32, p, a.pos[0], r.pol, a.force_old, a.force, r.cont_pos, r.areas, r.cms, noise, step, prime_cms)
+  if (p.periodic) {
+    if (mode) RING_CALL(true, 1); else RING_CALL(true, 0);
+  } else {
+    if (mode) RING_CALL(false, 1); else RING_CALL(false, 0);
+  }
+#undef RING_CALL
+}
+
+// RingsSystem ctor tail (src/rings/rings.jl:280-288): ids, continuos_pos, cms, chunks, forces!
+int rings_upload_finish(Handle *h) {
+  DevParams &p = h->p;
+  DevArrays &a = h->a;
+  RingsArrays &r = h->r;
+  const size_t n = (size_t)p.n;
+  RINGS_TRY(h, cudaMemcpyAsync(a.pos[0], a.st_pos, n * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream));
+  RINGS_TRY(h, cudaMemcpyAsync(r.pol, a.st_ang, (size_t)p.rings.num_rings * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  RINGS_LAUNCH(h, k_rings_ids, (p.n + TPB - 1) / TPB, TPB, p, a.idflag);
+  RINGS_TRY(h, cudaMemcpyAsync(a.st_id, a.idflag, n * sizeof(unsigned int), cudaMemcpyDeviceToDevice, h->stream));
+  if (p.n_spaces == 1) launch_check_inside(h->ctx(), p, a);
+  int st = h->check_device_flags();
+  if (st) return st;
+  if ((st = rings_bin(h))) return st;
+  launch_pair(h, false);
+  launch_ring(h, 0, nullptr, 1);
+  return h->check_device_flags();
+}
+
+int rings_calc_forces(Handle *h) {
+  int st = rings_bin(h);
+  if (st) return st;
+  launch_pair(h, true);
+  launch_ring(h, 0, nullptr, 0);
+  return h->check_device_flags();
+}
+
+int rings_step(Handle *h, const double *noise_dev) {
+  int st = rings_bin(h);  // update_chunks_all! (after update_cms!, which only reads last step's continuos_pos)
+  if (st) return st;
+  launch_pair(h, true);
+  launch_ring(h, 1, noise_dev, 0);
+  h->num_steps += 1;  // src/rings/integration.jl:541-542
+  h->time += h->p.dt;
+  return h->check_device_flags();
+}
+
+int rings_download_state(Handle *h, void *pos, void *second) {
+  const DevParams &p = h->p;
+  if (pos) RINGS_TRY(h, cudaMemcpyAsync(pos, h->a.pos[0], (size_t)p.n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  if (second) RINGS_TRY(h, cudaMemcpyAsync(second, h->r.pol, (size_t)p.rings.num_rings * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  return h->check_device_flags();
+}
+
+int rings_download_forces(Handle *h, void *forces) {
+  RINGS_TRY(h, cudaMemcpyAsync(forces, h->a.force, (size_t)h->p.n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  return h->check_device_flags();
+}
+
+int rings_download_info(Handle *h, void *areas, void *cms, void *cont_pos) {
+  const DevParams &p = h->p;
+  const size_t nr = (size_t)p.rings.num_rings;
+  if (areas) RINGS_TRY(h, cudaMemcpyAsync(areas, h->r.areas, nr * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (cms) RINGS_TRY(h, cudaMemcpyAsync(cms, h->r.cms, nr * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  if (cont_pos)
+    RINGS_TRY(h, cudaMemcpyAsync(cont_pos, p.periodic ? h->r.cont_pos : h->a.pos[0], (size_t)p.n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  return h->check_device_flags();
+}
+
+// cell_of_particle / counts / CSR lists of the index tiles
+__global__ void k_rings_cells_out(const __grid_constant__ DevParams p, const unsigned int *__restrict__ idflag,
+                                  const int *__restrict__ cell, int *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < p.n) out[i] = (idflag[i] & MAVI_INACTIVE_BIT) ? -1 : cell[i];
+}
+
+int rings_download_cells(Handle *h, int *cell_of_particle, int *counts, int *start, int *ids) {
+  const DevParams &p = h->p;
+  DevArrays &a = h->a;
+  if (cell_of_particle) {
+    RINGS_LAUNCH(h, k_rings_cells_out, (p.n + TPB - 1) / TPB, TPB, p, a.idflag, a.cell, a.st_cell);
+    RINGS_TRY(h, cudaMemcpyAsync(cell_of_particle, a.st_cell, (size_t)p.n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (counts || start || ids) {
+    std::vector<int> ts((size_t)p.nt * (MAVI_TR + 1) + 1), perm;
+    RINGS_TRY(h, cudaMemcpyAsync(ts.data(), a.tstart, ts.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (ids) {
+      perm.resize((size_t)p.nt * p.cap);
+      RINGS_TRY(h, cudaMemcpyAsync(perm.data(), a.perm, perm.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    }
+    RINGS_TRY(h, cudaStreamSynchronize(h->stream));
+    int acc = 0;
+    for (int c = 0; c < p.num_cells; c++) {
+      const int col = c / p.num_rows, row = c - col * p.num_rows;
+      const int tr = row / MAVI_TR;
+      const size_t q = (size_t)(col * p.tpc + tr) * (MAVI_TR + 1) + (row - tr * MAVI_TR);
+      const int b = ts[q], e = ts[q + 1];
+      if (counts) counts[c] = e - b;
+      if (start) start[c] = acc;
+      if (ids)
+        for (int j = b; j < e; j++) ids[acc + (j - b)] = perm[j];
+      acc += e - b;
+    }
+    if (start) start[p.num_cells] = acc;
+  }
+  return h->check_device_flags();
+}
+
 }  // namespace mavi

@@ -69,3 +69,50 @@ def make_oracle(case, threads=1):
     oracle = entry.load_oracle()
     return oracle.OracleSystem(state=case["mk"](), space_cfg=case["space"], dynamic_cfg=case["dyn"],
                                int_cfg=case["int_cfg"], lower=lower, threads=threads)
+
+
+# ---------------------------------------------------------------- Mavi.Rings fixtures (test/tests_rings/rings_utils.jl)
+def rings_case(kind="normal", num_cols=13, num_rows=13, use_chunks=True, seed=31415, rot_diff=None, wall="periodic", pad=0.1):
+    """`create_system_normal` (:27-99) / `create_system_types` (:193-296) with a seeded numpy RNG in place of Julia's
+    MersenneTwister (the reference's golden neighbour lists depend on Julia's RNG streams and cannot be reproduced)."""
+    from mavi_jl_b200.rings import configs as rc
+    from mavi_jl_b200.rings import init_states as ri
+    from mavi_jl_b200.rings.states import RingsState
+
+    rng = np.random.default_rng(seed)
+    if kind == "normal":
+        inter = rc.HarmTruncCfg(k_rep=20, k_atr=4, dist_eq=1, dist_max=1 + 0.2)
+        dyn = rc.RingsCfg(p0=3.5, relax_time=1, vo=1.0, mobility=1, rot_diff=0.05 if rot_diff is None else rot_diff,
+                          k_area=1, k_spring=20, l_spring=1, num_particles=10, interaction_finder=inter)
+        rings_pos, geom = ri.rectangular_grid(num_cols=num_cols, num_rows=num_rows, num_particles=10,
+                                              p_radius=dyn.particle_radius(), pad_x=pad, pad_y=pad)
+        types, num_particles = None, None
+        max_size = inter.dist_max * 1.1
+    else:
+        i1 = rc.HarmTruncCfg(k_rep=13, k_atr=0.1, dist_eq=1, dist_max=1 * 1.1)
+        i2 = rc.HarmTruncCfg(k_rep=13, k_atr=0.1, dist_eq=0.8, dist_max=0.8 * 1.1)
+        pd = i1.dist_eq / 2 + i2.dist_eq / 2
+        ip = rc.HarmTruncCfg(k_rep=13, k_atr=10, dist_eq=pd, dist_max=pd * 1.2)
+        finder = rc.InteractionMatrix([[i1, ip], [ip, i2]])
+        num_particles = [10, 5]
+        dyn = rc.RingsCfg(p0=3.5, relax_time=1, vo=1, mobility=1, rot_diff=0.5 if rot_diff is None else rot_diff, k_area=1,
+                          k_spring=20, l_spring=[i.dist_eq * 0.8 for i in rc.list_self_interactions(finder)],
+                          num_particles=num_particles, interaction_finder=finder)
+        types = rng.integers(1, 3, num_cols * num_rows)
+        rings_pos, geom = ri.rectangular_grid(num_cols=num_cols, num_rows=num_rows, num_particles=num_particles,
+                                              p_radius=[i1.particle_radius(), i2.particle_radius()], types=types,
+                                              pad_x=0.1, pad_y=0.1)
+        max_size = max(i.dist_max for i in rc.list_interactions(finder)) * 1.1
+    pol = ri.random_pol(num_cols * num_rows, rng=rng)
+    wall_t = pkg.PeriodicWalls() if wall == "periodic" else pkg.RigidWalls()
+    space = pkg.SpaceCfg(wall_type=wall_t, geometry_cfg=geom)
+    chunks = pkg.ChunksCfg(int(geom.length // max_size), int(geom.height // max_size)) if use_chunks else None
+    int_cfg = rc.RingsIntCfg(dt=0.01, p_chunks_cfg=chunks, device=pkg.CUDADevice(rng_mode="host_noise"))
+    mk = lambda: RingsState(rings_pos=rings_pos.copy(), pol=pol.copy(), types=None if types is None else types.copy(),  # noqa: E731
+                            num_particles=num_particles)
+    return dict(mk=mk, space=space, dyn=dyn, int_cfg=int_cfg, geom=geom, num_rings=num_cols * num_rows, rng=rng)
+
+
+def make_gpu_rings(case):
+    from mavi_jl_b200.rings.rings import RingsSystem
+    return RingsSystem(state=case["mk"](), space_cfg=case["space"], dynamic_cfg=case["dyn"], int_cfg=case["int_cfg"])

@@ -1,0 +1,167 @@
+"""Mavi.Rings: CPU known-answer / invariant tests of the oracle, and GPU parity tests against it.
+
+The reference's Rings tests (test/tests_rings/) hold (a) equivalence invariants `check_chunks` / `check_threaded` with
+threshold sum |dpos|^2 < 1e-4 after t = 10 (runtests.jl:5-11, tests_general.jl:16-45) — applied here to the oracle and to
+the device path — and (b) golden neighbour-id lists that depend on Julia's MersenneTwister streams (runtests.jl:17-34):
+not reproducible without Julia, and contact lists are a "next" row.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+pkg = H.pkg
+
+
+def _noise(case, steps, seed=5):
+    return np.random.default_rng(seed).standard_normal((steps, case["num_rings"]))
+
+
+# ---------------------------------------------------------------- CPU: oracle
+def test_regular_polygon_area_and_ring_radius(oracle):
+    """create_circle + get_ring_radius (src/rings/init_states.jl:10-25, src/rings/utils.jl:5-7): a regular n-gon of
+    circumradius R has area n/2 R^2 sin(2 pi/n) and side 2*p_radius."""
+    case = H.rings_case("normal", 3, 3, rot_diff=0.0)
+    o = H.make_oracle(case)
+    areas, cms, cont = o.rings_info()
+    from mavi_jl_b200.rings.configs import get_ring_radius
+    n, pr = 10, 0.5
+    R = get_ring_radius(pr, n)
+    assert np.allclose(areas, n / 2 * R * R * math.sin(2 * math.pi / n), rtol=1e-13)
+    st = case["mk"]()
+    side = np.linalg.norm(st.rings_pos[0, 1] - st.rings_pos[0, 0])
+    assert np.isclose(side, 2 * pr, rtol=1e-13)
+    assert np.allclose(cms, st.rings_pos.mean(1), atol=1e-12)
+    assert np.allclose(cont, st.pos)  # nothing wrapped at t = 0
+
+
+def test_isolated_ring_feels_only_the_area_force(oracle):
+    """An isolated regular ring with side == l_spring: springs are at rest, no pair forces, and area_forces!
+    (src/rings/integration.jl:140-195) gives F_i = -k_A (A - A0) * (dr.y, -dr.x)/2 with dr = r_{i+1} - r_{i-1},
+    i.e. modulus k_A |A - A0| * chord/2 along the outward radius when A < A0."""
+    case = H.rings_case("normal", 1, 1, use_chunks=False, rot_diff=0.0, pad=3.0)
+    o = H.make_oracle(case)
+    f = o.get_forces()
+    r0 = case["mk"]().rings_pos[0]
+    area = o.rings_info()[0][0]
+    A0 = (10 * 1.0 / 3.5) ** 2
+    dr = np.roll(r0, -1, 0) - np.roll(r0, 1, 0)
+    want = -1.0 * (area - A0) * np.stack([dr[:, 1], -dr[:, 0]], 1) / 2
+    assert np.abs(want).max() > 0.1
+    assert np.allclose(f, want, rtol=1e-10, atol=1e-12)
+    radial = (r0 - r0.mean(0)) / np.linalg.norm(r0 - r0.mean(0), axis=1)[:, None]
+    assert np.allclose(np.sign(A0 - area) * f / np.linalg.norm(f, axis=1)[:, None], radial, atol=1e-9)
+
+
+@pytest.mark.parametrize("kind", ["normal", "types"])
+def test_rings_chunks_equal_allpairs(oracle, kind):
+    """check_chunks (test/tests_rings/tests_general.jl:16-30): same seed, chunks vs all pairs, threshold 1e-4."""
+    n = 8 if kind == "normal" else 5
+    ca, cb = H.rings_case(kind, n, n, use_chunks=True), H.rings_case(kind, n, n, use_chunks=False)
+    a, b = H.make_oracle(ca), H.make_oracle(cb)
+    noise = _noise(ca, 300)
+    a.step(300, noise)
+    b.step(300, noise)
+    assert ((a.pos() - b.pos()) ** 2).sum() + ((a.second() - b.second()) ** 2).sum() < 1e-4
+    assert np.abs(a.pos() - b.pos()).max() < 1e-9
+
+
+def test_rings_threaded_equals_sequencial(oracle):
+    """check_threaded (test/tests_rings/tests_general.jl:32-45)."""
+    ca = H.rings_case("normal", 8, 8)
+    a, b = H.make_oracle(ca, threads=1), H.make_oracle(ca, threads=3)
+    noise = _noise(ca, 200)
+    a.step(200, noise)
+    b.step(200, noise)
+    assert ((a.pos() - b.pos()) ** 2).sum() < 1e-4
+    assert np.abs(a.pos() - b.pos()).max() < 1e-9
+
+
+def test_rings_cms_lag_one_step(oracle):
+    """update_cms! runs before the unwrap of the current step (src/rings/integration.jl:523-529): after a step, cms is
+    the centre of the PREVIOUS step's continuous positions."""
+    case = H.rings_case("normal", 4, 4, rot_diff=0.0)
+    o = H.make_oracle(case)
+    cont0 = o.rings_info()[2].reshape(16, 10, 2)
+    o.step(1)
+    _, cms1, cont1 = o.rings_info()
+    assert np.allclose(cms1, cont0.mean(1), atol=1e-13)
+    o.step(1)
+    assert np.allclose(o.rings_info()[1], cont1.reshape(16, 10, 2).mean(1), atol=1e-13)
+
+
+# ---------------------------------------------------------------- GPU parity
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,chunks", [("normal", True), ("normal", False), ("types", True), ("types", False)])
+def test_rings_gpu_construction_state(cuda_lib, kind, chunks):
+    """RingsSystem(...) primes continuos_pos, cms, chunks and runs forces! once (src/rings/rings.jl:280-288)."""
+    n = 13 if kind == "normal" else 5
+    case = H.rings_case(kind, n, n, use_chunks=chunks)
+    g, o = H.make_gpu_rings(case), H.make_oracle(case)
+    assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-12
+    for a, b in zip(g.rings_info(), o.rings_info()):
+        assert H.rel_err(a, b) < 1e-13
+    if chunks:
+        cg, ng = g.download_cells()
+        co, no = o.download_cells()
+        assert np.array_equal(cg, co) and np.array_equal(ng, no)
+        sg, ig = g.download_cell_lists()
+        so, io = o.download_cell_lists()
+        assert np.array_equal(sg, so) and np.array_equal(ig, io)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,chunks", [("normal", True), ("normal", False), ("types", True), ("types", False)])
+def test_rings_gpu_trajectory(cuda_lib, kind, chunks):
+    n = 13 if kind == "normal" else 5
+    case = H.rings_case(kind, n, n, use_chunks=chunks)
+    g, o = H.make_gpu_rings(case), H.make_oracle(case)
+    for block in range(4):
+        noise = _noise(case, 25, seed=block)
+        g.step(25, noise)
+        o.step(25, noise)
+        g.sync_to_host()
+        assert np.abs(g.state.pos - o.pos()).max() / case["geom"].length < 1e-12
+        assert np.abs(g.state.pol - o.second()).max() < 1e-11
+        assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-10
+        for a, b in zip(g.rings_info(), o.rings_info()):
+            assert H.rel_err(a, b) < 1e-11
+    assert g.time_info.num_steps == 100
+
+
+@pytest.mark.gpu
+def test_rings_gpu_reference_invariant_t10(cuda_lib):
+    """The reference's own acceptance bar: run to t = 10 (1000 steps, dt = 0.01) and require sum |dpos|^2 < 1e-4
+    between two code paths (test/tests_rings/runtests.jl:5-11) — here device (chunks) vs oracle (all pairs)."""
+    ca, cb = H.rings_case("normal", 13, 13, use_chunks=True), H.rings_case("normal", 13, 13, use_chunks=False)
+    g, o = H.make_gpu_rings(ca), H.make_oracle(cb)
+    noise = _noise(ca, 1000)
+    g.step(1000, noise)
+    o.step(1000, noise)
+    g.sync_to_host()
+    assert ((g.state.pos - o.pos()) ** 2).sum() + ((g.state.pol - o.second()) ** 2).sum() < 1e-4
+
+
+@pytest.mark.gpu
+def test_rings_gpu_philox_runs(cuda_lib):
+    from mavi_jl_b200.rings import configs as rc
+    case = H.rings_case("normal", 13, 13)
+    case["int_cfg"] = rc.RingsIntCfg(dt=0.01, p_chunks_cfg=case["int_cfg"].chunks_cfg, device=pkg.CUDADevice(rng_mode="philox", seed=3))
+    g = H.make_gpu_rings(case)
+    pol0 = g.state.pol.copy()
+    g.step(50)
+    g.sync_to_host()
+    assert np.isfinite(g.state.pos).all() and np.abs(g.state.pol - pol0).max() > 1e-3
+
+
+@pytest.mark.gpu
+def test_rings_asymmetric_matrix_rejected(cuda_lib):
+    from mavi_jl_b200.rings import configs as rc
+    case = H.rings_case("types", 5, 5)
+    m = case["dyn"].interaction_finder.matrix
+    m[0][1] = rc.HarmTruncCfg(k_rep=1, k_atr=1, dist_eq=0.9, dist_max=1.0)
+    with pytest.raises(pkg.MaviError) as e:
+        H.make_gpu_rings(case)
+    assert e.value.status == pkg.capi.ERR_UNSUPPORTED
