@@ -156,6 +156,12 @@ int32_t mavi_download_forces(MaviHandle *h, void *forces);
 /* multi-GPU only: original ids of the particles this rank currently owns, and their count */
 int32_t mavi_local_count(MaviHandle *h, int64_t *n_local);
 int32_t mavi_download_local(MaviHandle *h, int64_t *ids, void *pos, void *second, void *forces);
+/* multi-GPU x-slabs (MaviParams.world > 1, one process per GPU; the reference has no distributed path — it splits the
+ * same loop over cell columns across threads, src/integration.jl:159-194).  Rank 0 makes the NCCL id, the host
+ * broadcasts its 128 bytes to all ranks (MaviParams.nccl_unique_id); every rank uploads the particles whose cell
+ * column it owns (columns are split contiguously, the first num_cols % world ranks get one extra) with global ids. */
+int32_t mavi_nccl_unique_id(void *out128);
+int32_t mavi_upload_local(MaviHandle *h, const int64_t *ids, const void *pos, const void *second, int64_t n_local);
 
 /* ---- the hot path ---------------------------------------------------------------------------
  * mavi_step: nsteps x (newton_step! | szabo_step! | rtp_step!  src/integration.jl:507-535 |

@@ -84,6 +84,8 @@ SIGNATURES = {
     "mavi_download_forces": (C.c_int32, [_H, C.c_void_p]),
     "mavi_local_count": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
     "mavi_download_local": (C.c_int32, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mavi_nccl_unique_id": (C.c_int32, [C.c_void_p]),
+    "mavi_upload_local": (C.c_int32, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "mavi_step": (C.c_int32, [_H, C.c_int64, C.c_void_p]),
     "mavi_calc_forces": (C.c_int32, [_H]),
     "mavi_bin": (C.c_int32, [_H]),

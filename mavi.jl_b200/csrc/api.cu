@@ -77,10 +77,6 @@ static int validate_and_lower(Handle *h, const MaviParams *mp) {
     h->set_error("bad n / n_spaces");
     return MAVI_ERR_BAD_PARAMS;
   }
-  if (mp->world > 1) {
-    h->set_error("multi-GPU slabs are not built in this version");
-    return MAVI_ERR_UNSUPPORTED;
-  }
   memset(&p, 0, sizeof p);
   p.n = (int)mp->n;
   p.n_count = p.n;
@@ -174,6 +170,11 @@ static int validate_and_lower(Handle *h, const MaviParams *mp) {
                        4.0 * p.ch <= p.half[1]) ? 1 : 0;
   }
 
+  if (mp->world > 1) {
+    int st = slab_configure(h, mp);
+    if (st) return st;
+  }
+
   switch (mp->dynamics) {
     case MAVI_DYN_LJ:
       p.lj_sig2 = mp->dyn[0] * mp->dyn[0];
@@ -231,7 +232,9 @@ static void dev_free(Handle *h, void *ptr) {
 static int allocate(Handle *h) {
   const DevParams &p = h->p;
   DevArrays &a = h->a;
-  const size_t n = (size_t)p.n;
+  // slab mode: the owned count changes with migration -> head room in the dense arrays
+  h->n_cap = p.slab ? (int)(p.n * 1.25) + 4096 : p.n;
+  const size_t n = (size_t)h->n_cap;
   int st;
   memset(&a, 0, sizeof a);
   if ((st = dev_alloc(h, &a.st_pos, n))) return st;
@@ -267,28 +270,34 @@ int Handle::alloc_state(int n_active, int cap) {
                  A.mv_second, A.mv_force, A.mv_id, A.mv_cell};
   for (void *q : old) dev_free(this, q);
   p.n_active = p.num_cells > 0 ? n_active : 0;
-  p.n_count = n_active;
+  p.n_count = p.slab ? slab.n_global : n_active;
   if (p.num_cells > 0) {
     p.tpc = (p.num_rows + MAVI_TR - 1) / MAVI_TR;
     p.nt = p.num_cols * p.tpc;
     p.cap = cap;
-    long long slots = (long long)p.nt * cap + (p.n - n_active);
+    long long slots = (long long)p.nt * cap + (p.slab ? 0 : (p.n - n_active));
     if (slots > 0x7ffffff0LL) {
       set_error("tile layout needs %lld slots (> 2^31)", slots);
       return MAVI_ERR_BAD_PARAMS;
     }
     p.tail_base = p.nt * cap;
+    if (!p.slab) {
+      p.gcols = p.num_cols;
+      p.ord_cols = p.num_cols;
+      p.ord_col0 = 0;
+    }
+    p.nt_ord = p.ord_cols * p.tpc;
     magic_div((unsigned int)p.num_rows, &p.rows_mul, &p.rows_shr);
     magic_div((unsigned int)p.tpc, &p.tpc_mul, &p.tpc_shr);
-    magic_div((unsigned int)p.num_cols, &p.cols_mul, &p.cols_shr);
+    magic_div((unsigned int)p.ord_cols, &p.cols_mul, &p.cols_shr);
     p.inbox_cap = 16;
-    p.mv_cap = p.n / 4 > 4096 ? p.n / 4 : 4096;
+    p.mv_cap = n_cap / 4 > 4096 ? n_cap / 4 : 4096;
   } else {
-    p.tpc = p.nt = p.cap = 0;
+    p.tpc = p.nt = p.cap = p.nt_ord = 0;
     p.tail_base = 0;
     p.inbox_cap = p.mv_cap = 0;
   }
-  ns = (size_t)p.tail_base + (size_t)(p.n - p.n_active);
+  ns = (size_t)p.tail_base + (size_t)(p.slab ? 0 : (p.n - p.n_active));
   int st;
   for (int b = 0; b < 2; b++)
     if ((st = dev_alloc(this, &A.pos[b], ns))) return st;
@@ -329,7 +338,7 @@ int Handle::rebuild_from_staging(int n_active) {
   const bool second_is_vel = second_kind == SECOND_VEL;
   int cap = p.cap;
   if (p.num_cells > 0 && (a.pos[0] == nullptr || n_active != p.n_active || cap <= 0)) {
-    const long long ntiles = (long long)p.num_cols * ((p.num_rows + MAVI_TR - 1) / MAVI_TR);
+    const long long ntiles = (long long)(p.slab ? p.num_cols - 2 : p.num_cols) * ((p.num_rows + MAVI_TR - 1) / MAVI_TR);
     cap = round_up16(2.0 * (double)n_active / (double)ntiles + 16.0);
     int st = alloc_state(n_active, cap);
     if (st) return st;
@@ -355,7 +364,7 @@ int Handle::rebuild_from_staging(int n_active) {
     launch_build_tiles(ctx(), p, a, second_is_vel);
     int st = check_device_flags();
     if (st) return st;
-    if (!flags_host[FLAG_OVERFLOW]) return MAVI_OK;
+    if (!flags_host[FLAG_OVERFLOW]) return p.slab ? slab_after_build(this) : MAVI_OK;
     cap = round_up16(flags_host[FLAG_MAXCOUNT] * 1.25 + 8.0);
     if ((st = alloc_state(n_active, cap))) return st;
   }
@@ -407,6 +416,7 @@ int Handle::step_once(const double *noise_dev) {
   int st;
   LaunchCtx c = ctx();
   if (p.dynamics == MAVI_DYN_RINGS) return rings_step(this, noise_dev);
+  if (p.slab) return slab_step_once(this, noise_dev);
   if (int st0 = pending_out_of_grid()) return st0;
   const bool second_is_vel = second_kind == SECOND_VEL;
   if (prof) cudaEventRecord(ev[0], stream);
@@ -488,6 +498,12 @@ int32_t mavi_destroy(MaviHandle *hh) {
   if (!h) return MAVI_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  slab_destroy(h);
+  for (int d = 0; d < 2; d++) {
+    void *mig[] = {h->slab.mig_pos[d], h->slab.mig_second[d], h->slab.mig_force[d], h->slab.mig_id[d], h->slab.mig_ts[d]};
+    for (void *q : mig)
+      if (q) cudaFree(q);
+  }
   for (void *ptr : h->allocs)
     if (ptr) cudaFree(ptr);
   if (h->flags_host) cudaFreeHost(h->flags_host);
@@ -511,6 +527,10 @@ int32_t mavi_last_error(MaviHandle *hh, char *buf, int32_t n) {
 int32_t mavi_upload_state(MaviHandle *hh, const void *pos, const void *second, const uint8_t *active_mask, int64_t n) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || !pos || n != h->p.n) return MAVI_ERR_BAD_PARAMS;
+  if (h->p.slab) {
+    h->set_error("slab mode: use mavi_upload_local (every rank uploads the particles of its own cell columns)");
+    return MAVI_ERR_BAD_PARAMS;
+  }
   cudaSetDevice(h->device);
   DevArrays &a = h->a;
   LaunchCtx c = h->ctx();
@@ -552,6 +572,10 @@ int32_t mavi_download_state(MaviHandle *hh, void *pos, void *second) {
   LaunchCtx c = h->ctx();
   const size_t sn = (size_t)h->p.n;
   if (h->second_kind == SECOND_RING_POL) return rings_download_state(h, pos, second);
+  if (h->p.slab) {
+    h->set_error("slab mode: use mavi_download_local");
+    return MAVI_ERR_BAD_PARAMS;
+  }
   if (pos) {
     launch_unpermute2(c, h->p, a, a.pos[0], a.st_pos);
     CUDA_TRY(h, cudaMemcpyAsync(pos, a.st_pos, sn * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
@@ -586,16 +610,87 @@ int32_t mavi_local_count(MaviHandle *hh, int64_t *n_local) {
   return MAVI_OK;
 }
 
+// ids / state / forces of the particles this rank currently owns (single GPU: everything, in original-id order)
 int32_t mavi_download_local(MaviHandle *hh, int64_t *ids, void *pos, void *second, void *forces) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h) return MAVI_ERR_BAD_PARAMS;
-  // single GPU: the local set is everything, in original-id order
+  if (!h->p.slab) {
+    if (ids)
+      for (int64_t i = 0; i < h->p.n; i++) ids[i] = i;
+    int st = mavi_download_state(hh, pos, second);
+    if (st) return st;
+    if (forces) return mavi_download_forces(hh, forces);
+    return MAVI_OK;
+  }
+  cudaSetDevice(h->device);
+  DevArrays &a = h->a;
+  const size_t n = (size_t)h->p.n;
+  if ((int)n > h->n_cap) {
+    h->set_error("owned particle count %zu exceeds the staging capacity %d", n, h->n_cap);
+    return MAVI_ERR_CAPACITY;
+  }
+  const bool vel = h->second_kind == SECOND_VEL;
+  launch_compact_to_staging(h->ctx(), h->p, a, vel);
+  if (pos) CUDA_TRY(h, cudaMemcpyAsync(pos, a.st_pos, n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  if (second) {
+    if (vel) CUDA_TRY(h, cudaMemcpyAsync(second, a.st_vel, n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+    else CUDA_TRY(h, cudaMemcpyAsync(second, a.st_ang, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (forces) CUDA_TRY(h, cudaMemcpyAsync(forces, a.st_force, n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  std::vector<unsigned int> idbuf;
+  if (ids) {
+    idbuf.resize(n);
+    CUDA_TRY(h, cudaMemcpyAsync(idbuf.data(), a.st_id, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+  }
+  int st = h->check_device_flags();
   if (ids)
-    for (int64_t i = 0; i < h->p.n; i++) ids[i] = i;
-  int st = mavi_download_state(hh, pos, second);
+    for (size_t i = 0; i < n; i++) ids[i] = (int64_t)(idbuf[i] & ~MAVI_INACTIVE_BIT);
+  return st;
+}
+
+// slab mode upload: the particles whose cell column this rank owns, with their global original ids
+int32_t mavi_upload_local(MaviHandle *hh, const int64_t *ids, const void *pos, const void *second, int64_t n_local) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || !pos || !ids || n_local < 0) return MAVI_ERR_BAD_PARAMS;
+  if (!h->p.slab) {
+    h->set_error("mavi_upload_local is for slab mode (MaviParams.world > 1)");
+    return MAVI_ERR_BAD_PARAMS;
+  }
+  if (n_local > h->n_cap) {
+    h->set_error("n_local %lld exceeds the capacity %d derived from MaviParams.n", (long long)n_local, h->n_cap);
+    return MAVI_ERR_CAPACITY;
+  }
+  cudaSetDevice(h->device);
+  DevArrays &a = h->a;
+  const size_t sn = (size_t)n_local;
+  std::vector<unsigned int> id32(sn);
+  for (size_t i = 0; i < sn; i++) {
+    if (ids[i] < 0 || ids[i] >= 0x7fffffffLL) {
+      h->set_error("particle ids must fit in 31 bits");
+      return MAVI_ERR_BAD_PARAMS;
+    }
+    id32[i] = (unsigned int)ids[i];
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(a.st_pos, pos, sn * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  if (second) {
+    if (h->second_kind == SECOND_VEL)
+      CUDA_TRY(h, cudaMemcpyAsync(a.st_vel, second, sn * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+    else
+      CUDA_TRY(h, cudaMemcpyAsync(a.st_ang, second, sn * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(a.st_id, id32.data(), sn * sizeof(unsigned int), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(a.st_force, 0, sn * sizeof(double2), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(a.flags, 0, FLAG_COUNT * sizeof(int), h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->p.n = (int)n_local;
+  int st = h->rebuild_from_staging((int)n_local);
   if (st) return st;
-  if (forces) return mavi_download_forces(hh, forces);
-  return MAVI_OK;
+  return h->check_device_flags();
+}
+
+int32_t mavi_nccl_unique_id(void *out128) {
+  if (!out128) return MAVI_ERR_BAD_PARAMS;
+  return slab_unique_id(out128);
 }
 
 int32_t mavi_step(MaviHandle *hh, int64_t nsteps, const void *host_noise) {

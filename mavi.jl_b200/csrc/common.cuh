@@ -50,9 +50,17 @@ struct DevParams {
   int tail_base;  // first slot of the inactive tail = nt * cap
   int inbox_cap;  // per-tile capacity for particles arriving from other tiles in one step
   int mv_cap;     // capacity of the per-step inter-tile mover list
+  // x-slab domain decomposition (one process per GPU): the local grid is [left halo | owned columns | right halo];
+  // cell arithmetic stays GLOBAL (bit-exact global cell ids), only the column index is shifted into the local frame.
+  int slab;                   // 1 = slab mode
+  int gcols;                  // global number of cell columns (== num_cols when slab == 0)
+  int col_lo;                 // global column of local column 1 (slab mode)
+  int ord_cols, ord_col0;     // columns enumerated by the rank order: owned columns only
+  int nt_ord;                 // ord_cols * tpc
+  int seam_left, seam_right;  // the halo column lies across the periodic seam -> minimum image for pairs through it
   unsigned int rows_mul, rows_shr;  // magic number division by num_rows
   unsigned int tpc_mul, tpc_shr;    // ... by tpc
-  unsigned int cols_mul, cols_shr;  // ... by num_cols
+  unsigned int cols_mul, cols_shr;  // ... by ord_cols
   int periodic;              // calc_diff applies the minimum image (src/integration.jl:43-48)
   double grid_bl[2], grid_h, cl, ch;
   double size[2], half[2];   // main rectangle size and size/2
@@ -101,7 +109,7 @@ __device__ __forceinline__ int tile_of_cell(const DevParams &p, int cell) {
 // Kernels enumerate tiles TILE-ROW-MAJOR (order index o = tile_row * num_cols + col): 256 consecutive ranks are then a
 // block of ~6 adjacent columns x 32 rows whose neighbours are mostly the block's own particles (L1 hits).
 __device__ __forceinline__ int tile_of_order(const DevParams &p, int o) {
-  const int tr = div_cols(p, o), col = o - tr * p.num_cols;
+  const int tr = div_cols(p, o), col = o - tr * p.ord_cols + p.ord_col0;
   return col * p.tpc + tr;
 }
 __device__ __forceinline__ int tq_of(const DevParams &p, int col, int row) {
@@ -132,9 +140,16 @@ __device__ __forceinline__ int cell_of_point(const DevParams &p, double x, doubl
   if (!(fabs(rowf) < 2.0e9) || !(fabs(colf) < 2.0e9)) return -1;  // NaN/Inf -> InexactError in the reference
   int row = (int)rowf + 1, col = (int)colf + 1;
   row -= (row == p.num_rows + 1) ? 1 : 0;
-  col -= (col == p.num_cols + 1) ? 1 : 0;
-  if (row < 1 || row > p.num_rows || col < 1 || col > p.num_cols) return -1;
-  return (row - 1) + p.num_rows * (col - 1);
+  col -= (col == p.gcols + 1) ? 1 : 0;
+  if (row < 1 || row > p.num_rows || col < 1 || col > p.gcols) return -1;
+  int lcol = col - 1;
+  if (p.slab) {  // global column -> local frame [0 = left halo, 1..m owned, m+1 = right halo], periodic in x
+    lcol = lcol - p.col_lo + 1;
+    if (lcol < 0) lcol += p.gcols;
+    else if (lcol >= p.gcols) lcol -= p.gcols;
+    if (lcol >= p.num_cols) return -1;  // more than one column beyond the slab in one step
+  }
+  return (row - 1) + p.num_rows * lcol;
 }
 
 // Exact test "update_particle_chunk! would put (x, y) into `cell` again" without a division: the reference index is
@@ -147,9 +162,15 @@ __device__ __forceinline__ bool axis_in_cell(double t, int k, int n, double c) {
   return lo && hi;
 }
 __device__ __forceinline__ bool still_in_cell(const DevParams &p, double x, double y, int cell) {
-  const int col = div_rows(p, cell), row = cell - col * p.num_rows;
+  int col = div_rows(p, cell);
+  const int row = cell - col * p.num_rows;
+  if (p.slab) {  // local -> global column
+    col = col + p.col_lo - 1;
+    if (col < 0) col += p.gcols;
+    else if (col >= p.gcols) col -= p.gcols;
+  }
   return axis_in_cell(-y + p.grid_bl[1] + p.grid_h, row, p.num_rows, p.ch) &&
-         axis_in_cell(x - p.grid_bl[0], col, p.num_cols, p.cl);
+         axis_in_cell(x - p.grid_bl[0], col, p.gcols, p.cl);
 }
 
 // calc_diff component (src/integration.jl:38-48): strict '>', one image.

@@ -16,10 +16,24 @@ struct RingsArrays {
   double *pol = nullptr;        // state.pol, one angle per ring
 };
 
+// x-slab decomposition state (slab.cu)
+struct SlabState {
+  int world = 1, rank = 0, left = 0, right = 0;
+  int m = 0, m_left = 0, m_right = 0, col_lo = 0;
+  int n_global = 0;
+  struct ncclComm *comm = nullptr;
+  double2 *mig_pos[2] = {nullptr, nullptr}, *mig_second[2] = {nullptr, nullptr}, *mig_force[2] = {nullptr, nullptr};
+  unsigned int *mig_id[2] = {nullptr, nullptr};
+  int *mig_ts[2] = {nullptr, nullptr};
+  size_t mig_cs = 0;
+};
+
 struct Handle {
   DevParams p;
   DevArrays a;
   RingsArrays r;
+  SlabState slab;
+  int n_cap = 0;  // capacity of the dense staging arrays (slab mode: the owned count changes with migration)
   int device = 0;
   int flags_cfg = 0;
   cudaStream_t stream = nullptr;
@@ -50,6 +64,13 @@ struct Handle {
 
 // api.cu
 void mavi_magic_div(unsigned int d, unsigned int *mul, unsigned int *shr);
+
+// slab.cu
+int slab_unique_id(void *out128);
+int slab_configure(Handle *h, const MaviParams *mp);
+void slab_destroy(Handle *h);
+int slab_after_build(Handle *h);
+int slab_step_once(Handle *h, const double *noise_dev);
 
 // rings.cu
 int rings_lower(Handle *h, const MaviParams *mp);

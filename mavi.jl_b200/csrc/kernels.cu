@@ -33,7 +33,7 @@ __device__ __forceinline__ int slot_of_rank_cta(const DevParams &p, const int *_
   const int o0 = (blockIdx.x * TPB < p.n_active) ? __ldg(cta_first + blockIdx.x) : 0;
   if (threadIdx.x <= RANK_WIN) {
     const int o = o0 + threadIdx.x;
-    s_win[threadIdx.x] = (blockIdx.x * TPB < p.n_active && o <= p.nt) ? __ldg(tile_prefix + o) : 0x7fffffff;
+    s_win[threadIdx.x] = (blockIdx.x * TPB < p.n_active && o <= p.nt_ord) ? __ldg(tile_prefix + o) : 0x7fffffff;
   }
   __syncthreads();
   if (rank >= p.n_active) return p.tail_base + (rank - p.n_active);
@@ -93,9 +93,13 @@ __global__ void k_build_cell_index(const __grid_constant__ DevParams p, const do
   if (!(st_id[i] & MAVI_INACTIVE_BIT)) {
     double2 r = st_pos[i];
     c = cell_of_point(p, r.x, r.y);
+    if (c >= 0 && p.slab) {  // a full build only ever sees particles of the owned columns
+      const int lcol = div_rows(p, c);
+      if (lcol < 1 || lcol > p.num_cols - 2) c = -1;
+    }
     if (c < 0) {  // BoundsError in the reference (src/chunks.jl:144-146)
       atomicOr(&flags[FLAG_ERR], ERRBIT_OUT_OF_GRID);
-      c = 0;
+      c = p.slab ? p.num_rows : 0;
     }
     atomicAdd(&count[c], 1);
   }
@@ -175,9 +179,9 @@ __global__ void k_build_place(const __grid_constant__ DevParams p, const int *__
 // tile populations -> (scan) -> tile_prefix, then the first tile of every 256-rank block
 __global__ void k_tile_counts(const __grid_constant__ DevParams p, const int *__restrict__ tstart, int *__restrict__ out) {
   int o = blockIdx.x * blockDim.x + threadIdx.x;  // tile-row-major order index
-  if (o > p.nt) return;
+  if (o > p.nt_ord) return;
   int cnt = 0;
-  if (o < p.nt) {
+  if (o < p.nt_ord) {
     const int t = tile_of_order(p, o);
     cnt = tstart[(size_t)t * (MAVI_TR + 1) + MAVI_TR] - t * p.cap;
   }
@@ -187,7 +191,7 @@ __global__ void k_tile_counts(const __grid_constant__ DevParams p, const int *__
 __global__ void k_cta_first(const __grid_constant__ DevParams p, const int *__restrict__ tile_prefix,
                             int *__restrict__ cta_first) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= p.nt) return;
+  if (t >= p.nt_ord) return;
   const int lo = tile_prefix[t], hi = tile_prefix[t + 1];
   for (int b = (lo + TPB - 1) / TPB; b * TPB < hi; b++) cta_first[b] = t;
 }
@@ -279,12 +283,12 @@ void launch_exclusive_scan(const LaunchCtx &c, const int *in, int *out, int *par
   MAVI_LAUNCH(c, k_scan_final, nb, SCAN_TPB, 0, in, out, partials, n);
 }
 
-static void refresh_rank_maps(const LaunchCtx &c, const DevParams &p, const DevArrays &a) {
+void refresh_rank_maps(const LaunchCtx &c, const DevParams &p, const DevArrays &a) {
   if (p.nt == 0) return;
   int *tmp = a.perm;  // nt+1 ints of scratch
-  MAVI_LAUNCH(c, k_tile_counts, nblk(p.nt + 1), TPB, 0, p, a.tstart, tmp);
-  launch_exclusive_scan(c, tmp, a.tile_prefix, a.scan_partials, p.nt + 1);
-  MAVI_LAUNCH(c, k_cta_first, nblk(p.nt), TPB, 0, p, a.tile_prefix, a.cta_first);
+  MAVI_LAUNCH(c, k_tile_counts, nblk(p.nt_ord + 1), TPB, 0, p, a.tstart, tmp);
+  launch_exclusive_scan(c, tmp, a.tile_prefix, a.scan_partials, p.nt_ord + 1);
+  MAVI_LAUNCH(c, k_cta_first, nblk(p.nt_ord), TPB, 0, p, a.tile_prefix, a.cta_first);
 }
 
 void launch_build_tiles(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel) {
@@ -367,6 +371,7 @@ __global__ void k_repair_collect(const int *__restrict__ flags, const int *__res
   const int n = min(flags[FLAG_NMV], mv_cap);
   for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
     const int k = mv_src[m];
+    if (k < 0) continue;  // immigrant from another GPU: its record is already in the mover arrays (slab.cu)
     mv_pos[m] = pos[k];
     mv_second[m] = vel ? vel[k] : make_double2(ang[k], 0.0);
     mv_force[m] = force[k];
@@ -624,6 +629,7 @@ __device__ __forceinline__ double2 cell_pair_force(const DevParams &p, const int
       c2 = 0;
       use_mi = PER;
     }
+    if (p.slab && ((c2 == 0 && p.seam_left) || (c2 == Cn - 1 && p.seam_right))) use_mi = PER;
     const int *tc = tstart + (size_t)c2 * p.tpc * (MAVI_TR + 1);
     const int a = __ldg(tc + o1a), ea = __ldg(tc + o1b);
     const int b = two ? __ldg(tc + o2a) : ea, eb = two ? __ldg(tc + o2b) : ea;

@@ -67,6 +67,7 @@ void launch_init_staging_ids(const LaunchCtx &c, int n, const unsigned char *mas
 // incremental update_chunks!: repair the tiles touched by this step's movers, then refresh the rank maps
 void launch_repair_tiles(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel);
 void launch_exclusive_scan(const LaunchCtx &c, const int *in, int *out, int *partials, int n);
+void refresh_rank_maps(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
 
 // force + integrate passes
 void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool with_wall_forces);

@@ -365,6 +365,10 @@ static int rings_alloc_tiles(Handle *h, int cap) {
   p.cap = cap;
   p.n_active = 0;
   p.tail_base = 0;
+  p.gcols = p.num_cols;
+  p.ord_cols = p.num_cols;
+  p.ord_col0 = 0;
+  p.nt_ord = p.nt;
   mavi_magic_div((unsigned int)p.num_rows, &p.rows_mul, &p.rows_shr);
   mavi_magic_div((unsigned int)p.tpc, &p.tpc_mul, &p.tpc_shr);
   mavi_magic_div((unsigned int)p.num_cols, &p.cols_mul, &p.cols_shr);

@@ -59,7 +59,12 @@ class System:
         self._forces = None
         self._check(self._lib.mavi_create(C.byref(self._lowered.params), C.byref(self._h)))
         self._check(self._lib.mavi_set_time(self._h, self.time_info.num_steps, self.time_info.time))
-        self.upload_state()
+        self._slab = int_cfg.device.world > 1
+        if self._slab:
+            self.local_ids = np.ascontiguousarray(getattr(state, "ids"), dtype=np.int64)
+            self.upload_local()
+        else:
+            self.upload_state()
 
     # ------------------------------------------------------------------ plumbing
     def _check(self, status):
@@ -88,6 +93,28 @@ class System:
         second = np.ascontiguousarray(st.second, dtype=self._dtype)
         mask = st.active_mask()
         self._check(self._lib.mavi_upload_state(self._h, _ptr(pos), _ptr(second), _ptr(mask), self._n))
+
+    def upload_local(self):
+        """Slab mode: upload the particles of this rank's cell columns with their global ids."""
+        st = self.state
+        pos = np.ascontiguousarray(st.pos, dtype=self._dtype)
+        second = np.ascontiguousarray(st.second, dtype=self._dtype)
+        self._check(self._lib.mavi_upload_local(self._h, _ptr(self.local_ids), _ptr(pos), _ptr(second), len(pos)))
+
+    def local_count(self):
+        n = C.c_int64()
+        self._check(self._lib.mavi_local_count(self._h, C.byref(n)))
+        return n.value
+
+    def download_local(self):
+        """Slab mode: (ids, pos, second, forces) of the particles this rank currently owns."""
+        n = self.local_count()
+        ids = np.empty(n, dtype=np.int64)
+        pos = np.empty((n, 2), dtype=self._dtype)
+        second = np.empty((n, 2) if self.state.second.ndim == 2 else (n,), dtype=self._dtype)
+        forces = np.empty((n, 2), dtype=self._dtype)
+        self._check(self._lib.mavi_download_local(self._h, _ptr(ids), _ptr(pos), _ptr(second), _ptr(forces)))
+        return ids, pos, second, forces
 
     def sync_to_host(self):
         """`sync_to_host!(system)`: device state -> `system.state` arrays, and TimeInfo."""

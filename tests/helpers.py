@@ -1,9 +1,13 @@
 """Shared builders: ONE set of configs -> (device System, CPU oracle) pairs on identical seeded inputs."""
 from __future__ import annotations
 
+import os
+import sys
+
 import numpy as np
 
-import __graft_entry__ as entry
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as entry  # noqa: E402
 
 pkg = entry.load_package()
 from mavi_jl_b200.params import lower  # noqa: E402
