@@ -44,16 +44,34 @@ def measured_peak_hbm():
         return 6650.0, "fallback"
 
 
-def lj_workload(pkg, nx, ny, cuda_device=None, chunks=True):
-    """LJ lattice gas of SURVEY.md 8d (examples/chunks.jl geometry with README sigma=eps=1)."""
+def lj_workload(pkg, nx, ny, cuda_device=None, chunks=True, rank=0, world=1):
+    """LJ lattice gas of SURVEY.md 8d (examples/chunks.jl geometry with README sigma=eps=1).  With world > 1 the box is
+    `world` times as long (nx*world lattice columns) and only the particles of this rank's x-slab are generated."""
     dyn = pkg.LenJonesCfg(sigma=1.0, epsilon=1.0)
-    pos, geom = pkg.rectangular_grid(nx, ny, 0.4, pkg.particle_radius(dyn))
-    rng = np.random.default_rng(SEED)
-    vel = pkg.random_vel(nx * ny, 1 / 5, rng=rng)
-    space = pkg.SpaceCfg(wall_type=pkg.PeriodicWalls(), geometry_cfg=geom)
-    ccfg = pkg.ChunksCfg(num_cols=int(nx * 0.9), num_rows=int(ny * 0.9)) if chunks else None
+    r = pkg.particle_radius(dyn)
+    nxt = nx * world
+    ncols, nrows = int(nxt * 0.9), int(ny * 0.9)
+    ccfg = pkg.ChunksCfg(num_cols=ncols, num_rows=nrows) if chunks else None
     int_cfg = pkg.IntCfg(dt=0.001, chunks_cfg=ccfg, device=cuda_device or pkg.CUDADevice())
-    return dict(pos=pos, vel=vel, space=space, dyn=dyn, int_cfg=int_cfg, geom=geom)
+    rng = np.random.default_rng(SEED + rank)
+    if world == 1:
+        pos, geom = pkg.rectangular_grid(nx, ny, 0.4, r)
+        ids = None
+    else:
+        from mavi_jl_b200 import slabs
+        line, geom = pkg.rectangular_grid(nxt, 1, 0.4, r)          # lattice x coordinates (repeated addition)
+        colm, g2 = pkg.rectangular_grid(1, ny, 0.4, r)             # lattice y coordinates
+        geom = pkg.RectangleCfg(length=geom.length, height=g2.height)
+        xs, ys = line[:, 0], colm[:, 1]
+        mine_x = np.flatnonzero(slabs.owner_of_column(slabs.column_of(xs, 0.0, geom.length, ncols), ncols, world) == rank)
+        pos = np.empty((ny, len(mine_x), 2))
+        pos[..., 0] = xs[mine_x][None, :]
+        pos[..., 1] = ys[:, None]
+        pos = pos.reshape(-1, 2)
+        ids = (np.arange(ny)[:, None] * nxt + mine_x[None, :]).reshape(-1)
+    vel = pkg.random_vel(len(pos), 1 / 5, rng=rng)
+    space = pkg.SpaceCfg(wall_type=pkg.PeriodicWalls(), geometry_cfg=geom)
+    return dict(pos=pos, vel=vel, space=space, dyn=dyn, int_cfg=int_cfg, geom=geom, ids=ids, n_global=nxt * ny)
 
 
 class ClockSampler(threading.Thread):
@@ -146,10 +164,19 @@ def run_ours(args):
 
     nx, ny = args.nx, args.ny
     stream = torch.cuda.current_stream().cuda_stream
-    dev = pkg.CUDADevice(device=local_rank, stream=stream, flags=args.flags)
-    w = lj_workload(pkg, nx, ny, cuda_device=dev)
-    n = nx * ny
+    uid = None
+    if world > 1:
+        from mavi_jl_b200 import slabs
+        box = [slabs.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+    dev = pkg.CUDADevice(device=local_rank, stream=stream, flags=args.flags, rank=rank, world=world, nccl_unique_id=uid,
+                         n_global=nx * world * ny)
+    w = lj_workload(pkg, nx, ny, cuda_device=dev, rank=rank, world=world)
+    n = nx * ny  # particles per GPU (weak scaling)
     state = pkg.SecondLawState(pos=w["pos"], vel=w["vel"])
+    if world > 1:
+        state.ids = w["ids"]
     system = pkg.System(state=state, space_cfg=w["space"], dynamic_cfg=w["dyn"], int_cfg=w["int_cfg"])
 
     def barrier():
@@ -182,17 +209,24 @@ def run_ours(args):
 
     # ---- end to end through host buffers (`e2e`) -------------------------------------------------------
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
-    pin_pos = torch.empty((n, 2), dtype=torch.float64).pin_memory()
-    pin_vel = torch.empty((n, 2), dtype=torch.float64).pin_memory()
-    system.sync_to_host()
-    pin_pos.numpy()[...] = system.state.pos
-    pin_vel.numpy()[...] = system.state.vel
-    system.state.pos, system.state.vel = pin_pos.numpy(), pin_vel.numpy()
+    if world == 1:
+        pin_pos = torch.empty((n, 2), dtype=torch.float64).pin_memory()
+        pin_vel = torch.empty((n, 2), dtype=torch.float64).pin_memory()
+        system.sync_to_host()
+        pin_pos.numpy()[...] = system.state.pos
+        pin_vel.numpy()[...] = system.state.vel
+        system.state.pos, system.state.vel = pin_pos.numpy(), pin_vel.numpy()
 
-    def e2e_step():
-        system.upload_state()   # H2D pos+vel from pinned memory (+ constructor-time checks and binning)
-        system.step(1)
-        system.sync_to_host()   # D2H pos+vel into pinned memory
+        def e2e_step():
+            system.upload_state()   # H2D pos+vel from pinned memory (+ constructor-time checks and binning)
+            system.step(1)
+            system.sync_to_host()   # D2H pos+vel into pinned memory
+    else:
+        def e2e_step():
+            ids, pos, vel, _ = system.download_local()   # D2H ids+pos+vel(+forces) of the owned particles
+            system.local_ids, system.state.pos, system.state.vel = ids, pos, vel
+            system.upload_local()                        # H2D, re-binning, first halo exchange
+            system.step(1)
 
     e2e_step()
     barrier()
@@ -227,11 +261,11 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"LJ lattice gas {nx}x{ny}={n} particles per GPU, periodic rectangle, {int(nx * 0.9)}x{int(ny * 0.9)} chunks, "
                                f"f64, dt=0.001, newton_step! (2 force passes)", "l2": "state arrays (>=1.5 GB) exceed the 126 MB L2; no flush needed",
-                   "parallelism": "single GPU" if world == 1 else f"{world} independent x-slabs"},
+                   "parallelism": "single GPU" if world == 1 else f"{world} x-slabs of one {nx * world}x{ny} periodic box, NCCL halo+migration"},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_kind": peak_kind, "kernel_ms": dom_ms,
                      "step": {"achieved": step_achieved / world, "frac": step_achieved / world / peak, "bytes_per_particle_step": B_ALG_NEWTON},
-                     "phase_ms": {"bin_sort": phase_ms[0], "pass_a": phase_ms[1], "pass_b": phase_ms[2]}},
+                     "phase_ms": {"pass_a": phase_ms[1], "pass_b": phase_ms[2], "repair_exchange": phase_ms[3]}},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 32 * n,
                 "steps": e2e_steps, "what": "per step: mavi_upload_state(pos,vel from pinned host) + mavi_step(1) + mavi_download_state(pos,vel)"},

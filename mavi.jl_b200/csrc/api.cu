@@ -290,7 +290,7 @@ int Handle::alloc_state(int n_active, int cap) {
     magic_div((unsigned int)p.num_rows, &p.rows_mul, &p.rows_shr);
     magic_div((unsigned int)p.tpc, &p.tpc_mul, &p.tpc_shr);
     magic_div((unsigned int)p.ord_cols, &p.cols_mul, &p.cols_shr);
-    p.inbox_cap = 16;
+    p.inbox_cap = cap;  // a tile can never receive more than it can hold: inbox overflow implies tile overflow
     p.mv_cap = n_cap / 4 > 4096 ? n_cap / 4 : 4096;
   } else {
     p.tpc = p.nt = p.cap = p.nt_ord = 0;
@@ -445,7 +445,8 @@ int Handle::step_once(const double *noise_dev) {
   if ((st = check_device_flags())) return st;
   if (flags_host[FLAG_OVERFLOW]) {
     // a tile or inbox ran out of slots: nothing was modified by the repair; rebuild with a larger capacity
-    int cap = round_up16((flags_host[FLAG_MAXCOUNT] > p.cap ? flags_host[FLAG_MAXCOUNT] : p.cap) * 1.25 + 8.0);
+    // grow only when a tile really ran out of slots; a mover-list overflow just needs the rebuild
+    int cap = (flags_host[FLAG_OVERFLOW] & 1) ? round_up16((flags_host[FLAG_MAXCOUNT] > p.cap ? flags_host[FLAG_MAXCOUNT] : p.cap) * 1.25 + 8.0) : p.cap;
     launch_compact_to_staging(c, p, a, second_is_vel);
     const int n_active = p.n_active;
     if ((st = alloc_state(n_active, cap))) return st;

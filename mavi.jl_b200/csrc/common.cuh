@@ -88,7 +88,7 @@ struct DevParams {
 enum { ERRBIT_OUT_OF_GRID = 1, ERRBIT_NAN = 2, ERRBIT_OUTSIDE_SPACE = 4, ERRBIT_OOG_PENDING = 8 };
 
 // flags[] layout (device control word, mirrored to pinned host memory once per step)
-enum { FLAG_ERR = 0, FLAG_CHANGED = 1, FLAG_BIGMOVE = 2, FLAG_NFIX = 3, FLAG_NMV = 4, FLAG_OVERFLOW = 5, FLAG_MAXCOUNT = 6, FLAG_COUNT = 8 };
+enum { FLAG_ERR = 0, FLAG_CHANGED = 1, FLAG_BIGMOVE = 2, FLAG_NFIX = 3, FLAG_NMV = 4, FLAG_OVERFLOW = 5, FLAG_MAXCOUNT = 6, FLAG_TAIL = 7, FLAG_MAXINBOX = 8, FLAG_MAXINBOX_TILE = 9, FLAG_COUNT = 12 };
 
 #define MAVI_TR 32  // cell rows per tile
 

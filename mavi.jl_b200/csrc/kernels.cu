@@ -438,7 +438,11 @@ __global__ void __launch_bounds__(REPAIR_WARPS * 32) k_repair_tiles(
     if (!WRITE) {
       if (lane == 0) {
         atomicMax(&flags[FLAG_MAXCOUNT], total);
-        if (total > p.cap || nin > p.inbox_cap) flags[FLAG_OVERFLOW] = 1;
+        if (total > p.cap) atomicOr(&flags[FLAG_OVERFLOW], 1);
+        if (nin > p.inbox_cap) {
+          atomicOr(&flags[FLAG_OVERFLOW], 2);
+          if (atomicMax(&flags[FLAG_MAXINBOX], nin) < nin) flags[FLAG_MAXINBOX_TILE] = t;
+        }
       }
       continue;
     }
@@ -708,7 +712,7 @@ __device__ __forceinline__ void note_if_moved(const DevParams &p, const MoverSin
       ms.mv_src[m] = k;
       ms.inbox[(size_t)t_new * p.inbox_cap + i] = m;
     } else {
-      ms.flags[FLAG_OVERFLOW] = 1;
+      atomicOr(&ms.flags[FLAG_OVERFLOW], m < p.mv_cap ? 2 : 4);
     }
   }
 }

@@ -204,7 +204,7 @@ __global__ void k_ingest(const __grid_constant__ DevParams p, const int *__restr
       mv_cell[m] = c;
       inbox[(size_t)t * p.inbox_cap + i] = m;
     } else {
-      flags[FLAG_OVERFLOW] = 1;
+      atomicOr(&flags[FLAG_OVERFLOW], m < p.mv_cap ? 2 : 4);
     }
   }
 }
@@ -370,7 +370,9 @@ int slab_step_once(Handle *h, const double *noise_dev) {
   h->num_steps += 1;
   if ((st = slab_refresh_count(h))) return st;
   if (h->flags_host[FLAG_OVERFLOW]) {
-    h->set_error("a tile or inbox overflowed in slab mode (capacity %d); rebuild with a larger MaviParams.n hint", p.cap);
+    h->set_error("slab mode overflow (bits %d: 1 = tile capacity %d < %d, 2 = inbox capacity %d < %d at tile %d (column %d of %d), 4 = mover list %d)",
+                 h->flags_host[FLAG_OVERFLOW], p.cap, h->flags_host[FLAG_MAXCOUNT], p.inbox_cap, h->flags_host[FLAG_MAXINBOX],
+                 h->flags_host[FLAG_MAXINBOX_TILE], h->flags_host[FLAG_MAXINBOX_TILE] / p.tpc, p.num_cols, p.mv_cap);
     return MAVI_ERR_CAPACITY;
   }
   if ((st = slab_halo_exchange(h, a.pos[0], true))) return st;

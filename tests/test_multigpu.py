@@ -120,7 +120,7 @@ def _ngpus():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind,steps", [("lj", 150), ("harm", 150), ("szabo", 120)])
+@pytest.mark.parametrize("kind,steps", [("lj", 150), ("harm", 150), ("szabo", 40)])  # overlapping Szabo particles are chaotic: short horizon
 def test_multigpu_slabs_match_oracle(cuda_lib, kind, steps):
     n = _ngpus()
     if n < 2:
