@@ -1,0 +1,263 @@
+# MaviCUDA.jl — Julia glue that makes libmavi_cuda.so a drop-in `DeviceMode` of Mavi.jl.
+#
+# Usage (unchanged Mavi API, one new device type):
+#
+#     using Mavi, Mavi.Configs, MaviCUDA
+#     system = System(state=..., space_cfg=..., dynamic_cfg=LenJonesCfg(sigma=1, epsilon=1),
+#                     int_cfg=IntCfg(dt=0.001, chunks_cfg=ChunksCfg(900, 900), device=CUDADevice()))
+#     Mavi.run_system(system, tf=1)          # one mavi_step(h, nsteps) + one download
+#
+# Everything below binds EXACTLY the entry points of include/mavi.h (the same ones the Python host mirror in
+# mavi.jl_b200/ exercises through ctypes).  Julia is not installed in the build image, so this file is not executed by
+# the test-suite; it is kept small and mechanical.  Reference seams it plugs into:
+#   DeviceMode                  src/configs.jl:471-475
+#   calc_forces!(system, chunks, device)   src/integration.jl:112,159,197,226
+#   get_step_function           src/integration.jl:537-548, src/rings/integration.jl:545
+#   System ctor                 src/systems.jl:73-114
+module MaviCUDA
+
+using StaticArrays
+using Mavi
+using Mavi.Configs
+using Mavi.States
+using Mavi.Systems
+import Mavi.Integration: calc_forces!, newton_step!, szabo_step!, rtp_step!, get_step_function
+import Mavi.RunSystem: run_system
+
+export CUDADevice, sync_to_host!, upload_state!, device_energies
+
+const LIB = get(ENV, "MAVI_CUDA_LIB", "libmavi_cuda.so")
+const MAVI_MAX_SPACES = 8
+
+"`IntCfg(device=CUDADevice())` routes the per-step hot path to the GPU."
+Base.@kwdef struct CUDADevice <: DeviceMode
+    device::Int32 = 0
+    rng_mode::Symbol = :philox          # :host_noise (caller passes the draws) | :philox (device RNG)
+    seed::UInt64 = 24042001
+    sync_every::Int = 1                  # download state every k calls of a per-step function (GUI / experiments)
+end
+
+# ---- flat PODs of include/mavi.h (isbits, same field order) -------------------------------------------------------
+struct MaviLine
+    p1::NTuple{2,Float64}
+    p2::NTuple{2,Float64}
+end
+
+struct MaviSpace
+    wall::Int32
+    geom::Int32
+    rect_bl::NTuple{2,Float64}
+    rect_len::Float64
+    rect_h::Float64
+    circ_center::NTuple{2,Float64}
+    circ_radius::Float64
+    lines::Ptr{MaviLine}
+    n_lines::Int32
+    pot_kind::Int32
+    pot::NTuple{4,Float64}
+    pot_mode::Int32
+    _pad::Int32
+end
+
+struct MaviRingsParams
+    num_types::Int32
+    n_max::Int32
+    num_rings::Int64
+    p0::Ptr{Float64}; relax_time::Ptr{Float64}; vo::Ptr{Float64}; mobility::Ptr{Float64}
+    rot_diff::Ptr{Float64}; k_area::Ptr{Float64}; k_spring::Ptr{Float64}; l_spring::Ptr{Float64}
+    num_particles::Ptr{Int32}
+    interaction::Ptr{Float64}
+    types::Ptr{Int32}
+end
+
+struct MaviParams
+    struct_size::UInt32
+    dtype::Int32
+    n::Int64
+    n_spaces::Int32
+    _pad0::Int32
+    spaces::NTuple{MAVI_MAX_SPACES,MaviSpace}
+    grid_bl::NTuple{2,Float64}
+    grid_len::Float64
+    grid_h::Float64
+    num_cols::Int32
+    num_rows::Int32
+    dynamics::Int32
+    _pad1::Int32
+    dyn::NTuple{8,Float64}
+    particle_radius::Float64
+    rings::Ptr{MaviRingsParams}
+    dt::Float64
+    rng_mode::Int32
+    _pad2::Int32
+    seed::UInt64
+    device::Int32
+    flags::Int32
+    stream::Ptr{Cvoid}
+    rank::Int32
+    world::Int32
+    nccl_unique_id::Ptr{Cvoid}
+    n_global::Int64
+end
+
+const WALL = Dict(RigidWalls => 0, PeriodicWalls => 1, SlipperyWalls => 2)
+zero_space() = MaviSpace(0, 0, (0.0, 0.0), 0.0, 0.0, (0.0, 0.0), 0.0, C_NULL, 0, 0, (0.0, 0.0, 0.0, 0.0), 0, 0)
+
+function lower_space(w, g, keep)
+    wall = w isa PotentialWalls ? Int32(3) : Int32(WALL[typeof(w)])
+    pot_kind, pot, mode = Int32(0), (0.0, 0.0, 0.0, 0.0), Int32(2)
+    if w isa PotentialWalls
+        p = w.potential
+        if p isa LenJonesCfg
+            pot_kind, pot = Int32(1), (Float64(p.sigma), Float64(p.epsilon), 0.0, 0.0)
+        else
+            pot = (Float64(p.k_rep), Float64(p.k_atr), Float64(p.dist_eq), Float64(p.dist_max))
+        end
+        mode = w.mode isa Configs.Outside ? Int32(0) : w.mode isa Configs.Inside ? Int32(1) : Int32(2)
+    end
+    if g isa RectangleCfg
+        return MaviSpace(wall, 0, Tuple(Float64.(g.bottom_left)), g.length, g.height, (0.0, 0.0), 0.0, C_NULL, 0, pot_kind, pot, mode, 0)
+    elseif g isa CircleCfg
+        return MaviSpace(wall, 1, (0.0, 0.0), 0.0, 0.0, Tuple(Float64.(g.center)), g.radius, C_NULL, 0, pot_kind, pot, mode, 0)
+    else
+        lines = [MaviLine(Tuple(Float64.(l.p1)), Tuple(Float64.(l.p2))) for l in g.lines]
+        push!(keep, lines)
+        return MaviSpace(wall, 2, (0.0, 0.0), 0.0, 0.0, (0.0, 0.0), 0.0, pointer(lines), length(lines), pot_kind, pot, mode, 0)
+    end
+end
+
+dyn_block(c::LenJonesCfg) = (Int32(0), (c.sigma, c.epsilon, 0, 0, 0, 0, 0, 0))
+dyn_block(c::HarmTruncCfg) = (Int32(1), (c.k_rep, c.k_atr, c.dist_eq, c.dist_max, 0, 0, 0, 0))
+dyn_block(c::SzaboCfg) = (Int32(2), (c.vo, c.mobility, c.relax_time, c.k_rep, c.k_adh, c.r_eq, c.r_max, c.rot_diff))
+dyn_block(c::RunTumbleCfg) = (Int32(3), (c.vo, c.sigma, c.epsilon, c.tumble_rate, 0, 0, 0, 0))
+
+# ---- handle attached to a System (kept in a side table so that `System` itself is untouched) -----------------------
+mutable struct DeviceState
+    h::Ptr{Cvoid}
+    keep::Vector{Any}
+    calls::Int
+end
+const HANDLES = IdDict{Any,DeviceState}()
+
+function check(ds::DeviceState, status::Int32)
+    status == 0 && return
+    buf = Vector{UInt8}(undef, 512)
+    ccall((:mavi_last_error, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32), ds.h, buf, 512)
+    error("libmavi_cuda status $status: " * unsafe_string(pointer(buf)))   # reference: throw(...) / BoundsError
+end
+
+second_array(s::SecondLawState) = s.vel
+second_array(s::SelfPropelledState) = s.pol_angle
+
+"Create the device context for `system` and upload its state (what the `System` ctor does on the CPU: force buffers, Chunks, first update_chunks!)."
+function attach!(system::System)
+    dev = system.int_cfg.device::CUDADevice
+    keep = Any[]
+    sc = system.space_cfg
+    pairs = sc.wall_type isa ManyWalls ? collect(zip(sc.wall_type.list, sc.geometry_cfg.list)) : [(sc.wall_type, sc.geometry_cfg)]
+    spaces = [lower_space(w, g, keep) for (w, g) in pairs]
+    while length(spaces) < MAVI_MAX_SPACES; push!(spaces, zero_space()); end
+    bbox = Configs.get_bounding_box(sc.geometry_cfg)
+    cc = system.int_cfg.chunks_cfg
+    kind, dyn = dyn_block(system.dynamic_cfg)      # unknown DynamicCfg -> MethodError -> caller keeps the CPU path
+    params = Ref(MaviParams(sizeof(MaviParams), 0, length(system.state.pos), length(pairs), 0, Tuple(spaces),
+        Tuple(Float64.(bbox.bottom_left)), bbox.length, bbox.height,
+        isnothing(cc) ? 0 : cc.num_cols, isnothing(cc) ? 0 : cc.num_rows, kind, 0, Float64.(dyn),
+        minimum(particle_radius(system.dynamic_cfg)), C_NULL, system.int_cfg.dt,
+        dev.rng_mode == :host_noise ? 0 : 1, 0, dev.seed, dev.device, 0, C_NULL, 0, 1, C_NULL, 0))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    ds = DeviceState(C_NULL, keep, 0)
+    GC.@preserve keep begin
+        st = ccall((:mavi_create, LIB), Int32, (Ref{MaviParams}, Ref{Ptr{Cvoid}}), params, h)
+        ds.h = h[]
+        check(ds, st)
+    end
+    HANDLES[system] = ds
+    check(ds, ccall((:mavi_set_time, LIB), Int32, (Ptr{Cvoid}, Int64, Float64), ds.h, system.time_info.num_steps, system.time_info.time))
+    upload_state!(system)
+    finalizer(_ -> ccall((:mavi_destroy, LIB), Int32, (Ptr{Cvoid},), ds.h), ds)
+    return ds
+end
+
+handle(system) = get(() -> attach!(system), HANDLES, system)
+
+"Host state -> device (after the host edited `system.state`)."
+function upload_state!(system::System)
+    ds = handle(system)
+    st = system.state
+    mask = st.part_ids isa States.ParticleIds ? UInt8.(st.part_ids.mask) : UInt8[]
+    GC.@preserve st mask check(ds, ccall((:mavi_upload_state, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{UInt8}, Int64), ds.h, pointer(st.pos), pointer(second_array(st)),
+        isempty(mask) ? C_NULL : pointer(mask), length(st.pos)))
+end
+
+"`sync_to_host!(system)`: device state -> `system.state`, forces -> `get_forces(system)`.  Called by GUI / experiment / checkpoint hooks (SURVEY.md A.2)."
+function sync_to_host!(system::System)
+    ds = handle(system)
+    st = system.state
+    f = get_forces(system)
+    GC.@preserve st f begin
+        check(ds, ccall((:mavi_download_state, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), ds.h, pointer(st.pos), pointer(second_array(st))))
+        check(ds, ccall((:mavi_download_forces, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ds.h, pointer(f)))
+    end
+    return system
+end
+
+function device_step!(system::System, nsteps::Integer=1; noise=nothing)
+    ds = handle(system)
+    GC.@preserve noise check(ds, ccall((:mavi_step, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Cvoid}), ds.h, nsteps,
+        isnothing(noise) ? C_NULL : pointer(noise)))
+    for _ in 1:nsteps                      # update_time!, src/integration.jl:500-503 (same Float64 accumulation)
+        system.time_info.time += system.int_cfg.dt
+        system.time_info.num_steps += 1
+    end
+    ds.calls += 1
+    ds.calls % system.int_cfg.device.sync_every == 0 && sync_to_host!(system)
+    return nothing
+end
+
+const CUDASystem = System{T,ND,NT,S,W,G,D,<:IntCfg{<:Any,<:Any,CUDADevice}} where {T,ND,NT,S,W,G,D}
+
+# ---- the dispatch seam ------------------------------------------------------------------------------------------------
+newton_step!(system::CUDASystem) = device_step!(system, 1)
+szabo_step!(system::CUDASystem) = device_step!(system, 1)
+rtp_step!(system::CUDASystem) = device_step!(system, 1)
+
+function calc_forces!(system::System, chunks, ::CUDADevice)
+    ds = handle(system)
+    check(ds, ccall((:mavi_calc_forces, LIB), Int32, (Ptr{Cvoid},), ds.h))
+    f = get_forces(system)
+    GC.@preserve f check(ds, ccall((:mavi_download_forces, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ds.h, pointer(f)))
+end
+
+"`run_system` with the default step function: ONE `mavi_step(h, nsteps)` and one download."
+function run_system(system::CUDASystem; tf=nothing, num_steps=nothing, step_func=nothing)
+    if !isnothing(step_func)
+        return invoke(run_system, Tuple{Any}, system; tf=tf, num_steps=num_steps, step_func=step_func)
+    end
+    n = num_steps
+    if !isnothing(tf)
+        t, n = system.time_info.time, 0
+        while t < tf          # the reference's own loop condition on the Float64 accumulation time += dt
+            t += system.int_cfg.dt
+            n += 1
+        end
+    end
+    ds = handle(system)
+    check(ds, ccall((:mavi_step, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Cvoid}), ds.h, n, C_NULL))
+    for _ in 1:n
+        system.time_info.time += system.int_cfg.dt
+        system.time_info.num_steps += 1
+    end
+    sync_to_host!(system)
+end
+
+"(kinetic_energy, potential_energy) as device block reductions (src/quantities.jl)."
+function device_energies(system::System; stencil_only=false)
+    ds = handle(system)
+    ke, pe = Ref(0.0), Ref(0.0)
+    check(ds, ccall((:mavi_energies, LIB), Int32, (Ptr{Cvoid}, Int32, Ref{Float64}, Ref{Float64}), ds.h, stencil_only ? 1 : 0, ke, pe))
+    return ke[], pe[]
+end
+
+end # module
