@@ -119,11 +119,17 @@ class System:
     def sync_to_host(self):
         """`sync_to_host!(system)`: device state -> `system.state` arrays, and TimeInfo."""
         st = self.state
-        pos = np.empty((self._n, 2), dtype=self._dtype)
-        second = np.empty(st.second.shape, dtype=self._dtype)
+
+        def direct(a):  # download straight into the caller's array when layout and dtype allow (pinned buffers stay pinned)
+            return a.flags["C_CONTIGUOUS"] and a.flags["WRITEABLE"] and a.dtype == self._dtype
+
+        pos = st.pos if direct(st.pos) else np.empty((self._n, 2), dtype=self._dtype)
+        second = st.second if direct(st.second) else np.empty(st.second.shape, dtype=self._dtype)
         self._check(self._lib.mavi_download_state(self._h, _ptr(pos), _ptr(second)))
-        st.pos[...] = pos
-        st.second[...] = second
+        if pos is not st.pos:
+            st.pos[...] = pos
+        if second is not st.second:
+            st.second[...] = second
         ns, t = C.c_int64(), C.c_double()
         self._check(self._lib.mavi_get_time(self._h, C.byref(ns), C.byref(t)))
         self.time_info.num_steps, self.time_info.time = ns.value, t.value
