@@ -252,12 +252,12 @@ static int allocate(Handle *h) {
   if ((st = dev_alloc(h, &a.fix_idx, n))) return st;
   if ((st = dev_alloc(h, &a.fix_pos, n))) return st;
   if ((st = dev_alloc(h, &a.reduce_buf, 4096))) return st;
-  if ((st = dev_alloc(h, &a.cta_first, n / TPB + 2))) return st;
+  if ((st = dev_alloc(h, &a.cta_first, n / RPB + 2))) return st;
   CUDA_TRY(h, cudaMallocHost((void **)&h->flags_host, FLAG_COUNT * sizeof(int)));
   CUDA_TRY(h, cudaMemsetAsync(a.flags, 0, FLAG_COUNT * sizeof(int), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(a.count, 0, nc * sizeof(int), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(a.st_force, 0, n * sizeof(double2), h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(a.cta_first, 0, (n / TPB + 2) * sizeof(int), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(a.cta_first, 0, (n / RPB + 2) * sizeof(int), h->stream));
   if (h->second_kind == SECOND_RING_POL) return rings_allocate(h);
   return MAVI_OK;
 }

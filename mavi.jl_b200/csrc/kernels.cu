@@ -15,37 +15,47 @@ static inline int nblk(long long n, int tpb = TPB) { return (int)((n + tpb - 1) 
   } while (0)
 
 // rank (dense particle index) -> slot.  Ranks < n_active enumerate the tile populations in TILE-ROW-MAJOR order
-// (tile_prefix is the exclusive scan in that order); cta_first[b] is the order index of the tile holding rank b*TPB.
-// Ranks >= n_active are the inactive tail.  The CTA-level version stages the ~8 prefix entries a block needs in shared
-// memory so that threads do not chase dependent global loads.
+// (tile_prefix is the exclusive scan in that order); cta_first[b] is the order index of the tile holding rank b*RPB.
+// Ranks >= n_active are the inactive tail.  Blocks stage the prefix entries they need in shared memory once
+// (rank_window_stage) so that threads do not chase dependent global loads.
 __device__ __forceinline__ int slot_of_rank(const DevParams &p, const int *__restrict__ tile_prefix,
                                             const int *__restrict__ cta_first, int rank) {
   if (rank >= p.n_active) return p.tail_base + (rank - p.n_active);
-  int o = __ldg(cta_first + rank / TPB);
+  int o = __ldg(cta_first + rank / RPB);
   while (rank >= __ldg(tile_prefix + o + 1)) ++o;
   return tile_of_order(p, o) * p.cap + (rank - __ldg(tile_prefix + o));
 }
 
-constexpr int RANK_WIN = 32;  // prefix entries staged per CTA (a block of 256 ranks rarely spans more tiles)
-__device__ __forceinline__ int slot_of_rank_cta(const DevParams &p, const int *__restrict__ tile_prefix,
-                                                const int *__restrict__ cta_first, int rank, int *s_win) {
-  // all threads of the block must call this (it synchronises); rank may be >= p.n
-  const int o0 = (blockIdx.x * TPB < p.n_active) ? __ldg(cta_first + blockIdx.x) : 0;
+constexpr int RANK_WIN = 64;  // prefix entries staged per block (RPB ranks rarely span more tiles)
+// all threads of the block call this once; s_win needs RANK_WIN + 1 ints.  Contains a barrier.
+__device__ __forceinline__ void rank_window_stage(const DevParams &p, const int *__restrict__ tile_prefix,
+                                                  const int *__restrict__ cta_first, int *s_win) {
+  const bool in_tiles = blockIdx.x * RPB < p.n_active;
+  const int o0 = in_tiles ? __ldg(cta_first + blockIdx.x) : 0;
   if (threadIdx.x <= RANK_WIN) {
     const int o = o0 + threadIdx.x;
-    s_win[threadIdx.x] = (blockIdx.x * TPB < p.n_active && o <= p.nt_ord) ? __ldg(tile_prefix + o) : 0x7fffffff;
+    s_win[threadIdx.x] = (in_tiles && o <= p.nt_ord) ? __ldg(tile_prefix + o) : 0x7fffffff;
   }
   __syncthreads();
+}
+// slot of `rank` (a rank of this block) and the order index of its tile (-1 for the inactive tail)
+__device__ __forceinline__ int slot_from_window(const DevParams &p, const int *__restrict__ tile_prefix,
+                                                const int *__restrict__ cta_first, int rank, const int *s_win,
+                                                int *order_out) {
+  *order_out = -1;
   if (rank >= p.n_active) return p.tail_base + (rank - p.n_active);
-  // number of window entries (beyond the first) that are <= rank = tile offset inside the window
   int lo = 0;
 #pragma unroll
   for (int step = RANK_WIN / 2; step >= 1; step >>= 1)
     if (s_win[lo + step] <= rank) lo += step;
-  int o = o0 + lo;
-  if (lo == RANK_WIN - 1)  // window exhausted (very sparse tiles): finish with the global walk
+  int o = __ldg(cta_first + blockIdx.x) + lo;
+  int base = s_win[lo];
+  if (lo == RANK_WIN - 1) {  // window exhausted (very sparse tiles): finish with the global walk
     while (rank >= __ldg(tile_prefix + o + 1)) ++o;
-  return tile_of_order(p, o) * p.cap + (rank - ((lo == RANK_WIN - 1) ? __ldg(tile_prefix + o) : s_win[lo]));
+    base = __ldg(tile_prefix + o);
+  }
+  *order_out = o;
+  return tile_of_order(p, o) * p.cap + (rank - base);
 }
 
 // =========================================================================================================
@@ -193,7 +203,7 @@ __global__ void k_cta_first(const __grid_constant__ DevParams p, const int *__re
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= p.nt_ord) return;
   const int lo = tile_prefix[t], hi = tile_prefix[t + 1];
-  for (int b = (lo + TPB - 1) / TPB; b * TPB < hi; b++) cta_first[b] = t;
+  for (int b = (lo + RPB - 1) / RPB; b * RPB < hi; b++) cta_first[b] = t;
 }
 
 // ---- exclusive prefix scan (reduce / top / final), 4096 items per block ------------------------------------
@@ -659,6 +669,151 @@ __device__ __forceinline__ double2 cell_pair_force(const DevParams &p, const int
   return make_double2(fx, fy);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// CTA-cooperative staging.  The 256 ranks of a CTA are consecutive tiles of ONE tile row (tile-row-major order):
+// columns [cfirst, clast] x 32 cell rows.  One warp per column copies, for columns cfirst-1 .. clast+1, the cell
+// row above the tile row, the tile itself and the cell row below it into shared memory, back to back, and writes
+// the start of every cell row.  After that the neighbours of ANY particle of the block are 3 runs that are
+// contiguous in shared memory — tile holes, periodic wrap and grid edges have been resolved by the copy — and the
+// pair loop reads LDS.128 only.  CTAs that straddle two tile rows, span too many (sparse) tiles or overflow the
+// staging area fall back to the per-thread segment-table walk.
+constexpr int GMAX = 46;                 // block columns staged at most (plus the two side columns)
+constexpr int SROWS = MAVI_TR + 2;       // cell rows per staged column: above + 32 + below
+
+struct BlockStage {
+  int ok, use_mi, cfirst, ncol, r0, o_last;
+  int tile_src[GMAX + 2];                // global slot of the first particle of the column's tile
+  int src_a[GMAX + 2], src_b[GMAX + 2];  // global slot of the cell above / below the tile
+  int la[GMAX + 2], lt[GMAX + 2], lb[GMAX + 2];
+  int off[GMAX + 3];                     // start of each staged column in s_pos (exclusive scan of la+lt+lb)
+  int sstart[GMAX + 2][SROWS + 1];       // start (in s_pos) of each staged cell row; [SROWS] = end of the column
+};
+
+// rank_last_order: order index of the tile holding the last tiled rank of this block (computed by the caller)
+template <bool PER>
+__device__ __forceinline__ void block_stage(const DevParams &p, const int *__restrict__ tstart,
+                                            const int *__restrict__ cta_first, const double2 *__restrict__ pos,
+                                            int o_last, bool exact_minimg, BlockStage *bs, double2 *s_pos,
+                                            int s_pos_cap) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int R = p.num_rows, Cn = p.num_cols;
+  // ---- block geometry (every thread computes the same values: no serial section)
+  bool ok = o_last >= 0;
+  int o_first = 0, tr = 0, ncol = 0, cfirst = 0;
+  if (ok) {
+    o_first = __ldg(cta_first + blockIdx.x);
+    tr = div_cols(p, o_first);
+    ncol = o_last - o_first + 3;  // block columns + the two side columns
+    ok = tr == div_cols(p, o_last) && ncol <= GMAX + 2;
+    cfirst = o_first - tr * p.ord_cols + p.ord_col0;
+  }
+  const int r0 = tr * MAVI_TR;
+  if (threadIdx.x == 0) {
+    bs->ok = ok ? 1 : 0;
+    bs->use_mi = (PER && (exact_minimg || !p.fast_interior)) ? 1 : 0;
+    bs->cfirst = cfirst;
+    bs->ncol = ncol;
+    bs->r0 = r0;
+  }
+  if (!ok) {
+    __syncthreads();
+    return;
+  }
+  // ---- per-column descriptors, one thread per staged column (independent loads, issued together)
+  int c = 0;
+  bool exists = false;
+  if (threadIdx.x < ncol) {
+    const int j = threadIdx.x;
+    c = cfirst - 1 + j;
+    exists = true;
+    bool wrapped = false;
+    if (c < 0) { if (p.wrap_cols) { c = Cn - 1; wrapped = true; } else exists = false; }
+    else if (c >= Cn) { if (p.wrap_cols) { c = 0; wrapped = true; } else exists = false; }
+    if (exists && p.slab && ((c == 0 && p.seam_left) || (c == Cn - 1 && p.seam_right))) wrapped = true;
+    int ra = r0 - 1, rb = r0 + MAVI_TR;
+    bool has_a = exists, has_b = exists;
+    if (ra < 0) { if (p.wrap_rows) { ra = R - 1; wrapped = wrapped || exists; } else has_a = false; }
+    if (rb >= R) { if (p.wrap_rows) { rb = 0; wrapped = wrapped || exists; } else has_b = false; }
+    int la = 0, lt = 0, lb = 0, sa = 0, st = 0, sb = 0;
+    if (exists) {
+      const int *tt = tstart + (size_t)(c * p.tpc + tr) * (MAVI_TR + 1);
+      const int qa = has_a ? tq_of(p, c, ra) : 0, qb = has_b ? tq_of(p, c, rb) : 0;
+      st = __ldg(tt);
+      const int et = __ldg(tt + MAVI_TR);
+      const int a0 = has_a ? __ldg(tstart + qa) : 0, a1 = has_a ? __ldg(tstart + qa + 1) : 0;
+      const int b0 = has_b ? __ldg(tstart + qb) : 0, b1 = has_b ? __ldg(tstart + qb + 1) : 0;
+      lt = et - st; sa = a0; la = a1 - a0; sb = b0; lb = b1 - b0;
+    }
+    bs->tile_src[j] = st; bs->src_a[j] = sa; bs->src_b[j] = sb;
+    bs->la[j] = la; bs->lt[j] = lt; bs->lb[j] = lb;
+    if (wrapped && PER) bs->use_mi = 1;
+  }
+  __syncthreads();
+  // ---- dense packing: exclusive scan of the column sizes (warp 0; ncol <= 64)
+  if (w == 0) {
+    const int j0 = 2 * lane, j1 = 2 * lane + 1;
+    const int s0 = j0 < ncol ? bs->la[j0] + bs->lt[j0] + bs->lb[j0] : 0;
+    const int s1 = j1 < ncol ? bs->la[j1] + bs->lt[j1] + bs->lb[j1] : 0;
+    int incl = s0 + s1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int excl = incl - (s0 + s1);
+    if (j0 <= ncol) bs->off[j0] = excl;
+    if (j1 <= ncol) bs->off[j1] = excl + s0;
+    if (lane == 31 && incl > s_pos_cap) bs->ok = 0;  // staging area too small (very dense tiles): fall back
+  }
+  __syncthreads();
+  if (!bs->ok) return;
+  // ---- copy: one warp per column (coalesced), plus the starts of its cell rows
+  for (int j = w; j < ncol; j += TPB / 32) {
+    const int off = bs->off[j], la = bs->la[j], lt = bs->lt[j], lb = bs->lb[j];
+    const int src_t = bs->tile_src[j], src_a = bs->src_a[j], src_b = bs->src_b[j];
+    int cj = cfirst - 1 + j;
+    if (cj < 0) cj = Cn - 1;
+    else if (cj >= Cn) cj = 0;
+    const int *tt = tstart + (size_t)(cj * p.tpc + tr) * (MAVI_TR + 1);
+    // cell-row starts: row 0 = above, 1..rows = tile rows, rows+1 = below (directly after the last EXISTING row of a
+    // partial tile, so that the 3-row window of that row reaches it), everything after = end of the column
+    const int rows = min(MAVI_TR, R - r0);
+    for (int r = lane; r <= SROWS; r += 32) {
+      int v;
+      if (r == 0) v = off;
+      else if (r <= rows + 1) v = off + la + ((la + lt + lb) ? (__ldg(tt + (r - 1)) - src_t) : 0);
+      else v = off + la + lt + lb;
+      bs->sstart[j][r] = v;
+    }
+    for (int i = lane; i < la; i += 32) s_pos[off + i] = __ldg(pos + src_a + i);
+    for (int i = lane; i < lt; i += 32) s_pos[off + la + i] = __ldg(pos + src_t + i);
+    for (int i = lane; i < lb; i += 32) s_pos[off + la + lt + i] = __ldg(pos + src_b + i);
+  }
+  __syncthreads();
+}
+
+// pair force of the particle in slot k (cell = (col,row) of the staged block) from the staged positions
+template <int DYN, bool MINIMG>
+__device__ __forceinline__ void block_walk(const DevParams &p, const BlockStage *bs, const double2 *s_pos, int col,
+                                           int row, int k, double2 ri, double &fx, double &fy) {
+  const int jj = col - bs->cfirst + 1;   // staged column of the particle's own column
+  const int lr = row - bs->r0 + 1;       // staged row (1..32)
+  const int a0 = bs->sstart[jj - 1][lr - 1], b0 = bs->sstart[jj - 1][lr + 2];
+  const int a1 = bs->sstart[jj][lr - 1], b1 = bs->sstart[jj][lr + 2];
+  const int a2 = bs->sstart[jj + 1][lr - 1], b2 = bs->sstart[jj + 1][lr + 2];
+  const int self = bs->sstart[jj][1] + (k - bs->tile_src[jj]);
+  const int c1 = b0 - a0;              // neighbours t <  c1        -> a0 + t
+  const int c2 = c1 + (self - a1);     //          c1 <= t < c2    -> a1 + (t - c1)
+  const int c3 = c2 + (b1 - self - 1); //          c2 <= t < c3    -> self + 1 + (t - c2)
+  const int total = c3 + (b2 - a2);    //          c3 <= t         -> a2 + (t - c3)
+  const int d1 = (a1 - c1) - a0, d3 = (a2 - c3) - (a1 - c1) - 1;
+#pragma unroll 2
+  for (int t = 0; t < total; ++t) {
+    const int s = t + a0 + (t >= c1 ? d1 : 0) + (t >= c2 ? 1 : 0) + (t >= c3 ? d3 : 0);
+    accumulate_pair<DYN, MINIMG>(p, ri, s_pos[s], fx, fy);
+  }
+}
+
 // ALLP: chunks === nothing -> all pairs over active ids (src/integration.jl:197-224); slots = original order.
 // exact_minimg: force the minimum image everywhere (pass B after an abnormally large drift).
 //
@@ -666,10 +821,20 @@ __device__ __forceinline__ double2 cell_pair_force(const DevParams &p, const int
 // 8-adjacent cells, so |dr| < 2 cell widths <= size/4 on a grid of >= 8 cells per axis and the reference's
 // `abs(dr) > size/2` test is false -> skipped EXACTLY.  Stale cells (Verlet pass 2) are covered by the per-step
 // displacement guard (FLAG_BIGMOVE) which switches pass B to the exact path.
+struct ForceCtx {
+  const BlockStage *bs;  // CTA staging descriptor (shared memory)
+  const double2 *s_pos;  // staged positions
+  int *tbl;              // this thread's column of the fallback segment table (aliases s_pos)
+};
+
+constexpr int BS_BYTES = (sizeof(BlockStage) + 15) / 16 * 16;
+constexpr int SPOS_CAP = 2304;  // staged positions per CTA (36 KB); the fallback table needs 16 KB of the same area
+constexpr int PASS_SMEM = BS_BYTES + SPOS_CAP * (int)sizeof(double2);
+
 template <int DYN, bool PER, bool ALLP>
 __device__ __forceinline__ double2 pair_force(const DevParams &p, const int *__restrict__ tstart,
                                               const double2 *__restrict__ pos, const unsigned int *__restrict__ idflag,
-                                              int *__restrict__ lst, int cell, int k, double2 ri, bool exact_minimg) {
+                                              const ForceCtx &fc, int cell, int k, double2 ri, bool exact_minimg) {
   if (ALLP) {
     double fx = 0.0, fy = 0.0;
     for (int j = 0; j < p.n; j++) {
@@ -678,7 +843,34 @@ __device__ __forceinline__ double2 pair_force(const DevParams &p, const int *__r
     }
     return make_double2(fx, fy);
   }
-  return cell_pair_force<DYN, PER>(p, tstart, pos, lst, cell, k, ri, exact_minimg);
+  if (fc.bs->ok) {
+    const int col = div_rows(p, cell), row = cell - col * p.num_rows;
+    double fx = 0.0, fy = 0.0;
+    if (PER && fc.bs->use_mi) block_walk<DYN, true>(p, fc.bs, fc.s_pos, col, row, k, ri, fx, fy);
+    else block_walk<DYN, false>(p, fc.bs, fc.s_pos, col, row, k, ri, fx, fy);
+    return make_double2(fx, fy);
+  }
+  return cell_pair_force<DYN, PER>(p, tstart, pos, fc.tbl, cell, k, ri, exact_minimg);
+}
+
+// common prologue of the rank-mapped force kernels (all threads take part): stage the rank window, find the last
+// tiled rank's tile, stage the block
+template <bool PER, bool ALLP>
+__device__ __forceinline__ void force_prologue(const DevParams &p, const int *__restrict__ tstart,
+                                               const int *__restrict__ tile_prefix, const int *__restrict__ cta_first,
+                                               const double2 *__restrict__ pos, bool exact_minimg, unsigned char *dsm,
+                                               int *s_win, ForceCtx &fc) {
+  BlockStage *bs = reinterpret_cast<BlockStage *>(dsm);
+  double2 *s_pos = reinterpret_cast<double2 *>(dsm + BS_BYTES);
+  fc.bs = bs;
+  fc.s_pos = s_pos;
+  fc.tbl = reinterpret_cast<int *>(dsm + BS_BYTES) + threadIdx.x;
+  if (ALLP) return;
+  rank_window_stage(p, tile_prefix, cta_first, s_win);
+  int o_last = -1;
+  const int last_rank = min((int)(blockIdx.x * RPB + RPB - 1), p.n_active - 1);
+  if (last_rank >= (int)(blockIdx.x * RPB)) slot_from_window(p, tile_prefix, cta_first, last_rank, s_win, &o_last);
+  block_stage<PER>(p, tstart, cta_first, pos, o_last, exact_minimg, bs, s_pos, SPOS_CAP);
 }
 
 // The particle in slot k (sorted under cell c_old) now sits at (x, y).  If update_particle_chunk! would bin it
@@ -717,24 +909,36 @@ __device__ __forceinline__ void note_if_moved(const DevParams &p, const MoverSin
   }
 }
 
+// Every force kernel: block prologue (staging), then each thread handles RPB/TPB particles of the block.
+#define MAVI_FORCE_KERNEL_PROLOGUE(POS, EXACT)                                                    \
+  extern __shared__ __align__(16) unsigned char dsm[];                                            \
+  __shared__ int s_win[RANK_WIN + 1];                                                             \
+  ForceCtx fc;                                                                                    \
+  force_prologue<PER, ALLP>(p, tstart, tile_prefix, cta_first, POS, EXACT, dsm, s_win, fc);
+
+#define MAVI_FOR_EACH_PARTICLE                                                                    \
+  for (int it = 0; it < RPB / TPB; ++it) {                                                        \
+    const int rank = blockIdx.x * RPB + it * TPB + threadIdx.x;                                   \
+    if (rank >= p.n) break;                                                                       \
+    int order_;                                                                                   \
+    const int k = ALLP ? rank : slot_from_window(p, tile_prefix, cta_first, rank, s_win, &order_);
+
 // clean_forces! + calc_forces! (+ calc_walls_forces!): the force state after src/integration.jl:508-511.
 template <int DYN, bool PER, bool ALLP>
 __global__ void __launch_bounds__(TPB) k_force_only(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
                              const int *__restrict__ tile_prefix, const int *__restrict__ cta_first,
                              const int *__restrict__ cell, const unsigned int *__restrict__ idflag,
                              const double2 *__restrict__ pos, double2 *__restrict__ force, int with_walls) {
-  __shared__ int s_lst[ALLP ? 1 : 2 * SEG_MAX * TPB];
-  __shared__ int s_win[RANK_WIN + 1];
-  int rank = blockIdx.x * blockDim.x + threadIdx.x;
-  const int k = ALLP ? rank : slot_of_rank_cta(p, tile_prefix, cta_first, rank, s_win);
-  if (rank >= p.n) return;
-  double2 F = make_double2(0.0, 0.0);
-  if (!(idflag[k] & MAVI_INACTIVE_BIT)) {
-    double2 r = pos[k];
-    F = pair_force<DYN, PER, ALLP>(p, tstart, pos, idflag, s_lst + threadIdx.x, ALLP ? 0 : cell[k], k, r, false);
-    if (with_walls && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
+  MAVI_FORCE_KERNEL_PROLOGUE(pos, false)
+  MAVI_FOR_EACH_PARTICLE
+    double2 F = make_double2(0.0, 0.0);
+    if (!(idflag[k] & MAVI_INACTIVE_BIT)) {
+      double2 r = pos[k];
+      F = pair_force<DYN, PER, ALLP>(p, tstart, pos, idflag, fc, ALLP ? 0 : cell[k], k, r, false);
+      if (with_walls && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
+    }
+    force[k] = F;
   }
-  force[k] = F;
 }
 
 // newton_step! first half (src/integration.jl:507-512 + update_verlet! :418-424):
@@ -745,26 +949,24 @@ __global__ void __launch_bounds__(TPB) k_newton_a(const __grid_constant__ DevPar
                            const int *__restrict__ cell, const unsigned int *__restrict__ idflag,
                            const double2 *__restrict__ pos_in, const double2 *__restrict__ vel,
                            double2 *__restrict__ pos_out, double2 *__restrict__ f1, int *__restrict__ flags) {
-  __shared__ int s_lst[ALLP ? 1 : 2 * SEG_MAX * TPB];
-  __shared__ int s_win[RANK_WIN + 1];
-  int rank = blockIdx.x * blockDim.x + threadIdx.x;
-  const int k = ALLP ? rank : slot_of_rank_cta(p, tile_prefix, cta_first, rank, s_win);
-  if (rank >= p.n) return;
-  double2 r = pos_in[k];
-  double2 F = make_double2(0.0, 0.0);
-  if (!(idflag[k] & MAVI_INACTIVE_BIT)) {
-    F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, s_lst + threadIdx.x, ALLP ? 0 : cell[k], k, r, false);
-    if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
+  MAVI_FORCE_KERNEL_PROLOGUE(pos_in, false)
+  MAVI_FOR_EACH_PARTICLE
+    double2 r = pos_in[k];
+    double2 F = make_double2(0.0, 0.0);
+    if (!(idflag[k] & MAVI_INACTIVE_BIT)) {
+      F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, fc, ALLP ? 0 : cell[k], k, r, false);
+      if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
+    }
+    double2 v = vel[k];
+    double mx = v.x * p.dt + F.x * p.term, my = v.y * p.dt + F.y * p.term;
+    r.x = r.x + mx;
+    r.y = r.y + my;
+    // displacement guard of the min-image shortcut: a drift beyond one cell in one step makes pass B take the exact
+    // (minimum-image everywhere) path.  Never happens in a stable run; keeps the fast path assumption-free.
+    if (!ALLP && PER && !(fabs(mx) <= p.cl && fabs(my) <= p.ch)) flags[FLAG_BIGMOVE] = 1;
+    pos_out[k] = r;
+    f1[k] = F;
   }
-  double2 v = vel[k];
-  double mx = v.x * p.dt + F.x * p.term, my = v.y * p.dt + F.y * p.term;
-  r.x = r.x + mx;
-  r.y = r.y + my;
-  // displacement guard of the interior fast path: a drift beyond one cell in one step makes pass B take the exact
-  // (minimum-image everywhere) path.  Never happens in a stable run; keeps the fast path assumption-free.
-  if (!ALLP && PER && !(fabs(mx) <= p.cl && fabs(my) <= p.ch)) flags[FLAG_BIGMOVE] = 1;
-  pos_out[k] = r;
-  f1[k] = F;
 }
 
 // newton_step! second half (update_verlet! :426-430, walls! :513): F2 on the drifted positions with the STALE cell
@@ -777,32 +979,31 @@ __global__ void __launch_bounds__(TPB) k_newton_b(const __grid_constant__ DevPar
                            const unsigned int *__restrict__ idflag, const double2 *__restrict__ pos_in,
                            double2 *__restrict__ vel, const double2 *__restrict__ f1, double2 *__restrict__ f2,
                            int *__restrict__ fix_idx, double2 *__restrict__ fix_pos, const MoverSink ms) {
-  __shared__ int s_lst[ALLP ? 1 : 2 * SEG_MAX * TPB];
-  __shared__ int s_win[RANK_WIN + 1];
-  int rank = blockIdx.x * blockDim.x + threadIdx.x;
-  const int k = ALLP ? rank : slot_of_rank_cta(p, tile_prefix, cta_first, rank, s_win);
-  if (rank >= p.n) return;
-  double2 r = pos_in[k];
-  double2 F = make_double2(0.0, 0.0);
-  const bool active = !(idflag[k] & MAVI_INACTIVE_BIT);
-  const int c = ALLP ? 0 : ms.cell[k];
-  if (active) F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, s_lst + threadIdx.x, c, k, r, !ALLP && ms.flags[FLAG_BIGMOVE] != 0);
-  double2 v = vel[k];
-  double2 Fo = f1[k];
-  v.x = v.x + p.hdt * (F.x + Fo.x);
-  v.y = v.y + p.hdt * (F.y + Fo.y);
-  if (active) {
-    const double x0 = r.x, y0 = r.y;
-    apply_walls<true>(p, r.x, r.y, v.x, v.y, p.particle_radius);
-    if (r.x != x0 || r.y != y0) {
-      int m = atomicAdd(&ms.flags[FLAG_NFIX], 1);
-      fix_idx[m] = k;
-      fix_pos[m] = r;
+  const bool exact = !ALLP && ms.flags[FLAG_BIGMOVE] != 0;
+  MAVI_FORCE_KERNEL_PROLOGUE(pos_in, exact)
+  MAVI_FOR_EACH_PARTICLE
+    double2 r = pos_in[k];
+    double2 F = make_double2(0.0, 0.0);
+    const bool active = !(idflag[k] & MAVI_INACTIVE_BIT);
+    const int c = ALLP ? 0 : ms.cell[k];
+    if (active) F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, fc, c, k, r, exact);
+    double2 v = vel[k];
+    double2 Fo = f1[k];
+    v.x = v.x + p.hdt * (F.x + Fo.x);
+    v.y = v.y + p.hdt * (F.y + Fo.y);
+    if (active) {
+      const double x0 = r.x, y0 = r.y;
+      apply_walls<true>(p, r.x, r.y, v.x, v.y, p.particle_radius);
+      if (r.x != x0 || r.y != y0) {
+        int m = atomicAdd(&ms.flags[FLAG_NFIX], 1);
+        fix_idx[m] = k;
+        fix_pos[m] = r;
+      }
+      if (!ALLP) note_if_moved(p, ms, k, c, r.x, r.y);
     }
-    if (!ALLP) note_if_moved(p, ms, k, c, r.x, r.y);
+    vel[k] = v;
+    f2[k] = F;
   }
-  vel[k] = v;
-  f2[k] = F;
 }
 
 __global__ void k_apply_pos_fixes(const int *__restrict__ flags, const int *__restrict__ fix_idx,
@@ -819,59 +1020,57 @@ __global__ void __launch_bounds__(TPB) k_self_propelled(const __grid_constant__ 
                                  const unsigned int *__restrict__ idflag, const double2 *__restrict__ pos_in,
                                  double *__restrict__ ang, double2 *__restrict__ pos_out, double2 *__restrict__ force,
                                  const double *__restrict__ noise, unsigned long long step, const MoverSink ms) {
-  __shared__ int s_lst[ALLP ? 1 : 2 * SEG_MAX * TPB];
-  __shared__ int s_win[RANK_WIN + 1];
-  int rank = blockIdx.x * blockDim.x + threadIdx.x;
-  const int k = ALLP ? rank : slot_of_rank_cta(p, tile_prefix, cta_first, rank, s_win);
-  if (rank >= p.n) return;
-  const unsigned int idf = idflag[k];
-  const bool active = !(idf & MAVI_INACTIVE_BIT);
-  const unsigned int id = idf & ~MAVI_INACTIVE_BIT;
-  const int c = ALLP ? 0 : ms.cell[k];
-  double2 r = pos_in[k];
-  double2 F = make_double2(0.0, 0.0);
-  if (active) {
-    F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, s_lst + threadIdx.x, c, k, r, false);
-    if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
-  }
-  force[k] = F;
-  if ((int)id < p.n_count) {
-    double theta = ang[k];
-    double sn, cs;
-    sincos(theta, &sn, &cs);
-    if (DYN == MAVI_DYN_SZABO) {
-      const double vo = p.dyn[0], mu = p.dyn[1], relax_time = p.dyn[2], drot = p.dyn[7];
-      double velx = vo * cs + mu * F.x, vely = vo * sn + mu * F.y;
-      double speed = sqrt(fabs(velx) + fabs(vely));  // sqrt(sum(abs, vel)) (sic), :448
-      double cross_prod = speed > 0.0 ? (cs * vely - sn * velx) / speed : 0.0;
-      if (fabs(cross_prod) > 1.0) cross_prod = sign_d(cross_prod);
-      double nz = 0.0;
-      if (drot != 0.0) nz = (p.rng_mode == MAVI_RNG_HOST_NOISE) ? (noise ? noise[id] : 0.0) : philox_normal(p.seed, id, step);
-      double d_theta = 1.0 / relax_time * asin(cross_prod) * p.dt + sqrt(2.0 * drot * p.dt) * nz;
-      r.x += velx * p.dt;
-      r.y += vely * p.dt;
-      ang[k] = theta + d_theta;
-    } else {
-      const double vo = p.dyn[0], tumble_rate = p.dyn[3];
-      double velx = vo * cs + F.x, vely = vo * sn + F.y;
-      r.x += velx * p.dt;
-      r.y += vely * p.dt;
-      double u, u2;
-      if (p.rng_mode == MAVI_RNG_HOST_NOISE) {
-        u = noise ? noise[2 * (size_t)id] : 1.0;
-        u2 = noise ? noise[2 * (size_t)id + 1] : 0.0;
-      } else {
-        philox_uniform2(p.seed, id, step, u, u2);
-      }
-      if (u < tumble_rate * p.dt) ang[k] = 6.283185307179586 * u2;  // 2*pi*rand(), :495
+  MAVI_FORCE_KERNEL_PROLOGUE(pos_in, false)
+  MAVI_FOR_EACH_PARTICLE
+    const unsigned int idf = idflag[k];
+    const bool active = !(idf & MAVI_INACTIVE_BIT);
+    const unsigned int id = idf & ~MAVI_INACTIVE_BIT;
+    const int c = ALLP ? 0 : ms.cell[k];
+    double2 r = pos_in[k];
+    double2 F = make_double2(0.0, 0.0);
+    if (active) {
+      F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, fc, c, k, r, false);
+      if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
     }
+    force[k] = F;
+    if ((int)id < p.n_count) {
+      double theta = ang[k];
+      double sn, cs;
+      sincos(theta, &sn, &cs);
+      if (DYN == MAVI_DYN_SZABO) {
+        const double vo = p.dyn[0], mu = p.dyn[1], relax_time = p.dyn[2], drot = p.dyn[7];
+        double velx = vo * cs + mu * F.x, vely = vo * sn + mu * F.y;
+        double speed = sqrt(fabs(velx) + fabs(vely));  // sqrt(sum(abs, vel)) (sic), :448
+        double cross_prod = speed > 0.0 ? (cs * vely - sn * velx) / speed : 0.0;
+        if (fabs(cross_prod) > 1.0) cross_prod = sign_d(cross_prod);
+        double nz = 0.0;
+        if (drot != 0.0) nz = (p.rng_mode == MAVI_RNG_HOST_NOISE) ? (noise ? noise[id] : 0.0) : philox_normal(p.seed, id, step);
+        double d_theta = 1.0 / relax_time * asin(cross_prod) * p.dt + sqrt(2.0 * drot * p.dt) * nz;
+        r.x += velx * p.dt;
+        r.y += vely * p.dt;
+        ang[k] = theta + d_theta;
+      } else {
+        const double vo = p.dyn[0], tumble_rate = p.dyn[3];
+        double velx = vo * cs + F.x, vely = vo * sn + F.y;
+        r.x += velx * p.dt;
+        r.y += vely * p.dt;
+        double u, u2;
+        if (p.rng_mode == MAVI_RNG_HOST_NOISE) {
+          u = noise ? noise[2 * (size_t)id] : 1.0;
+          u2 = noise ? noise[2 * (size_t)id + 1] : 0.0;
+        } else {
+          philox_uniform2(p.seed, id, step, u, u2);
+        }
+        if (u < tumble_rate * p.dt) ang[k] = 6.283185307179586 * u2;  // 2*pi*rand(), :495
+      }
+    }
+    if (active) {
+      double vx = 0.0, vy = 0.0;
+      apply_walls<false>(p, r.x, r.y, vx, vy, p.particle_radius);
+      if (!ALLP) note_if_moved(p, ms, k, c, r.x, r.y);
+    }
+    pos_out[k] = r;
   }
-  if (active) {
-    double vx = 0.0, vy = 0.0;
-    apply_walls<false>(p, r.x, r.y, vx, vy, p.particle_radius);
-    if (!ALLP) note_if_moved(p, ms, k, c, r.x, r.y);
-  }
-  pos_out[k] = r;
 }
 
 // ---- dispatch over (dynamics, periodic, all-pairs) ----------------------------------------------------------
@@ -891,7 +1090,7 @@ static MoverSink mover_sink(const DevArrays &a) {
 void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool with_wall_forces) {
   const bool allp = p.num_cells == 0;
 #define CALL(D, P, A) \
-  MAVI_LAUNCH(c, (k_force_only<D, P, A>), nblk(p.n), TPB, 0, p, a.tstart, a.tile_prefix, a.cta_first, a.cell, a.idflag, a.pos[0], a.force, (int)with_wall_forces)
+  MAVI_LAUNCH(c, (k_force_only<D, P, A>), nblk(p.n, RPB), TPB, (A ? 64 : PASS_SMEM), p, a.tstart, a.tile_prefix, a.cta_first, a.cell, a.idflag, a.pos[0], a.force, (int)with_wall_forces)
   switch (p.dynamics) {
     case MAVI_DYN_LJ: MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, allp, CALL); break;
     case MAVI_DYN_HARMTRUNC: MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, allp, CALL); break;
@@ -904,7 +1103,7 @@ void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &
 void launch_newton_a(const LaunchCtx &c, const DevParams &p, const DevArrays &a) {
   const bool allp = p.num_cells == 0;
 #define CALL(D, P, A) \
-  MAVI_LAUNCH(c, (k_newton_a<D, P, A>), nblk(p.n), TPB, 0, p, a.tstart, a.tile_prefix, a.cta_first, a.cell, a.idflag, a.pos[0], a.vel, a.pos[1], a.force_old, a.flags)
+  MAVI_LAUNCH(c, (k_newton_a<D, P, A>), nblk(p.n, RPB), TPB, (A ? 64 : PASS_SMEM), p, a.tstart, a.tile_prefix, a.cta_first, a.cell, a.idflag, a.pos[0], a.vel, a.pos[1], a.force_old, a.flags)
   if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, allp, CALL);
   else MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, allp, CALL);
 #undef CALL
@@ -915,7 +1114,7 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p, const DevArrays &a)
   const MoverSink ms = mover_sink(a);
   // reads the drifted positions pos[1] (which become the current positions after the sparse wall fix-ups)
 #define CALL(D, P, A) \
-  MAVI_LAUNCH(c, (k_newton_b<D, P, A>), nblk(p.n), TPB, 0, p, a.tstart, a.tile_prefix, a.cta_first, a.idflag, a.pos[1], a.vel, a.force_old, a.force, a.fix_idx, a.fix_pos, ms)
+  MAVI_LAUNCH(c, (k_newton_b<D, P, A>), nblk(p.n, RPB), TPB, (A ? 64 : PASS_SMEM), p, a.tstart, a.tile_prefix, a.cta_first, a.idflag, a.pos[1], a.vel, a.force_old, a.force, a.fix_idx, a.fix_pos, ms)
   if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, allp, CALL);
   else MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, allp, CALL);
 #undef CALL
@@ -927,7 +1126,7 @@ void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArra
   const bool allp = p.num_cells == 0;
   const MoverSink ms = mover_sink(a);
 #define CALL(D, P, A) \
-  MAVI_LAUNCH(c, (k_self_propelled<D, P, A>), nblk(p.n), TPB, 0, p, a.tstart, a.tile_prefix, a.cta_first, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms)
+  MAVI_LAUNCH(c, (k_self_propelled<D, P, A>), nblk(p.n, RPB), TPB, (A ? 64 : PASS_SMEM), p, a.tstart, a.tile_prefix, a.cta_first, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms)
   if (p.dynamics == MAVI_DYN_SZABO) MAVI_DISPATCH_DYN(MAVI_DYN_SZABO, p.periodic, allp, CALL);
   else MAVI_DISPATCH_DYN(MAVI_DYN_RTP, p.periodic, allp, CALL);
 #undef CALL
@@ -966,7 +1165,6 @@ __global__ void k_kinetic(const __grid_constant__ DevParams p, const int *__rest
                           const int *__restrict__ cta_first, const double2 *__restrict__ vel,
                           double *__restrict__ partials) {
   double s = 0.0;
-  // whole 256-rank blocks per CTA so that cta_first[rank / TPB] stays valid
   for (int base = blockIdx.x * TPB; base < p.n; base += gridDim.x * TPB) {
     int rank = base + threadIdx.x;
     if (rank < p.n) {

@@ -4,7 +4,9 @@
 
 namespace mavi {
 
-constexpr int TPB = 256;  // threads per block of every rank-mapped kernel (cta_first[] is indexed by rank / TPB)
+constexpr int TPB = 256;   // threads per block
+constexpr int RPB = 1024;  // ranks per block of every rank-mapped kernel: each thread handles RPB/TPB particles
+                           // (cta_first[] is indexed by rank / RPB); amortises the CTA-level staging
 
 // Device arrays of one handle.
 //
