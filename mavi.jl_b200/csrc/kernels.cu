@@ -694,7 +694,7 @@ template <bool PER>
 __device__ __forceinline__ void block_stage(const DevParams &p, const int *__restrict__ tstart,
                                             const int *__restrict__ cta_first, const double2 *__restrict__ pos,
                                             int o_last, bool exact_minimg, BlockStage *bs, double2 *s_pos,
-                                            int s_pos_cap) {
+                                            unsigned char *s_row, int s_pos_cap) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int R = p.num_rows, Cn = p.num_cols;
   // ---- block geometry (every thread computes the same values: no serial section)
@@ -788,20 +788,23 @@ __device__ __forceinline__ void block_stage(const DevParams &p, const int *__res
     for (int i = lane; i < la; i += 32) s_pos[off + i] = __ldg(pos + src_a + i);
     for (int i = lane; i < lt; i += 32) s_pos[off + la + i] = __ldg(pos + src_t + i);
     for (int i = lane; i < lb; i += 32) s_pos[off + la + lt + i] = __ldg(pos + src_b + i);
+    // staged row (1..32) of every tile particle: lane r-1 owns tile row r
+    if (lane < rows && lt > 0) {
+      const int b = __ldg(tt + lane) - src_t, e = __ldg(tt + lane + 1) - src_t;
+      for (int i = b; i < e; i++) s_row[off + la + i] = (unsigned char)(lane + 1);
+    }
   }
   __syncthreads();
 }
 
 // pair force of the particle in slot k (cell = (col,row) of the staged block) from the staged positions
 template <int DYN, bool MINIMG>
-__device__ __forceinline__ void block_walk(const DevParams &p, const BlockStage *bs, const double2 *s_pos, int col,
-                                           int row, int k, double2 ri, double &fx, double &fy) {
-  const int jj = col - bs->cfirst + 1;   // staged column of the particle's own column
-  const int lr = row - bs->r0 + 1;       // staged row (1..32)
+__device__ __forceinline__ void block_walk(const DevParams &p, const BlockStage *bs, const double2 *s_pos, int jj,
+                                           int lr, int self, double2 ri, double &fx, double &fy) {
+  // jj = staged column of the particle's own column, lr = its staged row (1..32), self = its index in s_pos
   const int a0 = bs->sstart[jj - 1][lr - 1], b0 = bs->sstart[jj - 1][lr + 2];
   const int a1 = bs->sstart[jj][lr - 1], b1 = bs->sstart[jj][lr + 2];
   const int a2 = bs->sstart[jj + 1][lr - 1], b2 = bs->sstart[jj + 1][lr + 2];
-  const int self = bs->sstart[jj][1] + (k - bs->tile_src[jj]);
   const int c1 = b0 - a0;              // neighbours t <  c1        -> a0 + t
   const int c2 = c1 + (self - a1);     //          c1 <= t < c2    -> a1 + (t - c1)
   const int c3 = c2 + (b1 - self - 1); //          c2 <= t < c3    -> self + 1 + (t - c2)
@@ -822,35 +825,73 @@ __device__ __forceinline__ void block_walk(const DevParams &p, const BlockStage 
 // `abs(dr) > size/2` test is false -> skipped EXACTLY.  Stale cells (Verlet pass 2) are covered by the per-step
 // displacement guard (FLAG_BIGMOVE) which switches pass B to the exact path.
 struct ForceCtx {
-  const BlockStage *bs;  // CTA staging descriptor (shared memory)
-  const double2 *s_pos;  // staged positions
-  int *tbl;              // this thread's column of the fallback segment table (aliases s_pos)
+  const BlockStage *bs;        // CTA staging descriptor (shared memory)
+  const double2 *s_pos;        // staged positions
+  const unsigned char *s_row;  // staged row of every staged tile particle
+  int *tbl;                    // this thread's column of the fallback segment table (aliases s_pos)
 };
 
 constexpr int BS_BYTES = (sizeof(BlockStage) + 15) / 16 * 16;
 constexpr int SPOS_CAP = 2304;  // staged positions per CTA (36 KB); the fallback table needs 16 KB of the same area
-constexpr int PASS_SMEM = BS_BYTES + SPOS_CAP * (int)sizeof(double2);
+constexpr int PASS_SMEM = BS_BYTES + SPOS_CAP * ((int)sizeof(double2) + 1);
+
+// what a thread knows about the particle it is working on
+struct Particle {
+  int k;         // slot
+  int cell;      // cell it is binned under
+  bool active;
+  bool staged;   // position / row came from the staged block
+  int jj, lr, self;
+  double2 r;
+};
+
+// Fetch the particle of `rank`.  In a staged block everything comes from shared memory (no global load sits in front
+// of the pair loop); otherwise from the global arrays.
+template <bool ALLP>
+__device__ __forceinline__ Particle fetch_particle(const DevParams &p, const ForceCtx &fc, int rank, int k, int order,
+                                                   const double2 *__restrict__ pos, const int *__restrict__ cell,
+                                                   const unsigned int *__restrict__ idflag) {
+  Particle q;
+  q.k = k;
+  q.staged = !ALLP && order >= 0 && fc.bs->ok;
+  if (q.staged) {
+    const BlockStage *bs = fc.bs;
+    const int tr = div_cols(p, order);
+    const int col = order - tr * p.ord_cols + p.ord_col0;
+    q.jj = col - bs->cfirst + 1;
+    q.self = bs->sstart[q.jj][1] + (k - bs->tile_src[q.jj]);
+    q.lr = fc.s_row[q.self];
+    q.r = fc.s_pos[q.self];
+    q.cell = col * p.num_rows + bs->r0 + q.lr - 1;
+    q.active = true;  // tiles hold active particles only (inactive slots live in the tail)
+  } else {
+    q.jj = q.lr = q.self = 0;
+    q.r = pos[k];
+    q.cell = ALLP ? 0 : cell[k];
+    q.active = !(idflag[k] & MAVI_INACTIVE_BIT);
+  }
+  return q;
+}
 
 template <int DYN, bool PER, bool ALLP>
 __device__ __forceinline__ double2 pair_force(const DevParams &p, const int *__restrict__ tstart,
                                               const double2 *__restrict__ pos, const unsigned int *__restrict__ idflag,
-                                              const ForceCtx &fc, int cell, int k, double2 ri, bool exact_minimg) {
+                                              const ForceCtx &fc, const Particle &q, bool exact_minimg) {
   if (ALLP) {
     double fx = 0.0, fy = 0.0;
     for (int j = 0; j < p.n; j++) {
-      if (j == k || (idflag[j] & MAVI_INACTIVE_BIT)) continue;
-      accumulate_pair<DYN, PER>(p, ri, __ldg(pos + j), fx, fy);
+      if (j == q.k || (idflag[j] & MAVI_INACTIVE_BIT)) continue;
+      accumulate_pair<DYN, PER>(p, q.r, __ldg(pos + j), fx, fy);
     }
     return make_double2(fx, fy);
   }
-  if (fc.bs->ok) {
-    const int col = div_rows(p, cell), row = cell - col * p.num_rows;
+  if (q.staged) {
     double fx = 0.0, fy = 0.0;
-    if (PER && fc.bs->use_mi) block_walk<DYN, true>(p, fc.bs, fc.s_pos, col, row, k, ri, fx, fy);
-    else block_walk<DYN, false>(p, fc.bs, fc.s_pos, col, row, k, ri, fx, fy);
+    if (PER && fc.bs->use_mi) block_walk<DYN, true>(p, fc.bs, fc.s_pos, q.jj, q.lr, q.self, q.r, fx, fy);
+    else block_walk<DYN, false>(p, fc.bs, fc.s_pos, q.jj, q.lr, q.self, q.r, fx, fy);
     return make_double2(fx, fy);
   }
-  return cell_pair_force<DYN, PER>(p, tstart, pos, fc.tbl, cell, k, ri, exact_minimg);
+  return cell_pair_force<DYN, PER>(p, tstart, pos, fc.tbl, q.cell, q.k, q.r, exact_minimg);
 }
 
 // common prologue of the rank-mapped force kernels (all threads take part): stage the rank window, find the last
@@ -862,15 +903,17 @@ __device__ __forceinline__ void force_prologue(const DevParams &p, const int *__
                                                int *s_win, ForceCtx &fc) {
   BlockStage *bs = reinterpret_cast<BlockStage *>(dsm);
   double2 *s_pos = reinterpret_cast<double2 *>(dsm + BS_BYTES);
+  unsigned char *s_row = dsm + BS_BYTES + SPOS_CAP * sizeof(double2);
   fc.bs = bs;
   fc.s_pos = s_pos;
+  fc.s_row = s_row;
   fc.tbl = reinterpret_cast<int *>(dsm + BS_BYTES) + threadIdx.x;
   if (ALLP) return;
   rank_window_stage(p, tile_prefix, cta_first, s_win);
   int o_last = -1;
   const int last_rank = min((int)(blockIdx.x * RPB + RPB - 1), p.n_active - 1);
   if (last_rank >= (int)(blockIdx.x * RPB)) slot_from_window(p, tile_prefix, cta_first, last_rank, s_win, &o_last);
-  block_stage<PER>(p, tstart, cta_first, pos, o_last, exact_minimg, bs, s_pos, SPOS_CAP);
+  block_stage<PER>(p, tstart, cta_first, pos, o_last, exact_minimg, bs, s_pos, s_row, SPOS_CAP);
 }
 
 // The particle in slot k (sorted under cell c_old) now sits at (x, y).  If update_particle_chunk! would bin it
@@ -920,7 +963,7 @@ __device__ __forceinline__ void note_if_moved(const DevParams &p, const MoverSin
   for (int it = 0; it < RPB / TPB; ++it) {                                                        \
     const int rank = blockIdx.x * RPB + it * TPB + threadIdx.x;                                   \
     if (rank >= p.n) break;                                                                       \
-    int order_;                                                                                   \
+    int order_ = -1;                                                                              \
     const int k = ALLP ? rank : slot_from_window(p, tile_prefix, cta_first, rank, s_win, &order_);
 
 // clean_forces! + calc_forces! (+ calc_walls_forces!): the force state after src/integration.jl:508-511.
@@ -931,11 +974,11 @@ __global__ void __launch_bounds__(TPB) k_force_only(const __grid_constant__ DevP
                              const double2 *__restrict__ pos, double2 *__restrict__ force, int with_walls) {
   MAVI_FORCE_KERNEL_PROLOGUE(pos, false)
   MAVI_FOR_EACH_PARTICLE
+    const Particle q = fetch_particle<ALLP>(p, fc, rank, k, order_, pos, cell, idflag);
     double2 F = make_double2(0.0, 0.0);
-    if (!(idflag[k] & MAVI_INACTIVE_BIT)) {
-      double2 r = pos[k];
-      F = pair_force<DYN, PER, ALLP>(p, tstart, pos, idflag, fc, ALLP ? 0 : cell[k], k, r, false);
-      if (with_walls && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
+    if (q.active) {
+      F = pair_force<DYN, PER, ALLP>(p, tstart, pos, idflag, fc, q, false);
+      if (with_walls && p.has_force_walls) wall_forces(p, q.r.x, q.r.y, F.x, F.y);
     }
     force[k] = F;
   }
@@ -951,13 +994,14 @@ __global__ void __launch_bounds__(TPB) k_newton_a(const __grid_constant__ DevPar
                            double2 *__restrict__ pos_out, double2 *__restrict__ f1, int *__restrict__ flags) {
   MAVI_FORCE_KERNEL_PROLOGUE(pos_in, false)
   MAVI_FOR_EACH_PARTICLE
-    double2 r = pos_in[k];
+    const double2 v = vel[k];  // issued before the pair loop, consumed after it
+    const Particle q = fetch_particle<ALLP>(p, fc, rank, k, order_, pos_in, cell, idflag);
+    double2 r = q.r;
     double2 F = make_double2(0.0, 0.0);
-    if (!(idflag[k] & MAVI_INACTIVE_BIT)) {
-      F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, fc, ALLP ? 0 : cell[k], k, r, false);
+    if (q.active) {
+      F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, fc, q, false);
       if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
     }
-    double2 v = vel[k];
     double mx = v.x * p.dt + F.x * p.term, my = v.y * p.dt + F.y * p.term;
     r.x = r.x + mx;
     r.y = r.y + my;
@@ -982,13 +1026,14 @@ __global__ void __launch_bounds__(TPB) k_newton_b(const __grid_constant__ DevPar
   const bool exact = !ALLP && ms.flags[FLAG_BIGMOVE] != 0;
   MAVI_FORCE_KERNEL_PROLOGUE(pos_in, exact)
   MAVI_FOR_EACH_PARTICLE
-    double2 r = pos_in[k];
+    double2 v = vel[k];        // issued before the pair loop, consumed after it
+    const double2 Fo = f1[k];
+    const Particle q = fetch_particle<ALLP>(p, fc, rank, k, order_, pos_in, ms.cell, idflag);
+    double2 r = q.r;
     double2 F = make_double2(0.0, 0.0);
-    const bool active = !(idflag[k] & MAVI_INACTIVE_BIT);
-    const int c = ALLP ? 0 : ms.cell[k];
-    if (active) F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, fc, c, k, r, exact);
-    double2 v = vel[k];
-    double2 Fo = f1[k];
+    const bool active = q.active;
+    const int c = q.cell;
+    if (active) F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, fc, q, exact);
     v.x = v.x + p.hdt * (F.x + Fo.x);
     v.y = v.y + p.hdt * (F.y + Fo.y);
     if (active) {
@@ -1023,13 +1068,14 @@ __global__ void __launch_bounds__(TPB) k_self_propelled(const __grid_constant__ 
   MAVI_FORCE_KERNEL_PROLOGUE(pos_in, false)
   MAVI_FOR_EACH_PARTICLE
     const unsigned int idf = idflag[k];
-    const bool active = !(idf & MAVI_INACTIVE_BIT);
     const unsigned int id = idf & ~MAVI_INACTIVE_BIT;
-    const int c = ALLP ? 0 : ms.cell[k];
-    double2 r = pos_in[k];
+    const Particle q = fetch_particle<ALLP>(p, fc, rank, k, order_, pos_in, ms.cell, idflag);
+    const bool active = q.active;
+    const int c = q.cell;
+    double2 r = q.r;
     double2 F = make_double2(0.0, 0.0);
     if (active) {
-      F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, fc, c, k, r, false);
+      F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, fc, q, false);
       if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
     }
     force[k] = F;
