@@ -1,6 +1,8 @@
 // kernels.cu — padded-tile cell lists (full build + O(#movers) incremental repair), fused force+integrate passes and
 // energy reductions.  sm_100a.  No tensor cores: the path is FP64 vector math over HBM-resident SoA arrays (double2
 // loads), not a dense contraction.  Reference citations are relative to /root/reference/.
+#include <cuda_pipeline.h>
+
 #include "kernels.cuh"
 #include "walls.cuh"
 
@@ -39,11 +41,9 @@ __device__ __forceinline__ void rank_window_stage(const DevParams &p, const int 
   __syncthreads();
 }
 // slot of `rank` (a rank of this block) and the order index of its tile (-1 for the inactive tail)
-__device__ __forceinline__ int slot_from_window(const DevParams &p, const int *__restrict__ tile_prefix,
-                                                const int *__restrict__ cta_first, int rank, const int *s_win,
-                                                int *order_out) {
-  *order_out = -1;
-  if (rank >= p.n_active) return p.tail_base + (rank - p.n_active);
+__device__ __forceinline__ int2 slot_from_window(const DevParams &p, const int *__restrict__ tile_prefix,
+                                                 const int *__restrict__ cta_first, int rank, const int *s_win) {
+  if (rank >= p.n_active) return make_int2(p.tail_base + (rank - p.n_active), -1);
   int lo = 0;
 #pragma unroll
   for (int step = RANK_WIN / 2; step >= 1; step >>= 1)
@@ -54,8 +54,7 @@ __device__ __forceinline__ int slot_from_window(const DevParams &p, const int *_
     while (rank >= __ldg(tile_prefix + o + 1)) ++o;
     base = __ldg(tile_prefix + o);
   }
-  *order_out = o;
-  return tile_of_order(p, o) * p.cap + (rank - base);
+  return make_int2(tile_of_order(p, o) * p.cap + (rank - base), o);
 }
 
 // =========================================================================================================
@@ -785,15 +784,20 @@ __device__ __forceinline__ void block_stage(const DevParams &p, const int *__res
       else v = off + la + lt + lb;
       bs->sstart[j][r] = v;
     }
-    for (int i = lane; i < la; i += 32) s_pos[off + i] = __ldg(pos + src_a + i);
-    for (int i = lane; i < lt; i += 32) s_pos[off + la + i] = __ldg(pos + src_t + i);
-    for (int i = lane; i < lb; i += 32) s_pos[off + la + lt + i] = __ldg(pos + src_b + i);
+    // 16-byte asynchronous copies (LDGSTS): every piece of every column is in flight at once, no register staging
+    const int tot = la + lt + lb;
+    for (int i = lane; i < tot; i += 32) {
+      const int src = i < la ? src_a + i : (i < la + lt ? src_t + (i - la) : src_b + (i - la - lt));
+      __pipeline_memcpy_async(s_pos + off + i, pos + src, sizeof(double2));
+    }
     // staged row (1..32) of every tile particle: lane r-1 owns tile row r
     if (lane < rows && lt > 0) {
       const int b = __ldg(tt + lane) - src_t, e = __ldg(tt + lane + 1) - src_t;
       for (int i = b; i < e; i++) s_row[off + la + i] = (unsigned char)(lane + 1);
     }
   }
+  __pipeline_commit();
+  __pipeline_wait_prior(0);
   __syncthreads();
 }
 
@@ -912,7 +916,7 @@ __device__ __forceinline__ void force_prologue(const DevParams &p, const int *__
   rank_window_stage(p, tile_prefix, cta_first, s_win);
   int o_last = -1;
   const int last_rank = min((int)(blockIdx.x * RPB + RPB - 1), p.n_active - 1);
-  if (last_rank >= (int)(blockIdx.x * RPB)) slot_from_window(p, tile_prefix, cta_first, last_rank, s_win, &o_last);
+  if (last_rank >= (int)(blockIdx.x * RPB)) o_last = slot_from_window(p, tile_prefix, cta_first, last_rank, s_win).y;
   block_stage<PER>(p, tstart, cta_first, pos, o_last, exact_minimg, bs, s_pos, s_row, SPOS_CAP);
 }
 
@@ -963,8 +967,8 @@ __device__ __forceinline__ void note_if_moved(const DevParams &p, const MoverSin
   for (int it = 0; it < RPB / TPB; ++it) {                                                        \
     const int rank = blockIdx.x * RPB + it * TPB + threadIdx.x;                                   \
     if (rank >= p.n) break;                                                                       \
-    int order_ = -1;                                                                              \
-    const int k = ALLP ? rank : slot_from_window(p, tile_prefix, cta_first, rank, s_win, &order_);
+    const int2 so_ = ALLP ? make_int2(rank, -1) : slot_from_window(p, tile_prefix, cta_first, rank, s_win);   \
+    const int k = so_.x, order_ = so_.y;
 
 // clean_forces! + calc_forces! (+ calc_walls_forces!): the force state after src/integration.jl:508-511.
 template <int DYN, bool PER, bool ALLP>
@@ -1211,7 +1215,7 @@ __global__ void k_kinetic(const __grid_constant__ DevParams p, const int *__rest
                           const int *__restrict__ cta_first, const double2 *__restrict__ vel,
                           double *__restrict__ partials) {
   double s = 0.0;
-  for (int base = blockIdx.x * TPB; base < p.n; base += gridDim.x * TPB) {
+  for (int base = blockIdx.x * blockDim.x; base < p.n; base += gridDim.x * blockDim.x) {
     int rank = base + threadIdx.x;
     if (rank < p.n) {
       double2 v = vel[slot_of_rank(p, tile_prefix, cta_first, rank)];
@@ -1259,7 +1263,7 @@ __global__ void k_potential_stencil(const __grid_constant__ DevParams p, const i
                                     const int *__restrict__ cell, const unsigned int *__restrict__ idflag,
                                     const double2 *__restrict__ pos, double *__restrict__ partials) {
   double s = 0.0;
-  for (int base = blockIdx.x * TPB; base < p.n; base += gridDim.x * TPB) {
+  for (int base = blockIdx.x * blockDim.x; base < p.n; base += gridDim.x * blockDim.x) {
     int rank = base + threadIdx.x;
     if (rank >= p.n) continue;
     const int k = slot_of_rank(p, tile_prefix, cta_first, rank);
