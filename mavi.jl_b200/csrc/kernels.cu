@@ -956,6 +956,9 @@ __device__ __forceinline__ void note_if_moved(const DevParams &p, const MoverSin
   }
 }
 
+// pull a line towards L1 without tying up a register across the pair loop (the value is loaded after the loop)
+__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+
 // Every force kernel: block prologue (staging), then each thread handles RPB/TPB particles of the block.
 #define MAVI_FORCE_KERNEL_PROLOGUE(POS, EXACT)                                                    \
   extern __shared__ __align__(16) unsigned char dsm[];                                            \
@@ -998,7 +1001,7 @@ __global__ void __launch_bounds__(TPB) k_newton_a(const __grid_constant__ DevPar
                            double2 *__restrict__ pos_out, double2 *__restrict__ f1, int *__restrict__ flags) {
   MAVI_FORCE_KERNEL_PROLOGUE(pos_in, false)
   MAVI_FOR_EACH_PARTICLE
-    const double2 v = vel[k];  // issued before the pair loop, consumed after it
+    prefetch_l1(vel + k);  // needed only after the pair loop
     const Particle q = fetch_particle<ALLP>(p, fc, rank, k, order_, pos_in, cell, idflag);
     double2 r = q.r;
     double2 F = make_double2(0.0, 0.0);
@@ -1006,6 +1009,7 @@ __global__ void __launch_bounds__(TPB) k_newton_a(const __grid_constant__ DevPar
       F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, fc, q, false);
       if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
     }
+    const double2 v = vel[k];
     double mx = v.x * p.dt + F.x * p.term, my = v.y * p.dt + F.y * p.term;
     r.x = r.x + mx;
     r.y = r.y + my;
@@ -1030,14 +1034,16 @@ __global__ void __launch_bounds__(TPB) k_newton_b(const __grid_constant__ DevPar
   const bool exact = !ALLP && ms.flags[FLAG_BIGMOVE] != 0;
   MAVI_FORCE_KERNEL_PROLOGUE(pos_in, exact)
   MAVI_FOR_EACH_PARTICLE
-    double2 v = vel[k];        // issued before the pair loop, consumed after it
-    const double2 Fo = f1[k];
+    prefetch_l1(vel + k);  // needed only after the pair loop
+    prefetch_l1(f1 + k);
     const Particle q = fetch_particle<ALLP>(p, fc, rank, k, order_, pos_in, ms.cell, idflag);
     double2 r = q.r;
     double2 F = make_double2(0.0, 0.0);
     const bool active = q.active;
     const int c = q.cell;
     if (active) F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, fc, q, exact);
+    double2 v = vel[k];
+    const double2 Fo = f1[k];
     v.x = v.x + p.hdt * (F.x + Fo.x);
     v.y = v.y + p.hdt * (F.y + Fo.y);
     if (active) {
