@@ -913,10 +913,20 @@ __device__ __forceinline__ void force_prologue(const DevParams &p, const int *__
   fc.s_row = s_row;
   fc.tbl = reinterpret_cast<int *>(dsm + BS_BYTES) + threadIdx.x;
   if (ALLP) return;
-  rank_window_stage(p, tile_prefix, cta_first, s_win);
+  // last tile of the block: the tile holding the first rank of the NEXT block bounds it (at most one tile too many,
+  // which only stages one extra column) -> the staging does not have to wait for the rank window
   int o_last = -1;
-  const int last_rank = min((int)(blockIdx.x * RPB + RPB - 1), p.n_active - 1);
-  if (last_rank >= (int)(blockIdx.x * RPB)) o_last = slot_from_window(p, tile_prefix, cta_first, last_rank, s_win).y;
+  if ((long long)blockIdx.x * RPB < p.n_active)
+    o_last = ((long long)(blockIdx.x + 1) * RPB < p.n_active) ? __ldg(cta_first + blockIdx.x + 1) : p.nt_ord - 1;
+  // rank window (its barrier is the first barrier of block_stage)
+  {
+    const bool in_tiles = (long long)blockIdx.x * RPB < p.n_active;
+    const int o0 = in_tiles ? __ldg(cta_first + blockIdx.x) : 0;
+    if (threadIdx.x <= RANK_WIN) {
+      const int o = o0 + threadIdx.x;
+      s_win[threadIdx.x] = (in_tiles && o <= p.nt_ord) ? __ldg(tile_prefix + o) : 0x7fffffff;
+    }
+  }
   block_stage<PER>(p, tstart, cta_first, pos, o_last, exact_minimg, bs, s_pos, s_row, SPOS_CAP);
 }
 
