@@ -339,12 +339,20 @@ int Handle::rebuild_from_staging(int n_active) {
   int cap = p.cap;
   if (p.num_cells > 0 && (a.pos[0] == nullptr || n_active != p.n_active || cap <= 0)) {
     const long long ntiles = (long long)(p.slab ? p.num_cols - 2 : p.num_cols) * ((p.num_rows + MAVI_TR - 1) / MAVI_TR);
-    cap = round_up16(2.0 * (double)n_active / (double)ntiles + 16.0);
+    if (cap <= 0 || !p.slab) cap = round_up16(2.0 * (double)n_active / (double)ntiles + 16.0);
+    if (p.slab) {  // all ranks must agree on the tile capacity
+      int st = slab_allreduce_max(this, &cap);
+      if (st) return st;
+    }
     int st = alloc_state(n_active, cap);
     if (st) return st;
   } else if (a.pos[0] == nullptr || n_active != p.n_count) {
     int st = alloc_state(n_active, 0);
     if (st) return st;
+  } else if (p.slab) {
+    int st = slab_allreduce_max(this, &cap);  // keep the collective sequence identical on every rank
+    if (st) return st;
+    if (cap != p.cap && (st = alloc_state(n_active, cap))) return st;
   }
   for (int attempt = 0; attempt < 8; attempt++) {
     if (p.num_cells == 0) {
@@ -364,8 +372,10 @@ int Handle::rebuild_from_staging(int n_active) {
     launch_build_tiles(ctx(), p, a, second_is_vel);
     int st = check_device_flags();
     if (st) return st;
-    if (!flags_host[FLAG_OVERFLOW]) return p.slab ? slab_after_build(this) : MAVI_OK;
-    cap = round_up16(flags_host[FLAG_MAXCOUNT] * 1.25 + 8.0);
+    int need = flags_host[FLAG_OVERFLOW] ? round_up16(flags_host[FLAG_MAXCOUNT] * 1.25 + 8.0) : 0;
+    if (p.slab && (st = slab_allreduce_max(this, &need))) return st;  // if ANY rank overflowed, everybody grows
+    if (need == 0) return p.slab ? slab_after_build(this) : MAVI_OK;
+    cap = need > p.cap ? need : round_up16(p.cap * 1.25 + 8.0);
     if ((st = alloc_state(n_active, cap))) return st;
   }
   set_error("tile capacity did not converge");

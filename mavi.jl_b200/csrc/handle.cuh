@@ -70,6 +70,7 @@ int slab_unique_id(void *out128);
 int slab_configure(Handle *h, const MaviParams *mp);
 void slab_destroy(Handle *h);
 int slab_after_build(Handle *h);
+int slab_allreduce_max(Handle *h, int *value);
 int slab_step_once(Handle *h, const double *noise_dev);
 
 // rings.cu

@@ -32,6 +32,7 @@ struct NcclApi {
   ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
@@ -54,6 +55,7 @@ static const char *load_nccl() {
   NCCL_SYM(GroupEnd, "ncclGroupEnd")
   NCCL_SYM(Send, "ncclSend")
   NCCL_SYM(Recv, "ncclRecv")
+  NCCL_SYM(AllReduce, "ncclAllReduce")
   NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef NCCL_SYM
   return nullptr;
@@ -143,6 +145,17 @@ int slab_configure(Handle *h, const MaviParams *mp) {
   ncclUniqueId id;
   memcpy(&id, mp->nccl_unique_id, sizeof id);
   SLAB_NCCL(h, g_nccl.CommInitRank(&s.comm, s.world, id, s.rank));
+  return MAVI_OK;
+}
+
+// max over all ranks of one int (tile capacity agreement: every rank must use the SAME slots-per-column, because a
+// halo / emigrant column is shipped as one raw slab of tpc*cap slots)
+int slab_allreduce_max(Handle *h, int *value) {
+  int *d = h->a.flags + FLAG_COUNT - 1;  // last control word is scratch for this
+  SLAB_CUDA(h, cudaMemcpyAsync(d, value, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  SLAB_NCCL(h, g_nccl.AllReduce(d, d, 1, /*ncclInt32*/ 2, /*ncclMax*/ 2, h->slab.comm, h->stream));
+  SLAB_CUDA(h, cudaMemcpyAsync(value, d, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  SLAB_CUDA(h, cudaStreamSynchronize(h->stream));
   return MAVI_OK;
 }
 

@@ -126,8 +126,17 @@ def test_multigpu_slabs_match_oracle(cuda_lib, kind, steps):
     if n < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     world = 4 if n >= 4 else 2
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
-    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_worker.py"),
-                          kind, str(steps)], capture_output=True, text=True, env=env, timeout=600)
-    assert "MGPU_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", NCCL_DEBUG="WARN")
+    port = 29533 + {"lj": 0, "harm": 1, "szabo": 2}[kind]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py"), kind, str(steps)]
+    # own process group, so that a hung rank can be killed by its exact pgid without touching anything else
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, start_new_session=True)
+    try:
+        out, err = proc.communicate(timeout=150)
+    except subprocess.TimeoutExpired:
+        import signal
+        os.killpg(proc.pid, signal.SIGKILL)
+        out, err = proc.communicate()
+        pytest.fail("multi-GPU worker hung:\n" + out[-2000:] + err[-3000:])
+    assert "MGPU_OK" in out, out[-3000:] + err[-3000:]
