@@ -366,7 +366,7 @@ int Handle::rebuild_from_staging(int n_active) {
       return MAVI_OK;
     }
     CUDA_TRY(this, cudaMemsetAsync(a.count, 0, ((size_t)p.num_cells + 2) * sizeof(int), stream));
-    CUDA_TRY(this, cudaMemsetAsync(a.flags + 1, 0, (FLAG_COUNT - 1) * sizeof(int), stream));
+    CUDA_TRY(this, cudaMemsetAsync(a.flags + 1, 0, (FLAG_STEPS - 1) * sizeof(int), stream));
     CUDA_TRY(this, cudaMemsetAsync(a.tile_dirty, 0, ((size_t)p.nt + 1) * sizeof(int), stream));
     CUDA_TRY(this, cudaMemsetAsync(a.inbox_cnt, 0, ((size_t)p.nt + 1) * sizeof(int), stream));
     launch_build_tiles(ctx(), p, a, second_is_vel);
@@ -422,19 +422,17 @@ int Handle::check_device_flags() {
   return MAVI_OK;
 }
 
-int Handle::step_once(const double *noise_dev) {
+// Enqueue one step (no host synchronisation).  newton_step! / szabo_step! / rtp_step!, src/integration.jl:507-535.
+int Handle::enqueue_step(const double *noise_dev) {
   int st;
   LaunchCtx c = ctx();
-  if (p.dynamics == MAVI_DYN_RINGS) return rings_step(this, noise_dev);
-  if (p.slab) return slab_step_once(this, noise_dev);
-  if (int st0 = pending_out_of_grid()) return st0;
   const bool second_is_vel = second_kind == SECOND_VEL;
   if (prof) cudaEventRecord(ev[0], stream);
   if ((flags_cfg & MAVI_FLAG_RESORT_EVERY_STEP) && p.num_cells > 0) {
     if ((st = rebuild_from_current())) return st;  // A/B switch: global rebuild instead of the incremental repair
   }
-  // per-step control words: #dirty tiles, big-drift guard, #position fix-ups, #inter-tile movers
-  CUDA_TRY(this, cudaMemsetAsync(a.flags + 1, 0, 4 * sizeof(int), stream));
+  // per-step control words: #dirty tiles, big-drift guard, #position fix-ups, #inter-tile movers, "step ran"
+  launch_step_begin(c, a);
   if (prof) cudaEventRecord(ev[1], stream);
   if (second_is_vel) {
     launch_newton_a(c, p, a);  // pos[0] -> pos[1] (drift), F1 -> force_old
@@ -451,16 +449,61 @@ int Handle::step_once(const double *noise_dev) {
   if (prof) cudaEventRecord(ev[4], stream);
   time += p.dt;  // update_time!, src/integration.jl:500-503
   num_steps += 1;
-  // one small read-back per step: error word + tile overflow
-  if ((st = check_device_flags())) return st;
-  if (flags_host[FLAG_OVERFLOW]) {
-    // a tile or inbox ran out of slots: nothing was modified by the repair; rebuild with a larger capacity
-    // grow only when a tile really ran out of slots; a mover-list overflow just needs the rebuild
-    int cap = (flags_host[FLAG_OVERFLOW] & 1) ? round_up16((flags_host[FLAG_MAXCOUNT] > p.cap ? flags_host[FLAG_MAXCOUNT] : p.cap) * 1.25 + 8.0) : p.cap;
-    launch_compact_to_staging(c, p, a, second_is_vel);
-    const int n_active = p.n_active;
-    if ((st = alloc_state(n_active, cap))) return st;
-    if ((st = rebuild_from_staging(n_active))) return st;
+  return MAVI_OK;
+}
+
+// nsteps steps with the control words read back only every SYNC_EVERY steps.  A step whose repair overflowed (or that
+// pushed a particle out of the grid) latches a flag that turns every later kernel into a no-op; the device-side step
+// counter tells how many steps really ran, the host rolls its clock and the ping-pong parity back, grows the tiles and
+// resumes.
+int Handle::run_steps(long long nsteps, const double *noise_dev, size_t stride) {
+  constexpr int SYNC_EVERY = 32;
+  long long done_total = 0;
+  int st;
+  while (done_total < nsteps) {
+    if ((st = pending_out_of_grid())) return st;
+    if (p.dynamics == MAVI_DYN_RINGS || p.slab) {  // these paths synchronise every step themselves
+      const double *nz = noise_dev ? noise_dev + (size_t)done_total * stride : nullptr;
+      st = p.slab ? slab_step_once(this, nz) : rings_step(this, nz);
+      if (st) return st;
+      done_total += 1;
+      continue;
+    }
+    const int batch = (int)((nsteps - done_total) < SYNC_EVERY ? (nsteps - done_total) : SYNC_EVERY);
+    long long snap_steps[SYNC_EVERY + 1];
+    double snap_time[SYNC_EVERY + 1];
+    snap_steps[0] = num_steps;
+    snap_time[0] = time;
+    const int c0 = steps_seen;
+    for (int s = 0; s < batch; s++) {
+      if ((st = enqueue_step(noise_dev ? noise_dev + (size_t)(done_total + s) * stride : nullptr))) return st;
+      snap_steps[s + 1] = num_steps;
+      snap_time[s + 1] = time;
+    }
+    st = check_device_flags();
+    int done = flags_host[FLAG_STEPS] - c0;
+    if (flags_cfg & MAVI_FLAG_RESORT_EVERY_STEP) done = batch;
+    if (done < 0 || done > batch) done = batch;
+    steps_seen = flags_host[FLAG_STEPS];
+    if (done < batch) {  // some enqueued steps were no-ops: undo their host-side bookkeeping
+      num_steps = snap_steps[done];
+      time = snap_time[done];
+      if ((batch - done) & 1) std::swap(a.pos[0], a.pos[1]);
+    }
+    done_total += done;
+    if (st) return st;
+    if (flags_host[FLAG_OVERFLOW]) {
+      // a tile ran out of slots (or the mover list overflowed): nothing was modified by the repair of that step;
+      // rebuild, with a larger capacity when a tile was really full
+      const bool second_is_vel = second_kind == SECOND_VEL;
+      int cap = (flags_host[FLAG_OVERFLOW] & 1)
+                    ? round_up16((flags_host[FLAG_MAXCOUNT] > p.cap ? flags_host[FLAG_MAXCOUNT] : p.cap) * 1.25 + 8.0)
+                    : p.cap;
+      launch_compact_to_staging(ctx(), p, a, second_is_vel);
+      const int n_active = p.n_active;
+      if (cap != p.cap && (st = alloc_state(n_active, cap))) return st;
+      if ((st = rebuild_from_staging(n_active))) return st;
+    }
   }
   return MAVI_OK;
 }
@@ -556,6 +599,7 @@ int32_t mavi_upload_state(MaviHandle *hh, const void *pos, const void *second, c
       CUDA_TRY(h, cudaMemcpyAsync(a.st_ang, second, (size_t)h->p.rings.num_rings * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   }
   CUDA_TRY(h, cudaMemsetAsync(a.flags, 0, FLAG_COUNT * sizeof(int), h->stream));
+  h->steps_seen = 0;
   if (h->second_kind == SECOND_RING_POL) return rings_upload_finish(h);
   unsigned char *mask_dev = nullptr;
   int n_active = h->p.n;
@@ -692,6 +736,7 @@ int32_t mavi_upload_local(MaviHandle *hh, const int64_t *ids, const void *pos, c
   CUDA_TRY(h, cudaMemcpyAsync(a.st_id, id32.data(), sn * sizeof(unsigned int), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(a.st_force, 0, sn * sizeof(double2), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(a.flags, 0, FLAG_COUNT * sizeof(int), h->stream));
+  h->steps_seen = 0;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->p.n = (int)n_local;
   int st = h->rebuild_from_staging((int)n_local);
@@ -729,11 +774,9 @@ int32_t mavi_step(MaviHandle *hh, int64_t nsteps, const void *host_noise) {
     }
   }
   if (h->prof) cudaEventRecord(h->ev_call[0], h->stream);
-  for (int64_t s = 0; s < nsteps; s++) {
-    int st = h->step_once(noise_dev ? noise_dev + (size_t)s * stride : nullptr);
-    if (st) return st;
-  }
+  int st = h->run_steps(nsteps, noise_dev, stride);
   if (h->prof) cudaEventRecord(h->ev_call[1], h->stream);
+  if (st) return st;
   CUDA_TRY(h, cudaGetLastError());
   return h->check_device_flags();
 }

@@ -88,7 +88,24 @@ struct DevParams {
 enum { ERRBIT_OUT_OF_GRID = 1, ERRBIT_NAN = 2, ERRBIT_OUTSIDE_SPACE = 4, ERRBIT_OOG_PENDING = 8 };
 
 // flags[] layout (device control word, mirrored to pinned host memory once per step)
-enum { FLAG_ERR = 0, FLAG_CHANGED = 1, FLAG_BIGMOVE = 2, FLAG_NFIX = 3, FLAG_NMV = 4, FLAG_OVERFLOW = 5, FLAG_MAXCOUNT = 6, FLAG_TAIL = 7, FLAG_MAXINBOX = 8, FLAG_MAXINBOX_TILE = 9, FLAG_COUNT = 12 };
+enum {
+  FLAG_ERR = 0,
+  // reset at the start of every step:
+  FLAG_CHANGED = 1, FLAG_BIGMOVE = 2, FLAG_NFIX = 3, FLAG_NMV = 4, FLAG_RAN = 5,
+  FLAG_PER_STEP = 5,  // number of per-step words starting at index 1
+  // latched until handled by the host:
+  FLAG_OVERFLOW = 6, FLAG_MAXCOUNT = 7, FLAG_TAIL = 8, FLAG_MAXINBOX = 9, FLAG_MAXINBOX_TILE = 10,
+  FLAG_STEPS = 11,    // steps that really ran since the last upload (device-side step counter)
+  FLAG_SCRATCH = 12,
+  FLAG_COUNT = 16
+};
+
+// A step whose tile repair overflowed (or that pushed a particle out of the grid) leaves the layout un-repaired: every
+// kernel of the FOLLOWING steps sees the latched flag and returns at once, so the host may enqueue many steps and look
+// at the control words only occasionally; FLAG_STEPS counts the steps that really ran.
+__device__ __forceinline__ bool step_poisoned(const int *flags) {
+  return (flags[FLAG_OVERFLOW] != 0) || ((flags[FLAG_ERR] & ERRBIT_OOG_PENDING) != 0);
+}
 
 #define MAVI_TR 32  // cell rows per tile
 

@@ -43,6 +43,7 @@ struct Handle {
   int *flags_host = nullptr;  // pinned mirror of a.flags[0..3]
   bool prof = false;
   long long launches = 0;
+  int steps_seen = 0;  // host mirror of the device-side step counter flags[FLAG_STEPS]
   long long num_steps = 0;
   double time = 0.0;
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -59,7 +60,8 @@ struct Handle {
   int alloc_state(int n_active, int cap);
   int rebuild_from_staging(int n_active);
   int rebuild_from_current();
-  int step_once(const double *noise_dev);
+  int enqueue_step(const double *noise_dev);
+  int run_steps(long long nsteps, const double *noise_dev, size_t stride);
 };
 
 // api.cu

@@ -164,7 +164,7 @@ __global__ void k_build_place(const __grid_constant__ DevParams p, const int *__
   const unsigned int idf = st_id[i];
   int d;
   if (c < 0) {
-    d = p.tail_base + atomicAdd(&flags[7], 1);
+    d = p.tail_base + atomicAdd(&flags[FLAG_TAIL], 1);
   } else {
     const int col = c / p.num_rows, row = c - col * p.num_rows;
     const int q = tq_of(p, col, row);
@@ -376,7 +376,7 @@ __global__ void k_repair_collect(const int *__restrict__ flags, const int *__res
                                  double2 *__restrict__ mv_pos, double2 *__restrict__ mv_second,
                                  double2 *__restrict__ mv_force, unsigned int *__restrict__ mv_id,
                                  int *__restrict__ mv_cell, int mv_cap) {
-  if (flags[FLAG_OVERFLOW]) return;
+  if (!flags[FLAG_RAN]) return;
   const int n = min(flags[FLAG_NMV], mv_cap);
   for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
     const int k = mv_src[m];
@@ -412,6 +412,7 @@ __global__ void __launch_bounds__(REPAIR_WARPS * 32) k_repair_tiles(
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   RepairRec *rec = reinterpret_cast<RepairRec *>(smem_raw) + (size_t)w * p.cap;
   const int ndirty = flags[FLAG_CHANGED];
+  if (!flags[FLAG_RAN]) return;  // the step did not run (latched overflow / out-of-grid of an earlier step)
   if (WRITE && flags[FLAG_OVERFLOW]) return;
   for (int d = blockIdx.x * REPAIR_WARPS + w; d < ndirty; d += gridDim.x * REPAIR_WARPS) {
     const int t = dirty_list[d];
@@ -1009,6 +1010,7 @@ __global__ void __launch_bounds__(TPB) k_newton_a(const __grid_constant__ DevPar
                            const int *__restrict__ cell, const unsigned int *__restrict__ idflag,
                            const double2 *__restrict__ pos_in, const double2 *__restrict__ vel,
                            double2 *__restrict__ pos_out, double2 *__restrict__ f1, int *__restrict__ flags) {
+  if (!flags[FLAG_RAN]) return;
   MAVI_FORCE_KERNEL_PROLOGUE(pos_in, false)
   MAVI_FOR_EACH_PARTICLE
     prefetch_l1(vel + k);  // needed only after the pair loop
@@ -1041,6 +1043,7 @@ __global__ void __launch_bounds__(TPB) k_newton_b(const __grid_constant__ DevPar
                            const unsigned int *__restrict__ idflag, const double2 *__restrict__ pos_in,
                            double2 *__restrict__ vel, const double2 *__restrict__ f1, double2 *__restrict__ f2,
                            int *__restrict__ fix_idx, double2 *__restrict__ fix_pos, const MoverSink ms) {
+  if (!ms.flags[FLAG_RAN]) return;
   const bool exact = !ALLP && ms.flags[FLAG_BIGMOVE] != 0;
   MAVI_FORCE_KERNEL_PROLOGUE(pos_in, exact)
   MAVI_FOR_EACH_PARTICLE
@@ -1071,8 +1074,27 @@ __global__ void __launch_bounds__(TPB) k_newton_b(const __grid_constant__ DevPar
   }
 }
 
-__global__ void k_apply_pos_fixes(const int *__restrict__ flags, const int *__restrict__ fix_idx,
+// First kernel of every step: decides ONCE whether the step runs (no overflow / out-of-grid latched by an earlier
+// step) and clears the per-step control words.  Every other kernel of the step only looks at FLAG_RAN, so flags raised
+// DURING the step cannot stop it half way.
+__global__ void k_step_begin(int *__restrict__ flags) {
+  if (threadIdx.x == 0) {
+    const int run = step_poisoned(flags) ? 0 : 1;
+    flags[FLAG_CHANGED] = 0;
+    flags[FLAG_BIGMOVE] = 0;
+    flags[FLAG_NFIX] = 0;
+    flags[FLAG_NMV] = 0;
+    flags[FLAG_RAN] = run;
+  }
+}
+
+void launch_step_begin(const LaunchCtx &c, const DevArrays &a) { MAVI_LAUNCH(c, k_step_begin, 1, 32, 0, a.flags); }
+
+// applies the deferred wall position fix-ups and counts the step as done (runs after the integrate kernels of EVERY step)
+__global__ void k_apply_pos_fixes(int *__restrict__ flags, const int *__restrict__ fix_idx,
                                   const double2 *__restrict__ fix_pos, double2 *__restrict__ pos) {
+  if (!flags[FLAG_RAN]) return;  // poisoned by an EARLIER step: this step does not run
+  if (blockIdx.x == 0 && threadIdx.x == 0) flags[FLAG_STEPS] += 1;
   const int n = flags[FLAG_NFIX];
   for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) pos[fix_idx[m]] = fix_pos[m];
 }
@@ -1085,6 +1107,7 @@ __global__ void __launch_bounds__(TPB) k_self_propelled(const __grid_constant__ 
                                  const unsigned int *__restrict__ idflag, const double2 *__restrict__ pos_in,
                                  double *__restrict__ ang, double2 *__restrict__ pos_out, double2 *__restrict__ force,
                                  const double *__restrict__ noise, unsigned long long step, const MoverSink ms) {
+  if (!ms.flags[FLAG_RAN]) return;
   MAVI_FORCE_KERNEL_PROLOGUE(pos_in, false)
   MAVI_FOR_EACH_PARTICLE
     const unsigned int idf = idflag[k];
@@ -1196,6 +1219,7 @@ void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArra
   if (p.dynamics == MAVI_DYN_SZABO) MAVI_DISPATCH_DYN(MAVI_DYN_SZABO, p.periodic, allp, CALL);
   else MAVI_DISPATCH_DYN(MAVI_DYN_RTP, p.periodic, allp, CALL);
 #undef CALL
+  MAVI_LAUNCH(c, k_apply_pos_fixes, 1, 32, 0, a.flags, a.fix_idx, a.fix_pos, a.pos[1]);  // no fix-ups here: step counter only
 }
 
 // =========================================================================================================

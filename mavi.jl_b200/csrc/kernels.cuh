@@ -72,6 +72,7 @@ void launch_exclusive_scan(const LaunchCtx &c, const int *in, int *out, int *par
 void refresh_rank_maps(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
 
 // force + integrate passes
+void launch_step_begin(const LaunchCtx &c, const DevArrays &a);
 void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool with_wall_forces);
 void launch_newton_a(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
 void launch_newton_b(const LaunchCtx &c, const DevParams &p, const DevArrays &a);

@@ -397,7 +397,7 @@ int rings_bin(Handle *h) {
   if (int st0 = h->pending_out_of_grid()) return st0;
   for (int attempt = 0; attempt < 8; attempt++) {
     RINGS_TRY(h, cudaMemsetAsync(a.count, 0, ((size_t)p.num_cells + 2) * sizeof(int), h->stream));
-    RINGS_TRY(h, cudaMemsetAsync(a.flags + 1, 0, (FLAG_COUNT - 1) * sizeof(int), h->stream));
+    RINGS_TRY(h, cudaMemsetAsync(a.flags + 1, 0, (FLAG_STEPS - 1) * sizeof(int), h->stream));
     launch_build_index_tiles(h->ctx(), p, a.pos[0], a.idflag, a.cell, a.count, a.tstart, a.perm, a.flags);
     int st = h->check_device_flags();
     if (st) return st;

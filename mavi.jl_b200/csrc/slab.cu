@@ -151,7 +151,7 @@ int slab_configure(Handle *h, const MaviParams *mp) {
 // max over all ranks of one int (tile capacity agreement: every rank must use the SAME slots-per-column, because a
 // halo / emigrant column is shipped as one raw slab of tpc*cap slots)
 int slab_allreduce_max(Handle *h, int *value) {
-  int *d = h->a.flags + FLAG_COUNT - 1;  // last control word is scratch for this
+  int *d = h->a.flags + FLAG_SCRATCH;
   SLAB_CUDA(h, cudaMemcpyAsync(d, value, sizeof(int), cudaMemcpyHostToDevice, h->stream));
   SLAB_NCCL(h, g_nccl.AllReduce(d, d, 1, /*ncclInt32*/ 2, /*ncclMax*/ 2, h->slab.comm, h->stream));
   SLAB_CUDA(h, cudaMemcpyAsync(value, d, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -223,7 +223,7 @@ __global__ void k_ingest(const __grid_constant__ DevParams p, const int *__restr
 }
 
 __global__ void k_owned_count(const __grid_constant__ DevParams p, const int *__restrict__ tile_prefix, int *__restrict__ flags) {
-  flags[FLAG_MAXCOUNT + 1] = tile_prefix[p.nt_ord];
+  flags[FLAG_TAIL] = tile_prefix[p.nt_ord];
 }
 
 // ---- exchanges ------------------------------------------------------------------------------------------------------
@@ -341,7 +341,7 @@ static int slab_refresh_count(Handle *h) {
   h->launches++;
   int st = h->check_device_flags();
   if (st) return st;
-  h->p.n = h->p.n_active = h->flags_host[FLAG_MAXCOUNT + 1];
+  h->p.n = h->p.n_active = h->flags_host[FLAG_TAIL];
   h->p.n_count = h->slab.n_global;  // get_num_total_particles of the GLOBAL state (update_szabo!/update_rtp! loop 1:count)
   return MAVI_OK;
 }
@@ -362,7 +362,7 @@ int slab_step_once(Handle *h, const double *noise_dev) {
   if ((st = h->pending_out_of_grid())) return st;
   const bool vel = h->second_kind == SECOND_VEL;
   if (h->prof) cudaEventRecord(h->ev[0], h->stream);
-  SLAB_CUDA(h, cudaMemsetAsync(a.flags + 1, 0, 4 * sizeof(int), h->stream));
+  launch_step_begin(c, a);
   if (h->prof) cudaEventRecord(h->ev[1], h->stream);
   if (vel) {
     launch_newton_a(c, p, a);                                     // owned: pos[0] -> pos[1], F1
