@@ -133,7 +133,8 @@ typedef struct MaviParams {
 } MaviParams;
 
 /* flags */
-#define MAVI_FLAG_RESORT_EVERY_STEP 1 /* disable the "nobody changed cell -> keep order" fast path (A/B testing) */
+#define MAVI_FLAG_RESORT_EVERY_STEP 1 /* full update_chunks! rebuild every step instead of the incremental tile repair (A/B testing) */
+#define MAVI_FLAG_TIGHT_TILES 2       /* testing: tile capacity without slack, so that the overflow -> rebuild -> resume path is exercised */
 
 typedef struct MaviHandle MaviHandle;
 
@@ -205,6 +206,8 @@ int32_t mavi_last_error(MaviHandle *h, char *buf, int32_t n);
 /* ---- instrumentation (bench.py / tests) ------------------------------------------------------ */
 /* number of kernels this handle has launched since creation */
 int32_t mavi_launch_count(MaviHandle *h, int64_t *n);
+/* number of tile-overflow -> full rebuild events since creation */
+int32_t mavi_rebuild_count(MaviHandle *h, int64_t *n);
 /* device time of the last mavi_step call per phase, CUDA events on the launching stream:
  * ms[0]=bin+sort ms[1]=pass A ms[2]=pass B (or the single fused pass) ms[3]=exchange ms[4]=total */
 int32_t mavi_last_step_ms(MaviHandle *h, float *ms5);

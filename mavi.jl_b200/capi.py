@@ -28,6 +28,7 @@ WALLMODE_OUTSIDE, WALLMODE_INSIDE, WALLMODE_REPULSION = range(3)
 DYN_LJ, DYN_HARMTRUNC, DYN_SZABO, DYN_RTP, DYN_RINGS = range(5)
 RNG_HOST_NOISE, RNG_PHILOX = range(2)
 FLAG_RESORT_EVERY_STEP = 1
+FLAG_TIGHT_TILES = 2
 
 
 class MaviLine(C.Structure):
@@ -99,6 +100,7 @@ SIGNATURES = {
     "mavi_sync": (C.c_int32, [_H]),
     "mavi_last_error": (C.c_int32, [_H, C.c_char_p, C.c_int32]),
     "mavi_launch_count": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
+    "mavi_rebuild_count": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
     "mavi_last_step_ms": (C.c_int32, [_H, C.POINTER(C.c_float)]),
     "mavi_set_profiling": (C.c_int32, [_H, C.c_int32]),
 }

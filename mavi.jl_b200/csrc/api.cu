@@ -339,7 +339,7 @@ int Handle::rebuild_from_staging(int n_active) {
   int cap = p.cap;
   if (p.num_cells > 0 && (a.pos[0] == nullptr || n_active != p.n_active || cap <= 0)) {
     const long long ntiles = (long long)(p.slab ? p.num_cols - 2 : p.num_cols) * ((p.num_rows + MAVI_TR - 1) / MAVI_TR);
-    if (cap <= 0 || !p.slab) cap = round_up16(2.0 * (double)n_active / (double)ntiles + 16.0);
+    if (cap <= 0 || !p.slab) cap = (flags_cfg & MAVI_FLAG_TIGHT_TILES) ? 1 : round_up16(2.0 * (double)n_active / (double)ntiles + 16.0);
     if (p.slab) {  // all ranks must agree on the tile capacity
       int st = slab_allreduce_max(this, &cap);
       if (st) return st;
@@ -372,10 +372,10 @@ int Handle::rebuild_from_staging(int n_active) {
     launch_build_tiles(ctx(), p, a, second_is_vel);
     int st = check_device_flags();
     if (st) return st;
-    int need = flags_host[FLAG_OVERFLOW] ? round_up16(flags_host[FLAG_MAXCOUNT] * 1.25 + 8.0) : 0;
+    int need = flags_host[FLAG_OVERFLOW] ? ((flags_cfg & MAVI_FLAG_TIGHT_TILES) ? flags_host[FLAG_MAXCOUNT] : round_up16(flags_host[FLAG_MAXCOUNT] * 1.25 + 8.0)) : 0;
     if (p.slab && (st = slab_allreduce_max(this, &need))) return st;  // if ANY rank overflowed, everybody grows
     if (need == 0) return p.slab ? slab_after_build(this) : MAVI_OK;
-    cap = need > p.cap ? need : round_up16(p.cap * 1.25 + 8.0);
+    cap = need > p.cap ? need : ((flags_cfg & MAVI_FLAG_TIGHT_TILES) ? p.cap + 1 : round_up16(p.cap * 1.25 + 8.0));
     if ((st = alloc_state(n_active, cap))) return st;
   }
   set_error("tile capacity did not converge");
@@ -428,9 +428,6 @@ int Handle::enqueue_step(const double *noise_dev) {
   LaunchCtx c = ctx();
   const bool second_is_vel = second_kind == SECOND_VEL;
   if (prof) cudaEventRecord(ev[0], stream);
-  if ((flags_cfg & MAVI_FLAG_RESORT_EVERY_STEP) && p.num_cells > 0) {
-    if ((st = rebuild_from_current())) return st;  // A/B switch: global rebuild instead of the incremental repair
-  }
   // per-step control words: #dirty tiles, big-drift guard, #position fix-ups, #inter-tile movers, "step ran"
   launch_step_begin(c, a);
   if (prof) cudaEventRecord(ev[1], stream);
@@ -446,6 +443,7 @@ int Handle::enqueue_step(const double *noise_dev) {
   if (prof) cudaEventRecord(ev[3], stream);
   // update_chunks! for the NEXT step, incrementally: only tiles a particle left or entered are rewritten
   if (!(flags_cfg & MAVI_FLAG_RESORT_EVERY_STEP)) launch_repair_tiles(c, p, a, second_is_vel);
+  else if (p.num_cells > 0 && (st = rebuild_from_current())) return st;  // A/B switch: global rebuild instead of the repair
   if (prof) cudaEventRecord(ev[4], stream);
   time += p.dt;  // update_time!, src/integration.jl:500-503
   num_steps += 1;
@@ -496,9 +494,12 @@ int Handle::run_steps(long long nsteps, const double *noise_dev, size_t stride) 
       // a tile ran out of slots (or the mover list overflowed): nothing was modified by the repair of that step;
       // rebuild, with a larger capacity when a tile was really full
       const bool second_is_vel = second_kind == SECOND_VEL;
-      int cap = (flags_host[FLAG_OVERFLOW] & 1)
-                    ? round_up16((flags_host[FLAG_MAXCOUNT] > p.cap ? flags_host[FLAG_MAXCOUNT] : p.cap) * 1.25 + 8.0)
-                    : p.cap;
+      int cap = p.cap;
+      if (flags_host[FLAG_OVERFLOW] & 1) {
+        const int mx = flags_host[FLAG_MAXCOUNT] > p.cap ? flags_host[FLAG_MAXCOUNT] : p.cap + 1;
+        cap = (flags_cfg & MAVI_FLAG_TIGHT_TILES) ? mx : round_up16(mx * 1.25 + 8.0);
+      }
+      n_rebuilds++;
       launch_compact_to_staging(ctx(), p, a, second_is_vel);
       const int n_active = p.n_active;
       if (cap != p.cap && (st = alloc_state(n_active, cap))) return st;
@@ -932,6 +933,13 @@ int32_t mavi_launch_count(MaviHandle *hh, int64_t *n) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || !n) return MAVI_ERR_BAD_PARAMS;
   *n = h->launches;
+  return MAVI_OK;
+}
+
+int32_t mavi_rebuild_count(MaviHandle *hh, int64_t *n) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || !n) return MAVI_ERR_BAD_PARAMS;
+  *n = h->n_rebuilds;
   return MAVI_OK;
 }
 

@@ -43,6 +43,7 @@ struct Handle {
   int *flags_host = nullptr;  // pinned mirror of a.flags[0..3]
   bool prof = false;
   long long launches = 0;
+  long long n_rebuilds = 0;  // overflow -> rebuild events (instrumentation)
   int steps_seen = 0;  // host mirror of the device-side step counter flags[FLAG_STEPS]
   long long num_steps = 0;
   double time = 0.0;

@@ -196,6 +196,11 @@ class System:
         self._check(self._lib.mavi_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def rebuild_count(self):
+        n = C.c_int64()
+        self._check(self._lib.mavi_rebuild_count(self._h, C.byref(n)))
+        return n.value
+
     def set_profiling(self, on=True):
         self._check(self._lib.mavi_set_profiling(self._h, int(on)))
 

@@ -133,9 +133,10 @@ def test_newton_trajectory(cuda_lib, dyn, wall, chunks):
         assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-10
     assert g.time_info.num_steps == 100 and g.time_info.time == o.time()[1]
     if chunks:
+        o.update_chunks()  # device cells are always those of the current positions (the reference's NEXT update_chunks!)
         cg, _ = g.download_cells()
         co, _ = o.download_cells()
-        assert np.array_equal(cg, co)  # still the same (stale-after-step) cell assignment
+        assert np.array_equal(cg, co)
 
 
 def test_quick_start_c1(cuda_lib):
@@ -313,6 +314,30 @@ def test_bitwise_reproducible(cuda_lib):
         outs.append((g.state.pos.copy(), g.state.vel.copy(), g.get_forces()))
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("flag", ["tight", "resort"])
+def test_repair_paths_agree(cuda_lib, flag):
+    """The incremental tile repair, the full rebuild every step (MAVI_FLAG_RESORT_EVERY_STEP) and the
+    overflow -> rebuild -> resume path (forced by MAVI_FLAG_TIGHT_TILES: no slack in the tiles, steps enqueued in
+    batches and rolled back to the device-side step counter) all give the oracle's trajectory."""
+    case = H.newton_case(nx=40, ny=40, dyn=DYNS["harm"], wall="periodic", jitter=0.3, vmax=3.0, dt=0.002)
+    fl = pkg.capi.FLAG_TIGHT_TILES if flag == "tight" else pkg.capi.FLAG_RESORT_EVERY_STEP
+    case["int_cfg"] = pkg.IntCfg(dt=0.002, chunks_cfg=case["int_cfg"].chunks_cfg, device=pkg.CUDADevice(flags=fl))
+    g, o = _pair(case)
+    g.step(150)
+    o.step(150)
+    g.sync_to_host()
+    assert np.abs(g.state.pos - o.pos()).max() / case["geom"].length < TOL
+    assert H.rel_err(g.state.vel, o.second()) < 1e-10
+    assert g.time_info.num_steps == 150 and g.time_info.time == o.time()[1]
+    if flag == "tight":
+        assert g.rebuild_count() > 0  # the overflow path really ran
+    # the device keeps the binning of the CURRENT positions (what the reference's next update_chunks! produces)
+    o.update_chunks()
+    cg, ng = g.download_cells()
+    co, no = o.download_cells()
+    assert np.array_equal(ng, no) and np.array_equal(cg, co)
 
 
 def test_kernels_actually_launch(cuda_lib):
