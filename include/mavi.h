@@ -134,6 +134,7 @@ typedef struct MaviParams {
 
 /* flags */
 #define MAVI_FLAG_RESORT_EVERY_STEP 1 /* full update_chunks! rebuild every step instead of the incremental tile repair (A/B testing) */
+#define MAVI_FLAG_NO_FORCE_CARRY 4    /* Newton steps: always run the full first force pass instead of carrying F2 / the drift over from the previous step (A/B testing; results are bit-identical) */
 #define MAVI_FLAG_TIGHT_TILES 2       /* testing: tile capacity without slack, so that the overflow -> rebuild -> resume path is exercised */
 
 typedef struct MaviHandle MaviHandle;

@@ -29,6 +29,7 @@ DYN_LJ, DYN_HARMTRUNC, DYN_SZABO, DYN_RTP, DYN_RINGS = range(5)
 RNG_HOST_NOISE, RNG_PHILOX = range(2)
 FLAG_RESORT_EVERY_STEP = 1
 FLAG_TIGHT_TILES = 2
+FLAG_NO_FORCE_CARRY = 4
 
 
 class MaviLine(C.Structure):

@@ -267,7 +267,7 @@ int Handle::alloc_state(int n_active, int cap) {
   DevArrays &A = a;
   void *old[] = {A.pos[0], A.pos[1], A.vel, A.ang, A.idflag, A.cell, A.force, A.force_old, A.tstart, A.tile_prefix,
                  A.perm, A.scan_partials, A.tile_dirty, A.dirty_list, A.inbox_cnt, A.inbox, A.mv_src, A.mv_pos,
-                 A.mv_second, A.mv_force, A.mv_id, A.mv_cell};
+                 A.mv_second, A.mv_force, A.mv_id, A.mv_cell, A.chg};
   for (void *q : old) dev_free(this, q);
   p.n_active = p.num_cells > 0 ? n_active : 0;
   p.n_count = p.slab ? slab.n_global : n_active;
@@ -292,10 +292,11 @@ int Handle::alloc_state(int n_active, int cap) {
     magic_div((unsigned int)p.ord_cols, &p.cols_mul, &p.cols_shr);
     p.inbox_cap = cap;  // a tile can never receive more than it can hold: inbox overflow implies tile overflow
     p.mv_cap = n_cap / 4 > 4096 ? n_cap / 4 : 4096;
+    p.chg_cap = 2 * p.mv_cap;
   } else {
     p.tpc = p.nt = p.cap = p.nt_ord = 0;
     p.tail_base = 0;
-    p.inbox_cap = p.mv_cap = 0;
+    p.inbox_cap = p.mv_cap = p.chg_cap = 0;
   }
   ns = (size_t)p.tail_base + (size_t)(p.slab ? 0 : (p.n - p.n_active));
   int st;
@@ -326,6 +327,8 @@ int Handle::alloc_state(int n_active, int cap) {
   if ((st = dev_alloc(this, &A.mv_force, mv))) return st;
   if ((st = dev_alloc(this, &A.mv_id, mv))) return st;
   if ((st = dev_alloc(this, &A.mv_cell, mv))) return st;
+  if ((st = dev_alloc(this, &A.chg, (size_t)p.chg_cap + 2))) return st;
+  carry_valid = false;
   CUDA_TRY(this, cudaMemsetAsync(A.force_old, 0, ns * sizeof(double2), stream));
   CUDA_TRY(this, cudaMemsetAsync(A.pos[1], 0, ns * sizeof(double2), stream));
   return MAVI_OK;
@@ -336,6 +339,7 @@ static int round_up16(double x) { return ((int)std::ceil(x) + 15) / 16 * 16; }
 // update_chunks! from scratch: staging arrays -> tile layout.  Grows the tile capacity until every tile fits.
 int Handle::rebuild_from_staging(int n_active) {
   const bool second_is_vel = second_kind == SECOND_VEL;
+  carry_valid = false;  // new layout / new state: the next Newton step starts with the full first pass
   int cap = p.cap;
   if (p.num_cells > 0 && (a.pos[0] == nullptr || n_active != p.n_active || cap <= 0)) {
     const long long ntiles = (long long)(p.slab ? p.num_cols - 2 : p.num_cols) * ((p.num_rows + MAVI_TR - 1) / MAVI_TR);
@@ -367,6 +371,7 @@ int Handle::rebuild_from_staging(int n_active) {
     }
     CUDA_TRY(this, cudaMemsetAsync(a.count, 0, ((size_t)p.num_cells + 2) * sizeof(int), stream));
     CUDA_TRY(this, cudaMemsetAsync(a.flags + 1, 0, (FLAG_STEPS - 1) * sizeof(int), stream));
+    CUDA_TRY(this, cudaMemsetAsync(a.flags + FLAG_NCHG, 0, 2 * sizeof(int), stream));
     CUDA_TRY(this, cudaMemsetAsync(a.tile_dirty, 0, ((size_t)p.nt + 1) * sizeof(int), stream));
     CUDA_TRY(this, cudaMemsetAsync(a.inbox_cnt, 0, ((size_t)p.nt + 1) * sizeof(int), stream));
     launch_build_tiles(ctx(), p, a, second_is_vel);
@@ -431,10 +436,13 @@ int Handle::enqueue_step(const double *noise_dev) {
   // per-step control words: #dirty tiles, big-drift guard, #position fix-ups, #inter-tile movers, "step ran"
   launch_step_begin(c, a);
   if (prof) cudaEventRecord(ev[1], stream);
+  // Force carry (chunked Newton runs; MAVI_FLAG_NO_FORCE_CARRY switches it off): the second pass of the previous step
+  // already produced this step's F1 and drift, see k_newton_b.
+  const bool carry = second_is_vel && p.num_cells > 0 && !(flags_cfg & (MAVI_FLAG_NO_FORCE_CARRY | MAVI_FLAG_RESORT_EVERY_STEP));
   if (second_is_vel) {
-    launch_newton_a(c, p, a);  // pos[0] -> pos[1] (drift), F1 -> force_old
+    if (!carry || !carry_valid) launch_newton_a(c, p, a);  // pos[0] -> pos[1] (drift), F1 -> force_old
     if (prof) cudaEventRecord(ev[2], stream);
-    launch_newton_b(c, p, a);  // F2 from pos[1]; vel, force; sparse wall fix-ups applied to pos[1]
+    launch_newton_b(c, p, a, carry);  // F2 from pos[1]; vel, force; sparse wall fix-ups applied to pos[1]
   } else {
     if (prof) cudaEventRecord(ev[2], stream);
     launch_self_propelled(c, p, a, noise_dev, (unsigned long long)num_steps);
@@ -444,6 +452,10 @@ int Handle::enqueue_step(const double *noise_dev) {
   // update_chunks! for the NEXT step, incrementally: only tiles a particle left or entered are rewritten
   if (!(flags_cfg & MAVI_FLAG_RESORT_EVERY_STEP)) launch_repair_tiles(c, p, a, second_is_vel);
   else if (p.num_cells > 0 && (st = rebuild_from_current())) return st;  // A/B switch: global rebuild instead of the repair
+  if (carry) {
+    launch_carry_fixups(c, p, a);
+    carry_valid = true;
+  }
   if (prof) cudaEventRecord(ev[4], stream);
   time += p.dt;  // update_time!, src/integration.jl:500-503
   num_steps += 1;

@@ -50,6 +50,7 @@ struct DevParams {
   int tail_base;  // first slot of the inactive tail = nt * cap
   int inbox_cap;  // per-tile capacity for particles arriving from other tiles in one step
   int mv_cap;     // capacity of the per-step inter-tile mover list
+  int chg_cap;    // capacity of the per-step changed-cell list (force carry)
   // x-slab domain decomposition (one process per GPU): the local grid is [left halo | owned columns | right halo];
   // cell arithmetic stays GLOBAL (bit-exact global cell ids), only the column index is shifted into the local frame.
   int slab;                   // 1 = slab mode
@@ -97,7 +98,9 @@ enum {
   FLAG_OVERFLOW = 6, FLAG_MAXCOUNT = 7, FLAG_TAIL = 8, FLAG_MAXINBOX = 9, FLAG_MAXINBOX_TILE = 10,
   FLAG_STEPS = 11,    // steps that really ran since the last upload (device-side step counter)
   FLAG_SCRATCH = 12,
-  FLAG_COUNT = 16
+  // force carry (see k_newton_b): cells whose membership changed in this step, and the big-drift guard of the NEXT step
+  FLAG_NCHG = 16, FLAG_BIGMOVE_NEXT = 17,
+  FLAG_COUNT = 24
 };
 
 // A step whose tile repair overflowed (or that pushed a particle out of the grid) leaves the layout un-repaired: every

@@ -42,6 +42,7 @@ struct Handle {
   size_t ns = 0;  // number of particle slots (tiles * cap + inactive tail)
   int *flags_host = nullptr;  // pinned mirror of a.flags[0..3]
   bool prof = false;
+  bool carry_valid = false;  // pos[1] / force_old hold the drift and F1 of the next Newton step (force carry)
   long long launches = 0;
   long long n_rebuilds = 0;  // overflow -> rebuild events (instrumentation)
   int steps_seen = 0;  // host mirror of the device-side step counter flags[FLAG_STEPS]

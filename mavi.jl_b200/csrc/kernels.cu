@@ -936,21 +936,43 @@ __device__ __forceinline__ void force_prologue(const DevParams &p, const int *__
 // destination tile's inbox when it changes tile.
 struct MoverSink {
   int *cell, *tile_dirty, *dirty_list, *inbox_cnt, *inbox, *mv_src, *flags;
+  int *chg;  // changed-cell list of the force carry (nullptr: not recorded)
 };
 
 __device__ __forceinline__ void mark_dirty(const MoverSink &ms, int t) {
   if (atomicExch(&ms.tile_dirty[t], 1) == 0) ms.dirty_list[atomicAdd(&ms.flags[FLAG_CHANGED], 1)] = t;
 }
 
+// Force carry: cells whose membership (or a member's position) changed behind the back of the pair pass of this step.
+// Every particle that has such a cell in its stencil gets its next F1 recomputed (k_recompute_changed).
+__device__ __forceinline__ void note_changed_cells(const DevParams &p, const MoverSink &ms, int c0, int c1) {
+  if (!ms.chg) return;
+  const int q = atomicAdd(&ms.flags[FLAG_NCHG], 2);
+  if (q + 1 < p.chg_cap) {
+    ms.chg[q] = c0;
+    ms.chg[q + 1] = c1;
+  } else {
+    atomicOr(&ms.flags[FLAG_OVERFLOW], 8);
+  }
+}
+
+// `fixed`: walls! moved the particle (periodic wrap, slippery projection) after the pair pass read its position.
 __device__ __forceinline__ void note_if_moved(const DevParams &p, const MoverSink &ms, int k, int c_old, double x,
-                                              double y) {
-  if (still_in_cell(p, x, y, c_old)) return;
+                                              double y, bool fixed = false) {
+  if (still_in_cell(p, x, y, c_old)) {
+    if (fixed) note_changed_cells(p, ms, c_old, c_old);
+    return;
+  }
   int c_new = cell_of_point(p, x, y);
   if (c_new < 0) {  // left the grid: the reference throws BoundsError at its NEXT update_chunks! -> reported then
     atomicOr(&ms.flags[FLAG_ERR], ERRBIT_OOG_PENDING);
     return;
   }
-  if (c_new == c_old) return;
+  if (c_new == c_old) {
+    if (fixed) note_changed_cells(p, ms, c_old, c_old);
+    return;
+  }
+  note_changed_cells(p, ms, c_old, c_new);
   ms.cell[k] = c_new;
   const int t_old = tile_of_cell(p, c_old), t_new = tile_of_cell(p, c_new);
   mark_dirty(ms, t_old);
@@ -965,6 +987,16 @@ __device__ __forceinline__ void note_if_moved(const DevParams &p, const MoverSin
       atomicOr(&ms.flags[FLAG_OVERFLOW], m < p.mv_cap ? 2 : 4);
     }
   }
+}
+
+// Drift of update_verlet! (src/integration.jl:424): pos + vel dt + F dt^2/2, written with explicit FMAs so that every
+// kernel that produces a drifted position (k_newton_a, the carry in k_newton_b, the sparse fix-up kernels) rounds alike.
+__device__ __forceinline__ double2 verlet_drift(const DevParams &p, double2 r, double2 v, double2 F, bool &big) {
+  const double mx = fma(v.x, p.dt, F.x * p.term), my = fma(v.y, p.dt, F.y * p.term);
+  // displacement guard of the min-image shortcut: a drift beyond one cell in one step makes the pair pass that reads
+  // the drifted positions on stale cells take the exact (minimum-image everywhere) path.
+  big = !(fabs(mx) <= p.cl && fabs(my) <= p.ch);
+  return make_double2(r.x + mx, r.y + my);
 }
 
 // pull a line towards L1 without tying up a register across the pair loop (the value is loaded after the loop)
@@ -1022,12 +1054,9 @@ __global__ void __launch_bounds__(TPB) k_newton_a(const __grid_constant__ DevPar
       if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
     }
     const double2 v = vel[k];
-    double mx = v.x * p.dt + F.x * p.term, my = v.y * p.dt + F.y * p.term;
-    r.x = r.x + mx;
-    r.y = r.y + my;
-    // displacement guard of the min-image shortcut: a drift beyond one cell in one step makes pass B take the exact
-    // (minimum-image everywhere) path.  Never happens in a stable run; keeps the fast path assumption-free.
-    if (!ALLP && PER && !(fabs(mx) <= p.cl && fabs(my) <= p.ch)) flags[FLAG_BIGMOVE] = 1;
+    bool big;
+    r = verlet_drift(p, r, v, F, big);
+    if (!ALLP && PER && big) flags[FLAG_BIGMOVE] = 1;
     pos_out[k] = r;
     f1[k] = F;
   }
@@ -1037,12 +1066,22 @@ __global__ void __launch_bounds__(TPB) k_newton_a(const __grid_constant__ DevPar
 // lists and WITHOUT wall forces; vel += dt/2 (F2 + F1); walls!(active ids).  Position changes made by walls!
 // (periodic wrap, slippery projection) are deferred to a sparse fix-up list because neighbours still read the
 // unmodified drifted positions in this launch; the fresh cell of the FINAL position feeds the incremental repair.
-template <int DYN, bool PER, bool ALLP>
+//
+// CARRY (force carry, default for chunked Newton runs): the first half of the NEXT newton_step! recomputes the pair
+// forces at exactly the positions this kernel just used — F1(n+1) differs from F2(n) only for particles that have, in
+// their stencil, a cell whose membership changed (the re-binning between the two calls) or a particle that walls!
+// moved.  So this kernel also writes the next drift  pos'' = pos' + vel' dt + (F2 + wall forces) dt^2/2  and records the
+// changed cells; after the tile repair k_redrift_tiles / k_recompute_changed redo F1 and the drift for the few affected
+// particles with the fresh cell lists, and the next step starts directly with this kernel.  Results are bit-identical
+// to running k_newton_a every step (tests/test_gpu_core.py::test_force_carry_bitwise).
+//   f1 / f1_next: F1 of this step / of the next one (the same array, updated in place; f2 = get_forces stays F2)
+template <int DYN, bool PER, bool ALLP, bool CARRY>
 __global__ void __launch_bounds__(TPB) k_newton_b(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
                            const int *__restrict__ tile_prefix, const int *__restrict__ cta_first,
                            const unsigned int *__restrict__ idflag, const double2 *__restrict__ pos_in,
-                           double2 *__restrict__ vel, const double2 *__restrict__ f1, double2 *__restrict__ f2,
-                           int *__restrict__ fix_idx, double2 *__restrict__ fix_pos, const MoverSink ms) {
+                           double2 *__restrict__ vel, const double2 *f1, double2 *f2, double2 *f1_next,
+                           double2 *__restrict__ pos_next, int *__restrict__ fix_idx,
+                           double2 *__restrict__ fix_pos, const MoverSink ms) {
   if (!ms.flags[FLAG_RAN]) return;
   const bool exact = !ALLP && ms.flags[FLAG_BIGMOVE] != 0;
   MAVI_FORCE_KERNEL_PROLOGUE(pos_in, exact)
@@ -1062,15 +1101,91 @@ __global__ void __launch_bounds__(TPB) k_newton_b(const __grid_constant__ DevPar
     if (active) {
       const double x0 = r.x, y0 = r.y;
       apply_walls<true>(p, r.x, r.y, v.x, v.y, p.particle_radius);
-      if (r.x != x0 || r.y != y0) {
+      const bool fixed = (r.x != x0 || r.y != y0);
+      if (fixed) {
         int m = atomicAdd(&ms.flags[FLAG_NFIX], 1);
         fix_idx[m] = k;
         fix_pos[m] = r;
       }
-      if (!ALLP) note_if_moved(p, ms, k, c, r.x, r.y);
+      if (!ALLP) note_if_moved(p, ms, k, c, r.x, r.y, fixed);
     }
     vel[k] = v;
     f2[k] = F;
+    if (CARRY) {
+      double2 Fn = F;
+      if (p.has_force_walls && active) wall_forces(p, r.x, r.y, Fn.x, Fn.y);
+      f1_next[k] = Fn;
+      bool big;
+      pos_next[k] = verlet_drift(p, r, v, Fn, big);
+      if (PER && big) ms.flags[FLAG_BIGMOVE_NEXT] = 1;
+    }
+  }
+}
+
+// Force carry, after the tile repair (fresh cell lists, current positions in `pos`):
+// (1) the repair moved pos / vel / force of every particle of a dirty tile to new slots but not the carried drift:
+//     redo it (and F1 = F2 + wall forces) for those tiles, one warp per dirty tile.
+__global__ void k_redrift_tiles(const __grid_constant__ DevParams p, int *__restrict__ flags,
+                                const int *__restrict__ dirty_list, const int *__restrict__ tstart,
+                                const double2 *__restrict__ pos, const double2 *__restrict__ vel,
+                                const double2 *__restrict__ force, double2 *__restrict__ f1_next,
+                                double2 *__restrict__ pos_next) {
+  if (!flags[FLAG_RAN] || flags[FLAG_OVERFLOW]) return;
+  const int lane = threadIdx.x & 31, w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int nd = flags[FLAG_CHANGED];
+  for (int d = w; d < nd; d += nw) {
+    const int t = dirty_list[d];
+    const int b = t * p.cap, e = tstart[(size_t)t * (MAVI_TR + 1) + MAVI_TR];
+    for (int k = b + lane; k < e; k += 32) {
+      const double2 r = pos[k];
+      double2 F = force[k];
+      if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
+      f1_next[k] = F;
+      bool big;
+      pos_next[k] = verlet_drift(p, r, vel[k], F, big);
+      if (p.periodic && big) flags[FLAG_BIGMOVE_NEXT] = 1;
+    }
+  }
+}
+
+// (2) F1 and the drift of every particle that has a changed cell in its stencil, with the fresh cell lists: one warp
+//     per list entry, lane l < 9 takes the l-th cell of the entry's stencil (the stencil relation is symmetric).
+//     Entries may repeat and neighbourhoods overlap: the recomputation is idempotent (reads pos / vel, writes
+//     f1_next / pos_next), so concurrent duplicates store identical values.  Same neighbour order (column-1 rows
+//     r-1..r+1, own column, column+1) and the same pair arithmetic as the staged walk -> bit-identical to k_newton_a.
+template <int DYN, bool PER>
+__global__ void k_recompute_changed(const __grid_constant__ DevParams p, int *__restrict__ flags,
+                                    const int *__restrict__ chg, const int *__restrict__ tstart,
+                                    const double2 *__restrict__ pos, const double2 *__restrict__ vel,
+                                    double2 *__restrict__ f1_next, double2 *__restrict__ pos_next) {
+  if (!flags[FLAG_RAN] || flags[FLAG_OVERFLOW]) return;
+  const int lane = threadIdx.x & 31, w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int n = min(flags[FLAG_NCHG], p.chg_cap);
+  const int R = p.num_rows, Cn = p.num_cols;
+  for (int e = w; e < n; e += nw) {
+    if (lane >= 9) continue;
+    const int c0 = chg[e];
+    if ((e & 1) && c0 == chg[e - 1]) continue;  // (c, c) pair of a particle that was moved inside its cell
+    const int col0 = div_rows(p, c0), row0 = c0 - col0 * R;
+    int c2 = col0 + lane / 3 - 1, r2 = row0 + lane % 3 - 1;
+    if (c2 < 0) { if (!p.wrap_cols) continue; c2 = Cn - 1; }
+    else if (c2 >= Cn) { if (!p.wrap_cols) continue; c2 = 0; }
+    if (r2 < 0) { if (!p.wrap_rows) continue; r2 = R - 1; }
+    else if (r2 >= R) { if (!p.wrap_rows) continue; r2 = 0; }
+    const int cell = c2 * R + r2;
+    const int q = tq_of(p, c2, r2);
+    const int kb = tstart[q], ke = tstart[q + 1];
+    for (int k = kb; k < ke; k++) {
+      const double2 r = pos[k];
+      double fx = 0.0, fy = 0.0;
+      for_each_neighbor(p, tstart, cell, k, [&](int j) { accumulate_pair<DYN, PER>(p, r, __ldg(pos + j), fx, fy); });
+      if (p.has_force_walls) wall_forces(p, r.x, r.y, fx, fy);
+      const double2 F = make_double2(fx, fy);
+      f1_next[k] = F;
+      bool big;
+      pos_next[k] = verlet_drift(p, r, vel[k], F, big);
+      if (PER && big) flags[FLAG_BIGMOVE_NEXT] = 1;
+    }
   }
 }
 
@@ -1081,7 +1196,9 @@ __global__ void k_step_begin(int *__restrict__ flags) {
   if (threadIdx.x == 0) {
     const int run = step_poisoned(flags) ? 0 : 1;
     flags[FLAG_CHANGED] = 0;
-    flags[FLAG_BIGMOVE] = 0;
+    flags[FLAG_BIGMOVE] = flags[FLAG_BIGMOVE_NEXT];  // raised by the carried drift of the previous step
+    flags[FLAG_BIGMOVE_NEXT] = 0;
+    flags[FLAG_NCHG] = 0;
     flags[FLAG_NFIX] = 0;
     flags[FLAG_NMV] = 0;
     flags[FLAG_RAN] = run;
@@ -1173,7 +1290,7 @@ __global__ void __launch_bounds__(TPB) k_self_propelled(const __grid_constant__ 
   } while (0)
 
 static MoverSink mover_sink(const DevArrays &a) {
-  return MoverSink{a.cell, a.tile_dirty, a.dirty_list, a.inbox_cnt, a.inbox, a.mv_src, a.flags};
+  return MoverSink{a.cell, a.tile_dirty, a.dirty_list, a.inbox_cnt, a.inbox, a.mv_src, a.flags, nullptr};
 }
 
 void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool with_wall_forces) {
@@ -1198,16 +1315,39 @@ void launch_newton_a(const LaunchCtx &c, const DevParams &p, const DevArrays &a)
 #undef CALL
 }
 
-void launch_newton_b(const LaunchCtx &c, const DevParams &p, const DevArrays &a) {
+// carry: also write the next step's F1 / drift (into force_old / pos[0]) and record the changed cells
+void launch_newton_b(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool carry) {
   const bool allp = p.num_cells == 0;
-  const MoverSink ms = mover_sink(a);
+  MoverSink ms = mover_sink(a);
   // reads the drifted positions pos[1] (which become the current positions after the sparse wall fix-ups)
+#define ARGS p, a.tstart, a.tile_prefix, a.cta_first, a.idflag, a.pos[1], a.vel, a.force_old, a.force, a.force_old, a.pos[0], a.fix_idx, a.fix_pos, ms
 #define CALL(D, P, A) \
-  MAVI_LAUNCH(c, (k_newton_b<D, P, A>), nblk(p.n, RPB), TPB, (A ? 64 : PASS_SMEM), p, a.tstart, a.tile_prefix, a.cta_first, a.idflag, a.pos[1], a.vel, a.force_old, a.force, a.fix_idx, a.fix_pos, ms)
-  if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, allp, CALL);
-  else MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, allp, CALL);
+  MAVI_LAUNCH(c, (k_newton_b<D, P, A, false>), nblk(p.n, RPB), TPB, (A ? 64 : PASS_SMEM), ARGS)
+#define CALLC(D, P, A) \
+  MAVI_LAUNCH(c, (k_newton_b<D, P, false, true>), nblk(p.n, RPB), TPB, PASS_SMEM, ARGS)
+  if (carry && !allp) {
+    ms.chg = a.chg;
+    if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, false, CALLC);
+    else MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, false, CALLC);
+  } else {
+    if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, allp, CALL);
+    else MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, allp, CALL);
+  }
 #undef CALL
+#undef CALLC
+#undef ARGS
   MAVI_LAUNCH(c, k_apply_pos_fixes, 64, TPB, 0, a.flags, a.fix_idx, a.fix_pos, a.pos[1]);
+}
+
+// force carry, after the swap and the tile repair: pos[0] = current positions, pos[1] = carried drift
+void launch_carry_fixups(const LaunchCtx &c, const DevParams &p, const DevArrays &a) {
+  MAVI_LAUNCH(c, k_redrift_tiles, 148 * 2, TPB, 0, p, a.flags, a.dirty_list, a.tstart, a.pos[0], a.vel, a.force,
+              a.force_old, a.pos[1]);
+#define CALL(D, P, A) \
+  MAVI_LAUNCH(c, (k_recompute_changed<D, P>), 148 * 4, TPB, 0, p, a.flags, a.chg, a.tstart, a.pos[0], a.vel, a.force_old, a.pos[1])
+  if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, false, CALL);
+  else MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, false, CALL);
+#undef CALL
 }
 
 void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const double *noise,

@@ -45,6 +45,7 @@ struct DevArrays {
   double2 *mv_pos, *mv_second, *mv_force;
   unsigned int *mv_id;
   int *mv_cell;
+  int *chg;             // [chg_cap] cells whose membership changed in this step (force carry)
   // control
   int *flags;           // see FLAG_* in common.cuh
   int *fix_idx;         // sparse list of slots whose position walls! changed in pass B
@@ -75,7 +76,8 @@ void refresh_rank_maps(const LaunchCtx &c, const DevParams &p, const DevArrays &
 void launch_step_begin(const LaunchCtx &c, const DevArrays &a);
 void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool with_wall_forces);
 void launch_newton_a(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
-void launch_newton_b(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
+void launch_newton_b(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool carry = false);
+void launch_carry_fixups(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
 void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const double *noise,
                            unsigned long long step);
 

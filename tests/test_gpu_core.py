@@ -340,6 +340,64 @@ def test_repair_paths_agree(cuda_lib, flag):
     assert np.array_equal(ng, no) and np.array_equal(cg, co)
 
 
+def _with_flags(case, flags):
+    ic = case["int_cfg"]
+    case = dict(case)
+    case["int_cfg"] = pkg.IntCfg(dt=ic.dt, chunks_cfg=ic.chunks_cfg, device=pkg.CUDADevice(flags=flags))
+    return case
+
+
+@pytest.mark.parametrize("kind", ["lj_periodic_hot", "harm_rigid", "force_walls", "slippery", "masked", "tight"])
+def test_force_carry_bitwise(cuda_lib, kind):
+    """Force carry (default): the second pair pass of step n also produces F1 and the drift of step n+1, and only the
+    particles that have a re-binned (or wall-moved) particle in their stencil are recomputed with the fresh cell
+    lists.  Must be BIT-identical to running the full first pass every step (MAVI_FLAG_NO_FORCE_CARRY), also across
+    downloads, calc_forces! calls, re-uploads and overflow -> rebuild events in the middle of a run."""
+    if kind == "lj_periodic_hot":  # many cell changes and periodic wraps per step
+        case = H.newton_case(nx=40, ny=36, wall="periodic", jitter=0.3, vmax=3.0, dt=0.002)
+    elif kind == "harm_rigid":
+        case = H.newton_case(nx=40, ny=40, dyn=DYNS["harm"], wall="rigid", jitter=0.3, vmax=3.0, dt=0.002)
+    elif kind == "force_walls":
+        case = _wall_force_case(False)
+    elif kind == "slippery":
+        case = _wall_force_case(True)
+    elif kind == "masked":
+        mask = np.ones(32 * 32, dtype=bool)
+        mask[::5] = False
+        case = H.newton_case(nx=32, ny=32, dyn=DYNS["harm"], wall="periodic", jitter=0.3, vmax=2.0, dt=0.002, active_mask=mask)
+    else:
+        case = H.newton_case(nx=40, ny=40, dyn=DYNS["harm"], wall="periodic", jitter=0.3, vmax=3.0, dt=0.002)
+    base = pkg.capi.FLAG_TIGHT_TILES if kind == "tight" else 0
+    a = H.make_gpu(_with_flags(case, base))
+    b = H.make_gpu(_with_flags(case, base | pkg.capi.FLAG_NO_FORCE_CARRY))
+
+    def same():
+        a.sync_to_host()
+        b.sync_to_host()
+        assert np.array_equal(a.state.pos, b.state.pos)
+        assert np.array_equal(a.state.vel, b.state.vel)
+        assert np.array_equal(a.get_forces(), b.get_forces())
+
+    for n in (1, 2, 37, 120):
+        a.step(n)
+        b.step(n)
+        same()
+    a.calc_forces()   # calc_forces! between steps must not disturb the carried state
+    b.calc_forces()
+    same()
+    a.step(40)
+    b.step(40)
+    same()
+    a.upload_state()  # re-upload (the host copy is the synced state): carry is invalidated and rebuilt
+    b.upload_state()
+    a.step(25)
+    b.step(25)
+    same()
+    assert np.array_equal(a.download_cells()[0], b.download_cells()[0])
+    if kind == "tight":
+        assert a.rebuild_count() > 0
+
+
 def test_kernels_actually_launch(cuda_lib):
     g = H.make_gpu(H.newton_case(nx=16, ny=16))
     n0 = g.launch_count()
