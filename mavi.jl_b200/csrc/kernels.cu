@@ -1148,11 +1148,29 @@ __global__ void k_redrift_tiles(const __grid_constant__ DevParams p, int *__rest
   }
 }
 
+// F1 (fresh cell lists, + wall forces) and the drift of the particle in slot k.  Same neighbour order (column-1 rows
+// r-1..r+1, own column, column+1) and the same pair arithmetic as the staged walk -> bit-identical to k_newton_a.
+template <int DYN, bool PER>
+__device__ __forceinline__ void recompute_particle(const DevParams &p, int *__restrict__ flags,
+                                                   const int *__restrict__ tstart, const double2 *__restrict__ pos,
+                                                   const double2 *__restrict__ vel, double2 *__restrict__ f1_next,
+                                                   double2 *__restrict__ pos_next, int k, int cell) {
+  const double2 r = pos[k];
+  double fx = 0.0, fy = 0.0;
+  for_each_neighbor(p, tstart, cell, k, [&](int j) { accumulate_pair<DYN, PER>(p, r, __ldg(pos + j), fx, fy); });
+  if (p.has_force_walls) wall_forces(p, r.x, r.y, fx, fy);
+  const double2 F = make_double2(fx, fy);
+  f1_next[k] = F;
+  bool big;
+  pos_next[k] = verlet_drift(p, r, vel[k], F, big);
+  if (PER && big) flags[FLAG_BIGMOVE_NEXT] = 1;
+}
+
 // (2) F1 and the drift of every particle that has a changed cell in its stencil, with the fresh cell lists: one warp
-//     per list entry, lane l < 9 takes the l-th cell of the entry's stencil (the stencil relation is symmetric).
-//     Entries may repeat and neighbourhoods overlap: the recomputation is idempotent (reads pos / vel, writes
-//     f1_next / pos_next), so concurrent duplicates store identical values.  Same neighbour order (column-1 rows
-//     r-1..r+1, own column, column+1) and the same pair arithmetic as the staged walk -> bit-identical to k_newton_a.
+//     per list entry; lanes 0..8 look up the 9 cells of the entry's stencil (the stencil relation is symmetric), then
+//     the particles of those cells are dealt out one per lane.  Entries may repeat and neighbourhoods overlap: the
+//     recomputation is idempotent (reads pos / vel, writes f1_next / pos_next), so concurrent duplicates store
+//     identical values.
 template <int DYN, bool PER>
 __global__ void k_recompute_changed(const __grid_constant__ DevParams p, int *__restrict__ flags,
                                     const int *__restrict__ chg, const int *__restrict__ tstart,
@@ -1162,31 +1180,63 @@ __global__ void k_recompute_changed(const __grid_constant__ DevParams p, int *__
   const int lane = threadIdx.x & 31, w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   const int n = min(flags[FLAG_NCHG], p.chg_cap);
   const int R = p.num_rows, Cn = p.num_cols;
-  for (int e = w; e < n; e += nw) {
-    if (lane >= 9) continue;
+  for (int e = w; e < n; e += nw) {  // warp-uniform
     const int c0 = chg[e];
     if ((e & 1) && c0 == chg[e - 1]) continue;  // (c, c) pair of a particle that was moved inside its cell
     const int col0 = div_rows(p, c0), row0 = c0 - col0 * R;
-    int c2 = col0 + lane / 3 - 1, r2 = row0 + lane % 3 - 1;
-    if (c2 < 0) { if (!p.wrap_cols) continue; c2 = Cn - 1; }
-    else if (c2 >= Cn) { if (!p.wrap_cols) continue; c2 = 0; }
-    if (r2 < 0) { if (!p.wrap_rows) continue; r2 = R - 1; }
-    else if (r2 >= R) { if (!p.wrap_rows) continue; r2 = 0; }
-    const int cell = c2 * R + r2;
-    const int q = tq_of(p, c2, r2);
-    const int kb = tstart[q], ke = tstart[q + 1];
-    for (int k = kb; k < ke; k++) {
-      const double2 r = pos[k];
-      double fx = 0.0, fy = 0.0;
-      for_each_neighbor(p, tstart, cell, k, [&](int j) { accumulate_pair<DYN, PER>(p, r, __ldg(pos + j), fx, fy); });
-      if (p.has_force_walls) wall_forces(p, r.x, r.y, fx, fy);
-      const double2 F = make_double2(fx, fy);
-      f1_next[k] = F;
-      bool big;
-      pos_next[k] = verlet_drift(p, r, vel[k], F, big);
-      if (PER && big) flags[FLAG_BIGMOVE_NEXT] = 1;
+    int cnt = 0, kb = 0, cellv = 0;
+    if (lane < 9) {
+      int c2 = col0 + lane / 3 - 1, r2 = row0 + lane % 3 - 1;
+      bool ok = true;
+      if (c2 < 0) { ok = p.wrap_cols; c2 = Cn - 1; }
+      else if (c2 >= Cn) { ok = p.wrap_cols; c2 = 0; }
+      if (r2 < 0) { ok = ok && p.wrap_rows; r2 = R - 1; }
+      else if (r2 >= R) { ok = ok && p.wrap_rows; r2 = 0; }
+      if (ok) {
+        const int q = tq_of(p, c2, r2);
+        kb = tstart[q];
+        cnt = tstart[q + 1] - kb;
+        cellv = c2 * R + r2;
+      }
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 8);
+    for (int base = 0; base < total; base += 32) {  // warp-uniform
+      const int idx = base + lane;
+      int k = -1, cell = 0;
+#pragma unroll
+      for (int l = 0; l < 9; l++) {
+        const int il = __shfl_sync(0xffffffffu, incl, l), cl = __shfl_sync(0xffffffffu, cnt, l);
+        const int kl = __shfl_sync(0xffffffffu, kb, l), ce = __shfl_sync(0xffffffffu, cellv, l);
+        if (idx < il && idx >= il - cl) { k = kl + (idx - (il - cl)); cell = ce; }
+      }
+      if (k >= 0) recompute_particle<DYN, PER>(p, flags, tstart, pos, vel, f1_next, pos_next, k, cell);
     }
   }
+}
+
+// (3) slab mode: the neighbour rank's boundary column re-bins behind this rank's back, so every particle of the two
+//     owned boundary columns (local columns 1 and num_cols-2) is recomputed every step.
+template <int DYN, bool PER>
+__global__ void k_recompute_columns(const __grid_constant__ DevParams p, int *__restrict__ flags,
+                                    const int *__restrict__ tstart, const int *__restrict__ cell,
+                                    const double2 *__restrict__ pos, const double2 *__restrict__ vel,
+                                    double2 *__restrict__ f1_next, double2 *__restrict__ pos_next) {
+  if (!flags[FLAG_RAN] || flags[FLAG_OVERFLOW]) return;
+  const int cs = p.tpc * p.cap;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ncols = (p.num_cols - 2 > 1) ? 2 : 1;
+  if (i >= ncols * cs) return;
+  const int col = (i < cs) ? 1 : p.num_cols - 2;
+  const int k = col * cs + (i < cs ? i : i - cs);
+  const int t = k / p.cap;
+  if (k >= tstart[(size_t)t * (MAVI_TR + 1) + MAVI_TR]) return;  // slack slot
+  recompute_particle<DYN, PER>(p, flags, tstart, pos, vel, f1_next, pos_next, k, cell[k]);
 }
 
 // First kernel of every step: decides ONCE whether the step runs (no overflow / out-of-grid latched by an earlier
@@ -1340,14 +1390,29 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p, const DevArrays &a,
 }
 
 // force carry, after the swap and the tile repair: pos[0] = current positions, pos[1] = carried drift
-void launch_carry_fixups(const LaunchCtx &c, const DevParams &p, const DevArrays &a) {
+void launch_carry_redrift(const LaunchCtx &c, const DevParams &p, const DevArrays &a) {
   MAVI_LAUNCH(c, k_redrift_tiles, 148 * 2, TPB, 0, p, a.flags, a.dirty_list, a.tstart, a.pos[0], a.vel, a.force,
               a.force_old, a.pos[1]);
+}
+
+void launch_carry_recompute(const LaunchCtx &c, const DevParams &p, const DevArrays &a) {
 #define CALL(D, P, A) \
   MAVI_LAUNCH(c, (k_recompute_changed<D, P>), 148 * 4, TPB, 0, p, a.flags, a.chg, a.tstart, a.pos[0], a.vel, a.force_old, a.pos[1])
   if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, false, CALL);
   else MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, false, CALL);
 #undef CALL
+  if (!p.slab) return;
+  const int nthreads = 2 * p.tpc * p.cap;
+#define CALL(D, P, A) \
+  MAVI_LAUNCH(c, (k_recompute_columns<D, P>), nblk(nthreads), TPB, 0, p, a.flags, a.tstart, a.cell, a.pos[0], a.vel, a.force_old, a.pos[1])
+  if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, false, CALL);
+  else MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, false, CALL);
+#undef CALL
+}
+
+void launch_carry_fixups(const LaunchCtx &c, const DevParams &p, const DevArrays &a) {
+  launch_carry_redrift(c, p, a);
+  launch_carry_recompute(c, p, a);
 }
 
 void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const double *noise,

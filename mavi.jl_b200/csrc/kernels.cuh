@@ -77,6 +77,9 @@ void launch_step_begin(const LaunchCtx &c, const DevArrays &a);
 void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool with_wall_forces);
 void launch_newton_a(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
 void launch_newton_b(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool carry = false);
+// force carry (see k_newton_b): redo the carried drift of repaired tiles / recompute F1 around re-binned cells
+void launch_carry_redrift(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
+void launch_carry_recompute(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
 void launch_carry_fixups(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
 void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const double *noise,
                            unsigned long long step);

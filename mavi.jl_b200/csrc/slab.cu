@@ -191,7 +191,7 @@ __global__ void k_ingest(const __grid_constant__ DevParams p, const int *__restr
                          double2 *__restrict__ mv_second, double2 *__restrict__ mv_force,
                          unsigned int *__restrict__ mv_id, int *__restrict__ mv_cell, int *__restrict__ mv_src,
                          int *__restrict__ tile_dirty, int *__restrict__ dirty_list, int *__restrict__ inbox_cnt,
-                         int *__restrict__ inbox, int *__restrict__ flags) {
+                         int *__restrict__ inbox, int *__restrict__ flags, int *__restrict__ chg) {
   // one block per tile row of the column; threads over its slots
   const int tr = blockIdx.x;
   const int cnt = rts[tr * TR1 + MAVI_TR] - rts[tr * TR1];
@@ -206,6 +206,11 @@ __global__ void k_ingest(const __grid_constant__ DevParams p, const int *__restr
     }
     const int t = tile_of_cell(p, c);
     if (atomicExch(&tile_dirty[t], 1) == 0) dirty_list[atomicAdd(&flags[FLAG_CHANGED], 1)] = t;
+    if (chg) {  // force carry: the arrival changes the membership of its cell
+      const int q = atomicAdd(&flags[FLAG_NCHG], 2);
+      if (q + 1 < p.chg_cap) { chg[q] = c; chg[q + 1] = c; }
+      else atomicOr(&flags[FLAG_OVERFLOW], 8);
+    }
     const int m = atomicAdd(&flags[FLAG_NMV], 1);
     const int i = atomicAdd(&inbox_cnt[t], 1);
     if (m < p.mv_cap && i < p.inbox_cap) {
@@ -281,7 +286,7 @@ static int slab_alloc_mig(Handle *h) {
 
 // After the local repair the halo tiles (columns 0 and m+1) hold exactly the emigrants.  Ship both columns, then
 // queue what arrived as movers and run the tile repair a second time.
-static int slab_migrate(Handle *h) {
+static int slab_migrate(Handle *h, bool carry) {
   const DevParams &p = h->p;
   SlabState &s = h->slab;
   DevArrays &a = h->a;
@@ -320,10 +325,11 @@ static int slab_migrate(Handle *h) {
     k_ingest<<<p.tpc, 128, 0, h->stream>>>(p, s.mig_ts[d], sender_base, s.mig_pos[d], vel ? s.mig_second[d] : nullptr,
                                            vel ? nullptr : (const double *)s.mig_second[d], s.mig_force[d], s.mig_id[d],
                                            a.mv_pos, a.mv_second, a.mv_force, a.mv_id, a.mv_cell, a.mv_src, a.tile_dirty,
-                                           a.dirty_list, a.inbox_cnt, a.inbox, a.flags);
+                                           a.dirty_list, a.inbox_cnt, a.inbox, a.flags, carry ? a.chg : nullptr);
     h->launches++;
   }
   launch_repair_tiles(h->ctx(), p, a, vel);
+  if (carry) launch_carry_redrift(h->ctx(), p, a);  // tiles rewritten by the second repair round
   return MAVI_OK;
 }
 
@@ -364,11 +370,13 @@ int slab_step_once(Handle *h, const double *noise_dev) {
   if (h->prof) cudaEventRecord(h->ev[0], h->stream);
   launch_step_begin(c, a);
   if (h->prof) cudaEventRecord(h->ev[1], h->stream);
+  // force carry (see k_newton_b): F1 and the drift of this step were produced by the previous one
+  const bool carry = vel && !(h->flags_cfg & MAVI_FLAG_NO_FORCE_CARRY);
   if (vel) {
-    launch_newton_a(c, p, a);                                     // owned: pos[0] -> pos[1], F1
+    if (!carry || !h->carry_valid) launch_newton_a(c, p, a);      // owned: pos[0] -> pos[1], F1
     if (h->prof) cudaEventRecord(h->ev[2], h->stream);
     if ((st = slab_halo_exchange(h, a.pos[1], false))) return st; // drifted halo positions, same (stale) layout
-    launch_newton_b(c, p, a);
+    launch_newton_b(c, p, a, carry);
   } else {
     if (h->prof) cudaEventRecord(h->ev[2], h->stream);
     launch_self_propelled(c, p, a, noise_dev, (unsigned long long)h->num_steps);
@@ -378,17 +386,22 @@ int slab_step_once(Handle *h, const double *noise_dev) {
   // update_chunks! for the next step: halo tiles become the emigrant bins, local repair, migration, second repair
   clear_halo_columns(h);
   launch_repair_tiles(c, p, a, vel);
-  if ((st = slab_migrate(h))) return st;
+  if (carry) launch_carry_redrift(c, p, a);  // tiles rewritten by the first repair round (the list is reset below)
+  if ((st = slab_migrate(h, carry))) return st;
   h->time += p.dt;
   h->num_steps += 1;
   if ((st = slab_refresh_count(h))) return st;
   if (h->flags_host[FLAG_OVERFLOW]) {
-    h->set_error("slab mode overflow (bits %d: 1 = tile capacity %d < %d, 2 = inbox capacity %d < %d at tile %d (column %d of %d), 4 = mover list %d)",
+    h->set_error("slab mode overflow (bits %d: 1 = tile capacity %d < %d, 2 = inbox capacity %d < %d at tile %d (column %d of %d), 4 = mover list %d, 8 = changed-cell list)",
                  h->flags_host[FLAG_OVERFLOW], p.cap, h->flags_host[FLAG_MAXCOUNT], p.inbox_cap, h->flags_host[FLAG_MAXINBOX],
                  h->flags_host[FLAG_MAXINBOX_TILE], h->flags_host[FLAG_MAXINBOX_TILE] / p.tpc, p.num_cols, p.mv_cap);
     return MAVI_ERR_CAPACITY;
   }
   if ((st = slab_halo_exchange(h, a.pos[0], true))) return st;
+  if (carry) {  // needs the fresh halo (positions + layout)
+    launch_carry_recompute(c, p, a);
+    h->carry_valid = true;
+  }
   if (h->prof) cudaEventRecord(h->ev[4], h->stream);
   return MAVI_OK;
 }

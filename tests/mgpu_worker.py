@@ -33,7 +33,7 @@ def main():
     ccfg = case["int_cfg"].chunks_cfg
     owner = slabs.partition(st0.pos, case["geom"], ccfg.num_cols, world)
     mine = np.flatnonzero(owner == rank)
-    uid = [slabs.nccl_unique_id() if rank == 0 else None]
+    uid = [slabs.nccl_unique_id() if rank == 0 else None, slabs.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     dev = pkg.CUDADevice(device=local_rank, rank=rank, world=world, nccl_unique_id=uid[0], n_global=len(st0.pos),
                          rng_mode="host_noise")
@@ -47,6 +47,24 @@ def main():
     n0 = system.local_count()
     system.step(steps)
     ids, pos, second, forces = system.download_local()
+    same = True
+    if kind in ("lj", "harm"):
+        # force carry (default) vs the full first pass every step: bit-identical, also across slab boundaries
+        dev2 = pkg.CUDADevice(device=local_rank, rank=rank, world=world, nccl_unique_id=uid[1], n_global=len(st0.pos),
+                              rng_mode="host_noise", flags=pkg.capi.FLAG_NO_FORCE_CARRY)
+        st2 = pkg.SecondLawState(pos=st0.pos[mine], vel=st0.vel[mine])
+        st2.ids = mine
+        sys2 = pkg.System(state=st2, space_cfg=case["space"], dynamic_cfg=case["dyn"],
+                          int_cfg=pkg.IntCfg(dt=case["int_cfg"].dt, chunks_cfg=ccfg, device=dev2))
+        sys2.step(steps)
+        ids2, pos2, second2, forces2 = sys2.download_local()
+        o1, o2 = np.argsort(ids), np.argsort(ids2)
+        same = (np.array_equal(ids[o1], ids2[o2]) and np.array_equal(pos[o1], pos2[o2]) and
+                np.array_equal(second[o1], second2[o2]) and np.array_equal(forces[o1], forces2[o2]))
+        print(f"MGPU rank {rank}: carry == no-carry bitwise: {same}")
+        sys2.close()
+    sames = [None] * world
+    dist.all_gather_object(sames, same)
     gathered = [None] * world
     dist.gather_object((ids, pos, second, forces, n0), gathered if rank == 0 else None, dst=0)
     ok = True
@@ -68,7 +86,7 @@ def main():
         moved = int((owner_now != owner).sum())
         print(f"MGPU {kind} world={world} steps={steps} pos_err={perr:.3e} second_err={serr:.3e} force_err={ferr:.3e} "
               f"changed_owner={moved} count_delta={migrated}")
-        ok = perr < 1e-12 and serr < 1e-10 and ferr < 1e-9 and moved > 0
+        ok = perr < 1e-12 and serr < 1e-10 and ferr < 1e-9 and moved > 0 and all(sames)
         print("MGPU_OK" if ok else "MGPU_FAIL")
     dist.barrier()
     system.close()
