@@ -30,9 +30,13 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as entry  # noqa: E402
 
 SEED = 24042001
-B_ALG_NEWTON = 168.0  # algorithmic bytes per particle-step, Float64 Newton/LJ
+B_ALG_NEWTON = 168.0  # algorithmic bytes per particle-step, Float64 Newton/LJ: bin 24 + A 64 + B 80
 B_ALG_PASS_B = 80.0   # pass B: read pos', vel, F1 (48) + write vel', F2 (32)
 B_ALG_PASS_A = 64.0   # pass A: read pos, vel (32) + write pos', F1 (32)
+# Force carry (default): ONE launch per step = pass B fused with the next step's pass A.  Its own compulsory traffic is
+# read pos', vel, F1 (48) + write vel', F2, pos'' (48) = 96 B (F1 of the next step is F2) — the number
+# the kernel-level roofline uses; the step-level figure keeps SURVEY.md 8d's 168 B of the three-barrier formulation.
+B_ALG_FUSED = 96.0
 
 
 def measured_peak_hbm():
@@ -252,13 +256,33 @@ def run_ours(args):
             tr = json.load(f)["dram_bytes_per_launch"]
     except Exception:
         tr = {}
+    carry = not (args.flags & pkg.capi.FLAG_NO_FORCE_CARRY)
     dom = "pass_b" if phase_ms[2] >= phase_ms[1] else "pass_a"
-    if n == 16_000_000 and dom in tr:
-        traffic = tr[dom]
     dom_ms = phase_ms[2] if dom == "pass_b" else phase_ms[1]
     dom_bytes = (B_ALG_PASS_B if dom == "pass_b" else B_ALG_PASS_A) * n
+    if carry:
+        dom, dom_bytes = "fused_pass", B_ALG_FUSED * n
+    if n == 16_000_000 and dom in tr:
+        traffic = tr[dom]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     step_achieved = B_ALG_NEWTON * n * world / (ms * 1e-3 / args.steps) / 1e9
+    two_pass = None
+    if world == 1 and carry and not args.no_two_pass:
+        # A/B: the same workload with the carry switched off (two full force passes per step), for transparency
+        system.close()
+        del system
+        dev2 = pkg.CUDADevice(device=local_rank, stream=stream, flags=args.flags | pkg.capi.FLAG_NO_FORCE_CARRY)
+        w2 = lj_workload(pkg, nx, ny, cuda_device=dev2)
+        s2 = pkg.System(state=pkg.SecondLawState(pos=w2["pos"], vel=w2["vel"]), space_cfg=w2["space"], dynamic_cfg=w2["dyn"], int_cfg=w2["int_cfg"])
+        s2.step(args.warmup)
+        k2 = max(10, args.steps // 4)
+        barrier()
+        e0.record()
+        s2.step(k2)
+        e1.record()
+        barrier()
+        two_pass = {"ms_per_step": e0.elapsed_time(e1) / k2, "steps": k2, "what": "MAVI_FLAG_NO_FORCE_CARRY: full first + second force pass every step"}
+        s2.close()
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         rate, secs, threads, sample = cpu_reference_rate(pkg, args.cpu_steps, 1, sample_n=args.cpu_sample)
@@ -268,13 +292,18 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"LJ lattice gas {nx}x{ny}={n} particles per GPU, periodic rectangle, {int(nx * 0.9)}x{int(ny * 0.9)} chunks, "
-                               f"f64, dt=0.001, newton_step! (2 force passes)", "l2": "state arrays (>=1.5 GB) exceed the 126 MB L2; no flush needed",
+                               f"f64, dt=0.001, newton_step!", "l2": "state arrays (>=1.5 GB) exceed the 126 MB L2; no flush needed",
                    "parallelism": "single GPU" if world == 1 else f"{world} x-slabs of one {nx * world}x{ny} periodic box, NCCL halo+migration"},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_kind": peak_kind, "kernel_ms": dom_ms,
+                     "bytes_per_particle": dom_bytes / n,
+                     "what": ("k_newton_b<CARRY>: force pass 2 + kick + walls! + re-bin decision of step n fused with force pass 1 + drift of "
+                              "step n+1 (F1(n+1) = F2(n) except near re-binned particles, which are recomputed sparsely; bit-identical "
+                              "to two full passes)") if carry else "two full force passes per step (MAVI_FLAG_NO_FORCE_CARRY)",
                      "step": {"achieved": step_achieved / world, "frac": step_achieved / world / peak, "bytes_per_particle_step": B_ALG_NEWTON},
                      "phase_ms": {"pass_a": phase_ms[1], "pass_b": phase_ms[2], "repair_exchange": phase_ms[3]}},
         "cpu_baseline": cpu,
+        "two_pass": two_pass,
         "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 32 * n,
                 "steps": e2e_steps, "what": "per step: mavi_upload_state(pos,vel from pinned host) + mavi_step(1) + mavi_download_state(pos,vel)"},
         "gpu_launches": launches,
@@ -298,6 +327,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1000, help="CPU baseline sample: an n x n lattice")
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-two-pass", action="store_true", help="skip the A/B run with the force carry switched off")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -293,10 +293,17 @@ int Handle::alloc_state(int n_active, int cap) {
     p.inbox_cap = cap;  // a tile can never receive more than it can hold: inbox overflow implies tile overflow
     p.mv_cap = n_cap / 4 > 4096 ? n_cap / 4 : 4096;
     p.chg_cap = 2 * p.mv_cap;
+    {  // CTA = blk_cols tiles of one tile row, about 1000 particles (kernels.cu, tile-block force kernels)
+      const double mean_tile = (double)(n_active > 0 ? n_active : 1) / (double)((long long)p.ord_cols * p.tpc);
+      int g = (int)(1000.0 / (mean_tile > 1.0 ? mean_tile : 1.0));
+      p.blk_cols = g < 1 ? 1 : (g > 30 ? 30 : g);
+      p.blk_per_row = (p.ord_cols + p.blk_cols - 1) / p.blk_cols;
+    }
   } else {
     p.tpc = p.nt = p.cap = p.nt_ord = 0;
     p.tail_base = 0;
     p.inbox_cap = p.mv_cap = p.chg_cap = 0;
+    p.blk_cols = p.blk_per_row = 0;
   }
   ns = (size_t)p.tail_base + (size_t)(p.slab ? 0 : (p.n - p.n_active));
   int st;

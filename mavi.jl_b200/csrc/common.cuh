@@ -51,6 +51,7 @@ struct DevParams {
   int inbox_cap;  // per-tile capacity for particles arriving from other tiles in one step
   int mv_cap;     // capacity of the per-step inter-tile mover list
   int chg_cap;    // capacity of the per-step changed-cell list (force carry)
+  int blk_cols, blk_per_row;  // tile-block force kernels: own tiles (columns) per CTA, CTAs per tile row
   // x-slab domain decomposition (one process per GPU): the local grid is [left halo | owned columns | right halo];
   // cell arithmetic stays GLOBAL (bit-exact global cell ids), only the column index is shifted into the local frame.
   int slab;                   // 1 = slab mode

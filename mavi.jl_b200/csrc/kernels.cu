@@ -1266,6 +1266,42 @@ __global__ void k_apply_pos_fixes(int *__restrict__ flags, const int *__restrict
   for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) pos[fix_idx[m]] = fix_pos[m];
 }
 
+// update_szabo! (src/integration.jl:433-465) / update_rtp! (:467-498) for the particle in slot k (original id `id`)
+template <int DYN>
+__device__ __forceinline__ void self_propelled_update(const DevParams &p, double2 &r, const double2 F,
+                                                      double *__restrict__ ang, int k, unsigned int id,
+                                                      const double *__restrict__ noise, unsigned long long step) {
+  double theta = ang[k];
+  double sn, cs;
+  sincos(theta, &sn, &cs);
+  if (DYN == MAVI_DYN_SZABO) {
+    const double vo = p.dyn[0], mu = p.dyn[1], relax_time = p.dyn[2], drot = p.dyn[7];
+    double velx = vo * cs + mu * F.x, vely = vo * sn + mu * F.y;
+    double speed = sqrt(fabs(velx) + fabs(vely));  // sqrt(sum(abs, vel)) (sic), :448
+    double cross_prod = speed > 0.0 ? (cs * vely - sn * velx) / speed : 0.0;
+    if (fabs(cross_prod) > 1.0) cross_prod = sign_d(cross_prod);
+    double nz = 0.0;
+    if (drot != 0.0) nz = (p.rng_mode == MAVI_RNG_HOST_NOISE) ? (noise ? noise[id] : 0.0) : philox_normal(p.seed, id, step);
+    double d_theta = 1.0 / relax_time * asin(cross_prod) * p.dt + sqrt(2.0 * drot * p.dt) * nz;
+    r.x += velx * p.dt;
+    r.y += vely * p.dt;
+    ang[k] = theta + d_theta;
+  } else {
+    const double vo = p.dyn[0], tumble_rate = p.dyn[3];
+    double velx = vo * cs + F.x, vely = vo * sn + F.y;
+    r.x += velx * p.dt;
+    r.y += vely * p.dt;
+    double u, u2;
+    if (p.rng_mode == MAVI_RNG_HOST_NOISE) {
+      u = noise ? noise[2 * (size_t)id] : 1.0;
+      u2 = noise ? noise[2 * (size_t)id + 1] : 0.0;
+    } else {
+      philox_uniform2(p.seed, id, step, u, u2);
+    }
+    if (u < tumble_rate * p.dt) ang[k] = 6.283185307179586 * u2;  // 2*pi*rand(), :495
+  }
+}
+
 // szabo_step! / rtp_step! (src/integration.jl:517-535): forces + update_szabo! (:433-465) / update_rtp! (:467-498)
 // + walls! in ONE pass.  The update loops slots 1:count (not ids) like the reference.
 template <int DYN, bool PER, bool ALLP>
@@ -1289,37 +1325,7 @@ __global__ void __launch_bounds__(TPB) k_self_propelled(const __grid_constant__ 
       if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
     }
     force[k] = F;
-    if ((int)id < p.n_count) {
-      double theta = ang[k];
-      double sn, cs;
-      sincos(theta, &sn, &cs);
-      if (DYN == MAVI_DYN_SZABO) {
-        const double vo = p.dyn[0], mu = p.dyn[1], relax_time = p.dyn[2], drot = p.dyn[7];
-        double velx = vo * cs + mu * F.x, vely = vo * sn + mu * F.y;
-        double speed = sqrt(fabs(velx) + fabs(vely));  // sqrt(sum(abs, vel)) (sic), :448
-        double cross_prod = speed > 0.0 ? (cs * vely - sn * velx) / speed : 0.0;
-        if (fabs(cross_prod) > 1.0) cross_prod = sign_d(cross_prod);
-        double nz = 0.0;
-        if (drot != 0.0) nz = (p.rng_mode == MAVI_RNG_HOST_NOISE) ? (noise ? noise[id] : 0.0) : philox_normal(p.seed, id, step);
-        double d_theta = 1.0 / relax_time * asin(cross_prod) * p.dt + sqrt(2.0 * drot * p.dt) * nz;
-        r.x += velx * p.dt;
-        r.y += vely * p.dt;
-        ang[k] = theta + d_theta;
-      } else {
-        const double vo = p.dyn[0], tumble_rate = p.dyn[3];
-        double velx = vo * cs + F.x, vely = vo * sn + F.y;
-        r.x += velx * p.dt;
-        r.y += vely * p.dt;
-        double u, u2;
-        if (p.rng_mode == MAVI_RNG_HOST_NOISE) {
-          u = noise ? noise[2 * (size_t)id] : 1.0;
-          u2 = noise ? noise[2 * (size_t)id + 1] : 0.0;
-        } else {
-          philox_uniform2(p.seed, id, step, u, u2);
-        }
-        if (u < tumble_rate * p.dt) ang[k] = 6.283185307179586 * u2;  // 2*pi*rand(), :495
-      }
-    }
+    if ((int)id < p.n_count) self_propelled_update<DYN>(p, r, F, ang, k, id, noise, step);
     if (active) {
       double vx = 0.0, vy = 0.0;
       apply_walls<false>(p, r.x, r.y, vx, vy, p.particle_radius);
@@ -1327,6 +1333,309 @@ __global__ void __launch_bounds__(TPB) k_self_propelled(const __grid_constant__ 
     }
     pos_out[k] = r;
   }
+}
+
+// =========================================================================================================
+// Tile-block force kernels (chunked runs).  A CTA owns `blk_cols` consecutive tiles of ONE tile row (no rank map, no
+// search: the block geometry is arithmetic on blockIdx).  It stages, column by column, [cell row above | tile | cell
+// row below] of its columns and of the two side columns into shared memory (async 16-byte copies), together with
+//   cwin[j][lr]  = (first staged index of cell row lr-1, end of cell row lr+1) of staged column j  -> the three
+//                  neighbour runs of a particle are three LDS.64 away,
+//   list[q]      = staged index | column << 16 | row << 24 of the q-th OWN particle of the block,
+// and then warps pull 32 own particles at a time from a shared counter.  Columns are staged in chunks of as many as
+// fit, so dense regions only cost more chunks; a single column that does not fit falls back to a per-thread walk of
+// the global arrays.  Trailing blocks handle the inactive tail (slots of masked particles).
+// =========================================================================================================
+constexpr int G2MAX = 30;        // own columns per chunk (plus two side columns: one lane each in the scan)
+constexpr int SPOS2_CAP = 1536;  // staged positions per chunk
+constexpr int OWN2_CAP = 1280;   // own particles per chunk
+
+struct Chunk2 {
+  int nc, use_mi, nown, next, ok;
+  int wr[G2MAX + 2];  // column reached through a periodic wrap / the slab seam
+  int src_a[G2MAX + 2], src_t[G2MAX + 2], src_b[G2MAX + 2];
+  int la[G2MAX + 2], lt[G2MAX + 2], lb[G2MAX + 2];
+  int off[G2MAX + 3], ownoff[G2MAX + 3], gbase[G2MAX + 2];
+  int2 cwin[G2MAX + 2][MAVI_TR];  // [j][lr-1]
+};
+constexpr int C2_BYTES = (sizeof(Chunk2) + 15) / 16 * 16;
+constexpr int PASS2_SMEM = C2_BYTES + SPOS2_CAP * (int)sizeof(double2) + OWN2_CAP * (int)sizeof(unsigned int);
+
+// Stage the chunk of own columns starting at local column cs (at most `rem` columns) of tile row tr.
+template <bool PER>
+__device__ __forceinline__ void chunk_stage(const DevParams &p, const int *__restrict__ tstart,
+                                            const double2 *__restrict__ pos, int tr, int cs, int rem, bool exact_minimg,
+                                            Chunk2 *ck, double2 *s_pos, unsigned int *s_list) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int R = p.num_rows, Cn = p.num_cols;
+  const int r0 = tr * MAVI_TR;
+  const int rows = min(MAVI_TR, R - r0);
+  const int ncand = min(rem, G2MAX);
+  __syncthreads();  // previous chunk fully consumed
+  // ---- column descriptors (one thread per candidate column; independent loads)
+  if (threadIdx.x < ncand + 2) {
+    const int j = threadIdx.x;
+    int c = cs - 1 + j;
+    bool exists = true, wrapped = false;
+    if (c < 0) { if (p.wrap_cols) { c = Cn - 1; wrapped = true; } else exists = false; }
+    else if (c >= Cn) { if (p.wrap_cols) { c = 0; wrapped = true; } else exists = false; }
+    if (exists && p.slab && ((c == 0 && p.seam_left) || (c == Cn - 1 && p.seam_right))) wrapped = true;
+    int ra = r0 - 1, rb = r0 + MAVI_TR;
+    bool has_a = exists, has_b = exists;
+    if (ra < 0) { if (p.wrap_rows) { ra = R - 1; wrapped = wrapped || exists; } else has_a = false; }
+    if (rb >= R) { if (p.wrap_rows) { rb = 0; wrapped = wrapped || exists; } else has_b = false; }
+    int la = 0, lt = 0, lb = 0, sa = 0, st = 0, sb = 0;
+    if (exists) {
+      const int *tt = tstart + (size_t)(c * p.tpc + tr) * (MAVI_TR + 1);
+      const int qa = has_a ? tq_of(p, c, ra) : 0, qb = has_b ? tq_of(p, c, rb) : 0;
+      st = __ldg(tt);
+      const int et = __ldg(tt + MAVI_TR);
+      const int a0 = has_a ? __ldg(tstart + qa) : 0, a1 = has_a ? __ldg(tstart + qa + 1) : 0;
+      const int b0 = has_b ? __ldg(tstart + qb) : 0, b1 = has_b ? __ldg(tstart + qb + 1) : 0;
+      lt = et - st; sa = a0; la = a1 - a0; sb = b0; lb = b1 - b0;
+    }
+    ck->src_t[j] = st; ck->src_a[j] = sa; ck->src_b[j] = sb;
+    ck->la[j] = la; ck->lt[j] = lt; ck->lb[j] = lb;
+    ck->wr[j] = wrapped ? 1 : 0;
+  }
+  __syncthreads();
+  // ---- warp 0: prefix sums, greedy number of own columns that fit
+  if (w == 0) {
+    const int j = lane;
+    const bool in = j < ncand + 2;
+    const int sz = in ? ck->la[j] + ck->lt[j] + ck->lb[j] : 0;
+    const int own = (in && j >= 1 && j <= ncand) ? ck->lt[j] : 0;
+    int incl = sz, oincl = own;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o), u = __shfl_up_sync(0xffffffffu, oincl, o);
+      if (lane >= o) { incl += v; oincl += u; }
+    }
+    const int incl_next = __shfl_down_sync(0xffffffffu, incl, 1);  // staged total if this lane were the last own column
+    const bool fits = j >= 1 && j <= ncand && incl_next <= SPOS2_CAP && oincl <= OWN2_CAP;
+    const unsigned int bal = __ballot_sync(0xffffffffu, fits);
+    const int nc = bal ? 31 - __clz(bal) : 1;  // fits is monotone in j
+    const unsigned int wbal = __ballot_sync(0xffffffffu, in && j <= nc + 1 && ck->wr[j]);
+    ck->off[j] = incl - sz;
+    ck->ownoff[j] = oincl - own;
+    if (lane == 0) {
+      ck->nc = nc;
+      ck->ok = bal ? 1 : 0;
+      ck->next = 0;
+      ck->use_mi = (PER && (exact_minimg || !p.fast_interior || wbal)) ? 1 : 0;
+    }
+    if (j == nc) ck->nown = oincl;
+  }
+  __syncthreads();
+  if (!ck->ok) return;
+  const int nc = ck->nc;
+  // ---- copy: one warp per column (coalesced), cell-row windows and the own-particle list
+  for (int j = w; j < nc + 2; j += TPB / 32) {
+    const int off = ck->off[j], la = ck->la[j], lt = ck->lt[j], lb = ck->lb[j];
+    const int src_t = ck->src_t[j], src_a = ck->src_a[j], src_b = ck->src_b[j];
+    const int tot = la + lt + lb;
+    int cj = cs - 1 + j;
+    if (cj < 0) cj = Cn - 1;
+    else if (cj >= Cn) cj = 0;
+    const int *tt = tstart + (size_t)(cj * p.tpc + tr) * (MAVI_TR + 1);
+    // staged start of tile row lane+1 (rows beyond the grid start where the tile ends)
+    const int tsl = tot ? __ldg(tt + lane) - src_t : 0, tsn = tot ? __ldg(tt + lane + 1) - src_t : 0;
+    const int rs = off + la + tsl;
+    const int up = __shfl_up_sync(0xffffffffu, rs, 1), dn = __shfl_down_sync(0xffffffffu, rs, 2);
+    const int end = off + tot;
+    const int wa = lane == 0 ? off : up;                                              // start of row lr-1
+    const int wb = (lane + 3 >= rows + 2) ? end : (lane <= 29 ? dn : off + la + lt);  // end of row lr+1 = start of row lr+2
+    ck->cwin[j][lane] = make_int2(wa, wb);
+    if (lane == 0) ck->gbase[j] = src_t - (off + la);
+    if (j >= 1 && j <= nc && lane < rows) {
+      const int qb = ck->ownoff[j];
+      for (int i = tsl; i < tsn; i++)
+        s_list[qb + i] = (unsigned int)(off + la + i) | ((unsigned int)j << 16) | ((unsigned int)(lane + 1) << 24);
+    }
+    // 16-byte asynchronous copies (LDGSTS): every piece of every column is in flight at once, no register staging
+    for (int i = lane; i < tot; i += 32) {
+      const int src = i < la ? src_a + i : (i < la + lt ? src_t + (i - la) : src_b + (i - la - lt));
+      __pipeline_memcpy_async(s_pos + off + i, pos + src, sizeof(double2));
+    }
+  }
+  __pipeline_commit();
+  __pipeline_wait_prior(0);
+  __syncthreads();
+}
+
+// pair force on the staged particle (staged column jj, tile row lr, staged index self) from the staged positions
+template <int DYN, bool MINIMG>
+__device__ __forceinline__ void chunk_walk(const DevParams &p, const Chunk2 *ck, const double2 *s_pos, int jj, int lr,
+                                           int self, double2 ri, double &fx, double &fy) {
+  const int2 w0 = ck->cwin[jj - 1][lr - 1], w1 = ck->cwin[jj][lr - 1], w2 = ck->cwin[jj + 1][lr - 1];
+  // byte offsets into s_pos; neighbours t < c1 -> column jj-1, c1 <= t < c2 -> own column before self,
+  // c2 <= t < c3 -> own column after self, c3 <= t -> column jj+1
+  const int c1 = (w0.y - w0.x) * 16;
+  const int c2 = c1 + (self - w1.x) * 16;
+  const int c3 = c2 + (w1.y - self - 1) * 16;
+  const int total = c3 + (w2.y - w2.x) * 16;
+  const int o0 = w0.x * 16;
+  const int d1 = w1.x * 16 - c1 - o0, d3 = w2.x * 16 - c3 - (w1.x * 16 - c1) - 16;
+  const char *base = reinterpret_cast<const char *>(s_pos) + o0;
+#pragma unroll 4
+  for (int t = 0; t < total; t += 16) {
+    const int o = t + (t >= c1 ? d1 : 0) + (t >= c2 ? 16 : 0) + (t >= c3 ? d3 : 0);
+    accumulate_pair<DYN, MINIMG>(p, ri, *reinterpret_cast<const double2 *>(base + o), fx, fy);
+  }
+}
+
+// Drives a force kernel: calls pre(k) before and body(k, r, cell, active, F) after the pair force F of every particle
+// slot of this block (F = 0 for inactive slots).
+template <int DYN, bool PER, typename Pre, typename Body>
+__device__ __forceinline__ void for_each_block_particle(const DevParams &p, const int *__restrict__ tstart,
+                                                        const double2 *__restrict__ pos, const int *__restrict__ cell,
+                                                        bool exact_minimg, Pre &&pre, Body &&body) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  Chunk2 *ck = reinterpret_cast<Chunk2 *>(dsm);
+  double2 *s_pos = reinterpret_cast<double2 *>(dsm + C2_BYTES);
+  unsigned int *s_list = reinterpret_cast<unsigned int *>(dsm + C2_BYTES + SPOS2_CAP * sizeof(double2));
+  const int lane = threadIdx.x & 31;
+  const int nblk_tiles = p.blk_per_row * p.tpc;
+  if ((int)blockIdx.x >= nblk_tiles) {  // inactive tail: no pair forces
+    const int i = ((int)blockIdx.x - nblk_tiles) * TPB + threadIdx.x;
+    if (i < p.n - p.n_active) {
+      const int k = p.tail_base + i;
+      pre(k);
+      body(k, pos[k], 0, false, make_double2(0.0, 0.0));
+    }
+    return;
+  }
+  const int tr = (int)blockIdx.x / p.blk_per_row;
+  const int c_begin = p.ord_col0 + ((int)blockIdx.x - tr * p.blk_per_row) * p.blk_cols;
+  const int c_end = min(c_begin + p.blk_cols, p.ord_col0 + p.ord_cols);
+  const int r0 = tr * MAVI_TR;
+  for (int cs = c_begin; cs < c_end;) {
+    chunk_stage<PER>(p, tstart, pos, tr, cs, c_end - cs, exact_minimg, ck, s_pos, s_list);
+    const int nc = ck->nc;
+    if (ck->ok) {
+      const int nown = ck->nown;
+      const bool mi = PER && ck->use_mi;
+      for (;;) {
+        int q0 = 0;
+        if (lane == 0) q0 = atomicAdd(&ck->next, 32);
+        q0 = __shfl_sync(0xffffffffu, q0, 0);
+        if (q0 >= nown) break;
+        const int q = q0 + lane;
+        if (q < nown) {
+          const unsigned int u = s_list[q];
+          const int self = u & 0xffffu, jj = (u >> 16) & 0xffu, lr = u >> 24;
+          const int k = self + ck->gbase[jj];
+          pre(k);
+          const double2 r = s_pos[self];
+          double fx = 0.0, fy = 0.0;
+          if (mi) chunk_walk<DYN, true>(p, ck, s_pos, jj, lr, self, r, fx, fy);
+          else chunk_walk<DYN, false>(p, ck, s_pos, jj, lr, self, r, fx, fy);
+          body(k, r, (cs - 1 + jj) * p.num_rows + r0 + lr - 1, true, make_double2(fx, fy));
+        }
+      }
+    } else {
+      // a single column too dense for the staging area: per-thread walk over the global arrays
+      const int b = ck->src_t[1], e = b + ck->lt[1];
+      for (int k = b + threadIdx.x; k < e; k += TPB) {
+        pre(k);
+        const double2 r = pos[k];
+        const int c = cell[k];
+        double fx = 0.0, fy = 0.0;
+        for_each_neighbor(p, tstart, c, k, [&](int j) { accumulate_pair<DYN, PER>(p, r, __ldg(pos + j), fx, fy); });
+        body(k, r, c, true, make_double2(fx, fy));
+      }
+    }
+    cs += nc;
+  }
+}
+
+static inline int grid2(const DevParams &p) { return p.blk_per_row * p.tpc + nblk(p.n - p.n_active); }
+
+template <int DYN, bool PER>
+__global__ void __launch_bounds__(TPB) k_force_only2(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
+                              const int *__restrict__ cell, const double2 *__restrict__ pos,
+                              double2 *__restrict__ force, int with_walls) {
+  for_each_block_particle<DYN, PER>(p, tstart, pos, cell, false, [](int) {},
+    [&](int k, double2 r, int, bool active, double2 F) {
+      if (active && with_walls && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
+      force[k] = F;
+    });
+}
+
+template <int DYN, bool PER>
+__global__ void __launch_bounds__(TPB) k_newton_a2(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
+                            const int *__restrict__ cell, const double2 *__restrict__ pos_in,
+                            const double2 *__restrict__ vel, double2 *__restrict__ pos_out, double2 *__restrict__ f1,
+                            int *__restrict__ flags) {
+  if (!flags[FLAG_RAN]) return;
+  for_each_block_particle<DYN, PER>(p, tstart, pos_in, cell, false, [&](int k) { prefetch_l1(vel + k); },
+    [&](int k, double2 r, int, bool active, double2 F) {
+      if (active && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
+      bool big;
+      pos_out[k] = verlet_drift(p, r, vel[k], F, big);
+      if (PER && big) flags[FLAG_BIGMOVE] = 1;
+      f1[k] = F;
+    });
+}
+
+template <int DYN, bool PER, bool CARRY>
+__global__ void __launch_bounds__(TPB) k_newton_b2(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
+                            const double2 *__restrict__ pos_in, double2 *__restrict__ vel, const double2 *f1,
+                            double2 *f2, double2 *f1_next, double2 *__restrict__ pos_next,
+                            int *__restrict__ fix_idx, double2 *__restrict__ fix_pos, const MoverSink ms) {
+  if (!ms.flags[FLAG_RAN]) return;
+  const bool exact = ms.flags[FLAG_BIGMOVE] != 0;
+  for_each_block_particle<DYN, PER>(p, tstart, pos_in, ms.cell, exact,
+    [&](int k) { prefetch_l1(vel + k); prefetch_l1(f1 + k); },
+    [&](int k, double2 r, int c, bool active, double2 F) {
+      double2 v = vel[k];
+      const double2 Fo = f1[k];
+      v.x = v.x + p.hdt * (F.x + Fo.x);
+      v.y = v.y + p.hdt * (F.y + Fo.y);
+      if (active) {
+        const double x0 = r.x, y0 = r.y;
+        apply_walls<true>(p, r.x, r.y, v.x, v.y, p.particle_radius);
+        const bool fixed = (r.x != x0 || r.y != y0);
+        if (fixed) {
+          int m = atomicAdd(&ms.flags[FLAG_NFIX], 1);
+          fix_idx[m] = k;
+          fix_pos[m] = r;
+        }
+        note_if_moved(p, ms, k, c, r.x, r.y, fixed);
+      }
+      vel[k] = v;
+      f2[k] = F;
+      if (CARRY) {
+        double2 Fn = F;
+        if (p.has_force_walls && active) wall_forces(p, r.x, r.y, Fn.x, Fn.y);
+        f1_next[k] = Fn;
+        bool big;
+        pos_next[k] = verlet_drift(p, r, v, Fn, big);
+        if (PER && big) ms.flags[FLAG_BIGMOVE_NEXT] = 1;
+      }
+    });
+}
+
+template <int DYN, bool PER>
+__global__ void __launch_bounds__(TPB) k_self_propelled2(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
+                                  const unsigned int *__restrict__ idflag, const double2 *__restrict__ pos_in,
+                                  double *__restrict__ ang, double2 *__restrict__ pos_out, double2 *__restrict__ force,
+                                  const double *__restrict__ noise, unsigned long long step, const MoverSink ms) {
+  if (!ms.flags[FLAG_RAN]) return;
+  for_each_block_particle<DYN, PER>(p, tstart, pos_in, ms.cell, false,
+    [&](int k) { prefetch_l1(ang + k); prefetch_l1(idflag + k); },
+    [&](int k, double2 r, int c, bool active, double2 F) {
+      const unsigned int id = idflag[k] & ~MAVI_INACTIVE_BIT;
+      if (active && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
+      force[k] = F;
+      if ((int)id < p.n_count) self_propelled_update<DYN>(p, r, F, ang, k, id, noise, step);
+      if (active) {
+        double vx = 0.0, vy = 0.0;
+        apply_walls<false>(p, r.x, r.y, vx, vy, p.particle_radius);
+        note_if_moved(p, ms, k, c, r.x, r.y);
+      }
+      pos_out[k] = r;
+    });
 }
 
 // ---- dispatch over (dynamics, periodic, all-pairs) ----------------------------------------------------------
@@ -1343,25 +1652,54 @@ static MoverSink mover_sink(const DevArrays &a) {
   return MoverSink{a.cell, a.tile_dirty, a.dirty_list, a.inbox_cnt, a.inbox, a.mv_src, a.flags, nullptr};
 }
 
+// all-pairs runs (chunks === nothing) keep the rank-mapped kernels with ALLP = true; chunked runs use the tile-block ones
+#define MAVI_DISPATCH_ALLP(DYNV, PERV, CALL) \
+  do {                                       \
+    if (PERV) { CALL(DYNV, true, true); } else { CALL(DYNV, false, true); } \
+  } while (0)
+
+#define MAVI_DISPATCH2(DYNV, PERV, CALL) \
+  do {                                   \
+    if (PERV) { CALL(DYNV, true); } else { CALL(DYNV, false); } \
+  } while (0)
+
 void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool with_wall_forces) {
   const bool allp = p.num_cells == 0;
+  if (!allp) {
+#define CALL2(D, P) MAVI_LAUNCH(c, (k_force_only2<D, P>), grid2(p), TPB, PASS2_SMEM, p, a.tstart, a.cell, a.pos[0], a.force, (int)with_wall_forces)
+    switch (p.dynamics) {
+      case MAVI_DYN_LJ: MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALL2); break;
+      case MAVI_DYN_HARMTRUNC: MAVI_DISPATCH2(MAVI_DYN_HARMTRUNC, p.periodic, CALL2); break;
+      case MAVI_DYN_SZABO: MAVI_DISPATCH2(MAVI_DYN_SZABO, p.periodic, CALL2); break;
+      case MAVI_DYN_RTP: MAVI_DISPATCH2(MAVI_DYN_RTP, p.periodic, CALL2); break;
+    }
+#undef CALL2
+    return;
+  }
 #define CALL(D, P, A) \
   MAVI_LAUNCH(c, (k_force_only<D, P, A>), nblk(p.n, RPB), TPB, (A ? 64 : PASS_SMEM), p, a.tstart, a.tile_prefix, a.cta_first, a.cell, a.idflag, a.pos[0], a.force, (int)with_wall_forces)
   switch (p.dynamics) {
-    case MAVI_DYN_LJ: MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, allp, CALL); break;
-    case MAVI_DYN_HARMTRUNC: MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, allp, CALL); break;
-    case MAVI_DYN_SZABO: MAVI_DISPATCH_DYN(MAVI_DYN_SZABO, p.periodic, allp, CALL); break;
-    case MAVI_DYN_RTP: MAVI_DISPATCH_DYN(MAVI_DYN_RTP, p.periodic, allp, CALL); break;
+    case MAVI_DYN_LJ: MAVI_DISPATCH_ALLP(MAVI_DYN_LJ, p.periodic, CALL); break;
+    case MAVI_DYN_HARMTRUNC: MAVI_DISPATCH_ALLP(MAVI_DYN_HARMTRUNC, p.periodic, CALL); break;
+    case MAVI_DYN_SZABO: MAVI_DISPATCH_ALLP(MAVI_DYN_SZABO, p.periodic, CALL); break;
+    case MAVI_DYN_RTP: MAVI_DISPATCH_ALLP(MAVI_DYN_RTP, p.periodic, CALL); break;
   }
 #undef CALL
 }
 
 void launch_newton_a(const LaunchCtx &c, const DevParams &p, const DevArrays &a) {
   const bool allp = p.num_cells == 0;
+  if (!allp) {
+#define CALL2(D, P) MAVI_LAUNCH(c, (k_newton_a2<D, P>), grid2(p), TPB, PASS2_SMEM, p, a.tstart, a.cell, a.pos[0], a.vel, a.pos[1], a.force_old, a.flags)
+    if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALL2);
+    else MAVI_DISPATCH2(MAVI_DYN_HARMTRUNC, p.periodic, CALL2);
+#undef CALL2
+    return;
+  }
 #define CALL(D, P, A) \
   MAVI_LAUNCH(c, (k_newton_a<D, P, A>), nblk(p.n, RPB), TPB, (A ? 64 : PASS_SMEM), p, a.tstart, a.tile_prefix, a.cta_first, a.cell, a.idflag, a.pos[0], a.vel, a.pos[1], a.force_old, a.flags)
-  if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, allp, CALL);
-  else MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, allp, CALL);
+  if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_ALLP(MAVI_DYN_LJ, p.periodic, CALL);
+  else MAVI_DISPATCH_ALLP(MAVI_DYN_HARMTRUNC, p.periodic, CALL);
 #undef CALL
 }
 
@@ -1373,18 +1711,26 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p, const DevArrays &a,
 #define ARGS p, a.tstart, a.tile_prefix, a.cta_first, a.idflag, a.pos[1], a.vel, a.force_old, a.force, a.force_old, a.pos[0], a.fix_idx, a.fix_pos, ms
 #define CALL(D, P, A) \
   MAVI_LAUNCH(c, (k_newton_b<D, P, A, false>), nblk(p.n, RPB), TPB, (A ? 64 : PASS_SMEM), ARGS)
-#define CALLC(D, P, A) \
-  MAVI_LAUNCH(c, (k_newton_b<D, P, false, true>), nblk(p.n, RPB), TPB, PASS_SMEM, ARGS)
-  if (carry && !allp) {
-    ms.chg = a.chg;
-    if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, false, CALLC);
-    else MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, false, CALLC);
+  if (!allp) {
+#define ARGS2 p, a.tstart, a.pos[1], a.vel, a.force_old, a.force, a.force_old, a.pos[0], a.fix_idx, a.fix_pos, ms
+#define CALL2(D, P) MAVI_LAUNCH(c, (k_newton_b2<D, P, false>), grid2(p), TPB, PASS2_SMEM, ARGS2)
+#define CALL2C(D, P) MAVI_LAUNCH(c, (k_newton_b2<D, P, true>), grid2(p), TPB, PASS2_SMEM, ARGS2)
+    if (carry) {
+      ms.chg = a.chg;
+      if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALL2C);
+      else MAVI_DISPATCH2(MAVI_DYN_HARMTRUNC, p.periodic, CALL2C);
+    } else {
+      if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALL2);
+      else MAVI_DISPATCH2(MAVI_DYN_HARMTRUNC, p.periodic, CALL2);
+    }
+#undef CALL2
+#undef CALL2C
+#undef ARGS2
   } else {
-    if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, allp, CALL);
-    else MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, allp, CALL);
+    if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_ALLP(MAVI_DYN_LJ, p.periodic, CALL);
+    else MAVI_DISPATCH_ALLP(MAVI_DYN_HARMTRUNC, p.periodic, CALL);
   }
 #undef CALL
-#undef CALLC
 #undef ARGS
   MAVI_LAUNCH(c, k_apply_pos_fixes, 64, TPB, 0, a.flags, a.fix_idx, a.fix_pos, a.pos[1]);
 }
@@ -1419,10 +1765,18 @@ void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArra
                            unsigned long long step) {
   const bool allp = p.num_cells == 0;
   const MoverSink ms = mover_sink(a);
+  if (!allp) {
+#define CALL2(D, P) MAVI_LAUNCH(c, (k_self_propelled2<D, P>), grid2(p), TPB, PASS2_SMEM, p, a.tstart, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms)
+    if (p.dynamics == MAVI_DYN_SZABO) MAVI_DISPATCH2(MAVI_DYN_SZABO, p.periodic, CALL2);
+    else MAVI_DISPATCH2(MAVI_DYN_RTP, p.periodic, CALL2);
+#undef CALL2
+    MAVI_LAUNCH(c, k_apply_pos_fixes, 1, 32, 0, a.flags, a.fix_idx, a.fix_pos, a.pos[1]);  // no fix-ups here: step counter only
+    return;
+  }
 #define CALL(D, P, A) \
   MAVI_LAUNCH(c, (k_self_propelled<D, P, A>), nblk(p.n, RPB), TPB, (A ? 64 : PASS_SMEM), p, a.tstart, a.tile_prefix, a.cta_first, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms)
-  if (p.dynamics == MAVI_DYN_SZABO) MAVI_DISPATCH_DYN(MAVI_DYN_SZABO, p.periodic, allp, CALL);
-  else MAVI_DISPATCH_DYN(MAVI_DYN_RTP, p.periodic, allp, CALL);
+  if (p.dynamics == MAVI_DYN_SZABO) MAVI_DISPATCH_ALLP(MAVI_DYN_SZABO, p.periodic, CALL);
+  else MAVI_DISPATCH_ALLP(MAVI_DYN_RTP, p.periodic, CALL);
 #undef CALL
   MAVI_LAUNCH(c, k_apply_pos_fixes, 1, 32, 0, a.flags, a.fix_idx, a.fix_pos, a.pos[1]);  // no fix-ups here: step counter only
 }
