@@ -135,6 +135,8 @@ static int validate_and_lower(Handle *h, const MaviParams *mp) {
   p.periodic = (m0.wall == MAVI_WALL_PERIODIC && m0.geom == MAVI_GEOM_RECT) ? 1 : 0;
   p.size[0] = m0.rect_len; p.size[1] = m0.rect_h;
   p.half[0] = m0.rect_len / 2; p.half[1] = m0.rect_h / 2;
+  p.wall_fast = (mp->n_spaces == 1 && p.periodic) ? 1 : 0;
+  p.wall_ctr[0] = m0.rect_bl[0] + p.half[0]; p.wall_ctr[1] = m0.rect_bl[1] + p.half[1];
 
   // Chunks ctor, src/chunks.jl:26-40
   if (mp->num_cols > 0) {

@@ -81,6 +81,8 @@ struct DevParams {
   double dt, term, hdt;            // dt, dt^2/2, dt/2  (src/integration.jl:420-430)
   int n_spaces;
   int has_force_walls;
+  int wall_fast;             // 1: the space is ONE periodic rectangle (walls! fast path)
+  double wall_ctr[2];        // its centre bl + size/2
   DevSpace spaces[MAVI_MAX_SPACES];
   int rng_mode;
   unsigned long long seed;

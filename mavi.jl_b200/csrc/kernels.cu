@@ -3,6 +3,8 @@
 // loads), not a dense contraction.  Reference citations are relative to /root/reference/.
 #include <cuda_pipeline.h>
 
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "walls.cuh"
 
@@ -1342,7 +1344,7 @@ __global__ void __launch_bounds__(TPB) k_self_propelled(const __grid_constant__ 
 //   cwin[j][lr]  = (first staged index of cell row lr-1, end of cell row lr+1) of staged column j  -> the three
 //                  neighbour runs of a particle are three LDS.64 away,
 //   list[q]      = staged index | column << 16 | row << 24 of the q-th OWN particle of the block,
-// and then warps pull 32 own particles at a time from a shared counter.  Columns are staged in chunks of as many as
+// and then every thread takes own particles q = tid, tid + 256, ...  Columns are staged in chunks of as many as
 // fit, so dense regions only cost more chunks; a single column that does not fit falls back to a per-thread walk of
 // the global arrays.  Trailing blocks handle the inactive tail (slots of masked particles).
 // =========================================================================================================
@@ -1494,7 +1496,6 @@ __device__ __forceinline__ void for_each_block_particle(const DevParams &p, cons
   Chunk2 *ck = reinterpret_cast<Chunk2 *>(dsm);
   double2 *s_pos = reinterpret_cast<double2 *>(dsm + C2_BYTES);
   unsigned int *s_list = reinterpret_cast<unsigned int *>(dsm + C2_BYTES + SPOS2_CAP * sizeof(double2));
-  const int lane = threadIdx.x & 31;
   const int nblk_tiles = p.blk_per_row * p.tpc;
   if ((int)blockIdx.x >= nblk_tiles) {  // inactive tail: no pair forces
     const int i = ((int)blockIdx.x - nblk_tiles) * TPB + threadIdx.x;
@@ -1515,23 +1516,17 @@ __device__ __forceinline__ void for_each_block_particle(const DevParams &p, cons
     if (ck->ok) {
       const int nown = ck->nown;
       const bool mi = PER && ck->use_mi;
-      for (;;) {
-        int q0 = 0;
-        if (lane == 0) q0 = atomicAdd(&ck->next, 32);
-        q0 = __shfl_sync(0xffffffffu, q0, 0);
-        if (q0 >= nown) break;
-        const int q = q0 + lane;
-        if (q < nown) {
-          const unsigned int u = s_list[q];
-          const int self = u & 0xffffu, jj = (u >> 16) & 0xffu, lr = u >> 24;
-          const int k = self + ck->gbase[jj];
-          pre(k);
-          const double2 r = s_pos[self];
-          double fx = 0.0, fy = 0.0;
-          if (mi) chunk_walk<DYN, true>(p, ck, s_pos, jj, lr, self, r, fx, fy);
-          else chunk_walk<DYN, false>(p, ck, s_pos, jj, lr, self, r, fx, fy);
-          body(k, r, (cs - 1 + jj) * p.num_rows + r0 + lr - 1, true, make_double2(fx, fy));
-        }
+      // blk_cols is chosen so that a block holds about 1000 own particles: the last round of 256 is nearly full
+      for (int q = threadIdx.x; q < nown; q += TPB) {
+        const unsigned int u = s_list[q];
+        const int self = u & 0xffffu, jj = (u >> 16) & 0xffu, lr = u >> 24;
+        const int k = self + ck->gbase[jj];
+        pre(k);
+        const double2 r = s_pos[self];
+        double fx = 0.0, fy = 0.0;
+        if (mi) chunk_walk<DYN, true>(p, ck, s_pos, jj, lr, self, r, fx, fy);
+        else chunk_walk<DYN, false>(p, ck, s_pos, jj, lr, self, r, fx, fy);
+        body(k, r, (cs - 1 + jj) * p.num_rows + r0 + lr - 1, true, make_double2(fx, fy));
       }
     } else {
       // a single column too dense for the staging area: per-thread walk over the global arrays
@@ -1578,8 +1573,8 @@ __global__ void __launch_bounds__(TPB) k_newton_a2(const __grid_constant__ DevPa
     });
 }
 
-template <int DYN, bool PER, bool CARRY>
-__global__ void __launch_bounds__(TPB) k_newton_b2(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
+template <int DYN, bool PER, bool CARRY, int MINB>
+__global__ void __launch_bounds__(TPB, MINB) k_newton_b2(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
                             const double2 *__restrict__ pos_in, double2 *__restrict__ vel, const double2 *f1,
                             double2 *f2, double2 *f1_next, double2 *__restrict__ pos_next,
                             int *__restrict__ fix_idx, double2 *__restrict__ fix_pos, const MoverSink ms) {
@@ -1713,11 +1708,15 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p, const DevArrays &a,
   MAVI_LAUNCH(c, (k_newton_b<D, P, A, false>), nblk(p.n, RPB), TPB, (A ? 64 : PASS_SMEM), ARGS)
   if (!allp) {
 #define ARGS2 p, a.tstart, a.pos[1], a.vel, a.force_old, a.force, a.force_old, a.pos[0], a.fix_idx, a.fix_pos, ms
-#define CALL2(D, P) MAVI_LAUNCH(c, (k_newton_b2<D, P, false>), grid2(p), TPB, PASS2_SMEM, ARGS2)
-#define CALL2C(D, P) MAVI_LAUNCH(c, (k_newton_b2<D, P, true>), grid2(p), TPB, PASS2_SMEM, ARGS2)
+#define CALL2(D, P) MAVI_LAUNCH(c, (k_newton_b2<D, P, false, 4>), grid2(p), TPB, PASS2_SMEM, ARGS2)
+#define CALL2C(D, P) MAVI_LAUNCH(c, (k_newton_b2<D, P, true, 4>), grid2(p), TPB, PASS2_SMEM, ARGS2)
+    static const int minb = getenv("MAVI_K_MINB") ? atoi(getenv("MAVI_K_MINB")) : 4;  // tuning knob (A/B runs)
     if (carry) {
       ms.chg = a.chg;
-      if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALL2C);
+      if (p.dynamics == MAVI_DYN_LJ && p.periodic && minb == 3) MAVI_LAUNCH(c, (k_newton_b2<MAVI_DYN_LJ, true, true, 3>), grid2(p), TPB, PASS2_SMEM, ARGS2);
+      else if (p.dynamics == MAVI_DYN_LJ && p.periodic && minb == 5) MAVI_LAUNCH(c, (k_newton_b2<MAVI_DYN_LJ, true, true, 5>), grid2(p), TPB, PASS2_SMEM, ARGS2);
+      else if (p.dynamics == MAVI_DYN_LJ && p.periodic && minb == 6) MAVI_LAUNCH(c, (k_newton_b2<MAVI_DYN_LJ, true, true, 6>), grid2(p), TPB, PASS2_SMEM, ARGS2);
+      else if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALL2C);
       else MAVI_DISPATCH2(MAVI_DYN_HARMTRUNC, p.periodic, CALL2C);
     } else {
       if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALL2);

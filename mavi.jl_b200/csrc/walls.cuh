@@ -72,6 +72,14 @@ __device__ __forceinline__ void wall_forces(const DevParams &p, double x, double
 // vx/vy are only meaningful for SecondLawState (HAS_VEL); pr is the particle's radius.
 template <bool HAS_VEL>
 __device__ __forceinline__ void apply_walls(const DevParams &p, double &x, double &y, double &vx, double &vy, double pr) {
+  if (p.wall_fast == 1) {
+    // the common space: ONE periodic rectangle (:309-324); same arithmetic as the generic branch below with the
+    // centre bl + size/2 and size/2 taken from the parameter block ((size/2)*2 == size exactly)
+    const double dx = x - p.wall_ctr[0], dy = y - p.wall_ctr[1];
+    if (fabs(dx) > p.half[0]) x = x - sign_d(dx) * p.size[0];
+    if (fabs(dy) > p.half[1]) y = y - sign_d(dy) * p.size[1];
+    return;
+  }
   for (int k = 0; k < p.n_spaces; k++) {
     const DevSpace &sp = p.spaces[k];
     if (sp.wall == MAVI_WALL_RIGID && sp.geom == MAVI_GEOM_RECT) {
