@@ -486,6 +486,8 @@ int Handle::run_steps(long long nsteps, const double *noise_dev, size_t stride) 
       st = p.slab ? slab_step_once(this, nz) : rings_step(this, nz);
       if (st) return st;
       done_total += 1;
+      // slab steps are enqueued without host synchronisation; counts / overflow word every SYNC_EVERY steps and at the end
+      if (p.slab && (done_total == nsteps || done_total % SYNC_EVERY == 0) && (st = slab_sync_counts(this))) return st;
       continue;
     }
     const int batch = (int)((nsteps - done_total) < SYNC_EVERY ? (nsteps - done_total) : SYNC_EVERY);

@@ -55,7 +55,8 @@ struct Handle {
   size_t noise_cap = 0;
   char err[512] = {0};
 
-  LaunchCtx ctx() { return LaunchCtx{stream, &launches}; }
+  bool maps_valid = false;
+  LaunchCtx ctx() { return LaunchCtx{stream, &launches, &maps_valid}; }
   void set_error(const char *fmt, ...);
   int check_device_flags();
   int pending_out_of_grid();
@@ -76,6 +77,7 @@ void slab_destroy(Handle *h);
 int slab_after_build(Handle *h);
 int slab_allreduce_max(Handle *h, int *value);
 int slab_step_once(Handle *h, const double *noise_dev);
+int slab_sync_counts(Handle *h);
 
 // rings.cu
 int rings_lower(Handle *h, const MaviParams *mp);

@@ -300,6 +300,11 @@ void refresh_rank_maps(const LaunchCtx &c, const DevParams &p, const DevArrays &
   MAVI_LAUNCH(c, k_tile_counts, nblk(p.nt_ord + 1), TPB, 0, p, a.tstart, tmp);
   launch_exclusive_scan(c, tmp, a.tile_prefix, a.scan_partials, p.nt_ord + 1);
   MAVI_LAUNCH(c, k_cta_first, nblk(p.nt_ord), TPB, 0, p, a.tile_prefix, a.cta_first);
+  if (c.maps_valid) *c.maps_valid = true;
+}
+
+void ensure_rank_maps(const LaunchCtx &c, const DevParams &p, const DevArrays &a) {
+  if (!c.maps_valid || !*c.maps_valid) refresh_rank_maps(c, p, a);
 }
 
 void launch_build_tiles(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel) {
@@ -360,6 +365,7 @@ __global__ void k_compact(const __grid_constant__ DevParams p, const int *__rest
 }
 
 void launch_compact_to_staging(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel) {
+  ensure_rank_maps(c, p, a);
   MAVI_LAUNCH(c, k_compact, nblk(p.n), TPB, 0, p, a.tile_prefix, a.cta_first, a.pos[0], second_is_vel ? a.vel : nullptr,
               second_is_vel ? nullptr : a.ang, a.force, a.idflag, a.st_pos, second_is_vel ? a.st_vel : nullptr,
               second_is_vel ? nullptr : a.st_ang, a.st_force, a.st_id);
@@ -523,7 +529,8 @@ void launch_repair_tiles(const LaunchCtx &c, const DevParams &p, const DevArrays
   MAVI_LAUNCH(c, (k_repair_tiles<true>), grid, REPAIR_WARPS * 32, smem, p, a.flags, a.dirty_list, a.tile_dirty, a.inbox_cnt,
               a.inbox, a.tstart, a.pos[0], vel, ang, a.force, a.idflag, a.cell, a.mv_pos, a.mv_second, a.mv_force, a.mv_id,
               a.mv_cell);
-  refresh_rank_maps(c, p, a);
+  if (c.maps_valid) *c.maps_valid = false;  // tile populations changed; nothing in the step loop needs the rank maps
+  else refresh_rank_maps(c, p, a);
 }
 
 // =========================================================================================================
@@ -1827,6 +1834,7 @@ __global__ void k_kinetic(const __grid_constant__ DevParams p, const int *__rest
 void launch_kinetic_energy(const LaunchCtx &c, const DevParams &p, const DevArrays &a, double *out) {
   int nb = min(nblk(p.n, RED_TPB), RED_MAX_BLOCKS);
   if (nb < 1) nb = 1;
+  if (p.num_cells > 0) ensure_rank_maps(c, p, a);
   MAVI_LAUNCH(c, k_kinetic, nb, RED_TPB, 0, p, a.tile_prefix, a.cta_first, a.vel, a.reduce_buf);
   MAVI_LAUNCH(c, k_reduce_final, 1, RED_TPB, 0, a.reduce_buf, nb, 0.5, out);
 }
@@ -1889,6 +1897,7 @@ void launch_potential_energy(const LaunchCtx &c, const DevParams &p, const DevAr
     else MAVI_LAUNCH(c, (k_potential_exact<false>), nb, RED_TPB, 0, p, a.st_id, a.st_pos, a.reduce_buf);
     MAVI_LAUNCH(c, k_reduce_final, 1, RED_TPB, 0, a.reduce_buf, nb, eps4, out);
   } else {
+    ensure_rank_maps(c, p, a);
     if (p.periodic) MAVI_LAUNCH(c, (k_potential_stencil<true>), nb, RED_TPB, 0, p, a.tstart, a.tile_prefix, a.cta_first, a.cell, a.idflag, a.pos[0], a.reduce_buf);
     else MAVI_LAUNCH(c, (k_potential_stencil<false>), nb, RED_TPB, 0, p, a.tstart, a.tile_prefix, a.cta_first, a.cell, a.idflag, a.pos[0], a.reduce_buf);
     MAVI_LAUNCH(c, k_reduce_final, 1, RED_TPB, 0, a.reduce_buf, nb, 0.5 * eps4, out);
@@ -1944,12 +1953,15 @@ __global__ void k_ids_in_cell_order(const __grid_constant__ DevParams p, const i
 }
 
 void launch_unpermute2(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const double2 *in, double2 *out) {
+  if (p.num_cells > 0) ensure_rank_maps(c, p, a);
   MAVI_LAUNCH(c, k_unpermute2, nblk(p.n), TPB, 0, p, a.tile_prefix, a.cta_first, a.idflag, in, out);
 }
 void launch_unpermute1(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const double *in, double *out) {
+  if (p.num_cells > 0) ensure_rank_maps(c, p, a);
   MAVI_LAUNCH(c, k_unpermute1, nblk(p.n), TPB, 0, p, a.tile_prefix, a.cta_first, a.idflag, in, out);
 }
 void launch_unpermute_cells(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int *out) {
+  if (p.num_cells > 0) ensure_rank_maps(c, p, a);
   MAVI_LAUNCH(c, k_unpermute_cells, nblk(p.n), TPB, 0, p, a.tile_prefix, a.cta_first, a.idflag, a.cell, out);
 }
 void launch_cell_counts(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int *out) {

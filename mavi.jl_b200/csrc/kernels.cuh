@@ -56,6 +56,7 @@ struct DevArrays {
 struct LaunchCtx {
   cudaStream_t stream;
   long long *launches;  // incremented per kernel launch
+  bool *maps_valid;     // rank maps (tile_prefix / cta_first) match tstart; the step loop only invalidates them
 };
 
 // full build of the tile layout from the staging arrays (upload, mavi_bin, overflow fallback)
@@ -71,6 +72,8 @@ void launch_init_staging_ids(const LaunchCtx &c, int n, const unsigned char *mas
 void launch_repair_tiles(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel);
 void launch_exclusive_scan(const LaunchCtx &c, const int *in, int *out, int *partials, int n);
 void refresh_rank_maps(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
+// the rank -> slot maps are only needed by downloads, reductions and rebuilds: refreshed on demand
+void ensure_rank_maps(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
 
 // force + integrate passes
 void launch_step_begin(const LaunchCtx &c, const DevArrays &a);

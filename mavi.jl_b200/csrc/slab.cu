@@ -343,12 +343,27 @@ static void clear_halo_columns(Handle *h) {
 
 // number of owned particles after a (re)build / migration -> p.n, p.n_active
 static int slab_refresh_count(Handle *h) {
+  ensure_rank_maps(h->ctx(), h->p, h->a);
   k_owned_count<<<1, 1, 0, h->stream>>>(h->p, h->a.tile_prefix, h->a.flags);
   h->launches++;
   int st = h->check_device_flags();
   if (st) return st;
   h->p.n = h->p.n_active = h->flags_host[FLAG_TAIL];
   h->p.n_count = h->slab.n_global;  // get_num_total_particles of the GLOBAL state (update_szabo!/update_rtp! loop 1:count)
+  return MAVI_OK;
+}
+
+// Owned count + latched overflow word; called at the end of every mavi_step call (and every few steps inside it).
+int slab_sync_counts(Handle *h) {
+  const DevParams &p = h->p;
+  int st = slab_refresh_count(h);
+  if (st) return st;
+  if (h->flags_host[FLAG_OVERFLOW]) {
+    h->set_error("slab mode overflow (bits %d: 1 = tile capacity %d < %d, 2 = inbox capacity %d < %d at tile %d (column %d of %d), 4 = mover list %d, 8 = changed-cell list)",
+                 h->flags_host[FLAG_OVERFLOW], p.cap, h->flags_host[FLAG_MAXCOUNT], p.inbox_cap, h->flags_host[FLAG_MAXINBOX],
+                 h->flags_host[FLAG_MAXINBOX_TILE], h->flags_host[FLAG_MAXINBOX_TILE] / p.tpc, p.num_cols, p.mv_cap);
+    return MAVI_ERR_CAPACITY;
+  }
   return MAVI_OK;
 }
 
@@ -390,13 +405,7 @@ int slab_step_once(Handle *h, const double *noise_dev) {
   if ((st = slab_migrate(h, carry))) return st;
   h->time += p.dt;
   h->num_steps += 1;
-  if ((st = slab_refresh_count(h))) return st;
-  if (h->flags_host[FLAG_OVERFLOW]) {
-    h->set_error("slab mode overflow (bits %d: 1 = tile capacity %d < %d, 2 = inbox capacity %d < %d at tile %d (column %d of %d), 4 = mover list %d, 8 = changed-cell list)",
-                 h->flags_host[FLAG_OVERFLOW], p.cap, h->flags_host[FLAG_MAXCOUNT], p.inbox_cap, h->flags_host[FLAG_MAXINBOX],
-                 h->flags_host[FLAG_MAXINBOX_TILE], h->flags_host[FLAG_MAXINBOX_TILE] / p.tpc, p.num_cols, p.mv_cap);
-    return MAVI_ERR_CAPACITY;
-  }
+  // (no host synchronisation here: the owned count and the overflow word are read by slab_sync_counts)
   if ((st = slab_halo_exchange(h, a.pos[0], true))) return st;
   if (carry) {  // needs the fresh halo (positions + layout)
     launch_carry_recompute(c, p, a);
