@@ -255,6 +255,13 @@ static int allocate(Handle *h) {
   if ((st = dev_alloc(h, &a.fix_pos, n))) return st;
   if ((st = dev_alloc(h, &a.reduce_buf, 4096))) return st;
   if ((st = dev_alloc(h, &a.cta_first, n / RPB + 2))) return st;
+  if (p.slab) {  // emigrant / immigrant records (slab.cu)
+    a.em_cap = p.num_rows / 2 > 1024 ? p.num_rows / 2 : 1024;
+    for (int d = 0; d < 2; d++) {
+      if ((st = dev_alloc(h, &a.em_send[d], (size_t)a.em_cap))) return st;
+      if ((st = dev_alloc(h, &a.em_recv[d], (size_t)a.em_cap))) return st;
+    }
+  }
   CUDA_TRY(h, cudaMallocHost((void **)&h->flags_host, FLAG_COUNT * sizeof(int)));
   CUDA_TRY(h, cudaMemsetAsync(a.flags, 0, FLAG_COUNT * sizeof(int), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(a.count, 0, nc * sizeof(int), h->stream));
@@ -577,11 +584,6 @@ int32_t mavi_destroy(MaviHandle *hh) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   slab_destroy(h);
-  for (int d = 0; d < 2; d++) {
-    void *mig[] = {h->slab.mig_pos[d], h->slab.mig_second[d], h->slab.mig_force[d], h->slab.mig_id[d], h->slab.mig_ts[d]};
-    for (void *q : mig)
-      if (q) cudaFree(q);
-  }
   for (void *ptr : h->allocs)
     if (ptr) cudaFree(ptr);
   if (h->flags_host) cudaFreeHost(h->flags_host);

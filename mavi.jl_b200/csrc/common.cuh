@@ -103,6 +103,8 @@ enum {
   FLAG_SCRATCH = 12,
   // force carry (see k_newton_b): cells whose membership changed in this step, and the big-drift guard of the NEXT step
   FLAG_NCHG = 16, FLAG_BIGMOVE_NEXT = 17,
+  // slab mode: emigrants of this step towards the left / right neighbour, and the counts received from them
+  FLAG_NEM0 = 18, FLAG_NEM1 = 19, FLAG_NEMR0 = 20, FLAG_NEMR1 = 21,
   FLAG_COUNT = 24
 };
 
@@ -114,6 +116,13 @@ __device__ __forceinline__ bool step_poisoned(const int *flags) {
 }
 
 #define MAVI_TR 32  // cell rows per tile
+
+// slab mode: record of a particle that leaves this rank's columns (written by the integrate kernel, shipped as is)
+struct EmRec {
+  double2 pos, second, force;
+  unsigned int idflag;
+  int pad[3];
+};
 
 // index of (tile, local row) in tstart[]: tstart[tile*(MAVI_TR+1) + lr] = first slot of that cell's particles,
 // entry MAVI_TR = end of the tile's particles.

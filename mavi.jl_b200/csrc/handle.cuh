@@ -22,10 +22,6 @@ struct SlabState {
   int m = 0, m_left = 0, m_right = 0, col_lo = 0;
   int n_global = 0;
   struct ncclComm *comm = nullptr;
-  double2 *mig_pos[2] = {nullptr, nullptr}, *mig_second[2] = {nullptr, nullptr}, *mig_force[2] = {nullptr, nullptr};
-  unsigned int *mig_id[2] = {nullptr, nullptr};
-  int *mig_ts[2] = {nullptr, nullptr};
-  size_t mig_cs = 0;
 };
 
 struct Handle {

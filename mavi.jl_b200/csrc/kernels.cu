@@ -946,6 +946,10 @@ __device__ __forceinline__ void force_prologue(const DevParams &p, const int *__
 struct MoverSink {
   int *cell, *tile_dirty, *dirty_list, *inbox_cnt, *inbox, *mv_src, *flags;
   int *chg;  // changed-cell list of the force carry (nullptr: not recorded)
+  // slab mode: emigrant records towards the left [0] / right [1] neighbour
+  EmRec *em[2];
+  int em_cap;
+  const unsigned int *idflag;
 };
 
 __device__ __forceinline__ void mark_dirty(const MoverSink &ms, int t) {
@@ -966,8 +970,11 @@ __device__ __forceinline__ void note_changed_cells(const DevParams &p, const Mov
 }
 
 // `fixed`: walls! moved the particle (periodic wrap, slippery projection) after the pair pass read its position.
+// second_of(): the particle's second state record (velocity / angle) after this step — only evaluated for a particle
+// that leaves the rank (slab mode), together with `force`, to fill its emigrant record.
+template <typename SecondF>
 __device__ __forceinline__ void note_if_moved(const DevParams &p, const MoverSink &ms, int k, int c_old, double x,
-                                              double y, bool fixed = false) {
+                                              double y, bool fixed, double2 force, SecondF &&second_of) {
   if (still_in_cell(p, x, y, c_old)) {
     if (fixed) note_changed_cells(p, ms, c_old, c_old);
     return;
@@ -985,6 +992,23 @@ __device__ __forceinline__ void note_if_moved(const DevParams &p, const MoverSin
   ms.cell[k] = c_new;
   const int t_old = tile_of_cell(p, c_old), t_new = tile_of_cell(p, c_new);
   mark_dirty(ms, t_old);
+  if (p.slab) {
+    const int lc = div_rows(p, c_new);
+    if (lc == 0 || lc == p.num_cols - 1) {  // crossed into a halo column: goes to the neighbour rank, not into a tile
+      const int d = lc == 0 ? 0 : 1;
+      const int i = atomicAdd(&ms.flags[FLAG_NEM0 + d], 1);
+      if (i < ms.em_cap) {
+        EmRec &e = ms.em[d][i];
+        e.pos = make_double2(x, y);
+        e.second = second_of();
+        e.force = force;
+        e.idflag = ms.idflag[k];
+      } else {
+        atomicOr(&ms.flags[FLAG_OVERFLOW], 16);
+      }
+      return;
+    }
+  }
   if (t_new != t_old) {
     mark_dirty(ms, t_new);
     const int m = atomicAdd(&ms.flags[FLAG_NMV], 1);
@@ -1116,7 +1140,7 @@ __global__ void __launch_bounds__(TPB) k_newton_b(const __grid_constant__ DevPar
         fix_idx[m] = k;
         fix_pos[m] = r;
       }
-      if (!ALLP) note_if_moved(p, ms, k, c, r.x, r.y, fixed);
+      if (!ALLP) note_if_moved(p, ms, k, c, r.x, r.y, fixed, F, [&] { return v; });
     }
     vel[k] = v;
     f2[k] = F;
@@ -1258,6 +1282,8 @@ __global__ void k_step_begin(int *__restrict__ flags) {
     flags[FLAG_BIGMOVE] = flags[FLAG_BIGMOVE_NEXT];  // raised by the carried drift of the previous step
     flags[FLAG_BIGMOVE_NEXT] = 0;
     flags[FLAG_NCHG] = 0;
+    flags[FLAG_NEM0] = 0;
+    flags[FLAG_NEM1] = 0;
     flags[FLAG_NFIX] = 0;
     flags[FLAG_NMV] = 0;
     flags[FLAG_RAN] = run;
@@ -1338,7 +1364,7 @@ __global__ void __launch_bounds__(TPB) k_self_propelled(const __grid_constant__ 
     if (active) {
       double vx = 0.0, vy = 0.0;
       apply_walls<false>(p, r.x, r.y, vx, vy, p.particle_radius);
-      if (!ALLP) note_if_moved(p, ms, k, c, r.x, r.y);
+      if (!ALLP) note_if_moved(p, ms, k, c, r.x, r.y, false, F, [&] { return make_double2(ang[k], 0.0); });
     }
     pos_out[k] = r;
   }
@@ -1603,7 +1629,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_newton_b2(const __grid_constant__
           fix_idx[m] = k;
           fix_pos[m] = r;
         }
-        note_if_moved(p, ms, k, c, r.x, r.y, fixed);
+        note_if_moved(p, ms, k, c, r.x, r.y, fixed, F, [&] { return v; });
       }
       vel[k] = v;
       f2[k] = F;
@@ -1634,7 +1660,7 @@ __global__ void __launch_bounds__(TPB) k_self_propelled2(const __grid_constant__
       if (active) {
         double vx = 0.0, vy = 0.0;
         apply_walls<false>(p, r.x, r.y, vx, vy, p.particle_radius);
-        note_if_moved(p, ms, k, c, r.x, r.y);
+        note_if_moved(p, ms, k, c, r.x, r.y, false, F, [&] { return make_double2(ang[k], 0.0); });
       }
       pos_out[k] = r;
     });
@@ -1651,7 +1677,7 @@ __global__ void __launch_bounds__(TPB) k_self_propelled2(const __grid_constant__
   } while (0)
 
 static MoverSink mover_sink(const DevArrays &a) {
-  return MoverSink{a.cell, a.tile_dirty, a.dirty_list, a.inbox_cnt, a.inbox, a.mv_src, a.flags, nullptr};
+  return MoverSink{a.cell, a.tile_dirty, a.dirty_list, a.inbox_cnt, a.inbox, a.mv_src, a.flags, nullptr, {a.em_send[0], a.em_send[1]}, a.em_cap, a.idflag};
 }
 
 // all-pairs runs (chunks === nothing) keep the rank-mapped kernels with ALLP = true; chunked runs use the tile-block ones

@@ -46,6 +46,9 @@ struct DevArrays {
   unsigned int *mv_id;
   int *mv_cell;
   int *chg;             // [chg_cap] cells whose membership changed in this step (force carry)
+  // slab mode: emigrant records to / immigrant records from the left [0] and right [1] neighbour
+  EmRec *em_send[2], *em_recv[2];
+  int em_cap;
   // control
   int *flags;           // see FLAG_* in common.cuh
   int *fix_idx;         // sparse list of slots whose position walls! changed in pass B

@@ -181,24 +181,19 @@ __global__ void k_clear_column(const __grid_constant__ DevParams p, int *__restr
   tstart[(size_t)lcol * p.tpc * TR1 + i] = (lcol * p.tpc + tr) * p.cap;
 }
 
-// Immigrants: every particle of a received emigrant column (sender's halo tiles) is queued as an inter-tile mover
-// of THIS rank: record -> mover list, destination tile inbox, tile marked dirty.  The incremental repair then merges
-// it exactly like a local mover.
-__global__ void k_ingest(const __grid_constant__ DevParams p, const int *__restrict__ rts /* received tstart rows */,
-                         int sender_base, const double2 *__restrict__ rpos, const double2 *__restrict__ rsecond2,
-                         const double *__restrict__ rsecond1, const double2 *__restrict__ rforce,
-                         const unsigned int *__restrict__ rid, double2 *__restrict__ mv_pos,
-                         double2 *__restrict__ mv_second, double2 *__restrict__ mv_force,
-                         unsigned int *__restrict__ mv_id, int *__restrict__ mv_cell, int *__restrict__ mv_src,
-                         int *__restrict__ tile_dirty, int *__restrict__ dirty_list, int *__restrict__ inbox_cnt,
-                         int *__restrict__ inbox, int *__restrict__ flags, int *__restrict__ chg) {
-  // one block per tile row of the column; threads over its slots
-  const int tr = blockIdx.x;
-  const int cnt = rts[tr * TR1 + MAVI_TR] - rts[tr * TR1];
-  for (int l = threadIdx.x; l < cnt; l += blockDim.x) {
-    const int s = (rts[tr * TR1] - sender_base) + l;  // offset inside the received column slab
-    const double2 r = rpos[s];
-    int c = cell_of_point(p, r.x, r.y);
+// Immigrants: every received record is queued as an inter-tile mover of THIS rank: record -> mover list, destination
+// tile inbox, tile marked dirty.  The incremental repair then merges it exactly like a local mover.
+__global__ void k_ingest(const __grid_constant__ DevParams p, const EmRec *__restrict__ recs, int count_flag, int em_cap,
+                         int has_vel, double2 *__restrict__ mv_pos, double2 *__restrict__ mv_second,
+                         double2 *__restrict__ mv_force, unsigned int *__restrict__ mv_id, int *__restrict__ mv_cell,
+                         int *__restrict__ mv_src, int *__restrict__ tile_dirty, int *__restrict__ dirty_list,
+                         int *__restrict__ inbox_cnt, int *__restrict__ inbox, int *__restrict__ flags,
+                         int *__restrict__ chg) {
+  if (!flags[FLAG_RAN]) return;
+  const int n = min(flags[count_flag], em_cap);
+  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < n; l += gridDim.x * blockDim.x) {
+    const EmRec e = recs[l];
+    int c = cell_of_point(p, e.pos.x, e.pos.y);
     const int lcol = c >= 0 ? div_rows(p, c) : -1;
     if (c < 0 || lcol < 1 || lcol > p.num_cols - 2) {
       atomicOr(&flags[FLAG_ERR], ERRBIT_OUT_OF_GRID);
@@ -215,10 +210,10 @@ __global__ void k_ingest(const __grid_constant__ DevParams p, const int *__restr
     const int i = atomicAdd(&inbox_cnt[t], 1);
     if (m < p.mv_cap && i < p.inbox_cap) {
       mv_src[m] = -1;  // record already in place (k_repair_collect skips it)
-      mv_pos[m] = r;
-      mv_second[m] = rsecond2 ? rsecond2[s] : make_double2(rsecond1[s], 0.0);
-      mv_force[m] = rforce[s];
-      mv_id[m] = rid[s];
+      mv_pos[m] = e.pos;
+      mv_second[m] = e.second;
+      mv_force[m] = e.force;
+      mv_id[m] = e.idflag;
       mv_cell[m] = c;
       inbox[(size_t)t * p.inbox_cap + i] = m;
     } else {
@@ -265,80 +260,35 @@ int slab_halo_exchange(Handle *h, double2 *pos_buf, bool with_layout) {
   return MAVI_OK;
 }
 
-static int slab_alloc_mig(Handle *h) {
-  const DevParams &p = h->p;
-  SlabState &s = h->slab;
-  const size_t cs = col_slots(p), rows = (size_t)p.tpc * TR1;
-  if (s.mig_cs == cs) return MAVI_OK;
-  for (int d = 0; d < 2; d++) {
-    void *old[] = {s.mig_pos[d], s.mig_second[d], s.mig_force[d], s.mig_id[d], s.mig_ts[d]};
-    for (void *q : old)
-      if (q) cudaFree(q);
-    SLAB_CUDA(h, cudaMalloc((void **)&s.mig_pos[d], cs * sizeof(double2)));
-    SLAB_CUDA(h, cudaMalloc((void **)&s.mig_second[d], cs * sizeof(double2)));
-    SLAB_CUDA(h, cudaMalloc((void **)&s.mig_force[d], cs * sizeof(double2)));
-    SLAB_CUDA(h, cudaMalloc((void **)&s.mig_id[d], cs * sizeof(unsigned int)));
-    SLAB_CUDA(h, cudaMalloc((void **)&s.mig_ts[d], rows * sizeof(int)));
-  }
-  s.mig_cs = cs;
-  return MAVI_OK;
-}
-
-// After the local repair the halo tiles (columns 0 and m+1) hold exactly the emigrants.  Ship both columns, then
-// queue what arrived as movers and run the tile repair a second time.
+// Migration: the integrate kernel wrote the record of every particle that crossed into a halo column straight into
+// the emigrant buffer of that side (note_if_moved).  Ship both buffers (fixed capacity, the count travels separately)
+// and queue what arrived as movers; the ONE tile repair of the step then handles local movers and immigrants alike.
 static int slab_migrate(Handle *h, bool carry) {
   const DevParams &p = h->p;
   SlabState &s = h->slab;
   DevArrays &a = h->a;
-  int st = slab_alloc_mig(h);
-  if (st) return st;
   const bool vel = h->second_kind == SECOND_VEL;
-  const size_t cs = col_slots(p), m = (size_t)s.m, rows = (size_t)p.tpc * TR1;
-  const size_t sec_bytes = vel ? sizeof(double2) : sizeof(double);
-  char *second = vel ? (char *)a.vel : (char *)a.ang;
-  const size_t off[2] = {0, (m + 1) * cs};  // emigrant columns: 0 -> left neighbour, m+1 -> right neighbour
   const int peer[2] = {s.left, s.right};
+  const size_t bytes = (size_t)a.em_cap * sizeof(EmRec);
   SLAB_NCCL(h, g_nccl.GroupStart());
   for (int d = 0; d < 2; d++) {
-    SLAB_NCCL(h, g_nccl.Send(a.pos[0] + off[d], cs * sizeof(double2), ncclInt8, peer[d], s.comm, h->stream));
-    SLAB_NCCL(h, g_nccl.Send(second + off[d] * sec_bytes, cs * sec_bytes, ncclInt8, peer[d], s.comm, h->stream));
-    SLAB_NCCL(h, g_nccl.Send(a.force + off[d], cs * sizeof(double2), ncclInt8, peer[d], s.comm, h->stream));
-    SLAB_NCCL(h, g_nccl.Send(a.idflag + off[d], cs * sizeof(unsigned int), ncclInt8, peer[d], s.comm, h->stream));
-    SLAB_NCCL(h, g_nccl.Send(a.tstart + (d == 0 ? 0 : (m + 1)) * rows, rows * sizeof(int), ncclInt8, peer[d], s.comm, h->stream));
+    SLAB_NCCL(h, g_nccl.Send(a.flags + FLAG_NEM0 + d, sizeof(int), ncclInt8, peer[d], s.comm, h->stream));
+    SLAB_NCCL(h, g_nccl.Send(a.em_send[d], bytes, ncclInt8, peer[d], s.comm, h->stream));
   }
-  // with 2 GPUs both messages come from the same peer: its first batch is ITS column 0 (sent to its left = me, arriving
-  // from my right side), so slot 1 (from the right neighbour) is received first
+  // with 2 GPUs both messages come from the same peer: its first batch is what left through ITS left edge (towards me,
+  // arriving on my right side), so the buffer of the right neighbour is received first
   for (int d = 1; d >= 0; d--) {
-    SLAB_NCCL(h, g_nccl.Recv(s.mig_pos[d], cs * sizeof(double2), ncclInt8, peer[d], s.comm, h->stream));
-    SLAB_NCCL(h, g_nccl.Recv(s.mig_second[d], cs * sec_bytes, ncclInt8, peer[d], s.comm, h->stream));
-    SLAB_NCCL(h, g_nccl.Recv(s.mig_force[d], cs * sizeof(double2), ncclInt8, peer[d], s.comm, h->stream));
-    SLAB_NCCL(h, g_nccl.Recv(s.mig_id[d], cs * sizeof(unsigned int), ncclInt8, peer[d], s.comm, h->stream));
-    SLAB_NCCL(h, g_nccl.Recv(s.mig_ts[d], rows * sizeof(int), ncclInt8, peer[d], s.comm, h->stream));
+    SLAB_NCCL(h, g_nccl.Recv(a.flags + FLAG_NEMR0 + d, sizeof(int), ncclInt8, peer[d], s.comm, h->stream));
+    SLAB_NCCL(h, g_nccl.Recv(a.em_recv[d], bytes, ncclInt8, peer[d], s.comm, h->stream));
   }
   SLAB_NCCL(h, g_nccl.GroupEnd());
-  // second repair round: fresh mover list
-  SLAB_CUDA(h, cudaMemsetAsync(a.flags + FLAG_CHANGED, 0, sizeof(int), h->stream));
-  SLAB_CUDA(h, cudaMemsetAsync(a.flags + FLAG_NMV, 0, sizeof(int), h->stream));
   for (int d = 0; d < 2; d++) {
-    // what I receive from my LEFT neighbour is its column m_left+1; from my RIGHT neighbour its column 0
-    const int sender_base = d == 0 ? (int)((size_t)(s.m_left + 1) * cs) : 0;
-    k_ingest<<<p.tpc, 128, 0, h->stream>>>(p, s.mig_ts[d], sender_base, s.mig_pos[d], vel ? s.mig_second[d] : nullptr,
-                                           vel ? nullptr : (const double *)s.mig_second[d], s.mig_force[d], s.mig_id[d],
-                                           a.mv_pos, a.mv_second, a.mv_force, a.mv_id, a.mv_cell, a.mv_src, a.tile_dirty,
-                                           a.dirty_list, a.inbox_cnt, a.inbox, a.flags, carry ? a.chg : nullptr);
+    k_ingest<<<8, 128, 0, h->stream>>>(p, a.em_recv[d], FLAG_NEMR0 + d, a.em_cap, vel ? 1 : 0, a.mv_pos, a.mv_second,
+                                       a.mv_force, a.mv_id, a.mv_cell, a.mv_src, a.tile_dirty, a.dirty_list, a.inbox_cnt,
+                                       a.inbox, a.flags, carry ? a.chg : nullptr);
     h->launches++;
   }
-  launch_repair_tiles(h->ctx(), p, a, vel);
-  if (carry) launch_carry_redrift(h->ctx(), p, a);  // tiles rewritten by the second repair round
   return MAVI_OK;
-}
-
-static void clear_halo_columns(Handle *h) {
-  const DevParams &p = h->p;
-  const int nb = (p.tpc * TR1 + 255) / 256;
-  k_clear_column<<<nb, 256, 0, h->stream>>>(p, h->a.tstart, 0);
-  k_clear_column<<<nb, 256, 0, h->stream>>>(p, h->a.tstart, p.num_cols - 1);
-  h->launches += 2;
 }
 
 // number of owned particles after a (re)build / migration -> p.n, p.n_active
@@ -398,11 +348,10 @@ int slab_step_once(Handle *h, const double *noise_dev) {
   }
   std::swap(a.pos[0], a.pos[1]);
   if (h->prof) cudaEventRecord(h->ev[3], h->stream);
-  // update_chunks! for the next step: halo tiles become the emigrant bins, local repair, migration, second repair
-  clear_halo_columns(h);
-  launch_repair_tiles(c, p, a, vel);
-  if (carry) launch_carry_redrift(c, p, a);  // tiles rewritten by the first repair round (the list is reset below)
+  // update_chunks! for the next step: emigrants -> neighbours, immigrants queued as movers, ONE incremental repair
   if ((st = slab_migrate(h, carry))) return st;
+  launch_repair_tiles(c, p, a, vel);
+  if (carry) launch_carry_redrift(c, p, a);
   h->time += p.dt;
   h->num_steps += 1;
   // (no host synchronisation here: the owned count and the overflow word are read by slab_sync_counts)
