@@ -30,6 +30,8 @@ RNG_HOST_NOISE, RNG_PHILOX = range(2)
 FLAG_RESORT_EVERY_STEP = 1
 FLAG_TIGHT_TILES = 2
 FLAG_NO_FORCE_CARRY = 4
+FLAG_SMALL_BLOCKS = 8
+FLAG_SLAB_SELF = 16
 
 
 class MaviLine(C.Structure):

@@ -172,7 +172,7 @@ static int validate_and_lower(Handle *h, const MaviParams *mp) {
                        4.0 * p.ch <= p.half[1]) ? 1 : 0;
   }
 
-  if (mp->world > 1) {
+  if (mp->world > 1 || (mp->flags & MAVI_FLAG_SLAB_SELF)) {
     int st = slab_configure(h, mp);
     if (st) return st;
   }
@@ -306,13 +306,17 @@ int Handle::alloc_state(int n_active, int cap) {
       const double mean_tile = (double)(n_active > 0 ? n_active : 1) / (double)((long long)p.ord_cols * p.tpc);
       int g = (int)(1000.0 / (mean_tile > 1.0 ? mean_tile : 1.0));
       p.blk_cols = g < 1 ? 1 : (g > 30 ? 30 : g);
+      if (flags_cfg & MAVI_FLAG_SMALL_BLOCKS) p.blk_cols = 3;
       p.blk_per_row = (p.ord_cols + p.blk_cols - 1) / p.blk_cols;
+      p.blk_last = (p.ord_cols - (p.blk_per_row - 1) * p.blk_cols) >= 3 ? 1 : 2;
+      p.blk_mode = 0;
     }
   } else {
     p.tpc = p.nt = p.cap = p.nt_ord = 0;
     p.tail_base = 0;
     p.inbox_cap = p.mv_cap = p.chg_cap = 0;
-    p.blk_cols = p.blk_per_row = 0;
+    p.blk_cols = p.blk_per_row = p.blk_mode = 0;
+    p.blk_last = 1;
   }
   ns = (size_t)p.tail_base + (size_t)(p.slab ? 0 : (p.n - p.n_active));
   int st;

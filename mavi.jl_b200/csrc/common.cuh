@@ -52,6 +52,8 @@ struct DevParams {
   int mv_cap;     // capacity of the per-step inter-tile mover list
   int chg_cap;    // capacity of the per-step changed-cell list (force carry)
   int blk_cols, blk_per_row;  // tile-block force kernels: own tiles (columns) per CTA, CTAs per tile row
+  int blk_mode;   // 0: all blocks; 1: all but the first and the last blk_last blocks of every tile row; 2: only those
+  int blk_last;   // trailing blocks of a tile row that belong to the boundary group (2 when the last one is < 3 columns)
   // x-slab domain decomposition (one process per GPU): the local grid is [left halo | owned columns | right halo];
   // cell arithmetic stays GLOBAL (bit-exact global cell ids), only the column index is shifted into the local frame.
   int slab;                   // 1 = slab mode
@@ -176,10 +178,13 @@ __device__ __forceinline__ int cell_of_point(const DevParams &p, double x, doubl
   if (row < 1 || row > p.num_rows || col < 1 || col > p.gcols) return -1;
   int lcol = col - 1;
   if (p.slab) {  // global column -> local frame [0 = left halo, 1..m owned, m+1 = right halo], periodic in x
-    lcol = lcol - p.col_lo + 1;
-    if (lcol < 0) lcol += p.gcols;
-    else if (lcol >= p.gcols) lcol -= p.gcols;
-    if (lcol >= p.num_cols) return -1;  // more than one column beyond the slab in one step
+    int d = lcol - p.col_lo;
+    if (d < 0) d += p.gcols;  // [0, gcols): columns to the right of my first one
+    lcol = d + 1;
+    if (lcol > p.num_cols - 1) {  // beyond the right halo: the left halo is the only other column I hold
+      lcol -= p.gcols;
+      if (lcol != 0) return -1;  // more than one column beyond the slab in one step
+    }
   }
   return (row - 1) + p.num_rows * lcol;
 }

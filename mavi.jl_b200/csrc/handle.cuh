@@ -22,6 +22,9 @@ struct SlabState {
   int m = 0, m_left = 0, m_right = 0, col_lo = 0;
   int n_global = 0;
   struct ncclComm *comm = nullptr;
+  cudaStream_t side = nullptr;                  // the drifted-halo exchange overlaps with the interior blocks
+  cudaEvent_t ev_ready = nullptr, ev_halo = nullptr, ev_begin = nullptr, ev_side = nullptr;
+  bool side_busy = false;  // work of the step pipeline is in flight on the side stream (joined by slab_join)
 };
 
 struct Handle {
@@ -74,6 +77,7 @@ int slab_after_build(Handle *h);
 int slab_allreduce_max(Handle *h, int *value);
 int slab_step_once(Handle *h, const double *noise_dev);
 int slab_sync_counts(Handle *h);
+int slab_join(Handle *h);
 
 // rings.cu
 int rings_lower(Handle *h, const MaviParams *mp);

@@ -1187,7 +1187,8 @@ template <int DYN, bool PER>
 __device__ __forceinline__ void recompute_particle(const DevParams &p, int *__restrict__ flags,
                                                    const int *__restrict__ tstart, const double2 *__restrict__ pos,
                                                    const double2 *__restrict__ vel, double2 *__restrict__ f1_next,
-                                                   double2 *__restrict__ pos_next, int k, int cell) {
+                                                   double2 *__restrict__ pos_next, int k, int cell,
+                                                   bool report_big = true) {
   const double2 r = pos[k];
   double fx = 0.0, fy = 0.0;
   for_each_neighbor(p, tstart, cell, k, [&](int j) { accumulate_pair<DYN, PER>(p, r, __ldg(pos + j), fx, fy); });
@@ -1196,7 +1197,7 @@ __device__ __forceinline__ void recompute_particle(const DevParams &p, int *__re
   f1_next[k] = F;
   bool big;
   pos_next[k] = verlet_drift(p, r, vel[k], F, big);
-  if (PER && big) flags[FLAG_BIGMOVE_NEXT] = 1;
+  if (PER && big && report_big) flags[FLAG_BIGMOVE_NEXT] = 1;
 }
 
 // (2) F1 and the drift of every particle that has a changed cell in its stencil, with the fresh cell lists: one warp
@@ -1208,7 +1209,9 @@ template <int DYN, bool PER>
 __global__ void k_recompute_changed(const __grid_constant__ DevParams p, int *__restrict__ flags,
                                     const int *__restrict__ chg, const int *__restrict__ tstart,
                                     const double2 *__restrict__ pos, const double2 *__restrict__ vel,
-                                    double2 *__restrict__ f1_next, double2 *__restrict__ pos_next) {
+                                    double2 *__restrict__ f1_next, double2 *__restrict__ pos_next, int skip_edge) {
+  // slab mode: halo columns hold no state of this rank (skip_edge = 1); with skip_edge = 3 the two owned columns next
+  // to each halo are left to k_recompute_columns as well (it runs on the side stream, after the halo exchange)
   if (!flags[FLAG_RAN] || flags[FLAG_OVERFLOW]) return;
   const int lane = threadIdx.x & 31, w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   const int n = min(flags[FLAG_NCHG], p.chg_cap);
@@ -1225,6 +1228,7 @@ __global__ void k_recompute_changed(const __grid_constant__ DevParams p, int *__
       else if (c2 >= Cn) { ok = p.wrap_cols; c2 = 0; }
       if (r2 < 0) { ok = ok && p.wrap_rows; r2 = R - 1; }
       else if (r2 >= R) { ok = ok && p.wrap_rows; r2 = 0; }
+      if (skip_edge && (c2 < skip_edge || c2 >= Cn - skip_edge)) ok = false;
       if (ok) {
         const int q = tq_of(p, c2, r2);
         kb = tstart[q];
@@ -1253,23 +1257,27 @@ __global__ void k_recompute_changed(const __grid_constant__ DevParams p, int *__
   }
 }
 
-// (3) slab mode: the neighbour rank's boundary column re-bins behind this rank's back, so every particle of the two
-//     owned boundary columns (local columns 1 and num_cols-2) is recomputed every step.
+// (3) slab mode: the neighbour rank's boundary column re-bins behind this rank's back, so every particle of the owned
+//     boundary columns is recomputed every step: `depth` columns on each side (1: local columns 1 and num_cols-2;
+//     2: also the next ones, when the list-driven kernel above leaves them out).  report_big = 0: no big-drift flag (the
+//     blocks that read these particles take the exact minimum-image path anyway, see slab.cu).
 template <int DYN, bool PER>
 __global__ void k_recompute_columns(const __grid_constant__ DevParams p, int *__restrict__ flags,
                                     const int *__restrict__ tstart, const int *__restrict__ cell,
                                     const double2 *__restrict__ pos, const double2 *__restrict__ vel,
-                                    double2 *__restrict__ f1_next, double2 *__restrict__ pos_next) {
+                                    double2 *__restrict__ f1_next, double2 *__restrict__ pos_next, int depth,
+                                    int report_big) {
   if (!flags[FLAG_RAN] || flags[FLAG_OVERFLOW]) return;
   const int cs = p.tpc * p.cap;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int ncols = (p.num_cols - 2 > 1) ? 2 : 1;
-  if (i >= ncols * cs) return;
-  const int col = (i < cs) ? 1 : p.num_cols - 2;
-  const int k = col * cs + (i < cs ? i : i - cs);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * depth * cs) return;
+  const int ci = i / cs;                                                    // 0 .. 2*depth-1
+  const int col = ci < depth ? 1 + ci : p.num_cols - 2 - (ci - depth);      // left side, then right side
+  if (ci >= depth && col <= depth) return;                                   // narrow slab: column already covered
+  const int k = col * cs + (i - ci * cs);
   const int t = k / p.cap;
   if (k >= tstart[(size_t)t * (MAVI_TR + 1) + MAVI_TR]) return;  // slack slot
-  recompute_particle<DYN, PER>(p, flags, tstart, pos, vel, f1_next, pos_next, k, cell[k]);
+  recompute_particle<DYN, PER>(p, flags, tstart, pos, vel, f1_next, pos_next, k, cell[k], report_big != 0);
 }
 
 // First kernel of every step: decides ONCE whether the step runs (no overflow / out-of-grid latched by an earlier
@@ -1529,7 +1537,11 @@ __device__ __forceinline__ void for_each_block_particle(const DevParams &p, cons
   Chunk2 *ck = reinterpret_cast<Chunk2 *>(dsm);
   double2 *s_pos = reinterpret_cast<double2 *>(dsm + C2_BYTES);
   unsigned int *s_list = reinterpret_cast<unsigned int *>(dsm + C2_BYTES + SPOS2_CAP * sizeof(double2));
-  const int nblk_tiles = p.blk_per_row * p.tpc;
+  // blk_mode 1 / 2 split a launch into the blocks that never read a halo column and the first / last block of every
+  // tile row (slab mode: the halo exchange overlaps with the former)
+  const int bpr = p.blk_per_row;
+  const int per_row = p.blk_mode == 0 ? bpr : (p.blk_mode == 1 ? bpr - 1 - p.blk_last : 1 + p.blk_last);
+  const int nblk_tiles = per_row * p.tpc;
   if ((int)blockIdx.x >= nblk_tiles) {  // inactive tail: no pair forces
     const int i = ((int)blockIdx.x - nblk_tiles) * TPB + threadIdx.x;
     if (i < p.n - p.n_active) {
@@ -1539,8 +1551,11 @@ __device__ __forceinline__ void for_each_block_particle(const DevParams &p, cons
     }
     return;
   }
-  const int tr = (int)blockIdx.x / p.blk_per_row;
-  const int c_begin = p.ord_col0 + ((int)blockIdx.x - tr * p.blk_per_row) * p.blk_cols;
+  const int tr = (int)blockIdx.x / per_row;
+  int bcol = (int)blockIdx.x - tr * per_row;
+  if (p.blk_mode == 1) bcol += 1;
+  else if (p.blk_mode == 2) bcol = bcol ? bpr - bcol : 0;
+  const int c_begin = p.ord_col0 + bcol * p.blk_cols;
   const int c_end = min(c_begin + p.blk_cols, p.ord_col0 + p.ord_cols);
   const int r0 = tr * MAVI_TR;
   for (int cs = c_begin; cs < c_end;) {
@@ -1577,7 +1592,10 @@ __device__ __forceinline__ void for_each_block_particle(const DevParams &p, cons
   }
 }
 
-static inline int grid2(const DevParams &p) { return p.blk_per_row * p.tpc + nblk(p.n - p.n_active); }
+static inline int grid2(const DevParams &p) {
+  const int per_row = p.blk_mode == 0 ? p.blk_per_row : (p.blk_mode == 1 ? p.blk_per_row - 1 - p.blk_last : 1 + p.blk_last);
+  return per_row * p.tpc + (p.blk_mode == 2 ? 0 : nblk(p.n - p.n_active));
+}
 
 template <int DYN, bool PER>
 __global__ void __launch_bounds__(TPB) k_force_only2(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
@@ -1612,7 +1630,9 @@ __global__ void __launch_bounds__(TPB, MINB) k_newton_b2(const __grid_constant__
                             double2 *f2, double2 *f1_next, double2 *__restrict__ pos_next,
                             int *__restrict__ fix_idx, double2 *__restrict__ fix_pos, const MoverSink ms) {
   if (!ms.flags[FLAG_RAN]) return;
-  const bool exact = ms.flags[FLAG_BIGMOVE] != 0;
+  // slab mode, blocks next to a halo column (blk_mode 2): their boundary particles are re-drifted on the side stream
+  // without a big-drift report -> always the exact minimum-image path there
+  const bool exact = ms.flags[FLAG_BIGMOVE] != 0 || (p.slab && p.blk_mode == 2);
   for_each_block_particle<DYN, PER>(p, tstart, pos_in, ms.cell, exact,
     [&](int k) { prefetch_l1(vel + k); prefetch_l1(f1 + k); },
     [&](int k, double2 r, int c, bool active, double2 F) {
@@ -1666,6 +1686,17 @@ __global__ void __launch_bounds__(TPB) k_self_propelled2(const __grid_constant__
     });
 }
 
+// all-pairs runs (chunks === nothing) keep the rank-mapped kernels with ALLP = true; chunked runs use the tile-block ones
+#define MAVI_DISPATCH_ALLP(DYNV, PERV, CALL) \
+  do {                                       \
+    if (PERV) { CALL(DYNV, true, true); } else { CALL(DYNV, false, true); } \
+  } while (0)
+
+#define MAVI_DISPATCH2(DYNV, PERV, CALL) \
+  do {                                   \
+    if (PERV) { CALL(DYNV, true); } else { CALL(DYNV, false); } \
+  } while (0)
+
 // ---- dispatch over (dynamics, periodic, all-pairs) ----------------------------------------------------------
 #define MAVI_DISPATCH_DYN(DYNV, PERV, ALLPV, CALL)                                    \
   do {                                                                                \
@@ -1679,17 +1710,6 @@ __global__ void __launch_bounds__(TPB) k_self_propelled2(const __grid_constant__
 static MoverSink mover_sink(const DevArrays &a) {
   return MoverSink{a.cell, a.tile_dirty, a.dirty_list, a.inbox_cnt, a.inbox, a.mv_src, a.flags, nullptr, {a.em_send[0], a.em_send[1]}, a.em_cap, a.idflag};
 }
-
-// all-pairs runs (chunks === nothing) keep the rank-mapped kernels with ALLP = true; chunked runs use the tile-block ones
-#define MAVI_DISPATCH_ALLP(DYNV, PERV, CALL) \
-  do {                                       \
-    if (PERV) { CALL(DYNV, true, true); } else { CALL(DYNV, false, true); } \
-  } while (0)
-
-#define MAVI_DISPATCH2(DYNV, PERV, CALL) \
-  do {                                   \
-    if (PERV) { CALL(DYNV, true); } else { CALL(DYNV, false); } \
-  } while (0)
 
 void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool with_wall_forces) {
   const bool allp = p.num_cells == 0;
@@ -1731,8 +1751,14 @@ void launch_newton_a(const LaunchCtx &c, const DevParams &p, const DevArrays &a)
 #undef CALL
 }
 
+void launch_apply_pos_fixes(const LaunchCtx &c, const DevArrays &a) {
+  MAVI_LAUNCH(c, k_apply_pos_fixes, 64, TPB, 0, a.flags, a.fix_idx, a.fix_pos, a.pos[1]);
+}
+
 // carry: also write the next step's F1 / drift (into force_old / pos[0]) and record the changed cells
-void launch_newton_b(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool carry) {
+void launch_newton_b(const LaunchCtx &c, const DevParams &p_in, const DevArrays &a, bool carry, int blk_mode) {
+  DevParams p = p_in;
+  p.blk_mode = blk_mode;
   const bool allp = p.num_cells == 0;
   MoverSink ms = mover_sink(a);
   // reads the drifted positions pos[1] (which become the current positions after the sparse wall fix-ups)
@@ -1764,7 +1790,7 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p, const DevArrays &a,
   }
 #undef CALL
 #undef ARGS
-  MAVI_LAUNCH(c, k_apply_pos_fixes, 64, TPB, 0, a.flags, a.fix_idx, a.fix_pos, a.pos[1]);
+  if (blk_mode == 0) launch_apply_pos_fixes(c, a);
 }
 
 // force carry, after the swap and the tile repair: pos[0] = current positions, pos[1] = carried drift
@@ -1773,19 +1799,27 @@ void launch_carry_redrift(const LaunchCtx &c, const DevParams &p, const DevArray
               a.force_old, a.pos[1]);
 }
 
+// skip_edge / depth / report_big: see k_recompute_changed / k_recompute_columns
+void launch_carry_recompute_list(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int skip_edge) {
+#define CALL(D, P) \
+  MAVI_LAUNCH(c, (k_recompute_changed<D, P>), 148 * 4, TPB, 0, p, a.flags, a.chg, a.tstart, a.pos[0], a.vel, a.force_old, a.pos[1], skip_edge)
+  if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALL);
+  else MAVI_DISPATCH2(MAVI_DYN_HARMTRUNC, p.periodic, CALL);
+#undef CALL
+}
+
+void launch_carry_recompute_columns(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int depth, bool report_big) {
+  const int nthreads = 2 * depth * p.tpc * p.cap;
+#define CALL(D, P) \
+  MAVI_LAUNCH(c, (k_recompute_columns<D, P>), nblk(nthreads), TPB, 0, p, a.flags, a.tstart, a.cell, a.pos[0], a.vel, a.force_old, a.pos[1], depth, (int)report_big)
+  if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALL);
+  else MAVI_DISPATCH2(MAVI_DYN_HARMTRUNC, p.periodic, CALL);
+#undef CALL
+}
+
 void launch_carry_recompute(const LaunchCtx &c, const DevParams &p, const DevArrays &a) {
-#define CALL(D, P, A) \
-  MAVI_LAUNCH(c, (k_recompute_changed<D, P>), 148 * 4, TPB, 0, p, a.flags, a.chg, a.tstart, a.pos[0], a.vel, a.force_old, a.pos[1])
-  if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, false, CALL);
-  else MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, false, CALL);
-#undef CALL
-  if (!p.slab) return;
-  const int nthreads = 2 * p.tpc * p.cap;
-#define CALL(D, P, A) \
-  MAVI_LAUNCH(c, (k_recompute_columns<D, P>), nblk(nthreads), TPB, 0, p, a.flags, a.tstart, a.cell, a.pos[0], a.vel, a.force_old, a.pos[1])
-  if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_DYN(MAVI_DYN_LJ, p.periodic, false, CALL);
-  else MAVI_DISPATCH_DYN(MAVI_DYN_HARMTRUNC, p.periodic, false, CALL);
-#undef CALL
+  launch_carry_recompute_list(c, p, a, p.slab ? 1 : 0);
+  if (p.slab) launch_carry_recompute_columns(c, p, a, 1, true);
 }
 
 void launch_carry_fixups(const LaunchCtx &c, const DevParams &p, const DevArrays &a) {

@@ -82,10 +82,15 @@ void ensure_rank_maps(const LaunchCtx &c, const DevParams &p, const DevArrays &a
 void launch_step_begin(const LaunchCtx &c, const DevArrays &a);
 void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool with_wall_forces);
 void launch_newton_a(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
-void launch_newton_b(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool carry = false);
+// blk_mode: 0 = every block, then the wall position fix-ups; 1 = blocks that read no halo column; 2 = the first / last
+// block of every tile row (1 and 2: the caller applies the fix-ups after BOTH launches)
+void launch_apply_pos_fixes(const LaunchCtx &c, const DevArrays &a);
+void launch_newton_b(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool carry = false, int blk_mode = 0);
 // force carry (see k_newton_b): redo the carried drift of repaired tiles / recompute F1 around re-binned cells
 void launch_carry_redrift(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
 void launch_carry_recompute(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
+void launch_carry_recompute_list(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int skip_edge);
+void launch_carry_recompute_columns(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int depth, bool report_big);
 void launch_carry_fixups(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
 void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const double *noise,
                            unsigned long long step);

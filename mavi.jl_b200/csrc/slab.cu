@@ -14,6 +14,9 @@
 #include <utility>
 #include <vector>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "handle.cuh"
 
 namespace mavi {
@@ -108,18 +111,21 @@ int slab_configure(Handle *h, const MaviParams *mp) {
     h->set_error("Mavi.Rings runs on one GPU in this version (a ring may straddle a slab boundary)");
     return MAVI_ERR_UNSUPPORTED;
   }
-  if (!mp->nccl_unique_id) {
-    h->set_error("world > 1 needs MaviParams.nccl_unique_id (mavi_nccl_unique_id on rank 0, broadcast by the host)");
-    return MAVI_ERR_BAD_PARAMS;
+  const bool self = mp->world <= 1;  // MAVI_FLAG_SLAB_SELF: this rank is its own neighbour, no NCCL
+  if (!self) {
+    if (!mp->nccl_unique_id) {
+      h->set_error("world > 1 needs MaviParams.nccl_unique_id (mavi_nccl_unique_id on rank 0, broadcast by the host)");
+      return MAVI_ERR_BAD_PARAMS;
+    }
+    const char *e = load_nccl();
+    if (e) {
+      h->set_error("NCCL unavailable: %s", e);
+      return MAVI_ERR_NCCL;
+    }
   }
-  const char *e = load_nccl();
-  if (e) {
-    h->set_error("NCCL unavailable: %s", e);
-    return MAVI_ERR_NCCL;
-  }
-  s.world = mp->world;
+  s.world = self ? 1 : mp->world;
   s.n_global = (int)(mp->n_global > 0 ? mp->n_global : mp->n);
-  s.rank = mp->rank;
+  s.rank = self ? 0 : mp->rank;
   const int C = mp->num_cols;
   slab_columns(C, s.world, s.rank, &s.col_lo, &s.m);
   if (s.m < 2) {
@@ -142,15 +148,27 @@ int slab_configure(Handle *h, const MaviParams *mp) {
   p.wrap_rows = 1;
   p.seam_left = s.rank == 0;
   p.seam_right = s.rank == s.world - 1;
-  ncclUniqueId id;
-  memcpy(&id, mp->nccl_unique_id, sizeof id);
-  SLAB_NCCL(h, g_nccl.CommInitRank(&s.comm, s.world, id, s.rank));
+  if (!self) {
+    ncclUniqueId id;
+    memcpy(&id, mp->nccl_unique_id, sizeof id);
+    SLAB_NCCL(h, g_nccl.CommInitRank(&s.comm, s.world, id, s.rank));
+  }
+  {  // the side stream's small kernels must not queue behind the 16k blocks of the interior pass
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    SLAB_CUDA(h, cudaStreamCreateWithPriority(&s.side, cudaStreamNonBlocking, hi));
+  }
+  SLAB_CUDA(h, cudaEventCreateWithFlags(&s.ev_ready, cudaEventDisableTiming));
+  SLAB_CUDA(h, cudaEventCreateWithFlags(&s.ev_halo, cudaEventDisableTiming));
+  SLAB_CUDA(h, cudaEventCreateWithFlags(&s.ev_begin, cudaEventDisableTiming));
+  SLAB_CUDA(h, cudaEventCreateWithFlags(&s.ev_side, cudaEventDisableTiming));
   return MAVI_OK;
 }
 
 // max over all ranks of one int (tile capacity agreement: every rank must use the SAME slots-per-column, because a
 // halo / emigrant column is shipped as one raw slab of tpc*cap slots)
 int slab_allreduce_max(Handle *h, int *value) {
+  if (!h->slab.comm) return MAVI_OK;  // one-rank slab mode
   int *d = h->a.flags + FLAG_SCRATCH;
   SLAB_CUDA(h, cudaMemcpyAsync(d, value, sizeof(int), cudaMemcpyHostToDevice, h->stream));
   SLAB_NCCL(h, g_nccl.AllReduce(d, d, 1, /*ncclInt32*/ 2, /*ncclMax*/ 2, h->slab.comm, h->stream));
@@ -162,6 +180,15 @@ int slab_allreduce_max(Handle *h, int *value) {
 void slab_destroy(Handle *h) {
   if (h->slab.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->slab.comm);
   h->slab.comm = nullptr;
+  if (h->slab.side) cudaStreamDestroy(h->slab.side);
+  if (h->slab.ev_ready) cudaEventDestroy(h->slab.ev_ready);
+  if (h->slab.ev_halo) cudaEventDestroy(h->slab.ev_halo);
+  if (h->slab.ev_begin) cudaEventDestroy(h->slab.ev_begin);
+  if (h->slab.ev_side) cudaEventDestroy(h->slab.ev_side);
+  h->slab.ev_begin = h->slab.ev_side = nullptr;
+  h->slab.side_busy = false;
+  h->slab.side = nullptr;
+  h->slab.ev_ready = h->slab.ev_halo = nullptr;
 }
 
 // ---- kernels ------------------------------------------------------------------------------------------------------
@@ -230,31 +257,41 @@ __global__ void k_owned_count(const __grid_constant__ DevParams p, const int *__
 static size_t col_slots(const DevParams &p) { return (size_t)p.tpc * p.cap; }
 
 // halo positions (pos_buf = a.pos[0] or a.pos[1]); with_layout also ships the tstart rows of the boundary columns
-int slab_halo_exchange(Handle *h, double2 *pos_buf, bool with_layout) {
+int slab_halo_exchange(Handle *h, double2 *pos_buf, bool with_layout, cudaStream_t stream = nullptr) {
+  if (!stream) stream = h->stream;
   const DevParams &p = h->p;
   SlabState &s = h->slab;
   DevArrays &a = h->a;
   const size_t cs = col_slots(p), m = (size_t)s.m;
   const size_t rows = (size_t)p.tpc * TR1;
   // my boundary columns: local 1 (-> left neighbour's right halo) and local m (-> right neighbour's left halo)
+  if (!s.comm) {  // one-rank slab mode: I am my own left and right neighbour
+    SLAB_CUDA(h, cudaMemcpyAsync(pos_buf + (m + 1) * cs, pos_buf + 1 * cs, cs * sizeof(double2), cudaMemcpyDeviceToDevice, stream));
+    SLAB_CUDA(h, cudaMemcpyAsync(pos_buf + 0 * cs, pos_buf + m * cs, cs * sizeof(double2), cudaMemcpyDeviceToDevice, stream));
+    if (with_layout) {
+      SLAB_CUDA(h, cudaMemcpyAsync(a.tstart + (m + 1) * rows, a.tstart + 1 * rows, rows * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+      SLAB_CUDA(h, cudaMemcpyAsync(a.tstart + 0 * rows, a.tstart + m * rows, rows * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+    }
+  } else {
   SLAB_NCCL(h, g_nccl.GroupStart());
-  SLAB_NCCL(h, g_nccl.Send(pos_buf + 1 * cs, cs * sizeof(double2), ncclInt8, s.left, s.comm, h->stream));
-  SLAB_NCCL(h, g_nccl.Send(pos_buf + m * cs, cs * sizeof(double2), ncclInt8, s.right, s.comm, h->stream));
+  SLAB_NCCL(h, g_nccl.Send(pos_buf + 1 * cs, cs * sizeof(double2), ncclInt8, s.left, s.comm, stream));
+  SLAB_NCCL(h, g_nccl.Send(pos_buf + m * cs, cs * sizeof(double2), ncclInt8, s.right, s.comm, stream));
   // receive order matters when left == right (2 GPUs): the peer's FIRST send is its column 1 = my RIGHT halo
-  SLAB_NCCL(h, g_nccl.Recv(pos_buf + (m + 1) * cs, cs * sizeof(double2), ncclInt8, s.right, s.comm, h->stream));
-  SLAB_NCCL(h, g_nccl.Recv(pos_buf + 0 * cs, cs * sizeof(double2), ncclInt8, s.left, s.comm, h->stream));
+  SLAB_NCCL(h, g_nccl.Recv(pos_buf + (m + 1) * cs, cs * sizeof(double2), ncclInt8, s.right, s.comm, stream));
+  SLAB_NCCL(h, g_nccl.Recv(pos_buf + 0 * cs, cs * sizeof(double2), ncclInt8, s.left, s.comm, stream));
   if (with_layout) {
-    SLAB_NCCL(h, g_nccl.Send(a.tstart + 1 * rows, rows * sizeof(int), ncclInt8, s.left, s.comm, h->stream));
-    SLAB_NCCL(h, g_nccl.Send(a.tstart + m * rows, rows * sizeof(int), ncclInt8, s.right, s.comm, h->stream));
-    SLAB_NCCL(h, g_nccl.Recv(a.tstart + (m + 1) * rows, rows * sizeof(int), ncclInt8, s.right, s.comm, h->stream));
-    SLAB_NCCL(h, g_nccl.Recv(a.tstart + 0 * rows, rows * sizeof(int), ncclInt8, s.left, s.comm, h->stream));
+    SLAB_NCCL(h, g_nccl.Send(a.tstart + 1 * rows, rows * sizeof(int), ncclInt8, s.left, s.comm, stream));
+    SLAB_NCCL(h, g_nccl.Send(a.tstart + m * rows, rows * sizeof(int), ncclInt8, s.right, s.comm, stream));
+    SLAB_NCCL(h, g_nccl.Recv(a.tstart + (m + 1) * rows, rows * sizeof(int), ncclInt8, s.right, s.comm, stream));
+    SLAB_NCCL(h, g_nccl.Recv(a.tstart + 0 * rows, rows * sizeof(int), ncclInt8, s.left, s.comm, stream));
   }
   SLAB_NCCL(h, g_nccl.GroupEnd());
+  }
   if (with_layout) {
     // right halo came from the right neighbour's column 1; left halo from the left neighbour's column m_left
     const int nb = ((int)rows + 255) / 256;
-    k_rebase_tstart<<<nb, 256, 0, h->stream>>>(a.tstart + (m + 1) * rows, (int)rows, (int)((m + 1) * cs) - (int)(1 * cs));
-    k_rebase_tstart<<<nb, 256, 0, h->stream>>>(a.tstart + 0 * rows, (int)rows, 0 - (int)((size_t)s.m_left * cs));
+    k_rebase_tstart<<<nb, 256, 0, stream>>>(a.tstart + (m + 1) * rows, (int)rows, (int)((m + 1) * cs) - (int)(1 * cs));
+    k_rebase_tstart<<<nb, 256, 0, stream>>>(a.tstart + 0 * rows, (int)rows, 0 - (int)((size_t)s.m_left * cs));
     h->launches += 2;
   }
   return MAVI_OK;
@@ -270,6 +307,12 @@ static int slab_migrate(Handle *h, bool carry) {
   const bool vel = h->second_kind == SECOND_VEL;
   const int peer[2] = {s.left, s.right};
   const size_t bytes = (size_t)a.em_cap * sizeof(EmRec);
+  if (!s.comm) {  // one-rank slab mode: what leaves through my left edge arrives from my right, and vice versa
+    for (int d = 0; d < 2; d++) {
+      SLAB_CUDA(h, cudaMemcpyAsync(a.flags + FLAG_NEMR0 + (1 - d), a.flags + FLAG_NEM0 + d, sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
+      SLAB_CUDA(h, cudaMemcpyAsync(a.em_recv[1 - d], a.em_send[d], bytes, cudaMemcpyDeviceToDevice, h->stream));
+    }
+  } else {
   SLAB_NCCL(h, g_nccl.GroupStart());
   for (int d = 0; d < 2; d++) {
     SLAB_NCCL(h, g_nccl.Send(a.flags + FLAG_NEM0 + d, sizeof(int), ncclInt8, peer[d], s.comm, h->stream));
@@ -282,6 +325,7 @@ static int slab_migrate(Handle *h, bool carry) {
     SLAB_NCCL(h, g_nccl.Recv(a.em_recv[d], bytes, ncclInt8, peer[d], s.comm, h->stream));
   }
   SLAB_NCCL(h, g_nccl.GroupEnd());
+  }
   for (int d = 0; d < 2; d++) {
     k_ingest<<<8, 128, 0, h->stream>>>(p, a.em_recv[d], FLAG_NEMR0 + d, a.em_cap, vel ? 1 : 0, a.mv_pos, a.mv_second,
                                        a.mv_force, a.mv_id, a.mv_cell, a.mv_src, a.tile_dirty, a.dirty_list, a.inbox_cnt,
@@ -304,9 +348,12 @@ static int slab_refresh_count(Handle *h) {
 }
 
 // Owned count + latched overflow word; called at the end of every mavi_step call (and every few steps inside it).
+int slab_join(Handle *h);
 int slab_sync_counts(Handle *h) {
   const DevParams &p = h->p;
-  int st = slab_refresh_count(h);
+  int st = slab_join(h);
+  if (st) return st;
+  st = slab_refresh_count(h);
   if (st) return st;
   if (h->flags_host[FLAG_OVERFLOW]) {
     h->set_error("slab mode overflow (bits %d: 1 = tile capacity %d < %d, 2 = inbox capacity %d < %d at tile %d (column %d of %d), 4 = mover list %d, 8 = changed-cell list)",
@@ -325,23 +372,106 @@ int slab_after_build(Handle *h) {
 }
 
 // one step in slab mode (same operator order as Handle::step_once)
+// MAVI_SLAB_TRACE=<step>: per-phase device timeline of that step on stderr (debugging aid; synchronises once)
+struct SlabTrace {
+  static constexpr int N = 12;
+  cudaEvent_t ev[N];
+  bool on = false;
+  bool rec[N] = {};
+  void begin() { for (auto &e : ev) cudaEventCreate(&e); on = true; }
+  void mark(int i, cudaStream_t s) { if (on) { cudaEventRecord(ev[i], s); rec[i] = true; } }
+  void end(int rank, cudaStream_t main, cudaStream_t side, const int *flags_dev, const DevParams &p) {
+    if (!on) return;
+    cudaStreamSynchronize(main);
+    cudaStreamSynchronize(side);
+    int f[FLAG_COUNT];
+    cudaMemcpy(f, flags_dev, sizeof f, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[slab trace rank %d] flags: err=%d dirty=%d bigmove=%d nfix=%d nmv=%d ran=%d overflow=%d nchg=%d bigmove_next=%d nem=%d,%d nemr=%d,%d | n=%d cap=%d blk_cols=%d bpr=%d blk_last=%d cols=%d fast_interior=%d\n",
+            rank, f[FLAG_ERR], f[FLAG_CHANGED], f[FLAG_BIGMOVE], f[FLAG_NFIX], f[FLAG_NMV], f[FLAG_RAN], f[FLAG_OVERFLOW], f[FLAG_NCHG],
+            f[FLAG_BIGMOVE_NEXT], f[FLAG_NEM0], f[FLAG_NEM1], f[FLAG_NEMR0], f[FLAG_NEMR1], p.n, p.cap, p.blk_cols, p.blk_per_row,
+            p.blk_last, p.num_cols, p.fast_interior);
+    const char *names[N] = {"start", "step_begin", "K_int done", "fixes done (after side wait)", "migrate+ingest", "repair+redrift",
+                            "side: C (halo X+layout) done", "interior recompute done", "side: K_bnd start", "side: bnd recompute + A(next) done", "side: K_bnd done", ""};
+    for (int i = 1; i < 11; i++) {
+      if (!rec[i]) continue;
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev[0], ev[i]);
+      fprintf(stderr, "[slab trace rank %d] %-32s %8.1f us\n", rank, names[i], ms * 1e3f);
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    on = false;
+  }
+};
+
+// Joins the side stream into the main one (before anything that is not part of the step loop touches the state).
+int slab_join(Handle *h) {
+  if (!h->slab.side_busy) return MAVI_OK;
+  SLAB_CUDA(h, cudaEventRecord(h->slab.ev_side, h->slab.side));
+  SLAB_CUDA(h, cudaStreamWaitEvent(h->stream, h->slab.ev_side, 0));
+  return MAVI_OK;
+}
+
+// One step in slab mode.
+//
+// Newton steps with the force carry are pipelined over two streams.  Per step n, in steady state:
+//   side : ... [C(n-1): halo positions + layout] [boundary recompute(n-1)] [A(n): drifted halo]  K_bnd(n)
+//   main : step_begin(n)  K_int(n)  | wait side |  wall fix-ups, B(n): emigrant records, ingest, tile repair, re-drift,
+//          list-driven recompute of the interior
+// K_int = the blocks that read no halo column, K_bnd = the first / last block of every tile row.  The interior work of
+// step n+1 never touches the two owned columns next to a halo, so the exchanges C and A and the recomputation of those
+// columns (always done in full: the neighbour's boundary column re-bins behind this rank's back) overlap with K_int.
+// Communicator operations stay totally ordered by the events (B(n) -> C(n) -> A(n+1) -> B(n+1)), identically on all ranks.
 int slab_step_once(Handle *h, const double *noise_dev) {
   DevParams &p = h->p;
   DevArrays &a = h->a;
+  SlabState &s = h->slab;
   LaunchCtx c = h->ctx();
+  LaunchCtx cside = c;
+  cside.stream = s.side;
   int st;
+  static const long long trace_step = getenv("MAVI_SLAB_TRACE") ? atoll(getenv("MAVI_SLAB_TRACE")) : -1;
+  SlabTrace tr;
+  if (h->num_steps == trace_step) { cudaStreamSynchronize(h->stream); cudaStreamSynchronize(s.side); tr.begin(); }
+  tr.mark(0, h->stream);
   if ((st = h->pending_out_of_grid())) return st;
   const bool vel = h->second_kind == SECOND_VEL;
-  if (h->prof) cudaEventRecord(h->ev[0], h->stream);
-  launch_step_begin(c, a);
-  if (h->prof) cudaEventRecord(h->ev[1], h->stream);
   // force carry (see k_newton_b): F1 and the drift of this step were produced by the previous one
   const bool carry = vel && !(h->flags_cfg & MAVI_FLAG_NO_FORCE_CARRY);
-  if (vel) {
+  static const bool nopipe = getenv("MAVI_SLAB_NOPIPE") != nullptr;  // debugging aid: everything on the main stream
+  const bool piped = carry && !nopipe && p.blk_per_row >= 4 && p.blk_cols >= 3 && s.m >= 8;
+  if (h->prof) cudaEventRecord(h->ev[0], h->stream);
+  launch_step_begin(c, a);
+  tr.mark(1, h->stream);
+  if (h->prof) cudaEventRecord(h->ev[1], h->stream);
+  if (piped) {
+    if (!h->carry_valid) {
+      // prime the pipeline: full first pass, then the drifted halo on the side stream
+      if ((st = slab_join(h))) return st;
+      launch_newton_a(c, p, a);
+      SLAB_CUDA(h, cudaEventRecord(s.ev_ready, h->stream));
+      SLAB_CUDA(h, cudaStreamWaitEvent(s.side, s.ev_ready, 0));
+      if ((st = slab_halo_exchange(h, a.pos[1], false, s.side))) return st;
+      s.side_busy = true;
+    }
+    if (h->prof) cudaEventRecord(h->ev[2], h->stream);
+    SLAB_CUDA(h, cudaEventRecord(s.ev_begin, h->stream));  // FLAG_RAN and the per-step counters of this step are set
+    SLAB_CUDA(h, cudaStreamWaitEvent(s.side, s.ev_begin, 0));
+    tr.mark(8, s.side);
+    launch_newton_b(cside, p, a, true, 2);  // blocks next to a halo column, after A on the side stream
+    tr.mark(10, s.side);
+    SLAB_CUDA(h, cudaEventRecord(s.ev_halo, s.side));
+    launch_newton_b(c, p, a, true, 1);
+    tr.mark(2, h->stream);
+    SLAB_CUDA(h, cudaStreamWaitEvent(h->stream, s.ev_halo, 0));
+    launch_apply_pos_fixes(c, a);
+    tr.mark(3, h->stream);
+  } else if (vel) {
     if (!carry || !h->carry_valid) launch_newton_a(c, p, a);      // owned: pos[0] -> pos[1], F1
     if (h->prof) cudaEventRecord(h->ev[2], h->stream);
     if ((st = slab_halo_exchange(h, a.pos[1], false))) return st; // drifted halo positions, same (stale) layout
+    tr.mark(8, h->stream);
     launch_newton_b(c, p, a, carry);
+    tr.mark(3, h->stream);
   } else {
     if (h->prof) cudaEventRecord(h->ev[2], h->stream);
     launch_self_propelled(c, p, a, noise_dev, (unsigned long long)h->num_steps);
@@ -350,17 +480,36 @@ int slab_step_once(Handle *h, const double *noise_dev) {
   if (h->prof) cudaEventRecord(h->ev[3], h->stream);
   // update_chunks! for the next step: emigrants -> neighbours, immigrants queued as movers, ONE incremental repair
   if ((st = slab_migrate(h, carry))) return st;
+  tr.mark(4, h->stream);
   launch_repair_tiles(c, p, a, vel);
   if (carry) launch_carry_redrift(c, p, a);
+  tr.mark(5, h->stream);
   h->time += p.dt;
   h->num_steps += 1;
   // (no host synchronisation here: the owned count and the overflow word are read by slab_sync_counts)
-  if ((st = slab_halo_exchange(h, a.pos[0], true))) return st;
-  if (carry) {  // needs the fresh halo (positions + layout)
-    launch_carry_recompute(c, p, a);
+  if (piped) {
+    SLAB_CUDA(h, cudaEventRecord(s.ev_ready, h->stream));
+    launch_carry_recompute_list(c, p, a, 3);  // interior: leaves the halo and the two owned columns next to it alone
+    tr.mark(7, h->stream);
+    SLAB_CUDA(h, cudaStreamWaitEvent(s.side, s.ev_ready, 0));
+    if ((st = slab_halo_exchange(h, a.pos[0], true, s.side))) return st;  // C: fresh halo positions + layout
+    tr.mark(6, s.side);
+    launch_carry_recompute_columns(cside, p, a, 2, false);
+    if ((st = slab_halo_exchange(h, a.pos[1], false, s.side))) return st;  // A of the next step: drifted halo
+    tr.mark(9, s.side);
+    s.side_busy = true;
     h->carry_valid = true;
+  } else {
+    if ((st = slab_halo_exchange(h, a.pos[0], true))) return st;
+    tr.mark(6, h->stream);
+    if (carry) {  // needs the fresh halo (positions + layout)
+      launch_carry_recompute(c, p, a);
+      h->carry_valid = true;
+    }
+    tr.mark(7, h->stream);
   }
   if (h->prof) cudaEventRecord(h->ev[4], h->stream);
+  tr.end(s.rank, h->stream, s.side, a.flags, p);
   return MAVI_OK;
 }
 

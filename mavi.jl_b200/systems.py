@@ -59,9 +59,10 @@ class System:
         self._forces = None
         self._check(self._lib.mavi_create(C.byref(self._lowered.params), C.byref(self._h)))
         self._check(self._lib.mavi_set_time(self._h, self.time_info.num_steps, self.time_info.time))
-        self._slab = int_cfg.device.world > 1
+        self._slab = int_cfg.device.world > 1 or bool(int_cfg.device.flags & capi.FLAG_SLAB_SELF)
         if self._slab:
-            self.local_ids = np.ascontiguousarray(getattr(state, "ids"), dtype=np.int64)
+            ids = getattr(state, "ids", None)
+            self.local_ids = np.ascontiguousarray(np.arange(self._n) if ids is None else ids, dtype=np.int64)
             self.upload_local()
         else:
             self.upload_state()

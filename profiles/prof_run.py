@@ -14,8 +14,9 @@ pkg = entry.load_package()
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 kind = sys.argv[3] if len(sys.argv) > 3 else "lj"
-if kind == "lj":
-    w = bench.lj_workload(pkg, nx, nx)
+if kind in ("lj", "ljself"):
+    # ljself: the x-slab machinery on one GPU (MAVI_FLAG_SLAB_SELF), for profiling the multi-GPU step on one rank
+    w = bench.lj_workload(pkg, nx, nx, cuda_device=pkg.CUDADevice(flags=pkg.capi.FLAG_SLAB_SELF) if kind == "ljself" else None)
     s = pkg.System(state=pkg.SecondLawState(pos=w["pos"], vel=w["vel"]), space_cfg=w["space"], dynamic_cfg=w["dyn"], int_cfg=w["int_cfg"])
     n = nx * nx
 elif kind == "szabo":

@@ -18,6 +18,7 @@ from mavi_jl_b200 import slabs  # noqa: E402
 
 def main():
     kind, steps = sys.argv[1], int(sys.argv[2])
+    base_flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
     dist.init_process_group("gloo")
@@ -36,7 +37,7 @@ def main():
     uid = [slabs.nccl_unique_id() if rank == 0 else None, slabs.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     dev = pkg.CUDADevice(device=local_rank, rank=rank, world=world, nccl_unique_id=uid[0], n_global=len(st0.pos),
-                         rng_mode="host_noise")
+                         rng_mode="host_noise", flags=base_flags)
     int_cfg = pkg.IntCfg(dt=case["int_cfg"].dt, chunks_cfg=ccfg, device=dev)
     if kind in ("lj", "harm"):
         state = pkg.SecondLawState(pos=st0.pos[mine], vel=st0.vel[mine])
@@ -51,7 +52,7 @@ def main():
     if kind in ("lj", "harm"):
         # force carry (default) vs the full first pass every step: bit-identical, also across slab boundaries
         dev2 = pkg.CUDADevice(device=local_rank, rank=rank, world=world, nccl_unique_id=uid[1], n_global=len(st0.pos),
-                              rng_mode="host_noise", flags=pkg.capi.FLAG_NO_FORCE_CARRY)
+                              rng_mode="host_noise", flags=base_flags | pkg.capi.FLAG_NO_FORCE_CARRY)
         st2 = pkg.SecondLawState(pos=st0.pos[mine], vel=st0.vel[mine])
         st2.ids = mine
         sys2 = pkg.System(state=st2, space_cfg=case["space"], dynamic_cfg=case["dyn"],

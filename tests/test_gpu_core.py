@@ -398,6 +398,21 @@ def test_force_carry_bitwise(cuda_lib, kind):
         assert a.rebuild_count() > 0
 
 
+@pytest.mark.parametrize("dyn,wall", [("lj", "periodic"), ("harm", "rigid")])
+def test_small_blocks_agree(cuda_lib, dyn, wall):
+    """MAVI_FLAG_SMALL_BLOCKS (3 tile columns per CTA: many blocks per tile row, side columns shared between blocks) gives
+    bit-identical results to the default block size."""
+    case = H.newton_case(nx=64, ny=40, dyn=DYNS[dyn], wall=wall, jitter=0.3, vmax=2.0, dt=0.002)
+    a = H.make_gpu(_with_flags(case, 0))
+    b = H.make_gpu(_with_flags(case, pkg.capi.FLAG_SMALL_BLOCKS))
+    a.step(60)
+    b.step(60)
+    a.sync_to_host()
+    b.sync_to_host()
+    assert np.array_equal(a.state.pos, b.state.pos) and np.array_equal(a.state.vel, b.state.vel)
+    assert np.array_equal(a.get_forces(), b.get_forces())
+
+
 def test_kernels_actually_launch(cuda_lib):
     g = H.make_gpu(H.newton_case(nx=16, ny=16))
     n0 = g.launch_count()
@@ -426,3 +441,39 @@ def test_c2_one_million_properties(cuda_lib):
     assert np.array_equal(cell[ids], np.repeat(np.arange(len(counts)), counts))  # sorted by cell
     seg = ids[start[12345]:start[12345 + 50]]
     assert np.all(np.diff(cell[seg]) >= 0)
+
+
+# ---------------------------------------------------------------- the x-slab machinery on ONE GPU (MAVI_FLAG_SLAB_SELF)
+@pytest.mark.parametrize("kind,flags", [("lj", 0), ("lj", 8), ("harm", 8), ("szabo", 0)])
+def test_slab_self_mode_matches_plain(cuda_lib, kind, flags):
+    """One-rank slab mode: halo columns, the two-stream step pipeline (flags=8: several CTAs per tile row), boundary
+    recompute and local copies in place of NCCL.  Must reproduce the plain single-domain run: bit-identical for the
+    Newton dynamics, to rounding for Szabo (the minimum image is applied through the seam)."""
+    SELF = pkg.capi.FLAG_SLAB_SELF
+    if kind == "szabo":
+        case = H.sp_case("szabo", nx=40, ny=30, rot_diff=0.0)
+        ic = case["int_cfg"]
+        mkdev = lambda f: pkg.CUDADevice(rng_mode="host_noise", flags=f)  # noqa: E731
+    else:
+        case = H.newton_case(nx=64, ny=40, dyn=DYNS[kind], wall="periodic", jitter=0.3, vmax=3.0, dt=0.002)
+        ic = case["int_cfg"]
+        mkdev = lambda f: pkg.CUDADevice(flags=f)  # noqa: E731
+    a_case, b_case = dict(case), dict(case)
+    a_case["int_cfg"] = pkg.IntCfg(dt=ic.dt, chunks_cfg=ic.chunks_cfg, device=mkdev(flags))
+    b_case["int_cfg"] = pkg.IntCfg(dt=ic.dt, chunks_cfg=ic.chunks_cfg, device=mkdev(flags | SELF))
+    a = H.make_gpu(a_case)
+    b = H.make_gpu(b_case)
+    n = len(a.state.pos)
+    for steps in (1, 33, 80):
+        a.step(steps)
+        b.step(steps)
+        a.sync_to_host()
+        ids, pos, second, forces = b.download_local()
+        assert len(ids) == n and np.array_equal(np.sort(ids), np.arange(n))
+        o = np.argsort(ids)
+        if kind == "szabo":
+            assert np.abs(pos[o] - a.state.pos).max() / case["geom"].length < 1e-12
+        else:
+            assert np.array_equal(pos[o], a.state.pos)
+            assert np.array_equal(second[o], a.state.vel)
+            assert np.array_equal(forces[o], a.get_forces())

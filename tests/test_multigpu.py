@@ -120,16 +120,17 @@ def _ngpus():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("flags", [0, 8])  # 8 = MAVI_FLAG_SMALL_BLOCKS: several CTAs per tile row -> halo exchange overlapped with interior blocks
 @pytest.mark.parametrize("kind,steps", [("lj", 150), ("harm", 150), ("szabo", 40)])  # overlapping Szabo particles are chaotic: short horizon
-def test_multigpu_slabs_match_oracle(cuda_lib, kind, steps):
+def test_multigpu_slabs_match_oracle(cuda_lib, kind, steps, flags):
     n = _ngpus()
     if n < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     world = 4 if n >= 4 else 2
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", NCCL_DEBUG="WARN")
-    port = 29533 + {"lj": 0, "harm": 1, "szabo": 2}[kind]
+    port = 29533 + {"lj": 0, "harm": 1, "szabo": 2}[kind] + (3 if flags else 0)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
-           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py"), kind, str(steps)]
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py"), kind, str(steps), str(flags)]
     # own process group, so that a hung rank can be killed by its exact pgid without touching anything else
     proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, start_new_session=True)
     try:
