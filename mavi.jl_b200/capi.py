@@ -136,7 +136,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("MAVI_LIB_PATH") or LIB_PATH  # MAVI_LIB_PATH: A/B runs against another build
     if not os.path.exists(path):
         raise FileNotFoundError(
             f"{path} not found: build it with __graft_entry__.build() / make -C mavi.jl_b200/csrc. "

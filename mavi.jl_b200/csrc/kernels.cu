@@ -947,7 +947,8 @@ struct MoverSink {
   int *cell, *tile_dirty, *dirty_list, *inbox_cnt, *inbox, *mv_src, *flags;
   int *chg;  // changed-cell list of the force carry (nullptr: not recorded)
   // slab mode: emigrant records towards the left [0] / right [1] neighbour
-  EmRec *em[2];
+  EmRec *em0, *em1;  // (two scalars, not an array: a dynamically indexed member would force the whole kernel parameter
+                     // struct into local memory, one copy per thread)
   int em_cap;
   const unsigned int *idflag;
 };
@@ -969,16 +970,10 @@ __device__ __forceinline__ void note_changed_cells(const DevParams &p, const Mov
   }
 }
 
-// `fixed`: walls! moved the particle (periodic wrap, slippery projection) after the pair pass read its position.
-// second_of(): the particle's second state record (velocity / angle) after this step — only evaluated for a particle
-// that leaves the rank (slab mode), together with `force`, to fill its emigrant record.
-template <typename SecondF>
-__device__ __forceinline__ void note_if_moved(const DevParams &p, const MoverSink &ms, int k, int c_old, double x,
-                                              double y, bool fixed, double2 force, SecondF &&second_of) {
-  if (still_in_cell(p, x, y, c_old)) {
-    if (fixed) note_changed_cells(p, ms, c_old, c_old);
-    return;
-  }
+// The particle in slot k (binned under c_old) is no longer inside that cell: the rare path of note_if_moved, kept out
+// of line so that it costs the hot kernels no registers.
+__device__ __noinline__ void note_moved_slow(const DevParams &p, const MoverSink &ms, int k, int c_old, double x, double y,
+                                            bool fixed, double2 force, double2 second) {
   int c_new = cell_of_point(p, x, y);
   if (c_new < 0) {  // left the grid: the reference throws BoundsError at its NEXT update_chunks! -> reported then
     atomicOr(&ms.flags[FLAG_ERR], ERRBIT_OOG_PENDING);
@@ -998,9 +993,9 @@ __device__ __forceinline__ void note_if_moved(const DevParams &p, const MoverSin
       const int d = lc == 0 ? 0 : 1;
       const int i = atomicAdd(&ms.flags[FLAG_NEM0 + d], 1);
       if (i < ms.em_cap) {
-        EmRec &e = ms.em[d][i];
+        EmRec &e = (d == 0 ? ms.em0 : ms.em1)[i];
         e.pos = make_double2(x, y);
-        e.second = second_of();
+        e.second = second;
         e.force = force;
         e.idflag = ms.idflag[k];
       } else {
@@ -1020,6 +1015,22 @@ __device__ __forceinline__ void note_if_moved(const DevParams &p, const MoverSin
       atomicOr(&ms.flags[FLAG_OVERFLOW], m < p.mv_cap ? 2 : 4);
     }
   }
+}
+
+// The particle in slot k (sorted under cell c_old) now sits at (x, y).  If update_particle_chunk! would bin it
+// elsewhere, record its fresh cell, mark the tiles involved for the incremental repair and queue it in the destination
+// tile's inbox (or, in slab mode, in the emigrant records of the neighbour rank it moves to).
+// `fixed`: walls! moved the particle (periodic wrap, slippery projection) after the pair pass read its position.
+// second_of(): the particle's second state record (velocity / angle) after this step — only evaluated for a particle
+// that left its cell, to fill the emigrant record together with `force`.
+template <typename SecondF>
+__device__ __forceinline__ void note_if_moved(const DevParams &p, const MoverSink &ms, int k, int c_old, double x,
+                                              double y, bool fixed, double2 force, SecondF &&second_of) {
+  if (still_in_cell(p, x, y, c_old)) {
+    if (fixed) note_changed_cells(p, ms, c_old, c_old);
+    return;
+  }
+  note_moved_slow(p, ms, k, c_old, x, y, fixed, force, second_of());
 }
 
 // Drift of update_verlet! (src/integration.jl:424): pos + vel dt + F dt^2/2, written with explicit FMAs so that every
@@ -1628,7 +1639,8 @@ template <int DYN, bool PER, bool CARRY, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) k_newton_b2(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
                             const double2 *__restrict__ pos_in, double2 *__restrict__ vel, const double2 *f1,
                             double2 *f2, double2 *f1_next, double2 *__restrict__ pos_next,
-                            int *__restrict__ fix_idx, double2 *__restrict__ fix_pos, const MoverSink ms) {
+                            int *__restrict__ fix_idx, double2 *__restrict__ fix_pos,
+                            const __grid_constant__ MoverSink ms) {
   if (!ms.flags[FLAG_RAN]) return;
   // slab mode, blocks next to a halo column (blk_mode 2): their boundary particles are re-drifted on the side stream
   // without a big-drift report -> always the exact minimum-image path there
@@ -1668,7 +1680,8 @@ template <int DYN, bool PER>
 __global__ void __launch_bounds__(TPB) k_self_propelled2(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
                                   const unsigned int *__restrict__ idflag, const double2 *__restrict__ pos_in,
                                   double *__restrict__ ang, double2 *__restrict__ pos_out, double2 *__restrict__ force,
-                                  const double *__restrict__ noise, unsigned long long step, const MoverSink ms) {
+                                  const double *__restrict__ noise, unsigned long long step,
+                                  const __grid_constant__ MoverSink ms) {
   if (!ms.flags[FLAG_RAN]) return;
   for_each_block_particle<DYN, PER>(p, tstart, pos_in, ms.cell, false,
     [&](int k) { prefetch_l1(ang + k); prefetch_l1(idflag + k); },
@@ -1708,7 +1721,7 @@ __global__ void __launch_bounds__(TPB) k_self_propelled2(const __grid_constant__
   } while (0)
 
 static MoverSink mover_sink(const DevArrays &a) {
-  return MoverSink{a.cell, a.tile_dirty, a.dirty_list, a.inbox_cnt, a.inbox, a.mv_src, a.flags, nullptr, {a.em_send[0], a.em_send[1]}, a.em_cap, a.idflag};
+  return MoverSink{a.cell, a.tile_dirty, a.dirty_list, a.inbox_cnt, a.inbox, a.mv_src, a.flags, nullptr, a.em_send[0], a.em_send[1], a.em_cap, a.idflag};
 }
 
 void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool with_wall_forces) {
