@@ -79,35 +79,89 @@ def lj_workload(pkg, nx, ny, cuda_device=None, chunks=True, rank=0, world=1):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML (nvidia_ml_py) is
+    polled every ~5 ms so that a 0.1 s timed region still gets tens of samples; `nvidia-smi` (one sample per ~0.1 s
+    process start) is the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+        self.index, self.uuid, self.samples, self.stop_flag = index, uuid, [], threading.Event()
+        self.source = "nvidia-smi"
+        self.t_begin = self.t_end = None  # samples outside [t_begin, t_end] (perf_counter) are dropped when both are set
 
-    def run(self):
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
+
+    def _nvml_loop(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = None
+        if self.uuid:
+            for u in (self.uuid, self.uuid.encode()):
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(u)
+                    break
+                except Exception:
+                    h = None
+        if h is None:
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+        nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)  # fail here (-> fallback) rather than inside the loop
+        self.source = "nvml"
+        while not self.stop_flag.is_set():
+            sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            try:
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1e3
+            except Exception:
+                pw = 0.0
+            try:
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                r = 0
+            self.samples.append((time.perf_counter(), sm, mx, pw, [bool(r & b) for b in bits]))
+            self.stop_flag.wait(0.005)
+
+    def _smi_loop(self):
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                    s = [x.strip() for x in out.split(",")]
+                    self.samples.append((time.perf_counter(), float(s[0]), float(s[1]), float(s[2]),
+                                         [s[3 + i].lower().startswith("active") for i in range(4)]))
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02)
+
+    def run(self):
+        try:
+            self._nvml_loop()
+        except Exception:
+            self.source = "nvidia-smi"
+            self._smi_loop()
 
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
-        if not self.samples:
+        smp = self.samples
+        if self.t_begin is not None and self.t_end is not None:
+            inside = [s for s in smp if self.t_begin <= s[0] <= self.t_end]
+            smp = inside or smp  # a region shorter than one sampling period keeps the nearest samples
+        if not smp:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(sm)}
+        sm = sorted(s[1] for s in smp)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[4][i] for s in smp)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": smp[0][2], "reasons": reasons,
+                "power_w_max": max(s[3] for s in smp), "samples": len(sm), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------- CPU arm
@@ -192,14 +246,20 @@ def run_ours(args):
     system.step(args.warmup)
     system.set_profiling(True)
     launches0 = system.launch_count()
-    sampler = ClockSampler(local_rank)
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local_rank, uuid)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record()
     system.step(args.steps)
     e1.record()
     barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
     clocks = sampler.summary()
     launches = system.launch_count() - launches0
@@ -213,23 +273,33 @@ def run_ours(args):
 
     # ---- end to end through host buffers (`e2e`) -------------------------------------------------------
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
-    if world == 1:
+    slab_api = world > 1 or bool(args.flags & pkg.capi.FLAG_SLAB_SELF)
+    if not slab_api:
         pin_pos = torch.empty((n, 2), dtype=torch.float64).pin_memory()
         pin_vel = torch.empty((n, 2), dtype=torch.float64).pin_memory()
         system.sync_to_host()
         pin_pos.numpy()[...] = system.state.pos
         pin_vel.numpy()[...] = system.state.vel
         system.state.pos, system.state.vel = pin_pos.numpy(), pin_vel.numpy()
+        h2d = d2h = 32 * n
 
         def e2e_step():
             system.upload_state()   # H2D pos+vel from pinned memory (+ constructor-time checks and binning)
             system.step(1)
             system.sync_to_host()   # D2H pos+vel into pinned memory
     else:
+        # slab mode: the owned set changes with migration, so ids travel with pos+vel; pinned buffers sized for the
+        # staging capacity, forces are not downloaded
+        cap = int(n * 1.25) + 4096
+        pin = (torch.empty(cap, dtype=torch.int64).pin_memory(), torch.empty((cap, 2), dtype=torch.float64).pin_memory(),
+               torch.empty((cap, 2), dtype=torch.float64).pin_memory())
+        out = tuple(t_.numpy() for t_ in pin)
+        h2d = d2h = 40 * n
+
         def e2e_step():
-            ids, pos, vel, _ = system.download_local()   # D2H ids+pos+vel(+forces) of the owned particles
+            ids, pos, vel, _ = system.download_local(out=out, want_forces=False)   # D2H ids+pos+vel of the owned particles
             system.local_ids, system.state.pos, system.state.vel = ids, pos, vel
-            system.upload_local()                        # H2D, re-binning, first halo exchange
+            system.upload_local()                        # H2D from the same pinned buffers, re-binning, first halo exchange
             system.step(1)
 
     e2e_step()
@@ -304,8 +374,10 @@ def run_ours(args):
                      "phase_ms": {"pass_a": phase_ms[1], "pass_b": phase_ms[2], "repair_exchange": phase_ms[3]}},
         "cpu_baseline": cpu,
         "two_pass": two_pass,
-        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 32 * n,
-                "steps": e2e_steps, "what": "per step: mavi_upload_state(pos,vel from pinned host) + mavi_step(1) + mavi_download_state(pos,vel)"},
+        "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                "steps": e2e_steps,
+                "what": ("per step and rank: mavi_download_local(ids,pos,vel into pinned host) + mavi_upload_local(ids,pos,vel) + mavi_step(1)"
+                         if slab_api else "per step: mavi_upload_state(pos,vel from pinned host) + mavi_step(1) + mavi_download_state(pos,vel)")},
         "gpu_launches": launches,
         "clocks": clocks,
     }

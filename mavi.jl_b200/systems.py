@@ -107,13 +107,25 @@ class System:
         self._check(self._lib.mavi_local_count(self._h, C.byref(n)))
         return n.value
 
-    def download_local(self):
-        """Slab mode: (ids, pos, second, forces) of the particles this rank currently owns."""
+    def download_local(self, out=None, want_forces=True):
+        """Slab mode: (ids, pos, second, forces) of the particles this rank currently owns.  `out` = (ids, pos, second)
+        preallocated arrays with room for at least the owned count (e.g. pinned buffers): the download goes straight into
+        their prefix and views of it are returned.  want_forces=False skips the force download (forces is None)."""
         n = self.local_count()
-        ids = np.empty(n, dtype=np.int64)
-        pos = np.empty((n, 2), dtype=self._dtype)
-        second = np.empty((n, 2) if self.state.second.ndim == 2 else (n,), dtype=self._dtype)
-        forces = np.empty((n, 2), dtype=self._dtype)
+        sshape = (n, 2) if self.state.second.ndim == 2 else (n,)
+        if out is None:
+            ids = np.empty(n, dtype=np.int64)
+            pos = np.empty((n, 2), dtype=self._dtype)
+            second = np.empty(sshape, dtype=self._dtype)
+        else:
+            ids, pos, second = out[0][:n], out[1][:n], out[2][:n]
+            ok = (ids.dtype == np.int64 and pos.dtype == self._dtype and second.dtype == self._dtype and
+                  pos.shape == (n, 2) and second.shape == sshape and len(ids) == n and
+                  all(a.flags["C_CONTIGUOUS"] and a.flags["WRITEABLE"] for a in (ids, pos, second)))
+            if not ok:
+                raise ValueError("download_local(out=...): need writable C-contiguous (ids int64[>=n], pos T[>=n,2], "
+                                 f"second T[>=n{',2' if len(sshape) == 2 else ''}]) with n = {n}")
+        forces = np.empty((n, 2), dtype=self._dtype) if want_forces else None
         self._check(self._lib.mavi_download_local(self._h, _ptr(ids), _ptr(pos), _ptr(second), _ptr(forces)))
         return ids, pos, second, forces
 
