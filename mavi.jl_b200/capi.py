@@ -118,7 +118,7 @@ class MaviError(RuntimeError):
 
 def build_library(verbose=False):
     """Compile csrc/ for sm_100a with nvcc (cross-compiles without a GPU)."""
-    cmd = ["make", "-C", CSRC]
+    cmd = ["make", "-j", str(min(8, os.cpu_count() or 1)), "-C", CSRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout[-4000:])

@@ -8,10 +8,11 @@
 #include <vector>
 
 #include "handle.cuh"
+#include "api_decl.inc"
 
-using namespace mavi;
+using namespace MAVI_NS;
 
-namespace mavi {
+namespace MAVI_NS {
 
 void Handle::set_error(const char *fmt, ...) {
   va_list ap;
@@ -30,15 +31,15 @@ void Handle::set_error(const char *fmt, ...) {
   } while (0)
 
 // largest x with fl(sqrt(x)) <= d  ->  (sqrt(r2) > d)  <=>  (r2 > x), exactly
-static double sqrt_le_threshold(double d) {
-  double x = d * d;
+static real sqrt_le_threshold(real d) {
+  real x = d * d;
   while (std::sqrt(x) <= d) x = std::nextafter(x, INFINITY);
   while (std::sqrt(x) > d) x = std::nextafter(x, -INFINITY);
   return x;
 }
 // smallest x with fl(sqrt(x)) >= d  ->  (sqrt(r2) < d)  <=>  (r2 < x), exactly
-static double sqrt_ge_threshold(double d) {
-  double x = d * d;
+static real sqrt_ge_threshold(real d) {
+  real x = d * d;
   while (std::sqrt(x) >= d && x > 0) x = std::nextafter(x, -INFINITY);
   while (std::sqrt(x) < d) x = std::nextafter(x, INFINITY);
   return x;
@@ -69,9 +70,9 @@ static int validate_and_lower(Handle *h, const MaviParams *mp) {
     h->set_error("MaviParams.struct_size %u != %zu (ABI mismatch)", mp->struct_size, sizeof(MaviParams));
     return MAVI_ERR_BAD_PARAMS;
   }
-  if (mp->dtype != MAVI_F64) {
-    h->set_error("Float32 mode is not built in this version of libmavi_cuda.so");
-    return MAVI_ERR_UNSUPPORTED;
+  if (mp->dtype != (MAVI_REAL_IS_F32 ? MAVI_F32 : MAVI_F64)) {  // capi.cu routes by dtype
+    h->set_error("MaviParams.dtype %d reached the %s build", mp->dtype, MAVI_REAL_IS_F32 ? "Float32" : "Float64");
+    return MAVI_ERR_BAD_PARAMS;
   }
   if (mp->n < 0 || mp->n > 0x7fffffff || mp->n_spaces < 1 || mp->n_spaces > MAVI_MAX_SPACES) {
     h->set_error("bad n / n_spaces");
@@ -265,7 +266,7 @@ static int allocate(Handle *h) {
   CUDA_TRY(h, cudaMallocHost((void **)&h->flags_host, FLAG_COUNT * sizeof(int)));
   CUDA_TRY(h, cudaMemsetAsync(a.flags, 0, FLAG_COUNT * sizeof(int), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(a.count, 0, nc * sizeof(int), h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(a.st_force, 0, n * sizeof(double2), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(a.st_force, 0, n * sizeof(real2), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(a.cta_first, 0, (n / RPB + 2) * sizeof(int), h->stream));
   if (h->second_kind == SECOND_RING_POL) return rings_allocate(h);
   return MAVI_OK;
@@ -349,8 +350,8 @@ int Handle::alloc_state(int n_active, int cap) {
   if ((st = dev_alloc(this, &A.mv_cell, mv))) return st;
   if ((st = dev_alloc(this, &A.chg, (size_t)p.chg_cap + 2))) return st;
   carry_valid = false;
-  CUDA_TRY(this, cudaMemsetAsync(A.force_old, 0, ns * sizeof(double2), stream));
-  CUDA_TRY(this, cudaMemsetAsync(A.pos[1], 0, ns * sizeof(double2), stream));
+  CUDA_TRY(this, cudaMemsetAsync(A.force_old, 0, ns * sizeof(real2), stream));
+  CUDA_TRY(this, cudaMemsetAsync(A.pos[1], 0, ns * sizeof(real2), stream));
   return MAVI_OK;
 }
 
@@ -382,10 +383,10 @@ int Handle::rebuild_from_staging(int n_active) {
     if (p.num_cells == 0) {
       // chunks === nothing: slots are the original order; plain copies
       const size_t n = (size_t)p.n;
-      CUDA_TRY(this, cudaMemcpyAsync(a.pos[0], a.st_pos, n * sizeof(double2), cudaMemcpyDeviceToDevice, stream));
-      if (second_is_vel) CUDA_TRY(this, cudaMemcpyAsync(a.vel, a.st_vel, n * sizeof(double2), cudaMemcpyDeviceToDevice, stream));
-      else if (second_kind == SECOND_ANGLE) CUDA_TRY(this, cudaMemcpyAsync(a.ang, a.st_ang, n * sizeof(double), cudaMemcpyDeviceToDevice, stream));
-      CUDA_TRY(this, cudaMemcpyAsync(a.force, a.st_force, n * sizeof(double2), cudaMemcpyDeviceToDevice, stream));
+      CUDA_TRY(this, cudaMemcpyAsync(a.pos[0], a.st_pos, n * sizeof(real2), cudaMemcpyDeviceToDevice, stream));
+      if (second_is_vel) CUDA_TRY(this, cudaMemcpyAsync(a.vel, a.st_vel, n * sizeof(real2), cudaMemcpyDeviceToDevice, stream));
+      else if (second_kind == SECOND_ANGLE) CUDA_TRY(this, cudaMemcpyAsync(a.ang, a.st_ang, n * sizeof(real), cudaMemcpyDeviceToDevice, stream));
+      CUDA_TRY(this, cudaMemcpyAsync(a.force, a.st_force, n * sizeof(real2), cudaMemcpyDeviceToDevice, stream));
       CUDA_TRY(this, cudaMemcpyAsync(a.idflag, a.st_id, n * sizeof(unsigned int), cudaMemcpyDeviceToDevice, stream));
       return MAVI_OK;
     }
@@ -448,7 +449,7 @@ int Handle::check_device_flags() {
 }
 
 // Enqueue one step (no host synchronisation).  newton_step! / szabo_step! / rtp_step!, src/integration.jl:507-535.
-int Handle::enqueue_step(const double *noise_dev) {
+int Handle::enqueue_step(const real *noise_dev) {
   int st;
   LaunchCtx c = ctx();
   const bool second_is_vel = second_kind == SECOND_VEL;
@@ -486,14 +487,14 @@ int Handle::enqueue_step(const double *noise_dev) {
 // pushed a particle out of the grid) latches a flag that turns every later kernel into a no-op; the device-side step
 // counter tells how many steps really ran, the host rolls its clock and the ping-pong parity back, grows the tiles and
 // resumes.
-int Handle::run_steps(long long nsteps, const double *noise_dev, size_t stride) {
+int Handle::run_steps(long long nsteps, const real *noise_dev, size_t stride) {
   constexpr int SYNC_EVERY = 32;
   long long done_total = 0;
   int st;
   while (done_total < nsteps) {
     if ((st = pending_out_of_grid())) return st;
     if (p.dynamics == MAVI_DYN_RINGS || p.slab) {  // these paths synchronise every step themselves
-      const double *nz = noise_dev ? noise_dev + (size_t)done_total * stride : nullptr;
+      const real *nz = noise_dev ? noise_dev + (size_t)done_total * stride : nullptr;
       st = p.slab ? slab_step_once(this, nz) : rings_step(this, nz);
       if (st) return st;
       done_total += 1;
@@ -543,19 +544,22 @@ int Handle::run_steps(long long nsteps, const double *noise_dev, size_t stride) 
   return MAVI_OK;
 }
 
-}  // namespace mavi
+}  // namespace MAVI_NS
 
 // =========================================================================================================
 // C ABI
 // =========================================================================================================
-extern "C" {
+// The entry points of include/mavi.h for THIS arithmetic type (api_<name> == mavi_<name>); capi.cu holds the extern "C"
+// symbols and dispatches on MaviParams.dtype.
+namespace MAVI_NS {
 
-int32_t mavi_abi_version(void) { return MAVI_ABI_VERSION; }
 
-int32_t mavi_create(const MaviParams *params, MaviHandle **out) {
+int32_t api_abi_version(void) { return MAVI_ABI_VERSION; }
+
+int32_t api_create(const MaviParams *params, void **out) {
   if (!params || !out) return MAVI_ERR_BAD_PARAMS;
   Handle *h = new Handle();
-  *out = reinterpret_cast<MaviHandle *>(h);
+  *out = h;
   h->device = params->device;
   h->flags_cfg = params->flags;
   cudaError_t e = cudaSetDevice(h->device);
@@ -582,7 +586,7 @@ int32_t mavi_create(const MaviParams *params, MaviHandle **out) {
   return MAVI_OK;
 }
 
-int32_t mavi_destroy(MaviHandle *hh) {
+int32_t api_destroy(void *hh) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h) return MAVI_OK;
   cudaSetDevice(h->device);
@@ -600,7 +604,7 @@ int32_t mavi_destroy(MaviHandle *hh) {
   return MAVI_OK;
 }
 
-int32_t mavi_last_error(MaviHandle *hh, char *buf, int32_t n) {
+int32_t api_last_error(void *hh, char *buf, int32_t n) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || !buf || n <= 0) return MAVI_ERR_BAD_PARAMS;
   snprintf(buf, (size_t)n, "%s", h->err);
@@ -608,7 +612,7 @@ int32_t mavi_last_error(MaviHandle *hh, char *buf, int32_t n) {
 }
 
 // System ctor tail (src/systems.jl:73-114): ids, inside check, first update_chunks!.
-int32_t mavi_upload_state(MaviHandle *hh, const void *pos, const void *second, const uint8_t *active_mask, int64_t n) {
+int32_t api_upload_state(void *hh, const void *pos, const void *second, const uint8_t *active_mask, int64_t n) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || !pos || n != h->p.n) return MAVI_ERR_BAD_PARAMS;
   if (h->p.slab) {
@@ -619,14 +623,14 @@ int32_t mavi_upload_state(MaviHandle *hh, const void *pos, const void *second, c
   DevArrays &a = h->a;
   LaunchCtx c = h->ctx();
   const size_t sn = (size_t)n;
-  CUDA_TRY(h, cudaMemcpyAsync(a.st_pos, pos, sn * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(a.st_pos, pos, sn * sizeof(real2), cudaMemcpyHostToDevice, h->stream));
   if (second) {
     if (h->second_kind == SECOND_VEL)
-      CUDA_TRY(h, cudaMemcpyAsync(a.st_vel, second, sn * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(a.st_vel, second, sn * sizeof(real2), cudaMemcpyHostToDevice, h->stream));
     else if (h->second_kind == SECOND_ANGLE)
-      CUDA_TRY(h, cudaMemcpyAsync(a.st_ang, second, sn * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(a.st_ang, second, sn * sizeof(real), cudaMemcpyHostToDevice, h->stream));
     else
-      CUDA_TRY(h, cudaMemcpyAsync(a.st_ang, second, (size_t)h->p.rings.num_rings * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(a.st_ang, second, (size_t)h->p.rings.num_rings * sizeof(real), cudaMemcpyHostToDevice, h->stream));
   }
   CUDA_TRY(h, cudaMemsetAsync(a.flags, 0, FLAG_COUNT * sizeof(int), h->stream));
   h->steps_seen = 0;
@@ -641,7 +645,7 @@ int32_t mavi_upload_state(MaviHandle *hh, const void *pos, const void *second, c
     for (size_t i = 0; i < sn; i++) n_active += active_mask[i] != 0;
   }
   launch_init_staging_ids(c, h->p.n, mask_dev, a.st_id);
-  CUDA_TRY(h, cudaMemsetAsync(a.st_force, 0, sn * sizeof(double2), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(a.st_force, 0, sn * sizeof(real2), h->stream));
   if (h->p.n_spaces == 1) launch_check_inside(c, h->p, a);
   int st = h->check_device_flags();
   if (st) return st;
@@ -649,7 +653,7 @@ int32_t mavi_upload_state(MaviHandle *hh, const void *pos, const void *second, c
   return h->check_device_flags();
 }
 
-int32_t mavi_download_state(MaviHandle *hh, void *pos, void *second) {
+int32_t api_download_state(void *hh, void *pos, void *second) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h) return MAVI_ERR_BAD_PARAMS;
   cudaSetDevice(h->device);
@@ -663,32 +667,32 @@ int32_t mavi_download_state(MaviHandle *hh, void *pos, void *second) {
   }
   if (pos) {
     launch_unpermute2(c, h->p, a, a.pos[0], a.st_pos);
-    CUDA_TRY(h, cudaMemcpyAsync(pos, a.st_pos, sn * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(pos, a.st_pos, sn * sizeof(real2), cudaMemcpyDeviceToHost, h->stream));
   }
   if (second) {
     if (h->second_kind == SECOND_VEL) {
       launch_unpermute2(c, h->p, a, a.vel, a.st_vel);
-      CUDA_TRY(h, cudaMemcpyAsync(second, a.st_vel, sn * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(second, a.st_vel, sn * sizeof(real2), cudaMemcpyDeviceToHost, h->stream));
     } else {
       launch_unpermute1(c, h->p, a, a.ang, a.st_ang);
-      CUDA_TRY(h, cudaMemcpyAsync(second, a.st_ang, sn * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(second, a.st_ang, sn * sizeof(real), cudaMemcpyDeviceToHost, h->stream));
     }
   }
   return h->check_device_flags();
 }
 
-int32_t mavi_download_forces(MaviHandle *hh, void *forces) {
+int32_t api_download_forces(void *hh, void *forces) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || !forces) return MAVI_ERR_BAD_PARAMS;
   cudaSetDevice(h->device);
   DevArrays &a = h->a;
   if (h->second_kind == SECOND_RING_POL) return rings_download_forces(h, forces);
   launch_unpermute2(h->ctx(), h->p, a, a.force, a.st_force);
-  CUDA_TRY(h, cudaMemcpyAsync(forces, a.st_force, (size_t)h->p.n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(forces, a.st_force, (size_t)h->p.n * sizeof(real2), cudaMemcpyDeviceToHost, h->stream));
   return h->check_device_flags();
 }
 
-int32_t mavi_local_count(MaviHandle *hh, int64_t *n_local) {
+int32_t api_local_count(void *hh, int64_t *n_local) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || !n_local) return MAVI_ERR_BAD_PARAMS;
   *n_local = h->p.n;
@@ -696,15 +700,15 @@ int32_t mavi_local_count(MaviHandle *hh, int64_t *n_local) {
 }
 
 // ids / state / forces of the particles this rank currently owns (single GPU: everything, in original-id order)
-int32_t mavi_download_local(MaviHandle *hh, int64_t *ids, void *pos, void *second, void *forces) {
+int32_t api_download_local(void *hh, int64_t *ids, void *pos, void *second, void *forces) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h) return MAVI_ERR_BAD_PARAMS;
   if (!h->p.slab) {
     if (ids)
       for (int64_t i = 0; i < h->p.n; i++) ids[i] = i;
-    int st = mavi_download_state(hh, pos, second);
+    int st = api_download_state(hh, pos, second);
     if (st) return st;
-    if (forces) return mavi_download_forces(hh, forces);
+    if (forces) return api_download_forces(hh, forces);
     return MAVI_OK;
   }
   cudaSetDevice(h->device);
@@ -716,12 +720,12 @@ int32_t mavi_download_local(MaviHandle *hh, int64_t *ids, void *pos, void *secon
   }
   const bool vel = h->second_kind == SECOND_VEL;
   launch_compact_to_staging(h->ctx(), h->p, a, vel);
-  if (pos) CUDA_TRY(h, cudaMemcpyAsync(pos, a.st_pos, n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  if (pos) CUDA_TRY(h, cudaMemcpyAsync(pos, a.st_pos, n * sizeof(real2), cudaMemcpyDeviceToHost, h->stream));
   if (second) {
-    if (vel) CUDA_TRY(h, cudaMemcpyAsync(second, a.st_vel, n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
-    else CUDA_TRY(h, cudaMemcpyAsync(second, a.st_ang, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (vel) CUDA_TRY(h, cudaMemcpyAsync(second, a.st_vel, n * sizeof(real2), cudaMemcpyDeviceToHost, h->stream));
+    else CUDA_TRY(h, cudaMemcpyAsync(second, a.st_ang, n * sizeof(real), cudaMemcpyDeviceToHost, h->stream));
   }
-  if (forces) CUDA_TRY(h, cudaMemcpyAsync(forces, a.st_force, n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  if (forces) CUDA_TRY(h, cudaMemcpyAsync(forces, a.st_force, n * sizeof(real2), cudaMemcpyDeviceToHost, h->stream));
   std::vector<unsigned int> idbuf;
   if (ids) {
     idbuf.resize(n);
@@ -734,7 +738,7 @@ int32_t mavi_download_local(MaviHandle *hh, int64_t *ids, void *pos, void *secon
 }
 
 // slab mode upload: the particles whose cell column this rank owns, with their global original ids
-int32_t mavi_upload_local(MaviHandle *hh, const int64_t *ids, const void *pos, const void *second, int64_t n_local) {
+int32_t api_upload_local(void *hh, const int64_t *ids, const void *pos, const void *second, int64_t n_local) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || !pos || !ids || n_local < 0) return MAVI_ERR_BAD_PARAMS;
   if (!h->p.slab) {
@@ -756,15 +760,15 @@ int32_t mavi_upload_local(MaviHandle *hh, const int64_t *ids, const void *pos, c
     }
     id32[i] = (unsigned int)ids[i];
   }
-  CUDA_TRY(h, cudaMemcpyAsync(a.st_pos, pos, sn * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+  CUDA_TRY(h, cudaMemcpyAsync(a.st_pos, pos, sn * sizeof(real2), cudaMemcpyHostToDevice, h->stream));
   if (second) {
     if (h->second_kind == SECOND_VEL)
-      CUDA_TRY(h, cudaMemcpyAsync(a.st_vel, second, sn * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(a.st_vel, second, sn * sizeof(real2), cudaMemcpyHostToDevice, h->stream));
     else
-      CUDA_TRY(h, cudaMemcpyAsync(a.st_ang, second, sn * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(a.st_ang, second, sn * sizeof(real), cudaMemcpyHostToDevice, h->stream));
   }
   CUDA_TRY(h, cudaMemcpyAsync(a.st_id, id32.data(), sn * sizeof(unsigned int), cudaMemcpyHostToDevice, h->stream));
-  CUDA_TRY(h, cudaMemsetAsync(a.st_force, 0, sn * sizeof(double2), h->stream));
+  CUDA_TRY(h, cudaMemsetAsync(a.st_force, 0, sn * sizeof(real2), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(a.flags, 0, FLAG_COUNT * sizeof(int), h->stream));
   h->steps_seen = 0;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -774,16 +778,16 @@ int32_t mavi_upload_local(MaviHandle *hh, const int64_t *ids, const void *pos, c
   return h->check_device_flags();
 }
 
-int32_t mavi_nccl_unique_id(void *out128) {
+int32_t api_nccl_unique_id(void *out128) {
   if (!out128) return MAVI_ERR_BAD_PARAMS;
   return slab_unique_id(out128);
 }
 
-int32_t mavi_step(MaviHandle *hh, int64_t nsteps, const void *host_noise) {
+int32_t api_step(void *hh, int64_t nsteps, const void *host_noise) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || nsteps < 0) return MAVI_ERR_BAD_PARAMS;
   cudaSetDevice(h->device);
-  const double *noise_dev = nullptr;
+  const real *noise_dev = nullptr;
   size_t stride = 0;
   if (host_noise && h->p.rng_mode == MAVI_RNG_HOST_NOISE) {
     switch (h->p.dynamics) {
@@ -796,10 +800,10 @@ int32_t mavi_step(MaviHandle *hh, int64_t nsteps, const void *host_noise) {
     if (total > 0) {
       if (total > h->noise_cap) {
         if (h->noise_dev) cudaFree(h->noise_dev);
-        CUDA_TRY(h, cudaMalloc((void **)&h->noise_dev, total * sizeof(double)));
+        CUDA_TRY(h, cudaMalloc((void **)&h->noise_dev, total * sizeof(real)));
         h->noise_cap = total;
       }
-      CUDA_TRY(h, cudaMemcpyAsync(h->noise_dev, host_noise, total * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(h->noise_dev, host_noise, total * sizeof(real), cudaMemcpyHostToDevice, h->stream));
       noise_dev = h->noise_dev;
     }
   }
@@ -811,7 +815,7 @@ int32_t mavi_step(MaviHandle *hh, int64_t nsteps, const void *host_noise) {
   return h->check_device_flags();
 }
 
-int32_t mavi_calc_forces(MaviHandle *hh) {
+int32_t api_calc_forces(void *hh) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h) return MAVI_ERR_BAD_PARAMS;
   cudaSetDevice(h->device);
@@ -822,7 +826,7 @@ int32_t mavi_calc_forces(MaviHandle *hh) {
   return h->check_device_flags();
 }
 
-int32_t mavi_bin(MaviHandle *hh) {
+int32_t api_bin(void *hh) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h) return MAVI_ERR_BAD_PARAMS;
   cudaSetDevice(h->device);
@@ -834,7 +838,7 @@ int32_t mavi_bin(MaviHandle *hh) {
   return h->check_device_flags();
 }
 
-int32_t mavi_download_cells(MaviHandle *hh, int32_t *cell_of_particle, int32_t *counts) {
+int32_t api_download_cells(void *hh, int32_t *cell_of_particle, int32_t *counts) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || h->p.num_cells == 0) return MAVI_ERR_BAD_PARAMS;
   cudaSetDevice(h->device);
@@ -851,7 +855,7 @@ int32_t mavi_download_cells(MaviHandle *hh, int32_t *cell_of_particle, int32_t *
   return h->check_device_flags();
 }
 
-int32_t mavi_download_cell_lists(MaviHandle *hh, int32_t *start, int32_t *ids) {
+int32_t api_download_cell_lists(void *hh, int32_t *start, int32_t *ids) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || h->p.num_cells == 0) return MAVI_ERR_BAD_PARAMS;
   cudaSetDevice(h->device);
@@ -878,7 +882,7 @@ int32_t mavi_download_cell_lists(MaviHandle *hh, int32_t *start, int32_t *ids) {
 
 // The neighbour cells the stencil walker visits for `cell`, in visiting order (no de-duplication: 2-wide periodic
 // grids list a cell twice exactly where the reference double counts).  Mirrors for_each_neighbor (common.cuh).
-int32_t mavi_cell_neighbors(MaviHandle *hh, int32_t cell, int32_t *out8, int32_t *n) {
+int32_t api_cell_neighbors(void *hh, int32_t cell, int32_t *out8, int32_t *n) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || !out8 || !n || h->p.num_cells == 0 || cell < 0 || cell >= h->p.num_cells) return MAVI_ERR_BAD_PARAMS;
   const DevParams &p = h->p;
@@ -901,7 +905,7 @@ int32_t mavi_cell_neighbors(MaviHandle *hh, int32_t cell, int32_t *out8, int32_t
   return MAVI_OK;
 }
 
-int32_t mavi_energies(MaviHandle *hh, int32_t pe_mode, double *ke, double *pe) {
+int32_t api_energies(void *hh, int32_t pe_mode, double *ke, double *pe) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h) return MAVI_ERR_BAD_PARAMS;
   cudaSetDevice(h->device);
@@ -928,14 +932,14 @@ int32_t mavi_energies(MaviHandle *hh, int32_t pe_mode, double *ke, double *pe) {
   return st;
 }
 
-int32_t mavi_rings_download_info(MaviHandle *hh, void *areas, void *cms, void *cont_pos) {
+int32_t api_rings_download_info(void *hh, void *areas, void *cms, void *cont_pos) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || h->p.dynamics != MAVI_DYN_RINGS) return MAVI_ERR_BAD_PARAMS;
   cudaSetDevice(h->device);
   return rings_download_info(h, areas, cms, cont_pos);
 }
 
-int32_t mavi_get_time(MaviHandle *hh, int64_t *num_steps, double *time) {
+int32_t api_get_time(void *hh, int64_t *num_steps, double *time) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h) return MAVI_ERR_BAD_PARAMS;
   if (num_steps) *num_steps = h->num_steps;
@@ -943,7 +947,7 @@ int32_t mavi_get_time(MaviHandle *hh, int64_t *num_steps, double *time) {
   return MAVI_OK;
 }
 
-int32_t mavi_set_time(MaviHandle *hh, int64_t num_steps, double time) {
+int32_t api_set_time(void *hh, int64_t num_steps, double time) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h) return MAVI_ERR_BAD_PARAMS;
   h->num_steps = num_steps;
@@ -951,35 +955,35 @@ int32_t mavi_set_time(MaviHandle *hh, int64_t num_steps, double time) {
   return MAVI_OK;
 }
 
-int32_t mavi_sync(MaviHandle *hh) {
+int32_t api_sync(void *hh) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h) return MAVI_ERR_BAD_PARAMS;
   cudaSetDevice(h->device);
   return h->check_device_flags();
 }
 
-int32_t mavi_launch_count(MaviHandle *hh, int64_t *n) {
+int32_t api_launch_count(void *hh, int64_t *n) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || !n) return MAVI_ERR_BAD_PARAMS;
   *n = h->launches;
   return MAVI_OK;
 }
 
-int32_t mavi_rebuild_count(MaviHandle *hh, int64_t *n) {
+int32_t api_rebuild_count(void *hh, int64_t *n) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || !n) return MAVI_ERR_BAD_PARAMS;
   *n = h->n_rebuilds;
   return MAVI_OK;
 }
 
-int32_t mavi_set_profiling(MaviHandle *hh, int32_t on) {
+int32_t api_set_profiling(void *hh, int32_t on) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h) return MAVI_ERR_BAD_PARAMS;
   h->prof = on != 0;
   return MAVI_OK;
 }
 
-int32_t mavi_last_step_ms(MaviHandle *hh, float *ms5) {
+int32_t api_last_step_ms(void *hh, float *ms5) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h || !ms5) return MAVI_ERR_BAD_PARAMS;
   cudaSetDevice(h->device);
@@ -995,4 +999,4 @@ int32_t mavi_last_step_ms(MaviHandle *hh, float *ms5) {
   return MAVI_OK;
 }
 
-}  // extern "C"
+}  // namespace MAVI_NS

@@ -6,32 +6,33 @@
 #include <stdint.h>
 
 #include "../../include/mavi.h"
+#include "real.cuh"
 
-namespace mavi {
+namespace MAVI_NS {
 
 // One Line2D (src/configs.jl:95-117) with the frame the ctor derives, laid out as 9 doubles on the device.
 struct DevLine {
-  double p1[2], p2[2], normal[2], tangent[2], length;
+  real p1[2], p2[2], normal[2], tangent[2], length;
 };
 
 struct DevSpace {
   int wall, geom;
-  double rect_bl[2], rect_sz[2];
-  double cc[2], cr;
+  real rect_bl[2], rect_sz[2];
+  real cc[2], cr;
   const DevLine *lines;
   int n_lines;
   int pot_kind;
-  double pot[4];
-  double pot_cut2;  // largest r2 with sqrt(r2) <= dist_max (exact cutoff test without sqrt)
+  real pot[4];
+  real pot_cut2;  // largest r2 with sqrt(r2) <= dist_max (exact cutoff test without sqrt)
   int pot_mode;
 };
 
 struct DevRings {
   int num_types, n_max;
   int num_rings;
-  const double *p0, *relax_time, *vo, *mobility, *rot_diff, *k_area, *k_spring, *l_spring;
+  const real *p0, *relax_time, *vo, *mobility, *rot_diff, *k_area, *k_spring, *l_spring;
   const int *num_particles;
-  const double *interaction;  // [t1][t2][7]: k_rep,k_atr,dist_eq,dist_max, cut2, eq2_lo (exact r2 thresholds), 1/dist_eq
+  const real *interaction;  // [t1][t2][7]: k_rep,k_atr,dist_eq,dist_max, cut2, eq2_lo (exact r2 thresholds), 1/dist_eq
   const int *types;           // 0-based per ring, or nullptr
 };
 
@@ -66,25 +67,25 @@ struct DevParams {
   unsigned int tpc_mul, tpc_shr;    // ... by tpc
   unsigned int cols_mul, cols_shr;  // ... by ord_cols
   int periodic;              // calc_diff applies the minimum image (src/integration.jl:43-48)
-  double grid_bl[2], grid_h, cl, ch;
-  double size[2], half[2];   // main rectangle size and size/2
+  real grid_bl[2], grid_h, cl, ch;
+  real size[2], half[2];   // main rectangle size and size/2
   int dynamics;
-  double dyn[8];
+  real dyn[8];
   // derived pair-law constants
-  double lj_sig2, lj_24eps;        // LJ / RTP:  F/d = 24 eps s6 (2 s6 - 1) / r2,  s6 = (sig^2/r2)^3
-  double lj_c48, lj_c24;           // 48 eps / sig^2, 24 eps / sig^2:  F/d = u^4 (c48 u^3 - c24),  u = sig^2 / r2
+  real lj_sig2, lj_24eps;        // LJ / RTP:  F/d = 24 eps s6 (2 s6 - 1) / r2,  s6 = (sig^2/r2)^3
+  real lj_c48, lj_c24;           // 48 eps / sig^2, 24 eps / sig^2:  F/d = u^4 (c48 u^3 - c24),  u = sig^2 / r2
   int fast_interior;               // grid >= 8x8: interior cells may skip the minimum image (guarded, see kernels.cu)
-  double cut2;                     // exact r2 threshold of the law's cutoff (HarmTrunc dist_max, Szabo r_max, RTP 2^(1/6) sigma)
-  double eq2_lo;                   // HarmTrunc: smallest r2 with sqrt(r2) >= dist_eq  (d < dist_eq  <=>  r2 < eq2_lo)
-  double szabo_eq2_hi;             // Szabo: largest r2 with sqrt(r2) <= r_eq          (d > r_eq     <=>  r2 > szabo_eq2_hi)
-  double harm_inv_deq;             // HarmTrunc: 1/dist_eq
-  double szabo_fadh, szabo_frep;   // Szabo: k_adh/r_eq, k_rep/(r_max-r_eq)  (src/integration.jl:79-83)
-  double particle_radius;
-  double dt, term, hdt;            // dt, dt^2/2, dt/2  (src/integration.jl:420-430)
+  real cut2;                     // exact r2 threshold of the law's cutoff (HarmTrunc dist_max, Szabo r_max, RTP 2^(1/6) sigma)
+  real eq2_lo;                   // HarmTrunc: smallest r2 with sqrt(r2) >= dist_eq  (d < dist_eq  <=>  r2 < eq2_lo)
+  real szabo_eq2_hi;             // Szabo: largest r2 with sqrt(r2) <= r_eq          (d > r_eq     <=>  r2 > szabo_eq2_hi)
+  real harm_inv_deq;             // HarmTrunc: 1/dist_eq
+  real szabo_fadh, szabo_frep;   // Szabo: k_adh/r_eq, k_rep/(r_max-r_eq)  (src/integration.jl:79-83)
+  real particle_radius;
+  real dt, term, hdt;            // dt, dt^2/2, dt/2  (src/integration.jl:420-430)
   int n_spaces;
   int has_force_walls;
   int wall_fast;             // 1: the space is ONE periodic rectangle (walls! fast path)
-  double wall_ctr[2];        // its centre bl + size/2
+  real wall_ctr[2];        // its centre bl + size/2
   DevSpace spaces[MAVI_MAX_SPACES];
   int rng_mode;
   unsigned long long seed;
@@ -121,7 +122,7 @@ __device__ __forceinline__ bool step_poisoned(const int *flags) {
 
 // slab mode: record of a particle that leaves this rank's columns (written by the integrate kernel, shipped as is)
 struct EmRec {
-  double2 pos, second, force;
+  real2 pos, second, force;
   unsigned int idflag;
   int pad[3];
 };
@@ -158,19 +159,19 @@ __device__ __forceinline__ int tq_of(const DevParams &p, int col, int row) {
 // rem is exact, so the reference value is trunc(x/y) of the REAL quotient.  fl(x/y) can be off by one unit when x
 // is a rounded multiple of y; one FMA gives the sign of the exact remainder and fixes it.  Verified against the
 // fmod formulation (oracle mor_julia_div) in tests/test_oracle_kat.py and tests/test_gpu_binning.py.
-__device__ __forceinline__ double julia_div_pos(double x, double y) {
-  double ax = fabs(x);
-  double q = trunc(ax / y);
-  double rem = fma(-q, y, ax);  // sign (and zero-ness) of ax - q*y is exact
+__device__ __forceinline__ real julia_div_pos(real x, real y) {
+  real ax = fabs(x);
+  real q = trunc(ax / y);
+  real rem = fma(-q, y, ax);  // sign (and zero-ness) of ax - q*y is exact
   if (rem < 0.0) q -= 1.0;
   else if (rem >= y) q += 1.0;
   return copysign(q, x);
 }
 
 // update_particle_chunk! (src/chunks.jl:120-147): 0-based linear cell id (row fastest), or -1 if out of grid.
-__device__ __forceinline__ int cell_of_point(const DevParams &p, double x, double y) {
-  double rowf = julia_div_pos(-y + p.grid_bl[1] + p.grid_h, p.ch);
-  double colf = julia_div_pos(x - p.grid_bl[0], p.cl);
+__device__ __forceinline__ int cell_of_point(const DevParams &p, real x, real y) {
+  real rowf = julia_div_pos(-y + p.grid_bl[1] + p.grid_h, p.ch);
+  real colf = julia_div_pos(x - p.grid_bl[0], p.cl);
   if (!(fabs(rowf) < 2.0e9) || !(fabs(colf) < 2.0e9)) return -1;  // NaN/Inf -> InexactError in the reference
   int row = (int)rowf + 1, col = (int)colf + 1;
   row -= (row == p.num_rows + 1) ? 1 : 0;
@@ -193,12 +194,12 @@ __device__ __forceinline__ int cell_of_point(const DevParams &p, double x, doubl
 // trunc of the REAL quotient t/c, so index == k  <=>  k*c <= t < (k+1)*c with the products taken exactly; for a double t
 // that is  RU(k*c) <= t < RU((k+1)*c)  (RU = round-up multiply).  Edge conventions of src/chunks.jl:129-142: index -0
 // (t in (-c, 0)) maps to the first cell, index n (t in [n*c, (n+1)*c)) is clamped to the last cell.
-__device__ __forceinline__ bool axis_in_cell(double t, int k, int n, double c) {
-  bool lo = (k == 0) ? (t > -c) : (t >= __dmul_ru((double)k, c));
-  bool hi = t < __dmul_ru((double)((k == n - 1) ? n + 1 : k + 1), c);
+__device__ __forceinline__ bool axis_in_cell(real t, int k, int n, real c) {
+  bool lo = (k == 0) ? (t > -c) : (t >= mul_ru((real)k, c));
+  bool hi = t < mul_ru((real)((k == n - 1) ? n + 1 : k + 1), c);
   return lo && hi;
 }
-__device__ __forceinline__ bool still_in_cell(const DevParams &p, double x, double y, int cell) {
+__device__ __forceinline__ bool still_in_cell(const DevParams &p, real x, real y, int cell) {
   int col = div_rows(p, cell);
   const int row = cell - col * p.num_rows;
   if (p.slab) {  // local -> global column
@@ -212,68 +213,59 @@ __device__ __forceinline__ bool still_in_cell(const DevParams &p, double x, doub
 
 // calc_diff component (src/integration.jl:38-48): strict '>', one image.
 template <bool PERIODIC>
-__device__ __forceinline__ double min_image(double d, double half, double size) {
+__device__ __forceinline__ real min_image(real d, real half, real size) {
   if (PERIODIC) {
     if (fabs(d) > half) d -= copysign(size, d);
   }
   return d;
 }
 
-// 1/x to ~1 ulp without the special-case slow path of the IEEE division (x is a finite positive r^2 here).
-__device__ __forceinline__ double fast_rcp(double x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));  // MUFU.RCP64H, ~20 bits
-  double e = fma(-x, r, 1.0);   // |e| ~ 2^-20
-  double t = fma(e, e, e);      // r (1 + e + e^2) = (1/x)(1 - e^3): one cubic step instead of two Newton steps
-  return fma(r, t, r);
-}
-
 // r2 exactly as the reference rounds it: sum(dr.^2) = fl(fl(dx*dx) + fl(dy*dy)), no contraction.
-__device__ __forceinline__ double dist2_exact(double dx, double dy) {
-  return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+__device__ __forceinline__ real dist2_exact(real dx, real dy) {
+  return add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // Pair laws: coefficient c with force_on_i = c * dr  (dr = r_i - r_j, minimum image applied).
 template <int DYN>
-__device__ __forceinline__ double pair_coef(const DevParams &p, double r2);
+__device__ __forceinline__ real pair_coef(const DevParams &p, real r2);
 
 // LenJonesCfg, src/configs.jl:389-397: fmod/d = 4 eps (12 sig^12/d^14 - 6 sig^6/d^8); no cutoff.
 template <>
-__device__ __forceinline__ double pair_coef<MAVI_DYN_LJ>(const DevParams &p, double r2) {
-  double u = p.lj_sig2 * fast_rcp(r2);
-  double u2 = u * u;
-  double u3 = u2 * u;
-  double u4 = u2 * u2;
+__device__ __forceinline__ real pair_coef<MAVI_DYN_LJ>(const DevParams &p, real r2) {
+  real u = p.lj_sig2 * fast_rcp(r2);
+  real u2 = u * u;
+  real u3 = u2 * u;
+  real u4 = u2 * u2;
   return u4 * fma(u3, p.lj_c48, -p.lj_c24);  // 6 FP64 ops + 3 for the reciprocal
 }
 
 // HarmTruncCfg, src/configs.jl:354-368: 0 beyond dist_max; fmod/d = -k (d/d_eq - 1)/d = k (1/d - 1/d_eq).
 template <>
-__device__ __forceinline__ double pair_coef<MAVI_DYN_HARMTRUNC>(const DevParams &p, double r2) {
+__device__ __forceinline__ real pair_coef<MAVI_DYN_HARMTRUNC>(const DevParams &p, real r2) {
   if (r2 > p.cut2) return 0.0;
-  double k = (r2 < p.eq2_lo) ? p.dyn[0] : p.dyn[1];
-  double inv_d = rsqrt(r2);
+  real k = (r2 < p.eq2_lo) ? p.dyn[0] : p.dyn[1];
+  real inv_d = rsqrt(r2);
   return k * (inv_d - p.harm_inv_deq);
 }
 
 // SzaboCfg, src/integration.jl:68-87: -f_mod (d - r_eq) * dr with dr NOT normalised (kept).
 template <>
-__device__ __forceinline__ double pair_coef<MAVI_DYN_SZABO>(const DevParams &p, double r2) {
+__device__ __forceinline__ real pair_coef<MAVI_DYN_SZABO>(const DevParams &p, real r2) {
   if (r2 > p.cut2) return 0.0;
-  double d = sqrt(r2);
-  double f_mod = (r2 > p.szabo_eq2_hi) ? p.szabo_fadh : p.szabo_frep;
+  real d = sqrt(r2);
+  real f_mod = (r2 > p.szabo_eq2_hi) ? p.szabo_fadh : p.szabo_frep;
   return -f_mod * (d - p.dyn[5]);
 }
 
 // RunTumbleCfg, src/integration.jl:89-109: WCA, cutoff 2^(1/6) sigma.
 template <>
-__device__ __forceinline__ double pair_coef<MAVI_DYN_RTP>(const DevParams &p, double r2) {
+__device__ __forceinline__ real pair_coef<MAVI_DYN_RTP>(const DevParams &p, real r2) {
   if (r2 > p.cut2) return 0.0;
-  double u = p.lj_sig2 * fast_rcp(r2);
-  double u2 = u * u;
-  double u3 = u2 * u;
-  double u4 = u2 * u2;
+  real u = p.lj_sig2 * fast_rcp(r2);
+  real u2 = u * u;
+  real u3 = u2 * u;
+  real u4 = u2 * u2;
   return u4 * fma(u3, p.lj_c48, -p.lj_c24);
 }
 
@@ -347,6 +339,7 @@ __device__ __forceinline__ void philox_uniform2(unsigned long long seed, unsigne
 }
 
 // one standard normal (Box-Muller) for (id, step)
+// (drawn in double in both builds: the Float32 build rounds the variate once, at the point of use)
 __device__ __forceinline__ double philox_normal(unsigned long long seed, unsigned int id, unsigned long long step) {
   double u0, u1;
   philox_uniform2(seed, id, step, u0, u1);
@@ -354,6 +347,6 @@ __device__ __forceinline__ double philox_normal(unsigned long long seed, unsigne
   return r * cospi(2.0 * u1);
 }
 
-__device__ __forceinline__ double sign_d(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : x); }
+__device__ __forceinline__ real sign_d(real x) { return x > real(0) ? real(1) : (x < real(0) ? real(-1) : x); }
 
-}  // namespace mavi
+}  // namespace MAVI_NS

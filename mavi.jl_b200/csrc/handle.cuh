@@ -4,16 +4,16 @@
 
 #include "kernels.cuh"
 
-namespace mavi {
+namespace MAVI_NS {
 
 enum SecondKind { SECOND_VEL = 0, SECOND_ANGLE = 1, SECOND_RING_POL = 2 };
 
 // Rings scratch (RingsInfo, src/rings/rings.jl:118-128)
 struct RingsArrays {
-  double2 *cont_pos = nullptr;  // continuos_pos as of the last unwrap
-  double *areas = nullptr;
-  double2 *cms = nullptr;       // info.cms (lags one step, src/rings/integration.jl:523)
-  double *pol = nullptr;        // state.pol, one angle per ring
+  real2 *cont_pos = nullptr;  // continuos_pos as of the last unwrap
+  real *areas = nullptr;
+  real2 *cms = nullptr;       // info.cms (lags one step, src/rings/integration.jl:523)
+  real *pol = nullptr;        // state.pol, one angle per ring
 };
 
 // x-slab decomposition state (slab.cu)
@@ -50,7 +50,7 @@ struct Handle {
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_call[2] = {nullptr, nullptr};
   std::vector<void *> allocs;
-  double *noise_dev = nullptr;
+  real *noise_dev = nullptr;
   size_t noise_cap = 0;
   char err[512] = {0};
 
@@ -62,8 +62,8 @@ struct Handle {
   int alloc_state(int n_active, int cap);
   int rebuild_from_staging(int n_active);
   int rebuild_from_current();
-  int enqueue_step(const double *noise_dev);
-  int run_steps(long long nsteps, const double *noise_dev, size_t stride);
+  int enqueue_step(const real *noise_dev);
+  int run_steps(long long nsteps, const real *noise_dev, size_t stride);
 };
 
 // api.cu
@@ -75,7 +75,7 @@ int slab_configure(Handle *h, const MaviParams *mp);
 void slab_destroy(Handle *h);
 int slab_after_build(Handle *h);
 int slab_allreduce_max(Handle *h, int *value);
-int slab_step_once(Handle *h, const double *noise_dev);
+int slab_step_once(Handle *h, const real *noise_dev);
 int slab_sync_counts(Handle *h);
 int slab_join(Handle *h);
 
@@ -83,7 +83,7 @@ int slab_join(Handle *h);
 int rings_lower(Handle *h, const MaviParams *mp);
 int rings_allocate(Handle *h);
 int rings_upload_finish(Handle *h);
-int rings_step(Handle *h, const double *noise_dev);
+int rings_step(Handle *h, const real *noise_dev);
 int rings_calc_forces(Handle *h);
 int rings_download_info(Handle *h, void *areas, void *cms, void *cont_pos);
 int rings_download_state(Handle *h, void *pos, void *second);
@@ -91,4 +91,4 @@ int rings_download_forces(Handle *h, void *forces);
 int rings_bin(Handle *h);
 int rings_download_cells(Handle *h, int *cell_of_particle, int *counts, int *start, int *ids);
 
-}  // namespace mavi
+}  // namespace MAVI_NS

@@ -1,5 +1,5 @@
 // kernels.cu — padded-tile cell lists (full build + O(#movers) incremental repair), fused force+integrate passes and
-// energy reductions.  sm_100a.  No tensor cores: the path is FP64 vector math over HBM-resident SoA arrays (double2
+// energy reductions.  sm_100a.  No tensor cores: the path is FP64 vector math over HBM-resident SoA arrays (real2
 // loads), not a dense contraction.  Reference citations are relative to /root/reference/.
 #include <cuda_pipeline.h>
 
@@ -8,7 +8,7 @@
 #include "kernels.cuh"
 #include "walls.cuh"
 
-namespace mavi {
+namespace MAVI_NS {
 
 static inline int nblk(long long n, int tpb = TPB) { return (int)((n + tpb - 1) / tpb); }
 
@@ -65,15 +65,15 @@ __device__ __forceinline__ int2 slot_from_window(const DevParams &p, const int *
 
 // check_inside, src/space_checks.jl:9-61 (Rectangle: any coordinate < bottom_left or > top_right; Circle: |pos|^2 > R^2,
 // centre ignored (sic)); only single-geometry spaces are checked (ManyGeometries hits the generic no-op method).
-__global__ void k_check_inside(const __grid_constant__ DevParams p, const double2 *__restrict__ pos,
+__global__ void k_check_inside(const __grid_constant__ DevParams p, const real2 *__restrict__ pos,
                                const unsigned int *__restrict__ idflag, int *__restrict__ flags) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= p.n || (idflag[k] & MAVI_INACTIVE_BIT)) return;
   const DevSpace &sp = p.spaces[0];
-  double2 r = pos[k];
+  real2 r = pos[k];
   bool out = false;
   if (sp.geom == MAVI_GEOM_RECT) {
-    double trx = sp.rect_bl[0] + sp.rect_sz[0], try_ = sp.rect_bl[1] + sp.rect_sz[1];
+    real trx = sp.rect_bl[0] + sp.rect_sz[0], try_ = sp.rect_bl[1] + sp.rect_sz[1];
     out = (r.x < sp.rect_bl[0]) || (r.y < sp.rect_bl[1]) || (r.x > trx) || (r.y > try_);
   } else if (sp.geom == MAVI_GEOM_CIRCLE) {
     out = (r.x * r.x + r.y * r.y) > sp.cr * sp.cr;
@@ -95,14 +95,14 @@ void launch_init_staging_ids(const LaunchCtx &c, int n, const unsigned char *mas
 }
 
 // cell id of every staged particle (update_particle_chunk!, src/chunks.jl:120-147) + per-cell histogram
-__global__ void k_build_cell_index(const __grid_constant__ DevParams p, const double2 *__restrict__ st_pos,
+__global__ void k_build_cell_index(const __grid_constant__ DevParams p, const real2 *__restrict__ st_pos,
                                    const unsigned int *__restrict__ st_id, int *__restrict__ st_cell,
                                    int *__restrict__ count, int *__restrict__ flags) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n) return;
   int c = -1;  // inactive: never binned (active ids only)
   if (!(st_id[i] & MAVI_INACTIVE_BIT)) {
-    double2 r = st_pos[i];
+    real2 r = st_pos[i];
     c = cell_of_point(p, r.x, r.y);
     if (c >= 0 && p.slab) {  // a full build only ever sees particles of the owned columns
       const int lcol = div_rows(p, c);
@@ -155,10 +155,10 @@ __global__ void k_build_scatter(const __grid_constant__ DevParams p, const int *
 // summation order) independent of atomic scheduling -> bit-reproducible runs.  Inactive particles go to the tail.
 __global__ void k_build_place(const __grid_constant__ DevParams p, const int *__restrict__ st_cell,
                               const int *__restrict__ tstart, const int *__restrict__ perm,
-                              const double2 *__restrict__ st_pos, const double2 *__restrict__ st_vel,
-                              const double *__restrict__ st_ang, const double2 *__restrict__ st_force,
-                              const unsigned int *__restrict__ st_id, double2 *__restrict__ pos,
-                              double2 *__restrict__ vel, double *__restrict__ ang, double2 *__restrict__ force,
+                              const real2 *__restrict__ st_pos, const real2 *__restrict__ st_vel,
+                              const real *__restrict__ st_ang, const real2 *__restrict__ st_force,
+                              const unsigned int *__restrict__ st_id, real2 *__restrict__ pos,
+                              real2 *__restrict__ vel, real *__restrict__ ang, real2 *__restrict__ force,
                               unsigned int *__restrict__ idflag, int *__restrict__ cell, int *__restrict__ flags) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n || flags[FLAG_OVERFLOW]) return;
@@ -339,7 +339,7 @@ __global__ void k_sort_perm_cells(const __grid_constant__ DevParams p, const int
   }
 }
 
-void launch_build_index_tiles(const LaunchCtx &c, const DevParams &p, const double2 *pos, const unsigned int *idflag,
+void launch_build_index_tiles(const LaunchCtx &c, const DevParams &p, const real2 *pos, const unsigned int *idflag,
                               int *cell_out, int *count, int *tstart, int *perm, int *flags) {
   MAVI_LAUNCH(c, k_build_cell_index, nblk(p.n), TPB, 0, p, pos, idflag, cell_out, count, flags);
   MAVI_LAUNCH(c, k_build_layout, nblk(p.nt), TPB, 0, p, count, tstart, flags);
@@ -349,11 +349,11 @@ void launch_build_index_tiles(const LaunchCtx &c, const DevParams &p, const doub
 
 // dense copy of the current state into the staging arrays, in rank order
 __global__ void k_compact(const __grid_constant__ DevParams p, const int *__restrict__ tile_prefix,
-                          const int *__restrict__ cta_first, const double2 *__restrict__ pos,
-                          const double2 *__restrict__ vel, const double *__restrict__ ang,
-                          const double2 *__restrict__ force, const unsigned int *__restrict__ idflag,
-                          double2 *__restrict__ st_pos, double2 *__restrict__ st_vel, double *__restrict__ st_ang,
-                          double2 *__restrict__ st_force, unsigned int *__restrict__ st_id) {
+                          const int *__restrict__ cta_first, const real2 *__restrict__ pos,
+                          const real2 *__restrict__ vel, const real *__restrict__ ang,
+                          const real2 *__restrict__ force, const unsigned int *__restrict__ idflag,
+                          real2 *__restrict__ st_pos, real2 *__restrict__ st_vel, real *__restrict__ st_ang,
+                          real2 *__restrict__ st_force, unsigned int *__restrict__ st_id) {
   int rank = blockIdx.x * blockDim.x + threadIdx.x;
   if (rank >= p.n) return;
   const int k = slot_of_rank(p, tile_prefix, cta_first, rank);
@@ -378,11 +378,11 @@ void launch_compact_to_staging(const LaunchCtx &c, const DevParams &p, const Dev
 
 // copy the records of inter-tile movers aside so that source tiles can be rewritten independently
 __global__ void k_repair_collect(const int *__restrict__ flags, const int *__restrict__ mv_src,
-                                 const double2 *__restrict__ pos, const double2 *__restrict__ vel,
-                                 const double *__restrict__ ang, const double2 *__restrict__ force,
+                                 const real2 *__restrict__ pos, const real2 *__restrict__ vel,
+                                 const real *__restrict__ ang, const real2 *__restrict__ force,
                                  const unsigned int *__restrict__ idflag, const int *__restrict__ cell,
-                                 double2 *__restrict__ mv_pos, double2 *__restrict__ mv_second,
-                                 double2 *__restrict__ mv_force, unsigned int *__restrict__ mv_id,
+                                 real2 *__restrict__ mv_pos, real2 *__restrict__ mv_second,
+                                 real2 *__restrict__ mv_force, unsigned int *__restrict__ mv_id,
                                  int *__restrict__ mv_cell, int mv_cap) {
   if (!flags[FLAG_RAN]) return;
   const int n = min(flags[FLAG_NMV], mv_cap);
@@ -390,7 +390,7 @@ __global__ void k_repair_collect(const int *__restrict__ flags, const int *__res
     const int k = mv_src[m];
     if (k < 0) continue;  // immigrant from another GPU: its record is already in the mover arrays (slab.cu)
     mv_pos[m] = pos[k];
-    mv_second[m] = vel ? vel[k] : make_double2(ang[k], 0.0);
+    mv_second[m] = vel ? vel[k] : make_real2(ang[k], 0.0);
     mv_force[m] = force[k];
     mv_id[m] = idflag[k];
     mv_cell[m] = cell[k];
@@ -402,7 +402,7 @@ __global__ void k_repair_collect(const int *__restrict__ flags, const int *__res
 // the tile and its tstart[] row are rewritten in place (all reads are staged in shared memory first).
 constexpr int REPAIR_WARPS = 4;
 struct RepairRec {
-  double2 pos, second, force;
+  real2 pos, second, force;
   unsigned long long key;  // (cell << 32) | id  -> ascending cells, ascending ids inside a cell
   unsigned int idflag;
   int cell;
@@ -412,9 +412,9 @@ template <bool WRITE>
 __global__ void __launch_bounds__(REPAIR_WARPS * 32) k_repair_tiles(
     const __grid_constant__ DevParams p, int *__restrict__ flags, const int *__restrict__ dirty_list,
     int *__restrict__ tile_dirty, int *__restrict__ inbox_cnt, const int *__restrict__ inbox, int *__restrict__ tstart,
-    double2 *__restrict__ pos, double2 *__restrict__ vel, double *__restrict__ ang, double2 *__restrict__ force,
-    unsigned int *__restrict__ idflag, int *__restrict__ cell, const double2 *__restrict__ mv_pos,
-    const double2 *__restrict__ mv_second, const double2 *__restrict__ mv_force, const unsigned int *__restrict__ mv_id,
+    real2 *__restrict__ pos, real2 *__restrict__ vel, real *__restrict__ ang, real2 *__restrict__ force,
+    unsigned int *__restrict__ idflag, int *__restrict__ cell, const real2 *__restrict__ mv_pos,
+    const real2 *__restrict__ mv_second, const real2 *__restrict__ mv_force, const unsigned int *__restrict__ mv_id,
     const int *__restrict__ mv_cell) {
   extern __shared__ unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(REPAIR_WARPS * 32) k_repair_tiles(
         RepairRec &r = rec[e];
         const int k = base + l;
         r.pos = pos[k];
-        r.second = vel ? vel[k] : make_double2(ang[k], 0.0);
+        r.second = vel ? vel[k] : make_real2(ang[k], 0.0);
         r.force = force[k];
         r.idflag = idflag[k];
         r.cell = c;
@@ -516,8 +516,8 @@ __global__ void __launch_bounds__(REPAIR_WARPS * 32) k_repair_tiles(
 
 void launch_repair_tiles(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel) {
   if (p.nt == 0) return;
-  double2 *vel = second_is_vel ? a.vel : nullptr;
-  double *ang = second_is_vel ? nullptr : a.ang;
+  real2 *vel = second_is_vel ? a.vel : nullptr;
+  real *ang = second_is_vel ? nullptr : a.ang;
   const size_t smem = (size_t)REPAIR_WARPS * p.cap * sizeof(RepairRec);
   if (smem > 48 * 1024) cudaFuncSetAttribute(k_repair_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = 148 * 4;
@@ -538,12 +538,12 @@ void launch_repair_tiles(const LaunchCtx &c, const DevParams &p, const DevArrays
 // =========================================================================================================
 
 template <int DYN, bool MINIMG>
-__device__ __forceinline__ void accumulate_pair(const DevParams &p, double2 ri, double2 rj, double &fx, double &fy) {
-  double dx = min_image<MINIMG>(ri.x - rj.x, p.half[0], p.size[0]);
-  double dy = min_image<MINIMG>(ri.y - rj.y, p.half[1], p.size[1]);
+__device__ __forceinline__ void accumulate_pair(const DevParams &p, real2 ri, real2 rj, real &fx, real &fy) {
+  real dx = min_image<MINIMG>(ri.x - rj.x, p.half[0], p.size[0]);
+  real dy = min_image<MINIMG>(ri.y - rj.y, p.half[1], p.size[1]);
   // laws with a cutoff need r2 rounded exactly like the reference (bit-exact neighbour decisions); LJ has no cutoff
-  double r2 = (DYN == MAVI_DYN_LJ) ? fma(dx, dx, dy * dy) : dist2_exact(dx, dy);
-  double c = pair_coef<DYN>(p, r2);
+  real r2 = (DYN == MAVI_DYN_LJ) ? fma(dx, dx, dy * dy) : dist2_exact(dx, dy);
+  real c = pair_coef<DYN>(p, r2);
   fx = fma(c, dx, fx);
   fy = fma(c, dy, fy);
 }
@@ -580,16 +580,16 @@ struct SegWalker {
 };
 
 template <int DYN, bool MINIMG>
-__device__ __forceinline__ void walk_pairs(const DevParams &p, const double2 *__restrict__ pos, const int *tbl,
-                                           int total, double2 ri, double &fx, double &fy) {
+__device__ __forceinline__ void walk_pairs(const DevParams &p, const real2 *__restrict__ pos, const int *tbl,
+                                           int total, real2 ri, real &fx, real &fy) {
   SegWalker w;
   w.init(tbl, total);
-  double2 r0 = __ldg(pos + w.next());
-  double2 r1 = (total > 1) ? __ldg(pos + w.next()) : r0;
+  real2 r0 = __ldg(pos + w.next());
+  real2 r1 = (total > 1) ? __ldg(pos + w.next()) : r0;
   int t = 0;
 #pragma unroll 1
   for (; t + 2 <= total; t += 2) {
-    const double2 q0 = r0, q1 = r1;
+    const real2 q0 = r0, q1 = r1;
     if (t + 2 < total) r0 = __ldg(pos + w.next());
     if (t + 3 < total) r1 = __ldg(pos + w.next());
     accumulate_pair<DYN, MINIMG>(p, ri, q0, fx, fy);
@@ -599,12 +599,12 @@ __device__ __forceinline__ void walk_pairs(const DevParams &p, const double2 *__
 }
 
 template <int DYN, bool PER>
-__device__ __forceinline__ double2 cell_pair_force(const DevParams &p, const int *__restrict__ tstart,
-                                                   const double2 *__restrict__ pos, int *__restrict__ tbl, int cell,
-                                                   int k, double2 ri, bool exact_minimg) {
+__device__ __forceinline__ real2 cell_pair_force(const DevParams &p, const int *__restrict__ tstart,
+                                                   const real2 *__restrict__ pos, int *__restrict__ tbl, int cell,
+                                                   int k, real2 ri, bool exact_minimg) {
   const int R = p.num_rows, Cn = p.num_cols;
   const int col = div_rows(p, cell), row = cell - col * R;
-  double fx = 0.0, fy = 0.0;
+  real fx = 0.0, fy = 0.0;
   bool use_mi = PER && (exact_minimg || !p.fast_interior);
   // Rows row-1..row+1 as two row intervals [r1a,r1b] and [r2a,r2b], each inside ONE tile (second may be empty):
   // a tile edge between two of the rows splits them, a periodic wrap puts one interval at the far end of the column,
@@ -625,7 +625,7 @@ __device__ __forceinline__ double2 cell_pair_force(const DevParams &p, const int
   if ((r1a / MAVI_TR) != (r1b / MAVI_TR) || (r2b >= r2a && (r2a / MAVI_TR) != (r2b / MAVI_TR))) {
     // wrap AND tile edge at once (only when (R-1) % 32 == 0): generic per-cell walk
     for_each_neighbor(p, tstart, cell, k, [&](int j) { accumulate_pair<DYN, PER>(p, ri, __ldg(pos + j), fx, fy); });
-    return make_double2(fx, fy);
+    return make_real2(fx, fy);
   }
   const bool two = r2b >= r2a;
   const int t1 = r1a / MAVI_TR, t2 = r2a / MAVI_TR;
@@ -675,7 +675,7 @@ __device__ __forceinline__ double2 cell_pair_force(const DevParams &p, const int
     if (use_mi) walk_pairs<DYN, true>(p, pos, tbl, vtotal, ri, fx, fy);
     else walk_pairs<DYN, false>(p, pos, tbl, vtotal, ri, fx, fy);
   }
-  return make_double2(fx, fy);
+  return make_real2(fx, fy);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -701,8 +701,8 @@ struct BlockStage {
 // rank_last_order: order index of the tile holding the last tiled rank of this block (computed by the caller)
 template <bool PER>
 __device__ __forceinline__ void block_stage(const DevParams &p, const int *__restrict__ tstart,
-                                            const int *__restrict__ cta_first, const double2 *__restrict__ pos,
-                                            int o_last, bool exact_minimg, BlockStage *bs, double2 *s_pos,
+                                            const int *__restrict__ cta_first, const real2 *__restrict__ pos,
+                                            int o_last, bool exact_minimg, BlockStage *bs, real2 *s_pos,
                                             unsigned char *s_row, int s_pos_cap) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int R = p.num_rows, Cn = p.num_cols;
@@ -798,7 +798,7 @@ __device__ __forceinline__ void block_stage(const DevParams &p, const int *__res
     const int tot = la + lt + lb;
     for (int i = lane; i < tot; i += 32) {
       const int src = i < la ? src_a + i : (i < la + lt ? src_t + (i - la) : src_b + (i - la - lt));
-      __pipeline_memcpy_async(s_pos + off + i, pos + src, sizeof(double2));
+      __pipeline_memcpy_async(s_pos + off + i, pos + src, sizeof(real2));
     }
     // staged row (1..32) of every tile particle: lane r-1 owns tile row r
     if (lane < rows && lt > 0) {
@@ -813,8 +813,8 @@ __device__ __forceinline__ void block_stage(const DevParams &p, const int *__res
 
 // pair force of the particle in slot k (cell = (col,row) of the staged block) from the staged positions
 template <int DYN, bool MINIMG>
-__device__ __forceinline__ void block_walk(const DevParams &p, const BlockStage *bs, const double2 *s_pos, int jj,
-                                           int lr, int self, double2 ri, double &fx, double &fy) {
+__device__ __forceinline__ void block_walk(const DevParams &p, const BlockStage *bs, const real2 *s_pos, int jj,
+                                           int lr, int self, real2 ri, real &fx, real &fy) {
   // jj = staged column of the particle's own column, lr = its staged row (1..32), self = its index in s_pos
   const int a0 = bs->sstart[jj - 1][lr - 1], b0 = bs->sstart[jj - 1][lr + 2];
   const int a1 = bs->sstart[jj][lr - 1], b1 = bs->sstart[jj][lr + 2];
@@ -840,14 +840,14 @@ __device__ __forceinline__ void block_walk(const DevParams &p, const BlockStage 
 // displacement guard (FLAG_BIGMOVE) which switches pass B to the exact path.
 struct ForceCtx {
   const BlockStage *bs;        // CTA staging descriptor (shared memory)
-  const double2 *s_pos;        // staged positions
+  const real2 *s_pos;        // staged positions
   const unsigned char *s_row;  // staged row of every staged tile particle
   int *tbl;                    // this thread's column of the fallback segment table (aliases s_pos)
 };
 
 constexpr int BS_BYTES = (sizeof(BlockStage) + 15) / 16 * 16;
 constexpr int SPOS_CAP = 2304;  // staged positions per CTA (36 KB); the fallback table needs 16 KB of the same area
-constexpr int PASS_SMEM = BS_BYTES + SPOS_CAP * ((int)sizeof(double2) + 1);
+constexpr int PASS_SMEM = BS_BYTES + SPOS_CAP * ((int)sizeof(real2) + 1);
 
 // what a thread knows about the particle it is working on
 struct Particle {
@@ -856,14 +856,14 @@ struct Particle {
   bool active;
   bool staged;   // position / row came from the staged block
   int jj, lr, self;
-  double2 r;
+  real2 r;
 };
 
 // Fetch the particle of `rank`.  In a staged block everything comes from shared memory (no global load sits in front
 // of the pair loop); otherwise from the global arrays.
 template <bool ALLP>
 __device__ __forceinline__ Particle fetch_particle(const DevParams &p, const ForceCtx &fc, int rank, int k, int order,
-                                                   const double2 *__restrict__ pos, const int *__restrict__ cell,
+                                                   const real2 *__restrict__ pos, const int *__restrict__ cell,
                                                    const unsigned int *__restrict__ idflag) {
   Particle q;
   q.k = k;
@@ -888,22 +888,22 @@ __device__ __forceinline__ Particle fetch_particle(const DevParams &p, const For
 }
 
 template <int DYN, bool PER, bool ALLP>
-__device__ __forceinline__ double2 pair_force(const DevParams &p, const int *__restrict__ tstart,
-                                              const double2 *__restrict__ pos, const unsigned int *__restrict__ idflag,
+__device__ __forceinline__ real2 pair_force(const DevParams &p, const int *__restrict__ tstart,
+                                              const real2 *__restrict__ pos, const unsigned int *__restrict__ idflag,
                                               const ForceCtx &fc, const Particle &q, bool exact_minimg) {
   if (ALLP) {
-    double fx = 0.0, fy = 0.0;
+    real fx = 0.0, fy = 0.0;
     for (int j = 0; j < p.n; j++) {
       if (j == q.k || (idflag[j] & MAVI_INACTIVE_BIT)) continue;
       accumulate_pair<DYN, PER>(p, q.r, __ldg(pos + j), fx, fy);
     }
-    return make_double2(fx, fy);
+    return make_real2(fx, fy);
   }
   if (q.staged) {
-    double fx = 0.0, fy = 0.0;
+    real fx = 0.0, fy = 0.0;
     if (PER && fc.bs->use_mi) block_walk<DYN, true>(p, fc.bs, fc.s_pos, q.jj, q.lr, q.self, q.r, fx, fy);
     else block_walk<DYN, false>(p, fc.bs, fc.s_pos, q.jj, q.lr, q.self, q.r, fx, fy);
-    return make_double2(fx, fy);
+    return make_real2(fx, fy);
   }
   return cell_pair_force<DYN, PER>(p, tstart, pos, fc.tbl, q.cell, q.k, q.r, exact_minimg);
 }
@@ -913,11 +913,11 @@ __device__ __forceinline__ double2 pair_force(const DevParams &p, const int *__r
 template <bool PER, bool ALLP>
 __device__ __forceinline__ void force_prologue(const DevParams &p, const int *__restrict__ tstart,
                                                const int *__restrict__ tile_prefix, const int *__restrict__ cta_first,
-                                               const double2 *__restrict__ pos, bool exact_minimg, unsigned char *dsm,
+                                               const real2 *__restrict__ pos, bool exact_minimg, unsigned char *dsm,
                                                int *s_win, ForceCtx &fc) {
   BlockStage *bs = reinterpret_cast<BlockStage *>(dsm);
-  double2 *s_pos = reinterpret_cast<double2 *>(dsm + BS_BYTES);
-  unsigned char *s_row = dsm + BS_BYTES + SPOS_CAP * sizeof(double2);
+  real2 *s_pos = reinterpret_cast<real2 *>(dsm + BS_BYTES);
+  unsigned char *s_row = dsm + BS_BYTES + SPOS_CAP * sizeof(real2);
   fc.bs = bs;
   fc.s_pos = s_pos;
   fc.s_row = s_row;
@@ -972,8 +972,8 @@ __device__ __forceinline__ void note_changed_cells(const DevParams &p, const Mov
 
 // The particle in slot k (binned under c_old) is no longer inside that cell: the rare path of note_if_moved, kept out
 // of line so that it costs the hot kernels no registers.
-__device__ __noinline__ void note_moved_slow(const DevParams &p, const MoverSink &ms, int k, int c_old, double x, double y,
-                                            bool fixed, double2 force, double2 second) {
+__device__ __noinline__ void note_moved_slow(const DevParams &p, const MoverSink &ms, int k, int c_old, real x, real y,
+                                            bool fixed, real2 force, real2 second) {
   int c_new = cell_of_point(p, x, y);
   if (c_new < 0) {  // left the grid: the reference throws BoundsError at its NEXT update_chunks! -> reported then
     atomicOr(&ms.flags[FLAG_ERR], ERRBIT_OOG_PENDING);
@@ -994,7 +994,7 @@ __device__ __noinline__ void note_moved_slow(const DevParams &p, const MoverSink
       const int i = atomicAdd(&ms.flags[FLAG_NEM0 + d], 1);
       if (i < ms.em_cap) {
         EmRec &e = (d == 0 ? ms.em0 : ms.em1)[i];
-        e.pos = make_double2(x, y);
+        e.pos = make_real2(x, y);
         e.second = second;
         e.force = force;
         e.idflag = ms.idflag[k];
@@ -1024,8 +1024,8 @@ __device__ __noinline__ void note_moved_slow(const DevParams &p, const MoverSink
 // second_of(): the particle's second state record (velocity / angle) after this step — only evaluated for a particle
 // that left its cell, to fill the emigrant record together with `force`.
 template <typename SecondF>
-__device__ __forceinline__ void note_if_moved(const DevParams &p, const MoverSink &ms, int k, int c_old, double x,
-                                              double y, bool fixed, double2 force, SecondF &&second_of) {
+__device__ __forceinline__ void note_if_moved(const DevParams &p, const MoverSink &ms, int k, int c_old, real x,
+                                              real y, bool fixed, real2 force, SecondF &&second_of) {
   if (still_in_cell(p, x, y, c_old)) {
     if (fixed) note_changed_cells(p, ms, c_old, c_old);
     return;
@@ -1035,12 +1035,12 @@ __device__ __forceinline__ void note_if_moved(const DevParams &p, const MoverSin
 
 // Drift of update_verlet! (src/integration.jl:424): pos + vel dt + F dt^2/2, written with explicit FMAs so that every
 // kernel that produces a drifted position (k_newton_a, the carry in k_newton_b, the sparse fix-up kernels) rounds alike.
-__device__ __forceinline__ double2 verlet_drift(const DevParams &p, double2 r, double2 v, double2 F, bool &big) {
-  const double mx = fma(v.x, p.dt, F.x * p.term), my = fma(v.y, p.dt, F.y * p.term);
+__device__ __forceinline__ real2 verlet_drift(const DevParams &p, real2 r, real2 v, real2 F, bool &big) {
+  const real mx = fma(v.x, p.dt, F.x * p.term), my = fma(v.y, p.dt, F.y * p.term);
   // displacement guard of the min-image shortcut: a drift beyond one cell in one step makes the pair pass that reads
   // the drifted positions on stale cells take the exact (minimum-image everywhere) path.
   big = !(fabs(mx) <= p.cl && fabs(my) <= p.ch);
-  return make_double2(r.x + mx, r.y + my);
+  return make_real2(r.x + mx, r.y + my);
 }
 
 // pull a line towards L1 without tying up a register across the pair loop (the value is loaded after the loop)
@@ -1065,11 +1065,11 @@ template <int DYN, bool PER, bool ALLP>
 __global__ void __launch_bounds__(TPB) k_force_only(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
                              const int *__restrict__ tile_prefix, const int *__restrict__ cta_first,
                              const int *__restrict__ cell, const unsigned int *__restrict__ idflag,
-                             const double2 *__restrict__ pos, double2 *__restrict__ force, int with_walls) {
+                             const real2 *__restrict__ pos, real2 *__restrict__ force, int with_walls) {
   MAVI_FORCE_KERNEL_PROLOGUE(pos, false)
   MAVI_FOR_EACH_PARTICLE
     const Particle q = fetch_particle<ALLP>(p, fc, rank, k, order_, pos, cell, idflag);
-    double2 F = make_double2(0.0, 0.0);
+    real2 F = make_real2(0.0, 0.0);
     if (q.active) {
       F = pair_force<DYN, PER, ALLP>(p, tstart, pos, idflag, fc, q, false);
       if (with_walls && p.has_force_walls) wall_forces(p, q.r.x, q.r.y, F.x, F.y);
@@ -1084,20 +1084,20 @@ template <int DYN, bool PER, bool ALLP>
 __global__ void __launch_bounds__(TPB) k_newton_a(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
                            const int *__restrict__ tile_prefix, const int *__restrict__ cta_first,
                            const int *__restrict__ cell, const unsigned int *__restrict__ idflag,
-                           const double2 *__restrict__ pos_in, const double2 *__restrict__ vel,
-                           double2 *__restrict__ pos_out, double2 *__restrict__ f1, int *__restrict__ flags) {
+                           const real2 *__restrict__ pos_in, const real2 *__restrict__ vel,
+                           real2 *__restrict__ pos_out, real2 *__restrict__ f1, int *__restrict__ flags) {
   if (!flags[FLAG_RAN]) return;
   MAVI_FORCE_KERNEL_PROLOGUE(pos_in, false)
   MAVI_FOR_EACH_PARTICLE
     prefetch_l1(vel + k);  // needed only after the pair loop
     const Particle q = fetch_particle<ALLP>(p, fc, rank, k, order_, pos_in, cell, idflag);
-    double2 r = q.r;
-    double2 F = make_double2(0.0, 0.0);
+    real2 r = q.r;
+    real2 F = make_real2(0.0, 0.0);
     if (q.active) {
       F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, fc, q, false);
       if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
     }
-    const double2 v = vel[k];
+    const real2 v = vel[k];
     bool big;
     r = verlet_drift(p, r, v, F, big);
     if (!ALLP && PER && big) flags[FLAG_BIGMOVE] = 1;
@@ -1122,10 +1122,10 @@ __global__ void __launch_bounds__(TPB) k_newton_a(const __grid_constant__ DevPar
 template <int DYN, bool PER, bool ALLP, bool CARRY>
 __global__ void __launch_bounds__(TPB) k_newton_b(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
                            const int *__restrict__ tile_prefix, const int *__restrict__ cta_first,
-                           const unsigned int *__restrict__ idflag, const double2 *__restrict__ pos_in,
-                           double2 *__restrict__ vel, const double2 *f1, double2 *f2, double2 *f1_next,
-                           double2 *__restrict__ pos_next, int *__restrict__ fix_idx,
-                           double2 *__restrict__ fix_pos, const MoverSink ms) {
+                           const unsigned int *__restrict__ idflag, const real2 *__restrict__ pos_in,
+                           real2 *__restrict__ vel, const real2 *f1, real2 *f2, real2 *f1_next,
+                           real2 *__restrict__ pos_next, int *__restrict__ fix_idx,
+                           real2 *__restrict__ fix_pos, const MoverSink ms) {
   if (!ms.flags[FLAG_RAN]) return;
   const bool exact = !ALLP && ms.flags[FLAG_BIGMOVE] != 0;
   MAVI_FORCE_KERNEL_PROLOGUE(pos_in, exact)
@@ -1133,17 +1133,17 @@ __global__ void __launch_bounds__(TPB) k_newton_b(const __grid_constant__ DevPar
     prefetch_l1(vel + k);  // needed only after the pair loop
     prefetch_l1(f1 + k);
     const Particle q = fetch_particle<ALLP>(p, fc, rank, k, order_, pos_in, ms.cell, idflag);
-    double2 r = q.r;
-    double2 F = make_double2(0.0, 0.0);
+    real2 r = q.r;
+    real2 F = make_real2(0.0, 0.0);
     const bool active = q.active;
     const int c = q.cell;
     if (active) F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, fc, q, exact);
-    double2 v = vel[k];
-    const double2 Fo = f1[k];
+    real2 v = vel[k];
+    const real2 Fo = f1[k];
     v.x = v.x + p.hdt * (F.x + Fo.x);
     v.y = v.y + p.hdt * (F.y + Fo.y);
     if (active) {
-      const double x0 = r.x, y0 = r.y;
+      const real x0 = r.x, y0 = r.y;
       apply_walls<true>(p, r.x, r.y, v.x, v.y, p.particle_radius);
       const bool fixed = (r.x != x0 || r.y != y0);
       if (fixed) {
@@ -1156,7 +1156,7 @@ __global__ void __launch_bounds__(TPB) k_newton_b(const __grid_constant__ DevPar
     vel[k] = v;
     f2[k] = F;
     if (CARRY) {
-      double2 Fn = F;
+      real2 Fn = F;
       if (p.has_force_walls && active) wall_forces(p, r.x, r.y, Fn.x, Fn.y);
       f1_next[k] = Fn;
       bool big;
@@ -1171,9 +1171,9 @@ __global__ void __launch_bounds__(TPB) k_newton_b(const __grid_constant__ DevPar
 //     redo it (and F1 = F2 + wall forces) for those tiles, one warp per dirty tile.
 __global__ void k_redrift_tiles(const __grid_constant__ DevParams p, int *__restrict__ flags,
                                 const int *__restrict__ dirty_list, const int *__restrict__ tstart,
-                                const double2 *__restrict__ pos, const double2 *__restrict__ vel,
-                                const double2 *__restrict__ force, double2 *__restrict__ f1_next,
-                                double2 *__restrict__ pos_next) {
+                                const real2 *__restrict__ pos, const real2 *__restrict__ vel,
+                                const real2 *__restrict__ force, real2 *__restrict__ f1_next,
+                                real2 *__restrict__ pos_next) {
   if (!flags[FLAG_RAN] || flags[FLAG_OVERFLOW]) return;
   const int lane = threadIdx.x & 31, w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
   const int nd = flags[FLAG_CHANGED];
@@ -1181,8 +1181,8 @@ __global__ void k_redrift_tiles(const __grid_constant__ DevParams p, int *__rest
     const int t = dirty_list[d];
     const int b = t * p.cap, e = tstart[(size_t)t * (MAVI_TR + 1) + MAVI_TR];
     for (int k = b + lane; k < e; k += 32) {
-      const double2 r = pos[k];
-      double2 F = force[k];
+      const real2 r = pos[k];
+      real2 F = force[k];
       if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
       f1_next[k] = F;
       bool big;
@@ -1196,15 +1196,15 @@ __global__ void k_redrift_tiles(const __grid_constant__ DevParams p, int *__rest
 // r-1..r+1, own column, column+1) and the same pair arithmetic as the staged walk -> bit-identical to k_newton_a.
 template <int DYN, bool PER>
 __device__ __forceinline__ void recompute_particle(const DevParams &p, int *__restrict__ flags,
-                                                   const int *__restrict__ tstart, const double2 *__restrict__ pos,
-                                                   const double2 *__restrict__ vel, double2 *__restrict__ f1_next,
-                                                   double2 *__restrict__ pos_next, int k, int cell,
+                                                   const int *__restrict__ tstart, const real2 *__restrict__ pos,
+                                                   const real2 *__restrict__ vel, real2 *__restrict__ f1_next,
+                                                   real2 *__restrict__ pos_next, int k, int cell,
                                                    bool report_big = true) {
-  const double2 r = pos[k];
-  double fx = 0.0, fy = 0.0;
+  const real2 r = pos[k];
+  real fx = 0.0, fy = 0.0;
   for_each_neighbor(p, tstart, cell, k, [&](int j) { accumulate_pair<DYN, PER>(p, r, __ldg(pos + j), fx, fy); });
   if (p.has_force_walls) wall_forces(p, r.x, r.y, fx, fy);
-  const double2 F = make_double2(fx, fy);
+  const real2 F = make_real2(fx, fy);
   f1_next[k] = F;
   bool big;
   pos_next[k] = verlet_drift(p, r, vel[k], F, big);
@@ -1219,8 +1219,8 @@ __device__ __forceinline__ void recompute_particle(const DevParams &p, int *__re
 template <int DYN, bool PER>
 __global__ void k_recompute_changed(const __grid_constant__ DevParams p, int *__restrict__ flags,
                                     const int *__restrict__ chg, const int *__restrict__ tstart,
-                                    const double2 *__restrict__ pos, const double2 *__restrict__ vel,
-                                    double2 *__restrict__ f1_next, double2 *__restrict__ pos_next, int skip_edge) {
+                                    const real2 *__restrict__ pos, const real2 *__restrict__ vel,
+                                    real2 *__restrict__ f1_next, real2 *__restrict__ pos_next, int skip_edge) {
   // slab mode: halo columns hold no state of this rank (skip_edge = 1); with skip_edge = 3 the two owned columns next
   // to each halo are left to k_recompute_columns as well (it runs on the side stream, after the halo exchange)
   if (!flags[FLAG_RAN] || flags[FLAG_OVERFLOW]) return;
@@ -1275,8 +1275,8 @@ __global__ void k_recompute_changed(const __grid_constant__ DevParams p, int *__
 template <int DYN, bool PER>
 __global__ void k_recompute_columns(const __grid_constant__ DevParams p, int *__restrict__ flags,
                                     const int *__restrict__ tstart, const int *__restrict__ cell,
-                                    const double2 *__restrict__ pos, const double2 *__restrict__ vel,
-                                    double2 *__restrict__ f1_next, double2 *__restrict__ pos_next, int depth,
+                                    const real2 *__restrict__ pos, const real2 *__restrict__ vel,
+                                    real2 *__restrict__ f1_next, real2 *__restrict__ pos_next, int depth,
                                     int report_big) {
   if (!flags[FLAG_RAN] || flags[FLAG_OVERFLOW]) return;
   const int cs = p.tpc * p.cap;
@@ -1313,7 +1313,7 @@ void launch_step_begin(const LaunchCtx &c, const DevArrays &a) { MAVI_LAUNCH(c, 
 
 // applies the deferred wall position fix-ups and counts the step as done (runs after the integrate kernels of EVERY step)
 __global__ void k_apply_pos_fixes(int *__restrict__ flags, const int *__restrict__ fix_idx,
-                                  const double2 *__restrict__ fix_pos, double2 *__restrict__ pos) {
+                                  const real2 *__restrict__ fix_pos, real2 *__restrict__ pos) {
   if (!flags[FLAG_RAN]) return;  // poisoned by an EARLIER step: this step does not run
   if (blockIdx.x == 0 && threadIdx.x == 0) flags[FLAG_STEPS] += 1;
   const int n = flags[FLAG_NFIX];
@@ -1322,30 +1322,30 @@ __global__ void k_apply_pos_fixes(int *__restrict__ flags, const int *__restrict
 
 // update_szabo! (src/integration.jl:433-465) / update_rtp! (:467-498) for the particle in slot k (original id `id`)
 template <int DYN>
-__device__ __forceinline__ void self_propelled_update(const DevParams &p, double2 &r, const double2 F,
-                                                      double *__restrict__ ang, int k, unsigned int id,
-                                                      const double *__restrict__ noise, unsigned long long step) {
-  double theta = ang[k];
-  double sn, cs;
+__device__ __forceinline__ void self_propelled_update(const DevParams &p, real2 &r, const real2 F,
+                                                      real *__restrict__ ang, int k, unsigned int id,
+                                                      const real *__restrict__ noise, unsigned long long step) {
+  real theta = ang[k];
+  real sn, cs;
   sincos(theta, &sn, &cs);
   if (DYN == MAVI_DYN_SZABO) {
-    const double vo = p.dyn[0], mu = p.dyn[1], relax_time = p.dyn[2], drot = p.dyn[7];
-    double velx = vo * cs + mu * F.x, vely = vo * sn + mu * F.y;
-    double speed = sqrt(fabs(velx) + fabs(vely));  // sqrt(sum(abs, vel)) (sic), :448
-    double cross_prod = speed > 0.0 ? (cs * vely - sn * velx) / speed : 0.0;
+    const real vo = p.dyn[0], mu = p.dyn[1], relax_time = p.dyn[2], drot = p.dyn[7];
+    real velx = vo * cs + mu * F.x, vely = vo * sn + mu * F.y;
+    real speed = sqrt(fabs(velx) + fabs(vely));  // sqrt(sum(abs, vel)) (sic), :448
+    real cross_prod = speed > 0.0 ? (cs * vely - sn * velx) / speed : 0.0;
     if (fabs(cross_prod) > 1.0) cross_prod = sign_d(cross_prod);
-    double nz = 0.0;
+    real nz = 0.0;
     if (drot != 0.0) nz = (p.rng_mode == MAVI_RNG_HOST_NOISE) ? (noise ? noise[id] : 0.0) : philox_normal(p.seed, id, step);
-    double d_theta = 1.0 / relax_time * asin(cross_prod) * p.dt + sqrt(2.0 * drot * p.dt) * nz;
+    real d_theta = 1.0 / relax_time * asin(cross_prod) * p.dt + sqrt(2.0 * drot * p.dt) * nz;
     r.x += velx * p.dt;
     r.y += vely * p.dt;
     ang[k] = theta + d_theta;
   } else {
-    const double vo = p.dyn[0], tumble_rate = p.dyn[3];
-    double velx = vo * cs + F.x, vely = vo * sn + F.y;
+    const real vo = p.dyn[0], tumble_rate = p.dyn[3];
+    real velx = vo * cs + F.x, vely = vo * sn + F.y;
     r.x += velx * p.dt;
     r.y += vely * p.dt;
-    double u, u2;
+    double u, u2;  // uniforms are drawn (or read) and compared in double in both builds
     if (p.rng_mode == MAVI_RNG_HOST_NOISE) {
       u = noise ? noise[2 * (size_t)id] : 1.0;
       u2 = noise ? noise[2 * (size_t)id + 1] : 0.0;
@@ -1361,9 +1361,9 @@ __device__ __forceinline__ void self_propelled_update(const DevParams &p, double
 template <int DYN, bool PER, bool ALLP>
 __global__ void __launch_bounds__(TPB) k_self_propelled(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
                                  const int *__restrict__ tile_prefix, const int *__restrict__ cta_first,
-                                 const unsigned int *__restrict__ idflag, const double2 *__restrict__ pos_in,
-                                 double *__restrict__ ang, double2 *__restrict__ pos_out, double2 *__restrict__ force,
-                                 const double *__restrict__ noise, unsigned long long step, const MoverSink ms) {
+                                 const unsigned int *__restrict__ idflag, const real2 *__restrict__ pos_in,
+                                 real *__restrict__ ang, real2 *__restrict__ pos_out, real2 *__restrict__ force,
+                                 const real *__restrict__ noise, unsigned long long step, const MoverSink ms) {
   if (!ms.flags[FLAG_RAN]) return;
   MAVI_FORCE_KERNEL_PROLOGUE(pos_in, false)
   MAVI_FOR_EACH_PARTICLE
@@ -1372,8 +1372,8 @@ __global__ void __launch_bounds__(TPB) k_self_propelled(const __grid_constant__ 
     const Particle q = fetch_particle<ALLP>(p, fc, rank, k, order_, pos_in, ms.cell, idflag);
     const bool active = q.active;
     const int c = q.cell;
-    double2 r = q.r;
-    double2 F = make_double2(0.0, 0.0);
+    real2 r = q.r;
+    real2 F = make_real2(0.0, 0.0);
     if (active) {
       F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, fc, q, false);
       if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
@@ -1381,9 +1381,9 @@ __global__ void __launch_bounds__(TPB) k_self_propelled(const __grid_constant__ 
     force[k] = F;
     if ((int)id < p.n_count) self_propelled_update<DYN>(p, r, F, ang, k, id, noise, step);
     if (active) {
-      double vx = 0.0, vy = 0.0;
+      real vx = 0.0, vy = 0.0;
       apply_walls<false>(p, r.x, r.y, vx, vy, p.particle_radius);
-      if (!ALLP) note_if_moved(p, ms, k, c, r.x, r.y, false, F, [&] { return make_double2(ang[k], 0.0); });
+      if (!ALLP) note_if_moved(p, ms, k, c, r.x, r.y, false, F, [&] { return make_real2(ang[k], 0.0); });
     }
     pos_out[k] = r;
   }
@@ -1413,13 +1413,13 @@ struct Chunk2 {
   int2 cwin[G2MAX + 2][MAVI_TR];  // [j][lr-1]
 };
 constexpr int C2_BYTES = (sizeof(Chunk2) + 15) / 16 * 16;
-constexpr int PASS2_SMEM = C2_BYTES + SPOS2_CAP * (int)sizeof(double2) + OWN2_CAP * (int)sizeof(unsigned int);
+constexpr int PASS2_SMEM = C2_BYTES + SPOS2_CAP * (int)sizeof(real2) + OWN2_CAP * (int)sizeof(unsigned int);
 
 // Stage the chunk of own columns starting at local column cs (at most `rem` columns) of tile row tr.
 template <bool PER>
 __device__ __forceinline__ void chunk_stage(const DevParams &p, const int *__restrict__ tstart,
-                                            const double2 *__restrict__ pos, int tr, int cs, int rem, bool exact_minimg,
-                                            Chunk2 *ck, double2 *s_pos, unsigned int *s_list) {
+                                            const real2 *__restrict__ pos, int tr, int cs, int rem, bool exact_minimg,
+                                            Chunk2 *ck, real2 *s_pos, unsigned int *s_list) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int R = p.num_rows, Cn = p.num_cols;
   const int r0 = tr * MAVI_TR;
@@ -1509,7 +1509,7 @@ __device__ __forceinline__ void chunk_stage(const DevParams &p, const int *__res
     // 16-byte asynchronous copies (LDGSTS): every piece of every column is in flight at once, no register staging
     for (int i = lane; i < tot; i += 32) {
       const int src = i < la ? src_a + i : (i < la + lt ? src_t + (i - la) : src_b + (i - la - lt));
-      __pipeline_memcpy_async(s_pos + off + i, pos + src, sizeof(double2));
+      __pipeline_memcpy_async(s_pos + off + i, pos + src, sizeof(real2));
     }
   }
   __pipeline_commit();
@@ -1519,22 +1519,23 @@ __device__ __forceinline__ void chunk_stage(const DevParams &p, const int *__res
 
 // pair force on the staged particle (staged column jj, tile row lr, staged index self) from the staged positions
 template <int DYN, bool MINIMG>
-__device__ __forceinline__ void chunk_walk(const DevParams &p, const Chunk2 *ck, const double2 *s_pos, int jj, int lr,
-                                           int self, double2 ri, double &fx, double &fy) {
+__device__ __forceinline__ void chunk_walk(const DevParams &p, const Chunk2 *ck, const real2 *s_pos, int jj, int lr,
+                                           int self, real2 ri, real &fx, real &fy) {
   const int2 w0 = ck->cwin[jj - 1][lr - 1], w1 = ck->cwin[jj][lr - 1], w2 = ck->cwin[jj + 1][lr - 1];
   // byte offsets into s_pos; neighbours t < c1 -> column jj-1, c1 <= t < c2 -> own column before self,
   // c2 <= t < c3 -> own column after self, c3 <= t -> column jj+1
-  const int c1 = (w0.y - w0.x) * 16;
-  const int c2 = c1 + (self - w1.x) * 16;
-  const int c3 = c2 + (w1.y - self - 1) * 16;
-  const int total = c3 + (w2.y - w2.x) * 16;
-  const int o0 = w0.x * 16;
-  const int d1 = w1.x * 16 - c1 - o0, d3 = w2.x * 16 - c3 - (w1.x * 16 - c1) - 16;
+  constexpr int B = (int)sizeof(real2);  // bytes per staged position
+  const int c1 = (w0.y - w0.x) * B;
+  const int c2 = c1 + (self - w1.x) * B;
+  const int c3 = c2 + (w1.y - self - 1) * B;
+  const int total = c3 + (w2.y - w2.x) * B;
+  const int o0 = w0.x * B;
+  const int d1 = w1.x * B - c1 - o0, d3 = w2.x * B - c3 - (w1.x * B - c1) - B;
   const char *base = reinterpret_cast<const char *>(s_pos) + o0;
 #pragma unroll 4
-  for (int t = 0; t < total; t += 16) {
-    const int o = t + (t >= c1 ? d1 : 0) + (t >= c2 ? 16 : 0) + (t >= c3 ? d3 : 0);
-    accumulate_pair<DYN, MINIMG>(p, ri, *reinterpret_cast<const double2 *>(base + o), fx, fy);
+  for (int t = 0; t < total; t += B) {
+    const int o = t + (t >= c1 ? d1 : 0) + (t >= c2 ? B : 0) + (t >= c3 ? d3 : 0);
+    accumulate_pair<DYN, MINIMG>(p, ri, *reinterpret_cast<const real2 *>(base + o), fx, fy);
   }
 }
 
@@ -1542,12 +1543,12 @@ __device__ __forceinline__ void chunk_walk(const DevParams &p, const Chunk2 *ck,
 // slot of this block (F = 0 for inactive slots).
 template <int DYN, bool PER, typename Pre, typename Body>
 __device__ __forceinline__ void for_each_block_particle(const DevParams &p, const int *__restrict__ tstart,
-                                                        const double2 *__restrict__ pos, const int *__restrict__ cell,
+                                                        const real2 *__restrict__ pos, const int *__restrict__ cell,
                                                         bool exact_minimg, Pre &&pre, Body &&body) {
   extern __shared__ __align__(16) unsigned char dsm[];
   Chunk2 *ck = reinterpret_cast<Chunk2 *>(dsm);
-  double2 *s_pos = reinterpret_cast<double2 *>(dsm + C2_BYTES);
-  unsigned int *s_list = reinterpret_cast<unsigned int *>(dsm + C2_BYTES + SPOS2_CAP * sizeof(double2));
+  real2 *s_pos = reinterpret_cast<real2 *>(dsm + C2_BYTES);
+  unsigned int *s_list = reinterpret_cast<unsigned int *>(dsm + C2_BYTES + SPOS2_CAP * sizeof(real2));
   // blk_mode 1 / 2 split a launch into the blocks that never read a halo column and the first / last block of every
   // tile row (slab mode: the halo exchange overlaps with the former)
   const int bpr = p.blk_per_row;
@@ -1558,7 +1559,7 @@ __device__ __forceinline__ void for_each_block_particle(const DevParams &p, cons
     if (i < p.n - p.n_active) {
       const int k = p.tail_base + i;
       pre(k);
-      body(k, pos[k], 0, false, make_double2(0.0, 0.0));
+      body(k, pos[k], 0, false, make_real2(0.0, 0.0));
     }
     return;
   }
@@ -1581,22 +1582,22 @@ __device__ __forceinline__ void for_each_block_particle(const DevParams &p, cons
         const int self = u & 0xffffu, jj = (u >> 16) & 0xffu, lr = u >> 24;
         const int k = self + ck->gbase[jj];
         pre(k);
-        const double2 r = s_pos[self];
-        double fx = 0.0, fy = 0.0;
+        const real2 r = s_pos[self];
+        real fx = 0.0, fy = 0.0;
         if (mi) chunk_walk<DYN, true>(p, ck, s_pos, jj, lr, self, r, fx, fy);
         else chunk_walk<DYN, false>(p, ck, s_pos, jj, lr, self, r, fx, fy);
-        body(k, r, (cs - 1 + jj) * p.num_rows + r0 + lr - 1, true, make_double2(fx, fy));
+        body(k, r, (cs - 1 + jj) * p.num_rows + r0 + lr - 1, true, make_real2(fx, fy));
       }
     } else {
       // a single column too dense for the staging area: per-thread walk over the global arrays
       const int b = ck->src_t[1], e = b + ck->lt[1];
       for (int k = b + threadIdx.x; k < e; k += TPB) {
         pre(k);
-        const double2 r = pos[k];
+        const real2 r = pos[k];
         const int c = cell[k];
-        double fx = 0.0, fy = 0.0;
+        real fx = 0.0, fy = 0.0;
         for_each_neighbor(p, tstart, c, k, [&](int j) { accumulate_pair<DYN, PER>(p, r, __ldg(pos + j), fx, fy); });
-        body(k, r, c, true, make_double2(fx, fy));
+        body(k, r, c, true, make_real2(fx, fy));
       }
     }
     cs += nc;
@@ -1610,10 +1611,10 @@ static inline int grid2(const DevParams &p) {
 
 template <int DYN, bool PER>
 __global__ void __launch_bounds__(TPB) k_force_only2(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
-                              const int *__restrict__ cell, const double2 *__restrict__ pos,
-                              double2 *__restrict__ force, int with_walls) {
+                              const int *__restrict__ cell, const real2 *__restrict__ pos,
+                              real2 *__restrict__ force, int with_walls) {
   for_each_block_particle<DYN, PER>(p, tstart, pos, cell, false, [](int) {},
-    [&](int k, double2 r, int, bool active, double2 F) {
+    [&](int k, real2 r, int, bool active, real2 F) {
       if (active && with_walls && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
       force[k] = F;
     });
@@ -1621,12 +1622,12 @@ __global__ void __launch_bounds__(TPB) k_force_only2(const __grid_constant__ Dev
 
 template <int DYN, bool PER>
 __global__ void __launch_bounds__(TPB) k_newton_a2(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
-                            const int *__restrict__ cell, const double2 *__restrict__ pos_in,
-                            const double2 *__restrict__ vel, double2 *__restrict__ pos_out, double2 *__restrict__ f1,
+                            const int *__restrict__ cell, const real2 *__restrict__ pos_in,
+                            const real2 *__restrict__ vel, real2 *__restrict__ pos_out, real2 *__restrict__ f1,
                             int *__restrict__ flags) {
   if (!flags[FLAG_RAN]) return;
   for_each_block_particle<DYN, PER>(p, tstart, pos_in, cell, false, [&](int k) { prefetch_l1(vel + k); },
-    [&](int k, double2 r, int, bool active, double2 F) {
+    [&](int k, real2 r, int, bool active, real2 F) {
       if (active && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
       bool big;
       pos_out[k] = verlet_drift(p, r, vel[k], F, big);
@@ -1637,9 +1638,9 @@ __global__ void __launch_bounds__(TPB) k_newton_a2(const __grid_constant__ DevPa
 
 template <int DYN, bool PER, bool CARRY, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) k_newton_b2(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
-                            const double2 *__restrict__ pos_in, double2 *__restrict__ vel, const double2 *f1,
-                            double2 *f2, double2 *f1_next, double2 *__restrict__ pos_next,
-                            int *__restrict__ fix_idx, double2 *__restrict__ fix_pos,
+                            const real2 *__restrict__ pos_in, real2 *__restrict__ vel, const real2 *f1,
+                            real2 *f2, real2 *f1_next, real2 *__restrict__ pos_next,
+                            int *__restrict__ fix_idx, real2 *__restrict__ fix_pos,
                             const __grid_constant__ MoverSink ms) {
   if (!ms.flags[FLAG_RAN]) return;
   // slab mode, blocks next to a halo column (blk_mode 2): their boundary particles are re-drifted on the side stream
@@ -1647,13 +1648,13 @@ __global__ void __launch_bounds__(TPB, MINB) k_newton_b2(const __grid_constant__
   const bool exact = ms.flags[FLAG_BIGMOVE] != 0 || (p.slab && p.blk_mode == 2);
   for_each_block_particle<DYN, PER>(p, tstart, pos_in, ms.cell, exact,
     [&](int k) { prefetch_l1(vel + k); prefetch_l1(f1 + k); },
-    [&](int k, double2 r, int c, bool active, double2 F) {
-      double2 v = vel[k];
-      const double2 Fo = f1[k];
+    [&](int k, real2 r, int c, bool active, real2 F) {
+      real2 v = vel[k];
+      const real2 Fo = f1[k];
       v.x = v.x + p.hdt * (F.x + Fo.x);
       v.y = v.y + p.hdt * (F.y + Fo.y);
       if (active) {
-        const double x0 = r.x, y0 = r.y;
+        const real x0 = r.x, y0 = r.y;
         apply_walls<true>(p, r.x, r.y, v.x, v.y, p.particle_radius);
         const bool fixed = (r.x != x0 || r.y != y0);
         if (fixed) {
@@ -1666,7 +1667,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_newton_b2(const __grid_constant__
       vel[k] = v;
       f2[k] = F;
       if (CARRY) {
-        double2 Fn = F;
+        real2 Fn = F;
         if (p.has_force_walls && active) wall_forces(p, r.x, r.y, Fn.x, Fn.y);
         f1_next[k] = Fn;
         bool big;
@@ -1678,22 +1679,22 @@ __global__ void __launch_bounds__(TPB, MINB) k_newton_b2(const __grid_constant__
 
 template <int DYN, bool PER>
 __global__ void __launch_bounds__(TPB) k_self_propelled2(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
-                                  const unsigned int *__restrict__ idflag, const double2 *__restrict__ pos_in,
-                                  double *__restrict__ ang, double2 *__restrict__ pos_out, double2 *__restrict__ force,
-                                  const double *__restrict__ noise, unsigned long long step,
+                                  const unsigned int *__restrict__ idflag, const real2 *__restrict__ pos_in,
+                                  real *__restrict__ ang, real2 *__restrict__ pos_out, real2 *__restrict__ force,
+                                  const real *__restrict__ noise, unsigned long long step,
                                   const __grid_constant__ MoverSink ms) {
   if (!ms.flags[FLAG_RAN]) return;
   for_each_block_particle<DYN, PER>(p, tstart, pos_in, ms.cell, false,
     [&](int k) { prefetch_l1(ang + k); prefetch_l1(idflag + k); },
-    [&](int k, double2 r, int c, bool active, double2 F) {
+    [&](int k, real2 r, int c, bool active, real2 F) {
       const unsigned int id = idflag[k] & ~MAVI_INACTIVE_BIT;
       if (active && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
       force[k] = F;
       if ((int)id < p.n_count) self_propelled_update<DYN>(p, r, F, ang, k, id, noise, step);
       if (active) {
-        double vx = 0.0, vy = 0.0;
+        real vx = 0.0, vy = 0.0;
         apply_walls<false>(p, r.x, r.y, vx, vy, p.particle_radius);
-        note_if_moved(p, ms, k, c, r.x, r.y, false, F, [&] { return make_double2(ang[k], 0.0); });
+        note_if_moved(p, ms, k, c, r.x, r.y, false, F, [&] { return make_real2(ang[k], 0.0); });
       }
       pos_out[k] = r;
     });
@@ -1840,7 +1841,7 @@ void launch_carry_fixups(const LaunchCtx &c, const DevParams &p, const DevArrays
   launch_carry_recompute(c, p, a);
 }
 
-void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const double *noise,
+void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const real *noise,
                            unsigned long long step) {
   const bool allp = p.num_cells == 0;
   const MoverSink ms = mover_sink(a);
@@ -1890,14 +1891,14 @@ __global__ void k_reduce_final(const double *__restrict__ partials, int nb, doub
 
 // kinetic_energy, src/quantities.jl:12-18: sum over ALL slots of |v|^2, /2 (mass 1)
 __global__ void k_kinetic(const __grid_constant__ DevParams p, const int *__restrict__ tile_prefix,
-                          const int *__restrict__ cta_first, const double2 *__restrict__ vel,
+                          const int *__restrict__ cta_first, const real2 *__restrict__ vel,
                           double *__restrict__ partials) {
   double s = 0.0;
   for (int base = blockIdx.x * blockDim.x; base < p.n; base += gridDim.x * blockDim.x) {
     int rank = base + threadIdx.x;
     if (rank < p.n) {
-      double2 v = vel[slot_of_rank(p, tile_prefix, cta_first, rank)];
-      s += v.x * v.x + v.y * v.y;
+      real2 v = vel[slot_of_rank(p, tile_prefix, cta_first, rank)];
+      s += (double)v.x * v.x + (double)v.y * v.y;
     }
   }
   s = block_sum(s);
@@ -1916,17 +1917,17 @@ void launch_kinetic_energy(const LaunchCtx &c, const DevParams &p, const DevArra
 // exact mode: every pair i<j of slots 1:count, O(N^2), on the dense staging copy (no cutoff, min image)
 template <bool PER>
 __global__ void k_potential_exact(const __grid_constant__ DevParams p, const unsigned int *__restrict__ st_id,
-                                  const double2 *__restrict__ st_pos, double *__restrict__ partials) {
+                                  const real2 *__restrict__ st_pos, double *__restrict__ partials) {
   double s = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
     if ((int)(st_id[i] & ~MAVI_INACTIVE_BIT) >= p.n_count) continue;
-    const double2 ri = st_pos[i];
+    const real2 ri = st_pos[i];
     for (int j = i + 1; j < p.n; j++) {
       if ((int)(st_id[j] & ~MAVI_INACTIVE_BIT) >= p.n_count) continue;
-      const double2 rj = __ldg(st_pos + j);
-      double dx = min_image<PER>(ri.x - rj.x, p.half[0], p.size[0]);
-      double dy = min_image<PER>(ri.y - rj.y, p.half[1], p.size[1]);
-      double s2 = p.lj_sig2 / (dx * dx + dy * dy);
+      const real2 rj = __ldg(st_pos + j);
+      real dx = min_image<PER>(ri.x - rj.x, p.half[0], p.size[0]);
+      real dy = min_image<PER>(ri.y - rj.y, p.half[1], p.size[1]);
+      double s2 = (double)p.lj_sig2 / ((double)dx * dx + (double)dy * dy);
       double s6 = s2 * s2 * s2;
       s += s6 * s6 - s6;
     }
@@ -1940,19 +1941,19 @@ template <bool PER>
 __global__ void k_potential_stencil(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
                                     const int *__restrict__ tile_prefix, const int *__restrict__ cta_first,
                                     const int *__restrict__ cell, const unsigned int *__restrict__ idflag,
-                                    const double2 *__restrict__ pos, double *__restrict__ partials) {
+                                    const real2 *__restrict__ pos, double *__restrict__ partials) {
   double s = 0.0;
   for (int base = blockIdx.x * blockDim.x; base < p.n; base += gridDim.x * blockDim.x) {
     int rank = base + threadIdx.x;
     if (rank >= p.n) continue;
     const int k = slot_of_rank(p, tile_prefix, cta_first, rank);
     if (idflag[k] & MAVI_INACTIVE_BIT) continue;
-    const double2 ri = pos[k];
+    const real2 ri = pos[k];
     for_each_neighbor(p, tstart, cell[k], k, [&](int j) {
-      const double2 rj = __ldg(pos + j);
-      double dx = min_image<PER>(ri.x - rj.x, p.half[0], p.size[0]);
-      double dy = min_image<PER>(ri.y - rj.y, p.half[1], p.size[1]);
-      double s2 = p.lj_sig2 / (dx * dx + dy * dy);
+      const real2 rj = __ldg(pos + j);
+      real dx = min_image<PER>(ri.x - rj.x, p.half[0], p.size[0]);
+      real dy = min_image<PER>(ri.y - rj.y, p.half[1], p.size[1]);
+      double s2 = (double)p.lj_sig2 / ((double)dx * dx + (double)dy * dy);
       double s6 = s2 * s2 * s2;
       s += s6 * s6 - s6;
     });
@@ -1964,7 +1965,7 @@ __global__ void k_potential_stencil(const __grid_constant__ DevParams p, const i
 void launch_potential_energy(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int mode, double *out) {
   int nb = min(nblk(p.n, RED_TPB), RED_MAX_BLOCKS);
   if (nb < 1) nb = 1;
-  const double eps4 = 4.0 * p.dyn[1];
+  const double eps4 = 4.0 * (double)p.dyn[1];
   if (mode == 0) {  // caller has refreshed the staging copy
     if (p.periodic) MAVI_LAUNCH(c, (k_potential_exact<true>), nb, RED_TPB, 0, p, a.st_id, a.st_pos, a.reduce_buf);
     else MAVI_LAUNCH(c, (k_potential_exact<false>), nb, RED_TPB, 0, p, a.st_id, a.st_pos, a.reduce_buf);
@@ -1982,7 +1983,7 @@ void launch_potential_energy(const LaunchCtx &c, const DevParams &p, const DevAr
 // =========================================================================================================
 __global__ void k_unpermute2(const __grid_constant__ DevParams p, const int *__restrict__ tile_prefix,
                              const int *__restrict__ cta_first, const unsigned int *__restrict__ idflag,
-                             const double2 *__restrict__ in, double2 *__restrict__ out) {
+                             const real2 *__restrict__ in, real2 *__restrict__ out) {
   int rank = blockIdx.x * blockDim.x + threadIdx.x;
   if (rank >= p.n) return;
   const int k = slot_of_rank(p, tile_prefix, cta_first, rank);
@@ -1990,7 +1991,7 @@ __global__ void k_unpermute2(const __grid_constant__ DevParams p, const int *__r
 }
 __global__ void k_unpermute1(const __grid_constant__ DevParams p, const int *__restrict__ tile_prefix,
                              const int *__restrict__ cta_first, const unsigned int *__restrict__ idflag,
-                             const double *__restrict__ in, double *__restrict__ out) {
+                             const real *__restrict__ in, real *__restrict__ out) {
   int rank = blockIdx.x * blockDim.x + threadIdx.x;
   if (rank >= p.n) return;
   const int k = slot_of_rank(p, tile_prefix, cta_first, rank);
@@ -2025,11 +2026,11 @@ __global__ void k_ids_in_cell_order(const __grid_constant__ DevParams p, const i
   for (int j = b; j < e; j++) out[d + (j - b)] = (int)(idflag[j] & ~MAVI_INACTIVE_BIT);
 }
 
-void launch_unpermute2(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const double2 *in, double2 *out) {
+void launch_unpermute2(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const real2 *in, real2 *out) {
   if (p.num_cells > 0) ensure_rank_maps(c, p, a);
   MAVI_LAUNCH(c, k_unpermute2, nblk(p.n), TPB, 0, p, a.tile_prefix, a.cta_first, a.idflag, in, out);
 }
-void launch_unpermute1(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const double *in, double *out) {
+void launch_unpermute1(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const real *in, real *out) {
   if (p.num_cells > 0) ensure_rank_maps(c, p, a);
   MAVI_LAUNCH(c, k_unpermute1, nblk(p.n), TPB, 0, p, a.tile_prefix, a.cta_first, a.idflag, in, out);
 }
@@ -2047,4 +2048,4 @@ void launch_ids_in_cell_order(const LaunchCtx &c, const DevParams &p, const DevA
   MAVI_LAUNCH(c, k_ids_in_cell_order, nblk(p.num_cells), TPB, 0, p, a.tstart, a.count, a.idflag, out);
 }
 
-}  // namespace mavi
+}  // namespace MAVI_NS

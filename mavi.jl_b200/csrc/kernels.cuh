@@ -2,7 +2,7 @@
 #pragma once
 #include "common.cuh"
 
-namespace mavi {
+namespace MAVI_NS {
 
 constexpr int TPB = 256;   // threads per block
 constexpr int RPB = 1024;  // ranks per block of every rank-mapped kernel: each thread handles RPB/TPB particles
@@ -17,16 +17,16 @@ constexpr int RPB = 1024;  // ranks per block of every rank-mapped kernel: each 
 // Kernels run over RANKS 0..n-1 (dense) and map rank -> slot through tile_prefix[] / cta_first[].
 struct DevArrays {
   // slot-indexed state
-  double2 *pos[2];      // ping-pong: pos[0] is the current state
-  double2 *vel;         // SecondLawState velocities
-  double *ang;          // SelfPropelledState pol_angle
+  real2 *pos[2];      // ping-pong: pos[0] is the current state
+  real2 *vel;         // SecondLawState velocities
+  real *ang;          // SelfPropelledState pol_angle
   unsigned int *idflag; // original id of the particle in the slot (bit 31: inactive)
   int *cell;            // cell the particle is binned in
-  double2 *force;       // F (get_forces)
-  double2 *force_old;   // F1 of the Verlet step
+  real2 *force;       // F (get_forces)
+  real2 *force_old;   // F1 of the Verlet step
   // staging in dense rank order (upload, downloads, full rebuilds)
-  double2 *st_pos, *st_vel, *st_force;
-  double *st_ang;
+  real2 *st_pos, *st_vel, *st_force;
+  real *st_ang;
   unsigned int *st_id;
   int *st_cell;
   // tile bookkeeping
@@ -42,7 +42,7 @@ struct DevArrays {
   int *inbox_cnt;       // [nt] particles arriving from other tiles
   int *inbox;           // [nt*inbox_cap] -> index into the mover list
   int *mv_src;          // [mv_cap] source slot of an inter-tile mover
-  double2 *mv_pos, *mv_second, *mv_force;
+  real2 *mv_pos, *mv_second, *mv_force;
   unsigned int *mv_id;
   int *mv_cell;
   int *chg;             // [chg_cap] cells whose membership changed in this step (force carry)
@@ -52,7 +52,7 @@ struct DevArrays {
   // control
   int *flags;           // see FLAG_* in common.cuh
   int *fix_idx;         // sparse list of slots whose position walls! changed in pass B
-  double2 *fix_pos;
+  real2 *fix_pos;
   double *reduce_buf;
 };
 
@@ -66,7 +66,7 @@ struct LaunchCtx {
 void launch_check_inside(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
 void launch_build_tiles(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel);
 // Mavi.Rings: bin particle indices only (perm[slot] = particle index, ascending inside every cell)
-void launch_build_index_tiles(const LaunchCtx &c, const DevParams &p, const double2 *pos, const unsigned int *idflag,
+void launch_build_index_tiles(const LaunchCtx &c, const DevParams &p, const real2 *pos, const unsigned int *idflag,
                               int *cell_out, int *count, int *tstart, int *perm, int *flags);
 // dense copy of the current state into staging (rank order)
 void launch_compact_to_staging(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel);
@@ -92,7 +92,7 @@ void launch_carry_recompute(const LaunchCtx &c, const DevParams &p, const DevArr
 void launch_carry_recompute_list(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int skip_edge);
 void launch_carry_recompute_columns(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int depth, bool report_big);
 void launch_carry_fixups(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
-void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const double *noise,
+void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const real *noise,
                            unsigned long long step);
 
 // quantities
@@ -100,10 +100,10 @@ void launch_kinetic_energy(const LaunchCtx &c, const DevParams &p, const DevArra
 void launch_potential_energy(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int mode, double *out);
 
 // downloads (un-permute to original ids)
-void launch_unpermute2(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const double2 *in, double2 *out);
-void launch_unpermute1(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const double *in, double *out);
+void launch_unpermute2(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const real2 *in, real2 *out);
+void launch_unpermute1(const LaunchCtx &c, const DevParams &p, const DevArrays &a, const real *in, real *out);
 void launch_unpermute_cells(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int *out);
 void launch_cell_counts(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int *out);
 void launch_ids_in_cell_order(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int *out);
 
-}  // namespace mavi
+}  // namespace MAVI_NS

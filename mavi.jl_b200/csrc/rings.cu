@@ -12,7 +12,7 @@
 #include "handle.cuh"
 #include "walls.cuh"
 
-namespace mavi {
+namespace MAVI_NS {
 
 #define RINGS_TRY(h, expr)                                                                              \
   do {                                                                                                  \
@@ -48,35 +48,35 @@ template <bool PER>
 __global__ void __launch_bounds__(TPB) k_rings_pair(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
                                                     const int *__restrict__ perm, const int *__restrict__ cell,
                                                     const unsigned int *__restrict__ idflag,
-                                                    const double2 *__restrict__ pos, double2 *__restrict__ fpair,
+                                                    const real2 *__restrict__ pos, real2 *__restrict__ fpair,
                                                     int with_walls) {
-  extern __shared__ double s_inter[];  // [num_types^2][7]
+  extern __shared__ real s_inter[];  // [num_types^2][7]
   const DevRings &R = p.rings;
   for (int t = threadIdx.x; t < R.num_types * R.num_types * 7; t += blockDim.x) s_inter[t] = R.interaction[t];
   __syncthreads();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n) return;
-  double fx = 0.0, fy = 0.0;
+  real fx = 0.0, fy = 0.0;
   if (!(idflag[i] & MAVI_INACTIVE_BIT)) {
     const int ring = i / R.n_max;
     const int ti = ring_type(R, ring);
     const int np = R.num_particles[ti];
-    const double2 ri = pos[i];
+    const real2 ri = pos[i];
     auto visit = [&](int j) {
-      const double2 rj = __ldg(pos + j);
-      const double dx = min_image<PER>(ri.x - rj.x, p.half[0], p.size[0]);
-      const double dy = min_image<PER>(ri.y - rj.y, p.half[1], p.size[1]);
-      const double r2 = dist2_exact(dx, dy);
+      const real2 rj = __ldg(pos + j);
+      const real dx = min_image<PER>(ri.x - rj.x, p.half[0], p.size[0]);
+      const real dy = min_image<PER>(ri.y - rj.y, p.half[1], p.size[1]);
+      const real r2 = dist2_exact(dx, dy);
       const int rj_ring = j / R.n_max;
-      const double *ic = s_inter + 7 * (ti * R.num_types + ring_type(R, rj_ring));
+      const real *ic = s_inter + 7 * (ti * R.num_types + ring_type(R, rj_ring));
       if (r2 > ic[4]) return;  // dist > dist_max
       const bool same = rj_ring == ring;
       if (same) {
         const int diff = i > j ? i - j : j - i;
         if (diff == 1 || diff == np - 1) return;  // bonded neighbours inside the ring
       }
-      const double k = (r2 < ic[5]) ? ic[0] : (same ? 0.0 : ic[1]);  // no intra-ring attraction
-      const double c = k * (rsqrt(r2) - ic[6]);
+      const real k = (r2 < ic[5]) ? ic[0] : (same ? 0.0 : ic[1]);  // no intra-ring attraction
+      const real c = k * (rsqrt(r2) - ic[6]);
       fx = fma(c, dx, fx);
       fy = fma(c, dy, fy);
     };
@@ -92,19 +92,19 @@ __global__ void __launch_bounds__(TPB) k_rings_pair(const __grid_constant__ DevP
     }
     if (with_walls && p.has_force_walls) wall_forces(p, ri.x, ri.y, fx, fy);
   }
-  fpair[i] = make_double2(fx, fy);
+  fpair[i] = make_real2(fx, fy);
 }
 
 // One warp per ring.  MODE 0: forces! only (constructor priming / mavi_calc_forces); MODE 1: full step.
 template <bool PER, int MODE>
 __global__ void __launch_bounds__(RING_WARPS * 32) k_rings_ring(
-    const __grid_constant__ DevParams p, double2 *__restrict__ pos, double *__restrict__ pol,
-    const double2 *__restrict__ fpair, double2 *__restrict__ force, double2 *__restrict__ cont_pos,
-    double *__restrict__ areas, double2 *__restrict__ cms, const double *__restrict__ noise, unsigned long long step,
+    const __grid_constant__ DevParams p, real2 *__restrict__ pos, real *__restrict__ pol,
+    const real2 *__restrict__ fpair, real2 *__restrict__ force, real2 *__restrict__ cont_pos,
+    real *__restrict__ areas, real2 *__restrict__ cms, const real *__restrict__ noise, unsigned long long step,
     int prime_cms) {
-  __shared__ double2 s_pos[RING_WARPS][RING_NMAX];
-  __shared__ double2 s_cont[RING_WARPS][RING_NMAX];
-  __shared__ double2 s_vel[RING_WARPS][RING_NMAX];
+  __shared__ real2 s_pos[RING_WARPS][RING_NMAX];
+  __shared__ real2 s_cont[RING_WARPS][RING_NMAX];
+  __shared__ real2 s_vel[RING_WARPS][RING_NMAX];
   const DevRings &R = p.rings;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int ring = blockIdx.x * RING_WARPS + w;
@@ -112,20 +112,20 @@ __global__ void __launch_bounds__(RING_WARPS * 32) k_rings_ring(
   const int t = ring_type(R, ring);
   const int np = R.num_particles[t];
   const int base = ring * R.n_max;
-  double2 *sp = s_pos[w], *sc = s_cont[w], *sv = s_vel[w];
+  real2 *sp = s_pos[w], *sc = s_cont[w], *sv = s_vel[w];
   for (int i = lane; i < R.n_max; i += 32) sp[i] = pos[base + i];
   __syncwarp();
   // ---- update_cms! (src/rings/integration.jl:366-372) runs FIRST in step!: it still sees last step's continuos_pos
   if (MODE == 1 && lane == 0) {
-    double sx, sy;
+    real sx, sy;
     if (PER) { sx = cont_pos[base].x; sy = cont_pos[base].y; }
     else { sx = sp[0].x; sy = sp[0].y; }
     for (int i = 1; i < np; i++) {
-      const double2 c = PER ? cont_pos[base + i] : sp[i];
+      const real2 c = PER ? cont_pos[base + i] : sp[i];
       sx += c.x;
       sy += c.y;
     }
-    cms[ring] = make_double2(sx / np, sy / np);
+    cms[ring] = make_real2(sx / np, sy / np);
   }
   __syncwarp();
   // ---- update_continuos_pos! (:118-138): sequential unwrap, same accumulation order as the reference
@@ -133,9 +133,9 @@ __global__ void __launch_bounds__(RING_WARPS * 32) k_rings_ring(
     if (lane == 0) {
       sc[0] = sp[0];
       for (int i = 1; i < np; i++) {
-        const double dx = min_image<true>(sp[i].x - sp[i - 1].x, p.half[0], p.size[0]);
-        const double dy = min_image<true>(sp[i].y - sp[i - 1].y, p.half[1], p.size[1]);
-        sc[i] = make_double2(sc[i - 1].x + dx, sc[i - 1].y + dy);
+        const real dx = min_image<true>(sp[i].x - sp[i - 1].x, p.half[0], p.size[0]);
+        const real dy = min_image<true>(sp[i].y - sp[i - 1].y, p.half[1], p.size[1]);
+        sc[i] = make_real2(sc[i - 1].x + dx, sc[i - 1].y + dy);
       }
       for (int i = np; i < R.n_max; i++) sc[i] = sp[i];  // continuos_pos[:, ring] .= rings_pos[:, ring] first
     }
@@ -146,76 +146,76 @@ __global__ void __launch_bounds__(RING_WARPS * 32) k_rings_ring(
     __syncwarp();
   }
   // ---- calc_area (:103-116), shoelace, sequential
-  double area = 0.0;
+  real area = 0.0;
   if (lane == 0) {
     for (int i = 0; i < np - 1; i++) area += sc[i].x * sc[i + 1].y - sc[i].y * sc[i + 1].x;
     area += sc[np - 1].x * sc[0].y - sc[np - 1].y * sc[0].x;
     area = area / 2.0;
     areas[ring] = area;
     if (MODE == 0 && prime_cms) {  // constructor: update_cms! right after the first unwrap (src/rings/rings.jl:280-283)
-      double sx = sc[0].x, sy = sc[0].y;
+      real sx = sc[0].x, sy = sc[0].y;
       for (int i = 1; i < np; i++) { sx += sc[i].x; sy += sc[i].y; }
-      cms[ring] = make_double2(sx / np, sy / np);
+      cms[ring] = make_real2(sx / np, sy / np);
     }
   }
   area = __shfl_sync(0xffffffffu, area, 0);
   // ---- forces! (:197-226): pair forces + springs (:79-97) + area_forces! (:140-195)
-  const double k_spring = R.k_spring[t], l_spring = R.l_spring[t];
-  const double k_area = R.k_area[t], p0 = R.p0[t];
-  const double a0s = np * l_spring / p0;
-  const double fmod_area = k_area * (area - a0s * a0s);
-  const double vo = R.vo[t], mu = R.mobility[t];
-  const double theta = pol[ring];
-  double sn, cs;
+  const real k_spring = R.k_spring[t], l_spring = R.l_spring[t];
+  const real k_area = R.k_area[t], p0 = R.p0[t];
+  const real a0s = np * l_spring / p0;
+  const real fmod_area = k_area * (area - a0s * a0s);
+  const real vo = R.vo[t], mu = R.mobility[t];
+  const real theta = pol[ring];
+  real sn, cs;
   sincos(theta, &sn, &cs);
-  auto spring = [&](int a, int b, double &ox, double &oy) {  // springs_force(p1 = a, p2 = b)
-    const double dx = min_image<PER>(sp[a].x - sp[b].x, p.half[0], p.size[0]);
-    const double dy = min_image<PER>(sp[a].y - sp[b].y, p.half[1], p.size[1]);
-    const double dist = sqrt(dx * dx + dy * dy);
-    const double c = (-k_spring * (dist - l_spring)) / dist;
+  auto spring = [&](int a, int b, real &ox, real &oy) {  // springs_force(p1 = a, p2 = b)
+    const real dx = min_image<PER>(sp[a].x - sp[b].x, p.half[0], p.size[0]);
+    const real dy = min_image<PER>(sp[a].y - sp[b].y, p.half[1], p.size[1]);
+    const real dist = sqrt(dx * dx + dy * dy);
+    const real c = (-k_spring * (dist - l_spring)) / dist;
     ox = c * dx;
     oy = c * dy;
   };
   for (int i = lane; i < np; i += 32) {
     const int nxt = (i == np - 1) ? 0 : i + 1, prv = (i == 0) ? np - 1 : i - 1;
-    double2 F = fpair[base + i];
-    double ax, ay, bx, by;
+    real2 F = fpair[base + i];
+    real ax, ay, bx, by;
     spring(i, nxt, ax, ay);  // spring i: +f on its first particle
     spring(prv, i, bx, by);  // spring i-1: -f on its second particle
     F.x += ax; F.y += ay;
     F.x -= bx; F.y -= by;
-    const double dx = min_image<PER>(sp[nxt].x - sp[prv].x, p.half[0], p.size[0]);
-    const double dy = min_image<PER>(sp[nxt].y - sp[prv].y, p.half[1], p.size[1]);
+    const real dx = min_image<PER>(sp[nxt].x - sp[prv].x, p.half[0], p.size[0]);
+    const real dy = min_image<PER>(sp[nxt].y - sp[prv].y, p.half[1], p.size[1]);
     F.x -= fmod_area * (dy / 2);
     F.y -= fmod_area * (-dx / 2);
     force[base + i] = F;
     if (MODE == 1) {
       // update! (:300-351): overdamped active motion
-      const double vx = vo * cs + mu * F.x, vy = vo * sn + mu * F.y;
-      sv[i] = make_double2(vx, vy);
-      double x = sp[i].x + vx * p.dt, y = sp[i].y + vy * p.dt;
-      double dummy_vx = 0.0, dummy_vy = 0.0;
-      const double pr = R.interaction[7 * (t * R.num_types + t) + 2] / 2.0;  // get_particle_radius of the ring type
+      const real vx = vo * cs + mu * F.x, vy = vo * sn + mu * F.y;
+      sv[i] = make_real2(vx, vy);
+      real x = sp[i].x + vx * p.dt, y = sp[i].y + vy * p.dt;
+      real dummy_vx = 0.0, dummy_vy = 0.0;
+      const real pr = R.interaction[7 * (t * R.num_types + t) + 2] / 2.0;  // get_particle_radius of the ring type
       apply_walls<false>(p, x, y, dummy_vx, dummy_vy, pr);  // walls!(system), generic walls over the active ids
-      pos[base + i] = make_double2(x, y);
+      pos[base + i] = make_real2(x, y);
     }
   }
-  for (int i = np + lane; i < R.n_max; i += 32) force[base + i] = make_double2(0.0, 0.0);
+  for (int i = np + lane; i < R.n_max; i += 32) force[base + i] = make_real2(0.0, 0.0);
   if (MODE == 1) {
     __syncwarp();
     if (lane == 0) {
-      double vcx = 0.0, vcy = 0.0;
+      real vcx = 0.0, vcy = 0.0;
       for (int i = 0; i < np; i++) { vcx += sv[i].x; vcy += sv[i].y; }
       vcx /= np;
       vcy /= np;
-      const double speed = sqrt(vcx * vcx + vcy * vcy);
-      double cross_prod = 0.0;
+      const real speed = sqrt(vcx * vcx + vcy * vcy);
+      real cross_prod = 0.0;
       if (speed != 0.0) {
         cross_prod = (cs * vcy - sn * vcx) / speed;
         if (fabs(cross_prod) > 1.0) cross_prod = sign_d(cross_prod);
       }
-      const double drot = R.rot_diff[t];
-      double nz = 0.0;
+      const real drot = R.rot_diff[t];
+      real nz = 0.0;
       if (drot != 0.0)
         nz = (p.rng_mode == MAVI_RNG_HOST_NOISE) ? (noise ? noise[ring] : 0.0) : philox_normal(p.seed, (unsigned int)ring, step);
       pol[ring] = theta + (1.0 / R.relax_time[t] * asin(cross_prod) * p.dt + sqrt(2.0 * drot * p.dt) * nz);
@@ -242,14 +242,20 @@ static int up(Handle *h, const T **dst, const T *src, size_t n) {
   return MAVI_OK;
 }
 
-static double sqrt_le_thr(double d) {
-  double x = d * d;
+// per-type parameter arrays arrive as Float64 (MaviRingsParams) and are stored in the arithmetic type of this build
+static int upr(Handle *h, const real **dst, const double *src, size_t n) {
+  std::vector<real> tmp(src, src + n);
+  return up(h, dst, tmp.data(), n);
+}
+
+static real sqrt_le_thr(real d) {
+  real x = d * d;
   while (std::sqrt(x) <= d) x = std::nextafter(x, INFINITY);
   while (std::sqrt(x) > d) x = std::nextafter(x, -INFINITY);
   return x;
 }
-static double sqrt_ge_thr(double d) {
-  double x = d * d;
+static real sqrt_ge_thr(real d) {
+  real x = d * d;
   while (std::sqrt(x) >= d && x > 0) x = std::nextafter(x, -INFINITY);
   while (std::sqrt(x) < d) x = std::nextafter(x, INFINITY);
   return x;
@@ -271,7 +277,7 @@ int rings_lower(Handle *h, const MaviParams *mp) {
       h->set_error("ring type %d: num_particles must be in [3, n_max]", t + 1);
       return MAVI_ERR_BAD_PARAMS;
     }
-  std::vector<double> inter((size_t)nt * nt * 7);
+  std::vector<real> inter((size_t)nt * nt * 7);
   for (int a = 0; a < nt; a++)
     for (int b = 0; b < nt; b++) {
       const double *s = r->interaction + 4 * (a * nt + b), *st = r->interaction + 4 * (b * nt + a);
@@ -280,7 +286,7 @@ int rings_lower(Handle *h, const MaviParams *mp) {
           h->set_error("InteractionMatrix must be symmetric: the reference applies +f/-f of ONE evaluation to both particles");
           return MAVI_ERR_UNSUPPORTED;
         }
-      double *d = inter.data() + 7 * (a * nt + b);
+      real *d = inter.data() + 7 * (a * nt + b);
       d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
       d[4] = sqrt_le_thr(s[3]);  // dist > dist_max  <=>  r2 > d[4]
       d[5] = sqrt_ge_thr(s[2]);  // dist < dist_eq   <=>  r2 < d[5]
@@ -291,11 +297,11 @@ int rings_lower(Handle *h, const MaviParams *mp) {
   R.n_max = r->n_max;
   R.num_rings = (int)r->num_rings;
   int st;
-  if ((st = up(h, &R.p0, r->p0, nt)) || (st = up(h, &R.relax_time, r->relax_time, nt)) || (st = up(h, &R.vo, r->vo, nt)) ||
-      (st = up(h, &R.mobility, r->mobility, nt)) || (st = up(h, &R.rot_diff, r->rot_diff, nt)) ||
-      (st = up(h, &R.k_area, r->k_area, nt)) || (st = up(h, &R.k_spring, r->k_spring, nt)) ||
-      (st = up(h, &R.l_spring, r->l_spring, nt)) || (st = up(h, &R.num_particles, r->num_particles, nt)) ||
-      (st = up(h, &R.interaction, inter.data(), inter.size())))
+  if ((st = upr(h, &R.p0, r->p0, nt)) || (st = upr(h, &R.relax_time, r->relax_time, nt)) || (st = upr(h, &R.vo, r->vo, nt)) ||
+      (st = upr(h, &R.mobility, r->mobility, nt)) || (st = upr(h, &R.rot_diff, r->rot_diff, nt)) ||
+      (st = upr(h, &R.k_area, r->k_area, nt)) || (st = upr(h, &R.k_spring, r->k_spring, nt)) ||
+      (st = upr(h, &R.l_spring, r->l_spring, nt)) || (st = up(h, &R.num_particles, r->num_particles, nt)) ||
+      (st = up(h, &R.interaction, (const real *)inter.data(), inter.size())))
     return st;
   R.types = nullptr;
   long long n_active = 0;
@@ -332,19 +338,19 @@ int rings_allocate(Handle *h) {
     return MAVI_OK;
   };
   int st;
-  if ((st = al((void **)&a.pos[0], n * sizeof(double2))) || (st = al((void **)&a.force, n * sizeof(double2))) ||
-      (st = al((void **)&a.force_old, n * sizeof(double2))) || (st = al((void **)&a.idflag, n * sizeof(unsigned int))) ||
-      (st = al((void **)&a.cell, n * sizeof(int))) || (st = al((void **)&r.cont_pos, n * sizeof(double2))) ||
-      (st = al((void **)&r.areas, nr * sizeof(double))) || (st = al((void **)&r.cms, nr * sizeof(double2))) ||
-      (st = al((void **)&r.pol, nr * sizeof(double))))
+  if ((st = al((void **)&a.pos[0], n * sizeof(real2))) || (st = al((void **)&a.force, n * sizeof(real2))) ||
+      (st = al((void **)&a.force_old, n * sizeof(real2))) || (st = al((void **)&a.idflag, n * sizeof(unsigned int))) ||
+      (st = al((void **)&a.cell, n * sizeof(int))) || (st = al((void **)&r.cont_pos, n * sizeof(real2))) ||
+      (st = al((void **)&r.areas, nr * sizeof(real))) || (st = al((void **)&r.cms, nr * sizeof(real2))) ||
+      (st = al((void **)&r.pol, nr * sizeof(real))))
     return st;
   h->p.n_count = h->rings_n_active;
   h->ns = n;
-  RINGS_TRY(h, cudaMemsetAsync(a.force, 0, n * sizeof(double2), h->stream));
-  RINGS_TRY(h, cudaMemsetAsync(r.cont_pos, 0, n * sizeof(double2), h->stream));
+  RINGS_TRY(h, cudaMemsetAsync(a.force, 0, n * sizeof(real2), h->stream));
+  RINGS_TRY(h, cudaMemsetAsync(r.cont_pos, 0, n * sizeof(real2), h->stream));
   if (h->p.num_cells > 0) {
     const long long ntiles = (long long)h->p.num_cols * ((h->p.num_rows + MAVI_TR - 1) / MAVI_TR);
-    int cap = ((int)std::ceil(2.0 * h->rings_n_active / (double)ntiles + 16.0) + 15) / 16 * 16;
+    int cap = ((int)std::ceil(2.0 * h->rings_n_active / (real)ntiles + 16.0) + 15) / 16 * 16;
     return rings_alloc_tiles(h, cap);
   }
   return MAVI_OK;
@@ -412,7 +418,7 @@ int rings_bin(Handle *h) {
 static void launch_pair(Handle *h, bool with_walls) {
   const DevParams &p = h->p;
   DevArrays &a = h->a;
-  const size_t smem = (size_t)p.rings.num_types * p.rings.num_types * 7 * sizeof(double);
+  const size_t smem = (size_t)p.rings.num_types * p.rings.num_types * 7 * sizeof(real);
   const int grid = (p.n + TPB - 1) / TPB;
   if (p.periodic) {
     k_rings_pair<true><<<grid, TPB, smem, h->stream>>>(p, a.tstart, a.perm, a.cell, a.idflag, a.pos[0], a.force_old, (int)with_walls);
@@ -422,7 +428,7 @@ static void launch_pair(Handle *h, bool with_walls) {
   h->launches++;
 }
 
-static void launch_ring(Handle *h, int mode, const double *noise, int prime_cms) {
+static void launch_ring(Handle *h, int mode, const real *noise, int prime_cms) {
   const DevParams &p = h->p;
   DevArrays &a = h->a;
   RingsArrays &r = h->r;
@@ -445,8 +451,8 @@ int rings_upload_finish(Handle *h) {
   DevArrays &a = h->a;
   RingsArrays &r = h->r;
   const size_t n = (size_t)p.n;
-  RINGS_TRY(h, cudaMemcpyAsync(a.pos[0], a.st_pos, n * sizeof(double2), cudaMemcpyDeviceToDevice, h->stream));
-  RINGS_TRY(h, cudaMemcpyAsync(r.pol, a.st_ang, (size_t)p.rings.num_rings * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  RINGS_TRY(h, cudaMemcpyAsync(a.pos[0], a.st_pos, n * sizeof(real2), cudaMemcpyDeviceToDevice, h->stream));
+  RINGS_TRY(h, cudaMemcpyAsync(r.pol, a.st_ang, (size_t)p.rings.num_rings * sizeof(real), cudaMemcpyDeviceToDevice, h->stream));
   RINGS_LAUNCH(h, k_rings_ids, (p.n + TPB - 1) / TPB, TPB, p, a.idflag);
   RINGS_TRY(h, cudaMemcpyAsync(a.st_id, a.idflag, n * sizeof(unsigned int), cudaMemcpyDeviceToDevice, h->stream));
   if (p.n_spaces == 1) launch_check_inside(h->ctx(), p, a);
@@ -466,7 +472,7 @@ int rings_calc_forces(Handle *h) {
   return h->check_device_flags();
 }
 
-int rings_step(Handle *h, const double *noise_dev) {
+int rings_step(Handle *h, const real *noise_dev) {
   int st = rings_bin(h);  // update_chunks_all! (after update_cms!, which only reads last step's continuos_pos)
   if (st) return st;
   launch_pair(h, true);
@@ -478,23 +484,23 @@ int rings_step(Handle *h, const double *noise_dev) {
 
 int rings_download_state(Handle *h, void *pos, void *second) {
   const DevParams &p = h->p;
-  if (pos) RINGS_TRY(h, cudaMemcpyAsync(pos, h->a.pos[0], (size_t)p.n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
-  if (second) RINGS_TRY(h, cudaMemcpyAsync(second, h->r.pol, (size_t)p.rings.num_rings * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (pos) RINGS_TRY(h, cudaMemcpyAsync(pos, h->a.pos[0], (size_t)p.n * sizeof(real2), cudaMemcpyDeviceToHost, h->stream));
+  if (second) RINGS_TRY(h, cudaMemcpyAsync(second, h->r.pol, (size_t)p.rings.num_rings * sizeof(real), cudaMemcpyDeviceToHost, h->stream));
   return h->check_device_flags();
 }
 
 int rings_download_forces(Handle *h, void *forces) {
-  RINGS_TRY(h, cudaMemcpyAsync(forces, h->a.force, (size_t)h->p.n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  RINGS_TRY(h, cudaMemcpyAsync(forces, h->a.force, (size_t)h->p.n * sizeof(real2), cudaMemcpyDeviceToHost, h->stream));
   return h->check_device_flags();
 }
 
 int rings_download_info(Handle *h, void *areas, void *cms, void *cont_pos) {
   const DevParams &p = h->p;
   const size_t nr = (size_t)p.rings.num_rings;
-  if (areas) RINGS_TRY(h, cudaMemcpyAsync(areas, h->r.areas, nr * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  if (cms) RINGS_TRY(h, cudaMemcpyAsync(cms, h->r.cms, nr * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+  if (areas) RINGS_TRY(h, cudaMemcpyAsync(areas, h->r.areas, nr * sizeof(real), cudaMemcpyDeviceToHost, h->stream));
+  if (cms) RINGS_TRY(h, cudaMemcpyAsync(cms, h->r.cms, nr * sizeof(real2), cudaMemcpyDeviceToHost, h->stream));
   if (cont_pos)
-    RINGS_TRY(h, cudaMemcpyAsync(cont_pos, p.periodic ? h->r.cont_pos : h->a.pos[0], (size_t)p.n * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+    RINGS_TRY(h, cudaMemcpyAsync(cont_pos, p.periodic ? h->r.cont_pos : h->a.pos[0], (size_t)p.n * sizeof(real2), cudaMemcpyDeviceToHost, h->stream));
   return h->check_device_flags();
 }
 
@@ -537,4 +543,4 @@ int rings_download_cells(Handle *h, int *cell_of_particle, int *counts, int *sta
   return h->check_device_flags();
 }
 
-}  // namespace mavi
+}  // namespace MAVI_NS

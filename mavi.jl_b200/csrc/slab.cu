@@ -19,7 +19,7 @@
 
 #include "handle.cuh"
 
-namespace mavi {
+namespace MAVI_NS {
 
 // ---- minimal NCCL surface, resolved at run time so that single-GPU users need no NCCL at all ---------------------
 typedef struct ncclComm *ncclComm_t;
@@ -211,8 +211,8 @@ __global__ void k_clear_column(const __grid_constant__ DevParams p, int *__restr
 // Immigrants: every received record is queued as an inter-tile mover of THIS rank: record -> mover list, destination
 // tile inbox, tile marked dirty.  The incremental repair then merges it exactly like a local mover.
 __global__ void k_ingest(const __grid_constant__ DevParams p, const EmRec *__restrict__ recs, int count_flag, int em_cap,
-                         int has_vel, double2 *__restrict__ mv_pos, double2 *__restrict__ mv_second,
-                         double2 *__restrict__ mv_force, unsigned int *__restrict__ mv_id, int *__restrict__ mv_cell,
+                         int has_vel, real2 *__restrict__ mv_pos, real2 *__restrict__ mv_second,
+                         real2 *__restrict__ mv_force, unsigned int *__restrict__ mv_id, int *__restrict__ mv_cell,
                          int *__restrict__ mv_src, int *__restrict__ tile_dirty, int *__restrict__ dirty_list,
                          int *__restrict__ inbox_cnt, int *__restrict__ inbox, int *__restrict__ flags,
                          int *__restrict__ chg) {
@@ -257,7 +257,7 @@ __global__ void k_owned_count(const __grid_constant__ DevParams p, const int *__
 static size_t col_slots(const DevParams &p) { return (size_t)p.tpc * p.cap; }
 
 // halo positions (pos_buf = a.pos[0] or a.pos[1]); with_layout also ships the tstart rows of the boundary columns
-int slab_halo_exchange(Handle *h, double2 *pos_buf, bool with_layout, cudaStream_t stream = nullptr) {
+int slab_halo_exchange(Handle *h, real2 *pos_buf, bool with_layout, cudaStream_t stream = nullptr) {
   if (!stream) stream = h->stream;
   const DevParams &p = h->p;
   SlabState &s = h->slab;
@@ -266,19 +266,19 @@ int slab_halo_exchange(Handle *h, double2 *pos_buf, bool with_layout, cudaStream
   const size_t rows = (size_t)p.tpc * TR1;
   // my boundary columns: local 1 (-> left neighbour's right halo) and local m (-> right neighbour's left halo)
   if (!s.comm) {  // one-rank slab mode: I am my own left and right neighbour
-    SLAB_CUDA(h, cudaMemcpyAsync(pos_buf + (m + 1) * cs, pos_buf + 1 * cs, cs * sizeof(double2), cudaMemcpyDeviceToDevice, stream));
-    SLAB_CUDA(h, cudaMemcpyAsync(pos_buf + 0 * cs, pos_buf + m * cs, cs * sizeof(double2), cudaMemcpyDeviceToDevice, stream));
+    SLAB_CUDA(h, cudaMemcpyAsync(pos_buf + (m + 1) * cs, pos_buf + 1 * cs, cs * sizeof(real2), cudaMemcpyDeviceToDevice, stream));
+    SLAB_CUDA(h, cudaMemcpyAsync(pos_buf + 0 * cs, pos_buf + m * cs, cs * sizeof(real2), cudaMemcpyDeviceToDevice, stream));
     if (with_layout) {
       SLAB_CUDA(h, cudaMemcpyAsync(a.tstart + (m + 1) * rows, a.tstart + 1 * rows, rows * sizeof(int), cudaMemcpyDeviceToDevice, stream));
       SLAB_CUDA(h, cudaMemcpyAsync(a.tstart + 0 * rows, a.tstart + m * rows, rows * sizeof(int), cudaMemcpyDeviceToDevice, stream));
     }
   } else {
   SLAB_NCCL(h, g_nccl.GroupStart());
-  SLAB_NCCL(h, g_nccl.Send(pos_buf + 1 * cs, cs * sizeof(double2), ncclInt8, s.left, s.comm, stream));
-  SLAB_NCCL(h, g_nccl.Send(pos_buf + m * cs, cs * sizeof(double2), ncclInt8, s.right, s.comm, stream));
+  SLAB_NCCL(h, g_nccl.Send(pos_buf + 1 * cs, cs * sizeof(real2), ncclInt8, s.left, s.comm, stream));
+  SLAB_NCCL(h, g_nccl.Send(pos_buf + m * cs, cs * sizeof(real2), ncclInt8, s.right, s.comm, stream));
   // receive order matters when left == right (2 GPUs): the peer's FIRST send is its column 1 = my RIGHT halo
-  SLAB_NCCL(h, g_nccl.Recv(pos_buf + (m + 1) * cs, cs * sizeof(double2), ncclInt8, s.right, s.comm, stream));
-  SLAB_NCCL(h, g_nccl.Recv(pos_buf + 0 * cs, cs * sizeof(double2), ncclInt8, s.left, s.comm, stream));
+  SLAB_NCCL(h, g_nccl.Recv(pos_buf + (m + 1) * cs, cs * sizeof(real2), ncclInt8, s.right, s.comm, stream));
+  SLAB_NCCL(h, g_nccl.Recv(pos_buf + 0 * cs, cs * sizeof(real2), ncclInt8, s.left, s.comm, stream));
   if (with_layout) {
     SLAB_NCCL(h, g_nccl.Send(a.tstart + 1 * rows, rows * sizeof(int), ncclInt8, s.left, s.comm, stream));
     SLAB_NCCL(h, g_nccl.Send(a.tstart + m * rows, rows * sizeof(int), ncclInt8, s.right, s.comm, stream));
@@ -421,7 +421,7 @@ int slab_join(Handle *h) {
 // step n+1 never touches the two owned columns next to a halo, so the exchanges C and A and the recomputation of those
 // columns (always done in full: the neighbour's boundary column re-bins behind this rank's back) overlap with K_int.
 // Communicator operations stay totally ordered by the events (B(n) -> C(n) -> A(n+1) -> B(n+1)), identically on all ranks.
-int slab_step_once(Handle *h, const double *noise_dev) {
+int slab_step_once(Handle *h, const real *noise_dev) {
   DevParams &p = h->p;
   DevArrays &a = h->a;
   SlabState &s = h->slab;
@@ -513,4 +513,4 @@ int slab_step_once(Handle *h, const double *noise_dev) {
   return MAVI_OK;
 }
 
-}  // namespace mavi
+}  // namespace MAVI_NS
