@@ -13,14 +13,16 @@ class RingsState:
     def __init__(self, *, rings_pos, pol, num_particles=None, types=None, active_state=None):
         if active_state is not None:
             raise NotImplementedError("variable ring count (sources/sinks) is a 'next' row (SURVEY.md 8f #3)")
-        rp = np.asarray(rings_pos, dtype=np.float64)
+        rp = np.asarray(rings_pos)
+        T = np.float32 if rp.dtype == np.float32 else np.float64  # element type of the state (Float32 mode keeps it)
+        rp = rp.astype(T, copy=False)
         if rp.ndim == 3 and rp.shape[0] == 2 and rp.shape[2] != 2:
             rp = np.transpose(rp, (2, 1, 0))  # Julia Array{T,3}(2, n_max, num_rings)
         assert rp.ndim == 3 and rp.shape[2] == 2
         self.rings_pos = np.ascontiguousarray(rp)
         self.num_rings, self.n_max = rp.shape[0], rp.shape[1]
         self.pos = self.rings_pos.reshape(-1, 2)
-        self.pol = np.ascontiguousarray(pol, dtype=np.float64)
+        self.pol = np.ascontiguousarray(pol, dtype=T)
         if isinstance(num_particles, (list, tuple, np.ndarray)) and types is None:
             raise ValueError("argument 'types' is empty!")
         self.num_particles = self.n_max if num_particles is None else num_particles
