@@ -85,6 +85,7 @@ static int validate_and_lower(Handle *h, const MaviParams *mp) {
   for (int i = 0; i < 8; i++) p.dyn[i] = mp->dyn[i];
   p.particle_radius = mp->particle_radius;
   p.dt = mp->dt;
+  h->dt_host = mp->dt;
   p.term = mp->dt * mp->dt / 2;  // dt^2/2
   p.hdt = mp->dt / 2;
   p.rng_mode = mp->rng_mode;
@@ -449,6 +450,17 @@ int Handle::check_device_flags() {
 }
 
 // Enqueue one step (no host synchronisation).  newton_step! / szabo_step! / rtp_step!, src/integration.jl:507-535.
+int Handle::ensure_id64(size_t n) {
+  if (n <= id64_cap) return MAVI_OK;
+  if (id64_dev) cudaFree(id64_dev);
+  id64_dev = nullptr;
+  id64_cap = 0;
+  const size_t cap = n > (size_t)n_cap ? n : (size_t)n_cap;
+  CUDA_TRY(this, cudaMalloc((void **)&id64_dev, cap * sizeof(long long)));
+  id64_cap = cap;
+  return MAVI_OK;
+}
+
 int Handle::enqueue_step(const real *noise_dev) {
   int st;
   LaunchCtx c = ctx();
@@ -478,7 +490,7 @@ int Handle::enqueue_step(const real *noise_dev) {
     carry_valid = true;
   }
   if (prof) cudaEventRecord(ev[4], stream);
-  time += p.dt;  // update_time!, src/integration.jl:500-503
+  time += dt_host;  // update_time!, src/integration.jl:500-503
   num_steps += 1;
   return MAVI_OK;
 }
@@ -596,6 +608,7 @@ int32_t api_destroy(void *hh) {
     if (ptr) cudaFree(ptr);
   if (h->flags_host) cudaFreeHost(h->flags_host);
   if (h->noise_dev) cudaFree(h->noise_dev);
+  if (h->id64_dev) cudaFree(h->id64_dev);
   for (int i = 0; i < 5; i++)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   for (int i = 0; i < 2; i++)
@@ -726,15 +739,13 @@ int32_t api_download_local(void *hh, int64_t *ids, void *pos, void *second, void
     else CUDA_TRY(h, cudaMemcpyAsync(second, a.st_ang, n * sizeof(real), cudaMemcpyDeviceToHost, h->stream));
   }
   if (forces) CUDA_TRY(h, cudaMemcpyAsync(forces, a.st_force, n * sizeof(real2), cudaMemcpyDeviceToHost, h->stream));
-  std::vector<unsigned int> idbuf;
-  if (ids) {
-    idbuf.resize(n);
-    CUDA_TRY(h, cudaMemcpyAsync(idbuf.data(), a.st_id, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+  if (ids && n > 0) {  // u32 -> int64 on the device, one copy straight into the caller's buffer
+    int st = h->ensure_id64(n);
+    if (st) return st;
+    launch_ids_to_i64(h->ctx(), (int)n, a.st_id, h->id64_dev);
+    CUDA_TRY(h, cudaMemcpyAsync(ids, h->id64_dev, n * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
   }
-  int st = h->check_device_flags();
-  if (ids)
-    for (size_t i = 0; i < n; i++) ids[i] = (int64_t)(idbuf[i] & ~MAVI_INACTIVE_BIT);
-  return st;
+  return h->check_device_flags();
 }
 
 // slab mode upload: the particles whose cell column this rank owns, with their global original ids
@@ -752,13 +763,20 @@ int32_t api_upload_local(void *hh, const int64_t *ids, const void *pos, const vo
   cudaSetDevice(h->device);
   DevArrays &a = h->a;
   const size_t sn = (size_t)n_local;
-  std::vector<unsigned int> id32(sn);
+  long long id_min = 0, id_max = 0;
   for (size_t i = 0; i < sn; i++) {
-    if (ids[i] < 0 || ids[i] >= 0x7fffffffLL) {
-      h->set_error("particle ids must fit in 31 bits");
-      return MAVI_ERR_BAD_PARAMS;
-    }
-    id32[i] = (unsigned int)ids[i];
+    id_min = ids[i] < id_min ? ids[i] : id_min;
+    id_max = ids[i] > id_max ? ids[i] : id_max;
+  }
+  if (id_min < 0 || id_max >= 0x7fffffffLL) {
+    h->set_error("particle ids must fit in 31 bits");
+    return MAVI_ERR_BAD_PARAMS;
+  }
+  if (sn > 0) {  // int64 -> u32 on the device
+    int st = h->ensure_id64(sn);
+    if (st) return st;
+    CUDA_TRY(h, cudaMemcpyAsync(h->id64_dev, ids, sn * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    launch_ids_from_i64(h->ctx(), (int)sn, h->id64_dev, a.st_id);
   }
   CUDA_TRY(h, cudaMemcpyAsync(a.st_pos, pos, sn * sizeof(real2), cudaMemcpyHostToDevice, h->stream));
   if (second) {
@@ -767,7 +785,6 @@ int32_t api_upload_local(void *hh, const int64_t *ids, const void *pos, const vo
     else
       CUDA_TRY(h, cudaMemcpyAsync(a.st_ang, second, sn * sizeof(real), cudaMemcpyHostToDevice, h->stream));
   }
-  CUDA_TRY(h, cudaMemcpyAsync(a.st_id, id32.data(), sn * sizeof(unsigned int), cudaMemcpyHostToDevice, h->stream));
   CUDA_TRY(h, cudaMemsetAsync(a.st_force, 0, sn * sizeof(real2), h->stream));
   CUDA_TRY(h, cudaMemsetAsync(a.flags, 0, FLAG_COUNT * sizeof(int), h->stream));
   h->steps_seen = 0;
@@ -800,6 +817,7 @@ int32_t api_step(void *hh, int64_t nsteps, const void *host_noise) {
     if (total > 0) {
       if (total > h->noise_cap) {
         if (h->noise_dev) cudaFree(h->noise_dev);
+  if (h->id64_dev) cudaFree(h->id64_dev);
         CUDA_TRY(h, cudaMalloc((void **)&h->noise_dev, total * sizeof(real)));
         h->noise_cap = total;
       }

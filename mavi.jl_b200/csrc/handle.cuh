@@ -47,11 +47,15 @@ struct Handle {
   int steps_seen = 0;  // host mirror of the device-side step counter flags[FLAG_STEPS]
   long long num_steps = 0;
   double time = 0.0;
+  double dt_host = 0.0;  // IntCfg.dt as the host passed it (Float64): TimeInfo accumulates it in Float64 in both builds
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_call[2] = {nullptr, nullptr};
   std::vector<void *> allocs;
   real *noise_dev = nullptr;
   size_t noise_cap = 0;
+  long long *id64_dev = nullptr;  // slab mode: staging for the int64 ids of mavi_upload_local / mavi_download_local
+  size_t id64_cap = 0;
+  int ensure_id64(size_t n);
   char err[512] = {0};
 
   bool maps_valid = false;

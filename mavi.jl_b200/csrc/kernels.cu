@@ -94,6 +94,22 @@ void launch_init_staging_ids(const LaunchCtx &c, int n, const unsigned char *mas
   MAVI_LAUNCH(c, k_init_staging_ids, nblk(n), TPB, 0, n, mask, st_id);
 }
 
+// slab-mode state movement: original ids cross the ABI as int64 and live as u32 (+ inactive bit) on the device
+__global__ void k_ids_to_i64(int n, const unsigned int *__restrict__ st_id, long long *__restrict__ out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = (long long)(st_id[k] & ~MAVI_INACTIVE_BIT);
+}
+__global__ void k_ids_from_i64(int n, const long long *__restrict__ in, unsigned int *__restrict__ st_id) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) st_id[k] = (unsigned int)in[k];
+}
+void launch_ids_to_i64(const LaunchCtx &c, int n, const unsigned int *st_id, long long *out) {
+  MAVI_LAUNCH(c, k_ids_to_i64, nblk(n), TPB, 0, n, st_id, out);
+}
+void launch_ids_from_i64(const LaunchCtx &c, int n, const long long *in, unsigned int *st_id) {
+  MAVI_LAUNCH(c, k_ids_from_i64, nblk(n), TPB, 0, n, in, st_id);
+}
+
 // cell id of every staged particle (update_particle_chunk!, src/chunks.jl:120-147) + per-cell histogram
 __global__ void k_build_cell_index(const __grid_constant__ DevParams p, const real2 *__restrict__ st_pos,
                                    const unsigned int *__restrict__ st_id, int *__restrict__ st_cell,

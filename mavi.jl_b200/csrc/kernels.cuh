@@ -71,6 +71,8 @@ void launch_build_index_tiles(const LaunchCtx &c, const DevParams &p, const real
 // dense copy of the current state into staging (rank order)
 void launch_compact_to_staging(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel);
 void launch_init_staging_ids(const LaunchCtx &c, int n, const unsigned char *mask, unsigned int *st_id);
+void launch_ids_to_i64(const LaunchCtx &c, int n, const unsigned int *st_id, long long *out);
+void launch_ids_from_i64(const LaunchCtx &c, int n, const long long *in, unsigned int *st_id);
 // incremental update_chunks!: repair the tiles touched by this step's movers, then refresh the rank maps
 void launch_repair_tiles(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel);
 void launch_exclusive_scan(const LaunchCtx &c, const int *in, int *out, int *partials, int n);

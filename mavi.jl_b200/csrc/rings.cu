@@ -478,7 +478,7 @@ int rings_step(Handle *h, const real *noise_dev) {
   launch_pair(h, true);
   launch_ring(h, 1, noise_dev, 0);
   h->num_steps += 1;  // src/rings/integration.jl:541-542
-  h->time += h->p.dt;
+  h->time += h->dt_host;
   return h->check_device_flags();
 }
 

@@ -484,7 +484,7 @@ int slab_step_once(Handle *h, const real *noise_dev) {
   launch_repair_tiles(c, p, a, vel);
   if (carry) launch_carry_redrift(c, p, a);
   tr.mark(5, h->stream);
-  h->time += p.dt;
+  h->time += h->dt_host;
   h->num_steps += 1;
   // (no host synchronisation here: the owned count and the overflow word are read by slab_sync_counts)
   if (piped) {

@@ -1,4 +1,4 @@
-"""Short workloads for ncu captures: python profiles/prof_run.py [nx] [steps] [lj|szabo|rings]."""
+"""Short workloads for ncu captures: python profiles/prof_run.py [nx] [steps] [lj|lj32|ljself|szabo|rings]."""
 import os
 import sys
 import time
@@ -14,10 +14,11 @@ pkg = entry.load_package()
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 kind = sys.argv[3] if len(sys.argv) > 3 else "lj"
-if kind in ("lj", "ljself"):
+if kind in ("lj", "ljself", "lj32"):
     # ljself: the x-slab machinery on one GPU (MAVI_FLAG_SLAB_SELF), for profiling the multi-GPU step on one rank
     w = bench.lj_workload(pkg, nx, nx, cuda_device=pkg.CUDADevice(flags=pkg.capi.FLAG_SLAB_SELF) if kind == "ljself" else None)
-    s = pkg.System(state=pkg.SecondLawState(pos=w["pos"], vel=w["vel"]), space_cfg=w["space"], dynamic_cfg=w["dyn"], int_cfg=w["int_cfg"])
+    T = np.float32 if kind == "lj32" else np.float64  # lj32: Float32 mode (mavi_f32 build) on the same workload
+    s = pkg.System(state=pkg.SecondLawState(pos=w["pos"].astype(T), vel=w["vel"].astype(T)), space_cfg=w["space"], dynamic_cfg=w["dyn"], int_cfg=w["int_cfg"])
     n = nx * nx
 elif kind == "szabo":
     # BASELINE config C3: examples/szabo.jl parameters, lattice offset 1, cells (n-1)^2, dt 0.01, Philox noise

@@ -41,6 +41,12 @@ def _f32_pair(case):
     return dev, ora
 
 
+def _outliers(a, b, tol):
+    """fraction of particles whose vector differs by more than tol * ||b||_inf"""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float((np.abs(a - b).max(axis=1) > tol * np.abs(b).max()).mean())
+
+
 def _with_flags(case, flags, **kw):
     c = dict(case)
     ic = case["int_cfg"]
@@ -117,8 +123,14 @@ def test_f32_newton_trajectory(cuda_lib, dyn, wall):
         o.step(25)
         g.sync_to_host()
         assert np.abs(g.state.pos - o.pos()).max() / case["geom"].length < TOL32
-        assert H.rel_err(g.state.vel, o.second()) < 1e-4
-        assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-3   # cut-off decisions of single pairs may differ in Float32
+        if dyn == "lj":  # smooth law: every element agrees
+            assert H.rel_err(g.state.vel, o.second()) < 1e-4
+            assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-3
+        else:
+            # HarmTrunc jumps by k_atr (d_max/d_eq - 1) at the cut-off: a pair that crosses d_max one step earlier or
+            # later in Float32 kicks its two particles by ~0.6 dt.  All but a few particles must agree.
+            assert _outliers(g.state.vel, o.second(), 1e-4) < 0.02
+            assert _outliers(g.get_forces(), o.get_forces(), 1e-3) < 0.02
     ke_g, pe_g = g.energies()
     ke_o, pe_o = o.energies()
     assert abs(ke_g - ke_o) < 1e-4 * abs(ke_o)
@@ -199,7 +211,9 @@ def test_f32_rings_trajectory(cuda_lib, kind, chunks):
     dev, ora = _f32_pair(case)
     g, o = H.make_gpu_rings(dev), H.make_oracle(ora)
     assert g._dtype == F32
-    assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-4   # spring forces: differences of nearly equal lengths
+    # stiff springs / contacts (k = 20) through the periodic seam: the box size itself is rounded to Float32
+    # (ulp(L) ~ 4e-6 at L ~ 40), which bounds the force error by ~ k ulp(L) per pair, a few 1e-4 of the largest force
+    assert H.rel_err(g.get_forces(), o.get_forces()) < 5e-4
     noise = np.random.default_rng(3).standard_normal((20, case["num_rings"])).astype(F32)
     g.step(20, noise)
     o.step(20, noise.astype(np.float64))
