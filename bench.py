@@ -90,6 +90,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.uuid, self.samples, self.stop_flag = index, uuid, [], threading.Event()
         self.source = "nvidia-smi"
+        self.ready = threading.Event()    # set once the first sample is in: the timed region starts after that
         self.t_begin = self.t_end = None  # samples outside [t_begin, t_end] (perf_counter) are dropped when both are set
 
     def mark_begin(self):
@@ -116,7 +117,7 @@ class ClockSampler(threading.Thread):
                 nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
         nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)  # fail here (-> fallback) rather than inside the loop
         self.source = "nvml"
-        while not self.stop_flag.is_set():
+        while True:  # at least one sample, also when stop is requested early
             sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
             try:
                 pw = nv.nvmlDeviceGetPowerUsage(h) / 1e3
@@ -127,10 +128,12 @@ class ClockSampler(threading.Thread):
             except Exception:
                 r = 0
             self.samples.append((time.perf_counter(), sm, mx, pw, [bool(r & b) for b in bits]))
-            self.stop_flag.wait(0.005)
+            self.ready.set()
+            if self.stop_flag.wait(0.005):
+                break
 
     def _smi_loop(self):
-        while not self.stop_flag.is_set():
+        while True:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -140,7 +143,9 @@ class ClockSampler(threading.Thread):
                                          [s[3 + i].lower().startswith("active") for i in range(4)]))
             except Exception:
                 pass
-            self.stop_flag.wait(0.02)
+            self.ready.set()
+            if self.stop_flag.wait(0.02):
+                break
 
     def run(self):
         try:
@@ -252,6 +257,7 @@ def run_ours(args):
         uuid = None
     sampler = ClockSampler(local_rank, uuid)
     sampler.start()
+    sampler.ready.wait(timeout=10)  # NVML initialised and the first sample taken before the timed region starts
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.mark_begin()
@@ -340,7 +346,7 @@ def run_ours(args):
     if world == 1 and carry and not args.no_two_pass:
         # A/B: the same workload with the carry switched off (two full force passes per step), for transparency
         system.close()
-        del system
+        system = None
         dev2 = pkg.CUDADevice(device=local_rank, stream=stream, flags=args.flags | pkg.capi.FLAG_NO_FORCE_CARRY)
         w2 = lj_workload(pkg, nx, ny, cuda_device=dev2)
         s2 = pkg.System(state=pkg.SecondLawState(pos=w2["pos"], vel=w2["vel"]), space_cfg=w2["space"], dynamic_cfg=w2["dyn"], int_cfg=w2["int_cfg"])
@@ -353,6 +359,28 @@ def run_ours(args):
         barrier()
         two_pass = {"ms_per_step": e0.elapsed_time(e1) / k2, "steps": k2, "what": "MAVI_FLAG_NO_FORCE_CARRY: full first + second force pass every step"}
         s2.close()
+    float32 = None
+    if world == 1 and not args.no_f32 and not slab_api:
+        # the optional Float32 mode (mavi_f32 build of the same kernels) on the same workload, for reference; the
+        # headline metric stays Float64.  88 B per particle-step (half of the 168 B + the 4-byte cell index)
+        if system is not None:
+            system.close()
+            system = None
+        w3 = lj_workload(pkg, nx, ny, cuda_device=pkg.CUDADevice(device=local_rank, stream=stream, flags=args.flags))
+        s3 = pkg.System(state=pkg.SecondLawState(pos=w3["pos"].astype(np.float32), vel=w3["vel"].astype(np.float32)),
+                        space_cfg=w3["space"], dynamic_cfg=w3["dyn"], int_cfg=w3["int_cfg"])
+        s3.step(args.warmup)
+        k3 = max(10, args.steps // 2)
+        barrier()
+        e0.record()
+        s3.step(k3)
+        e1.record()
+        barrier()
+        ms3 = e0.elapsed_time(e1) / k3
+        float32 = {"ms_per_step": ms3, "steps": k3, "value": n / (ms3 * 1e-3), "unit": "particle-steps/s",
+                   "roofline_step_frac": 88.0 * n / (ms3 * 1e-3) / 1e9 / peak, "bytes_per_particle_step": 88.0,
+                   "what": "MaviParams.dtype = MAVI_F32 (Float32 state and arithmetic), same kernels compiled with real = float"}
+        s3.close()
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         rate, secs, threads, sample = cpu_reference_rate(pkg, args.cpu_steps, 1, sample_n=args.cpu_sample)
@@ -374,6 +402,7 @@ def run_ours(args):
                      "phase_ms": {"pass_a": phase_ms[1], "pass_b": phase_ms[2], "repair_exchange": phase_ms[3]}},
         "cpu_baseline": cpu,
         "two_pass": two_pass,
+        "float32": float32,
         "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                 "steps": e2e_steps,
                 "what": ("per step and rank: mavi_download_local(ids,pos,vel into pinned host) + mavi_upload_local(ids,pos,vel) + mavi_step(1)"
@@ -400,6 +429,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-two-pass", action="store_true", help="skip the A/B run with the force carry switched off")
+    ap.add_argument("--no-f32", action="store_true", help="skip the Float32-mode side measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -39,6 +39,9 @@ enum {
   MAVI_ERR_UNSUPPORTED = 8
 };
 
+/* element type T of the state (src/states.jl:75-125; Float32 via NUM_T, src/init_states.jl:34,63).  The library holds
+ * two builds of every kernel (real = double / float); MaviParams.dtype picks one per handle.  All `void *` state,
+ * force, noise and Rings-info buffers are T[...]; parameters, times and energies are always double. */
 enum { MAVI_F64 = 0, MAVI_F32 = 1 };
 
 /* WallType subtypes, src/configs.jl:235-279 */

@@ -160,7 +160,9 @@ function attach!(system::System)
     bbox = Configs.get_bounding_box(sc.geometry_cfg)
     cc = system.int_cfg.chunks_cfg
     kind, dyn = dyn_block(system.dynamic_cfg)      # unknown DynamicCfg -> MethodError -> caller keeps the CPU path
-    params = Ref(MaviParams(sizeof(MaviParams), 0, length(system.state.pos), length(pairs), 0, Tuple(spaces),
+    T = eltype(eltype(system.state.pos))            # Float64 (default) or Float32: the state's element type picks the build
+    T in (Float64, Float32) || error("CUDADevice supports Float64 and Float32 states, got $T")
+    params = Ref(MaviParams(sizeof(MaviParams), T === Float32 ? 1 : 0, length(system.state.pos), length(pairs), 0, Tuple(spaces),
         Tuple(Float64.(bbox.bottom_left)), bbox.length, bbox.height,
         isnothing(cc) ? 0 : cc.num_cols, isnothing(cc) ? 0 : cc.num_rows, kind, 0, Float64.(dyn),
         minimum(particle_radius(system.dynamic_cfg)), C_NULL, system.int_cfg.dt,
