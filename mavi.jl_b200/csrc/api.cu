@@ -279,7 +279,11 @@ int Handle::alloc_state(int n_active, int cap) {
   void *old[] = {A.pos[0], A.pos[1], A.vel, A.ang, A.idflag, A.cell, A.force, A.force_old, A.tstart, A.tile_prefix,
                  A.perm, A.scan_partials, A.tile_dirty, A.dirty_list, A.inbox_cnt, A.inbox, A.mv_src, A.mv_pos,
                  A.mv_second, A.mv_force, A.mv_id, A.mv_cell, A.chg};
-  for (void *q : old) dev_free(this, q);
+  // slab mode: the owned count changes with every migration, but every array size depends only on the local grid, the
+  // tile capacity and the staging capacity -> a re-upload with an unchanged capacity keeps the allocations
+  const bool reuse = p.slab && p.num_cells > 0 && A.pos[0] != nullptr && cap == p.cap && cap > 0;
+  if (!reuse)
+    for (void *q : old) dev_free(this, q);
   p.n_active = p.num_cells > 0 ? n_active : 0;
   p.n_count = p.slab ? slab.n_global : n_active;
   if (p.num_cells > 0) {
@@ -322,6 +326,12 @@ int Handle::alloc_state(int n_active, int cap) {
   }
   ns = (size_t)p.tail_base + (size_t)(p.slab ? 0 : (p.n - p.n_active));
   int st;
+  if (reuse) {
+    carry_valid = false;
+    CUDA_TRY(this, cudaMemsetAsync(A.force_old, 0, ns * sizeof(real2), stream));
+    CUDA_TRY(this, cudaMemsetAsync(A.pos[1], 0, ns * sizeof(real2), stream));
+    return MAVI_OK;
+  }
   for (int b = 0; b < 2; b++)
     if ((st = dev_alloc(this, &A.pos[b], ns))) return st;
   if (second_kind == SECOND_VEL) {
