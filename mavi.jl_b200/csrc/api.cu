@@ -196,6 +196,8 @@ static int validate_and_lower(Handle *h, const MaviParams *mp) {
       p.szabo_eq2_hi = sqrt_le_threshold(mp->dyn[5]);
       p.szabo_fadh = mp->dyn[4] / mp->dyn[5];
       p.szabo_frep = mp->dyn[3] / (mp->dyn[6] - mp->dyn[5]);
+      p.szabo_inv_tau = 1.0 / mp->dyn[2];
+      p.szabo_namp = std::sqrt(2.0 * mp->dyn[7] * mp->dt);
       break;
     case MAVI_DYN_RTP:
       p.lj_sig2 = mp->dyn[1] * mp->dyn[1];

@@ -80,6 +80,7 @@ struct DevParams {
   real szabo_eq2_hi;             // Szabo: largest r2 with sqrt(r2) <= r_eq          (d > r_eq     <=>  r2 > szabo_eq2_hi)
   real harm_inv_deq;             // HarmTrunc: 1/dist_eq
   real szabo_fadh, szabo_frep;   // Szabo: k_adh/r_eq, k_rep/(r_max-r_eq)  (src/integration.jl:79-83)
+  real szabo_inv_tau, szabo_namp;  // Szabo: 1/relax_time, sqrt(2 rot_diff dt)  (src/integration.jl:460), hoisted out of the kernel
   real particle_radius;
   real dt, term, hdt;            // dt, dt^2/2, dt/2  (src/integration.jl:420-430)
   int n_spaces;
@@ -338,13 +339,17 @@ __device__ __forceinline__ void philox_uniform2(unsigned long long seed, unsigne
   u1 = u01_from_bits(c[2], c[3]);
 }
 
-// one standard normal (Box-Muller) for (id, step)
-// (drawn in double in both builds: the Float32 build rounds the variate once, at the point of use)
+// one standard normal (Box-Muller) for (id, step).  Production-mode noise only has to be N(0,1) to statistical accuracy
+// (the reference draws from Julia's ziggurat randn, which no device stream can reproduce), so the transform runs in single
+// precision: 24-bit uniforms, u0 in (0,1) -> |z| <= sqrt(2 ln 2^25) = 5.9; about 5x fewer instructions than the
+// double-precision log / cospi (the Szabo kernel spent 19 % of its instructions here, profiles/r01_ncu_szabo_rings.md).
 __device__ __forceinline__ double philox_normal(unsigned long long seed, unsigned int id, unsigned long long step) {
-  double u0, u1;
-  philox_uniform2(seed, id, step, u0, u1);
-  double r = sqrt(-2.0 * log(1.0 - u0));  // 1-u0 in (0,1]
-  return r * cospi(2.0 * u1);
+  unsigned int c[4] = {id, (unsigned int)step, (unsigned int)(step >> 32), 0x4d415649u};
+  philox4x32(c, (unsigned int)seed, (unsigned int)(seed >> 32));
+  const float u0 = ((float)(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+  const float u1 = (float)(c[2] >> 8) * (1.0f / 16777216.0f);           // [0,1)
+  const float r = sqrtf(-2.0f * logf(u0));
+  return (double)(r * cospif(2.0f * u1));
 }
 
 __device__ __forceinline__ real sign_d(real x) { return x > real(0) ? real(1) : (x < real(0) ? real(-1) : x); }

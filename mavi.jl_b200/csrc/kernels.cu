@@ -1345,14 +1345,14 @@ __device__ __forceinline__ void self_propelled_update(const DevParams &p, real2 
   real sn, cs;
   sincos(theta, &sn, &cs);
   if (DYN == MAVI_DYN_SZABO) {
-    const real vo = p.dyn[0], mu = p.dyn[1], relax_time = p.dyn[2], drot = p.dyn[7];
+    const real vo = p.dyn[0], mu = p.dyn[1], drot = p.dyn[7];
     real velx = vo * cs + mu * F.x, vely = vo * sn + mu * F.y;
     real speed = sqrt(fabs(velx) + fabs(vely));  // sqrt(sum(abs, vel)) (sic), :448
     real cross_prod = speed > 0.0 ? (cs * vely - sn * velx) / speed : 0.0;
     if (fabs(cross_prod) > 1.0) cross_prod = sign_d(cross_prod);
     real nz = 0.0;
     if (drot != 0.0) nz = (p.rng_mode == MAVI_RNG_HOST_NOISE) ? (noise ? noise[id] : 0.0) : philox_normal(p.seed, id, step);
-    real d_theta = 1.0 / relax_time * asin(cross_prod) * p.dt + sqrt(2.0 * drot * p.dt) * nz;
+    real d_theta = p.szabo_inv_tau * asin(cross_prod) * p.dt + p.szabo_namp * nz;  // 1/relax_time * asin(c) * dt + sqrt(2 D_r dt) * randn()
     r.x += velx * p.dt;
     r.y += vely * p.dt;
     ang[k] = theta + d_theta;

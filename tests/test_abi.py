@@ -56,3 +56,37 @@ def test_missing_library_fails_loudly(mavi, tmp_path):
     import pytest
     with pytest.raises(FileNotFoundError):
         mavi.capi.load_library(str(tmp_path / "nope.so"))
+
+
+def test_both_arithmetic_builds_are_linked(mavi):
+    """libmavi_cuda.so carries the Float64 and the Float32 build of every per-type entry point (csrc/api_decl.inc)."""
+    import subprocess
+    path = mavi.build_library()
+    syms = subprocess.check_output(["nm", "-C", "--defined-only", path], text=True)
+    decl = open(os.path.join(entry.PKG_DIR, "csrc", "api_decl.inc")).read()
+    names = re.findall(r"\b(api_[a-z0-9_]+)\(", decl)
+    assert len(names) == len(_declared_symbols())
+    for ns in ("mavi_f64", "mavi_f32"):
+        for n in names:
+            assert f"{ns}::{n}(" in syms, f"{ns}::{n} missing"
+
+
+def test_create_without_a_device_fails_loudly(mavi):
+    """No CPU fallback: on a box without a CUDA device mavi_create returns MAVI_ERR_CUDA (both dtypes) with a message,
+    and the handle can still be queried and destroyed.  (On a GPU box this test is a no-op.)"""
+    import numpy as np
+    import pytest
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a CUDA device is present")
+    except ImportError:
+        pass
+    for T in (np.float64, np.float32):
+        pos, geom = mavi.rectangular_grid(4, 4, 0.4, 0.5)
+        st = mavi.SecondLawState(pos=pos.astype(T), vel=np.zeros_like(pos, dtype=T))
+        with pytest.raises(mavi.MaviError) as e:
+            mavi.System(state=st, space_cfg=mavi.SpaceCfg(wall_type=mavi.PeriodicWalls(), geometry_cfg=geom),
+                        dynamic_cfg=mavi.LenJonesCfg(sigma=1.0, epsilon=1.0),
+                        int_cfg=mavi.IntCfg(dt=0.001, chunks_cfg=mavi.ChunksCfg(num_cols=3, num_rows=3)))
+        assert e.value.status == mavi.capi.ERR_CUDA and "no CPU fallback" in str(e.value)
