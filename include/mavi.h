@@ -201,6 +201,22 @@ int32_t mavi_energies(MaviHandle *h, int32_t pe_mode, double *ke, double *pe);
  * areas[num_rings], cms[2*num_rings], cont_pos[2*n] (continuos_pos).  Any pointer may be NULL. */
 int32_t mavi_rings_download_info(MaviHandle *h, void *areas, void *cms, void *cont_pos);
 
+/* ---- particle contact lists, src/rings/neighbors.jl:11-136 (RingsSystem p_neighbors_cfg, src/rings/rings.jl:143-158) ----
+ * mavi_rings_set_neighbors: NeighborsCfg(only_count, type, tol).  mode MAVI_NEIGH_COUNT == only_count=true,
+ * MAVI_NEIGH_LIST keeps up to MAVI_NEIGH_MAX = 15 neighbour ids per particle (num_max_neighbors, src/rings/rings.jl:145);
+ * type_all != 0 is type = :all, 0 is :rings (particles of the same ring are not neighbours).  Call it after
+ * mavi_create and before mavi_upload_state to have the constructor's first forces! fill the lists like the reference
+ * (src/rings/rings.jl:280-288); every later forces! (mavi_step, mavi_calc_forces) cleans and refills them
+ * (neigh_clean!, src/rings/integration.jl:362; neigh_update!, :42).
+ * mavi_rings_download_neighbors: count[n] (get_neigh_count) and list[n][15] (get_neigh_list; 0-based particle ids in
+ * ASCENDING order, -1 padded — the reference appends in pair-enumeration order and compares sorted lists).  Either
+ * pointer may be NULL.  MAVI_ERR_CAPACITY when a particle has more than 15 contacts in list mode (the reference's
+ * BoundsError). */
+enum { MAVI_NEIGH_OFF = 0, MAVI_NEIGH_COUNT = 1, MAVI_NEIGH_LIST = 2 };
+#define MAVI_NEIGH_MAX 15
+int32_t mavi_rings_set_neighbors(MaviHandle *h, int32_t mode, int32_t type_all, double tol);
+int32_t mavi_rings_download_neighbors(MaviHandle *h, int32_t *count, int32_t *list);
+
 /* TimeInfo, src/systems.jl:30-33 (time += dt accumulated in Float64, src/integration.jl:500-503) */
 int32_t mavi_get_time(MaviHandle *h, int64_t *num_steps, double *time);
 int32_t mavi_set_time(MaviHandle *h, int64_t num_steps, double time);

@@ -32,6 +32,8 @@ FLAG_TIGHT_TILES = 2
 FLAG_NO_FORCE_CARRY = 4
 FLAG_SMALL_BLOCKS = 8
 FLAG_SLAB_SELF = 16
+NEIGH_OFF, NEIGH_COUNT, NEIGH_LIST = range(3)
+NEIGH_MAX = 15
 
 
 class MaviLine(C.Structure):
@@ -98,6 +100,8 @@ SIGNATURES = {
     "mavi_cell_neighbors": (C.c_int32, [_H, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mavi_energies": (C.c_int32, [_H, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mavi_rings_download_info": (C.c_int32, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mavi_rings_set_neighbors": (C.c_int32, [_H, C.c_int32, C.c_int32, C.c_double]),
+    "mavi_rings_download_neighbors": (C.c_int32, [_H, C.c_void_p, C.c_void_p]),
     "mavi_get_time": (C.c_int32, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "mavi_set_time": (C.c_int32, [_H, C.c_int64, C.c_double]),
     "mavi_sync": (C.c_int32, [_H]),

@@ -969,6 +969,20 @@ int32_t api_rings_download_info(void *hh, void *areas, void *cms, void *cont_pos
   return rings_download_info(h, areas, cms, cont_pos);
 }
 
+int32_t api_rings_set_neighbors(void *hh, int32_t mode, int32_t type_all, double tol) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return MAVI_ERR_BAD_PARAMS;
+  cudaSetDevice(h->device);
+  return rings_set_neighbors(h, mode, type_all, tol);
+}
+
+int32_t api_rings_download_neighbors(void *hh, int32_t *count, int32_t *list) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return MAVI_ERR_BAD_PARAMS;
+  cudaSetDevice(h->device);
+  return rings_download_neighbors(h, count, list);
+}
+
 int32_t api_get_time(void *hh, int64_t *num_steps, double *time) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h) return MAVI_ERR_BAD_PARAMS;

@@ -79,6 +79,12 @@ int32_t mavi_energies(MaviHandle *h, int32_t pe_mode, double *ke, double *pe) { 
 int32_t mavi_rings_download_info(MaviHandle *h, void *areas, void *cms, void *cont_pos) {
   MAVI_FWD(h, api_rings_download_info(impl, areas, cms, cont_pos));
 }
+int32_t mavi_rings_set_neighbors(MaviHandle *h, int32_t mode, int32_t type_all, double tol) {
+  MAVI_FWD(h, api_rings_set_neighbors(impl, mode, type_all, tol));
+}
+int32_t mavi_rings_download_neighbors(MaviHandle *h, int32_t *count, int32_t *list) {
+  MAVI_FWD(h, api_rings_download_neighbors(impl, count, list));
+}
 int32_t mavi_get_time(MaviHandle *h, int64_t *num_steps, double *time) { MAVI_FWD(h, api_get_time(impl, num_steps, time)); }
 int32_t mavi_set_time(MaviHandle *h, int64_t num_steps, double time) { MAVI_FWD(h, api_set_time(impl, num_steps, time)); }
 int32_t mavi_sync(MaviHandle *h) { MAVI_FWD(h, api_sync(impl)); }

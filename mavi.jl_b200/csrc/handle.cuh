@@ -14,6 +14,12 @@ struct RingsArrays {
   real *areas = nullptr;
   real2 *cms = nullptr;       // info.cms (lags one step, src/rings/integration.jl:523)
   real *pol = nullptr;        // state.pol, one angle per ring
+  // ParticleNeighbors (src/rings/neighbors.jl, src/rings/rings.jl:143-158): contact counts / lists of the last forces!
+  int *neigh_count = nullptr;   // [n]
+  int *neigh_list = nullptr;    // [n][MAVI_NEIGH_MAX], ascending ids, -1 padded (list mode only)
+  int neigh_mode = 0;           // MAVI_NEIGH_*
+  int neigh_all = 0;            // 1: type = :all, 0: type = :rings (other rings only)
+  double neigh_tol = 1.1;       // NeighborsCfg.tol
 };
 
 // x-slab decomposition state (slab.cu)
@@ -94,5 +100,7 @@ int rings_download_state(Handle *h, void *pos, void *second);
 int rings_download_forces(Handle *h, void *forces);
 int rings_bin(Handle *h);
 int rings_download_cells(Handle *h, int *cell_of_particle, int *counts, int *start, int *ids);
+int rings_set_neighbors(Handle *h, int mode, int type_all, double tol);
+int rings_download_neighbors(Handle *h, int *count, int *list);
 
 }  // namespace MAVI_NS

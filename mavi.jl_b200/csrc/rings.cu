@@ -95,6 +95,58 @@ __global__ void __launch_bounds__(TPB) k_rings_pair(const __grid_constant__ DevP
   fpair[i] = make_real2(fx, fy);
 }
 
+// neigh_update!(::ParticleNeighbors, ...) (src/rings/neighbors.jl:125-134) over the pair set of calc_forces!, as a gather:
+// particle i counts (and lists) every j of its stencil with  dist < max_dist * tol  and (type == :all or other ring),
+// max_dist = 2 particle_radius(interaction_cfg) = dist_eq (src/rings/integration.jl:40-41).  The reference appends in
+// pair-enumeration order and its own test compares sorted lists (test/tests_rings/tests_general.jl:84-95): the device
+// list is ascending.  Separate from k_rings_pair so that runs without neighbour tracking are untouched.
+template <bool PER>
+__global__ void __launch_bounds__(TPB) k_rings_neighbors(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
+                                                         const int *__restrict__ perm, const int *__restrict__ cell,
+                                                         const unsigned int *__restrict__ idflag,
+                                                         const real2 *__restrict__ pos, int type_all, real tol,
+                                                         int *__restrict__ count, int *__restrict__ list) {
+  const DevRings &R = p.rings;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  int cnt = 0;
+  int mine[MAVI_NEIGH_MAX];
+  if (!(idflag[i] & MAVI_INACTIVE_BIT)) {
+    const int ring = i / R.n_max;
+    const int ti = ring_type(R, ring);
+    const real2 ri = pos[i];
+    auto visit = [&](int j) {
+      const int rj_ring = j / R.n_max;
+      if (!type_all && rj_ring == ring) return;
+      const real2 rj = __ldg(pos + j);
+      const real dx = min_image<PER>(ri.x - rj.x, p.half[0], p.size[0]);
+      const real dy = min_image<PER>(ri.y - rj.y, p.half[1], p.size[1]);
+      const real dist = sqrt(dist2_exact(dx, dy));
+      const real max_dist = R.interaction[7 * (ti * R.num_types + ring_type(R, rj_ring)) + 2];  // 2 * (dist_eq / 2)
+      if (dist < max_dist * tol) {
+        if (list && cnt < MAVI_NEIGH_MAX) {  // insertion keeps the list ascending
+          int q = cnt;
+          while (q > 0 && mine[q - 1] > j) { mine[q] = mine[q - 1]; --q; }
+          mine[q] = j;
+        }
+        ++cnt;
+      }
+    };
+    if (p.num_cells == 0) {
+      for (int j = 0; j < p.n; j++)
+        if (j != i && !(idflag[j] & MAVI_INACTIVE_BIT)) visit(j);
+    } else {
+      for_each_neighbor(p, tstart, cell[i], -1, [&](int s) {
+        const int j = __ldg(perm + s);
+        if (j != i) visit(j);
+      });
+    }
+  }
+  count[i] = cnt;
+  if (list)
+    for (int q = 0; q < MAVI_NEIGH_MAX; q++) list[(size_t)i * MAVI_NEIGH_MAX + q] = (q < cnt) ? mine[q] : -1;
+}
+
 // One warp per ring.  MODE 0: forces! only (constructor priming / mavi_calc_forces); MODE 1: full step.
 template <bool PER, int MODE>
 __global__ void __launch_bounds__(RING_WARPS * 32) k_rings_ring(
@@ -426,6 +478,15 @@ static void launch_pair(Handle *h, bool with_walls) {
     k_rings_pair<false><<<grid, TPB, smem, h->stream>>>(p, a.tstart, a.perm, a.cell, a.idflag, a.pos[0], a.force_old, (int)with_walls);
   }
   h->launches++;
+  RingsArrays &r = h->r;
+  if (r.neigh_mode != MAVI_NEIGH_OFF && r.neigh_count) {  // neigh_clean! + neigh_update! of this forces! call
+    int *list = r.neigh_mode == MAVI_NEIGH_LIST ? r.neigh_list : nullptr;
+    if (p.periodic) {
+      RINGS_LAUNCH(h, (k_rings_neighbors<true>), grid, TPB, p, a.tstart, a.perm, a.cell, a.idflag, a.pos[0], r.neigh_all, (real)r.neigh_tol, r.neigh_count, list);
+    } else {
+      RINGS_LAUNCH(h, (k_rings_neighbors<false>), grid, TPB, p, a.tstart, a.perm, a.cell, a.idflag, a.pos[0], r.neigh_all, (real)r.neigh_tol, r.neigh_count, list);
+    }
+  }
 }
 
 static void launch_ring(Handle *h, int mode, const real *noise, int prime_cms) {
@@ -541,6 +602,67 @@ int rings_download_cells(Handle *h, int *cell_of_particle, int *counts, int *sta
     if (start) start[p.num_cells] = acc;
   }
   return h->check_device_flags();
+}
+
+// NeighborsCfg (src/rings/neighbors.jl:11-15) for the particle contact lists; mode MAVI_NEIGH_OFF frees nothing and
+// simply stops the tracking.  Takes effect at the next forces! (upload, mavi_calc_forces, mavi_step).
+int rings_set_neighbors(Handle *h, int mode, int type_all, double tol) {
+  if (h->p.dynamics != MAVI_DYN_RINGS) {
+    h->set_error("contact lists are a Mavi.Rings feature (RingsSystem p_neighbors_cfg)");
+    return MAVI_ERR_BAD_PARAMS;
+  }
+  if (mode < MAVI_NEIGH_OFF || mode > MAVI_NEIGH_LIST || !(tol > 0.0)) {
+    h->set_error("bad neighbour mode / tol");
+    return MAVI_ERR_BAD_PARAMS;
+  }
+  RingsArrays &r = h->r;
+  const size_t n = (size_t)h->p.n;
+  auto al = [&](int **ptr, size_t count) -> int {
+    if (*ptr) return MAVI_OK;
+    if (cudaMalloc((void **)ptr, (count ? count : 1) * sizeof(int)) != cudaSuccess) {
+      h->set_error("cudaMalloc failed (neighbour lists)");
+      return MAVI_ERR_CUDA;
+    }
+    h->allocs.push_back((void *)*ptr);
+    return MAVI_OK;
+  };
+  int st;
+  if (mode != MAVI_NEIGH_OFF && (st = al(&r.neigh_count, n))) return st;
+  if (mode == MAVI_NEIGH_LIST && (st = al(&r.neigh_list, n * MAVI_NEIGH_MAX))) return st;
+  if (mode != MAVI_NEIGH_OFF) RINGS_TRY(h, cudaMemsetAsync(r.neigh_count, 0, (n ? n : 1) * sizeof(int), h->stream));
+  if (mode == MAVI_NEIGH_LIST) RINGS_TRY(h, cudaMemsetAsync(r.neigh_list, 0xff, (n ? n : 1) * MAVI_NEIGH_MAX * sizeof(int), h->stream));
+  r.neigh_mode = mode;
+  r.neigh_all = type_all ? 1 : 0;
+  r.neigh_tol = tol;
+  return MAVI_OK;
+}
+
+// get_neigh_count / get_neigh_list (src/rings/neighbors.jl:58-62) for every particle slot
+int rings_download_neighbors(Handle *h, int *count, int *list) {
+  RingsArrays &r = h->r;
+  if (r.neigh_mode == MAVI_NEIGH_OFF || !r.neigh_count) {
+    h->set_error("neighbour tracking is off (mavi_rings_set_neighbors)");
+    return MAVI_ERR_BAD_PARAMS;
+  }
+  if (list && r.neigh_mode != MAVI_NEIGH_LIST) {
+    h->set_error("only_count mode keeps no lists");
+    return MAVI_ERR_BAD_PARAMS;
+  }
+  const size_t n = (size_t)h->p.n;
+  std::vector<int> tmp;
+  int *cdst = count;
+  if (!cdst && list) { tmp.resize(n); cdst = tmp.data(); }
+  if (cdst) RINGS_TRY(h, cudaMemcpyAsync(cdst, r.neigh_count, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (list) RINGS_TRY(h, cudaMemcpyAsync(list, r.neigh_list, n * MAVI_NEIGH_MAX * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  int st = h->check_device_flags();
+  if (st) return st;
+  if (list)
+    for (size_t i = 0; i < n; i++)
+      if (cdst[i] > MAVI_NEIGH_MAX) {  // the reference writes past its 15-entry table here (BoundsError)
+        h->set_error("particle %zu has %d contacts, more than the %d a list holds (BoundsError in the reference)", i, cdst[i], MAVI_NEIGH_MAX);
+        return MAVI_ERR_CAPACITY;
+      }
+  return MAVI_OK;
 }
 
 }  // namespace MAVI_NS

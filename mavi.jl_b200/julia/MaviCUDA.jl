@@ -262,4 +262,30 @@ function device_energies(system::System; stencil_only=false)
     return ke[], pe[]
 end
 
+"""
+Particle contact lists of a RingsSystem built with `p_neighbors_cfg` (src/rings/rings.jl:143-158): call
+`enable_particle_neighbors!` right after `mavi_create` (inside `attach!`, before the upload) and
+`sync_particle_neighbors!` wherever host code reads `system.info.p_neigh` (src/rings/neighbors.jl:58-62).
+Ids cross the ABI 0-based; lists come back ascending (the reference appends in pair order and compares sorted lists).
+"""
+function enable_particle_neighbors!(ds::DeviceState, p_neigh)
+    neigh = p_neigh.neighbors
+    mode = isnothing(neigh.list) ? 1 : 2                       # MAVI_NEIGH_COUNT / MAVI_NEIGH_LIST
+    check(ds, ccall((:mavi_rings_set_neighbors, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Float64),
+                    ds.h, mode, p_neigh.type == :all ? 1 : 0, neigh.cfg.tol))
+end
+
+function sync_particle_neighbors!(system)
+    ds = handle(system)
+    neigh = system.info.p_neigh.neighbors
+    n = size(neigh.count, 1)
+    count = Vector{Int32}(undef, n)
+    list = isnothing(neigh.list) ? Int32[] : Matrix{Int32}(undef, 15, n)   # num_max_neighbors = 15, column per particle
+    GC.@preserve count list check(ds, ccall((:mavi_rings_download_neighbors, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}),
+        ds.h, pointer(count), isempty(list) ? C_NULL : pointer(list)))
+    neigh.count[:, 1] .= count
+    isnothing(neigh.list) || (neigh.list[:, :, 1] .= list .+ 1)            # back to 1-based ids (padding -1 -> 0)
+    return neigh
+end
+
 end # module

@@ -97,6 +97,19 @@ class RingsCfg(DynamicCfg):
         return r[0] if len(r) == 1 else r
 
 
+@dataclass
+class NeighborsCfg:
+    """src/rings/neighbors.jl:11-15.  `type` is "rings" (:rings, particles of other rings only) or "all" (:all)."""
+    only_count: bool = False
+    type: str = "all"
+    tol: float = 1.1
+
+    def __post_init__(self):
+        self.type = str(self.type).lstrip(":")
+        if self.type not in ("rings", "all"):
+            raise ValueError("NeighborsCfg.type must be :rings or :all")
+
+
 def RingsIntCfg(*, dt, p_chunks_cfg=None, r_chunks_cfg=None, invasions_cfg=None, device=None):
     """src/rings/configs.jl:343-351.  Ring-level chunks / invasions are "next" rows (SURVEY.md 8f #4)."""
     if r_chunks_cfg is not None or invasions_cfg is not None:

@@ -38,7 +38,7 @@ def _ptr(a):
 
 class System:
     def __init__(self, *, state, space_cfg: SpaceCfg, dynamic_cfg, int_cfg, info=None, debug_info=None,
-                 time_info=None, sys_type="standard", rng=None):
+                 time_info=None, sys_type="standard", rng=None, p_neighbors_cfg=None):
         self.state = state
         self.space_cfg = space_cfg
         self.dynamic_cfg = dynamic_cfg
@@ -59,6 +59,13 @@ class System:
         self._forces = None
         self._check(self._lib.mavi_create(C.byref(self._lowered.params), C.byref(self._h)))
         self._check(self._lib.mavi_set_time(self._h, self.time_info.num_steps, self.time_info.time))
+        self.p_neighbors_cfg = p_neighbors_cfg
+        if p_neighbors_cfg is not None:
+            # RingsInfo(p_neighbors_cfg=...), src/rings/rings.jl:143-158: before the upload, so that the constructor's
+            # first forces! fills the lists like the reference's (src/rings/rings.jl:280-288)
+            mode = capi.NEIGH_COUNT if p_neighbors_cfg.only_count else capi.NEIGH_LIST
+            self._check(self._lib.mavi_rings_set_neighbors(self._h, mode, int(p_neighbors_cfg.type == "all"),
+                                                           float(p_neighbors_cfg.tol)))
         self._slab = int_cfg.device.world > 1 or bool(int_cfg.device.flags & capi.FLAG_SLAB_SELF)
         if self._slab:
             ids = getattr(state, "ids", None)
@@ -222,6 +229,17 @@ class System:
         self._check(self._lib.mavi_last_step_ms(self._h, ms))
         return list(ms)
 
+    def particle_neighbors(self):
+        """(count[n], lists): contact counts and, unless only_count, the neighbour ids of every particle (ascending;
+        the reference appends in pair-enumeration order and compares sorted lists)."""
+        if self.p_neighbors_cfg is None:
+            raise ValueError("the system was built without p_neighbors_cfg")
+        count = np.zeros(self._n, dtype=np.int32)
+        only = self.p_neighbors_cfg.only_count
+        lst = None if only else np.empty((self._n, capi.NEIGH_MAX), dtype=np.int32)
+        self._check(self._lib.mavi_rings_download_neighbors(self._h, _ptr(count), _ptr(lst)))
+        return count, (None if only else [lst[i, :count[i]].tolist() for i in range(self._n)])
+
     def rings_info(self):
         nr = self.state.num_rings
         areas = np.empty(nr, dtype=self._dtype)
@@ -233,6 +251,16 @@ class System:
 
 def get_forces(system):
     return system.get_forces()
+
+
+def get_neigh_count(system):
+    """`get_neigh_count(system.info.p_neigh)`, src/rings/neighbors.jl:62 (downloads)."""
+    return system.particle_neighbors()[0]
+
+
+def get_neigh_list(system, pid):
+    """`get_neigh_list(system.info.p_neigh, id)`, src/rings/neighbors.jl:58-61 (0-based ids, ascending)."""
+    return system.particle_neighbors()[1][pid]
 
 
 def get_num_total_particles(system):

@@ -38,6 +38,13 @@ struct OrSystem {
   int8_t *neigh_n;
   /* RingsInfo (src/rings/rings.jl:118-128) */
   double *cont_pos, *areas, *cms;
+  /* ParticleNeighbors (src/rings/neighbors.jl:52-56, src/rings/rings.jl:143-158): one slice (the thread slices of the
+   * Threaded device are summed by neigh_sum_buffers, :76-100; here updates go to the main slice under a lock) */
+  int32_t pn_mode, pn_all;
+  double pn_tol;
+  int32_t *pn_count; /* [n] */
+  int32_t *pn_list;  /* [n][15], pair-enumeration order like the reference */
+  int32_t pn_overflow;
   int64_t num_steps;
   double time;
   char err[256];
@@ -138,6 +145,23 @@ static void rings_interaction(const OrSystem *s, int64_t i, int64_t j, double *f
   mor_calc_diff(s, s->pos + 2 * i, s->pos + 2 * j, dr);
   double dist = sqrt(dr[0] * dr[0] + dr[1] * dr[1]);
   const double k_rep = ic[0], k_atr = ic[1], dist_eq = ic[2], dist_max = ic[3];
+  if (s->pn_mode) {
+    /* max_dist = 2 * particle_radius(interaction_cfg) (src/rings/integration.jl:40-41; HarmTruncCfg radius = dist_eq/2,
+     * src/configs.jl:418-421); neigh_update!(::ParticleNeighbors, ...) src/rings/neighbors.jl:125-134 */
+    double max_dist = 2 * (dist_eq / 2);
+    if (dist < max_dist * s->pn_tol && (s->pn_all || ri != rj)) {
+      OrSystem *m = (OrSystem *)s;
+#pragma omp critical(mor_neigh)
+      {
+        /* neigh_update_data!, src/rings/neighbors.jl:102-116 */
+        int32_t ci = ++m->pn_count[i], cj = ++m->pn_count[j];
+        if (m->pn_mode == MAVI_NEIGH_LIST) {
+          if (ci <= MAVI_NEIGH_MAX) m->pn_list[i * MAVI_NEIGH_MAX + ci - 1] = (int32_t)j; else m->pn_overflow = 1;
+          if (cj <= MAVI_NEIGH_MAX) m->pn_list[j * MAVI_NEIGH_MAX + cj - 1] = (int32_t)i; else m->pn_overflow = 1;
+        }
+      }
+    }
+  }
   f[0] = 0.0; f[1] = 0.0;
   if (dist > dist_max) return;
   if (ri == rj) {
@@ -690,6 +714,10 @@ static double calc_area(const double *pts, int32_t np) {
 
 /* forces!, src/rings/integration.jl:197-226 = calc_forces! + springs (:79-97) + area_forces! (:140-195) */
 static void rings_forces(OrSystem *s) {
+  if (s->pn_mode) { /* neigh_clean!, src/rings/integration.jl:362 */
+    memset(s->pn_count, 0, sizeof(int32_t) * (size_t)s->n);
+    if (s->pn_list) memset(s->pn_list, 0xff, sizeof(int32_t) * (size_t)s->n * MAVI_NEIGH_MAX);
+  }
   mor_pair_forces(s);
   double *forces = s->forces[0];
   const int64_t nm = s->rp.n_max;
@@ -984,6 +1012,7 @@ void mor_destroy(OrSystem *s) {
   }
   free(s->chunk_particles); free(s->num_in_chunk); free(s->neigh); free(s->neigh_n);
   free(s->cont_pos); free(s->areas); free(s->cms);
+  free(s->pn_count); free(s->pn_list);
   free(s);
 }
 
@@ -1101,6 +1130,34 @@ int32_t mor_cell_neighbors(OrSystem *s, int32_t cell, int32_t *out4, int32_t *n)
 }
 
 int64_t mor_chunk_capacity(OrSystem *s) { return s->nc; }
+
+/* NeighborsCfg for the particle contact lists (RingsSystem p_neighbors_cfg); call before mor_upload_state to have the
+ * constructor's forces! fill them (src/rings/rings.jl:280-288) */
+int32_t mor_rings_set_neighbors(OrSystem *s, int32_t mode, int32_t type_all, double tol) {
+  if (s->p.dynamics != MAVI_DYN_RINGS || mode < MAVI_NEIGH_OFF || mode > MAVI_NEIGH_LIST) return MAVI_ERR_BAD_PARAMS;
+  free(s->pn_count); free(s->pn_list);
+  s->pn_count = NULL; s->pn_list = NULL;
+  s->pn_mode = mode; s->pn_all = type_all ? 1 : 0; s->pn_tol = tol; s->pn_overflow = 0;
+  if (mode) s->pn_count = (int32_t *)calloc((size_t)s->n + 1, sizeof(int32_t));
+  if (mode == MAVI_NEIGH_LIST) {
+    s->pn_list = (int32_t *)malloc(sizeof(int32_t) * ((size_t)s->n * MAVI_NEIGH_MAX + 1));
+    memset(s->pn_list, 0xff, sizeof(int32_t) * ((size_t)s->n * MAVI_NEIGH_MAX + 1));
+  }
+  return MAVI_OK;
+}
+
+/* get_neigh_count / get_neigh_list, src/rings/neighbors.jl:58-62 (lists in the reference's append order, -1 padded) */
+int32_t mor_rings_download_neighbors(OrSystem *s, int32_t *count, int32_t *list) {
+  if (!s->pn_mode) return MAVI_ERR_BAD_PARAMS;
+  if (list && s->pn_mode != MAVI_NEIGH_LIST) return MAVI_ERR_BAD_PARAMS;
+  if (s->pn_overflow) {
+    snprintf(s->err, sizeof s->err, "a particle has more than %d contacts: BoundsError in the reference", MAVI_NEIGH_MAX);
+    return MAVI_ERR_CAPACITY;
+  }
+  if (count) memcpy(count, s->pn_count, sizeof(int32_t) * (size_t)s->n);
+  if (list) memcpy(list, s->pn_list, sizeof(int32_t) * (size_t)s->n * MAVI_NEIGH_MAX);
+  return MAVI_OK;
+}
 
 int32_t mor_rings_download_info(OrSystem *s, double *areas, double *cms, double *cont_pos) {
   if (s->p.dynamics != MAVI_DYN_RINGS) return MAVI_ERR_BAD_PARAMS;

@@ -47,6 +47,8 @@ int64_t mor_chunk_capacity(OrSystem *s); /* nc of src/chunks.jl:32-35 */
 
 int32_t mor_energies(OrSystem *s, int32_t pe_mode, double *ke, double *pe);
 int32_t mor_rings_download_info(OrSystem *s, double *areas, double *cms, double *cont_pos);
+int32_t mor_rings_set_neighbors(OrSystem *s, int32_t mode, int32_t type_all, double tol);
+int32_t mor_rings_download_neighbors(OrSystem *s, int32_t *count, int32_t *list);
 int32_t mor_get_time(OrSystem *s, int64_t *num_steps, double *time);
 
 /* fine-grained operators for unit tests (each is one reference function) */

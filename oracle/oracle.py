@@ -41,7 +41,9 @@ def load():
         "mor_bin": (i32, [H]), "mor_download_cells": (i32, [H, vp, vp]), "mor_download_cell_lists": (i32, [H, vp, vp]),
         "mor_cell_neighbors": (i32, [H, i32, C.POINTER(i32), C.POINTER(i32)]), "mor_chunk_capacity": (i64, [H]),
         "mor_energies": (i32, [H, i32, C.POINTER(dbl), C.POINTER(dbl)]),
-        "mor_rings_download_info": (i32, [H, vp, vp, vp]), "mor_get_time": (i32, [H, C.POINTER(i64), C.POINTER(dbl)]),
+        "mor_rings_download_info": (i32, [H, vp, vp, vp]),
+        "mor_rings_set_neighbors": (i32, [H, i32, i32, dbl]), "mor_rings_download_neighbors": (i32, [H, vp, vp]),
+        "mor_get_time": (i32, [H, C.POINTER(i64), C.POINTER(dbl)]),
         "mor_clean_forces": (None, [H]), "mor_update_chunks": (i32, [H]), "mor_pair_forces": (None, [H]),
         "mor_walls_forces": (None, [H]), "mor_walls": (None, [H]), "mor_update_verlet": (None, [H]),
         "mor_julia_div": (dbl, [dbl, dbl]), "mor_calc_diff": (None, [H, vp, vp, vp]),
@@ -68,7 +70,7 @@ class OracleError(RuntimeError):
 class OracleSystem:
     """The oracle behind the same surface as the host mirror's `System` (built from the same configs)."""
 
-    def __init__(self, *, state, space_cfg, dynamic_cfg, int_cfg, lower, threads=1):
+    def __init__(self, *, state, space_cfg, dynamic_cfg, int_cfg, lower, threads=1, p_neighbors_cfg=None):
         self.lib = load()
         self.state = state
         self._lowered = lower(state, space_cfg, dynamic_cfg, int_cfg)
@@ -78,6 +80,10 @@ class OracleSystem:
         self._check(st)
         if threads > 1:
             self.lib.mor_set_threads(self.h, threads)
+        self.p_neighbors_cfg = p_neighbors_cfg
+        if p_neighbors_cfg is not None:  # RingsSystem(p_neighbors_cfg=...), src/rings/rings.jl:143-158
+            self._check(self.lib.mor_rings_set_neighbors(self.h, 1 if p_neighbors_cfg.only_count else 2,
+                                                         int(p_neighbors_cfg.type == "all"), float(p_neighbors_cfg.tol)))
         pos = np.ascontiguousarray(state.pos, dtype=np.float64)
         second = np.ascontiguousarray(state.second, dtype=np.float64)
         mask = state.active_mask()
@@ -159,6 +165,14 @@ class OracleSystem:
         areas, cms, cont = np.empty(nr), np.empty((nr, 2)), np.empty((self.n, 2))
         self._check(self.lib.mor_rings_download_info(self.h, _ptr(areas), _ptr(cms), _ptr(cont)))
         return areas, cms, cont
+
+    def particle_neighbors(self):
+        """(count[n], lists) — lists[i] in the reference's append order (None with only_count)."""
+        count = np.zeros(self.n, dtype=np.int32)
+        only = self.p_neighbors_cfg.only_count
+        lst = None if only else np.empty((self.n, 15), dtype=np.int32)
+        self._check(self.lib.mor_rings_download_neighbors(self.h, _ptr(count), _ptr(lst)))
+        return count, (None if only else [lst[i, :count[i]].tolist() for i in range(self.n)])
 
     def time(self):
         ns, t = C.c_int64(), C.c_double()

@@ -165,3 +165,105 @@ def test_rings_asymmetric_matrix_rejected(cuda_lib):
     with pytest.raises(pkg.MaviError) as e:
         H.make_gpu_rings(case)
     assert e.value.status == pkg.capi.ERR_UNSUPPORTED
+
+
+# ---------------------------------------------------------------- particle contact lists (src/rings/neighbors.jl)
+def _make_oracle_neigh(case, cfg, threads=1):
+    import __graft_entry__ as entry
+    from mavi_jl_b200.params import lower
+    return entry.load_oracle().OracleSystem(state=case["mk"](), space_cfg=case["space"], dynamic_cfg=case["dyn"],
+                                            int_cfg=case["int_cfg"], lower=lower, threads=threads, p_neighbors_cfg=cfg)
+
+
+def _brute_force_contacts(case, pos, cfg):
+    """Independent numpy restatement of neigh_update!(::ParticleNeighbors, ...) (src/rings/neighbors.jl:125-134) over ALL
+    pairs: dist < 2 particle_radius(interaction(ti, tj)) * tol and (type == :all or other ring)."""
+    st = case["mk"]()
+    n_max, n = st.n_max, len(st.pos)
+    ring = np.arange(n) // n_max
+    active = np.array([(i % n_max) < st.ring_num_particles(i // n_max) for i in range(n)])
+    ty = np.zeros(st.num_rings, dtype=int) if st.types is None else np.asarray(st.types) - 1
+    dyn = case["dyn"]
+    deq = np.array([[dyn.interaction(a, b).dist_eq for b in range(dyn.num_types)] for a in range(dyn.num_types)])
+    size = np.array([case["geom"].length, case["geom"].height])
+    out = []
+    for i in range(n):
+        if not active[i]:
+            out.append([])
+            continue
+        dr = pos[i] - pos
+        dr = dr - (np.abs(dr) > size / 2) * np.copysign(size, dr)
+        dist = np.sqrt((dr ** 2).sum(-1))
+        ok = active & (dist < 2 * (deq[ty[ring[i]], ty[ring]] / 2) * cfg.tol) & (np.arange(n) != i)
+        if cfg.type == "rings":
+            ok &= ring != ring[i]
+        out.append(np.flatnonzero(ok).tolist())
+    return out
+
+
+@pytest.mark.parametrize("ntype", ["all", "rings"])
+@pytest.mark.parametrize("kind", ["normal", "types"])
+def test_oracle_contact_lists_match_brute_force(oracle, kind, ntype):
+    from mavi_jl_b200.rings.configs import NeighborsCfg
+    n = 6 if kind == "normal" else 5
+    case = H.rings_case(kind, n, n)
+    cfg = NeighborsCfg(only_count=False, type=ntype, tol=1.1)
+    o = _make_oracle_neigh(case, cfg)
+    o.step(60, _noise(case, 60))           # rings collide: contacts between different rings appear
+    # the lists belong to the forces! of the LAST step, i.e. to the positions before its update!: replay one step less
+    o2 = _make_oracle_neigh(case, cfg)
+    o2.step(59, _noise(case, 60)[:59])
+    want = _brute_force_contacts(case, o2.pos(), cfg)
+    count, lists = o.particle_neighbors()
+    assert [sorted(l) for l in lists] == want
+    assert count.tolist() == [len(w) for w in want]
+    if ntype == "all":   # bonded ring neighbours sit at distance l_spring <= dist_eq < dist_eq * tol
+        assert min(len(w) for w, a in zip(want, count) if a or w) >= 2
+    else:
+        assert sum(len(w) for w in want) > 0
+    # only_count = true: the same counts, no lists (src/rings/neighbors.jl:102-107)
+    oc = _make_oracle_neigh(case, NeighborsCfg(only_count=True, type=ntype, tol=1.1))
+    oc.step(60, _noise(case, 60))
+    c2, l2 = oc.particle_neighbors()
+    assert l2 is None and np.array_equal(c2, count)
+
+
+def test_oracle_contact_lists_chunks_threads_allpairs_agree(oracle):
+    """The reference's own check_particle_neighbors_all loop (test/tests_rings/tests_general.jl:147-180): Sequencial /
+    Threaded x chunks / no chunks must give the same sorted lists."""
+    from mavi_jl_b200.rings.configs import NeighborsCfg
+    cfg = NeighborsCfg(only_count=False, type="rings", tol=1.1)
+    outs = []
+    for use_chunks, threads in ((True, 1), (False, 1), (True, 4)):
+        case = H.rings_case("normal", 5, 5, use_chunks=use_chunks)
+        o = _make_oracle_neigh(case, cfg, threads=threads)
+        o.step(100, _noise(case, 100))
+        count, lists = o.particle_neighbors()
+        outs.append((count.tolist(), [sorted(l) for l in lists]))
+    assert outs[0] == outs[1] == outs[2]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ntype", ["all", "rings"])
+@pytest.mark.parametrize("kind,chunks", [("normal", True), ("normal", False), ("types", True)])
+def test_rings_gpu_contact_lists(cuda_lib, kind, chunks, ntype):
+    from mavi_jl_b200.rings.configs import NeighborsCfg
+    from mavi_jl_b200.rings.rings import RingsSystem
+    n = 8 if kind == "normal" else 5
+    case = H.rings_case(kind, n, n, use_chunks=chunks)
+    for only_count in (False, True):
+        cfg = NeighborsCfg(only_count=only_count, type=ntype, tol=1.1)
+        g = RingsSystem(state=case["mk"](), space_cfg=case["space"], dynamic_cfg=case["dyn"], int_cfg=case["int_cfg"],
+                        p_neighbors_cfg=cfg)
+        o = _make_oracle_neigh(case, cfg)
+        for steps in (0, 1, 60):   # 0: the constructor's forces! already filled them (src/rings/rings.jl:280-288)
+            if steps:
+                nz = _noise(case, steps, seed=steps)
+                g.step(steps, nz)
+                o.step(steps, nz)
+            cg, lg = g.particle_neighbors()
+            co, lo = o.particle_neighbors()
+            assert np.array_equal(cg, co)
+            if not only_count:
+                assert lg == [sorted(l) for l in lo]
+        assert cg.sum() > 0
