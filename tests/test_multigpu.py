@@ -98,16 +98,18 @@ sys.exit(0 if ok else 1)
 '''
 
 
-def test_gloo_world2_slab_host_logic(tmp_path):
-    """world_size-2 gloo run on CPU: partition, halo selection (one cell column per side), id routing and the
-    broadcast of the communicator id behave; forces from (owned + halo) equal the global oracle forces."""
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_slab_host_logic(tmp_path, world):
+    """world_size-2 / -3 gloo runs on CPU (3: distinct left and right neighbours, uneven column split): partition, halo
+    selection (one cell column per side), id routing and the broadcast of the communicator id behave; forces from
+    (owned + halo) equal the global oracle forces."""
     script = tmp_path / "gloo_worker.py"
     script.write_text(_GLOO_WORKER)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
-    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-                          "127.0.0.1", "--master-port", "29531", str(script), ROOT], capture_output=True, text=True, env=env, timeout=300)
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+                          "127.0.0.1", "--master-port", str(29529 + world), str(script), ROOT], capture_output=True, text=True, env=env, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-    assert res.stdout.count("ok=True") == 2
+    assert res.stdout.count("ok=True") == world
 
 
 # ---------------------------------------------------------------- GPU: NCCL slabs vs oracle
