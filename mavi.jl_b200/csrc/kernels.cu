@@ -20,43 +20,14 @@ static inline int nblk(long long n, int tpb = TPB) { return (int)((n + tpb - 1) 
 
 // rank (dense particle index) -> slot.  Ranks < n_active enumerate the tile populations in TILE-ROW-MAJOR order
 // (tile_prefix is the exclusive scan in that order); cta_first[b] is the order index of the tile holding rank b*RPB.
-// Ranks >= n_active are the inactive tail.  Blocks stage the prefix entries they need in shared memory once
-// (rank_window_stage) so that threads do not chase dependent global loads.
+// Ranks >= n_active are the inactive tail.  Used by the download / reduction kernels only: the force kernels are
+// tile-block kernels that need no rank map.
 __device__ __forceinline__ int slot_of_rank(const DevParams &p, const int *__restrict__ tile_prefix,
                                             const int *__restrict__ cta_first, int rank) {
   if (rank >= p.n_active) return p.tail_base + (rank - p.n_active);
   int o = __ldg(cta_first + rank / RPB);
   while (rank >= __ldg(tile_prefix + o + 1)) ++o;
   return tile_of_order(p, o) * p.cap + (rank - __ldg(tile_prefix + o));
-}
-
-constexpr int RANK_WIN = 64;  // prefix entries staged per block (RPB ranks rarely span more tiles)
-// all threads of the block call this once; s_win needs RANK_WIN + 1 ints.  Contains a barrier.
-__device__ __forceinline__ void rank_window_stage(const DevParams &p, const int *__restrict__ tile_prefix,
-                                                  const int *__restrict__ cta_first, int *s_win) {
-  const bool in_tiles = blockIdx.x * RPB < p.n_active;
-  const int o0 = in_tiles ? __ldg(cta_first + blockIdx.x) : 0;
-  if (threadIdx.x <= RANK_WIN) {
-    const int o = o0 + threadIdx.x;
-    s_win[threadIdx.x] = (in_tiles && o <= p.nt_ord) ? __ldg(tile_prefix + o) : 0x7fffffff;
-  }
-  __syncthreads();
-}
-// slot of `rank` (a rank of this block) and the order index of its tile (-1 for the inactive tail)
-__device__ __forceinline__ int2 slot_from_window(const DevParams &p, const int *__restrict__ tile_prefix,
-                                                 const int *__restrict__ cta_first, int rank, const int *s_win) {
-  if (rank >= p.n_active) return make_int2(p.tail_base + (rank - p.n_active), -1);
-  int lo = 0;
-#pragma unroll
-  for (int step = RANK_WIN / 2; step >= 1; step >>= 1)
-    if (s_win[lo + step] <= rank) lo += step;
-  int o = __ldg(cta_first + blockIdx.x) + lo;
-  int base = s_win[lo];
-  if (lo == RANK_WIN - 1) {  // window exhausted (very sparse tiles): finish with the global walk
-    while (rank >= __ldg(tile_prefix + o + 1)) ++o;
-    base = __ldg(tile_prefix + o);
-  }
-  return make_int2(tile_of_order(p, o) * p.cap + (rank - base), o);
 }
 
 // =========================================================================================================
@@ -564,396 +535,18 @@ __device__ __forceinline__ void accumulate_pair(const DevParams &p, real2 ri, re
   fy = fma(c, dy, fy);
 }
 
-// Neighbour enumeration through a per-thread SEGMENT TABLE in shared memory.  The neighbours of a particle (own cell
-// + the 8 surrounding cells) are at most 7 contiguous runs of slots: rows row-1..row+1 of each of the 3 columns, each
-// split in two where a tile edge (the slack of the upper tile = a hole in slot space) lies in between, and the own
-// column split once more around the particle itself.  Each thread writes its runs as (slot offset, virtual end) pairs
-// and then walks ONE flat virtual index 0..total-1: slot = index + offset, and the table is consulted only when the
-// index crosses a run boundary.  A warp therefore waits for the max over lanes of the neighbour COUNT (not a sum of
-// per-run maxima), every lane executes the same loop body, and positions are fetched two neighbours ahead.
-constexpr int SEG_MAX = 8;
-
-struct SegWalker {
-  const int *tbl;  // [2*SEG_MAX][TPB] column of this thread: ends at [2s], offsets at [2s+1]
-  int s, brk, off, u, total;
-  __device__ __forceinline__ void init(const int *t, int total_) {
-    tbl = t;
-    s = 0;
-    u = 0;
-    total = total_;
-    brk = tbl[0];
-    off = tbl[TPB];
-  }
-  // slot of the next neighbour (call at most `total` times)
-  __device__ __forceinline__ int next() {
-    if (u >= brk) {
-      ++s;
-      brk = tbl[(2 * s) * TPB];
-      off = tbl[(2 * s + 1) * TPB];
-    }
-    return (u++) + off;
-  }
-};
-
-template <int DYN, bool MINIMG>
-__device__ __forceinline__ void walk_pairs(const DevParams &p, const real2 *__restrict__ pos, const int *tbl,
-                                           int total, real2 ri, real &fx, real &fy) {
-  SegWalker w;
-  w.init(tbl, total);
-  real2 r0 = __ldg(pos + w.next());
-  real2 r1 = (total > 1) ? __ldg(pos + w.next()) : r0;
-  int t = 0;
-#pragma unroll 1
-  for (; t + 2 <= total; t += 2) {
-    const real2 q0 = r0, q1 = r1;
-    if (t + 2 < total) r0 = __ldg(pos + w.next());
-    if (t + 3 < total) r1 = __ldg(pos + w.next());
-    accumulate_pair<DYN, MINIMG>(p, ri, q0, fx, fy);
-    accumulate_pair<DYN, MINIMG>(p, ri, q1, fx, fy);
-  }
-  if (t < total) accumulate_pair<DYN, MINIMG>(p, ri, r0, fx, fy);
-}
-
+// All-pairs mode (chunks === nothing, src/integration.jl:197-224): every active particle interacts with every other
+// active one in ascending-id order; slots are the original ids.  O(N^2): the reference's own small-N path (README
+// quick start, C1), kept as simple thread-per-particle kernels.
 template <int DYN, bool PER>
-__device__ __forceinline__ real2 cell_pair_force(const DevParams &p, const int *__restrict__ tstart,
-                                                   const real2 *__restrict__ pos, int *__restrict__ tbl, int cell,
-                                                   int k, real2 ri, bool exact_minimg) {
-  const int R = p.num_rows, Cn = p.num_cols;
-  const int col = div_rows(p, cell), row = cell - col * R;
+__device__ __forceinline__ real2 allpairs_force(const DevParams &p, const real2 *__restrict__ pos,
+                                                const unsigned int *__restrict__ idflag, int k, real2 r) {
   real fx = 0.0, fy = 0.0;
-  bool use_mi = PER && (exact_minimg || !p.fast_interior);
-  // Rows row-1..row+1 as two row intervals [r1a,r1b] and [r2a,r2b], each inside ONE tile (second may be empty):
-  // a tile edge between two of the rows splits them, a periodic wrap puts one interval at the far end of the column,
-  // a clipped (walled) edge just shortens the first interval.
-  int r1a = row - 1, r1b = row + 1, r2a = 0, r2b = -1;
-  if (row == 0) {
-    r1a = 0;
-    if (p.wrap_rows) { r2a = 0; r2b = (R > 1) ? 1 : 0; r1a = r1b = R - 1; use_mi = PER; }
-    else r1b = (R > 1) ? 1 : 0;
-  } else if (row == R - 1) {
-    r1b = R - 1;
-    if (p.wrap_rows) { r2a = r2b = 0; use_mi = PER; }
-  }
-  if (r2b < r2a && (r1a / MAVI_TR) != (r1b / MAVI_TR)) {  // tile edge inside the interval: split it
-    const int edge = (r1b / MAVI_TR) * MAVI_TR;           // first row of the lower tile
-    r2a = edge; r2b = r1b; r1b = edge - 1;
-  }
-  if ((r1a / MAVI_TR) != (r1b / MAVI_TR) || (r2b >= r2a && (r2a / MAVI_TR) != (r2b / MAVI_TR))) {
-    // wrap AND tile edge at once (only when (R-1) % 32 == 0): generic per-cell walk
-    for_each_neighbor(p, tstart, cell, k, [&](int j) { accumulate_pair<DYN, PER>(p, ri, __ldg(pos + j), fx, fy); });
-    return make_real2(fx, fy);
-  }
-  const bool two = r2b >= r2a;
-  const int t1 = r1a / MAVI_TR, t2 = r2a / MAVI_TR;
-  const int o1a = t1 * (MAVI_TR + 1) + (r1a - t1 * MAVI_TR), o1b = t1 * (MAVI_TR + 1) + (r1b - t1 * MAVI_TR) + 1;
-  const int o2a = t2 * (MAVI_TR + 1) + (r2a - t2 * MAVI_TR), o2b = t2 * (MAVI_TR + 1) + (r2b - t2 * MAVI_TR) + 1;
-  int S = 0, vtotal = 0;
-  auto add_seg = [&](int first, int len) {
-    if (len > 0) {
-      tbl[(2 * S + 1) * TPB] = first - vtotal;
-      vtotal += len;
-      tbl[(2 * S) * TPB] = vtotal;
-      ++S;
-    }
-  };
-#pragma unroll
-  for (int dc = -1; dc <= 1; dc++) {
-    int c2 = col + dc;
-    if (c2 < 0) {
-      if (!p.wrap_cols) continue;
-      c2 = Cn - 1;
-      use_mi = PER;
-    } else if (c2 >= Cn) {
-      if (!p.wrap_cols) continue;
-      c2 = 0;
-      use_mi = PER;
-    }
-    if (p.slab && ((c2 == 0 && p.seam_left) || (c2 == Cn - 1 && p.seam_right))) use_mi = PER;
-    const int *tc = tstart + (size_t)c2 * p.tpc * (MAVI_TR + 1);
-    const int a = __ldg(tc + o1a), ea = __ldg(tc + o1b);
-    const int b = two ? __ldg(tc + o2a) : ea, eb = two ? __ldg(tc + o2b) : ea;
-    if (dc != 0) {
-      add_seg(a, ea - a);
-      add_seg(b, eb - b);
-    } else if (k < ea && k >= a) {  // own column: split around self
-      add_seg(a, k - a);
-      add_seg(k + 1, ea - k - 1);
-      add_seg(b, eb - b);
-    } else {
-      add_seg(a, ea - a);
-      add_seg(b, k - b);
-      add_seg(k + 1, eb - k - 1);
-    }
-  }
-  if (vtotal > 0) {
-    // Minimum image: needed only for neighbours reached through a wrapped row/column (or always, in exact mode);
-    // applying it to the other neighbours of such a particle is an exact no-op, so the choice is per particle.
-    if (use_mi) walk_pairs<DYN, true>(p, pos, tbl, vtotal, ri, fx, fy);
-    else walk_pairs<DYN, false>(p, pos, tbl, vtotal, ri, fx, fy);
+  for (int j = 0; j < p.n; j++) {
+    if (j == k || (idflag[j] & MAVI_INACTIVE_BIT)) continue;
+    accumulate_pair<DYN, PER>(p, r, __ldg(pos + j), fx, fy);
   }
   return make_real2(fx, fy);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// CTA-cooperative staging.  The 256 ranks of a CTA are consecutive tiles of ONE tile row (tile-row-major order):
-// columns [cfirst, clast] x 32 cell rows.  One warp per column copies, for columns cfirst-1 .. clast+1, the cell
-// row above the tile row, the tile itself and the cell row below it into shared memory, back to back, and writes
-// the start of every cell row.  After that the neighbours of ANY particle of the block are 3 runs that are
-// contiguous in shared memory — tile holes, periodic wrap and grid edges have been resolved by the copy — and the
-// pair loop reads LDS.128 only.  CTAs that straddle two tile rows, span too many (sparse) tiles or overflow the
-// staging area fall back to the per-thread segment-table walk.
-constexpr int GMAX = 46;                 // block columns staged at most (plus the two side columns)
-constexpr int SROWS = MAVI_TR + 2;       // cell rows per staged column: above + 32 + below
-
-struct BlockStage {
-  int ok, use_mi, cfirst, ncol, r0, o_last;
-  int tile_src[GMAX + 2];                // global slot of the first particle of the column's tile
-  int src_a[GMAX + 2], src_b[GMAX + 2];  // global slot of the cell above / below the tile
-  int la[GMAX + 2], lt[GMAX + 2], lb[GMAX + 2];
-  int off[GMAX + 3];                     // start of each staged column in s_pos (exclusive scan of la+lt+lb)
-  int sstart[GMAX + 2][SROWS + 1];       // start (in s_pos) of each staged cell row; [SROWS] = end of the column
-};
-
-// rank_last_order: order index of the tile holding the last tiled rank of this block (computed by the caller)
-template <bool PER>
-__device__ __forceinline__ void block_stage(const DevParams &p, const int *__restrict__ tstart,
-                                            const int *__restrict__ cta_first, const real2 *__restrict__ pos,
-                                            int o_last, bool exact_minimg, BlockStage *bs, real2 *s_pos,
-                                            unsigned char *s_row, int s_pos_cap) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int R = p.num_rows, Cn = p.num_cols;
-  // ---- block geometry (every thread computes the same values: no serial section)
-  bool ok = o_last >= 0;
-  int o_first = 0, tr = 0, ncol = 0, cfirst = 0;
-  if (ok) {
-    o_first = __ldg(cta_first + blockIdx.x);
-    tr = div_cols(p, o_first);
-    ncol = o_last - o_first + 3;  // block columns + the two side columns
-    ok = tr == div_cols(p, o_last) && ncol <= GMAX + 2;
-    cfirst = o_first - tr * p.ord_cols + p.ord_col0;
-  }
-  const int r0 = tr * MAVI_TR;
-  if (threadIdx.x == 0) {
-    bs->ok = ok ? 1 : 0;
-    bs->use_mi = (PER && (exact_minimg || !p.fast_interior)) ? 1 : 0;
-    bs->cfirst = cfirst;
-    bs->ncol = ncol;
-    bs->r0 = r0;
-  }
-  if (!ok) {
-    __syncthreads();
-    return;
-  }
-  // ---- per-column descriptors, one thread per staged column (independent loads, issued together)
-  int c = 0;
-  bool exists = false;
-  if (threadIdx.x < ncol) {
-    const int j = threadIdx.x;
-    c = cfirst - 1 + j;
-    exists = true;
-    bool wrapped = false;
-    if (c < 0) { if (p.wrap_cols) { c = Cn - 1; wrapped = true; } else exists = false; }
-    else if (c >= Cn) { if (p.wrap_cols) { c = 0; wrapped = true; } else exists = false; }
-    if (exists && p.slab && ((c == 0 && p.seam_left) || (c == Cn - 1 && p.seam_right))) wrapped = true;
-    int ra = r0 - 1, rb = r0 + MAVI_TR;
-    bool has_a = exists, has_b = exists;
-    if (ra < 0) { if (p.wrap_rows) { ra = R - 1; wrapped = wrapped || exists; } else has_a = false; }
-    if (rb >= R) { if (p.wrap_rows) { rb = 0; wrapped = wrapped || exists; } else has_b = false; }
-    int la = 0, lt = 0, lb = 0, sa = 0, st = 0, sb = 0;
-    if (exists) {
-      const int *tt = tstart + (size_t)(c * p.tpc + tr) * (MAVI_TR + 1);
-      const int qa = has_a ? tq_of(p, c, ra) : 0, qb = has_b ? tq_of(p, c, rb) : 0;
-      st = __ldg(tt);
-      const int et = __ldg(tt + MAVI_TR);
-      const int a0 = has_a ? __ldg(tstart + qa) : 0, a1 = has_a ? __ldg(tstart + qa + 1) : 0;
-      const int b0 = has_b ? __ldg(tstart + qb) : 0, b1 = has_b ? __ldg(tstart + qb + 1) : 0;
-      lt = et - st; sa = a0; la = a1 - a0; sb = b0; lb = b1 - b0;
-    }
-    bs->tile_src[j] = st; bs->src_a[j] = sa; bs->src_b[j] = sb;
-    bs->la[j] = la; bs->lt[j] = lt; bs->lb[j] = lb;
-    if (wrapped && PER) bs->use_mi = 1;
-  }
-  __syncthreads();
-  // ---- dense packing: exclusive scan of the column sizes (warp 0; ncol <= 64)
-  if (w == 0) {
-    const int j0 = 2 * lane, j1 = 2 * lane + 1;
-    const int s0 = j0 < ncol ? bs->la[j0] + bs->lt[j0] + bs->lb[j0] : 0;
-    const int s1 = j1 < ncol ? bs->la[j1] + bs->lt[j1] + bs->lb[j1] : 0;
-    int incl = s0 + s1;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const int excl = incl - (s0 + s1);
-    if (j0 <= ncol) bs->off[j0] = excl;
-    if (j1 <= ncol) bs->off[j1] = excl + s0;
-    if (lane == 31 && incl > s_pos_cap) bs->ok = 0;  // staging area too small (very dense tiles): fall back
-  }
-  __syncthreads();
-  if (!bs->ok) return;
-  // ---- copy: one warp per column (coalesced), plus the starts of its cell rows
-  for (int j = w; j < ncol; j += TPB / 32) {
-    const int off = bs->off[j], la = bs->la[j], lt = bs->lt[j], lb = bs->lb[j];
-    const int src_t = bs->tile_src[j], src_a = bs->src_a[j], src_b = bs->src_b[j];
-    int cj = cfirst - 1 + j;
-    if (cj < 0) cj = Cn - 1;
-    else if (cj >= Cn) cj = 0;
-    const int *tt = tstart + (size_t)(cj * p.tpc + tr) * (MAVI_TR + 1);
-    // cell-row starts: row 0 = above, 1..rows = tile rows, rows+1 = below (directly after the last EXISTING row of a
-    // partial tile, so that the 3-row window of that row reaches it), everything after = end of the column
-    const int rows = min(MAVI_TR, R - r0);
-    for (int r = lane; r <= SROWS; r += 32) {
-      int v;
-      if (r == 0) v = off;
-      else if (r <= rows + 1) v = off + la + ((la + lt + lb) ? (__ldg(tt + (r - 1)) - src_t) : 0);
-      else v = off + la + lt + lb;
-      bs->sstart[j][r] = v;
-    }
-    // 16-byte asynchronous copies (LDGSTS): every piece of every column is in flight at once, no register staging
-    const int tot = la + lt + lb;
-    for (int i = lane; i < tot; i += 32) {
-      const int src = i < la ? src_a + i : (i < la + lt ? src_t + (i - la) : src_b + (i - la - lt));
-      __pipeline_memcpy_async(s_pos + off + i, pos + src, sizeof(real2));
-    }
-    // staged row (1..32) of every tile particle: lane r-1 owns tile row r
-    if (lane < rows && lt > 0) {
-      const int b = __ldg(tt + lane) - src_t, e = __ldg(tt + lane + 1) - src_t;
-      for (int i = b; i < e; i++) s_row[off + la + i] = (unsigned char)(lane + 1);
-    }
-  }
-  __pipeline_commit();
-  __pipeline_wait_prior(0);
-  __syncthreads();
-}
-
-// pair force of the particle in slot k (cell = (col,row) of the staged block) from the staged positions
-template <int DYN, bool MINIMG>
-__device__ __forceinline__ void block_walk(const DevParams &p, const BlockStage *bs, const real2 *s_pos, int jj,
-                                           int lr, int self, real2 ri, real &fx, real &fy) {
-  // jj = staged column of the particle's own column, lr = its staged row (1..32), self = its index in s_pos
-  const int a0 = bs->sstart[jj - 1][lr - 1], b0 = bs->sstart[jj - 1][lr + 2];
-  const int a1 = bs->sstart[jj][lr - 1], b1 = bs->sstart[jj][lr + 2];
-  const int a2 = bs->sstart[jj + 1][lr - 1], b2 = bs->sstart[jj + 1][lr + 2];
-  const int c1 = b0 - a0;              // neighbours t <  c1        -> a0 + t
-  const int c2 = c1 + (self - a1);     //          c1 <= t < c2    -> a1 + (t - c1)
-  const int c3 = c2 + (b1 - self - 1); //          c2 <= t < c3    -> self + 1 + (t - c2)
-  const int total = c3 + (b2 - a2);    //          c3 <= t         -> a2 + (t - c3)
-  const int d1 = (a1 - c1) - a0, d3 = (a2 - c3) - (a1 - c1) - 1;
-#pragma unroll 2
-  for (int t = 0; t < total; ++t) {
-    const int s = t + a0 + (t >= c1 ? d1 : 0) + (t >= c2 ? 1 : 0) + (t >= c3 ? d3 : 0);
-    accumulate_pair<DYN, MINIMG>(p, ri, s_pos[s], fx, fy);
-  }
-}
-
-// ALLP: chunks === nothing -> all pairs over active ids (src/integration.jl:197-224); slots = original order.
-// exact_minimg: force the minimum image everywhere (pass B after an abnormally large drift).
-//
-// Minimum-image shortcut (exactness argument): with fresh cells both particles of a non-wrapped pair lie inside
-// 8-adjacent cells, so |dr| < 2 cell widths <= size/4 on a grid of >= 8 cells per axis and the reference's
-// `abs(dr) > size/2` test is false -> skipped EXACTLY.  Stale cells (Verlet pass 2) are covered by the per-step
-// displacement guard (FLAG_BIGMOVE) which switches pass B to the exact path.
-struct ForceCtx {
-  const BlockStage *bs;        // CTA staging descriptor (shared memory)
-  const real2 *s_pos;        // staged positions
-  const unsigned char *s_row;  // staged row of every staged tile particle
-  int *tbl;                    // this thread's column of the fallback segment table (aliases s_pos)
-};
-
-constexpr int BS_BYTES = (sizeof(BlockStage) + 15) / 16 * 16;
-constexpr int SPOS_CAP = 2304;  // staged positions per CTA (36 KB); the fallback table needs 16 KB of the same area
-constexpr int PASS_SMEM = BS_BYTES + SPOS_CAP * ((int)sizeof(real2) + 1);
-
-// what a thread knows about the particle it is working on
-struct Particle {
-  int k;         // slot
-  int cell;      // cell it is binned under
-  bool active;
-  bool staged;   // position / row came from the staged block
-  int jj, lr, self;
-  real2 r;
-};
-
-// Fetch the particle of `rank`.  In a staged block everything comes from shared memory (no global load sits in front
-// of the pair loop); otherwise from the global arrays.
-template <bool ALLP>
-__device__ __forceinline__ Particle fetch_particle(const DevParams &p, const ForceCtx &fc, int rank, int k, int order,
-                                                   const real2 *__restrict__ pos, const int *__restrict__ cell,
-                                                   const unsigned int *__restrict__ idflag) {
-  Particle q;
-  q.k = k;
-  q.staged = !ALLP && order >= 0 && fc.bs->ok;
-  if (q.staged) {
-    const BlockStage *bs = fc.bs;
-    const int tr = div_cols(p, order);
-    const int col = order - tr * p.ord_cols + p.ord_col0;
-    q.jj = col - bs->cfirst + 1;
-    q.self = bs->sstart[q.jj][1] + (k - bs->tile_src[q.jj]);
-    q.lr = fc.s_row[q.self];
-    q.r = fc.s_pos[q.self];
-    q.cell = col * p.num_rows + bs->r0 + q.lr - 1;
-    q.active = true;  // tiles hold active particles only (inactive slots live in the tail)
-  } else {
-    q.jj = q.lr = q.self = 0;
-    q.r = pos[k];
-    q.cell = ALLP ? 0 : cell[k];
-    q.active = !(idflag[k] & MAVI_INACTIVE_BIT);
-  }
-  return q;
-}
-
-template <int DYN, bool PER, bool ALLP>
-__device__ __forceinline__ real2 pair_force(const DevParams &p, const int *__restrict__ tstart,
-                                              const real2 *__restrict__ pos, const unsigned int *__restrict__ idflag,
-                                              const ForceCtx &fc, const Particle &q, bool exact_minimg) {
-  if (ALLP) {
-    real fx = 0.0, fy = 0.0;
-    for (int j = 0; j < p.n; j++) {
-      if (j == q.k || (idflag[j] & MAVI_INACTIVE_BIT)) continue;
-      accumulate_pair<DYN, PER>(p, q.r, __ldg(pos + j), fx, fy);
-    }
-    return make_real2(fx, fy);
-  }
-  if (q.staged) {
-    real fx = 0.0, fy = 0.0;
-    if (PER && fc.bs->use_mi) block_walk<DYN, true>(p, fc.bs, fc.s_pos, q.jj, q.lr, q.self, q.r, fx, fy);
-    else block_walk<DYN, false>(p, fc.bs, fc.s_pos, q.jj, q.lr, q.self, q.r, fx, fy);
-    return make_real2(fx, fy);
-  }
-  return cell_pair_force<DYN, PER>(p, tstart, pos, fc.tbl, q.cell, q.k, q.r, exact_minimg);
-}
-
-// common prologue of the rank-mapped force kernels (all threads take part): stage the rank window, find the last
-// tiled rank's tile, stage the block
-template <bool PER, bool ALLP>
-__device__ __forceinline__ void force_prologue(const DevParams &p, const int *__restrict__ tstart,
-                                               const int *__restrict__ tile_prefix, const int *__restrict__ cta_first,
-                                               const real2 *__restrict__ pos, bool exact_minimg, unsigned char *dsm,
-                                               int *s_win, ForceCtx &fc) {
-  BlockStage *bs = reinterpret_cast<BlockStage *>(dsm);
-  real2 *s_pos = reinterpret_cast<real2 *>(dsm + BS_BYTES);
-  unsigned char *s_row = dsm + BS_BYTES + SPOS_CAP * sizeof(real2);
-  fc.bs = bs;
-  fc.s_pos = s_pos;
-  fc.s_row = s_row;
-  fc.tbl = reinterpret_cast<int *>(dsm + BS_BYTES) + threadIdx.x;
-  if (ALLP) return;
-  // last tile of the block: the tile holding the first rank of the NEXT block bounds it (at most one tile too many,
-  // which only stages one extra column) -> the staging does not have to wait for the rank window
-  int o_last = -1;
-  if ((long long)blockIdx.x * RPB < p.n_active)
-    o_last = ((long long)(blockIdx.x + 1) * RPB < p.n_active) ? __ldg(cta_first + blockIdx.x + 1) : p.nt_ord - 1;
-  // rank window (its barrier is the first barrier of block_stage)
-  {
-    const bool in_tiles = (long long)blockIdx.x * RPB < p.n_active;
-    const int o0 = in_tiles ? __ldg(cta_first + blockIdx.x) : 0;
-    if (threadIdx.x <= RANK_WIN) {
-      const int o = o0 + threadIdx.x;
-      s_win[threadIdx.x] = (in_tiles && o <= p.nt_ord) ? __ldg(tile_prefix + o) : 0x7fffffff;
-    }
-  }
-  block_stage<PER>(p, tstart, cta_first, pos, o_last, exact_minimg, bs, s_pos, s_row, SPOS_CAP);
 }
 
 // The particle in slot k (sorted under cell c_old) now sits at (x, y).  If update_particle_chunk! would bin it
@@ -1062,33 +655,24 @@ __device__ __forceinline__ real2 verlet_drift(const DevParams &p, real2 r, real2
 // pull a line towards L1 without tying up a register across the pair loop (the value is loaded after the loop)
 __device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 
-// Every force kernel: block prologue (staging), then each thread handles RPB/TPB particles of the block.
-#define MAVI_FORCE_KERNEL_PROLOGUE(POS, EXACT)                                                    \
-  extern __shared__ __align__(16) unsigned char dsm[];                                            \
-  __shared__ int s_win[RANK_WIN + 1];                                                             \
-  ForceCtx fc;                                                                                    \
-  force_prologue<PER, ALLP>(p, tstart, tile_prefix, cta_first, POS, EXACT, dsm, s_win, fc);
-
-#define MAVI_FOR_EACH_PARTICLE                                                                    \
-  for (int it = 0; it < RPB / TPB; ++it) {                                                        \
-    const int rank = blockIdx.x * RPB + it * TPB + threadIdx.x;                                   \
-    if (rank >= p.n) break;                                                                       \
-    const int2 so_ = ALLP ? make_int2(rank, -1) : slot_from_window(p, tile_prefix, cta_first, rank, s_win);   \
-    const int k = so_.x, order_ = so_.y;
+// each thread of the all-pairs kernels handles RPB/TPB slots of its block
+#define MAVI_FOR_EACH_SLOT                                           \
+  for (int it = 0; it < RPB / TPB; ++it) {                           \
+    const int k = blockIdx.x * RPB + it * TPB + threadIdx.x;         \
+    if (k >= p.n) break;
 
 // clean_forces! + calc_forces! (+ calc_walls_forces!): the force state after src/integration.jl:508-511.
-template <int DYN, bool PER, bool ALLP>
-__global__ void __launch_bounds__(TPB) k_force_only(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
-                             const int *__restrict__ tile_prefix, const int *__restrict__ cta_first,
-                             const int *__restrict__ cell, const unsigned int *__restrict__ idflag,
-                             const real2 *__restrict__ pos, real2 *__restrict__ force, int with_walls) {
-  MAVI_FORCE_KERNEL_PROLOGUE(pos, false)
-  MAVI_FOR_EACH_PARTICLE
-    const Particle q = fetch_particle<ALLP>(p, fc, rank, k, order_, pos, cell, idflag);
+template <int DYN, bool PER>
+__global__ void __launch_bounds__(TPB) k_force_only(const __grid_constant__ DevParams p,
+                                                    const unsigned int *__restrict__ idflag,
+                                                    const real2 *__restrict__ pos, real2 *__restrict__ force,
+                                                    int with_walls) {
+  MAVI_FOR_EACH_SLOT
+    const real2 r = pos[k];
     real2 F = make_real2(0.0, 0.0);
-    if (q.active) {
-      F = pair_force<DYN, PER, ALLP>(p, tstart, pos, idflag, fc, q, false);
-      if (with_walls && p.has_force_walls) wall_forces(p, q.r.x, q.r.y, F.x, F.y);
+    if (!(idflag[k] & MAVI_INACTIVE_BIT)) {
+      F = allpairs_force<DYN, PER>(p, pos, idflag, k, r);
+      if (with_walls && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
     }
     force[k] = F;
   }
@@ -1096,27 +680,22 @@ __global__ void __launch_bounds__(TPB) k_force_only(const __grid_constant__ DevP
 
 // newton_step! first half (src/integration.jl:507-512 + update_verlet! :418-424):
 //   F1 = pair forces + wall forces;  pos' = pos + vel dt + F1 dt^2/2  (every slot, active or not).
-template <int DYN, bool PER, bool ALLP>
-__global__ void __launch_bounds__(TPB) k_newton_a(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
-                           const int *__restrict__ tile_prefix, const int *__restrict__ cta_first,
-                           const int *__restrict__ cell, const unsigned int *__restrict__ idflag,
-                           const real2 *__restrict__ pos_in, const real2 *__restrict__ vel,
-                           real2 *__restrict__ pos_out, real2 *__restrict__ f1, int *__restrict__ flags) {
+template <int DYN, bool PER>
+__global__ void __launch_bounds__(TPB) k_newton_a(const __grid_constant__ DevParams p,
+                                                  const unsigned int *__restrict__ idflag,
+                                                  const real2 *__restrict__ pos_in, const real2 *__restrict__ vel,
+                                                  real2 *__restrict__ pos_out, real2 *__restrict__ f1,
+                                                  int *__restrict__ flags) {
   if (!flags[FLAG_RAN]) return;
-  MAVI_FORCE_KERNEL_PROLOGUE(pos_in, false)
-  MAVI_FOR_EACH_PARTICLE
-    prefetch_l1(vel + k);  // needed only after the pair loop
-    const Particle q = fetch_particle<ALLP>(p, fc, rank, k, order_, pos_in, cell, idflag);
-    real2 r = q.r;
+  MAVI_FOR_EACH_SLOT
+    real2 r = pos_in[k];
     real2 F = make_real2(0.0, 0.0);
-    if (q.active) {
-      F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, fc, q, false);
+    if (!(idflag[k] & MAVI_INACTIVE_BIT)) {
+      F = allpairs_force<DYN, PER>(p, pos_in, idflag, k, r);
       if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
     }
-    const real2 v = vel[k];
     bool big;
-    r = verlet_drift(p, r, v, F, big);
-    if (!ALLP && PER && big) flags[FLAG_BIGMOVE] = 1;
+    r = verlet_drift(p, r, vel[k], F, big);
     pos_out[k] = r;
     f1[k] = F;
   }
@@ -1135,25 +714,20 @@ __global__ void __launch_bounds__(TPB) k_newton_a(const __grid_constant__ DevPar
 // particles with the fresh cell lists, and the next step starts directly with this kernel.  Results are bit-identical
 // to running k_newton_a every step (tests/test_gpu_core.py::test_force_carry_bitwise).
 //   f1 / f1_next: F1 of this step / of the next one (the same array, updated in place; f2 = get_forces stays F2)
-template <int DYN, bool PER, bool ALLP, bool CARRY>
-__global__ void __launch_bounds__(TPB) k_newton_b(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
-                           const int *__restrict__ tile_prefix, const int *__restrict__ cta_first,
-                           const unsigned int *__restrict__ idflag, const real2 *__restrict__ pos_in,
-                           real2 *__restrict__ vel, const real2 *f1, real2 *f2, real2 *f1_next,
-                           real2 *__restrict__ pos_next, int *__restrict__ fix_idx,
-                           real2 *__restrict__ fix_pos, const MoverSink ms) {
-  if (!ms.flags[FLAG_RAN]) return;
-  const bool exact = !ALLP && ms.flags[FLAG_BIGMOVE] != 0;
-  MAVI_FORCE_KERNEL_PROLOGUE(pos_in, exact)
-  MAVI_FOR_EACH_PARTICLE
-    prefetch_l1(vel + k);  // needed only after the pair loop
-    prefetch_l1(f1 + k);
-    const Particle q = fetch_particle<ALLP>(p, fc, rank, k, order_, pos_in, ms.cell, idflag);
-    real2 r = q.r;
+// All-pairs version (no cell lists, hence no re-binning and no carry); the tile-block version is k_newton_b2.
+template <int DYN, bool PER>
+__global__ void __launch_bounds__(TPB) k_newton_b(const __grid_constant__ DevParams p,
+                                                  const unsigned int *__restrict__ idflag,
+                                                  const real2 *__restrict__ pos_in, real2 *__restrict__ vel,
+                                                  const real2 *__restrict__ f1, real2 *__restrict__ f2,
+                                                  int *__restrict__ fix_idx, real2 *__restrict__ fix_pos,
+                                                  int *__restrict__ flags) {
+  if (!flags[FLAG_RAN]) return;
+  MAVI_FOR_EACH_SLOT
+    real2 r = pos_in[k];
     real2 F = make_real2(0.0, 0.0);
-    const bool active = q.active;
-    const int c = q.cell;
-    if (active) F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, fc, q, exact);
+    const bool active = !(idflag[k] & MAVI_INACTIVE_BIT);
+    if (active) F = allpairs_force<DYN, PER>(p, pos_in, idflag, k, r);
     real2 v = vel[k];
     const real2 Fo = f1[k];
     v.x = v.x + p.hdt * (F.x + Fo.x);
@@ -1161,24 +735,14 @@ __global__ void __launch_bounds__(TPB) k_newton_b(const __grid_constant__ DevPar
     if (active) {
       const real x0 = r.x, y0 = r.y;
       apply_walls<true>(p, r.x, r.y, v.x, v.y, p.particle_radius);
-      const bool fixed = (r.x != x0 || r.y != y0);
-      if (fixed) {
-        int m = atomicAdd(&ms.flags[FLAG_NFIX], 1);
+      if (r.x != x0 || r.y != y0) {  // neighbours still read the unmodified drifted positions in this launch
+        int m = atomicAdd(&flags[FLAG_NFIX], 1);
         fix_idx[m] = k;
         fix_pos[m] = r;
       }
-      if (!ALLP) note_if_moved(p, ms, k, c, r.x, r.y, fixed, F, [&] { return v; });
     }
     vel[k] = v;
     f2[k] = F;
-    if (CARRY) {
-      real2 Fn = F;
-      if (p.has_force_walls && active) wall_forces(p, r.x, r.y, Fn.x, Fn.y);
-      f1_next[k] = Fn;
-      bool big;
-      pos_next[k] = verlet_drift(p, r, v, Fn, big);
-      if (PER && big) ms.flags[FLAG_BIGMOVE_NEXT] = 1;
-    }
   }
 }
 
@@ -1374,24 +938,22 @@ __device__ __forceinline__ void self_propelled_update(const DevParams &p, real2 
 
 // szabo_step! / rtp_step! (src/integration.jl:517-535): forces + update_szabo! (:433-465) / update_rtp! (:467-498)
 // + walls! in ONE pass.  The update loops slots 1:count (not ids) like the reference.
-template <int DYN, bool PER, bool ALLP>
-__global__ void __launch_bounds__(TPB) k_self_propelled(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
-                                 const int *__restrict__ tile_prefix, const int *__restrict__ cta_first,
-                                 const unsigned int *__restrict__ idflag, const real2 *__restrict__ pos_in,
-                                 real *__restrict__ ang, real2 *__restrict__ pos_out, real2 *__restrict__ force,
-                                 const real *__restrict__ noise, unsigned long long step, const MoverSink ms) {
-  if (!ms.flags[FLAG_RAN]) return;
-  MAVI_FORCE_KERNEL_PROLOGUE(pos_in, false)
-  MAVI_FOR_EACH_PARTICLE
+template <int DYN, bool PER>
+__global__ void __launch_bounds__(TPB) k_self_propelled(const __grid_constant__ DevParams p,
+                                                        const unsigned int *__restrict__ idflag,
+                                                        const real2 *__restrict__ pos_in, real *__restrict__ ang,
+                                                        real2 *__restrict__ pos_out, real2 *__restrict__ force,
+                                                        const real *__restrict__ noise, unsigned long long step,
+                                                        int *__restrict__ flags) {
+  if (!flags[FLAG_RAN]) return;
+  MAVI_FOR_EACH_SLOT
     const unsigned int idf = idflag[k];
     const unsigned int id = idf & ~MAVI_INACTIVE_BIT;
-    const Particle q = fetch_particle<ALLP>(p, fc, rank, k, order_, pos_in, ms.cell, idflag);
-    const bool active = q.active;
-    const int c = q.cell;
-    real2 r = q.r;
+    const bool active = !(idf & MAVI_INACTIVE_BIT);
+    real2 r = pos_in[k];
     real2 F = make_real2(0.0, 0.0);
     if (active) {
-      F = pair_force<DYN, PER, ALLP>(p, tstart, pos_in, idflag, fc, q, false);
+      F = allpairs_force<DYN, PER>(p, pos_in, idflag, k, r);
       if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
     }
     force[k] = F;
@@ -1399,7 +961,6 @@ __global__ void __launch_bounds__(TPB) k_self_propelled(const __grid_constant__ 
     if (active) {
       real vx = 0.0, vy = 0.0;
       apply_walls<false>(p, r.x, r.y, vx, vy, p.particle_radius);
-      if (!ALLP) note_if_moved(p, ms, k, c, r.x, r.y, false, F, [&] { return make_real2(ang[k], 0.0); });
     }
     pos_out[k] = r;
   }
@@ -1716,25 +1277,10 @@ __global__ void __launch_bounds__(TPB) k_self_propelled2(const __grid_constant__
     });
 }
 
-// all-pairs runs (chunks === nothing) keep the rank-mapped kernels with ALLP = true; chunked runs use the tile-block ones
-#define MAVI_DISPATCH_ALLP(DYNV, PERV, CALL) \
-  do {                                       \
-    if (PERV) { CALL(DYNV, true, true); } else { CALL(DYNV, false, true); } \
-  } while (0)
-
+// dispatch over the periodic flag (the dynamics is switched on by the callers)
 #define MAVI_DISPATCH2(DYNV, PERV, CALL) \
   do {                                   \
     if (PERV) { CALL(DYNV, true); } else { CALL(DYNV, false); } \
-  } while (0)
-
-// ---- dispatch over (dynamics, periodic, all-pairs) ----------------------------------------------------------
-#define MAVI_DISPATCH_DYN(DYNV, PERV, ALLPV, CALL)                                    \
-  do {                                                                                \
-    if (PERV) {                                                                       \
-      if (ALLPV) { CALL(DYNV, true, true); } else { CALL(DYNV, true, false); }        \
-    } else {                                                                          \
-      if (ALLPV) { CALL(DYNV, false, true); } else { CALL(DYNV, false, false); }      \
-    }                                                                                 \
   } while (0)
 
 static MoverSink mover_sink(const DevArrays &a) {
@@ -1754,13 +1300,12 @@ void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &
 #undef CALL2
     return;
   }
-#define CALL(D, P, A) \
-  MAVI_LAUNCH(c, (k_force_only<D, P, A>), nblk(p.n, RPB), TPB, (A ? 64 : PASS_SMEM), p, a.tstart, a.tile_prefix, a.cta_first, a.cell, a.idflag, a.pos[0], a.force, (int)with_wall_forces)
+#define CALL(D, P) MAVI_LAUNCH(c, (k_force_only<D, P>), nblk(p.n, RPB), TPB, 0, p, a.idflag, a.pos[0], a.force, (int)with_wall_forces)
   switch (p.dynamics) {
-    case MAVI_DYN_LJ: MAVI_DISPATCH_ALLP(MAVI_DYN_LJ, p.periodic, CALL); break;
-    case MAVI_DYN_HARMTRUNC: MAVI_DISPATCH_ALLP(MAVI_DYN_HARMTRUNC, p.periodic, CALL); break;
-    case MAVI_DYN_SZABO: MAVI_DISPATCH_ALLP(MAVI_DYN_SZABO, p.periodic, CALL); break;
-    case MAVI_DYN_RTP: MAVI_DISPATCH_ALLP(MAVI_DYN_RTP, p.periodic, CALL); break;
+    case MAVI_DYN_LJ: MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALL); break;
+    case MAVI_DYN_HARMTRUNC: MAVI_DISPATCH2(MAVI_DYN_HARMTRUNC, p.periodic, CALL); break;
+    case MAVI_DYN_SZABO: MAVI_DISPATCH2(MAVI_DYN_SZABO, p.periodic, CALL); break;
+    case MAVI_DYN_RTP: MAVI_DISPATCH2(MAVI_DYN_RTP, p.periodic, CALL); break;
   }
 #undef CALL
 }
@@ -1774,10 +1319,9 @@ void launch_newton_a(const LaunchCtx &c, const DevParams &p, const DevArrays &a)
 #undef CALL2
     return;
   }
-#define CALL(D, P, A) \
-  MAVI_LAUNCH(c, (k_newton_a<D, P, A>), nblk(p.n, RPB), TPB, (A ? 64 : PASS_SMEM), p, a.tstart, a.tile_prefix, a.cta_first, a.cell, a.idflag, a.pos[0], a.vel, a.pos[1], a.force_old, a.flags)
-  if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_ALLP(MAVI_DYN_LJ, p.periodic, CALL);
-  else MAVI_DISPATCH_ALLP(MAVI_DYN_HARMTRUNC, p.periodic, CALL);
+#define CALL(D, P) MAVI_LAUNCH(c, (k_newton_a<D, P>), nblk(p.n, RPB), TPB, 0, p, a.idflag, a.pos[0], a.vel, a.pos[1], a.force_old, a.flags)
+  if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALL);
+  else MAVI_DISPATCH2(MAVI_DYN_HARMTRUNC, p.periodic, CALL);
 #undef CALL
 }
 
@@ -1792,9 +1336,8 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p_in, const DevArrays 
   const bool allp = p.num_cells == 0;
   MoverSink ms = mover_sink(a);
   // reads the drifted positions pos[1] (which become the current positions after the sparse wall fix-ups)
-#define ARGS p, a.tstart, a.tile_prefix, a.cta_first, a.idflag, a.pos[1], a.vel, a.force_old, a.force, a.force_old, a.pos[0], a.fix_idx, a.fix_pos, ms
-#define CALL(D, P, A) \
-  MAVI_LAUNCH(c, (k_newton_b<D, P, A, false>), nblk(p.n, RPB), TPB, (A ? 64 : PASS_SMEM), ARGS)
+#define ARGS p, a.idflag, a.pos[1], a.vel, a.force_old, a.force, a.fix_idx, a.fix_pos, a.flags
+#define CALL(D, P) MAVI_LAUNCH(c, (k_newton_b<D, P>), nblk(p.n, RPB), TPB, 0, ARGS)
   if (!allp) {
 #define ARGS2 p, a.tstart, a.pos[1], a.vel, a.force_old, a.force, a.force_old, a.pos[0], a.fix_idx, a.fix_pos, ms
 #define CALL2(D, P) MAVI_LAUNCH(c, (k_newton_b2<D, P, false, 4>), grid2(p), TPB, PASS2_SMEM, ARGS2)
@@ -1815,8 +1358,8 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p_in, const DevArrays 
 #undef CALL2C
 #undef ARGS2
   } else {
-    if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH_ALLP(MAVI_DYN_LJ, p.periodic, CALL);
-    else MAVI_DISPATCH_ALLP(MAVI_DYN_HARMTRUNC, p.periodic, CALL);
+    if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALL);
+    else MAVI_DISPATCH2(MAVI_DYN_HARMTRUNC, p.periodic, CALL);
   }
 #undef CALL
 #undef ARGS
@@ -1869,10 +1412,9 @@ void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArra
     MAVI_LAUNCH(c, k_apply_pos_fixes, 1, 32, 0, a.flags, a.fix_idx, a.fix_pos, a.pos[1]);  // no fix-ups here: step counter only
     return;
   }
-#define CALL(D, P, A) \
-  MAVI_LAUNCH(c, (k_self_propelled<D, P, A>), nblk(p.n, RPB), TPB, (A ? 64 : PASS_SMEM), p, a.tstart, a.tile_prefix, a.cta_first, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms)
-  if (p.dynamics == MAVI_DYN_SZABO) MAVI_DISPATCH_ALLP(MAVI_DYN_SZABO, p.periodic, CALL);
-  else MAVI_DISPATCH_ALLP(MAVI_DYN_RTP, p.periodic, CALL);
+#define CALL(D, P) MAVI_LAUNCH(c, (k_self_propelled<D, P>), nblk(p.n, RPB), TPB, 0, p, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, a.flags)
+  if (p.dynamics == MAVI_DYN_SZABO) MAVI_DISPATCH2(MAVI_DYN_SZABO, p.periodic, CALL);
+  else MAVI_DISPATCH2(MAVI_DYN_RTP, p.periodic, CALL);
 #undef CALL
   MAVI_LAUNCH(c, k_apply_pos_fixes, 1, 32, 0, a.flags, a.fix_idx, a.fix_pos, a.pos[1]);  // no fix-ups here: step counter only
 }
