@@ -1342,13 +1342,9 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p_in, const DevArrays 
 #define ARGS2 p, a.tstart, a.pos[1], a.vel, a.force_old, a.force, a.force_old, a.pos[0], a.fix_idx, a.fix_pos, ms
 #define CALL2(D, P) MAVI_LAUNCH(c, (k_newton_b2<D, P, false, 4>), grid2(p), TPB, PASS2_SMEM, ARGS2)
 #define CALL2C(D, P) MAVI_LAUNCH(c, (k_newton_b2<D, P, true, 4>), grid2(p), TPB, PASS2_SMEM, ARGS2)
-    static const int minb = getenv("MAVI_K_MINB") ? atoi(getenv("MAVI_K_MINB")) : 4;  // tuning knob (A/B runs)
     if (carry) {
       ms.chg = a.chg;
-      if (p.dynamics == MAVI_DYN_LJ && p.periodic && minb == 3) MAVI_LAUNCH(c, (k_newton_b2<MAVI_DYN_LJ, true, true, 3>), grid2(p), TPB, PASS2_SMEM, ARGS2);
-      else if (p.dynamics == MAVI_DYN_LJ && p.periodic && minb == 5) MAVI_LAUNCH(c, (k_newton_b2<MAVI_DYN_LJ, true, true, 5>), grid2(p), TPB, PASS2_SMEM, ARGS2);
-      else if (p.dynamics == MAVI_DYN_LJ && p.periodic && minb == 6) MAVI_LAUNCH(c, (k_newton_b2<MAVI_DYN_LJ, true, true, 6>), grid2(p), TPB, PASS2_SMEM, ARGS2);
-      else if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALL2C);
+      if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALL2C);
       else MAVI_DISPATCH2(MAVI_DYN_HARMTRUNC, p.periodic, CALL2C);
     } else {
       if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALL2);
