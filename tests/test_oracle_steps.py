@@ -263,3 +263,179 @@ def test_rigid_wall_newton_steps_match_second_restatement(oracle):
     assert np.abs(o.pos() - np.array(pos)).max() < 1e-12 * case["geom"].length
     assert H.rel_err(o.second(), np.array(vel)) < 1e-11
     assert np.abs(np.array(vel) - st.vel).max() > 0.1
+
+
+# ---------------------------------------------------------------- Mavi.Rings: whole steps vs a second restatement
+class RefRings:
+    """Plain-Python restatement of the Rings constructor tail and step! (src/rings/rings.jl:276-288,
+    src/rings/integration.jl:32-226, :300-372, :522-543), all-pairs pair enumeration (src/integration.jl:197-224)."""
+
+    def __init__(self, case, noise):
+        st = case["mk"]()
+        self.nr, self.nmax = st.num_rings, st.n_max
+        self.pos = [np.array(p, dtype=np.float64) for p in st.pos]          # scalar idx = ring * n_max + p
+        self.pol = [float(a) for a in st.pol]
+        self.types = None if st.types is None else [int(t) - 1 for t in st.types]
+        self.dyn = case["dyn"]
+        self.np_of = [st.ring_num_particles(r) for r in range(self.nr)]
+        self.size = np.array([case["geom"].length, case["geom"].height])
+        self.periodic = isinstance(case["space"].wall_type, pkg.PeriodicWalls)
+        self.dt = case["int_cfg"].dt
+        self.noise = noise
+        n = len(self.pos)
+        self.cont = [np.zeros(2) for _ in range(n)]
+        self.cms = [np.zeros(2) for _ in range(self.nr)]
+        self.areas = [0.0] * self.nr
+        self.forces = [np.zeros(2) for _ in range(n)]
+        self.ids = [r * self.nmax + q for r in range(self.nr) for q in range(self.np_of[r])]
+        # RingsSystem ctor tail, src/rings/rings.jl:280-288
+        self.update_continuos_pos()
+        self.update_cms()
+        self.clean()
+        self.forces_()
+
+    def ty(self, ring):
+        return 0 if self.types is None else self.types[ring]
+
+    def calc_diff(self, r1, r2):
+        dr = r1 - r2
+        if self.periodic:
+            dr = dr - (np.abs(dr) > (self.size / 2)) * np.copysign(self.size, dr)
+        return dr
+
+    def ring_points(self, ring):  # get_continuos_pos, src/rings/rings.jl:31-43
+        src = self.cont if self.periodic else self.pos
+        return [src[ring * self.nmax + q] for q in range(self.np_of[ring])]
+
+    def update_continuos_pos(self):  # src/rings/integration.jl:118-138
+        if not self.periodic:
+            return
+        for ring in range(self.nr):
+            b = ring * self.nmax
+            for q in range(self.nmax):
+                self.cont[b + q] = self.pos[b + q].copy()
+            for q in range(1, self.np_of[ring]):
+                self.cont[b + q] = self.cont[b + q - 1] + self.calc_diff(self.pos[b + q], self.pos[b + q - 1])
+
+    def update_cms(self):  # src/rings/integration.jl:366-372
+        for ring in range(self.nr):
+            pts = self.ring_points(ring)
+            self.cms[ring] = sum(pts[1:], pts[0].copy()) / len(pts)
+
+    def clean(self):
+        self.forces = [np.zeros(2) for _ in self.pos]
+
+    def calc_interaction(self, i, j):  # src/rings/integration.jl:32-77
+        ri, rj = i // self.nmax, j // self.nmax
+        ic = self.dyn.interaction(self.ty(ri), self.ty(rj))
+        dr = self.calc_diff(self.pos[i], self.pos[j])
+        dist = math.sqrt(dr[0] ** 2 + dr[1] ** 2)
+        if dist > ic.dist_max:
+            return np.zeros(2)
+        if ri == rj:
+            diff = abs(i - j)
+            if diff == 1 or diff == self.np_of[ri] - 1:
+                return np.zeros(2)
+        if dist < ic.dist_eq:
+            fmod = -ic.k_rep * (dist / ic.dist_eq - 1)
+        elif ri == rj:
+            fmod = 0.0
+        else:
+            fmod = -ic.k_atr * (dist / ic.dist_eq - 1)
+        return fmod / dist * dr
+
+    def forces_(self):  # forces!, src/rings/integration.jl:197-226
+        ids = self.ids
+        for a in range(len(ids)):
+            for b in range(a + 1, len(ids)):
+                f = self.calc_interaction(ids[a], ids[b])
+                self.forces[ids[a]] = self.forces[ids[a]] + f
+                self.forces[ids[b]] = self.forces[ids[b]] - f
+        d = self.dyn
+        for ring in range(self.nr):
+            n, t, b = self.np_of[ring], self.ty(ring), ring * self.nmax
+            k, l = d.k_spring[t], d.l_spring[t]
+            for s in range(n):   # springs_force, :79-97
+                p1, p2 = b + s, b + (0 if s == n - 1 else s + 1)
+                dr = self.calc_diff(self.pos[p1], self.pos[p2])
+                dist = math.sqrt(dr[0] ** 2 + dr[1] ** 2)
+                f = (-k * (dist - l)) / dist * dr
+                self.forces[p1] = self.forces[p1] + f
+                self.forces[p2] = self.forces[p2] - f
+        for ring in range(self.nr):  # area_forces!, :140-195 (+ calc_area :103-116)
+            n, t, b = self.np_of[ring], self.ty(ring), ring * self.nmax
+            pts = self.ring_points(ring)
+            area = 0.0
+            for q in range(n - 1):
+                area += pts[q][0] * pts[q + 1][1] - pts[q][1] * pts[q + 1][0]
+            area += pts[-1][0] * pts[0][1] - pts[-1][1] * pts[0][0]
+            area = area / 2.0
+            self.areas[ring] = area
+            area0 = (n * d.l_spring[t] / d.p0[t]) ** 2
+            for q in range(n):
+                fmod = d.k_area[t] * (area - area0)
+                id1 = n - 1 if q == 0 else q - 1
+                id2 = 0 if q == n - 1 else q + 1
+                dr = self.calc_diff(self.pos[b + id2], self.pos[b + id1])
+                a_deriv = np.array([dr[1], -dr[0]]) / 2
+                self.forces[b + q] = self.forces[b + q] - fmod * a_deriv
+
+    def update(self, step):  # update!, src/rings/integration.jl:300-351
+        d = self.dyn
+        for ring in range(self.nr):
+            n, t, b = self.np_of[ring], self.ty(ring), ring * self.nmax
+            theta = self.pol[ring]
+            pol = np.array([math.cos(theta), math.sin(theta)])
+            vel_cm = np.zeros(2)
+            for q in range(n):
+                vel = d.vo[t] * pol + d.mobility[t] * self.forces[b + q]
+                vel_cm = vel_cm + vel
+                self.pos[b + q] = self.pos[b + q] + vel * self.dt
+            vel_cm = vel_cm / n
+            speed = math.sqrt(vel_cm[0] ** 2 + vel_cm[1] ** 2)
+            if speed == 0:
+                cross = 0
+            else:
+                cross = (pol[0] * vel_cm[1] - pol[1] * vel_cm[0]) / speed
+                if abs(cross) > 1:
+                    cross = math.copysign(1.0, cross)
+            self.pol[ring] = theta + (1 / d.relax_time[t] * math.asin(cross) * self.dt +
+                                      math.sqrt(2 * d.rot_diff[t] * self.dt) * self.noise[step][ring])
+
+    def walls(self):  # the core periodic walls! over the active ids (src/integration.jl:309-324)
+        if not self.periodic:
+            return
+        half = self.size / 2
+        for i in self.ids:
+            diff = self.pos[i] - half
+            out = np.abs(diff) > half
+            if out.any():
+                self.pos[i] = self.pos[i] - np.sign(diff) * (half * 2) * out
+
+    def step(self, nsteps):  # step!, src/rings/integration.jl:522-543
+        for s in range(nsteps):
+            self.update_cms()
+            self.update_continuos_pos()
+            self.clean()
+            self.forces_()
+            self.update(s)
+            self.walls()
+
+
+@pytest.mark.parametrize("kind,use_chunks", [("normal", False), ("normal", True), ("types", True)])
+def test_rings_steps_match_second_restatement(oracle, kind, use_chunks):
+    n = 4
+    case = H.rings_case(kind, n, n, use_chunks=use_chunks)
+    steps = 40
+    noise = np.random.default_rng(9).standard_normal((steps, n * n))
+    o, r = H.make_oracle(case), RefRings(case, noise)
+    assert H.rel_err(o.get_forces(), np.array(r.forces)) < 1e-12      # constructor state
+    o.step(steps, noise)
+    r.step(steps)
+    assert np.abs(o.pos() - np.array(r.pos)).max() < 1e-12 * case["geom"].length
+    assert np.abs(o.second() - np.array(r.pol)).max() < 1e-11
+    assert H.rel_err(o.get_forces(), np.array(r.forces)) < 1e-10
+    areas, cms, cont = o.rings_info()
+    assert H.rel_err(areas, np.array(r.areas)) < 1e-12 and H.rel_err(cms, np.array(r.cms)) < 1e-12
+    active = np.array(r.ids)
+    assert H.rel_err(cont[active], np.array(r.cont)[active]) < 1e-12
