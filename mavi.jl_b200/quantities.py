@@ -4,10 +4,10 @@ from __future__ import annotations
 
 def kinetic_energy(system):
     """`kinetic_energy(state)`, src/quantities.jl:12-18 (takes the system: the state lives on the device)."""
-    return system.energies(0)[0]
+    return system.energies(0, want_pe=False)[0]
 
 
 def potential_energy(system, dynamic_cfg=None, stencil_only=False):
     """`potential_energy(system, ::LenJonesCfg)`, src/quantities.jl:46-66: exact all-pairs O(N^2).
     stencil_only=True sums only the cell-stencil pair set (labelled deviation, SURVEY.md A.3 #11)."""
-    return system.energies(1 if stencil_only else 0)[1]
+    return system.energies(1 if stencil_only else 0, want_ke=False)[1]

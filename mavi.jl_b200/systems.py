@@ -206,10 +206,13 @@ class System:
         return [out[i] for i in range(n.value)]
 
     # ------------------------------------------------------------------ quantities / instrumentation
-    def energies(self, pe_mode=0):
+    def energies(self, pe_mode=0, want_ke=True, want_pe=True):
+        """(kinetic_energy, potential_energy); a quantity that is not wanted is not computed (NULL pointer) and comes
+        back as None — the exact potential energy is O(N^2) like the reference's (src/quantities.jl:46-66)."""
         ke, pe = C.c_double(), C.c_double()
-        self._check(self._lib.mavi_energies(self._h, pe_mode, C.byref(ke), C.byref(pe)))
-        return ke.value, pe.value
+        self._check(self._lib.mavi_energies(self._h, pe_mode, C.byref(ke) if want_ke else None,
+                                            C.byref(pe) if want_pe else None))
+        return (ke.value if want_ke else None), (pe.value if want_pe else None)
 
     def launch_count(self):
         n = C.c_int64()
