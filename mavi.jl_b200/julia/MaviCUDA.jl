@@ -24,7 +24,7 @@ using Mavi.Systems
 import Mavi.Integration: calc_forces!, newton_step!, szabo_step!, rtp_step!, get_step_function
 import Mavi.RunSystem: run_system
 
-export CUDADevice, sync_to_host!, upload_state!, device_energies
+export CUDADevice, sync_to_host!, upload_state!, device_energies, sync_rings_info!, sync_particle_neighbors!
 
 const LIB = get(ENV, "MAVI_CUDA_LIB", "libmavi_cuda.so")
 const MAVI_MAX_SPACES = 8
@@ -130,6 +130,35 @@ dyn_block(c::LenJonesCfg) = (Int32(0), (c.sigma, c.epsilon, 0, 0, 0, 0, 0, 0))
 dyn_block(c::HarmTruncCfg) = (Int32(1), (c.k_rep, c.k_atr, c.dist_eq, c.dist_max, 0, 0, 0, 0))
 dyn_block(c::SzaboCfg) = (Int32(2), (c.vo, c.mobility, c.relax_time, c.k_rep, c.k_adh, c.r_eq, c.r_max, c.rot_diff))
 dyn_block(c::RunTumbleCfg) = (Int32(3), (c.vo, c.sigma, c.epsilon, c.tumble_rate, 0, 0, 0, 0))
+dyn_block(::Mavi.Rings.Configs.RingsCfg) = (Int32(4), (0, 0, 0, 0, 0, 0, 0, 0))   # parameters travel in MaviRingsParams
+
+"""
+RingsCfg + RingsState -> MaviRingsParams (src/rings/configs.jl:95-107, src/rings/states.jl:74-124).  Scalars are
+broadcast to one entry per ring type; the InteractionMatrix becomes [t1][t2][k_rep,k_atr,dist_eq,dist_max] (row-major for
+the C side).  Every array is pushed to `keep` so that it outlives the `mavi_create` call.
+"""
+function lower_rings(cfg, state, keep)
+    nt = cfg.num_types
+    vecf(x) = (v = x isa Number ? fill(Float64(x), nt) : Float64.(x); push!(keep, v); v)
+    np = state.num_particles isa Integer ? fill(Int32(state.num_particles), nt) : Int32.(state.num_particles)
+    push!(keep, np)
+    finder = cfg.interaction_finder
+    inter = Float64[]
+    for a in 1:nt, b in 1:nt
+        ic = Mavi.Rings.Configs.get_interaction_cfg(a, b, finder)
+        append!(inter, (ic.k_rep, ic.k_atr, ic.dist_eq, ic.dist_max))
+    end
+    push!(keep, inter)
+    types = isnothing(state.types) ? Int32[] : Int32.(state.types)       # 1-based, as MaviRingsParams.types expects
+    push!(keep, types)
+    n_max, num_rings = size(state.rings_pos)
+    rp = Ref(MaviRingsParams(nt, n_max, num_rings,
+        pointer(vecf(cfg.p0)), pointer(vecf(cfg.relax_time)), pointer(vecf(cfg.vo)), pointer(vecf(cfg.mobility)),
+        pointer(vecf(cfg.rot_diff)), pointer(vecf(cfg.k_area)), pointer(vecf(cfg.k_spring)), pointer(vecf(cfg.l_spring)),
+        pointer(np), pointer(inter), isempty(types) ? C_NULL : pointer(types)))
+    push!(keep, rp)
+    return Base.unsafe_convert(Ptr{MaviRingsParams}, rp)
+end
 
 # ---- handle attached to a System (kept in a side table so that `System` itself is untouched) -----------------------
 mutable struct DeviceState
@@ -148,6 +177,7 @@ end
 
 second_array(s::SecondLawState) = s.vel
 second_array(s::SelfPropelledState) = s.pol_angle
+second_array(s::Mavi.Rings.States.RingsState) = s.pol          # one polarisation angle per ring
 
 "Create the device context for `system` and upload its state (what the `System` ctor does on the CPU: force buffers, Chunks, first update_chunks!)."
 function attach!(system::System)
@@ -160,12 +190,13 @@ function attach!(system::System)
     bbox = Configs.get_bounding_box(sc.geometry_cfg)
     cc = system.int_cfg.chunks_cfg
     kind, dyn = dyn_block(system.dynamic_cfg)      # unknown DynamicCfg -> MethodError -> caller keeps the CPU path
+    rings_ptr = kind == 4 ? lower_rings(system.dynamic_cfg, system.state, keep) : Ptr{MaviRingsParams}(C_NULL)
     T = eltype(eltype(system.state.pos))            # Float64 (default) or Float32: the state's element type picks the build
     T in (Float64, Float32) || error("CUDADevice supports Float64 and Float32 states, got $T")
     params = Ref(MaviParams(sizeof(MaviParams), T === Float32 ? 1 : 0, length(system.state.pos), length(pairs), 0, Tuple(spaces),
         Tuple(Float64.(bbox.bottom_left)), bbox.length, bbox.height,
         isnothing(cc) ? 0 : cc.num_cols, isnothing(cc) ? 0 : cc.num_rows, kind, 0, Float64.(dyn),
-        minimum(particle_radius(system.dynamic_cfg)), C_NULL, system.int_cfg.dt,
+        minimum(particle_radius(system.dynamic_cfg)), rings_ptr, system.int_cfg.dt,
         dev.rng_mode == :host_noise ? 0 : 1, 0, dev.seed, dev.device, 0, C_NULL, 0, 1, C_NULL, 0))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     ds = DeviceState(C_NULL, keep, 0)
@@ -176,6 +207,9 @@ function attach!(system::System)
     end
     HANDLES[system] = ds
     check(ds, ccall((:mavi_set_time, LIB), Int32, (Ptr{Cvoid}, Int64, Float64), ds.h, system.time_info.num_steps, system.time_info.time))
+    if kind == 4 && !isnothing(system.info.p_neigh)      # RingsSystem(p_neighbors_cfg=...): before the upload, whose
+        enable_particle_neighbors!(ds, system.info.p_neigh)   # forces! fills the lists like the reference's constructor
+    end
     upload_state!(system)
     finalizer(_ -> ccall((:mavi_destroy, LIB), Int32, (Ptr{Cvoid},), ds.h), ds)
     return ds
@@ -230,6 +264,23 @@ function calc_forces!(system::System, chunks, ::CUDADevice)
     check(ds, ccall((:mavi_calc_forces, LIB), Int32, (Ptr{Cvoid},), ds.h))
     f = get_forces(system)
     GC.@preserve f check(ds, ccall((:mavi_download_forces, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ds.h, pointer(f)))
+end
+
+# Mavi.Rings: `Rings.Integration.step!` (src/rings/integration.jl:522-543) and the RingsInfo fields host code reads
+# (src/rings/rings.jl:118-128; SURVEY.md A.2).  `noise` = one randn per ring and step in :host_noise mode.
+function Mavi.Rings.Integration.step!(system::CUDASystem; noise=nothing)
+    device_step!(system, 1; noise=noise)
+    system.int_cfg.device.sync_every == 1 && sync_rings_info!(system)
+    return nothing
+end
+
+function sync_rings_info!(system)
+    ds = handle(system)
+    info = system.info
+    GC.@preserve info check(ds, ccall((:mavi_rings_download_info, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+        ds.h, pointer(info.areas), pointer(info.cms), pointer(info.continuos_pos)))
+    isnothing(info.p_neigh) || sync_particle_neighbors!(system)
+    return info
 end
 
 "`run_system` with the default step function: ONE `mavi_step(h, nsteps)` and one download."
