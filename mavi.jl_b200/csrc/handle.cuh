@@ -65,7 +65,7 @@ struct Handle {
   char err[512] = {0};
 
   bool maps_valid = false;
-  LaunchCtx ctx() { return LaunchCtx{stream, &launches, &maps_valid}; }
+  LaunchCtx ctx() { return LaunchCtx{stream, &launches, &maps_valid, flags_cfg}; }
   void set_error(const char *fmt, ...);
   int check_device_flags();
   int pending_out_of_grid();

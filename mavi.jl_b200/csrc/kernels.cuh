@@ -60,6 +60,7 @@ struct LaunchCtx {
   cudaStream_t stream;
   long long *launches;  // incremented per kernel launch
   bool *maps_valid;     // rank maps (tile_prefix / cta_first) match tstart; the step loop only invalidates them
+  int flags;            // MaviParams.flags (kernel-variant switches)
 };
 
 // full build of the tile layout from the staging arrays (upload, mavi_bin, overflow fallback)
