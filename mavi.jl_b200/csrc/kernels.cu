@@ -1551,7 +1551,14 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p_in, const DevArrays 
 #define CALL2C(D, P) MAVI_LAUNCH(c, (k_newton_b2<D, P, true, 4>), grid2(p), TPB, PASS2_SMEM, ARGS2)
     if (carry && (c.flags & MAVI_FLAG_WARP_TILES) && !p.slab && blk_mode == 0) {  // experimental, see k_newton_b2w
       ms.chg = a.chg;
-#define CALLW(D, P) MAVI_LAUNCH(c, (k_newton_b2w<D, P, true>), gridw(p), TPB, PASSW_SMEM, ARGS2)
+      // more than the 48 KB a kernel gets by default: opt in once per instantiation
+#define CALLW(D, P)                                                                                               \
+  do {                                                                                                            \
+    static const cudaError_t attr_ = cudaFuncSetAttribute((const void *)k_newton_b2w<D, P, true>,                 \
+                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, PASSW_SMEM); \
+    (void)attr_;                                                                                                  \
+    MAVI_LAUNCH(c, (k_newton_b2w<D, P, true>), gridw(p), TPB, PASSW_SMEM, ARGS2);                                 \
+  } while (0)
       if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALLW);
       else MAVI_DISPATCH2(MAVI_DYN_HARMTRUNC, p.periodic, CALLW);
 #undef CALLW
