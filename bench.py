@@ -342,49 +342,111 @@ def run_ours(args):
         traffic = tr[dom]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     step_achieved = B_ALG_NEWTON * n * world / (ms * 1e-3 / args.steps) / 1e9
-    two_pass = None
-    if world == 1 and carry and not args.no_two_pass:
-        # A/B: the same workload with the carry switched off (two full force passes per step), for transparency
+    # ---- side measurements (never part of `value`; each one is fault-isolated so that it cannot cost the line) --------
+    def timed_steps(sysx, k):
+        barrier()
+        e0.record()
+        sysx.step(k)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / k
+
+    def side(fn):
+        try:
+            return fn()
+        except Exception as exc:  # noqa: BLE001 — report, do not lose the main measurement
+            return {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
+    if world == 1:
         system.close()
         system = None
-        dev2 = pkg.CUDADevice(device=local_rank, stream=stream, flags=args.flags | pkg.capi.FLAG_NO_FORCE_CARRY)
-        w2 = lj_workload(pkg, nx, ny, cuda_device=dev2)
+    mkdev = lambda **kw: pkg.CUDADevice(device=local_rank, stream=stream, **kw)  # noqa: E731
+
+    def m_two_pass():
+        # A/B: the same workload with the carry switched off (two full force passes per step), for transparency
+        w2 = lj_workload(pkg, nx, ny, cuda_device=mkdev(flags=args.flags | pkg.capi.FLAG_NO_FORCE_CARRY))
         s2 = pkg.System(state=pkg.SecondLawState(pos=w2["pos"], vel=w2["vel"]), space_cfg=w2["space"], dynamic_cfg=w2["dyn"], int_cfg=w2["int_cfg"])
-        s2.step(args.warmup)
-        k2 = max(10, args.steps // 4)
-        barrier()
-        e0.record()
-        s2.step(k2)
-        e1.record()
-        barrier()
-        two_pass = {"ms_per_step": e0.elapsed_time(e1) / k2, "steps": k2, "what": "MAVI_FLAG_NO_FORCE_CARRY: full first + second force pass every step"}
-        s2.close()
-    float32 = None
-    if world == 1 and not args.no_f32 and not slab_api:
+        try:
+            s2.step(args.warmup)
+            k2 = max(10, args.steps // 4)
+            return {"ms_per_step": timed_steps(s2, k2), "steps": k2, "what": "MAVI_FLAG_NO_FORCE_CARRY: full first + second force pass every step"}
+        finally:
+            s2.close()
+
+    def m_float32():
         # the optional Float32 mode (mavi_f32 build of the same kernels) on the same workload, for reference; the
-        # headline metric stays Float64.  88 B per particle-step (half of the 168 B + the 4-byte cell index)
-        if system is not None:
-            system.close()
-            system = None
-        w3 = lj_workload(pkg, nx, ny, cuda_device=pkg.CUDADevice(device=local_rank, stream=stream, flags=args.flags))
+        # headline metric stays Float64.  88 B per particle-step
+        w3 = lj_workload(pkg, nx, ny, cuda_device=mkdev(flags=args.flags))
         s3 = pkg.System(state=pkg.SecondLawState(pos=w3["pos"].astype(np.float32), vel=w3["vel"].astype(np.float32)),
                         space_cfg=w3["space"], dynamic_cfg=w3["dyn"], int_cfg=w3["int_cfg"])
-        s3.step(args.warmup)
-        k3 = max(10, args.steps // 2)
-        barrier()
-        e0.record()
-        s3.step(k3)
-        e1.record()
-        barrier()
-        ms3 = e0.elapsed_time(e1) / k3
-        float32 = {"ms_per_step": ms3, "steps": k3, "value": n / (ms3 * 1e-3), "unit": "particle-steps/s",
-                   "roofline_step_frac": 88.0 * n / (ms3 * 1e-3) / 1e9 / peak, "bytes_per_particle_step": 88.0,
-                   "what": "MaviParams.dtype = MAVI_F32 (Float32 state and arithmetic), same kernels compiled with real = float"}
-        s3.close()
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+        try:
+            s3.step(args.warmup)
+            k3 = max(10, args.steps // 2)
+            ms3 = timed_steps(s3, k3)
+            return {"ms_per_step": ms3, "steps": k3, "value": n / (ms3 * 1e-3), "unit": "particle-steps/s",
+                    "roofline_step_frac": 88.0 * n / (ms3 * 1e-3) / 1e9 / peak, "bytes_per_particle_step": 88.0,
+                    "what": "MaviParams.dtype = MAVI_F32 (Float32 state and arithmetic), same kernels compiled with real = float"}
+        finally:
+            s3.close()
+
+    def m_szabo():
+        # BASELINE config C3 on this GPU: examples/szabo.jl parameters, lattice offset 1, cells (n-1)^2, dt 0.01, Philox noise
+        dyn = pkg.SzaboCfg(vo=1.0, mobility=1.0, relax_time=1.0, k_rep=10.0, k_adh=0.75, r_eq=1.0, r_max=1.1, rot_diff=0.01)
+        pos, geom = pkg.rectangular_grid(nx, ny, 1.0, pkg.particle_radius(dyn))
+        ang = np.random.default_rng(SEED).random(nx * ny) * 2 * np.pi
+        s4 = pkg.System(state=pkg.SelfPropelledState(pos=pos, pol_angle=ang),
+                        space_cfg=pkg.SpaceCfg(wall_type=pkg.PeriodicWalls(), geometry_cfg=geom), dynamic_cfg=dyn,
+                        int_cfg=pkg.IntCfg(dt=0.01, chunks_cfg=pkg.ChunksCfg(nx - 1, ny - 1), device=mkdev(rng_mode="philox")))
+        try:
+            s4.step(args.warmup)
+            k4 = max(10, args.steps // 4)
+            ms4 = timed_steps(s4, k4)
+            return {"ms_per_step": ms4, "steps": k4, "value": n / (ms4 * 1e-3), "unit": "particle-steps/s",
+                    "roofline_step_frac": 88.0 * n / (ms4 * 1e-3) / 1e9 / peak, "bytes_per_particle_step": 88.0,
+                    "what": f"BASELINE config C3 on one GPU: Szabo self-propelled particles {nx}x{ny}, periodic, f64, szabo_step!, Philox noise"}
+        finally:
+            s4.close()
+
+    def m_rings():
+        # BASELINE config C4: 400 x 250 rings x 10 particles (test/tests_rings/rings_utils.jl:35-53 parameters), periodic
+        from mavi_jl_b200.rings import configs as rc
+        from mavi_jl_b200.rings import init_states as ri
+        from mavi_jl_b200.rings.rings import RingsSystem
+        from mavi_jl_b200.rings.states import RingsState
+        inter = rc.HarmTruncCfg(k_rep=20, k_atr=4, dist_eq=1, dist_max=1 + 0.2)
+        dyn = rc.RingsCfg(p0=3.5, relax_time=1, vo=1.0, mobility=1, rot_diff=0.05, k_area=1, k_spring=20, l_spring=1,
+                          num_particles=10, interaction_finder=inter)
+        cols, rows = 400, 250
+        rings_pos, geom = ri.rectangular_grid(num_cols=cols, num_rows=rows, num_particles=10, p_radius=dyn.particle_radius(),
+                                              pad_x=0.1, pad_y=0.1)
+        pol = ri.random_pol(cols * rows, rng=np.random.default_rng(SEED))
+        max_size = inter.dist_max * 1.1
+        chunks = pkg.ChunksCfg(int(geom.length // max_size), int(geom.height // max_size))
+        s5 = RingsSystem(state=RingsState(rings_pos=rings_pos, pol=pol),
+                         space_cfg=pkg.SpaceCfg(wall_type=pkg.PeriodicWalls(), geometry_cfg=geom), dynamic_cfg=dyn,
+                         int_cfg=rc.RingsIntCfg(dt=0.01, p_chunks_cfg=chunks, device=mkdev(rng_mode="philox")))
+        try:
+            s5.step(args.warmup)
+            k5 = max(10, args.steps // 4)
+            ms5 = timed_steps(s5, k5)
+            n5 = cols * rows * 10
+            return {"ms_per_step": ms5, "steps": k5, "value": n5 / (ms5 * 1e-3), "unit": "particle-steps/s",
+                    "roofline_step_frac": 108.0 * n5 / (ms5 * 1e-3) / 1e9 / peak, "bytes_per_particle_step": 108.0,
+                    "what": "BASELINE config C4: Mavi.Rings, 100k rings x 10 particles, periodic, f64, Rings step!, Philox noise"}
+        finally:
+            s5.close()
+
+    slab_api_main = world > 1 or bool(args.flags & pkg.capi.FLAG_SLAB_SELF)
+    two_pass = side(m_two_pass) if (world == 1 and carry and not args.no_two_pass and not slab_api_main) else None
+    float32 = side(m_float32) if (world == 1 and not args.no_f32 and not slab_api_main) else None
+    other = None
+    if world == 1 and not args.no_other_configs and not slab_api_main:
+        other = {"szabo_c3": side(m_szabo), "rings_c4": side(m_rings)}
+    def m_cpu():
         rate, secs, threads, sample = cpu_reference_rate(pkg, args.cpu_steps, 1, sample_n=args.cpu_sample)
-        cpu = {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample}
+        return {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample}
+
+    cpu = side(m_cpu) if (world == 1 and not args.no_cpu_baseline) else None
     line = {
         "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -403,6 +465,7 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "two_pass": two_pass,
         "float32": float32,
+        "other_configs": other,
         "e2e": {"value": e2e_value, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                 "steps": e2e_steps,
                 "what": ("per step and rank: mavi_download_local(ids,pos,vel into pinned host) + mavi_upload_local(ids,pos,vel) + mavi_step(1)"
@@ -430,6 +493,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-two-pass", action="store_true", help="skip the A/B run with the force carry switched off")
     ap.add_argument("--no-f32", action="store_true", help="skip the Float32-mode side measurement")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the Szabo (C3) and Rings (C4) side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
