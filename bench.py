@@ -33,10 +33,13 @@ SEED = 24042001
 B_ALG_NEWTON = 168.0  # algorithmic bytes per particle-step, Float64 Newton/LJ: bin 24 + A 64 + B 80
 B_ALG_PASS_B = 80.0   # pass B: read pos', vel, F1 (48) + write vel', F2 (32)
 B_ALG_PASS_A = 64.0   # pass A: read pos, vel (32) + write pos', F1 (32)
-# Force carry (default): ONE launch per step = pass B fused with the next step's pass A.  Its own compulsory traffic is
-# read pos', vel, F1 (48) + write vel', F2, pos'' (48) = 96 B (F1 of the next step is F2) — the number
-# the kernel-level roofline uses; the step-level figure keeps SURVEY.md 8d's 168 B of the three-barrier formulation.
-B_ALG_FUSED = 96.0
+# Force carry (default): ONE launch per step does pass B of step n AND pass A of step n+1.  `roofline.achieved` follows
+# the bench contract literally: SURVEY.md 8d's per-unit figure for the work the launch does (80 + 64 = 144 B per particle)
+# x the particles it processes / its duration.  The launch's OWN compulsory traffic is smaller because the fusion removes
+# re-reads (read pos', vel, F1 = 48; write vel', F2 == F1(n+1), pos'' = 48 -> 96 B): reported beside it as
+# `roofline.min_traffic`, together with the measured DRAM bytes (`traffic`) — DESIGN.md 4.
+B_ALG_FUSED = B_ALG_PASS_B + B_ALG_PASS_A
+B_MIN_FUSED = 96.0
 
 
 def measured_peak_hbm():
@@ -457,6 +460,12 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_kind": peak_kind, "kernel_ms": dom_ms,
                      "bytes_per_particle": dom_bytes / n,
+                     "accounting": ("SURVEY.md 8d algorithmic bytes of the work this launch does: pass B of step n (80 B) + pass A "
+                                    "of step n+1 (64 B) per particle") if carry else "SURVEY.md 8d algorithmic bytes of this pass",
+                     "min_traffic": ({"bytes_per_particle": B_MIN_FUSED, "achieved": B_MIN_FUSED * n / (dom_ms * 1e-3) / 1e9,
+                                      "frac": B_MIN_FUSED * n / (dom_ms * 1e-3) / 1e9 / peak,
+                                      "what": "the fused launch's own compulsory DRAM traffic (the fusion removes the re-reads "
+                                              "between the two passes); compare with `traffic`"} if (carry and dom_ms > 0) else None),
                      "what": ("k_newton_b<CARRY>: force pass 2 + kick + walls! + re-bin decision of step n fused with force pass 1 + drift of "
                               "step n+1 (F1(n+1) = F2(n) except near re-binned particles, which are recomputed sparsely; bit-identical "
                               "to two full passes)") if carry else "two full force passes per step (MAVI_FLAG_NO_FORCE_CARRY)",
