@@ -447,7 +447,11 @@ def run_ours(args):
         other = {"szabo_c3": side(m_szabo), "rings_c4": side(m_rings)}
     def m_cpu():
         rate, secs, threads, sample = cpu_reference_rate(pkg, args.cpu_steps, 1, sample_n=args.cpu_sample)
-        return {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample}
+        out = {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample}
+        # the reference's DEFAULT device is Sequencial (one thread, src/configs.jl:471-487): reported beside the Threaded figure
+        r1, _, _, s1 = cpu_reference_rate(pkg, max(2, args.cpu_steps // 3), 1, sample_n=max(100, args.cpu_sample // 2), threads=1)
+        out["sequencial"] = {"value": r1, "cores": 1, "sample": s1}
+        return out
 
     cpu = side(m_cpu) if (world == 1 and not args.no_cpu_baseline) else None
     line = {
