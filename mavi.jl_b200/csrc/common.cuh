@@ -67,7 +67,8 @@ struct DevParams {
   unsigned int tpc_mul, tpc_shr;    // ... by tpc
   unsigned int cols_mul, cols_shr;  // ... by ord_cols
   int periodic;              // calc_diff applies the minimum image (src/integration.jl:43-48)
-  real grid_bl[2], grid_h, cl, ch;
+  double grid_bl[2], grid_h, cl, ch;  // Float64 in BOTH builds: Chunks keeps chunk_length / chunk_height and the geometry in
+                                      // Float64 (src/chunks.jl:13,27-30), so a Float32 state is binned with Float64 arithmetic
   real size[2], half[2];   // main rectangle size and size/2
   int dynamics;
   real dyn[8];
@@ -160,19 +161,20 @@ __device__ __forceinline__ int tq_of(const DevParams &p, int col, int row) {
 // rem is exact, so the reference value is trunc(x/y) of the REAL quotient.  fl(x/y) can be off by one unit when x
 // is a rounded multiple of y; one FMA gives the sign of the exact remainder and fixes it.  Verified against the
 // fmod formulation (oracle mor_julia_div) in tests/test_oracle_kat.py and tests/test_gpu_binning.py.
-__device__ __forceinline__ real julia_div_pos(real x, real y) {
-  real ax = fabs(x);
-  real q = trunc(ax / y);
-  real rem = fma(-q, y, ax);  // sign (and zero-ness) of ax - q*y is exact
+__device__ __forceinline__ double julia_div_pos(double x, double y) {
+  double ax = fabs(x);
+  double q = trunc(ax / y);
+  double rem = fma(-q, y, ax);  // sign (and zero-ness) of ax - q*y is exact
   if (rem < 0.0) q -= 1.0;
   else if (rem >= y) q += 1.0;
   return copysign(q, x);
 }
 
 // update_particle_chunk! (src/chunks.jl:120-147): 0-based linear cell id (row fastest), or -1 if out of grid.
-__device__ __forceinline__ int cell_of_point(const DevParams &p, real x, real y) {
-  real rowf = julia_div_pos(-y + p.grid_bl[1] + p.grid_h, p.ch);
-  real colf = julia_div_pos(x - p.grid_bl[0], p.cl);
+// Positions of a Float32 state are promoted: div(-pos[2] + bottom_left[2] + space_h, chunk_h) mixes Float32 and Float64.
+__device__ __forceinline__ int cell_of_point(const DevParams &p, double x, double y) {
+  double rowf = julia_div_pos(-y + p.grid_bl[1] + p.grid_h, p.ch);
+  double colf = julia_div_pos(x - p.grid_bl[0], p.cl);
   if (!(fabs(rowf) < 2.0e9) || !(fabs(colf) < 2.0e9)) return -1;  // NaN/Inf -> InexactError in the reference
   int row = (int)rowf + 1, col = (int)colf + 1;
   row -= (row == p.num_rows + 1) ? 1 : 0;
@@ -195,12 +197,12 @@ __device__ __forceinline__ int cell_of_point(const DevParams &p, real x, real y)
 // trunc of the REAL quotient t/c, so index == k  <=>  k*c <= t < (k+1)*c with the products taken exactly; for a double t
 // that is  RU(k*c) <= t < RU((k+1)*c)  (RU = round-up multiply).  Edge conventions of src/chunks.jl:129-142: index -0
 // (t in (-c, 0)) maps to the first cell, index n (t in [n*c, (n+1)*c)) is clamped to the last cell.
-__device__ __forceinline__ bool axis_in_cell(real t, int k, int n, real c) {
-  bool lo = (k == 0) ? (t > -c) : (t >= mul_ru((real)k, c));
-  bool hi = t < mul_ru((real)((k == n - 1) ? n + 1 : k + 1), c);
+__device__ __forceinline__ bool axis_in_cell(double t, int k, int n, double c) {
+  bool lo = (k == 0) ? (t > -c) : (t >= __dmul_ru((double)k, c));
+  bool hi = t < __dmul_ru((double)((k == n - 1) ? n + 1 : k + 1), c);
   return lo && hi;
 }
-__device__ __forceinline__ bool still_in_cell(const DevParams &p, real x, real y, int cell) {
+__device__ __forceinline__ bool still_in_cell(const DevParams &p, double x, double y, int cell) {
   int col = div_rows(p, cell);
   const int row = cell - col * p.num_rows;
   if (p.slab) {  // local -> global column
