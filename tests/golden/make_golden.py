@@ -5,7 +5,7 @@ t = 10, test/tests_rings/runtests.jl:17-34) depend on Julia's MersenneTwister st
 image, so NO fixture here comes from a run of the reference.  The snapshots below are outputs of the CPU oracle
 (oracle/mavi_oracle.c) on the seeded cases of tests/helpers.py, frozen at the commit where the oracle agreed with the
 independent restatements of tests/test_oracle_kat.py and tests/test_oracle_steps.py.  They pin the ORACLE against silent
-drift (tests/test_golden.py), nothing more; tolerances are 1e-12 because libm's sin/cos/asin may differ in the last ulp
+drift (tests/test_snapshots.py), nothing more; tolerances are 1e-12 because libm's sin/cos/asin may differ in the last ulp
 between machines.
 """
 import os
