@@ -79,37 +79,6 @@ def test_f32_float64_state_on_float32_device(cuda_lib):
     assert np.array_equal(g.state.pos, p0.astype(F32).astype(np.float64))
 
 
-@pytest.mark.parametrize("wall", ["periodic", "rigid"])
-def test_f32_cell_assignment_bit_exact(cuda_lib, wall):
-    """A Float32 state is binned with Float64 arithmetic, like the reference: Chunks keeps chunk_length / chunk_height and
-    the geometry in Float64 (src/chunks.jl:13,27-30), so div(-pos[2] + bottom_left[2] + space_h, chunk_h) promotes the
-    Float32 coordinate.  The cells must therefore equal, bit for bit, those of the Float64 oracle fed with the same
-    (Float32-representable) positions, and the trunc of the exact rational quotient."""
-    case = H.newton_case(nx=30, ny=26, wall=wall, jitter=0.45)
-    dev, ora = _f32_pair(case)
-    g, o = H.make_gpu(dev), H.make_oracle(ora)
-    cell, counts = g.download_cells()
-    co, no = o.download_cells()
-    assert np.array_equal(cell, co) and np.array_equal(counts, no)
-    p = g._lowered.params
-    cl, ch = p.grid_len / p.num_cols, p.grid_h / p.num_rows
-    pos = g.state.pos
-    for i in range(0, len(pos), 7):
-        x, y = float(pos[i, 0]), float(pos[i, 1])          # Float32 values, widened exactly
-        ty = -y + p.grid_bl[1] + p.grid_h                  # Float64, left to right (src/chunks.jl:129)
-        tx = x - p.grid_bl[0]
-        row = int(Fraction(ty) / Fraction(ch)) + 1         # int() truncates toward zero
-        col = int(Fraction(tx) / Fraction(cl)) + 1
-        row -= row == p.num_rows + 1
-        col -= col == p.num_cols + 1
-        assert cell[i] == (col - 1) * p.num_rows + (row - 1), i
-    g.step(10)
-    o.step(10)
-    o.update_chunks()   # device cells are always those of the current positions (the reference's NEXT update_chunks!)
-    same = g.download_cells()[0] == o.download_cells()[0]   # trajectories differ at Float32 level: nearly all cells agree
-    assert same.mean() > 0.98
-
-
 @pytest.mark.parametrize("chunks", [True, False])
 @pytest.mark.parametrize("wall", ["periodic", "rigid"])
 @pytest.mark.parametrize("dyn", ["lj", "harm"])
@@ -245,3 +214,34 @@ def test_f32_bitwise_reproducible(cuda_lib):
         outs.append((g.state.pos.copy(), g.state.vel.copy(), g.get_forces()))
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("wall", ["periodic", "rigid"])
+def test_f32_cell_assignment_bit_exact(cuda_lib, wall):
+    """A Float32 state is binned with Float64 arithmetic, like the reference: Chunks keeps chunk_length / chunk_height and
+    the geometry in Float64 (src/chunks.jl:13,27-30), so div(-pos[2] + bottom_left[2] + space_h, chunk_h) promotes the
+    Float32 coordinate.  The cells must therefore equal, bit for bit, those of the Float64 oracle fed with the same
+    (Float32-representable) positions, and the trunc of the exact rational quotient."""
+    case = H.newton_case(nx=30, ny=26, wall=wall, jitter=0.45)
+    dev, ora = _f32_pair(case)
+    g, o = H.make_gpu(dev), H.make_oracle(ora)
+    cell, counts = g.download_cells()
+    co, no = o.download_cells()
+    assert np.array_equal(cell, co) and np.array_equal(counts, no)
+    p = g._lowered.params
+    cl, ch = p.grid_len / p.num_cols, p.grid_h / p.num_rows
+    pos = g.state.pos
+    for i in range(0, len(pos), 7):
+        x, y = float(pos[i, 0]), float(pos[i, 1])          # Float32 values, widened exactly
+        ty = -y + p.grid_bl[1] + p.grid_h                  # Float64, left to right (src/chunks.jl:129)
+        tx = x - p.grid_bl[0]
+        row = int(Fraction(ty) / Fraction(ch)) + 1         # int() truncates toward zero
+        col = int(Fraction(tx) / Fraction(cl)) + 1
+        row -= row == p.num_rows + 1
+        col -= col == p.num_cols + 1
+        assert cell[i] == (col - 1) * p.num_rows + (row - 1), i
+    g.step(10)
+    o.step(10)
+    o.update_chunks()   # device cells are always those of the current positions (the reference's NEXT update_chunks!)
+    same = g.download_cells()[0] == o.download_cells()[0]   # trajectories differ at Float32 level: nearly all cells agree
+    assert same.mean() > 0.98
