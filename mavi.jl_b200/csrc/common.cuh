@@ -160,7 +160,7 @@ __device__ __forceinline__ int tq_of(const DevParams &p, int col, int row) {
 // Exact Base.div(x::Float64, y::Float64) = round((x - rem(x,y))/y) for y > 0 (call sites src/chunks.jl:129-130).
 // rem is exact, so the reference value is trunc(x/y) of the REAL quotient.  fl(x/y) can be off by one unit when x
 // is a rounded multiple of y; one FMA gives the sign of the exact remainder and fixes it.  Verified against the
-// fmod formulation (oracle mor_julia_div) in tests/test_oracle_kat.py and tests/test_gpu_binning.py.
+// fmod formulation (oracle mor_julia_div) in tests/test_oracle_kat.py and tests/test_gpu_core.py (test_cell_assignment_*).
 __device__ __forceinline__ double julia_div_pos(double x, double y) {
   double ax = fabs(x);
   double q = trunc(ax / y);
