@@ -222,7 +222,8 @@ def _numpy_forces(pos, dyn, geom, periodic):
         c = fmod / d
     elif isinstance(dyn, pkg.HarmTruncCfg):
         fmod = np.where(d < dyn.dist_eq, -dyn.k_rep * (d / dyn.dist_eq - 1), -dyn.k_atr * (d / dyn.dist_eq - 1))
-        c = np.where(d > dyn.dist_max, 0.0, fmod / d)
+        with np.errstate(invalid="ignore"):  # inf / inf on the diagonal, masked by the where
+            c = np.where(d > dyn.dist_max, 0.0, fmod / d)
     elif isinstance(dyn, pkg.SzaboCfg):
         fm = np.where(d > dyn.r_eq, dyn.k_adh / dyn.r_eq, dyn.k_rep / (dyn.r_max - dyn.r_eq))
         c = np.where(d > dyn.r_max, 0.0, -fm * (d - dyn.r_eq))
