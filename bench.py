@@ -173,24 +173,45 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_rate(pkg, steps, warmup, sample_n=1000, threads=None):
-    """The reference algorithm on the host cores: CPU oracle in Threaded mode (column-partitioned pair loop with private
-    force slices, src/integration.jl:159-194; serial re-bin; two force passes) on a bounded sample of the workload."""
+def workload_config(nx, ny, world):
+    """`config` of the JSON line — identical in both arms (the reference arm times the same workload)."""
+    n = nx * ny
+    return {"workload": f"LJ lattice gas {nx}x{ny}={n} particles per GPU, periodic rectangle, {int(nx * 0.9)}x{int(ny * 0.9)} chunks, "
+                        f"f64, dt=0.001, newton_step!", "l2": "state arrays (>=1.5 GB) exceed the 126 MB L2; no flush needed",
+            "parallelism": "single GPU" if world == 1 else f"{world} x-slabs of one {nx * world}x{ny} periodic box, NCCL halo+migration"}
+
+
+def host_mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable"):
+                return int(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
+
+
+def cpu_reference_rate(pkg, steps, warmup, nx=1000, ny=1000, threads=None, fast=True):
+    """The reference algorithm on the host cores: the C restatement (oracle source) in Threaded mode (column-partitioned
+    pair loop with private force slices, src/integration.jl:159-194; serial re-bin; two force passes), built with
+    `-O3 -march=native -fopenmp` as BASELINE.md 4 prescribes (`fast`; a separate target from the parity oracle)."""
     oracle = entry.load_oracle()
     from mavi_jl_b200.params import lower
     threads = threads or os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(threads))
-    w = lj_workload(pkg, sample_n, sample_n)
+    w = lj_workload(pkg, nx, ny)
     st = pkg.SecondLawState(pos=w["pos"], vel=w["vel"])
     o = oracle.OracleSystem(state=st, space_cfg=w["space"], dynamic_cfg=w["dyn"], int_cfg=w["int_cfg"], lower=lower,
-                            threads=threads)
+                            threads=threads, fast=fast)
     if warmup:
         o.step(warmup)
     t0 = time.perf_counter()
     o.step(steps)
     dt = time.perf_counter() - t0
-    n = sample_n * sample_n
-    return n * steps / dt, dt, threads, f"LJ lattice {sample_n}x{sample_n} = {n} particles (same density/cell ratio as the 16M workload), {steps} steps"
+    o.close()
+    n = nx * ny
+    return n * steps / dt, dt, threads, (f"LJ lattice {nx}x{ny} = {n} particles, {steps} timed steps after {warmup} warm-up, "
+                                        f"{'-O3 -march=native' if fast else '-O2 -ffp-contract=off'} -fopenmp, {threads} threads")
 
 
 def run_reference(args):
@@ -198,17 +219,128 @@ def run_reference(args):
     if rank != 0:
         return
     pkg = entry.load_package()
-    rate, secs, threads, sample = cpu_reference_rate(pkg, args.steps, args.warmup, sample_n=args.cpu_sample)
+    # the metric's own workload (16M) when the host has the memory for the reference's cell table (1.9 GB) + state,
+    # else a bounded 1M sample of the same lattice (same density and particles per cell)
+    full = host_mem_available_gb() > 24.0 and not args.cpu_small
+    nx, ny = (args.nx, args.ny) if full else (args.cpu_sample, args.cpu_sample)
+    rate, secs, threads, sample = cpu_reference_rate(pkg, args.steps, args.warmup, nx=nx, ny=ny)
     line = {
         "impl": "reference", "metric": "particle-steps/s", "value": rate, "unit": "particle-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "LJ lattice gas 4000x4000=16M, periodic, 3600x3600 chunks, f64, dt=0.001 (bounded sample on CPU)"},
+        "config": workload_config(args.nx, args.ny, args.gpus),
         "cpu_baseline": {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference algorithm restated in C (oracle, Threaded mode); Julia is not installed, parity unpinned",
+        "note": ("reference ALGORITHM restated in C (oracle source, Threaded mode, -O3 -march=native -fopenmp); the reference "
+                 "itself is Julia, which is not installed: parity unpinned"),
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- parity probe
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    sc = np.abs(b).max()
+    return float(np.abs(a - b).max() / (sc if sc > 0 else 1.0))
+
+
+def parity_probe_single(pkg, nx, ny, stream, local_rank, flags, steps=3):
+    """N = 1: the bench workload itself, `steps` newton_step!s from the initial state on the device (first pass + carried
+    steps) against the PARITY oracle (-O2 -ffp-contract=off, Threaded) — every particle compared."""
+    from mavi_jl_b200.params import lower
+    oracle = entry.load_oracle()
+    t0 = time.perf_counter()
+    w = lj_workload(pkg, nx, ny, cuda_device=pkg.CUDADevice(device=local_rank, stream=stream, flags=flags))
+    g = pkg.System(state=pkg.SecondLawState(pos=w["pos"].copy(), vel=w["vel"].copy()), space_cfg=w["space"],
+                   dynamic_cfg=w["dyn"], int_cfg=w["int_cfg"])
+    try:
+        g.step(steps)
+        g.sync_to_host()
+        gp, gv, gf = g.state.pos, g.state.vel, g.get_forces()
+        cg, _ = g.download_cells()
+    finally:
+        g.close()
+    threads = os.cpu_count() or 1
+    o = oracle.OracleSystem(state=pkg.SecondLawState(pos=w["pos"], vel=w["vel"]), space_cfg=w["space"], dynamic_cfg=w["dyn"],
+                            int_cfg=w["int_cfg"], lower=lower, threads=threads)
+    o.step(steps)
+    co, _ = o.download_cells()
+    errs = {"pos": float(np.abs(gp - o.pos()).max() / w["geom"].length), "vel": _rel(gv, o.second()), "force": _rel(gf, o.get_forces())}
+    out = {"max_rel_err": max(errs.values()), "n_checked": int(nx * ny), "errs": errs, "cells_bit_exact": bool(np.array_equal(cg, co)),
+           "steps": steps, "against": f"parity oracle (C restatement, Threaded, {threads} threads), every particle, {steps} steps from the initial state",
+           "seconds": time.perf_counter() - t0}
+    o.close()
+    return out
+
+
+def parity_probe_slabs(pkg, dist, system, w, nx, ny, rank, world, local_rank, stream, total_steps, strip_cols=2):
+    """N > 1: after the timed region every rank hands rank 0 the particles it holds within `strip_cols` cell columns of its
+    two slab boundaries (ids, positions, velocities, forces); rank 0 re-runs the SAME global system for the same number of
+    steps as ONE single-domain device run (no slabs, no NCCL: the path tests/ compare with the oracle) and checks (1) the
+    strips hold exactly the particles the single-domain run has there, (2) their state agrees, (3) the owned counts sum to
+    the global particle count.  All ranks take part in the collectives unconditionally."""
+    import torch
+    from mavi_jl_b200 import slabs
+    t0 = time.perf_counter()
+    geom = w["geom"]
+    ncols = int(nx * world * 0.9)
+    cl = geom.length / ncols
+    ids, pos, vel, frc = system.download_local()
+    lo, m = slabs.slab_columns(ncols, world, rank)
+    col = slabs.column_of(pos[:, 0], 0.0, geom.length, ncols)
+    d = (col - lo) % ncols                      # 0 .. m-1 for owned columns
+    sel = (d < strip_cols) | (d >= m - strip_cols)
+    mine = {"ids": ids[sel].copy(), "pos": pos[sel].copy(), "vel": vel[sel].copy(), "force": frc[sel].copy(), "n_local": int(len(ids)),
+            "foreign": int(((d < 0) | (d >= m)).sum())}
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(mine, gathered, dst=0)
+    out = None
+    if rank == 0:
+        try:
+            n_global = nx * world * ny
+            gp = np.empty((n_global, 2))
+            gv = np.empty((n_global, 2))
+            for r in range(world):          # the per-rank generators, placed by global id
+                wr = w if r == 0 else lj_workload(pkg, nx, ny, rank=r, world=world)
+                gp[wr["ids"]] = wr["pos"]
+                gv[wr["ids"]] = wr["vel"]
+            dyn = w["dyn"]
+            int_cfg = pkg.IntCfg(dt=0.001, chunks_cfg=pkg.ChunksCfg(num_cols=ncols, num_rows=int(ny * 0.9)),
+                                 device=pkg.CUDADevice(device=local_rank, stream=stream))
+            ref = pkg.System(state=pkg.SecondLawState(pos=gp, vel=gv), space_cfg=w["space"], dynamic_cfg=dyn, int_cfg=int_cfg)
+            try:
+                ref.step(total_steps)
+                ref.sync_to_host()
+                rf = ref.get_forces()
+            finally:
+                ref.close()
+            rp, rv = ref.state.pos, ref.state.vel
+            gid = np.concatenate([g["ids"] for g in gathered])
+            spos = np.concatenate([g["pos"] for g in gathered])
+            svel = np.concatenate([g["vel"] for g in gathered])
+            sfrc = np.concatenate([g["force"] for g in gathered])
+            # the particles the single-domain run has inside the same strips
+            rcol = slabs.column_of(rp[:, 0], 0.0, geom.length, ncols)
+            in_strip = np.zeros(n_global, dtype=bool)
+            for r in range(world):
+                lo_r, m_r = slabs.slab_columns(ncols, world, r)
+                dr = (rcol - lo_r) % ncols
+                in_strip |= (dr < strip_cols) | ((dr >= m_r - strip_cols) & (dr < m_r))
+            want = np.flatnonzero(in_strip)
+            same_set = bool(len(gid) == len(want) and np.array_equal(np.sort(gid), want))
+            errs = {"pos": float(np.abs(spos - rp[gid]).max() / geom.length), "vel": _rel(svel, rv[gid]), "force": _rel(sfrc, rf[gid])}
+            total = sum(g["n_local"] for g in gathered)
+            out = {"max_rel_err": max(errs.values()), "n_checked": int(len(gid)), "errs": errs, "strip_sets_equal": same_set,
+                   "bitwise_equal": bool(np.array_equal(spos, rp[gid]) and np.array_equal(svel, rv[gid]) and np.array_equal(sfrc, rf[gid])),
+                   "owned_total": int(total), "n_global": int(n_global), "count_conserved": bool(total == n_global),
+                   "foreign_particles": int(sum(g["foreign"] for g in gathered)), "steps": int(total_steps),
+                   "against": (f"single-domain run of the same {nx * world}x{ny} system on one GPU (the path tests/ compare with the "
+                               f"oracle), particles within {strip_cols} cell columns of every slab boundary, after {total_steps} steps"),
+                   "seconds": time.perf_counter() - t0}
+        except Exception as exc:  # noqa: BLE001
+            out = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    dist.barrier()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
@@ -279,6 +411,12 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     value = world * n * args.steps / (ms * 1e-3)
+    counters = system.counters()  # cell changes / tile repairs / emigrants summed over warm-up + timed steps (this rank)
+
+    # ---- parity probe at N > 1: the slab result against a single-domain run of the same global system ------------
+    probe = None
+    if world > 1 and not args.no_probe:
+        probe = parity_probe_slabs(pkg, dist, system, w, nx, ny, rank, world, local_rank, stream, args.warmup + args.steps)
 
     # ---- end to end through host buffers (`e2e`) -------------------------------------------------------
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
@@ -331,7 +469,7 @@ def run_ours(args):
     peak, peak_kind = measured_peak_hbm()
     traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (same N only)
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             tr = json.load(f)["dram_bytes_per_launch"]
     except Exception:
         tr = {}
@@ -341,7 +479,7 @@ def run_ours(args):
     dom_bytes = (B_ALG_PASS_B if dom == "pass_b" else B_ALG_PASS_A) * n
     if carry:
         dom, dom_bytes = "fused_pass", B_ALG_FUSED * n
-    if n == 16_000_000 and dom in tr:
+    if n == 16_000_000 and world == 1 and dom in tr:   # a capture of THIS kernel on THIS workload exists; null otherwise
         traffic = tr[dom]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     step_achieved = B_ALG_NEWTON * n * world / (ms * 1e-3 / args.steps) / 1e9
@@ -439,18 +577,52 @@ def run_ours(args):
         finally:
             s5.close()
 
+    def m_hot():
+        # the same box once the lattice has broken up: `hot_steps` more steps (dt = 0.001; the offset-0.4 lattice sits above
+        # the LJ minimum, so it is unstable and heats up), then the same timed region.  Re-binning traffic is O(movers):
+        # this is the step cost at a realistic mover rate; tile overflows on the way grow the tiles and rebuild.
+        w6 = lj_workload(pkg, nx, ny, cuda_device=mkdev(flags=args.flags))
+        s6 = pkg.System(state=pkg.SecondLawState(pos=w6["pos"], vel=w6["vel"]), space_cfg=w6["space"], dynamic_cfg=w6["dyn"], int_cfg=w6["int_cfg"])
+        try:
+            s6.step(args.hot_steps)
+            c0 = s6.counters()
+            k6 = args.steps
+            ms6 = timed_steps(s6, k6)
+            c1 = s6.counters()
+            ke, _ = s6.energies(want_pe=False)
+            return {"ms_per_step": ms6, "steps": k6, "value": n / (ms6 * 1e-3), "unit": "particle-steps/s", "steps_before": args.hot_steps,
+                    "rebinned_per_step": (c1["rebinned"] - c0["rebinned"]) / k6, "tiles_repaired_per_step": (c1["tiles_repaired"] - c0["tiles_repaired"]) / k6,
+                    "rebuilds_total": c1["rebuilds"], "tile_cap": c1["tile_cap"], "kinetic_energy_per_particle": ke / n,
+                    "roofline_step_frac": B_ALG_NEWTON * n / (ms6 * 1e-3) / 1e9 / peak,
+                    "what": f"same workload after {args.hot_steps} steps (lattice broken up), force carry + incremental repair"}
+        finally:
+            s6.close()
+
     slab_api_main = world > 1 or bool(args.flags & pkg.capi.FLAG_SLAB_SELF)
+    hot = side(m_hot) if (world == 1 and args.hot_steps > 0 and not slab_api_main) else None
+    if world == 1 and not args.no_probe and not slab_api_main:
+        probe = side(lambda: parity_probe_single(pkg, nx, ny, stream, local_rank, args.flags))
     two_pass = side(m_two_pass) if (world == 1 and carry and not args.no_two_pass and not slab_api_main) else None
     float32 = side(m_float32) if (world == 1 and not args.no_f32 and not slab_api_main) else None
     other = None
     if world == 1 and not args.no_other_configs and not slab_api_main:
         other = {"szabo_c3": side(m_szabo), "rings_c4": side(m_rings)}
     def m_cpu():
-        rate, secs, threads, sample = cpu_reference_rate(pkg, args.cpu_steps, 1, sample_n=args.cpu_sample)
-        out = {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample}
+        # the C restatement built -O3 -march=native -fopenmp, all host cores, at 1M and (memory permitting) at
+        # the metric's own 16M; `value` is the 16M figure when it ran.  Bounded: a few timed steps each.
+        cs = args.cpu_sample
+        rate, secs, threads, sample = cpu_reference_rate(pkg, args.cpu_steps, 1, nx=cs, ny=cs)
+        out = {"value": rate, "unit": "particle-steps/s", "cores": threads, "kind": "port", "sample": sample,
+               "n1m": {"value": rate, "sample": sample}}
+        if host_mem_available_gb() > 24.0 and not args.cpu_small:
+            r16, _, _, s16 = cpu_reference_rate(pkg, max(2, args.cpu_steps // 3), 1, nx=nx, ny=ny)
+            out.update({"value": r16, "sample": s16, "n16m": {"value": r16, "sample": s16}})
         # the reference's DEFAULT device is Sequencial (one thread, src/configs.jl:471-487): reported beside the Threaded figure
-        r1, _, _, s1 = cpu_reference_rate(pkg, max(2, args.cpu_steps // 3), 1, sample_n=max(100, args.cpu_sample // 2), threads=1)
+        r1, _, _, s1 = cpu_reference_rate(pkg, max(2, args.cpu_steps // 3), 1, nx=max(100, cs // 2), ny=max(100, cs // 2), threads=1)
         out["sequencial"] = {"value": r1, "cores": 1, "sample": s1}
+        # the parity oracle build (-O2 -ffp-contract=off) of the same source, for transparency about what -O3 buys
+        r2, _, _, s2 = cpu_reference_rate(pkg, max(2, args.cpu_steps // 3), 1, nx=cs, ny=cs, fast=False)
+        out["parity_build"] = {"value": r2, "sample": s2}
         return out
 
     cpu = side(m_cpu) if (world == 1 and not args.no_cpu_baseline) else None
@@ -458,9 +630,7 @@ def run_ours(args):
         "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"LJ lattice gas {nx}x{ny}={n} particles per GPU, periodic rectangle, {int(nx * 0.9)}x{int(ny * 0.9)} chunks, "
-                               f"f64, dt=0.001, newton_step!", "l2": "state arrays (>=1.5 GB) exceed the 126 MB L2; no flush needed",
-                   "parallelism": "single GPU" if world == 1 else f"{world} x-slabs of one {nx * world}x{ny} periodic box, NCCL halo+migration"},
+        "config": workload_config(nx, ny, world),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_kind": peak_kind, "kernel_ms": dom_ms,
                      "bytes_per_particle": dom_bytes / n,
@@ -476,6 +646,9 @@ def run_ours(args):
                      "step": {"achieved": step_achieved / world, "frac": step_achieved / world / peak, "bytes_per_particle_step": B_ALG_NEWTON},
                      "phase_ms": {"pass_a": phase_ms[1], "pass_b": phase_ms[2], "repair_exchange": phase_ms[3]}},
         "cpu_baseline": cpu,
+        "parity_probe": probe,
+        "rebinned_per_step": counters["rebinned"] / max(counters["steps"], 1),
+        "hot": hot,
         "two_pass": two_pass,
         "float32": float32,
         "other_configs": other,
@@ -504,6 +677,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1000, help="CPU baseline sample: an n x n lattice")
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-small", action="store_true", help="CPU legs: the 1M sample only (skip the 16M run)")
+    ap.add_argument("--no-probe", action="store_true", help="skip the parity probe")
+    ap.add_argument("--hot-steps", type=int, default=2000, help="steps before the `hot` side measurement (0 = skip)")
     ap.add_argument("--no-two-pass", action="store_true", help="skip the A/B run with the force carry switched off")
     ap.add_argument("--no-f32", action="store_true", help="skip the Float32-mode side measurement")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the Szabo (C3) and Rings (C4) side measurements")

@@ -140,7 +140,6 @@ typedef struct MaviParams {
 #define MAVI_FLAG_NO_FORCE_CARRY 4    /* Newton steps: always run the full first force pass instead of carrying F2 / the drift over from the previous step (A/B testing; results are bit-identical) */
 #define MAVI_FLAG_SMALL_BLOCKS 8      /* testing: 3 tile columns per CTA, so that block splitting, chunking and the slab overlap path run on small systems */
 #define MAVI_FLAG_SLAB_SELF 16        /* world == 1 only: run the x-slab machinery (halo columns, emigrant records, two-stream step pipeline) with this rank as its own periodic neighbour, device copies instead of NCCL; state moves through mavi_upload_local / mavi_download_local.  Lets the multi-GPU path be tested and profiled on one GPU */
-#define MAVI_FLAG_WARP_TILES 32       /* EXPERIMENTAL, default off, not yet validated on hardware: warp-private staging in the fused Newton force pass (k_newton_b2w, kernels.cu); results must be bit-identical to the default kernel */
 #define MAVI_FLAG_TIGHT_TILES 2       /* testing: tile capacity without slack, so that the overflow -> rebuild -> resume path is exercised */
 
 typedef struct MaviHandle MaviHandle;
@@ -176,7 +175,8 @@ int32_t mavi_upload_local(MaviHandle *h, const int64_t *ids, const void *pos, co
  *                      Rings step!  src/rings/integration.jl:522-543), chosen like get_step_function.
  * host_noise (MAVI_RNG_HOST_NOISE): per step  Szabo T[n] (randn, src/integration.jl:460) |
  *   RTP T[2n] (u, u2 pairs, src/integration.jl:493-495) | Rings T[num_rings] (randn, src/rings/integration.jl:348);
- *   may be NULL when the stochastic amplitude is zero or for Newton dynamics. */
+ *   may be NULL when the stochastic amplitude is zero or for Newton dynamics.  The row is indexed by the ORIGINAL
+ *   particle id: in x-slab mode n is MaviParams.n_global and every rank passes the same full global rows. */
 int32_t mavi_step(MaviHandle *h, int64_t nsteps, const void *host_noise);
 /* clean_forces! + update_chunks! + calc_forces! (+ Rings: springs, area forces) + calc_walls_forces!:
  * the force state a reference system holds right after these calls (src/integration.jl:508-511) */
@@ -235,6 +235,10 @@ int32_t mavi_rebuild_count(MaviHandle *h, int64_t *n);
  * ms[0]=bin+sort ms[1]=pass A ms[2]=pass B (or the single fused pass) ms[3]=exchange ms[4]=total */
 int32_t mavi_last_step_ms(MaviHandle *h, float *ms5);
 int32_t mavi_set_profiling(MaviHandle *h, int32_t on);
+/* totals since the last upload: out8[0] steps run, [1] particles re-binned (cell changes = what update_chunks! would move,
+ * src/chunks.jl:150-163), [2] inter-tile movers, [3] tiles repaired, [4] slab emigrants, [5] tile-overflow rebuilds,
+ * [6] tile capacity (slots), [7] number of tiles.  Synchronises. */
+int32_t mavi_counters(MaviHandle *h, int64_t *out8);
 
 #ifdef __cplusplus
 }

@@ -32,7 +32,6 @@ FLAG_TIGHT_TILES = 2
 FLAG_NO_FORCE_CARRY = 4
 FLAG_SMALL_BLOCKS = 8
 FLAG_SLAB_SELF = 16
-FLAG_WARP_TILES = 32  # experimental kernel variant, default off (include/mavi.h)
 NEIGH_OFF, NEIGH_COUNT, NEIGH_LIST = range(3)
 NEIGH_MAX = 15
 
@@ -111,6 +110,7 @@ SIGNATURES = {
     "mavi_rebuild_count": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
     "mavi_last_step_ms": (C.c_int32, [_H, C.POINTER(C.c_float)]),
     "mavi_set_profiling": (C.c_int32, [_H, C.c_int32]),
+    "mavi_counters": (C.c_int32, [_H, C.POINTER(C.c_int64)]),
 }
 
 

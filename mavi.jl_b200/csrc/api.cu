@@ -32,6 +32,8 @@ void Handle::set_error(const char *fmt, ...) {
 
 // largest x with fl(sqrt(x)) <= d  ->  (sqrt(r2) > d)  <=>  (r2 > x), exactly
 static real sqrt_le_threshold(real d) {
+  if (!(d > 0)) return d < 0 ? real(-1) : real(0);  // sqrt(r2) > d for every r2 > 0 (d = 0) or for every r2 at all (d < 0); NaN -> 0
+  if (std::isinf(d)) return d;                      // "no cutoff"
   real x = d * d;
   while (std::sqrt(x) <= d) x = std::nextafter(x, INFINITY);
   while (std::sqrt(x) > d) x = std::nextafter(x, -INFINITY);
@@ -39,6 +41,8 @@ static real sqrt_le_threshold(real d) {
 }
 // smallest x with fl(sqrt(x)) >= d  ->  (sqrt(r2) < d)  <=>  (r2 < x), exactly
 static real sqrt_ge_threshold(real d) {
+  if (!(d > 0)) return real(0);  // sqrt(r2) < d never holds
+  if (std::isinf(d)) return d;
   real x = d * d;
   while (std::sqrt(x) >= d && x > 0) x = std::nextafter(x, -INFINITY);
   while (std::sqrt(x) < d) x = std::nextafter(x, INFINITY);
@@ -712,6 +716,10 @@ int32_t api_download_forces(void *hh, void *forces) {
   cudaSetDevice(h->device);
   DevArrays &a = h->a;
   if (h->second_kind == SECOND_RING_POL) return rings_download_forces(h, forces);
+  if (h->p.slab) {
+    h->set_error("slab mode: use mavi_download_local (ids are global; this entry point un-permutes into a dense local array)");
+    return MAVI_ERR_BAD_PARAMS;
+  }
   launch_unpermute2(h->ctx(), h->p, a, a.force, a.st_force);
   CUDA_TRY(h, cudaMemcpyAsync(forces, a.st_force, (size_t)h->p.n * sizeof(real2), cudaMemcpyDeviceToHost, h->stream));
   return h->check_device_flags();
@@ -819,9 +827,12 @@ int32_t api_step(void *hh, int64_t nsteps, const void *host_noise) {
   const real *noise_dev = nullptr;
   size_t stride = 0;
   if (host_noise && h->p.rng_mode == MAVI_RNG_HOST_NOISE) {
+    // the kernels index the noise row with the ORIGINAL id: in slab mode that is the global id, so every rank passes the
+    // full global row (n_global entries per step), not one entry per owned particle
+    const size_t n_ids = h->p.slab ? (size_t)h->slab.n_global : (size_t)h->p.n;
     switch (h->p.dynamics) {
-      case MAVI_DYN_SZABO: stride = (size_t)h->p.n; break;
-      case MAVI_DYN_RTP: stride = 2 * (size_t)h->p.n; break;
+      case MAVI_DYN_SZABO: stride = n_ids; break;
+      case MAVI_DYN_RTP: stride = 2 * n_ids; break;
       case MAVI_DYN_RINGS: stride = (size_t)h->p.rings.num_rings; break;
       default: stride = 0;
     }
@@ -829,7 +840,8 @@ int32_t api_step(void *hh, int64_t nsteps, const void *host_noise) {
     if (total > 0) {
       if (total > h->noise_cap) {
         if (h->noise_dev) cudaFree(h->noise_dev);
-  if (h->id64_dev) cudaFree(h->id64_dev);
+        h->noise_dev = nullptr;
+        h->noise_cap = 0;
         CUDA_TRY(h, cudaMalloc((void **)&h->noise_dev, total * sizeof(real)));
         h->noise_cap = total;
       }
@@ -874,6 +886,10 @@ int32_t api_download_cells(void *hh, int32_t *cell_of_particle, int32_t *counts)
   cudaSetDevice(h->device);
   DevArrays &a = h->a;
   if (h->p.dynamics == MAVI_DYN_RINGS) return rings_download_cells(h, cell_of_particle, counts, nullptr, nullptr);
+  if (h->p.slab) {
+    h->set_error("slab mode: use mavi_download_local (ids are global; this entry point un-permutes into a dense local array)");
+    return MAVI_ERR_BAD_PARAMS;
+  }
   if (cell_of_particle) {
     launch_unpermute_cells(h->ctx(), h->p, a, a.st_cell);
     CUDA_TRY(h, cudaMemcpyAsync(cell_of_particle, a.st_cell, (size_t)h->p.n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -891,6 +907,10 @@ int32_t api_download_cell_lists(void *hh, int32_t *start, int32_t *ids) {
   cudaSetDevice(h->device);
   DevArrays &a = h->a;
   if (h->p.dynamics == MAVI_DYN_RINGS) return rings_download_cells(h, nullptr, nullptr, start, ids);
+  if (h->p.slab) {
+    h->set_error("slab mode: use mavi_download_local (ids are global; this entry point un-permutes into a dense local array)");
+    return MAVI_ERR_BAD_PARAMS;
+  }
   if (start) {
     std::vector<int> counts((size_t)h->p.num_cells);
     launch_cell_counts(h->ctx(), h->p, a, a.perm);
@@ -943,6 +963,10 @@ int32_t api_energies(void *hh, int32_t pe_mode, double *ke, double *pe) {
   LaunchCtx c = h->ctx();
   double *out = a.reduce_buf + 2048;
   double host[2] = {NAN, NAN};
+  if (h->p.slab && pe && pe_mode == 0) {
+    h->set_error("slab mode: the exact O(N^2) potential energy is single-GPU only (SURVEY.md 8e); use pe_mode 1");
+    return MAVI_ERR_BAD_PARAMS;
+  }
   if (ke && h->second_kind == SECOND_VEL) {
     launch_kinetic_energy(c, h->p, a, out);
     CUDA_TRY(h, cudaMemcpyAsync(&host[0], out, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1018,6 +1042,27 @@ int32_t api_rebuild_count(void *hh, int64_t *n) {
   if (!h || !n) return MAVI_ERR_BAD_PARAMS;
   *n = h->n_rebuilds;
   return MAVI_OK;
+}
+
+// instrumentation: out[0] = steps run since the last upload, [1] = particles re-binned (cell changes), [2] = inter-tile
+// movers, [3] = tiles repaired, [4] = emigrants (slab mode), [5] = tile-overflow rebuilds, [6] = tile capacity, [7] = tiles
+int32_t api_counters(void *hh, int64_t *out8) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || !out8) return MAVI_ERR_BAD_PARAMS;
+  cudaSetDevice(h->device);
+  if (h->p.slab) slab_join(h);
+  int st = h->check_device_flags();
+  const int *f = h->flags_host;
+  // the totals are folded in by the NEXT step's first kernel: add the words of the last step that ran
+  out8[0] = f[FLAG_STEPS];
+  out8[1] = (int64_t)f[FLAG_CUM_CHG] + f[FLAG_NMOVED];
+  out8[2] = (int64_t)f[FLAG_CUM_MV] + f[FLAG_NMV];
+  out8[3] = (int64_t)f[FLAG_CUM_DIRTY] + f[FLAG_CHANGED];
+  out8[4] = (int64_t)f[FLAG_CUM_EM] + f[FLAG_NEM0] + f[FLAG_NEM1];
+  out8[5] = h->n_rebuilds;
+  out8[6] = h->p.cap;
+  out8[7] = h->p.nt;
+  return st;
 }
 
 int32_t api_set_profiling(void *hh, int32_t on) {

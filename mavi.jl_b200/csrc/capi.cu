@@ -92,5 +92,6 @@ int32_t mavi_launch_count(MaviHandle *h, int64_t *n) { MAVI_FWD(h, api_launch_co
 int32_t mavi_rebuild_count(MaviHandle *h, int64_t *n) { MAVI_FWD(h, api_rebuild_count(impl, n)); }
 int32_t mavi_last_step_ms(MaviHandle *h, float *ms5) { MAVI_FWD(h, api_last_step_ms(impl, ms5)); }
 int32_t mavi_set_profiling(MaviHandle *h, int32_t on) { MAVI_FWD(h, api_set_profiling(impl, on)); }
+int32_t mavi_counters(MaviHandle *h, int64_t *out8) { MAVI_FWD(h, api_counters(impl, out8)); }
 
 }  // extern "C"

@@ -110,6 +110,9 @@ enum {
   FLAG_NCHG = 16, FLAG_BIGMOVE_NEXT = 17,
   // slab mode: emigrants of this step towards the left / right neighbour, and the counts received from them
   FLAG_NEM0 = 18, FLAG_NEM1 = 19, FLAG_NEMR0 = 20, FLAG_NEMR1 = 21,
+  // instrumentation (mavi_counters): changed-cell records and inter-tile movers summed over the steps since the last upload
+  FLAG_CUM_CHG = 22, FLAG_CUM_MV = 23, FLAG_CUM_DIRTY = 13, FLAG_CUM_EM = 14,
+  FLAG_NMOVED = 15,  // per step: particles whose cell changed (re-binned by the incremental repair)
   FLAG_COUNT = 24
 };
 

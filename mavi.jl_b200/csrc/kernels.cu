@@ -593,6 +593,7 @@ __device__ __noinline__ void note_moved_slow(const DevParams &p, const MoverSink
     return;
   }
   note_changed_cells(p, ms, c_old, c_new);
+  atomicAdd(&ms.flags[FLAG_NMOVED], 1);
   ms.cell[k] = c_new;
   const int t_old = tile_of_cell(p, c_old), t_new = tile_of_cell(p, c_new);
   mark_dirty(ms, t_old);
@@ -877,6 +878,12 @@ __global__ void k_recompute_columns(const __grid_constant__ DevParams p, int *__
 __global__ void k_step_begin(int *__restrict__ flags) {
   if (threadIdx.x == 0) {
     const int run = step_poisoned(flags) ? 0 : 1;
+    // instrumentation: totals of the previous step (wrap-around after 2^31 records is harmless, the host takes differences)
+    flags[FLAG_CUM_CHG] += flags[FLAG_NMOVED];
+    flags[FLAG_NMOVED] = 0;
+    flags[FLAG_CUM_MV] += flags[FLAG_NMV];
+    flags[FLAG_CUM_DIRTY] += flags[FLAG_CHANGED];
+    flags[FLAG_CUM_EM] += flags[FLAG_NEM0] + flags[FLAG_NEM1];
     flags[FLAG_CHANGED] = 0;
     flags[FLAG_BIGMOVE] = flags[FLAG_BIGMOVE_NEXT];  // raised by the carried drift of the previous step
     flags[FLAG_BIGMOVE_NEXT] = 0;
@@ -1213,7 +1220,7 @@ __global__ void __launch_bounds__(TPB) k_newton_a2(const __grid_constant__ DevPa
     });
 }
 
-// pre(k) / body(k, r, cell, active, F) of the second Newton pass (shared by the CTA-tile and the warp-tile kernels)
+// pre(k) / body(k, r, cell, active, F) of the second Newton pass
 #define MAVI_NEWTON_B_LAMBDAS \
     [&](int k) { prefetch_l1(vel + k); prefetch_l1(f1 + k); }, \
     [&](int k, real2 r, int c, bool active, real2 F) { \
@@ -1255,210 +1262,6 @@ __global__ void __launch_bounds__(TPB, MINB) k_newton_b2(const __grid_constant__
   // without a big-drift report -> always the exact minimum-image path there
   const bool exact = ms.flags[FLAG_BIGMOVE] != 0 || (p.slab && p.blk_mode == 2);
   for_each_block_particle<DYN, PER>(p, tstart, pos_in, ms.cell, exact, MAVI_NEWTON_B_LAMBDAS);
-}
-
-// =========================================================================================================
-// EXPERIMENTAL — warp-private tiles (MAVI_FLAG_WARP_TILES; default OFF; written at the end of round 1 without GPU time
-// left, so it has NOT run on hardware yet: tests/test_gpu_core.py::test_warp_tiles_agree is its acceptance test).
-// Motivation (profiles/r01_ncu_newton_summary.md, r1m): in the CTA-tile kernel 16 % of the warp-stall samples sit on
-// the three __syncthreads() of chunk_stage and 12 % on the dependent loads of its prologue.  Here every WARP stages its
-// own run of WC columns (+ one side column each way) of one tile row into a private slice of shared memory and only
-// ever executes __syncwarp(): no CTA barrier, the 32 resident warps of an SM drift apart and hide each other's staging
-// latency.  Costs: (WC + 2) / WC staged positions per own position instead of ~1.08 (served by L1 / L2, neighbouring
-// warps of a CTA stage adjacent runs), and the per-column staging work is done by one warp for WC + 2 columns.
-// Same neighbour order and arithmetic as chunk_walk -> results must be bit-identical to the default kernel.
-// Not for slab mode (the blk_mode split of the halo overlap is not implemented here).
-// =========================================================================================================
-constexpr int WC = 3;            // own columns per warp tile
-constexpr int WJ = WC + 2;       // staged columns
-constexpr int WPOS_CAP = 256;    // staged positions per warp (mean 5 x 42 = 210 at 1.23 particles per cell)
-constexpr int WOWN_CAP = 160;    // own particles per warp (mean 3 x 39 = 118)
-
-struct WChunk {
-  int nc, use_mi, nown, ok;
-  int wr[WJ], src_a[WJ], src_t[WJ], src_b[WJ], la[WJ], lt[WJ], lb[WJ];
-  int off[WJ + 1], ownoff[WJ + 1], gbase[WJ];
-  int2 cwin[WJ][MAVI_TR];  // [j][lr-1]
-};
-constexpr int WCH_BYTES = (sizeof(WChunk) + 15) / 16 * 16;
-constexpr int WARP_SMEM = (WCH_BYTES + WPOS_CAP * (int)sizeof(real2) + WOWN_CAP * (int)sizeof(unsigned int) + 15) / 16 * 16;
-constexpr int PASSW_SMEM = (TPB / 32) * WARP_SMEM;
-
-// chunk_stage for ONE warp: stage own columns cs .. cs+nc-1 (nc <= min(rem, WC) as many as fit) of tile row tr.
-template <bool PER>
-__device__ __forceinline__ void warp_stage(const DevParams &p, const int *__restrict__ tstart,
-                                           const real2 *__restrict__ pos, int tr, int cs, int rem, bool exact_minimg,
-                                           WChunk *ck, real2 *s_pos, unsigned int *s_list) {
-  const int lane = threadIdx.x & 31;
-  const int R = p.num_rows, Cn = p.num_cols;
-  const int r0 = tr * MAVI_TR;
-  const int rows = min(MAVI_TR, R - r0);
-  const int ncand = min(rem, WC);
-  __syncwarp();  // previous chunk fully consumed by every lane
-  // ---- column descriptors: lane j < ncand + 2 describes staged column j (registers; written to shared memory below)
-  const int j = lane;
-  const bool in = j < ncand + 2;
-  int la = 0, lt = 0, lb = 0, sa = 0, st = 0, sb = 0;
-  bool wrapped = false;
-  if (in) {
-    int c = cs - 1 + j;
-    bool exists = true;
-    if (c < 0) { if (p.wrap_cols) { c = Cn - 1; wrapped = true; } else exists = false; }
-    else if (c >= Cn) { if (p.wrap_cols) { c = 0; wrapped = true; } else exists = false; }
-    int ra = r0 - 1, rb = r0 + MAVI_TR;
-    bool has_a = exists, has_b = exists;
-    if (ra < 0) { if (p.wrap_rows) { ra = R - 1; wrapped = wrapped || exists; } else has_a = false; }
-    if (rb >= R) { if (p.wrap_rows) { rb = 0; wrapped = wrapped || exists; } else has_b = false; }
-    if (exists) {
-      const int *tt = tstart + (size_t)(c * p.tpc + tr) * (MAVI_TR + 1);
-      const int qa = has_a ? tq_of(p, c, ra) : 0, qb = has_b ? tq_of(p, c, rb) : 0;
-      st = __ldg(tt);
-      const int et = __ldg(tt + MAVI_TR);
-      const int a0 = has_a ? __ldg(tstart + qa) : 0, a1 = has_a ? __ldg(tstart + qa + 1) : 0;
-      const int b0 = has_b ? __ldg(tstart + qb) : 0, b1 = has_b ? __ldg(tstart + qb + 1) : 0;
-      lt = et - st; sa = a0; la = a1 - a0; sb = b0; lb = b1 - b0;
-    }
-  }
-  // ---- prefix sums over the lanes, greedy number of own columns that fit
-  const int sz = in ? la + lt + lb : 0;
-  const int own = (in && j >= 1 && j <= ncand) ? lt : 0;
-  int incl = sz, oincl = own;
-#pragma unroll
-  for (int o = 1; o < 8; o <<= 1) {  // WJ <= 8 lanes carry data
-    const int v = __shfl_up_sync(0xffffffffu, incl, o), u = __shfl_up_sync(0xffffffffu, oincl, o);
-    if (lane >= o) { incl += v; oincl += u; }
-  }
-  const int incl_next = __shfl_down_sync(0xffffffffu, incl, 1);  // staged total if this lane were the last own column
-  const bool fits = j >= 1 && j <= ncand && incl_next <= WPOS_CAP && oincl <= WOWN_CAP;
-  const unsigned int bal = __ballot_sync(0xffffffffu, fits);
-  const int nc = bal ? 31 - __clz(bal) : 1;  // fits is monotone in j
-  const unsigned int wbal = __ballot_sync(0xffffffffu, in && j <= nc + 1 && wrapped);
-  if (in) {
-    ck->src_t[j] = st; ck->src_a[j] = sa; ck->src_b[j] = sb;
-    ck->la[j] = la; ck->lt[j] = lt; ck->lb[j] = lb;
-    ck->wr[j] = wrapped ? 1 : 0;
-    ck->off[j] = incl - sz;
-    ck->ownoff[j] = oincl - own;
-  }
-  if (lane == 0) {
-    ck->nc = nc;
-    ck->ok = bal ? 1 : 0;
-    ck->use_mi = (PER && (exact_minimg || !p.fast_interior || wbal)) ? 1 : 0;
-  }
-  if (j == nc) ck->nown = oincl;
-  __syncwarp();
-  if (!bal) return;  // warp-uniform
-  // ---- copy, cell-row windows and the own-particle list: the whole warp, one staged column after the other
-  for (int jj = 0; jj < nc + 2; jj++) {
-    const int off = ck->off[jj], cla = ck->la[jj], clt = ck->lt[jj], clb = ck->lb[jj];
-    const int src_t = ck->src_t[jj], src_a = ck->src_a[jj], src_b = ck->src_b[jj];
-    const int tot = cla + clt + clb;
-    int cj = cs - 1 + jj;
-    if (cj < 0) cj = Cn - 1;
-    else if (cj >= Cn) cj = 0;
-    const int *tt = tstart + (size_t)(cj * p.tpc + tr) * (MAVI_TR + 1);
-    // staged start of tile row lane+1 (rows beyond the grid start where the tile ends)
-    const int tsl = tot ? __ldg(tt + lane) - src_t : 0, tsn = tot ? __ldg(tt + lane + 1) - src_t : 0;
-    const int rs = off + cla + tsl;
-    const int up = __shfl_up_sync(0xffffffffu, rs, 1), dn = __shfl_down_sync(0xffffffffu, rs, 2);
-    const int end = off + tot;
-    const int wa = lane == 0 ? off : up;                                                // start of row lr-1
-    const int wb = (lane + 3 >= rows + 2) ? end : (lane <= 29 ? dn : off + cla + clt);  // start of row lr+2
-    ck->cwin[jj][lane] = make_int2(wa, wb);
-    if (lane == 0) ck->gbase[jj] = src_t - (off + cla);
-    if (jj >= 1 && jj <= nc && lane < rows) {
-      const int qb = ck->ownoff[jj];
-      for (int i = tsl; i < tsn; i++)
-        s_list[qb + i] = (unsigned int)(off + cla + i) | ((unsigned int)jj << 16) | ((unsigned int)(lane + 1) << 24);
-    }
-    for (int i = lane; i < tot; i += 32) {
-      const int src = i < cla ? src_a + i : (i < cla + clt ? src_t + (i - cla) : src_b + (i - cla - clt));
-      __pipeline_memcpy_async(s_pos + off + i, pos + src, sizeof(real2));
-    }
-  }
-  __pipeline_commit();
-  __pipeline_wait_prior(0);
-  __syncwarp();
-}
-
-// for_each_block_particle with warp-private tiles: CTA b of tile row tr holds 8 warps, warp w owns columns
-// [ord_col0 + (b*8 + w) * WC, + WC).  Trailing blocks handle the inactive tail.
-template <int DYN, bool PER, typename Pre, typename Body>
-__device__ __forceinline__ void for_each_warp_particle(const DevParams &p, const int *__restrict__ tstart,
-                                                       const real2 *__restrict__ pos, const int *__restrict__ cell,
-                                                       bool exact_minimg, Pre &&pre, Body &&body) {
-  extern __shared__ __align__(16) unsigned char dsm[];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  unsigned char *mine = dsm + (size_t)w * WARP_SMEM;
-  WChunk *ck = reinterpret_cast<WChunk *>(mine);
-  real2 *s_pos = reinterpret_cast<real2 *>(mine + WCH_BYTES);
-  unsigned int *s_list = reinterpret_cast<unsigned int *>(mine + WCH_BYTES + WPOS_CAP * sizeof(real2));
-  const int groups = (p.ord_cols + WC - 1) / WC;           // warp tiles per tile row
-  const int per_row = (groups + TPB / 32 - 1) / (TPB / 32);  // CTAs per tile row
-  const int nblk_tiles = per_row * p.tpc;
-  if ((int)blockIdx.x >= nblk_tiles) {  // inactive tail: no pair forces
-    const int i = ((int)blockIdx.x - nblk_tiles) * TPB + threadIdx.x;
-    if (i < p.n - p.n_active) {
-      const int k = p.tail_base + i;
-      pre(k);
-      body(k, pos[k], 0, false, make_real2(0.0, 0.0));
-    }
-    return;
-  }
-  const int tr = (int)blockIdx.x / per_row;
-  const int g = ((int)blockIdx.x - tr * per_row) * (TPB / 32) + w;
-  if (g >= groups) return;  // whole warp
-  const int c_begin = p.ord_col0 + g * WC;
-  const int c_end = min(c_begin + WC, p.ord_col0 + p.ord_cols);
-  const int r0 = tr * MAVI_TR;
-  for (int cs = c_begin; cs < c_end;) {
-    warp_stage<PER>(p, tstart, pos, tr, cs, c_end - cs, exact_minimg, ck, s_pos, s_list);
-    const int nc = ck->nc;
-    if (ck->ok) {
-      const int nown = ck->nown;
-      const bool mi = PER && ck->use_mi;
-      for (int q = lane; q < nown; q += 32) {
-        const unsigned int u = s_list[q];
-        const int self = u & 0xffffu, jj = (u >> 16) & 0xffu, lr = u >> 24;
-        const int k = self + ck->gbase[jj];
-        pre(k);
-        const real2 r = s_pos[self];
-        real fx = 0.0, fy = 0.0;
-        if (mi) chunk_walk<DYN, true>(p, ck, s_pos, jj, lr, self, r, fx, fy);
-        else chunk_walk<DYN, false>(p, ck, s_pos, jj, lr, self, r, fx, fy);
-        body(k, r, (cs - 1 + jj) * p.num_rows + r0 + lr - 1, true, make_real2(fx, fy));
-      }
-    } else {
-      // a single column too dense for the warp's staging area: per-lane walk over the global arrays
-      const int b = ck->src_t[1], e = b + ck->lt[1];
-      for (int k = b + lane; k < e; k += 32) {
-        pre(k);
-        const real2 r = pos[k];
-        const int c = cell[k];
-        real fx = 0.0, fy = 0.0;
-        for_each_neighbor(p, tstart, c, k, [&](int jn) { accumulate_pair<DYN, PER>(p, r, __ldg(pos + jn), fx, fy); });
-        body(k, r, c, true, make_real2(fx, fy));
-      }
-    }
-    cs += nc;
-  }
-}
-
-static inline int gridw(const DevParams &p) {
-  const int groups = (p.ord_cols + WC - 1) / WC;
-  const int per_row = (groups + TPB / 32 - 1) / (TPB / 32);
-  return per_row * p.tpc + nblk(p.n - p.n_active);
-}
-
-template <int DYN, bool PER, bool CARRY>
-__global__ void __launch_bounds__(TPB, 4) k_newton_b2w(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
-                            const real2 *__restrict__ pos_in, real2 *__restrict__ vel, const real2 *f1,
-                            real2 *f2, real2 *f1_next, real2 *__restrict__ pos_next,
-                            int *__restrict__ fix_idx, real2 *__restrict__ fix_pos,
-                            const __grid_constant__ MoverSink ms) {
-  if (!ms.flags[FLAG_RAN]) return;
-  const bool exact = ms.flags[FLAG_BIGMOVE] != 0;
-  for_each_warp_particle<DYN, PER>(p, tstart, pos_in, ms.cell, exact, MAVI_NEWTON_B_LAMBDAS);
 }
 
 template <int DYN, bool PER>
@@ -1549,20 +1352,7 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p_in, const DevArrays 
 #define ARGS2 p, a.tstart, a.pos[1], a.vel, a.force_old, a.force, a.force_old, a.pos[0], a.fix_idx, a.fix_pos, ms
 #define CALL2(D, P) MAVI_LAUNCH(c, (k_newton_b2<D, P, false, 4>), grid2(p), TPB, PASS2_SMEM, ARGS2)
 #define CALL2C(D, P) MAVI_LAUNCH(c, (k_newton_b2<D, P, true, 4>), grid2(p), TPB, PASS2_SMEM, ARGS2)
-    if (carry && (c.flags & MAVI_FLAG_WARP_TILES) && !p.slab && blk_mode == 0) {  // experimental, see k_newton_b2w
-      ms.chg = a.chg;
-      // more than the 48 KB a kernel gets by default: opt in once per instantiation
-#define CALLW(D, P)                                                                                               \
-  do {                                                                                                            \
-    static const cudaError_t attr_ = cudaFuncSetAttribute((const void *)k_newton_b2w<D, P, true>,                 \
-                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, PASSW_SMEM); \
-    (void)attr_;                                                                                                  \
-    MAVI_LAUNCH(c, (k_newton_b2w<D, P, true>), gridw(p), TPB, PASSW_SMEM, ARGS2);                                 \
-  } while (0)
-      if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALLW);
-      else MAVI_DISPATCH2(MAVI_DYN_HARMTRUNC, p.periodic, CALLW);
-#undef CALLW
-    } else if (carry) {
+    if (carry) {
       ms.chg = a.chg;
       if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALL2C);
       else MAVI_DISPATCH2(MAVI_DYN_HARMTRUNC, p.periodic, CALL2C);

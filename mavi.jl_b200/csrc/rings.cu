@@ -301,12 +301,16 @@ static int upr(Handle *h, const real **dst, const double *src, size_t n) {
 }
 
 static real sqrt_le_thr(real d) {
+  if (!(d > 0)) return d < 0 ? real(-1) : real(0);
+  if (std::isinf(d)) return d;  // "no cutoff"
   real x = d * d;
   while (std::sqrt(x) <= d) x = std::nextafter(x, INFINITY);
   while (std::sqrt(x) > d) x = std::nextafter(x, -INFINITY);
   return x;
 }
 static real sqrt_ge_thr(real d) {
+  if (!(d > 0)) return real(0);
+  if (std::isinf(d)) return d;
   real x = d * d;
   while (std::sqrt(x) >= d && x > 0) x = std::nextafter(x, -INFINITY);
   while (std::sqrt(x) < d) x = std::nextafter(x, INFINITY);

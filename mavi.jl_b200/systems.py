@@ -162,12 +162,25 @@ class System:
     def step(self, nsteps=1, host_noise=None):
         """nsteps x the step function `get_step_function(system)` selects (src/integration.jl:537-548)."""
         noise = None if host_noise is None else np.ascontiguousarray(host_noise, dtype=self._dtype)
+        if noise is not None:
+            need = self.noise_stride() * int(nsteps)
+            if noise.size < need:
+                raise ValueError(f"host_noise has {noise.size} entries, mavi_step reads {need} "
+                                 f"({self.noise_stride()} per step x {nsteps} steps)")
         self._check(self._lib.mavi_step(self._h, nsteps, _ptr(noise)))
         # time_info advances on the host exactly like update_time! (time += dt per step, Float64)
         dt = float(self.int_cfg.dt)
         for _ in range(nsteps):
             self.time_info.time += dt
             self.time_info.num_steps += 1
+
+    def noise_stride(self):
+        """Host-noise entries mavi_step reads per step (include/mavi.h): Szabo n, RTP 2n, Rings num_rings; in slab mode n
+        is the GLOBAL particle count (the kernels index the row with the original id)."""
+        p = self._lowered.params
+        n = int(p.n_global) if (self._slab and p.n_global > 0) else self._n
+        return {capi.DYN_SZABO: n, capi.DYN_RTP: 2 * n,
+                capi.DYN_RINGS: getattr(self.state, "num_rings", 0)}.get(p.dynamics, 0)
 
     def calc_forces(self):
         self._check(self._lib.mavi_calc_forces(self._h))
@@ -223,6 +236,14 @@ class System:
         n = C.c_int64()
         self._check(self._lib.mavi_rebuild_count(self._h, C.byref(n)))
         return n.value
+
+    def counters(self):
+        """Totals since the last upload (mavi_counters): steps, rebinned particles, inter-tile movers, repaired tiles,
+        slab emigrants, overflow rebuilds, tile capacity, tiles."""
+        out = (C.c_int64 * 8)()
+        self._check(self._lib.mavi_counters(self._h, out))
+        keys = ("steps", "rebinned", "tile_movers", "tiles_repaired", "emigrants", "rebuilds", "tile_cap", "tiles")
+        return dict(zip(keys, (int(v) for v in out)))
 
     def set_profiling(self, on=True):
         self._check(self._lib.mavi_set_profiling(self._h, int(on)))

@@ -14,6 +14,37 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmavi_oracle.so")
 _lib = None
+_fast_lib = None
+
+
+def _cpu_signature():
+    """Short hash of this host's CPU model + ISA flags: the -march=native build below is only valid on the CPU it was
+    compiled on (the GPU box differs from the build container), so the file name carries it."""
+    import hashlib
+    try:
+        txt = open("/proc/cpuinfo").read()
+        keep = [l for l in txt.splitlines() if l.startswith(("model name", "flags"))][:2]
+    except OSError:
+        keep = []
+    return hashlib.md5("\n".join(keep).encode()).hexdigest()[:10]
+
+
+def fast_lib_path():
+    return os.path.join(_HERE, f"libmavi_oracle_fast_{_cpu_signature()}.so")
+
+
+def build_fast(verbose=False):
+    """The TIMING build of the same source (`-O3 -march=native -fopenmp`), a separate target from the
+    parity oracle (`-O2 -ffp-contract=off`): used by bench.py's cpu_baseline / --impl reference legs only."""
+    path = fast_lib_path()
+    if os.path.exists(path):
+        return path
+    res = subprocess.run(["make", "-C", _HERE, "fast", f"FAST_SO={os.path.basename(path)}"], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-3000:], res.stderr[-3000:])
+    if res.returncode != 0:
+        raise RuntimeError("building the -O3 -march=native oracle failed")
+    return path
 
 
 def build(verbose=False):
@@ -25,13 +56,18 @@ def build(verbose=False):
     return LIB_PATH
 
 
-def load():
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        build()
-    lib = C.CDLL(LIB_PATH)
+def load(fast=False):
+    global _lib, _fast_lib
+    if fast:
+        if _fast_lib is not None:
+            return _fast_lib
+        lib = C.CDLL(build_fast())
+    else:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            build()
+        lib = C.CDLL(LIB_PATH)
     H, vp, i32, i64, dbl = C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_double
     sig = {
         "mor_create": (i32, [vp, C.POINTER(H)]), "mor_destroy": (None, [H]), "mor_set_threads": (None, [H, i32]),
@@ -53,7 +89,10 @@ def load():
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    _lib = lib
+    if fast:
+        _fast_lib = lib
+    else:
+        _lib = lib
     return lib
 
 
@@ -70,8 +109,8 @@ class OracleError(RuntimeError):
 class OracleSystem:
     """The oracle behind the same surface as the host mirror's `System` (built from the same configs)."""
 
-    def __init__(self, *, state, space_cfg, dynamic_cfg, int_cfg, lower, threads=1, p_neighbors_cfg=None):
-        self.lib = load()
+    def __init__(self, *, state, space_cfg, dynamic_cfg, int_cfg, lower, threads=1, p_neighbors_cfg=None, fast=False):
+        self.lib = load(fast=fast)  # fast: the -O3 -march=native timing build (never used for parity checks)
         self.state = state
         self._lowered = lower(state, space_cfg, dynamic_cfg, int_cfg)
         self.n = len(state.pos)

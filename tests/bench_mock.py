@@ -32,6 +32,10 @@ class FakeSystem:
     def set_profiling(self, on): pass
     def launch_count(self): return self.n_launch
     def last_step_ms(self): return [0.0, 0.003, 0.58, 0.07, 0.66]
+    def counters(self): return dict(steps=self.n_launch // 8, rebinned=10 * self.n_launch, tile_movers=1, tiles_repaired=2, emigrants=0, rebuilds=0, tile_cap=96, tiles=12)
+    def energies(self, pe_mode=0, want_ke=True, want_pe=True): return 1.0, None
+    def get_forces(self): return np.zeros((self._n, 2))
+    def download_cells(self): return np.zeros(self._n, dtype=np.int32), np.zeros(4, dtype=np.int32)
     def sync_to_host(self): return self
     def upload_state(self): pass
     def upload_local(self): pass
@@ -44,7 +48,7 @@ rr.System = FakeSystem
 pkg.load_library = lambda: None
 bench.entry.load_package = lambda: pkg
 
-for argv in (["--nx", "60", "--ny", "50", "--steps", "20", "--cpu-sample", "40", "--cpu-steps", "2"],
+for argv in (["--nx", "60", "--ny", "50", "--steps", "20", "--cpu-sample", "40", "--cpu-steps", "2", "--no-probe", "--hot-steps", "7"],
              ["--nx", "60", "--ny", "50", "--steps", "20", "--flags", "16", "--no-cpu-baseline"],
              ["--nx", "60", "--ny", "50", "--steps", "20", "--flags", "4", "--no-cpu-baseline", "--no-other-configs"]):
     sys.argv = ["bench.py"] + argv
@@ -54,8 +58,8 @@ for argv in (["--nx", "60", "--ny", "50", "--steps", "20", "--cpu-sample", "40",
     out = [l for l in buf.getvalue().splitlines() if l.startswith("{")]
     assert len(out) == 1, buf.getvalue()
     d = json.loads(out[0])
-    print(argv[-3:], "keys ok:", all(k in d for k in ("metric","value","roofline","cpu_baseline","e2e","gpu_launches","clocks","two_pass","float32","other_configs")))
-    for k in ("cpu_baseline", "two_pass", "float32", "other_configs"):
+    print(argv[-3:], "keys ok:", all(k in d for k in ("metric","value","roofline","cpu_baseline","e2e","gpu_launches","clocks","two_pass","float32","other_configs","parity_probe","hot","rebinned_per_step")))
+    for k in ("cpu_baseline", "two_pass", "float32", "other_configs", "hot"):
         v = d[k]
         if isinstance(v, dict) and ("error" in v or any(isinstance(x, dict) and "error" in x for x in v.values())):
             print("  SIDE ERROR in", k, v)

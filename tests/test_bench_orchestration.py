@@ -16,10 +16,13 @@ def test_bench_line_is_produced_for_the_main_flag_combinations():
 def test_reference_arm_prints_one_json_line():
     import json
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
-                          "--cpu-sample", "120"], capture_output=True, text=True, timeout=600)
+                          "--cpu-sample", "120", "--cpu-small"], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # both arms describe the same workload with the same `config` (the driver compares them)
+    import bench
+    assert d["config"] == bench.workload_config(4000, 4000, 1)

@@ -414,45 +414,6 @@ def test_small_blocks_agree(cuda_lib, dyn, wall):
     assert np.array_equal(a.get_forces(), b.get_forces())
 
 
-@pytest.mark.skipif(not os.environ.get("MAVI_TEST_EXPERIMENTAL"),
-                    reason="MAVI_FLAG_WARP_TILES (k_newton_b2w) was written after the round-1 GPU budget ran out and has "
-                           "not run on hardware yet; set MAVI_TEST_EXPERIMENTAL=1 to run its acceptance test")
-@pytest.mark.parametrize("kind", ["lj_periodic_hot", "harm_rigid", "force_walls", "masked", "lj_small_grid"])
-def test_warp_tiles_agree(cuda_lib, kind):
-    """Experimental warp-private staging of the fused Newton pass: must be BIT-identical to the default CTA-tile kernel
-    (same neighbour order, same arithmetic), through re-binning, wall fix-ups, masks and calc_forces! calls."""
-    if kind == "lj_periodic_hot":
-        case = H.newton_case(nx=70, ny=66, wall="periodic", jitter=0.3, vmax=3.0, dt=0.002)
-    elif kind == "harm_rigid":
-        case = H.newton_case(nx=40, ny=40, dyn=DYNS["harm"], wall="rigid", jitter=0.3, vmax=3.0, dt=0.002)
-    elif kind == "force_walls":
-        case = _wall_force_case(False)
-    elif kind == "masked":
-        mask = np.ones(32 * 32, dtype=bool)
-        mask[::5] = False
-        case = H.newton_case(nx=32, ny=32, dyn=DYNS["harm"], wall="periodic", jitter=0.3, vmax=2.0, dt=0.002, active_mask=mask)
-    else:  # fewer columns than one warp tile, 2-row periodic wrap
-        case = H.newton_case(nx=6, ny=6, wall="periodic", jitter=0.3, vmax=1.0, dt=0.002, cells=(2, 2))
-    a = H.make_gpu(_with_flags(case, 0))
-    b = H.make_gpu(_with_flags(case, pkg.capi.FLAG_WARP_TILES))
-    for n in (1, 2, 37, 120):
-        a.step(n)
-        b.step(n)
-        a.sync_to_host()
-        b.sync_to_host()
-        assert np.array_equal(a.state.pos, b.state.pos)
-        assert np.array_equal(a.state.vel, b.state.vel)
-        assert np.array_equal(a.get_forces(), b.get_forces())
-    a.calc_forces()
-    b.calc_forces()
-    a.step(40)
-    b.step(40)
-    a.sync_to_host()
-    b.sync_to_host()
-    assert np.array_equal(a.state.pos, b.state.pos) and np.array_equal(a.get_forces(), b.get_forces())
-    assert np.array_equal(a.download_cells()[0], b.download_cells()[0])
-
-
 def test_kernels_actually_launch(cuda_lib):
     g = H.make_gpu(H.newton_case(nx=16, ny=16))
     n0 = g.launch_count()
