@@ -121,14 +121,19 @@ typedef struct MaviParams {
   double dt; /* IntCfg.dt */
 
   int32_t rng_mode; /* MAVI_RNG_* */
-  int32_t _pad2;
+  int32_t n_gpus;   /* 0 / 1: one GPU (MaviParams.device).  G > 1: ONE process drives G GPUs (devices device .. device+G-1)
+                     * through this one handle — the reference's driver is a single process (src/run_system.jl:7-23,
+                     * src/systems.jl:73-114): the library partitions the state into x-slabs of cell columns on
+                     * mavi_upload_state, steps all slabs concurrently (halo / migration over NCCL, NVLink) and un-permutes
+                     * on download.  Needs a single periodic rectangle with chunks; not Mavi.Rings; stream must be NULL. */
   uint64_t seed;
 
   int32_t device; /* CUDA device ordinal */
   int32_t flags;  /* MAVI_FLAG_* */
   void *stream;   /* cudaStream_t to enqueue on, or NULL for the legacy default stream */
 
-  /* x-slab domain decomposition, one process per GPU.  world<=1 -> single GPU. */
+  /* x-slab domain decomposition with ONE PROCESS PER GPU (torchrun-style launchers; exclusive with n_gpus > 1).
+   * world<=1 -> not used. */
   int32_t rank;
   int32_t world;
   const void *nccl_unique_id; /* ncclUniqueId bytes (128), same on every rank */
@@ -192,6 +197,12 @@ int32_t mavi_download_cell_lists(MaviHandle *h, int32_t *start, int32_t *ids);
 /* neighbour stencil actually used by the pair kernels for cell `cell`: up to 8 neighbour cell ids
  * (the reference's half stencil src/chunks.jl:61-118 united with its mirror image); returns count in *n. */
 int32_t mavi_cell_neighbors(MaviHandle *h, int32_t cell, int32_t *out8, int32_t *n);
+
+/* update_particle_chunk! (src/chunks.jl:120-147) evaluated on the HOST with the device's exact arithmetic (Base.div as trunc
+ * of the real quotient, the clamp of index n+1): cell_out[i] = 0-based linear cell id of point i, -1 outside the grid.
+ * pos is T[2n] with T = params->dtype; only the grid fields of params are read.  Needs no GPU: host-side callers that
+ * route particles to slabs (one process per GPU) use it so that host and device can never disagree on a cell. */
+int32_t mavi_cells_of_points(const MaviParams *params, const void *pos, int64_t n, int32_t *cell_out);
 
 /* ---- quantities, src/quantities.jl ----------------------------------------------------------
  * ke = kinetic_energy (:12-18; NaN for states without vel).  pe_mode 0: exact all-pairs LJ

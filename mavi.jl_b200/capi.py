@@ -73,7 +73,7 @@ class MaviParams(C.Structure):
         ("dyn", C.c_double * 8), ("particle_radius", C.c_double),
         ("rings", C.POINTER(MaviRingsParams)),
         ("dt", C.c_double),
-        ("rng_mode", C.c_int32), ("_pad2", C.c_int32), ("seed", C.c_uint64),
+        ("rng_mode", C.c_int32), ("n_gpus", C.c_int32), ("seed", C.c_uint64),
         ("device", C.c_int32), ("flags", C.c_int32), ("stream", C.c_void_p),
         ("rank", C.c_int32), ("world", C.c_int32), ("nccl_unique_id", C.c_void_p), ("n_global", C.c_int64),
     ]
@@ -98,6 +98,7 @@ SIGNATURES = {
     "mavi_download_cells": (C.c_int32, [_H, C.c_void_p, C.c_void_p]),
     "mavi_download_cell_lists": (C.c_int32, [_H, C.c_void_p, C.c_void_p]),
     "mavi_cell_neighbors": (C.c_int32, [_H, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "mavi_cells_of_points": (C.c_int32, [C.POINTER(MaviParams), C.c_void_p, C.c_int64, C.c_void_p]),
     "mavi_energies": (C.c_int32, [_H, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mavi_rings_download_info": (C.c_int32, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mavi_rings_set_neighbors": (C.c_int32, [_H, C.c_int32, C.c_int32, C.c_double]),

@@ -243,6 +243,9 @@ class CUDADevice(DeviceMode):
     float32: bool = False
     flags: int = 0
     stream: Optional[int] = None
+    # ONE process, n_gpus GPUs inside the handle (devices device .. device+n_gpus-1): the library partitions the state
+    # into x-slabs on upload and un-permutes on download; System(...) is used exactly as with one GPU
+    n_gpus: int = 1
     # x-slab decomposition, one process per GPU
     rank: int = 0
     world: int = 1

@@ -768,6 +768,19 @@ int32_t api_download_local(void *hh, int64_t *ids, void *pos, void *second, void
   return h->check_device_flags();
 }
 
+// internal (multi.cu): GLOBAL cell ids of the owned particles, in the order mavi_download_local lists them
+int32_t api_download_local_cells(void *hh, int32_t *cells) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h || !cells || h->p.num_cells == 0) return MAVI_ERR_BAD_PARAMS;
+  cudaSetDevice(h->device);
+  if (h->p.slab) slab_join(h);
+  const size_t n = (size_t)h->p.n;
+  if ((int)n > h->n_cap) return MAVI_ERR_CAPACITY;
+  launch_compact_cells(h->ctx(), h->p, h->a, h->a.st_cell);
+  CUDA_TRY(h, cudaMemcpyAsync(cells, h->a.st_cell, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  return h->check_device_flags();
+}
+
 // slab mode upload: the particles whose cell column this rank owns, with their global original ids
 int32_t api_upload_local(void *hh, const int64_t *ids, const void *pos, const void *second, int64_t n_local) {
   Handle *h = reinterpret_cast<Handle *>(hh);

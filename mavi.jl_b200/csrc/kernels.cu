@@ -351,6 +351,30 @@ __global__ void k_compact(const __grid_constant__ DevParams p, const int *__rest
   st_id[rank] = idflag[k];
 }
 
+// GLOBAL cell id (the reference's, src/chunks.jl:129-130) of every owned particle, in the rank order of k_compact
+__global__ void k_compact_cells(const __grid_constant__ DevParams p, const int *__restrict__ tile_prefix,
+                                const int *__restrict__ cta_first, const int *__restrict__ cell, int *__restrict__ out) {
+  int rank = blockIdx.x * blockDim.x + threadIdx.x;
+  if (rank >= p.n) return;
+  int c = -1;
+  if (rank < p.n_active) {
+    c = cell[slot_of_rank(p, tile_prefix, cta_first, rank)];
+    if (p.slab) {  // local frame [0 = left halo, 1..m owned, m+1 = right halo] -> global column
+      const int lcol = div_rows(p, c), row = c - lcol * p.num_rows;
+      int g = lcol - 1 + p.col_lo;
+      if (g < 0) g += p.gcols;
+      else if (g >= p.gcols) g -= p.gcols;
+      c = g * p.num_rows + row;
+    }
+  }
+  out[rank] = c;
+}
+
+void launch_compact_cells(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int *out) {
+  ensure_rank_maps(c, p, a);
+  MAVI_LAUNCH(c, k_compact_cells, nblk(p.n), TPB, 0, p, a.tile_prefix, a.cta_first, a.cell, out);
+}
+
 void launch_compact_to_staging(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel) {
   ensure_rank_maps(c, p, a);
   MAVI_LAUNCH(c, k_compact, nblk(p.n), TPB, 0, p, a.tile_prefix, a.cta_first, a.pos[0], second_is_vel ? a.vel : nullptr,

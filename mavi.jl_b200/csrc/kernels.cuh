@@ -71,6 +71,7 @@ void launch_build_index_tiles(const LaunchCtx &c, const DevParams &p, const real
                               int *cell_out, int *count, int *tstart, int *perm, int *flags);
 // dense copy of the current state into staging (rank order)
 void launch_compact_to_staging(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel);
+void launch_compact_cells(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int *out);
 void launch_init_staging_ids(const LaunchCtx &c, int n, const unsigned char *mask, unsigned int *st_id);
 void launch_ids_to_i64(const LaunchCtx &c, int n, const unsigned int *st_id, long long *out);
 void launch_ids_from_i64(const LaunchCtx &c, int n, const long long *in, unsigned int *st_id);

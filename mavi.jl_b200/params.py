@@ -139,6 +139,7 @@ def lower(state, space_cfg: SpaceCfg, dynamic_cfg, int_cfg) -> LoweredParams:
     p.dt = float(int_cfg.dt)
 
     p.rng_mode = capi.RNG_HOST_NOISE if dev.rng_mode == "host_noise" else capi.RNG_PHILOX
+    p.n_gpus = int(dev.n_gpus)
     p.seed = dev.seed
     p.device = dev.device
     p.flags = dev.flags

@@ -445,14 +445,16 @@ def test_c2_one_million_properties(cuda_lib):
 
 
 # ---------------------------------------------------------------- the x-slab machinery on ONE GPU (MAVI_FLAG_SLAB_SELF)
-@pytest.mark.parametrize("kind,flags", [("lj", 0), ("lj", 8), ("harm", 8), ("szabo", 0)])
+@pytest.mark.parametrize("kind,flags", [("lj", 0), ("lj", 8), ("harm", 8), ("szabo", 0), ("szabo_noise", 0), ("rtp", 0)])
 def test_slab_self_mode_matches_plain(cuda_lib, kind, flags):
     """One-rank slab mode: halo columns, the two-stream step pipeline (flags=8: several CTAs per tile row), boundary
     recompute and local copies in place of NCCL.  Must reproduce the plain single-domain run: bit-identical for the
     Newton dynamics, to rounding for Szabo (the minimum image is applied through the seam)."""
     SELF = pkg.capi.FLAG_SLAB_SELF
-    if kind == "szabo":
-        case = H.sp_case("szabo", nx=40, ny=30, rot_diff=0.0)
+    sp = kind in ("szabo", "szabo_noise", "rtp")
+    if sp:
+        # szabo_noise / rtp: host noise rows are indexed by the ORIGINAL id (global row in slab mode) through migration
+        case = H.sp_case("rtp" if kind == "rtp" else "szabo", nx=40, ny=30, rot_diff=0.0 if kind == "szabo" else 0.05)
         ic = case["int_cfg"]
         mkdev = lambda f: pkg.CUDADevice(rng_mode="host_noise", flags=f)  # noqa: E731
     else:
@@ -465,15 +467,23 @@ def test_slab_self_mode_matches_plain(cuda_lib, kind, flags):
     a = H.make_gpu(a_case)
     b = H.make_gpu(b_case)
     n = len(a.state.pos)
+    rng = np.random.default_rng(99)
     for steps in (1, 33, 80):
-        a.step(steps)
-        b.step(steps)
+        noise = None
+        if kind == "szabo_noise":
+            noise = rng.standard_normal((steps, n))
+        elif kind == "rtp":
+            noise = rng.random((steps, 2 * n))
+            noise[:, 0::2] *= 0.02   # u < tumble_rate * dt = 0.001 for ~5 % of the particles per step
+        a.step(steps, noise)
+        b.step(steps, noise)
         a.sync_to_host()
         ids, pos, second, forces = b.download_local()
         assert len(ids) == n and np.array_equal(np.sort(ids), np.arange(n))
         o = np.argsort(ids)
-        if kind == "szabo":
+        if sp:
             assert np.abs(pos[o] - a.state.pos).max() / case["geom"].length < 1e-12
+            assert np.abs(second[o] - a.state.pol_angle).max() < 1e-10
         else:
             assert np.array_equal(pos[o], a.state.pos)
             assert np.array_equal(second[o], a.state.vel)

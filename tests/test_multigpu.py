@@ -143,3 +143,113 @@ def test_multigpu_slabs_match_oracle(cuda_lib, kind, steps, flags):
         out, err = proc.communicate()
         pytest.fail("multi-GPU worker hung:\n" + out[-2000:] + err[-3000:])
     assert "MGPU_OK" in out, out[-3000:] + err[-3000:]
+
+
+# ---------------------------------------------------------------- host cell rule (mavi_cells_of_points), CPU
+def test_cells_of_points_bit_exact_against_oracle(oracle):
+    """mavi_cells_of_points (the rule the single-process multi-GPU handle and slabs.column_of partition with) ==
+    update_particle_chunk! as the oracle restates it, including points placed exactly on cell edges."""
+    from mavi_jl_b200 import slabs
+    case = H.newton_case(nx=60, ny=44, wall="periodic", jitter=0.45)
+    ccfg = case["int_cfg"].chunks_cfg
+    geom = case["geom"]
+    st = case["mk"]()
+    rng = np.random.default_rng(3)
+    pos = st.pos.copy()
+    cl, ch = geom.length / ccfg.num_cols, geom.height / ccfg.num_rows
+    k = rng.integers(0, ccfg.num_cols + 1, len(pos) // 3)
+    pos[: len(k), 0] = k * cl                                       # rounded multiples of the cell length
+    pos[len(k): 2 * len(k), 0] = np.nextafter(k * cl, 0)
+    r = rng.integers(0, ccfg.num_rows + 1, len(pos) // 3)
+    pos[: len(r), 1] = geom.height - r * ch
+    pos = np.clip(pos, 0.0, [geom.length, geom.height])
+    case2 = dict(case, mk=lambda: pkg.SecondLawState(pos=pos.copy(), vel=st.vel.copy()))
+    o = H.make_oracle(case2)
+    cell, _ = o.download_cells()
+    got = slabs.cells_of_points(pos, geom, ccfg.num_cols, ccfg.num_rows)
+    assert np.array_equal(got, cell)
+    # outside the grid -> -1 (BoundsError in the reference)
+    out = slabs.cells_of_points(np.array([[-2 * cl, 1.0], [1.0, geom.height + 2 * ch], [np.nan, 1.0]]), geom, ccfg.num_cols, ccfg.num_rows)
+    assert np.all(out == -1)
+    # Float32 points are promoted (Chunks keeps Float64 geometry, src/chunks.jl:13,27-30)
+    p32 = pos.astype(np.float32)
+    assert np.array_equal(slabs.cells_of_points(p32, geom, ccfg.num_cols, ccfg.num_rows),
+                          slabs.cells_of_points(p32.astype(np.float64), geom, ccfg.num_cols, ccfg.num_rows))
+
+
+def test_single_process_multi_gpu_fails_loudly_without_devices(cuda_lib):
+    """MaviParams.n_gpus > 1 with fewer visible devices: MAVI_ERR_CUDA and a message, never a silent single-GPU / CPU run.
+    Unsupported configurations are rejected before any device is touched."""
+    if _ngpus() >= 2:
+        pytest.skip("this box has the devices")
+    case = H.newton_case(nx=24, ny=24, wall="periodic")
+    case["int_cfg"] = pkg.IntCfg(dt=0.001, chunks_cfg=case["int_cfg"].chunks_cfg, device=pkg.CUDADevice(n_gpus=2))
+    with pytest.raises(pkg.MaviError) as e:
+        H.make_gpu(case)
+    assert e.value.status == pkg.capi.ERR_CUDA and "CUDA devices" in str(e.value)
+    rigid = H.newton_case(nx=24, ny=24, wall="rigid")
+    rigid["int_cfg"] = pkg.IntCfg(dt=0.001, chunks_cfg=rigid["int_cfg"].chunks_cfg, device=pkg.CUDADevice(n_gpus=2))
+    with pytest.raises(pkg.MaviError) as e:
+        H.make_gpu(rigid)
+    assert e.value.status == pkg.capi.ERR_UNSUPPORTED
+
+
+# ---------------------------------------------------------------- GPU: ONE process, several GPUs inside the handle
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,steps,flags", [("lj", 150, 0), ("lj", 150, 8), ("harm", 150, 8), ("szabo", 40, 0), ("rtp", 40, 0)])
+def test_single_process_multi_gpu_matches_oracle(cuda_lib, kind, steps, flags):
+    """MaviParams.n_gpus: the plain mavi_upload_state / mavi_step / mavi_download_state calls of ONE
+    process drive all GPUs; results against the single-domain oracle, cells bit-exact, time info, energies."""
+    n = _ngpus()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    G = 4 if n >= 4 else 2
+    if kind in ("lj", "harm"):
+        dyn = None if kind == "lj" else pkg.HarmTruncCfg(k_rep=10.0, k_atr=3.0, dist_eq=1.0, dist_max=1.2)
+        case = H.newton_case(nx=72, ny=40, dyn=dyn, wall="periodic", jitter=0.2, vmax=3.0, dt=0.002)
+        mkdev = lambda: pkg.CUDADevice(n_gpus=G, flags=flags)  # noqa: E731
+    else:
+        case = H.sp_case(kind, nx=64, ny=40, rot_diff=0.05)
+        mkdev = lambda: pkg.CUDADevice(n_gpus=G, flags=flags, rng_mode="host_noise")  # noqa: E731
+    ic = case["int_cfg"]
+    case["int_cfg"] = pkg.IntCfg(dt=ic.dt, chunks_cfg=ic.chunks_cfg, device=mkdev())
+    g, o = H.make_gpu(case), H.make_oracle(case)
+    npart = len(g.state.pos)
+    cg, ng = g.download_cells()
+    co, no = o.download_cells()
+    assert np.array_equal(cg, co) and np.array_equal(ng, no)
+    noise = None
+    rng = np.random.default_rng(5)
+    if kind == "szabo":
+        noise = rng.standard_normal((steps, npart))
+    elif kind == "rtp":
+        noise = rng.random((steps, 2 * npart))
+        noise[:, 0::2] *= 0.02
+    g.step(steps, noise)
+    o.step(steps, noise)
+    g.sync_to_host()
+    assert np.abs(g.state.pos - o.pos()).max() / case["geom"].length < 1e-12
+    assert H.rel_err(g.state.second, o.second()) < 1e-10
+    assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-9
+    assert g.time_info.num_steps == steps and g.time_info.time == o.time()[1]
+    if kind in ("lj", "harm"):
+        cg, ng = g.download_cells()
+        co, no = o.download_cells()
+        assert np.array_equal(cg, co) and np.array_equal(ng, no)
+        sg, ig = g.download_cell_lists()
+        so, io = o.download_cell_lists()
+        assert np.array_equal(sg, so) and np.array_equal(ig, io)
+        ke, _ = g.energies(want_pe=False)
+        assert abs(ke - o.energies()[0]) <= 1e-12 * abs(ke)
+        c = g.counters()
+        assert c["steps"] == steps and c["rebinned"] > 0 and c["emigrants"] > 0   # particles did cross slab boundaries
+    # the host edits the state and uploads again (GUI / checkpoint hook): same handle, new partition
+    g.state.pos[:] = o.pos()
+    g.state.second[:] = o.second()
+    g.upload_state()
+    g.step(5, None if noise is None else noise[:5])
+    o.step(5, None if noise is None else noise[:5])
+    g.sync_to_host()
+    assert np.abs(g.state.pos - o.pos()).max() / case["geom"].length < 1e-12
+    assert g.launch_count() > 0
+    g.close()
