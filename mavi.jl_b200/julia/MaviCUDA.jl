@@ -35,6 +35,9 @@ Base.@kwdef struct CUDADevice <: DeviceMode
     rng_mode::Symbol = :philox          # :host_noise (caller passes the draws) | :philox (device RNG)
     seed::UInt64 = 24042001
     sync_every::Int = 1                  # download state every k calls of a per-step function (GUI / experiments)
+    n_gpus::Int32 = 1                    # > 1: this ONE process drives devices device .. device+n_gpus-1 through the one
+                                         # handle (MaviParams.n_gpus): x-slabs of cell columns inside the library, halo and
+                                         # migration over NCCL/NVLink; the System is used exactly as with one GPU
 end
 
 # ---- flat PODs of include/mavi.h (isbits, same field order) -------------------------------------------------------
@@ -89,7 +92,7 @@ struct MaviParams
     rings::Ptr{MaviRingsParams}
     dt::Float64
     rng_mode::Int32
-    _pad2::Int32
+    n_gpus::Int32
     seed::UInt64
     device::Int32
     flags::Int32
@@ -197,7 +200,7 @@ function attach!(system::System)
         Tuple(Float64.(bbox.bottom_left)), bbox.length, bbox.height,
         isnothing(cc) ? 0 : cc.num_cols, isnothing(cc) ? 0 : cc.num_rows, kind, 0, Float64.(dyn),
         minimum(particle_radius(system.dynamic_cfg)), rings_ptr, system.int_cfg.dt,
-        dev.rng_mode == :host_noise ? 0 : 1, 0, dev.seed, dev.device, 0, C_NULL, 0, 1, C_NULL, 0))
+        dev.rng_mode == :host_noise ? 0 : 1, dev.n_gpus, dev.seed, dev.device, 0, C_NULL, 0, 1, C_NULL, 0))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     ds = DeviceState(C_NULL, keep, 0)
     GC.@preserve keep begin
@@ -252,7 +255,12 @@ function device_step!(system::System, nsteps::Integer=1; noise=nothing)
     return nothing
 end
 
-const CUDASystem = System{T,ND,NT,S,W,G,D,<:IntCfg{<:Any,<:Any,CUDADevice}} where {T,ND,NT,S,W,G,D}
+# Every System whose IntCfg carries a CUDADevice (RingsIntCfg is the same IntCfg with `extra`, src/rings/configs.jl:344-352).
+# The leading eight type parameters of `System` are spelled out WITH the bounds its definition declares
+# (src/systems.jl:45-48); the trailing six (ChunksT, SysT, SpaceDataT, InfoT, DebugT, RNGT) stay free with their own bounds.
+const CUDAIntCfg = IntCfg{<:Number,<:Union{ChunksCfg,Nothing},CUDADevice,<:Any}
+const CUDASystem = System{T,ND,NT,StateT,WallTypeT,GeometryCfgT,DynamicCfgT,IntCfgT} where {
+    T,ND,NT,StateT<:State{ND,T},WallTypeT<:WallType,GeometryCfgT<:GeometryCfg,DynamicCfgT<:DynamicCfg,IntCfgT<:CUDAIntCfg}
 
 # ---- the dispatch seam ------------------------------------------------------------------------------------------------
 newton_step!(system::CUDASystem) = device_step!(system, 1)
