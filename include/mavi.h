@@ -145,6 +145,7 @@ typedef struct MaviParams {
 #define MAVI_FLAG_NO_FORCE_CARRY 4    /* Newton steps: always run the full first force pass instead of carrying F2 / the drift over from the previous step (A/B testing; results are bit-identical) */
 #define MAVI_FLAG_SMALL_BLOCKS 8      /* testing: 3 tile columns per CTA, so that block splitting, chunking and the slab overlap path run on small systems */
 #define MAVI_FLAG_SLAB_SELF 16        /* world == 1 only: run the x-slab machinery (halo columns, emigrant records, two-stream step pipeline) with this rank as its own periodic neighbour, device copies instead of NCCL; state moves through mavi_upload_local / mavi_download_local.  Lets the multi-GPU path be tested and profiled on one GPU */
+#define MAVI_FLAG_LEGACY_STAGING 32    /* A/B testing: the round-1 force kernels (one CTA per tile block, cp.async staging behind CTA barriers) instead of the persistent producer/consumer kernels with bulk-async staging; results are bit-identical */
 #define MAVI_FLAG_TIGHT_TILES 2       /* testing: tile capacity without slack, so that the overflow -> rebuild -> resume path is exercised */
 
 typedef struct MaviHandle MaviHandle;

@@ -32,6 +32,7 @@ FLAG_TIGHT_TILES = 2
 FLAG_NO_FORCE_CARRY = 4
 FLAG_SMALL_BLOCKS = 8
 FLAG_SLAB_SELF = 16
+FLAG_LEGACY_STAGING = 32  # A/B: round-1 force kernels (include/mavi.h)
 NEIGH_OFF, NEIGH_COUNT, NEIGH_LIST = range(3)
 NEIGH_MAX = 15
 

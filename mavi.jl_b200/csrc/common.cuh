@@ -113,7 +113,9 @@ enum {
   // instrumentation (mavi_counters): changed-cell records and inter-tile movers summed over the steps since the last upload
   FLAG_CUM_CHG = 22, FLAG_CUM_MV = 23, FLAG_CUM_DIRTY = 13, FLAG_CUM_EM = 14,
   FLAG_NMOVED = 15,  // per step: particles whose cell changed (re-binned by the incremental repair)
-  FLAG_COUNT = 24
+  // persistent tile-block kernels: next work item of the launch on the main stream [0] / of the boundary-block launch [1]
+  FLAG_WORK0 = 24, FLAG_WORK1 = 25,
+  FLAG_COUNT = 32
 };
 
 // A step whose tile repair overflowed (or that pushed a particle out of the grid) leaves the layout un-repaired: every

@@ -916,6 +916,8 @@ __global__ void k_step_begin(int *__restrict__ flags) {
     flags[FLAG_NEM1] = 0;
     flags[FLAG_NFIX] = 0;
     flags[FLAG_NMV] = 0;
+    flags[FLAG_WORK0] = 0;
+    flags[FLAG_WORK1] = 0;
     flags[FLAG_RAN] = run;
   }
 }
@@ -1212,6 +1214,288 @@ __device__ __forceinline__ void for_each_block_particle(const DevParams &p, cons
   }
 }
 
+// =========================================================================================================
+// Pipelined tile-block kernels (the hot passes of chunked runs: k_newton_p, k_self_propelled_p).
+//
+// Same decomposition and the same per-particle arithmetic as for_each_block_particle above (so results are bit-identical
+// to it), but the staging is taken off the compute warps' critical path — profiles/r01_ncu_newton_summary.md: 46 % of the
+// warp-stall samples of the round-1 kernel sat in chunk_stage (three CTA barriers, dependent tstart loads, LDGSTS landing):
+//   * PERSISTENT CTAs (3 per SM) fetch tile blocks from a device-side work counter (zeroed by k_step_begin);
+//   * ONE PRODUCER WARP per CTA stages chunk k+1 into the second of two shared-memory buffers while the EIGHT CONSUMER
+//     WARPS run the pair loops of chunk k: column descriptors live in the producer's registers (lane = column), the
+//     prefix sums are warp scans, and every contiguous run of positions ([cell row above | tile | cell row below] of each
+//     staged column) is ONE bulk-async copy (cp.async.bulk.shared::cluster.global, UBLKCP) that completes on the
+//     buffer's `full` mbarrier — no per-thread address arithmetic, no register staging, no CTA barrier anywhere;
+//   * consumers wait on `full` (mbarrier parity), walk their particles, and release the buffer through `empty`; a warp
+//     that finishes its share of a chunk early simply starts on the next one.
+// Float32 build: a float2 run is only 8-byte aligned, below the 16 bytes bulk copies need, so there the producer warp
+// copies the runs itself (plain loads / stores) before it arrives on `full`.
+// =========================================================================================================
+constexpr int PIPE_CW = 8;                           // consumer warps per CTA
+constexpr int PIPE_CT = PIPE_CW * 32;                // consumer threads
+constexpr int PIPE_THREADS = PIPE_CT + 32;           // + the producer warp (the LAST warp of the CTA)
+constexpr int PIPE_CTAS_PER_SM = 3;
+constexpr int PG_MAX = 30;                           // own columns per chunk (+ two side columns: one producer lane each)
+constexpr int PSPOS_CAP = 1280;                      // staged positions per chunk
+constexpr int POWN_CAP = 1024;                       // own particles per chunk
+constexpr bool PIPE_BULK = sizeof(real2) == 16;      // bulk-async copies need 16-byte aligned runs (Float64 build)
+
+struct PChunk {
+  int state;        // 1: a staged chunk, 0: no more work for this CTA
+  int nc, use_mi, nown, ok, tr, cs;
+  int src_t1, lt1;  // !ok: the one column that does not fit the staging area (walked in global memory)
+  int gbase[PG_MAX + 2];
+  int2 cwin[PG_MAX + 2][MAVI_TR];  // [j][lr-1] = (first staged index of cell row lr-1, end of cell row lr+1)
+};
+constexpr int PCH_BYTES = (sizeof(PChunk) + 15) / 16 * 16;
+constexpr int PBUF_BYTES = PCH_BYTES + PSPOS_CAP * (int)sizeof(real2) + POWN_CAP * (int)sizeof(unsigned int);
+constexpr int PIPE_SMEM = 64 + 2 * PBUF_BYTES;       // [4 mbarriers | buffer 0 | buffer 1]
+
+__device__ __forceinline__ unsigned int smem_u32(const void *ptr) { return (unsigned int)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned int bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.release.cta.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int parity) {
+  asm volatile(
+      "{\n\t.reg .pred ok;\n"
+      "W%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 ok, [%0], %1;\n\t"
+      "@!ok bra W%=;\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// one contiguous run global -> shared, completing `bytes` on the mbarrier (UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned int bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// PRODUCER WARP: stage the chunk of own columns starting at local column cs (at most `rem` columns) of tile row tr into
+// one buffer and arrive on its `full` barrier.  Returns the number of own columns taken.  Same layout as chunk_stage.
+template <bool PER>
+__device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restrict__ tstart, const real2 *__restrict__ pos,
+                                          int tr, int cs, int rem, bool exact_minimg, PChunk *ck, real2 *s_pos,
+                                          unsigned int *s_list, unsigned long long *full_bar) {
+  const int lane = threadIdx.x & 31;
+  const int R = p.num_rows, Cn = p.num_cols;
+  const int r0 = tr * MAVI_TR;
+  const int rows = min(MAVI_TR, R - r0);
+  const int ncand = min(rem, PG_MAX);
+  // ---- column descriptors: lane j describes staged column j (0 .. ncand+1); independent loads
+  const int j = lane;
+  const bool in = j < ncand + 2;
+  int la = 0, lt = 0, lb = 0, sa = 0, st = 0, sb = 0, cj = 0;
+  bool wrapped = false;
+  if (in) {
+    int c = cs - 1 + j;
+    bool exists = true;
+    if (c < 0) { if (p.wrap_cols) { c = Cn - 1; wrapped = true; } else exists = false; }
+    else if (c >= Cn) { if (p.wrap_cols) { c = 0; wrapped = true; } else exists = false; }
+    if (exists && p.slab && ((c == 0 && p.seam_left) || (c == Cn - 1 && p.seam_right))) wrapped = true;
+    int ra = r0 - 1, rb = r0 + MAVI_TR;
+    bool has_a = exists, has_b = exists;
+    if (ra < 0) { if (p.wrap_rows) { ra = R - 1; wrapped = wrapped || exists; } else has_a = false; }
+    if (rb >= R) { if (p.wrap_rows) { rb = 0; wrapped = wrapped || exists; } else has_b = false; }
+    cj = exists ? c : 0;
+    if (exists) {
+      const int *tt = tstart + (size_t)(c * p.tpc + tr) * (MAVI_TR + 1);
+      const int qa = has_a ? tq_of(p, c, ra) : 0, qb = has_b ? tq_of(p, c, rb) : 0;
+      st = __ldg(tt);
+      const int et = __ldg(tt + MAVI_TR);
+      const int a0 = has_a ? __ldg(tstart + qa) : 0, a1 = has_a ? __ldg(tstart + qa + 1) : 0;
+      const int b0 = has_b ? __ldg(tstart + qb) : 0, b1 = has_b ? __ldg(tstart + qb + 1) : 0;
+      lt = et - st; sa = a0; la = a1 - a0; sb = b0; lb = b1 - b0;
+    }
+  }
+  // ---- prefix sums over the lanes, greedy number of own columns that fit
+  const int sz = la + lt + lb;
+  const int own = (in && j >= 1 && j <= ncand) ? lt : 0;
+  int incl = sz, oincl = own;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o), u = __shfl_up_sync(0xffffffffu, oincl, o);
+    if (lane >= o) { incl += v; oincl += u; }
+  }
+  const int incl_next = __shfl_down_sync(0xffffffffu, incl, 1);  // staged total if this lane were the last own column
+  const bool fits = j >= 1 && j <= ncand && incl_next <= PSPOS_CAP && oincl <= POWN_CAP;
+  const unsigned int bal = __ballot_sync(0xffffffffu, fits);
+  const int nc = bal ? 31 - __clz(bal) : 1;  // fits is monotone in j
+  const unsigned int wbal = __ballot_sync(0xffffffffu, in && j <= nc + 1 && wrapped);
+  const int off = incl - sz, ownoff = oincl - own;
+  const int total = __shfl_sync(0xffffffffu, incl, nc + 1);
+  const int nown = __shfl_sync(0xffffffffu, oincl, nc);
+  const int st1 = __shfl_sync(0xffffffffu, st, 1), lt1 = __shfl_sync(0xffffffffu, lt, 1);
+  if (lane == 0) {
+    ck->state = 1;
+    ck->nc = nc;
+    ck->ok = bal ? 1 : 0;
+    ck->use_mi = (PER && (exact_minimg || !p.fast_interior || wbal)) ? 1 : 0;
+    ck->nown = nown;
+    ck->tr = tr;
+    ck->cs = cs;
+    ck->src_t1 = st1;
+    ck->lt1 = lt1;
+    if (PIPE_BULK && bal) mbar_expect_tx(full_bar, (unsigned int)total * (unsigned int)sizeof(real2));
+  }
+  __syncwarp();
+  if (bal) {
+    // ---- positions: every contiguous run is one bulk-async copy, issued by the lane that owns the column
+    if (PIPE_BULK) {
+      if (j <= nc + 1) {
+        if (la) bulk_g2s(s_pos + off, pos + sa, (unsigned int)la * (unsigned int)sizeof(real2), full_bar);
+        if (lt) bulk_g2s(s_pos + off + la, pos + st, (unsigned int)lt * (unsigned int)sizeof(real2), full_bar);
+        if (lb) bulk_g2s(s_pos + off + la + lt, pos + sb, (unsigned int)lb * (unsigned int)sizeof(real2), full_bar);
+      }
+    }
+    // ---- cell-row windows and the own-particle list: one staged column after the other, lane = cell row of the tile
+    for (int jj = 0; jj < nc + 2; jj++) {
+      const int offj = __shfl_sync(0xffffffffu, off, jj), laj = __shfl_sync(0xffffffffu, la, jj);
+      const int ltj = __shfl_sync(0xffffffffu, lt, jj), lbj = __shfl_sync(0xffffffffu, lb, jj);
+      const int stj = __shfl_sync(0xffffffffu, st, jj), cjj = __shfl_sync(0xffffffffu, cj, jj);
+      const int qbj = __shfl_sync(0xffffffffu, ownoff, jj);
+      const int tot = laj + ltj + lbj;
+      const int *tt = tstart + (size_t)(cjj * p.tpc + tr) * (MAVI_TR + 1);
+      // staged start of tile row lane+1 (rows beyond the grid start where the tile ends)
+      const int tsl = tot ? __ldg(tt + lane) - stj : 0, tsn = tot ? __ldg(tt + lane + 1) - stj : 0;
+      const int rs = offj + laj + tsl;
+      const int up = __shfl_up_sync(0xffffffffu, rs, 1), dn = __shfl_down_sync(0xffffffffu, rs, 2);
+      const int end = offj + tot;
+      const int wa = lane == 0 ? offj : up;                                                 // start of row lr-1
+      const int wb = (lane + 3 >= rows + 2) ? end : (lane <= 29 ? dn : offj + laj + ltj);   // end of row lr+1
+      ck->cwin[jj][lane] = make_int2(wa, wb);
+      if (lane == 0) ck->gbase[jj] = stj - (offj + laj);
+      if (jj >= 1 && jj <= nc && lane < rows) {
+        for (int i = tsl; i < tsn; i++)
+          s_list[qbj + i] = (unsigned int)(offj + laj + i) | ((unsigned int)jj << 16) | ((unsigned int)(lane + 1) << 24);
+      }
+      if (!PIPE_BULK) {  // Float32 build: the warp copies the three runs of this column itself
+        const int saj = __shfl_sync(0xffffffffu, sa, jj), sbj = __shfl_sync(0xffffffffu, sb, jj);
+        for (int i = lane; i < tot; i += 32) {
+          const int src = i < laj ? saj + i : (i < laj + ltj ? stj + (i - laj) : sbj + (i - laj - ltj));
+          s_pos[offj + i] = __ldg(pos + src);
+        }
+      }
+    }
+  }
+  __syncwarp();  // every lane's descriptor / list / position stores are ordered before the arrival below
+  if (lane == 0) mbar_arrive(full_bar);
+  return nc;
+}
+
+// Drives a pipelined force kernel: pre(k) before and body(k, r, cell, active, F) after the pair force F of every
+// particle slot (F = 0 for the inactive tail).  work: device counter of the next tile block (see FLAG_WORK*).
+template <int DYN, bool PER, typename Pre, typename Body>
+__device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const int *__restrict__ tstart,
+                                                       const real2 *__restrict__ pos, const int *__restrict__ cell,
+                                                       bool exact_minimg, int *__restrict__ work, Pre &&pre, Body &&body) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(dsm);  // [0,1] full, [2,3] empty
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int bpr = p.blk_per_row;
+  const int per_row = p.blk_mode == 0 ? bpr : (p.blk_mode == 1 ? bpr - 1 - p.blk_last : 1 + p.blk_last);
+  const int nitems = per_row * p.tpc;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], PIPE_CW);
+    mbar_init(&bars[3], PIPE_CW);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the async proxy (bulk copies) sees the initialised barriers
+  }
+  __syncthreads();  // the only CTA barrier of the kernel
+  if (w == PIPE_CW) {
+    // ================================ producer warp ================================
+    int k = 0;
+    for (;;) {
+      int item = 0;
+      if (lane == 0) item = atomicAdd(work, 1);
+      item = __shfl_sync(0xffffffffu, item, 0);
+      if (item >= nitems) break;
+      const int tr = item / per_row;
+      int bcol = item - tr * per_row;
+      if (p.blk_mode == 1) bcol += 1;
+      else if (p.blk_mode == 2) bcol = bcol ? bpr - bcol : 0;
+      const int c_begin = p.ord_col0 + bcol * p.blk_cols;
+      const int c_end = min(c_begin + p.blk_cols, p.ord_col0 + p.ord_cols);
+      for (int cs = c_begin; cs < c_end; k++) {
+        const int b = k & 1;
+        if (k >= 2) mbar_wait(&bars[2 + b], (unsigned int)(((k >> 1) & 1) ^ 1));  // the consumers released this buffer
+        unsigned char *buf = dsm + 64 + (size_t)b * PBUF_BYTES;
+        cs += pipe_stage<PER>(p, tstart, pos, tr, cs, c_end - cs, exact_minimg, reinterpret_cast<PChunk *>(buf),
+                              reinterpret_cast<real2 *>(buf + PCH_BYTES),
+                              reinterpret_cast<unsigned int *>(buf + PCH_BYTES + PSPOS_CAP * sizeof(real2)), &bars[b]);
+      }
+    }
+    const int b = k & 1;  // end marker
+    if (k >= 2) mbar_wait(&bars[2 + b], (unsigned int)(((k >> 1) & 1) ^ 1));
+    if (lane == 0) {
+      reinterpret_cast<PChunk *>(dsm + 64 + (size_t)b * PBUF_BYTES)->state = 0;
+      mbar_arrive(&bars[b]);
+    }
+    return;
+  }
+  // ================================ consumer warps ================================
+  if (p.blk_mode != 2) {  // inactive tail: no pair forces
+    const int ntail = p.n - p.n_active;
+    for (int i = (int)blockIdx.x * PIPE_CT + (int)threadIdx.x; i < ntail; i += (int)gridDim.x * PIPE_CT) {
+      const int k = p.tail_base + i;
+      pre(k);
+      body(k, pos[k], 0, false, make_real2(0.0, 0.0));
+    }
+  }
+  for (int kc = 0;; kc++) {
+    const int b = kc & 1;
+    unsigned char *buf = dsm + 64 + (size_t)b * PBUF_BYTES;
+    const PChunk *ck = reinterpret_cast<const PChunk *>(buf);
+    const real2 *s_pos = reinterpret_cast<const real2 *>(buf + PCH_BYTES);
+    const unsigned int *s_list = reinterpret_cast<const unsigned int *>(buf + PCH_BYTES + PSPOS_CAP * sizeof(real2));
+    mbar_wait(&bars[b], (unsigned int)((kc >> 1) & 1));
+    if (!ck->state) break;
+    const int cs = ck->cs, r0 = ck->tr * MAVI_TR;
+    if (ck->ok) {
+      const int nown = ck->nown;
+      const bool mi = PER && ck->use_mi;
+      for (int q = threadIdx.x; q < nown; q += PIPE_CT) {
+        const unsigned int u = s_list[q];
+        const int self = u & 0xffffu, jj = (u >> 16) & 0xffu, lr = u >> 24;
+        const int k = self + ck->gbase[jj];
+        pre(k);
+        const real2 r = s_pos[self];
+        real fx = 0.0, fy = 0.0;
+        if (mi) chunk_walk<DYN, true>(p, ck, s_pos, jj, lr, self, r, fx, fy);
+        else chunk_walk<DYN, false>(p, ck, s_pos, jj, lr, self, r, fx, fy);
+        body(k, r, (cs - 1 + jj) * p.num_rows + r0 + lr - 1, true, make_real2(fx, fy));
+      }
+    } else {
+      // a single column too dense for the staging area: per-thread walk over the global arrays
+      const int b0 = ck->src_t1, e0 = b0 + ck->lt1;
+      for (int k = b0 + (int)threadIdx.x; k < e0; k += PIPE_CT) {
+        pre(k);
+        const real2 r = pos[k];
+        const int c = cell[k];
+        real fx = 0.0, fy = 0.0;
+        for_each_neighbor(p, tstart, c, k, [&](int jn) { accumulate_pair<DYN, PER>(p, r, __ldg(pos + jn), fx, fy); });
+        body(k, r, c, true, make_real2(fx, fy));
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bars[2 + b]);  // this warp is done with the buffer
+  }
+}
+
+static inline int grid_pipe(const DevParams &p) {
+  const int per_row = p.blk_mode == 0 ? p.blk_per_row : (p.blk_mode == 1 ? p.blk_per_row - 1 - p.blk_last : 1 + p.blk_last);
+  const int items = per_row * p.tpc;
+  const int want = 148 * PIPE_CTAS_PER_SM;
+  return items < want ? (items > 0 ? items : 1) : want;
+}
+
 static inline int grid2(const DevParams &p) {
   const int per_row = p.blk_mode == 0 ? p.blk_per_row : (p.blk_mode == 1 ? p.blk_per_row - 1 - p.blk_last : 1 + p.blk_last);
   return per_row * p.tpc + (p.blk_mode == 2 ? 0 : nblk(p.n - p.n_active));
@@ -1286,6 +1570,40 @@ __global__ void __launch_bounds__(TPB, MINB) k_newton_b2(const __grid_constant__
   // without a big-drift report -> always the exact minimum-image path there
   const bool exact = ms.flags[FLAG_BIGMOVE] != 0 || (p.slab && p.blk_mode == 2);
   for_each_block_particle<DYN, PER>(p, tstart, pos_in, ms.cell, exact, MAVI_NEWTON_B_LAMBDAS);
+}
+
+// the pipelined version of k_newton_b2 (default); work item counter: FLAG_WORK0 / FLAG_WORK1 (boundary-block launch)
+template <int DYN, bool PER, bool CARRY>
+__global__ void __launch_bounds__(PIPE_THREADS, PIPE_CTAS_PER_SM) k_newton_p(
+    const __grid_constant__ DevParams p, const int *__restrict__ tstart, const real2 *__restrict__ pos_in,
+    real2 *__restrict__ vel, const real2 *f1, real2 *f2, real2 *f1_next, real2 *__restrict__ pos_next,
+    int *__restrict__ fix_idx, real2 *__restrict__ fix_pos, const __grid_constant__ MoverSink ms) {
+  if (!ms.flags[FLAG_RAN]) return;
+  const bool exact = ms.flags[FLAG_BIGMOVE] != 0 || (p.slab && p.blk_mode == 2);
+  pipe_for_each_particle<DYN, PER>(p, tstart, pos_in, ms.cell, exact, ms.flags + (p.blk_mode == 2 ? FLAG_WORK1 : FLAG_WORK0),
+                                   MAVI_NEWTON_B_LAMBDAS);
+}
+
+template <int DYN, bool PER>
+__global__ void __launch_bounds__(PIPE_THREADS, PIPE_CTAS_PER_SM) k_self_propelled_p(
+    const __grid_constant__ DevParams p, const int *__restrict__ tstart, const unsigned int *__restrict__ idflag,
+    const real2 *__restrict__ pos_in, real *__restrict__ ang, real2 *__restrict__ pos_out, real2 *__restrict__ force,
+    const real *__restrict__ noise, unsigned long long step, const __grid_constant__ MoverSink ms) {
+  if (!ms.flags[FLAG_RAN]) return;
+  pipe_for_each_particle<DYN, PER>(p, tstart, pos_in, ms.cell, false, ms.flags + FLAG_WORK0,
+    [&](int k) { prefetch_l1(ang + k); prefetch_l1(idflag + k); },
+    [&](int k, real2 r, int c, bool active, real2 F) {
+      const unsigned int id = idflag[k] & ~MAVI_INACTIVE_BIT;
+      if (active && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
+      force[k] = F;
+      if ((int)id < p.n_count) self_propelled_update<DYN>(p, r, F, ang, k, id, noise, step);
+      if (active) {
+        real vx = 0.0, vy = 0.0;
+        apply_walls<false>(p, r.x, r.y, vx, vy, p.particle_radius);
+        note_if_moved(p, ms, k, c, r.x, r.y, false, F, [&] { return make_real2(ang[k], 0.0); });
+      }
+      pos_out[k] = r;
+    });
 }
 
 template <int DYN, bool PER>
@@ -1376,7 +1694,26 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p_in, const DevArrays 
 #define ARGS2 p, a.tstart, a.pos[1], a.vel, a.force_old, a.force, a.force_old, a.pos[0], a.fix_idx, a.fix_pos, ms
 #define CALL2(D, P) MAVI_LAUNCH(c, (k_newton_b2<D, P, false, 4>), grid2(p), TPB, PASS2_SMEM, ARGS2)
 #define CALL2C(D, P) MAVI_LAUNCH(c, (k_newton_b2<D, P, true, 4>), grid2(p), TPB, PASS2_SMEM, ARGS2)
-    if (carry) {
+    // pipelined persistent kernels (default); more than the 48 KB a kernel gets by default: opt in once per instantiation
+#define CALLP_(D, P, CARRYV)                                                                                        \
+  do {                                                                                                              \
+    static const cudaError_t attr_ = cudaFuncSetAttribute((const void *)k_newton_p<D, P, CARRYV>,                   \
+                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);  \
+    (void)attr_;                                                                                                    \
+    MAVI_LAUNCH(c, (k_newton_p<D, P, CARRYV>), grid_pipe(p), PIPE_THREADS, PIPE_SMEM, ARGS2);                       \
+  } while (0)
+#define CALLP(D, P) CALLP_(D, P, false)
+#define CALLPC(D, P) CALLP_(D, P, true)
+    if (!(c.flags & MAVI_FLAG_LEGACY_STAGING)) {
+      if (carry) {
+        ms.chg = a.chg;
+        if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALLPC);
+        else MAVI_DISPATCH2(MAVI_DYN_HARMTRUNC, p.periodic, CALLPC);
+      } else {
+        if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALLP);
+        else MAVI_DISPATCH2(MAVI_DYN_HARMTRUNC, p.periodic, CALLP);
+      }
+    } else if (carry) {
       ms.chg = a.chg;
       if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALL2C);
       else MAVI_DISPATCH2(MAVI_DYN_HARMTRUNC, p.periodic, CALL2C);
@@ -1386,6 +1723,9 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p_in, const DevArrays 
     }
 #undef CALL2
 #undef CALL2C
+#undef CALLP_
+#undef CALLP
+#undef CALLPC
 #undef ARGS2
   } else {
     if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALL);
@@ -1436,8 +1776,21 @@ void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArra
   const MoverSink ms = mover_sink(a);
   if (!allp) {
 #define CALL2(D, P) MAVI_LAUNCH(c, (k_self_propelled2<D, P>), grid2(p), TPB, PASS2_SMEM, p, a.tstart, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms)
-    if (p.dynamics == MAVI_DYN_SZABO) MAVI_DISPATCH2(MAVI_DYN_SZABO, p.periodic, CALL2);
-    else MAVI_DISPATCH2(MAVI_DYN_RTP, p.periodic, CALL2);
+#define CALLP(D, P)                                                                                                 \
+  do {                                                                                                              \
+    static const cudaError_t attr_ = cudaFuncSetAttribute((const void *)k_self_propelled_p<D, P>,                   \
+                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);  \
+    (void)attr_;                                                                                                    \
+    MAVI_LAUNCH(c, (k_self_propelled_p<D, P>), grid_pipe(p), PIPE_THREADS, PIPE_SMEM, p, a.tstart, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms); \
+  } while (0)
+    if (!(c.flags & MAVI_FLAG_LEGACY_STAGING)) {
+      if (p.dynamics == MAVI_DYN_SZABO) MAVI_DISPATCH2(MAVI_DYN_SZABO, p.periodic, CALLP);
+      else MAVI_DISPATCH2(MAVI_DYN_RTP, p.periodic, CALLP);
+    } else {
+      if (p.dynamics == MAVI_DYN_SZABO) MAVI_DISPATCH2(MAVI_DYN_SZABO, p.periodic, CALL2);
+      else MAVI_DISPATCH2(MAVI_DYN_RTP, p.periodic, CALL2);
+    }
+#undef CALLP
 #undef CALL2
     MAVI_LAUNCH(c, k_apply_pos_fixes, 1, 32, 0, a.flags, a.fix_idx, a.fix_pos, a.pos[1]);  // no fix-ups here: step counter only
     return;

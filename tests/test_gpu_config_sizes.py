@@ -22,7 +22,13 @@ def _noise(n, steps, seed):
     return np.random.default_rng(seed).standard_normal((steps, n))
 
 
-def _cells_equal(g, o):
+def _cells_equal(g, o, rebin=False):
+    """Cell assignment and per-cell counts, bit-exact.  After steps the reference's Chunks are STALE (binned at the start
+    of the last step, src/integration.jl:507-515) while the device layout is already the fresh binning of the final
+    positions: rebin=True runs update_chunks! on both sides first."""
+    if rebin:
+        g.update_chunks()
+        o.update_chunks()
     cg, ng = g.download_cells()
     co, no = o.download_cells()
     return np.array_equal(cg, co) and np.array_equal(ng, no)
@@ -44,7 +50,7 @@ def test_c2_lj_one_million_matches_oracle(cuda_lib):
     assert np.abs(g.state.pos - o.pos()).max() / L < 1e-12
     assert H.rel_err(g.state.vel, o.second()) < 1e-12
     assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-12
-    assert _cells_equal(g, o)
+    assert _cells_equal(g, o, rebin=True)
     sg, ig = g.download_cell_lists()
     so, io = o.download_cell_lists()
     assert np.array_equal(sg, so) and np.array_equal(ig, io)  # chunk_particles: ascending ids inside every cell
@@ -62,7 +68,7 @@ def test_c2_harmtrunc_one_million_rigid_matches_oracle(cuda_lib):
     assert np.abs(g.state.pos - o.pos()).max() / case["geom"].length < 1e-12
     assert H.rel_err(g.state.vel, o.second()) < 1e-12
     assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-12
-    assert _cells_equal(g, o)
+    assert _cells_equal(g, o, rebin=True)
 
 
 def test_c3_szabo_one_million_matches_oracle(cuda_lib):
@@ -78,7 +84,7 @@ def test_c3_szabo_one_million_matches_oracle(cuda_lib):
     assert np.abs(g.state.pos - o.pos()).max() / case["geom"].length < 1e-12
     assert np.abs(g.state.pol_angle - o.second()).max() < 1e-11
     assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-12
-    assert _cells_equal(g, o)
+    assert _cells_equal(g, o, rebin=True)
 
 
 def test_c4_rings_100k_matches_oracle(cuda_lib):
@@ -167,23 +173,29 @@ def test_rings_with_circle_obstacles_matches_oracle(cuda_lib, main_wall):
 
 def test_headline_16m_three_steps_match_oracle(cuda_lib):
     """The bench.py workload itself (LJ lattice 4000 x 4000 = 16M, periodic, 3600 x 3600 chunks, dt = 0.001, |v| <= 0.2):
-    3 newton_step!s (first pass + two carried steps) against the Threaded oracle.  Needs ~8 GB of host memory."""
+    3 newton_step!s (first pass + two carried steps) against the Threaded oracle.  Needs ~8 GB of host memory.
+    The lattice is PERFECT, so net forces are cancellation residues (|F| ~ 1e-2 of one pair force): the force error is
+    taken relative to max(|F|_inf, one pair force at the lattice spacing) (SURVEY.md 7 "parity metric under cancellation");
+    the plain norm-wise figure is bounded at 1e-11."""
     import bench
     w = bench.lj_workload(pkg, 4000, 4000)
-    case = dict(mk=lambda: pkg.SecondLawState(pos=w["pos"], vel=w["vel"]), space=w["space"], dyn=w["dyn"],
+    case = dict(mk=lambda: pkg.SecondLawState(pos=w["pos"].copy(), vel=w["vel"].copy()), space=w["space"], dyn=w["dyn"],
                 int_cfg=w["int_cfg"], geom=w["geom"])
     g = H.make_gpu(case)
     g.step(3)
-    g.sync_to_host()          # downloads into fresh arrays?  no: state arrays are the uploaded ones -> copy first
-    gp, gv, gf = g.state.pos.copy(), g.state.vel.copy(), g.get_forces()
+    g.sync_to_host()
+    gp, gv, gf = g.state.pos, g.state.vel, g.get_forces()
+    g.update_chunks()
     cg, ng = g.download_cells()
     g.close()
-    w = bench.lj_workload(pkg, 4000, 4000)
-    case["mk"] = lambda: pkg.SecondLawState(pos=w["pos"], vel=w["vel"])
     o = H.make_oracle(case, threads=THREADS)
     o.step(3)
+    of = o.get_forces()
     assert np.abs(gp - o.pos()).max() / w["geom"].length < 1e-12
     assert H.rel_err(gv, o.second()) < 1e-12
-    assert H.rel_err(gf, o.get_forces()) < 1e-12
+    df = np.abs(gf - of).max()
+    assert df / max(np.abs(of).max(), bench.lj_pair_force_scale(pkg)) < 1e-12
+    assert df / np.abs(of).max() < 1e-11
+    o.update_chunks()
     co, no = o.download_cells()
     assert np.array_equal(cg, co) and np.array_equal(ng, no)

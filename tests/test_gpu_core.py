@@ -344,7 +344,8 @@ def test_repair_paths_agree(cuda_lib, flag):
 def _with_flags(case, flags):
     ic = case["int_cfg"]
     case = dict(case)
-    case["int_cfg"] = pkg.IntCfg(dt=ic.dt, chunks_cfg=ic.chunks_cfg, device=pkg.CUDADevice(flags=flags))
+    import dataclasses
+    case["int_cfg"] = pkg.IntCfg(dt=ic.dt, chunks_cfg=ic.chunks_cfg, device=dataclasses.replace(ic.device, flags=flags))
     return case
 
 
@@ -412,6 +413,61 @@ def test_small_blocks_agree(cuda_lib, dyn, wall):
     b.sync_to_host()
     assert np.array_equal(a.state.pos, b.state.pos) and np.array_equal(a.state.vel, b.state.vel)
     assert np.array_equal(a.get_forces(), b.get_forces())
+
+
+@pytest.mark.parametrize("kind", ["lj_periodic_hot", "harm_rigid", "force_walls", "masked", "lj_small_grid", "lj_dense", "szabo", "rtp"])
+def test_pipelined_kernels_match_legacy_staging(cuda_lib, kind):
+    """The persistent producer/consumer force kernels (bulk-async staging through mbarriers, the default) must be
+    BIT-identical to the round-1 kernels (MAVI_FLAG_LEGACY_STAGING: one CTA per tile block, cp.async behind CTA barriers):
+    same neighbour order, same arithmetic — through re-binning, wall fix-ups, masks, chunk splitting (small blocks), dense
+    columns that do not fit the staging area, and calc_forces! calls."""
+    LEG = pkg.capi.FLAG_LEGACY_STAGING
+    extra = 0
+    sp = kind in ("szabo", "rtp")
+    if kind == "lj_periodic_hot":
+        case = H.newton_case(nx=70, ny=66, wall="periodic", jitter=0.3, vmax=3.0, dt=0.002)
+        extra = pkg.capi.FLAG_SMALL_BLOCKS   # many work items per tile row: the work counter and both buffers cycle
+    elif kind == "harm_rigid":
+        case = H.newton_case(nx=40, ny=40, dyn=DYNS["harm"], wall="rigid", jitter=0.3, vmax=3.0, dt=0.002)
+    elif kind == "force_walls":
+        case = _wall_force_case(False)
+    elif kind == "masked":
+        mask = np.ones(32 * 32, dtype=bool)
+        mask[::5] = False
+        case = H.newton_case(nx=32, ny=32, dyn=DYNS["harm"], wall="periodic", jitter=0.3, vmax=2.0, dt=0.002, active_mask=mask)
+    elif kind == "lj_small_grid":   # 2-row / 2-column periodic wrap
+        case = H.newton_case(nx=6, ny=6, wall="periodic", jitter=0.3, vmax=1.0, dt=0.002, cells=(2, 2))
+    elif kind == "lj_dense":        # ~60 particles per cell: several chunks per block, some columns beyond the staging area
+        case = H.newton_case(nx=96, ny=96, dyn=DYNS["harm"], wall="periodic", jitter=0.3, vmax=1.0, dt=0.001, cells=(12, 12))
+    else:
+        case = H.sp_case(kind, nx=48, ny=40, rot_diff=0.05)
+    a = H.make_gpu(_with_flags(case, extra))
+    b = H.make_gpu(_with_flags(case, extra | LEG))
+    n = len(a.state.pos)
+    rng = np.random.default_rng(17)
+    for steps in (1, 2, 37, 120):
+        noise = None
+        if kind == "szabo":
+            noise = rng.standard_normal((steps, n))
+        elif kind == "rtp":
+            noise = rng.random((steps, 2 * n))
+            noise[:, 0::2] *= 0.02
+        a.step(steps, noise)
+        b.step(steps, noise)
+        a.sync_to_host()
+        b.sync_to_host()
+        assert np.array_equal(a.state.pos, b.state.pos)
+        assert np.array_equal(a.state.second, b.state.second)
+        assert np.array_equal(a.get_forces(), b.get_forces())
+    if not sp:
+        a.calc_forces()
+        b.calc_forces()
+        a.step(40)
+        b.step(40)
+        a.sync_to_host()
+        b.sync_to_host()
+        assert np.array_equal(a.state.pos, b.state.pos) and np.array_equal(a.get_forces(), b.get_forces())
+    assert np.array_equal(a.download_cells()[0], b.download_cells()[0])
 
 
 def test_kernels_actually_launch(cuda_lib):
