@@ -521,9 +521,34 @@ int Handle::run_steps(long long nsteps, const real *noise_dev, size_t stride) {
   int st;
   while (done_total < nsteps) {
     if ((st = pending_out_of_grid())) return st;
-    if (p.dynamics == MAVI_DYN_RINGS || p.slab) {  // these paths synchronise every step themselves
+    if (p.dynamics == MAVI_DYN_RINGS) {
+      // Rings: up to SYNC_EVERY steps enqueued back to back; an index-tile overflow latches, the device step counter
+      // tells how many steps ran, the host clock is rolled back and the rest is re-run with larger tiles
+      const int batch = (int)((nsteps - done_total) < SYNC_EVERY ? (nsteps - done_total) : SYNC_EVERY);
+      long long snap_steps[SYNC_EVERY + 1];
+      double snap_time[SYNC_EVERY + 1];
+      snap_steps[0] = num_steps;
+      snap_time[0] = time;
+      const int c0 = steps_seen;
+      for (int s = 0; s < batch; s++) {
+        if ((st = rings_step(this, noise_dev ? noise_dev + (size_t)(done_total + s) * stride : nullptr))) return st;
+        snap_steps[s + 1] = num_steps;
+        snap_time[s + 1] = time;
+      }
+      st = check_device_flags();
+      int done = flags_host[FLAG_STEPS] - c0;
+      if (done < 0 || done > batch) done = batch;
+      steps_seen = flags_host[FLAG_STEPS];
+      num_steps = snap_steps[done];
+      time = snap_time[done];
+      done_total += done;
+      if (st) return st;
+      if (flags_host[FLAG_OVERFLOW] && (st = rings_grow_tiles(this))) return st;
+      continue;
+    }
+    if (p.slab) {  // this path synchronises by itself (slab_sync_counts)
       const real *nz = noise_dev ? noise_dev + (size_t)done_total * stride : nullptr;
-      st = p.slab ? slab_step_once(this, nz) : rings_step(this, nz);
+      st = slab_step_once(this, nz);
       if (st) return st;
       done_total += 1;
       // slab steps are enqueued without host synchronisation; counts / overflow word every SYNC_EVERY steps and at the end

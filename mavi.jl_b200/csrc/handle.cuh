@@ -94,6 +94,7 @@ int rings_lower(Handle *h, const MaviParams *mp);
 int rings_allocate(Handle *h);
 int rings_upload_finish(Handle *h);
 int rings_step(Handle *h, const real *noise_dev);
+int rings_grow_tiles(Handle *h);
 int rings_calc_forces(Handle *h);
 int rings_download_info(Handle *h, void *areas, void *cms, void *cont_pos);
 int rings_download_state(Handle *h, void *pos, void *second);

@@ -624,6 +624,10 @@ __device__ __noinline__ void note_moved_slow(const DevParams &p, const MoverSink
   if (p.slab) {
     const int lc = div_rows(p, c_new);
     if (lc == 0 || lc == p.num_cols - 1) {  // crossed into a halo column: goes to the neighbour rank, not into a tile
+      if (p.blk_mode == 1) {  // interior block of the pipelined slab step: the emigrant buffers are already on their way
+        atomicOr(&ms.flags[FLAG_ERR], ERRBIT_OUT_OF_GRID);  // >= 3 cell columns in ONE step: the run has blown up
+        return;
+      }
       const int d = lc == 0 ? 0 : 1;
       const int i = atomicAdd(&ms.flags[FLAG_NEM0 + d], 1);
       if (i < ms.em_cap) {
@@ -657,10 +661,29 @@ __device__ __noinline__ void note_moved_slow(const DevParams &p, const MoverSink
 // `fixed`: walls! moved the particle (periodic wrap, slippery projection) after the pair pass read its position.
 // second_of(): the particle's second state record (velocity / angle) after this step — only evaluated for a particle
 // that left its cell, to fill the emigrant record together with `force`.
-template <typename SecondF>
+// in_cell(x, y): the exact "update_particle_chunk! would bin it into c_old again" test — still_in_cell() itself (InCellExact)
+// or the same comparisons against per-chunk tables of the cell edges (InCellTab, pipelined kernels).
+struct InCellExact {
+  const DevParams &p;
+  int c;
+  __device__ __forceinline__ bool operator()(double x, double y) const { return still_in_cell(p, x, y, c); }
+};
+struct InCellTab {  // edges of the particle's cell as axis_in_cell() compares them: lo <= t < hi on both axes
+  const DevParams &p;
+  double xlo, xhi, ylo, yhi;
+  __device__ __forceinline__ bool operator()(double x, double y) const {
+    const double tx = x - p.grid_bl[0], ty = -y + p.grid_bl[1] + p.grid_h;
+    return tx >= xlo && tx < xhi && ty >= ylo && ty < yhi;
+  }
+};
+struct InCellNone {
+  __device__ __forceinline__ bool operator()(double, double) const { return true; }
+};
+
+template <typename SecondF, typename InCell>
 __device__ __forceinline__ void note_if_moved(const DevParams &p, const MoverSink &ms, int k, int c_old, real x,
-                                              real y, bool fixed, real2 force, SecondF &&second_of) {
-  if (still_in_cell(p, x, y, c_old)) {
+                                              real y, bool fixed, real2 force, SecondF &&second_of, const InCell &in_cell) {
+  if (in_cell(x, y)) {
     if (fixed) note_changed_cells(p, ms, c_old, c_old);
     return;
   }
@@ -1169,7 +1192,7 @@ __device__ __forceinline__ void for_each_block_particle(const DevParams &p, cons
     if (i < p.n - p.n_active) {
       const int k = p.tail_base + i;
       pre(k);
-      body(k, pos[k], 0, false, make_real2(0.0, 0.0));
+      body(k, pos[k], 0, false, make_real2(0.0, 0.0), InCellNone{});
     }
     return;
   }
@@ -1196,7 +1219,8 @@ __device__ __forceinline__ void for_each_block_particle(const DevParams &p, cons
         real fx = 0.0, fy = 0.0;
         if (mi) chunk_walk<DYN, true>(p, ck, s_pos, jj, lr, self, r, fx, fy);
         else chunk_walk<DYN, false>(p, ck, s_pos, jj, lr, self, r, fx, fy);
-        body(k, r, (cs - 1 + jj) * p.num_rows + r0 + lr - 1, true, make_real2(fx, fy));
+        const int cc = (cs - 1 + jj) * p.num_rows + r0 + lr - 1;
+        body(k, r, cc, true, make_real2(fx, fy), InCellExact{p, cc});
       }
     } else {
       // a single column too dense for the staging area: per-thread walk over the global arrays
@@ -1207,7 +1231,7 @@ __device__ __forceinline__ void for_each_block_particle(const DevParams &p, cons
         const int c = cell[k];
         real fx = 0.0, fy = 0.0;
         for_each_neighbor(p, tstart, c, k, [&](int j) { accumulate_pair<DYN, PER>(p, r, __ldg(pos + j), fx, fy); });
-        body(k, r, c, true, make_real2(fx, fy));
+        body(k, r, c, true, make_real2(fx, fy), InCellExact{p, c});
       }
     }
     cs += nc;
@@ -1245,6 +1269,10 @@ struct PChunk {
   int nc, use_mi, nown, ok, tr, cs;
   int src_t1, lt1;  // !ok: the one column that does not fit the staging area (walked in global memory)
   int gbase[PG_MAX + 2];
+  int pad_;
+  // edges of the cells as axis_in_cell() compares them (lo <= t < hi): staged column j / cell row lr-1 of the tile
+  double2 xb[PG_MAX + 2];
+  double2 yb[MAVI_TR];
   int2 cwin[PG_MAX + 2][MAVI_TR];  // [j][lr-1] = (first staged index of cell row lr-1, end of cell row lr+1)
 };
 constexpr int PCH_BYTES = (sizeof(PChunk) + 15) / 16 * 16;
@@ -1342,6 +1370,25 @@ __device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restr
     ck->src_t1 = st1;
     ck->lt1 = lt1;
     if (PIPE_BULK && bal) mbar_expect_tx(full_bar, (unsigned int)total * (unsigned int)sizeof(real2));
+  }
+  {  // ---- cell edges for the exact "still in its cell" test of the epilogue (see axis_in_cell / still_in_cell)
+    if (in) {
+      int g = cs - 1 + j;  // staged local column -> global column
+      if (g < 0) g += Cn;
+      else if (g >= Cn) g -= Cn;
+      if (p.slab) {
+        g = g + p.col_lo - 1;
+        if (g < 0) g += p.gcols;
+        else if (g >= p.gcols) g -= p.gcols;
+      }
+      const double lo = g == 0 ? nextafter(-p.cl, 1.0) : __dmul_ru((double)g, p.cl);  // t > -c  <=>  t >= nextafter(-c, +inf)
+      const double hi = __dmul_ru((double)((g == p.gcols - 1) ? p.gcols + 1 : g + 1), p.cl);
+      ck->xb[j] = make_double2(lo, hi);
+    }
+    const int row = r0 + lane;
+    const double lo = row == 0 ? nextafter(-p.ch, 1.0) : __dmul_ru((double)row, p.ch);
+    const double hi = __dmul_ru((double)((row == R - 1) ? R + 1 : row + 1), p.ch);
+    ck->yb[lane] = make_double2(lo, hi);
   }
   __syncwarp();
   if (bal) {
@@ -1446,7 +1493,7 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
     for (int i = (int)blockIdx.x * PIPE_CT + (int)threadIdx.x; i < ntail; i += (int)gridDim.x * PIPE_CT) {
       const int k = p.tail_base + i;
       pre(k);
-      body(k, pos[k], 0, false, make_real2(0.0, 0.0));
+      body(k, pos[k], 0, false, make_real2(0.0, 0.0), InCellNone{});
     }
   }
   for (int kc = 0;; kc++) {
@@ -1470,7 +1517,8 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
         real fx = 0.0, fy = 0.0;
         if (mi) chunk_walk<DYN, true>(p, ck, s_pos, jj, lr, self, r, fx, fy);
         else chunk_walk<DYN, false>(p, ck, s_pos, jj, lr, self, r, fx, fy);
-        body(k, r, (cs - 1 + jj) * p.num_rows + r0 + lr - 1, true, make_real2(fx, fy));
+        const double2 xe = ck->xb[jj], ye = ck->yb[lr - 1];
+        body(k, r, (cs - 1 + jj) * p.num_rows + r0 + lr - 1, true, make_real2(fx, fy), InCellTab{p, xe.x, xe.y, ye.x, ye.y});
       }
     } else {
       // a single column too dense for the staging area: per-thread walk over the global arrays
@@ -1481,7 +1529,7 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
         const int c = cell[k];
         real fx = 0.0, fy = 0.0;
         for_each_neighbor(p, tstart, c, k, [&](int jn) { accumulate_pair<DYN, PER>(p, r, __ldg(pos + jn), fx, fy); });
-        body(k, r, c, true, make_real2(fx, fy));
+        body(k, r, c, true, make_real2(fx, fy), InCellExact{p, c});
       }
     }
     __syncwarp();
@@ -1506,7 +1554,7 @@ __global__ void __launch_bounds__(TPB) k_force_only2(const __grid_constant__ Dev
                               const int *__restrict__ cell, const real2 *__restrict__ pos,
                               real2 *__restrict__ force, int with_walls) {
   for_each_block_particle<DYN, PER>(p, tstart, pos, cell, false, [](int) {},
-    [&](int k, real2 r, int, bool active, real2 F) {
+    [&](int k, real2 r, int, bool active, real2 F, auto) {
       if (active && with_walls && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
       force[k] = F;
     });
@@ -1519,7 +1567,7 @@ __global__ void __launch_bounds__(TPB) k_newton_a2(const __grid_constant__ DevPa
                             int *__restrict__ flags) {
   if (!flags[FLAG_RAN]) return;
   for_each_block_particle<DYN, PER>(p, tstart, pos_in, cell, false, [&](int k) { prefetch_l1(vel + k); },
-    [&](int k, real2 r, int, bool active, real2 F) {
+    [&](int k, real2 r, int, bool active, real2 F, auto) {
       if (active && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
       bool big;
       pos_out[k] = verlet_drift(p, r, vel[k], F, big);
@@ -1531,7 +1579,7 @@ __global__ void __launch_bounds__(TPB) k_newton_a2(const __grid_constant__ DevPa
 // pre(k) / body(k, r, cell, active, F) of the second Newton pass
 #define MAVI_NEWTON_B_LAMBDAS \
     [&](int k) { prefetch_l1(vel + k); prefetch_l1(f1 + k); }, \
-    [&](int k, real2 r, int c, bool active, real2 F) { \
+    [&](int k, real2 r, int c, bool active, real2 F, auto in_cell) { \
       real2 v = vel[k]; \
       const real2 Fo = f1[k]; \
       v.x = v.x + p.hdt * (F.x + Fo.x); \
@@ -1545,7 +1593,7 @@ __global__ void __launch_bounds__(TPB) k_newton_a2(const __grid_constant__ DevPa
           fix_idx[m] = k; \
           fix_pos[m] = r; \
         } \
-        note_if_moved(p, ms, k, c, r.x, r.y, fixed, F, [&] { return v; }); \
+        note_if_moved(p, ms, k, c, r.x, r.y, fixed, F, [&] { return v; }, in_cell); \
       } \
       vel[k] = v; \
       f2[k] = F; \
@@ -1592,7 +1640,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_CTAS_PER_SM) k_self_propell
   if (!ms.flags[FLAG_RAN]) return;
   pipe_for_each_particle<DYN, PER>(p, tstart, pos_in, ms.cell, false, ms.flags + FLAG_WORK0,
     [&](int k) { prefetch_l1(ang + k); prefetch_l1(idflag + k); },
-    [&](int k, real2 r, int c, bool active, real2 F) {
+    [&](int k, real2 r, int c, bool active, real2 F, auto in_cell) {
       const unsigned int id = idflag[k] & ~MAVI_INACTIVE_BIT;
       if (active && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
       force[k] = F;
@@ -1600,7 +1648,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, PIPE_CTAS_PER_SM) k_self_propell
       if (active) {
         real vx = 0.0, vy = 0.0;
         apply_walls<false>(p, r.x, r.y, vx, vy, p.particle_radius);
-        note_if_moved(p, ms, k, c, r.x, r.y, false, F, [&] { return make_real2(ang[k], 0.0); });
+        note_if_moved(p, ms, k, c, r.x, r.y, false, F, [&] { return make_real2(ang[k], 0.0); }, in_cell);
       }
       pos_out[k] = r;
     });
@@ -1615,7 +1663,7 @@ __global__ void __launch_bounds__(TPB) k_self_propelled2(const __grid_constant__
   if (!ms.flags[FLAG_RAN]) return;
   for_each_block_particle<DYN, PER>(p, tstart, pos_in, ms.cell, false,
     [&](int k) { prefetch_l1(ang + k); prefetch_l1(idflag + k); },
-    [&](int k, real2 r, int c, bool active, real2 F) {
+    [&](int k, real2 r, int c, bool active, real2 F, auto in_cell) {
       const unsigned int id = idflag[k] & ~MAVI_INACTIVE_BIT;
       if (active && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
       force[k] = F;
@@ -1623,7 +1671,7 @@ __global__ void __launch_bounds__(TPB) k_self_propelled2(const __grid_constant__
       if (active) {
         real vx = 0.0, vy = 0.0;
         apply_walls<false>(p, r.x, r.y, vx, vy, p.particle_radius);
-        note_if_moved(p, ms, k, c, r.x, r.y, false, F, [&] { return make_real2(ang[k], 0.0); });
+        note_if_moved(p, ms, k, c, r.x, r.y, false, F, [&] { return make_real2(ang[k], 0.0); }, in_cell);
       }
       pos_out[k] = r;
     });

@@ -6,6 +6,7 @@
 //   k_rings_ring : update_cms! -> update_continuos_pos! -> calc_area -> springs -> area_forces! -> update! -> walls!
 //                                                                                              (warp per ring)
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -49,9 +50,10 @@ __global__ void __launch_bounds__(TPB) k_rings_pair(const __grid_constant__ DevP
                                                     const int *__restrict__ perm, const int *__restrict__ cell,
                                                     const unsigned int *__restrict__ idflag,
                                                     const real2 *__restrict__ pos, real2 *__restrict__ fpair,
-                                                    int with_walls) {
+                                                    int with_walls, const int *__restrict__ flags) {
   extern __shared__ real s_inter[];  // [num_types^2][7]
   const DevRings &R = p.rings;
+  if (flags[FLAG_OVERFLOW]) return;  // the index tiles of this step overflowed: the step does not run (rings_run_steps re-runs it)
   for (int t = threadIdx.x; t < R.num_types * R.num_types * 7; t += blockDim.x) s_inter[t] = R.interaction[t];
   __syncthreads();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -105,8 +107,10 @@ __global__ void __launch_bounds__(TPB) k_rings_neighbors(const __grid_constant__
                                                          const int *__restrict__ perm, const int *__restrict__ cell,
                                                          const unsigned int *__restrict__ idflag,
                                                          const real2 *__restrict__ pos, int type_all, real tol,
-                                                         int *__restrict__ count, int *__restrict__ list) {
+                                                         int *__restrict__ count, int *__restrict__ list,
+                                                         const int *__restrict__ flags) {
   const DevRings &R = p.rings;
+  if (flags[FLAG_OVERFLOW]) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n) return;
   int cnt = 0;
@@ -153,14 +157,15 @@ __global__ void __launch_bounds__(RING_WARPS * 32) k_rings_ring(
     const __grid_constant__ DevParams p, real2 *__restrict__ pos, real *__restrict__ pol,
     const real2 *__restrict__ fpair, real2 *__restrict__ force, real2 *__restrict__ cont_pos,
     real *__restrict__ areas, real2 *__restrict__ cms, const real *__restrict__ noise, unsigned long long step,
-    int prime_cms) {
+    int prime_cms, int *__restrict__ flags) {
   __shared__ real2 s_pos[RING_WARPS][RING_NMAX];
   __shared__ real2 s_cont[RING_WARPS][RING_NMAX];
   __shared__ real2 s_vel[RING_WARPS][RING_NMAX];
   const DevRings &R = p.rings;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int ring = blockIdx.x * RING_WARPS + w;
-  if (ring >= R.num_rings) return;
+  if (ring >= R.num_rings || flags[FLAG_OVERFLOW]) return;
+  if (MODE == 1 && ring == 0 && lane == 0) flags[FLAG_STEPS] += 1;  // steps that really ran (device-side step counter)
   const int t = ring_type(R, ring);
   const int np = R.num_particles[t];
   const int base = ring * R.n_max;
@@ -272,6 +277,140 @@ __global__ void __launch_bounds__(RING_WARPS * 32) k_rings_ring(
         nz = (p.rng_mode == MAVI_RNG_HOST_NOISE) ? (noise ? noise[ring] : 0.0) : philox_normal(p.seed, (unsigned int)ring, step);
       pol[ring] = theta + (1.0 / R.relax_time[t] * asin(cross_prod) * p.dt + sqrt(2.0 * drot * p.dt) * nz);
     }
+  }
+}
+
+
+// THREAD per ring (rings of up to RING_T_NMAX particles; the default for the small rings of the reference's fixtures and
+// BASELINE config C4).  The warp-per-ring kernel above keeps 10 of 32 lanes busy on 10-particle rings and runs its four
+// order-sensitive sums (cms, unwrap, shoelace area, mean velocity) on ONE lane while 31 wait: 200 us for 100 k rings
+// (profiles/r01_ncu_szabo_rings.md).  Here a lane owns a ring and walks its particles in the reference's order, so all
+// sums keep the reference's accumulation order and all 32 lanes work; consecutive lanes read consecutive rings (stride
+// n_max positions: every 32-byte sector is used by two consecutive iterations out of L1).
+constexpr int RING_T_NMAX = 32;
+constexpr int RING_T_TPB = 128;
+
+template <bool PER, int MODE>
+__global__ void __launch_bounds__(RING_T_TPB) k_rings_ring_t(
+    const __grid_constant__ DevParams p, real2 *__restrict__ pos, real *__restrict__ pol,
+    const real2 *__restrict__ fpair, real2 *__restrict__ force, real2 *__restrict__ cont_pos,
+    real *__restrict__ areas, real2 *__restrict__ cms, const real *__restrict__ noise, unsigned long long step,
+    int prime_cms, int *__restrict__ flags) {
+  const DevRings &R = p.rings;
+  const int ring = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ring >= R.num_rings || flags[FLAG_OVERFLOW]) return;
+  if (MODE == 1 && ring == 0) flags[FLAG_STEPS] += 1;  // steps that really ran (device-side step counter)
+  const int t = ring_type(R, ring);
+  const int np = R.num_particles[t];
+  const int base = ring * R.n_max;
+  // ---- update_cms! (src/rings/integration.jl:366-372) runs FIRST in step!: it still sees last step's continuos_pos
+  if (MODE == 1) {
+    const real2 *src = PER ? cont_pos : pos;
+    real sx = src[base].x, sy = src[base].y;
+    for (int i = 1; i < np; i++) {
+      const real2 c = src[base + i];
+      sx += c.x;
+      sy += c.y;
+    }
+    cms[ring] = make_real2(sx / np, sy / np);
+  }
+  // ---- update_continuos_pos! (:118-138) + calc_area (:103-116) + (constructor) update_cms!: one walk, sequential sums
+  const real2 p0v = pos[base];
+  real2 c_prev = p0v, r_prev = p0v;  // continuos_pos / rings_pos of particle i-1
+  const real2 c0 = p0v;
+  real area = 0.0, sx = p0v.x, sy = p0v.y;
+  if (PER) cont_pos[base] = c0;
+  for (int i = 1; i < np; i++) {
+    const real2 ri = pos[base + i];
+    real2 ci = ri;
+    if (PER) {
+      const real dx = min_image<true>(ri.x - r_prev.x, p.half[0], p.size[0]);
+      const real dy = min_image<true>(ri.y - r_prev.y, p.half[1], p.size[1]);
+      ci = make_real2(c_prev.x + dx, c_prev.y + dy);
+      cont_pos[base + i] = ci;
+    }
+    area += c_prev.x * ci.y - c_prev.y * ci.x;
+    sx += ci.x;
+    sy += ci.y;
+    c_prev = ci;
+    r_prev = ri;
+  }
+  if (PER)
+    for (int i = np; i < R.n_max; i++) cont_pos[base + i] = pos[base + i];  // continuos_pos[:, ring] .= rings_pos[:, ring] first
+  area += c_prev.x * c0.y - c_prev.y * c0.x;
+  area = area / 2.0;
+  areas[ring] = area;
+  if (MODE == 0 && prime_cms) cms[ring] = make_real2(sx / np, sy / np);  // src/rings/rings.jl:280-283
+  // ---- forces! (:197-226): pair forces + springs (:79-97) + area_forces! (:140-195); update! (:300-351); walls!
+  const real k_spring = R.k_spring[t], l_spring = R.l_spring[t];
+  const real k_area = R.k_area[t], p0 = R.p0[t];
+  const real a0s = np * l_spring / p0;
+  const real fmod_area = k_area * (area - a0s * a0s);
+  const real vo = R.vo[t], mu = R.mobility[t];
+  const real theta = pol[ring];
+  real sn, cs;
+  sincos(theta, &sn, &cs);
+  const real pr = R.interaction[7 * (t * R.num_types + t) + 2] / 2.0;  // get_particle_radius of the ring type
+  auto spring = [&](real2 a, real2 b, real &ox, real &oy) {  // springs_force(p1 = a, p2 = b)
+    const real dx = min_image<PER>(a.x - b.x, p.half[0], p.size[0]);
+    const real dy = min_image<PER>(a.y - b.y, p.half[1], p.size[1]);
+    const real dist = sqrt(dx * dx + dy * dy);
+    const real c = (-k_spring * (dist - l_spring)) / dist;
+    ox = c * dx;
+    oy = c * dy;
+  };
+  const real2 r_last = pos[base + np - 1];
+  real2 rp = r_last, rc = p0v;  // previous / current particle (old positions: every new position is written after its last use)
+  real bx, by;                  // spring (i-1, i): computed once, used as "next" of i-1 and "previous" of i
+  spring(rp, rc, bx, by);
+  const real lbx = bx, lby = by;  // spring (np-1, 0)
+  real vcx = 0.0, vcy = 0.0;
+  real2 new_first = p0v;
+  for (int i = 0; i < np; i++) {
+    const real2 rn = (i == np - 1) ? p0v : pos[base + i + 1];
+    real2 F = fpair[base + i];
+    real ax, ay;
+    if (i == np - 1) { ax = lbx; ay = lby; }
+    else spring(rc, rn, ax, ay);  // spring i: +f on its first particle
+    F.x += ax; F.y += ay;
+    F.x -= bx; F.y -= by;         // spring i-1: -f on its second particle
+    const real dx = min_image<PER>(rn.x - rp.x, p.half[0], p.size[0]);
+    const real dy = min_image<PER>(rn.y - rp.y, p.half[1], p.size[1]);
+    F.x -= fmod_area * (dy / 2);
+    F.y -= fmod_area * (-dx / 2);
+    force[base + i] = F;
+    if (MODE == 1) {
+      const real vx = vo * cs + mu * F.x, vy = vo * sn + mu * F.y;
+      vcx += vx;
+      vcy += vy;
+      real x = rc.x + vx * p.dt, y = rc.y + vy * p.dt;
+      real dummy_vx = 0.0, dummy_vy = 0.0;
+      apply_walls<false>(p, x, y, dummy_vx, dummy_vy, pr);  // walls!(system), generic walls over the active ids
+      // pos[base+i-1 .. ] are no longer read: particle i-1 was "previous" for i only, held in rp; particle 0 is held in p0v
+      if (i == 0) new_first = make_real2(x, y);
+      else pos[base + i] = make_real2(x, y);
+    }
+    rp = rc;
+    rc = rn;
+    bx = ax;
+    by = ay;
+  }
+  if (MODE == 1) pos[base] = new_first;
+  for (int i = np; i < R.n_max; i++) force[base + i] = make_real2(0.0, 0.0);
+  if (MODE == 1) {
+    vcx /= np;
+    vcy /= np;
+    const real speed = sqrt(vcx * vcx + vcy * vcy);
+    real cross_prod = 0.0;
+    if (speed != 0.0) {
+      cross_prod = (cs * vcy - sn * vcx) / speed;
+      if (fabs(cross_prod) > 1.0) cross_prod = sign_d(cross_prod);
+    }
+    const real drot = R.rot_diff[t];
+    real nz = 0.0;
+    if (drot != 0.0)
+      nz = (p.rng_mode == MAVI_RNG_HOST_NOISE) ? (noise ? noise[ring] : 0.0) : philox_normal(p.seed, (unsigned int)ring, step);
+    pol[ring] = theta + (1.0 / R.relax_time[t] * asin(cross_prod) * p.dt + sqrt(2.0 * drot * p.dt) * nz);
   }
 }
 
@@ -477,18 +616,18 @@ static void launch_pair(Handle *h, bool with_walls) {
   const size_t smem = (size_t)p.rings.num_types * p.rings.num_types * 7 * sizeof(real);
   const int grid = (p.n + TPB - 1) / TPB;
   if (p.periodic) {
-    k_rings_pair<true><<<grid, TPB, smem, h->stream>>>(p, a.tstart, a.perm, a.cell, a.idflag, a.pos[0], a.force_old, (int)with_walls);
+    k_rings_pair<true><<<grid, TPB, smem, h->stream>>>(p, a.tstart, a.perm, a.cell, a.idflag, a.pos[0], a.force_old, (int)with_walls, a.flags);
   } else {
-    k_rings_pair<false><<<grid, TPB, smem, h->stream>>>(p, a.tstart, a.perm, a.cell, a.idflag, a.pos[0], a.force_old, (int)with_walls);
+    k_rings_pair<false><<<grid, TPB, smem, h->stream>>>(p, a.tstart, a.perm, a.cell, a.idflag, a.pos[0], a.force_old, (int)with_walls, a.flags);
   }
   h->launches++;
   RingsArrays &r = h->r;
   if (r.neigh_mode != MAVI_NEIGH_OFF && r.neigh_count) {  // neigh_clean! + neigh_update! of this forces! call
     int *list = r.neigh_mode == MAVI_NEIGH_LIST ? r.neigh_list : nullptr;
     if (p.periodic) {
-      RINGS_LAUNCH(h, (k_rings_neighbors<true>), grid, TPB, p, a.tstart, a.perm, a.cell, a.idflag, a.pos[0], r.neigh_all, (real)r.neigh_tol, r.neigh_count, list);
+      RINGS_LAUNCH(h, (k_rings_neighbors<true>), grid, TPB, p, a.tstart, a.perm, a.cell, a.idflag, a.pos[0], r.neigh_all, (real)r.neigh_tol, r.neigh_count, list, a.flags);
     } else {
-      RINGS_LAUNCH(h, (k_rings_neighbors<false>), grid, TPB, p, a.tstart, a.perm, a.cell, a.idflag, a.pos[0], r.neigh_all, (real)r.neigh_tol, r.neigh_count, list);
+      RINGS_LAUNCH(h, (k_rings_neighbors<false>), grid, TPB, p, a.tstart, a.perm, a.cell, a.idflag, a.pos[0], r.neigh_all, (real)r.neigh_tol, r.neigh_count, list, a.flags);
     }
   }
 }
@@ -500,8 +639,21 @@ static void launch_ring(Handle *h, int mode, const real *noise, int prime_cms) {
   const int grid = (p.rings.num_rings + RING_WARPS - 1) / RING_WARPS;
   if (grid == 0) return;
   const unsigned long long step = (unsigned long long)h->num_steps;
+  static const bool warp_kernel = getenv("MAVI_RINGS_WARP_KERNEL") != nullptr;  // A/B switch (tests): the warp-per-ring kernel
+  if (p.rings.n_max <= RING_T_NMAX && !warp_kernel) {
+    const int gt = (p.rings.num_rings + RING_T_TPB - 1) / RING_T_TPB;
+#define RING_CALL_T(PER, MODE) \
+  RINGS_LAUNCH(h, (k_rings_ring_t<PER, MODE>), gt, RING_T_TPB, p, a.pos[0], r.pol, a.force_old, a.force, r.cont_pos, r.areas, r.cms, noise, step, prime_cms, a.flags)
+    if (p.periodic) {
+      if (mode) RING_CALL_T(true, 1); else RING_CALL_T(true, 0);
+    } else {
+      if (mode) RING_CALL_T(false, 1); else RING_CALL_T(false, 0);
+    }
+#undef RING_CALL_T
+    return;
+  }
 #define RING_CALL(PER, MODE) \
-  RINGS_LAUNCH(h, (k_rings_ring<PER, MODE>), grid, RING_WARPS * 32, p, a.pos[0], r.pol, a.force_old, a.force, r.cont_pos, r.areas, r.cms, noise, step, prime_cms)
+  RINGS_LAUNCH(h, (k_rings_ring<PER, MODE>), grid, RING_WARPS * 32, p, a.pos[0], r.pol, a.force_old, a.force, r.cont_pos, r.areas, r.cms, noise, step, prime_cms, a.flags)
   if (p.periodic) {
     if (mode) RING_CALL(true, 1); else RING_CALL(true, 0);
   } else {
@@ -537,14 +689,31 @@ int rings_calc_forces(Handle *h) {
   return h->check_device_flags();
 }
 
+// One Rings step!, enqueued without host synchronisation.  If the index tiles overflow, the step latches FLAG_OVERFLOW and
+// it and every later enqueued step turn into no-ops (the ring-ordered state is untouched); FLAG_STEPS counts the steps
+// that really ran and Handle::run_steps grows the tiles and re-runs the rest.
 int rings_step(Handle *h, const real *noise_dev) {
-  int st = rings_bin(h);  // update_chunks_all! (after update_cms!, which only reads last step's continuos_pos)
-  if (st) return st;
+  DevParams &p = h->p;
+  DevArrays &a = h->a;
+  if (p.num_cells > 0) {  // update_chunks_all! (after update_cms!, which only reads last step's continuos_pos)
+    RINGS_TRY(h, cudaMemsetAsync(a.count, 0, ((size_t)p.num_cells + 2) * sizeof(int), h->stream));
+    launch_build_index_tiles(h->ctx(), p, a.pos[0], a.idflag, a.cell, a.count, a.tstart, a.perm, a.flags);
+  }
   launch_pair(h, true);
   launch_ring(h, 1, noise_dev, 0);
   h->num_steps += 1;  // src/rings/integration.jl:541-542
   h->time += h->dt_host;
-  return h->check_device_flags();
+  return MAVI_OK;
+}
+
+// after a latched overflow: larger index tiles, latch cleared
+int rings_grow_tiles(Handle *h) {
+  const int cap = ((int)std::ceil(h->flags_host[FLAG_MAXCOUNT] * 1.25 + 8.0) + 15) / 16 * 16;
+  int st = rings_alloc_tiles(h, cap > h->p.cap ? cap : h->p.cap + 16);
+  if (st) return st;
+  RINGS_TRY(h, cudaMemsetAsync(h->a.flags + FLAG_OVERFLOW, 0, sizeof(int), h->stream));
+  h->n_rebuilds++;
+  return MAVI_OK;
 }
 
 int rings_download_state(Handle *h, void *pos, void *second) {

@@ -300,7 +300,7 @@ int slab_halo_exchange(Handle *h, real2 *pos_buf, bool with_layout, cudaStream_t
 // Migration: the integrate kernel wrote the record of every particle that crossed into a halo column straight into
 // the emigrant buffer of that side (note_if_moved).  Ship both buffers (fixed capacity, the count travels separately)
 // and queue what arrived as movers; the ONE tile repair of the step then handles local movers and immigrants alike.
-static int slab_migrate(Handle *h, bool carry) {
+static int slab_migrate(Handle *h, bool carry, cudaStream_t stream) {
   const DevParams &p = h->p;
   SlabState &s = h->slab;
   DevArrays &a = h->a;
@@ -309,25 +309,25 @@ static int slab_migrate(Handle *h, bool carry) {
   const size_t bytes = (size_t)a.em_cap * sizeof(EmRec);
   if (!s.comm) {  // one-rank slab mode: what leaves through my left edge arrives from my right, and vice versa
     for (int d = 0; d < 2; d++) {
-      SLAB_CUDA(h, cudaMemcpyAsync(a.flags + FLAG_NEMR0 + (1 - d), a.flags + FLAG_NEM0 + d, sizeof(int), cudaMemcpyDeviceToDevice, h->stream));
-      SLAB_CUDA(h, cudaMemcpyAsync(a.em_recv[1 - d], a.em_send[d], bytes, cudaMemcpyDeviceToDevice, h->stream));
+      SLAB_CUDA(h, cudaMemcpyAsync(a.flags + FLAG_NEMR0 + (1 - d), a.flags + FLAG_NEM0 + d, sizeof(int), cudaMemcpyDeviceToDevice, stream));
+      SLAB_CUDA(h, cudaMemcpyAsync(a.em_recv[1 - d], a.em_send[d], bytes, cudaMemcpyDeviceToDevice, stream));
     }
   } else {
   SLAB_NCCL(h, g_nccl.GroupStart());
   for (int d = 0; d < 2; d++) {
-    SLAB_NCCL(h, g_nccl.Send(a.flags + FLAG_NEM0 + d, sizeof(int), ncclInt8, peer[d], s.comm, h->stream));
-    SLAB_NCCL(h, g_nccl.Send(a.em_send[d], bytes, ncclInt8, peer[d], s.comm, h->stream));
+    SLAB_NCCL(h, g_nccl.Send(a.flags + FLAG_NEM0 + d, sizeof(int), ncclInt8, peer[d], s.comm, stream));
+    SLAB_NCCL(h, g_nccl.Send(a.em_send[d], bytes, ncclInt8, peer[d], s.comm, stream));
   }
   // with 2 GPUs both messages come from the same peer: its first batch is what left through ITS left edge (towards me,
   // arriving on my right side), so the buffer of the right neighbour is received first
   for (int d = 1; d >= 0; d--) {
-    SLAB_NCCL(h, g_nccl.Recv(a.flags + FLAG_NEMR0 + d, sizeof(int), ncclInt8, peer[d], s.comm, h->stream));
-    SLAB_NCCL(h, g_nccl.Recv(a.em_recv[d], bytes, ncclInt8, peer[d], s.comm, h->stream));
+    SLAB_NCCL(h, g_nccl.Recv(a.flags + FLAG_NEMR0 + d, sizeof(int), ncclInt8, peer[d], s.comm, stream));
+    SLAB_NCCL(h, g_nccl.Recv(a.em_recv[d], bytes, ncclInt8, peer[d], s.comm, stream));
   }
   SLAB_NCCL(h, g_nccl.GroupEnd());
   }
   for (int d = 0; d < 2; d++) {
-    k_ingest<<<8, 128, 0, h->stream>>>(p, a.em_recv[d], FLAG_NEMR0 + d, a.em_cap, vel ? 1 : 0, a.mv_pos, a.mv_second,
+    k_ingest<<<8, 128, 0, stream>>>(p, a.em_recv[d], FLAG_NEMR0 + d, a.em_cap, vel ? 1 : 0, a.mv_pos, a.mv_second,
                                        a.mv_force, a.mv_id, a.mv_cell, a.mv_src, a.tile_dirty, a.dirty_list, a.inbox_cnt,
                                        a.inbox, a.flags, carry ? a.chg : nullptr);
     h->launches++;
@@ -414,13 +414,13 @@ int slab_join(Handle *h) {
 // One step in slab mode.
 //
 // Newton steps with the force carry are pipelined over two streams.  Per step n, in steady state:
-//   side : ... [C(n-1): halo positions + layout] [boundary recompute(n-1)] [A(n): drifted halo]  K_bnd(n)
-//   main : step_begin(n)  K_int(n)  | wait side |  wall fix-ups, B(n): emigrant records, ingest, tile repair, re-drift,
-//          list-driven recompute of the interior
+//   side : ... [C(n-1): halo positions + layout] [boundary recompute(n-1)] [A(n): drifted halo]  K_bnd(n)  B(n): emigrant
+//          records + ingest
+//   main : step_begin(n)  K_int(n)  | wait side |  wall fix-ups, tile repair, re-drift, list-driven recompute of the interior
 // K_int = the blocks that read no halo column, K_bnd = the first / last block of every tile row.  The interior work of
 // step n+1 never touches the two owned columns next to a halo, so the exchanges C and A and the recomputation of those
 // columns (always done in full: the neighbour's boundary column re-bins behind this rank's back) overlap with K_int.
-// Communicator operations stay totally ordered by the events (B(n) -> C(n) -> A(n+1) -> B(n+1)), identically on all ranks.
+// Communicator operations all live on the side stream (A(n) -> B(n) -> C(n) -> A(n+1)), identically ordered on all ranks.
 int slab_step_once(Handle *h, const real *noise_dev) {
   DevParams &p = h->p;
   DevArrays &a = h->a;
@@ -459,6 +459,12 @@ int slab_step_once(Handle *h, const real *noise_dev) {
     tr.mark(8, s.side);
     launch_newton_b(cside, p, a, true, 2);  // blocks next to a halo column, after A on the side stream
     tr.mark(10, s.side);
+    // B: every emigrant comes out of a boundary block (a particle of an interior block would have to cross >= 3 cell
+    // columns in one step; note_moved_slow reports that loudly), so the migration exchange and the ingestion of the
+    // immigrants run on the side stream right away, overlapped with the interior blocks.  k_ingest only appends to the
+    // mover / dirty / changed-cell lists with the same atomics the interior blocks use.
+    if ((st = slab_migrate(h, carry, s.side))) return st;
+    tr.mark(4, s.side);
     SLAB_CUDA(h, cudaEventRecord(s.ev_halo, s.side));
     launch_newton_b(c, p, a, true, 1);
     tr.mark(2, h->stream);
@@ -479,8 +485,10 @@ int slab_step_once(Handle *h, const real *noise_dev) {
   std::swap(a.pos[0], a.pos[1]);
   if (h->prof) cudaEventRecord(h->ev[3], h->stream);
   // update_chunks! for the next step: emigrants -> neighbours, immigrants queued as movers, ONE incremental repair
-  if ((st = slab_migrate(h, carry))) return st;
-  tr.mark(4, h->stream);
+  if (!piped) {
+    if ((st = slab_migrate(h, carry, h->stream))) return st;
+    tr.mark(4, h->stream);
+  }
   launch_repair_tiles(c, p, a, vel);
   if (carry) launch_carry_redrift(c, p, a);
   tr.mark(5, h->stream);
