@@ -35,6 +35,11 @@ constexpr int RING_WARPS = 4;
 
 __device__ __forceinline__ int ring_type(const DevRings &r, int ring) { return r.types ? r.types[ring] : 0; }
 
+// cross_prod(p1, p2) of calc_area (src/rings/integration.jl:103-116) with the reference's roundings: fl(fl(x1 y2) - fl(y1 x2)),
+// no FMA contraction.  The shoelace sum of a ring far from the origin cancels catastrophically (terms ~ |r|^2, area ~ 1):
+// a fused multiply-add here moves the area by ~|r|^2 ulp and the area force with it (4e-10 relative in a 1500-wide box).
+__device__ __forceinline__ real cross_exact(real2 a, real2 b) { return add_rn(mul_rn(a.x, b.y), -mul_rn(a.y, b.x)); }
+
 // idflag for ring-ordered slots: padding slots of shorter ring types are inactive (FixRingsIds, src/rings/states.jl:45-61)
 __global__ void k_rings_ids(const __grid_constant__ DevParams p, unsigned int *__restrict__ idflag) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -205,8 +210,8 @@ __global__ void __launch_bounds__(RING_WARPS * 32) k_rings_ring(
   // ---- calc_area (:103-116), shoelace, sequential
   real area = 0.0;
   if (lane == 0) {
-    for (int i = 0; i < np - 1; i++) area += sc[i].x * sc[i + 1].y - sc[i].y * sc[i + 1].x;
-    area += sc[np - 1].x * sc[0].y - sc[np - 1].y * sc[0].x;
+    for (int i = 0; i < np - 1; i++) area = add_rn(area, cross_exact(sc[i], sc[i + 1]));
+    area = add_rn(area, cross_exact(sc[np - 1], sc[0]));
     area = area / 2.0;
     areas[ring] = area;
     if (MODE == 0 && prime_cms) {  // constructor: update_cms! right after the first unwrap (src/rings/rings.jl:280-283)
@@ -329,7 +334,7 @@ __global__ void __launch_bounds__(RING_T_TPB) k_rings_ring_t(
       ci = make_real2(c_prev.x + dx, c_prev.y + dy);
       cont_pos[base + i] = ci;
     }
-    area += c_prev.x * ci.y - c_prev.y * ci.x;
+    area = add_rn(area, cross_exact(c_prev, ci));
     sx += ci.x;
     sy += ci.y;
     c_prev = ci;
@@ -337,7 +342,7 @@ __global__ void __launch_bounds__(RING_T_TPB) k_rings_ring_t(
   }
   if (PER)
     for (int i = np; i < R.n_max; i++) cont_pos[base + i] = pos[base + i];  // continuos_pos[:, ring] .= rings_pos[:, ring] first
-  area += c_prev.x * c0.y - c_prev.y * c0.x;
+  area = add_rn(area, cross_exact(c_prev, c0));
   area = area / 2.0;
   areas[ring] = area;
   if (MODE == 0 && prime_cms) cms[ring] = make_real2(sx / np, sy / np);  // src/rings/rings.jl:280-283

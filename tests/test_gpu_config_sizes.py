@@ -62,12 +62,17 @@ def test_c2_harmtrunc_one_million_rigid_matches_oracle(cuda_lib):
     dyn = pkg.HarmTruncCfg(k_rep=10.0, k_atr=1.0, dist_eq=1.0, dist_max=1.3)
     case = H.newton_case(nx=1000, ny=1000, dyn=dyn, wall="rigid", jitter=0.3, vmax=1.0, dt=0.002)
     g, o = H.make_gpu(case), H.make_oracle(case, threads=THREADS)
+    g.calc_forces()
+    o.calc_forces()
+    assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-12   # identical positions: the force evaluation itself
     g.step(10)
     o.step(10)
     g.sync_to_host()
     assert np.abs(g.state.pos - o.pos()).max() / case["geom"].length < 1e-12
     assert H.rel_err(g.state.vel, o.second()) < 1e-12
-    assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-12
+    # after steps the two sides hold positions that differ in the last bit (ulp(1100) = 2e-13): a stiff law (k_rep = 10)
+    # turns that into a few 1e-12 of force
+    assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-11
     assert _cells_equal(g, o, rebin=True)
 
 
@@ -78,12 +83,17 @@ def test_c3_szabo_one_million_matches_oracle(cuda_lib):
     g, o = H.make_gpu(case), H.make_oracle(case, threads=THREADS)
     n = 1000 * 1000
     noise = _noise(n, 10, seed=7)
+    g.calc_forces()
+    o.calc_forces()
+    assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-12   # identical positions
     g.step(10, noise)
     o.step(10, noise)
     g.sync_to_host()
     assert np.abs(g.state.pos - o.pos()).max() / case["geom"].length < 1e-12
     assert np.abs(g.state.pol_angle - o.second()).max() < 1e-11
-    assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-12
+    # Szabo's repulsion is k_rep / (r_max - r_eq) = 100 per unit length: last-bit position differences (ulp(1500) = 2e-13)
+    # show up as 1e-11 of force after steps
+    assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-10
     assert _cells_equal(g, o, rebin=True)
 
 
@@ -92,7 +102,7 @@ def test_c4_rings_100k_matches_oracle(cuda_lib):
     test/tests_rings/rings_utils.jl:35-53; constructor state + 5 step!s with host noise."""
     case = H.rings_case("normal", 400, 250)
     g, o = H.make_gpu_rings(case), H.make_oracle(case, threads=THREADS)
-    assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-12
+    assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-11   # area force: shoelace cancellation in a 1500-wide box
     assert _cells_equal(g, o)
     noise = _noise(case["num_rings"], 5, seed=11)
     g.step(5, noise)
@@ -127,10 +137,12 @@ def _ring_bbox_hits(rp, circle):
     return (lo[:, 0] <= ch[0]) & (hi[:, 0] >= cl[0]) & (lo[:, 1] <= ch[1]) & (hi[:, 1] >= cl[1])
 
 
-@pytest.mark.parametrize("main_wall", ["periodic", "rigid"])
+@pytest.mark.parametrize("main_wall", ["periodic"])
 def test_rings_with_circle_obstacles_matches_oracle(cuda_lib, main_wall):
-    """examples/rings_circle_obs.jl:60-79: rings on a grid, two SlipperyWalls circle obstacles in a periodic rectangle
-    (and the same with RigidWalls as the main wall), rings overlapping an obstacle removed; 150 step!s."""
+    """examples/rings_circle_obs.jl:60-79: rings on a grid, two SlipperyWalls circle obstacles in a periodic rectangle, rings
+    overlapping an obstacle removed; 150 step!s.  (RigidWalls as the main wall of a RingsSystem is not a valid reference
+    configuration: walls!(::RigidWalls, ::RectangleCfg) flips `state.vel`, which a RingsState does not have,
+    src/integration.jl:271-285.)"""
     from mavi_jl_b200.rings import configs as rc
     from mavi_jl_b200.rings import init_states as ri
     from mavi_jl_b200.rings.states import RingsState
@@ -193,9 +205,17 @@ def test_headline_16m_three_steps_match_oracle(cuda_lib):
     of = o.get_forces()
     assert np.abs(gp - o.pos()).max() / w["geom"].length < 1e-12
     assert H.rel_err(gv, o.second()) < 1e-12
-    df = np.abs(gf - of).max()
-    assert df / max(np.abs(of).max(), bench.lj_pair_force_scale(pkg)) < 1e-12
-    assert df / np.abs(of).max() < 1e-11
+    # positions agree to the last bit or two (ulp(4700) = 9e-13) and the LJ force goes like r^-13: one ulp of a coordinate
+    # is 13 * 9e-13 / 1.35 = 9e-12 of a pair force.  The force EVALUATION is checked on identical positions below.
+    assert np.abs(gf - of).max() / np.abs(of).max() < 2e-11
+    # forces from identical positions: the oracle takes the device's state and both run clean + update_chunks + calc_forces
+    g2 = H.make_gpu(dict(case, mk=lambda: pkg.SecondLawState(pos=gp.copy(), vel=gv.copy())))
+    g2.calc_forces()
+    gf2 = g2.get_forces()
+    g2.close()
+    o2 = H.make_oracle(dict(case, mk=lambda: pkg.SecondLawState(pos=gp.copy(), vel=gv.copy())), threads=THREADS)
+    o2.calc_forces()
+    assert H.rel_err(gf2, o2.get_forces()) < 1e-12
     o.update_chunks()
     co, no = o.download_cells()
     assert np.array_equal(cg, co) and np.array_equal(ng, no)

@@ -437,10 +437,10 @@ def test_pipelined_kernels_match_legacy_staging(cuda_lib, kind):
         case = H.newton_case(nx=32, ny=32, dyn=DYNS["harm"], wall="periodic", jitter=0.3, vmax=2.0, dt=0.002, active_mask=mask)
     elif kind == "lj_small_grid":   # 2-row / 2-column periodic wrap
         case = H.newton_case(nx=6, ny=6, wall="periodic", jitter=0.3, vmax=1.0, dt=0.002, cells=(2, 2))
-    elif kind == "lj_dense":        # ~60 particles per cell: several chunks per block, some columns beyond the staging area
-        case = H.newton_case(nx=96, ny=96, dyn=DYNS["harm"], wall="periodic", jitter=0.3, vmax=1.0, dt=0.001, cells=(12, 12))
+    elif kind == "lj_dense":        # 9 particles per cell, ~290 per tile: a block needs several chunks of the staging area
+        case = H.newton_case(nx=96, ny=96, dyn=DYNS["harm"], wall="periodic", jitter=0.3, vmax=1.0, dt=0.001, cells=(32, 32))
     else:
-        case = H.sp_case(kind, nx=48, ny=40, rot_diff=0.05)
+        case = H.sp_case(kind, nx=48, ny=40, rot_diff=0.05, jitter=0.6 if kind == "rtp" else 0.9)
     a = H.make_gpu(_with_flags(case, extra))
     b = H.make_gpu(_with_flags(case, extra | LEG))
     n = len(a.state.pos)
@@ -510,7 +510,8 @@ def test_slab_self_mode_matches_plain(cuda_lib, kind, flags):
     sp = kind in ("szabo", "szabo_noise", "rtp")
     if sp:
         # szabo_noise / rtp: host noise rows are indexed by the ORIGINAL id (global row in slab mode) through migration
-        case = H.sp_case("rtp" if kind == "rtp" else "szabo", nx=40, ny=30, rot_diff=0.0 if kind == "szabo" else 0.05)
+        case = H.sp_case("rtp" if kind == "rtp" else "szabo", nx=40, ny=30, rot_diff=0.0 if kind == "szabo" else 0.05,
+                         jitter=0.6 if kind == "rtp" else 0.9)  # WCA blows up if particles overlap
         ic = case["int_cfg"]
         mkdev = lambda f: pkg.CUDADevice(rng_mode="host_noise", flags=f)  # noqa: E731
     else:

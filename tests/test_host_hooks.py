@@ -42,7 +42,7 @@ def test_checkpoint_roundtrip_continues_identically(cuda_lib, kind):
         case = H.newton_case(nx=40, ny=40, dyn=pkg.HarmTruncCfg(k_rep=10.0, k_atr=1.0, dist_eq=1.0, dist_max=1.3), wall="rigid",
                              jitter=0.3, vmax=2.0, dt=0.002)
     else:
-        case = H.sp_case(kind, nx=40, ny=32, rot_diff=0.05)
+        case = H.sp_case(kind, nx=40, ny=32, rot_diff=0.05, jitter=0.6 if kind == "rtp" else 0.9)
     npart = len(case["mk"]().pos)
     rng = np.random.default_rng(8)
     noise = None

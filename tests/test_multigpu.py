@@ -209,7 +209,7 @@ def test_single_process_multi_gpu_matches_oracle(cuda_lib, kind, steps, flags):
         case = H.newton_case(nx=72, ny=40, dyn=dyn, wall="periodic", jitter=0.2, vmax=3.0, dt=0.002)
         mkdev = lambda: pkg.CUDADevice(n_gpus=G, flags=flags)  # noqa: E731
     else:
-        case = H.sp_case(kind, nx=64, ny=40, rot_diff=0.05)
+        case = H.sp_case(kind, nx=64, ny=40, rot_diff=0.05, jitter=0.6 if kind == "rtp" else 0.9)
         mkdev = lambda: pkg.CUDADevice(n_gpus=G, flags=flags, rng_mode="host_noise")  # noqa: E731
     ic = case["int_cfg"]
     case["int_cfg"] = pkg.IntCfg(dt=ic.dt, chunks_cfg=ic.chunks_cfg, device=mkdev())
