@@ -1277,7 +1277,8 @@ struct PChunk {
 };
 constexpr int PCH_BYTES = (sizeof(PChunk) + 15) / 16 * 16;
 constexpr int PBUF_BYTES = PCH_BYTES + PSPOS_CAP * (int)sizeof(real2) + POWN_CAP * (int)sizeof(unsigned int);
-constexpr int PIPE_SMEM = 64 + 2 * PBUF_BYTES;       // [4 mbarriers | buffer 0 | buffer 1]
+constexpr int PTS_BYTES = 32 * (MAVI_TR + 1) * (int)sizeof(int);  // producer scratch: tstart rows of the staged columns
+constexpr int PIPE_SMEM = 64 + 2 * PBUF_BYTES + PTS_BYTES;       // [4 mbarriers | buffer 0 | buffer 1 | producer scratch]
 
 __device__ __forceinline__ unsigned int smem_u32(const void *ptr) { return (unsigned int)__cvta_generic_to_shared(ptr); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
@@ -1289,12 +1290,15 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.release.cta.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
+// The waiting warp is SUSPENDED by the hardware (suspend-time hint, woken as soon as the phase completes) instead of
+// spinning: the first version of this kernel spent 29 % of its issued instructions in this loop
+// (profiles/r02_ncu_newton_summary.md), slots taken from the very producer warp the consumers were waiting for.
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int parity) {
   asm volatile(
       "{\n\t.reg .pred ok;\n"
       "W%=:\n\t"
-      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 ok, [%0], %1;\n\t"
-      "@!ok bra W%=;\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 ok, [%0], %1, %2;\n\t"
+      "@!ok bra W%=;\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(100000u)
       : "memory");
 }
 // one contiguous run global -> shared, completing `bytes` on the mbarrier (UBLKCP)
@@ -1309,7 +1313,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned in
 template <bool PER>
 __device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restrict__ tstart, const real2 *__restrict__ pos,
                                           int tr, int cs, int rem, bool exact_minimg, PChunk *ck, real2 *s_pos,
-                                          unsigned int *s_list, unsigned long long *full_bar) {
+                                          unsigned int *s_list, unsigned long long *full_bar, int *s_ts) {
   const int lane = threadIdx.x & 31;
   const int R = p.num_rows, Cn = p.num_cols;
   const int r0 = tr * MAVI_TR;
@@ -1331,14 +1335,24 @@ __device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restr
     if (ra < 0) { if (p.wrap_rows) { ra = R - 1; wrapped = wrapped || exists; } else has_a = false; }
     if (rb >= R) { if (p.wrap_rows) { rb = 0; wrapped = wrapped || exists; } else has_b = false; }
     cj = exists ? c : 0;
+    int *row = s_ts + j * (MAVI_TR + 1);
     if (exists) {
       const int *tt = tstart + (size_t)(c * p.tpc + tr) * (MAVI_TR + 1);
       const int qa = has_a ? tq_of(p, c, ra) : 0, qb = has_b ? tq_of(p, c, rb) : 0;
-      st = __ldg(tt);
-      const int et = __ldg(tt + MAVI_TR);
+      // the whole tstart row of the column in ONE round trip (33 independent loads per lane), kept in shared memory
+      // relative to the tile start for the window / list pass below (row stride 33 words: conflict-free across lanes)
+      int v[MAVI_TR + 1];
+#pragma unroll
+      for (int r = 0; r <= MAVI_TR; r++) v[r] = __ldg(tt + r);
       const int a0 = has_a ? __ldg(tstart + qa) : 0, a1 = has_a ? __ldg(tstart + qa + 1) : 0;
       const int b0 = has_b ? __ldg(tstart + qb) : 0, b1 = has_b ? __ldg(tstart + qb + 1) : 0;
-      lt = et - st; sa = a0; la = a1 - a0; sb = b0; lb = b1 - b0;
+      st = v[0];
+#pragma unroll
+      for (int r = 0; r <= MAVI_TR; r++) row[r] = v[r] - st;
+      lt = v[MAVI_TR] - st; sa = a0; la = a1 - a0; sb = b0; lb = b1 - b0;
+    } else {
+#pragma unroll
+      for (int r = 0; r <= MAVI_TR; r++) row[r] = 0;
     }
   }
   // ---- prefix sums over the lanes, greedy number of own columns that fit
@@ -1404,12 +1418,11 @@ __device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restr
     for (int jj = 0; jj < nc + 2; jj++) {
       const int offj = __shfl_sync(0xffffffffu, off, jj), laj = __shfl_sync(0xffffffffu, la, jj);
       const int ltj = __shfl_sync(0xffffffffu, lt, jj), lbj = __shfl_sync(0xffffffffu, lb, jj);
-      const int stj = __shfl_sync(0xffffffffu, st, jj), cjj = __shfl_sync(0xffffffffu, cj, jj);
+      const int stj = __shfl_sync(0xffffffffu, st, jj);
       const int qbj = __shfl_sync(0xffffffffu, ownoff, jj);
       const int tot = laj + ltj + lbj;
-      const int *tt = tstart + (size_t)(cjj * p.tpc + tr) * (MAVI_TR + 1);
       // staged start of tile row lane+1 (rows beyond the grid start where the tile ends)
-      const int tsl = tot ? __ldg(tt + lane) - stj : 0, tsn = tot ? __ldg(tt + lane + 1) - stj : 0;
+      const int tsl = s_ts[jj * (MAVI_TR + 1) + lane], tsn = s_ts[jj * (MAVI_TR + 1) + lane + 1];
       const int rs = offj + laj + tsl;
       const int up = __shfl_up_sync(0xffffffffu, rs, 1), dn = __shfl_down_sync(0xffffffffu, rs, 2);
       const int end = offj + tot;
@@ -1476,7 +1489,8 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
         unsigned char *buf = dsm + 64 + (size_t)b * PBUF_BYTES;
         cs += pipe_stage<PER>(p, tstart, pos, tr, cs, c_end - cs, exact_minimg, reinterpret_cast<PChunk *>(buf),
                               reinterpret_cast<real2 *>(buf + PCH_BYTES),
-                              reinterpret_cast<unsigned int *>(buf + PCH_BYTES + PSPOS_CAP * sizeof(real2)), &bars[b]);
+                              reinterpret_cast<unsigned int *>(buf + PCH_BYTES + PSPOS_CAP * sizeof(real2)), &bars[b],
+                              reinterpret_cast<int *>(dsm + 64 + 2 * (size_t)PBUF_BYTES));
       }
     }
     const int b = k & 1;  // end marker

@@ -14,9 +14,10 @@ pkg = entry.load_package()
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 kind = sys.argv[3] if len(sys.argv) > 3 else "lj"
+flags = int(sys.argv[4]) if len(sys.argv) > 4 else 0   # MAVI_FLAG_* (32 = legacy staging kernels)
 if kind in ("lj", "ljself", "lj32"):
     # ljself: the x-slab machinery on one GPU (MAVI_FLAG_SLAB_SELF), for profiling the multi-GPU step on one rank
-    w = bench.lj_workload(pkg, nx, nx, cuda_device=pkg.CUDADevice(flags=pkg.capi.FLAG_SLAB_SELF) if kind == "ljself" else None)
+    w = bench.lj_workload(pkg, nx, nx, cuda_device=pkg.CUDADevice(flags=flags | (pkg.capi.FLAG_SLAB_SELF if kind == "ljself" else 0)))
     T = np.float32 if kind == "lj32" else np.float64  # lj32: Float32 mode (mavi_f32 build) on the same workload
     s = pkg.System(state=pkg.SecondLawState(pos=w["pos"].astype(T), vel=w["vel"].astype(T)), space_cfg=w["space"], dynamic_cfg=w["dyn"], int_cfg=w["int_cfg"])
     n = nx * nx
@@ -26,7 +27,7 @@ elif kind == "szabo":
     pos, geom = pkg.rectangular_grid(nx, nx, 1.0, pkg.particle_radius(dyn))
     ang = np.random.default_rng(bench.SEED).random(nx * nx) * 2 * np.pi
     s = pkg.System(state=pkg.SelfPropelledState(pos=pos, pol_angle=ang), space_cfg=pkg.SpaceCfg(wall_type=pkg.PeriodicWalls(), geometry_cfg=geom),
-                   dynamic_cfg=dyn, int_cfg=pkg.IntCfg(dt=0.01, chunks_cfg=pkg.ChunksCfg(nx - 1, nx - 1), device=pkg.CUDADevice(rng_mode="philox")))
+                   dynamic_cfg=dyn, int_cfg=pkg.IntCfg(dt=0.01, chunks_cfg=pkg.ChunksCfg(nx - 1, nx - 1), device=pkg.CUDADevice(rng_mode="philox", flags=flags)))
     n = nx * nx
 else:
     # BASELINE config C4: 400 x 250 rings x 10 particles (test/tests_rings/rings_utils.jl:35-53 parameters), two types
