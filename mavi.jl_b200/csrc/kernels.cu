@@ -1044,6 +1044,7 @@ struct Chunk2 {
   int la[G2MAX + 2], lt[G2MAX + 2], lb[G2MAX + 2];
   int off[G2MAX + 3], ownoff[G2MAX + 3], gbase[G2MAX + 2];
   int2 cwin[G2MAX + 2][MAVI_TR];  // [j][lr-1]
+  __device__ __forceinline__ int2 win(int j, int r) const { return cwin[j][r]; }
 };
 constexpr int C2_BYTES = (sizeof(Chunk2) + 15) / 16 * 16;
 constexpr int PASS2_SMEM = C2_BYTES + SPOS2_CAP * (int)sizeof(real2) + OWN2_CAP * (int)sizeof(unsigned int);
@@ -1154,7 +1155,7 @@ __device__ __forceinline__ void chunk_stage(const DevParams &p, const int *__res
 template <int DYN, bool MINIMG, typename CK>
 __device__ __forceinline__ void chunk_walk(const DevParams &p, const CK *ck, const real2 *s_pos, int jj, int lr,
                                            int self, real2 ri, real &fx, real &fy) {
-  const int2 w0 = ck->cwin[jj - 1][lr - 1], w1 = ck->cwin[jj][lr - 1], w2 = ck->cwin[jj + 1][lr - 1];
+  const int2 w0 = ck->win(jj - 1, lr - 1), w1 = ck->win(jj, lr - 1), w2 = ck->win(jj + 1, lr - 1);
   // byte offsets into s_pos; neighbours t < c1 -> column jj-1, c1 <= t < c2 -> own column before self,
   // c2 <= t < c3 -> own column after self, c3 <= t -> column jj+1
   constexpr int B = (int)sizeof(real2);  // bytes per staged position
@@ -1273,7 +1274,10 @@ struct PChunk {
   // edges of the cells as axis_in_cell() compares them (lo <= t < hi): staged column j / cell row lr-1 of the tile
   double2 xb[PG_MAX + 2];
   double2 yb[MAVI_TR];
-  int2 cwin[PG_MAX + 2][MAVI_TR];  // [j][lr-1] = (first staged index of cell row lr-1, end of cell row lr+1)
+  // (first staged index of cell row lr-1, end of cell row lr+1) of staged column j, stored [lr-1][j]: the producer's lanes
+  // (one per column) write consecutive words, a consumer reads its three windows j-1, j, j+1 from 24 consecutive bytes
+  int2 cwin_t[MAVI_TR][PG_MAX + 2];
+  __device__ __forceinline__ int2 win(int j, int r) const { return cwin_t[r][j]; }
 };
 constexpr int PCH_BYTES = (sizeof(PChunk) + 15) / 16 * 16;
 constexpr int PBUF_BYTES = PCH_BYTES + PSPOS_CAP * (int)sizeof(real2) + POWN_CAP * (int)sizeof(unsigned int);
@@ -1370,7 +1374,9 @@ __device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restr
   const int nc = bal ? 31 - __clz(bal) : 1;  // fits is monotone in j
   const unsigned int wbal = __ballot_sync(0xffffffffu, in && j <= nc + 1 && wrapped);
   const int off = incl - sz, ownoff = oincl - own;
-  const int total = __shfl_sync(0xffffffffu, incl, nc + 1);
+  int tile_total = (in && j <= nc + 1) ? lt : 0;   // positions that arrive through bulk copies (the tile runs)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tile_total += __shfl_xor_sync(0xffffffffu, tile_total, o);
   const int nown = __shfl_sync(0xffffffffu, oincl, nc);
   const int st1 = __shfl_sync(0xffffffffu, st, 1), lt1 = __shfl_sync(0xffffffffu, lt, 1);
   if (lane == 0) {
@@ -1383,7 +1389,7 @@ __device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restr
     ck->cs = cs;
     ck->src_t1 = st1;
     ck->lt1 = lt1;
-    if (PIPE_BULK && bal) mbar_expect_tx(full_bar, (unsigned int)total * (unsigned int)sizeof(real2));
+    if (PIPE_BULK && bal && tile_total) mbar_expect_tx(full_bar, (unsigned int)tile_total * (unsigned int)sizeof(real2));
   }
   {  // ---- cell edges for the exact "still in its cell" test of the epilogue (see axis_in_cell / still_in_cell)
     if (in) {
@@ -1406,39 +1412,34 @@ __device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restr
   }
   __syncwarp();
   if (bal) {
-    // ---- positions: every contiguous run is one bulk-async copy, issued by the lane that owns the column
-    if (PIPE_BULK) {
-      if (j <= nc + 1) {
-        if (la) bulk_g2s(s_pos + off, pos + sa, (unsigned int)la * (unsigned int)sizeof(real2), full_bar);
+    if (j <= nc + 1) {
+      // ---- positions.  The tile run of the column ([first .. last cell row of the tile], ~40 positions) is ONE bulk-async
+      // copy that completes on the buffer's `full` barrier; the one cell row above and below (a couple of positions each)
+      // are copied by the lane itself — three bulk copies per column cost more issue slots than they save
+      if (PIPE_BULK) {
         if (lt) bulk_g2s(s_pos + off + la, pos + st, (unsigned int)lt * (unsigned int)sizeof(real2), full_bar);
-        if (lb) bulk_g2s(s_pos + off + la + lt, pos + sb, (unsigned int)lb * (unsigned int)sizeof(real2), full_bar);
+        for (int i = 0; i < la; i++) s_pos[off + i] = __ldg(pos + sa + i);
+        for (int i = 0; i < lb; i++) s_pos[off + la + lt + i] = __ldg(pos + sb + i);
+      } else {  // Float32 build: a float2 run is only 8-byte aligned
+        for (int i = 0; i < la; i++) s_pos[off + i] = __ldg(pos + sa + i);
+        for (int i = 0; i < lt; i++) s_pos[off + la + i] = __ldg(pos + st + i);
+        for (int i = 0; i < lb; i++) s_pos[off + la + lt + i] = __ldg(pos + sb + i);
       }
-    }
-    // ---- cell-row windows and the own-particle list: one staged column after the other, lane = cell row of the tile
-    for (int jj = 0; jj < nc + 2; jj++) {
-      const int offj = __shfl_sync(0xffffffffu, off, jj), laj = __shfl_sync(0xffffffffu, la, jj);
-      const int ltj = __shfl_sync(0xffffffffu, lt, jj), lbj = __shfl_sync(0xffffffffu, lb, jj);
-      const int stj = __shfl_sync(0xffffffffu, st, jj);
-      const int qbj = __shfl_sync(0xffffffffu, ownoff, jj);
-      const int tot = laj + ltj + lbj;
-      // staged start of tile row lane+1 (rows beyond the grid start where the tile ends)
-      const int tsl = s_ts[jj * (MAVI_TR + 1) + lane], tsn = s_ts[jj * (MAVI_TR + 1) + lane + 1];
-      const int rs = offj + laj + tsl;
-      const int up = __shfl_up_sync(0xffffffffu, rs, 1), dn = __shfl_down_sync(0xffffffffu, rs, 2);
-      const int end = offj + tot;
-      const int wa = lane == 0 ? offj : up;                                                 // start of row lr-1
-      const int wb = (lane + 3 >= rows + 2) ? end : (lane <= 29 ? dn : offj + laj + ltj);   // end of row lr+1
-      ck->cwin[jj][lane] = make_int2(wa, wb);
-      if (lane == 0) ck->gbase[jj] = stj - (offj + laj);
-      if (jj >= 1 && jj <= nc && lane < rows) {
-        for (int i = tsl; i < tsn; i++)
-          s_list[qbj + i] = (unsigned int)(offj + laj + i) | ((unsigned int)jj << 16) | ((unsigned int)(lane + 1) << 24);
+      // ---- cell-row windows and the own-particle list of the column, from its tstart row in shared memory
+      const int *row = s_ts + j * (MAVI_TR + 1);
+      const int base = off + la;             // staged index of the first particle of the tile
+      const int end = off + la + lt + lb;    // end of the staged column
+      ck->gbase[j] = st - base;
+      for (int r = 0; r < MAVI_TR; r++) {    // r = lr - 1
+        const int wa = r == 0 ? off : base + row[r - 1];                                        // start of cell row lr-1
+        const int wb = (r + 3 >= rows + 2) ? end : (r <= 29 ? base + row[r + 2] : base + lt);   // end of cell row lr+1
+        ck->cwin_t[r][j] = make_int2(wa, wb);
       }
-      if (!PIPE_BULK) {  // Float32 build: the warp copies the three runs of this column itself
-        const int saj = __shfl_sync(0xffffffffu, sa, jj), sbj = __shfl_sync(0xffffffffu, sb, jj);
-        for (int i = lane; i < tot; i += 32) {
-          const int src = i < laj ? saj + i : (i < laj + ltj ? stj + (i - laj) : sbj + (i - laj - ltj));
-          s_pos[offj + i] = __ldg(pos + src);
+      if (j >= 1 && j <= nc) {
+        int r = 0;
+        for (int i = 0; i < lt; i++) {
+          while (i >= row[r + 1]) ++r;       // cell row of the i-th particle of the tile (rows beyond the grid are empty)
+          s_list[ownoff + i] = (unsigned int)(base + i) | ((unsigned int)j << 16) | ((unsigned int)(r + 1) << 24);
         }
       }
     }
