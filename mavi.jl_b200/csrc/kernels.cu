@@ -1256,9 +1256,8 @@ __device__ __forceinline__ void for_each_block_particle(const DevParams &p, cons
 // Float32 build: a float2 run is only 8-byte aligned, below the 16 bytes bulk copies need, so there the producer warp
 // copies the runs itself (plain loads / stores) before it arrives on `full`.
 // =========================================================================================================
-constexpr int PIPE_CW = 8;                           // consumer warps per CTA
-constexpr int PIPE_CT = PIPE_CW * 32;                // consumer threads
-constexpr int PIPE_THREADS = PIPE_CT + 32;           // + the producer warp (the LAST warp of the CTA)
+// consumer warps per CTA (template parameter CW): 8 -> 288 threads, 72 registers (a few spills in the particle loop),
+// 24 consumer warps per SM; 7 -> 256 threads, 80 registers, no spills, 21 consumer warps per SM.  MAVI_PIPE_CW picks.
 constexpr int PIPE_CTAS_PER_SM = 3;
 constexpr int PG_MAX = 30;                           // own columns per chunk (+ two side columns: one producer lane each)
 constexpr int PSPOS_CAP = 1280;                      // staged positions per chunk
@@ -1430,16 +1429,16 @@ __device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restr
       const int base = off + la;             // staged index of the first particle of the tile
       const int end = off + la + lt + lb;    // end of the staged column
       ck->gbase[j] = st - base;
+      const bool own = j >= 1 && j <= nc;
+      unsigned int *lst = s_list + ownoff;
+#pragma unroll 8
       for (int r = 0; r < MAVI_TR; r++) {    // r = lr - 1
         const int wa = r == 0 ? off : base + row[r - 1];                                        // start of cell row lr-1
         const int wb = (r + 3 >= rows + 2) ? end : (r <= 29 ? base + row[r + 2] : base + lt);   // end of cell row lr+1
         ck->cwin_t[r][j] = make_int2(wa, wb);
-      }
-      if (j >= 1 && j <= nc) {
-        int r = 0;
-        for (int i = 0; i < lt; i++) {
-          while (i >= row[r + 1]) ++r;       // cell row of the i-th particle of the tile (rows beyond the grid are empty)
-          s_list[ownoff + i] = (unsigned int)(base + i) | ((unsigned int)j << 16) | ((unsigned int)(r + 1) << 24);
+        if (own) {  // own-particle list: the particles of cell row r (rows beyond the grid are empty)
+          const unsigned int tag = ((unsigned int)j << 16) | ((unsigned int)(r + 1) << 24);
+          for (int i = row[r]; i < row[r + 1]; i++) lst[i] = (unsigned int)(base + i) | tag;
         }
       }
     }
@@ -1451,10 +1450,11 @@ __device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restr
 
 // Drives a pipelined force kernel: pre(k) before and body(k, r, cell, active, F) after the pair force F of every
 // particle slot (F = 0 for the inactive tail).  work: device counter of the next tile block (see FLAG_WORK*).
-template <int DYN, bool PER, typename Pre, typename Body>
+template <int DYN, bool PER, int PIPE_CW, typename Pre, typename Body>
 __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const int *__restrict__ tstart,
                                                        const real2 *__restrict__ pos, const int *__restrict__ cell,
                                                        bool exact_minimg, int *__restrict__ work, Pre &&pre, Body &&body) {
+  constexpr int PIPE_CT = PIPE_CW * 32;  // consumer threads; the producer is the LAST warp of the CTA
   extern __shared__ __align__(16) unsigned char dsm[];
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(dsm);  // [0,1] full, [2,3] empty
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1552,6 +1552,15 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
   }
 }
 
+// consumer warps per CTA of the pipelined kernels (A/B switch, see PIPE_CTAS_PER_SM)
+static inline int pipe_cw() {
+  static const int cw = [] {
+    const char *e = getenv("MAVI_PIPE_CW");
+    return (e && atoi(e) == 7) ? 7 : 8;
+  }();
+  return cw;
+}
+
 static inline int grid_pipe(const DevParams &p) {
   const int per_row = p.blk_mode == 0 ? p.blk_per_row : (p.blk_mode == 1 ? p.blk_per_row - 1 - p.blk_last : 1 + p.blk_last);
   const int items = per_row * p.tpc;
@@ -1636,24 +1645,24 @@ __global__ void __launch_bounds__(TPB, MINB) k_newton_b2(const __grid_constant__
 }
 
 // the pipelined version of k_newton_b2 (default); work item counter: FLAG_WORK0 / FLAG_WORK1 (boundary-block launch)
-template <int DYN, bool PER, bool CARRY>
-__global__ void __launch_bounds__(PIPE_THREADS, PIPE_CTAS_PER_SM) k_newton_p(
+template <int DYN, bool PER, bool CARRY, int CW>
+__global__ void __launch_bounds__(CW * 32 + 32, PIPE_CTAS_PER_SM) k_newton_p(
     const __grid_constant__ DevParams p, const int *__restrict__ tstart, const real2 *__restrict__ pos_in,
     real2 *__restrict__ vel, const real2 *f1, real2 *f2, real2 *f1_next, real2 *__restrict__ pos_next,
     int *__restrict__ fix_idx, real2 *__restrict__ fix_pos, const __grid_constant__ MoverSink ms) {
   if (!ms.flags[FLAG_RAN]) return;
   const bool exact = ms.flags[FLAG_BIGMOVE] != 0 || (p.slab && p.blk_mode == 2);
-  pipe_for_each_particle<DYN, PER>(p, tstart, pos_in, ms.cell, exact, ms.flags + (p.blk_mode == 2 ? FLAG_WORK1 : FLAG_WORK0),
-                                   MAVI_NEWTON_B_LAMBDAS);
+  pipe_for_each_particle<DYN, PER, CW>(p, tstart, pos_in, ms.cell, exact, ms.flags + (p.blk_mode == 2 ? FLAG_WORK1 : FLAG_WORK0),
+                                       MAVI_NEWTON_B_LAMBDAS);
 }
 
-template <int DYN, bool PER>
-__global__ void __launch_bounds__(PIPE_THREADS, PIPE_CTAS_PER_SM) k_self_propelled_p(
+template <int DYN, bool PER, int CW>
+__global__ void __launch_bounds__(CW * 32 + 32, PIPE_CTAS_PER_SM) k_self_propelled_p(
     const __grid_constant__ DevParams p, const int *__restrict__ tstart, const unsigned int *__restrict__ idflag,
     const real2 *__restrict__ pos_in, real *__restrict__ ang, real2 *__restrict__ pos_out, real2 *__restrict__ force,
     const real *__restrict__ noise, unsigned long long step, const __grid_constant__ MoverSink ms) {
   if (!ms.flags[FLAG_RAN]) return;
-  pipe_for_each_particle<DYN, PER>(p, tstart, pos_in, ms.cell, false, ms.flags + FLAG_WORK0,
+  pipe_for_each_particle<DYN, PER, CW>(p, tstart, pos_in, ms.cell, false, ms.flags + FLAG_WORK0,
     [&](int k) { prefetch_l1(ang + k); prefetch_l1(idflag + k); },
     [&](int k, real2 r, int c, bool active, real2 F, auto in_cell) {
       const unsigned int id = idflag[k] & ~MAVI_INACTIVE_BIT;
@@ -1758,12 +1767,17 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p_in, const DevArrays 
 #define CALL2(D, P) MAVI_LAUNCH(c, (k_newton_b2<D, P, false, 4>), grid2(p), TPB, PASS2_SMEM, ARGS2)
 #define CALL2C(D, P) MAVI_LAUNCH(c, (k_newton_b2<D, P, true, 4>), grid2(p), TPB, PASS2_SMEM, ARGS2)
     // pipelined persistent kernels (default); more than the 48 KB a kernel gets by default: opt in once per instantiation
-#define CALLP_(D, P, CARRYV)                                                                                        \
+#define CALLP__(D, P, CARRYV, CWV)                                                                                  \
   do {                                                                                                              \
-    static const cudaError_t attr_ = cudaFuncSetAttribute((const void *)k_newton_p<D, P, CARRYV>,                   \
+    static const cudaError_t attr_ = cudaFuncSetAttribute((const void *)k_newton_p<D, P, CARRYV, CWV>,              \
                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);  \
     (void)attr_;                                                                                                    \
-    MAVI_LAUNCH(c, (k_newton_p<D, P, CARRYV>), grid_pipe(p), PIPE_THREADS, PIPE_SMEM, ARGS2);                       \
+    MAVI_LAUNCH(c, (k_newton_p<D, P, CARRYV, CWV>), grid_pipe(p), CWV * 32 + 32, PIPE_SMEM, ARGS2);                 \
+  } while (0)
+#define CALLP_(D, P, CARRYV)                         \
+  do {                                               \
+    if (pipe_cw() == 7) CALLP__(D, P, CARRYV, 7);    \
+    else CALLP__(D, P, CARRYV, 8);                   \
   } while (0)
 #define CALLP(D, P) CALLP_(D, P, false)
 #define CALLPC(D, P) CALLP_(D, P, true)
@@ -1786,6 +1800,7 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p_in, const DevArrays 
     }
 #undef CALL2
 #undef CALL2C
+#undef CALLP__
 #undef CALLP_
 #undef CALLP
 #undef CALLPC
@@ -1839,12 +1854,17 @@ void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArra
   const MoverSink ms = mover_sink(a);
   if (!allp) {
 #define CALL2(D, P) MAVI_LAUNCH(c, (k_self_propelled2<D, P>), grid2(p), TPB, PASS2_SMEM, p, a.tstart, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms)
-#define CALLP(D, P)                                                                                                 \
+#define CALLP_(D, P, CWV)                                                                                           \
   do {                                                                                                              \
-    static const cudaError_t attr_ = cudaFuncSetAttribute((const void *)k_self_propelled_p<D, P>,                   \
+    static const cudaError_t attr_ = cudaFuncSetAttribute((const void *)k_self_propelled_p<D, P, CWV>,              \
                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);  \
     (void)attr_;                                                                                                    \
-    MAVI_LAUNCH(c, (k_self_propelled_p<D, P>), grid_pipe(p), PIPE_THREADS, PIPE_SMEM, p, a.tstart, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms); \
+    MAVI_LAUNCH(c, (k_self_propelled_p<D, P, CWV>), grid_pipe(p), CWV * 32 + 32, PIPE_SMEM, p, a.tstart, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms); \
+  } while (0)
+#define CALLP(D, P)                        \
+  do {                                     \
+    if (pipe_cw() == 7) CALLP_(D, P, 7);   \
+    else CALLP_(D, P, 8);                  \
   } while (0)
     if (!(c.flags & MAVI_FLAG_LEGACY_STAGING)) {
       if (p.dynamics == MAVI_DYN_SZABO) MAVI_DISPATCH2(MAVI_DYN_SZABO, p.periodic, CALLP);
@@ -1854,6 +1874,7 @@ void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArra
       else MAVI_DISPATCH2(MAVI_DYN_RTP, p.periodic, CALL2);
     }
 #undef CALLP
+#undef CALLP_
 #undef CALL2
     MAVI_LAUNCH(c, k_apply_pos_fixes, 1, 32, 0, a.flags, a.fix_idx, a.fix_pos, a.pos[1]);  // no fix-ups here: step counter only
     return;
