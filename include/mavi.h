@@ -230,6 +230,39 @@ enum { MAVI_NEIGH_OFF = 0, MAVI_NEIGH_COUNT = 1, MAVI_NEIGH_LIST = 2 };
 int32_t mavi_rings_set_neighbors(MaviHandle *h, int32_t mode, int32_t type_all, double tol);
 int32_t mavi_rings_download_neighbors(MaviHandle *h, int32_t *count, int32_t *list);
 
+/* ---- sources, sinks and a variable number of rings, src/rings/sources.jl, src/rings/states.jl:173-227 -------------------
+ * RingsSystem(source_cfg = [SourceCfg(...), SinkCfg(...), ...]) with RingsState(active_state = ActiveState(mask)).  At the head
+ * of every step! (src/rings/integration.jl:353-358,523-526), after update_cms!, the list is processed in order:
+ *   sink   : every active ring whose centre of mass (info.cms, as of this step's update_cms!) lies inside the geometry is
+ *            removed (remove_ring!);
+ *   source : size[0] x size[1] spawn areas (bounding box of spawn_pos + pad, laid out from bottom_left with `offset`); every
+ *            area that holds no active particle (is_inside(pos, bbox, pad)) spawns a ring into the FIRST free ring slot
+ *            (add_ring!: rings_pos[:, slot] = spawn_pos + shift, pol = spawn_pol, uid = max(uids) + 1, cms primed);
+ * then update_ids! recomputes the active ids.  num_spawn_pos must equal n_max.
+ * ring_active: [num_rings] ActiveState mask (non-zero = active) of the uploaded state; NULL = all active (FixRingsIds).
+ * spawn_draws: the rand(rng) values consumed by `spawn_pol = :random` sources (pol = draw * 2 pi), in spawn order — the
+ *   reference draws them from system.rng, which no device stream reproduces; NULL = Philox4x32 keyed (seed, spawn count).
+ * Call after mavi_create and before mavi_upload_state. */
+enum { MAVI_SRC_SOURCE = 0, MAVI_SRC_SINK = 1 };
+typedef struct MaviSourceSink {
+  int32_t kind;            /* MAVI_SRC_* */
+  int32_t num_spawn_pos;   /* source: length(SourceCfg.spawn_pos) */
+  const double *spawn_pos; /* source: [2 * num_spawn_pos] */
+  double bottom_left[2];   /* source: SourceCfg.bottom_left */
+  double spawn_pol;        /* source: SourceCfg.spawn_pol; NaN = :random */
+  double pad;              /* source */
+  double offset[2];        /* source */
+  int32_t size[2];         /* source */
+  int32_t sink_geom;       /* sink: MAVI_GEOM_RECT / MAVI_GEOM_CIRCLE */
+  int32_t _pad;
+  double sink_rect_bl[2], sink_rect_len, sink_rect_h; /* sink: RectangleCfg */
+  double sink_circ_center[2], sink_circ_radius;       /* sink: CircleCfg */
+} MaviSourceSink;
+int32_t mavi_rings_set_sources(MaviHandle *h, const MaviSourceSink *list, int32_t n, const uint8_t *ring_active,
+                               const double *spawn_draws, int64_t n_draws);
+/* VarRingsIds after the last step: mask[num_rings], uids[num_rings] (either may be NULL), number of active rings */
+int32_t mavi_rings_download_active(MaviHandle *h, uint8_t *ring_active, int64_t *uids, int64_t *num_active);
+
 /* TimeInfo, src/systems.jl:30-33 (time += dt accumulated in Float64, src/integration.jl:500-503) */
 int32_t mavi_get_time(MaviHandle *h, int64_t *num_steps, double *time);
 int32_t mavi_set_time(MaviHandle *h, int64_t num_steps, double time);

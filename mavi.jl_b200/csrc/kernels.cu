@@ -1273,10 +1273,12 @@ struct PChunk {
   // edges of the cells as axis_in_cell() compares them (lo <= t < hi): staged column j / cell row lr-1 of the tile
   double2 xb[PG_MAX + 2];
   double2 yb[MAVI_TR];
-  // (first staged index of cell row lr-1, end of cell row lr+1) of staged column j, stored [lr-1][j]: the producer's lanes
-  // (one per column) write consecutive words, a consumer reads its three windows j-1, j, j+1 from 24 consecutive bytes
-  int2 cwin_t[MAVI_TR][PG_MAX + 2];
-  __device__ __forceinline__ int2 win(int j, int r) const { return cwin_t[r][j]; }
+  // ext[j][k]: staged index where cell row k-1 of staged column j starts — k = 0 is the cell row ABOVE the tile, k = 1 ..
+  // 32 the tile's own rows, then the row below and, past it, the end of the column.  The window of a particle in cell row
+  // r (0-based) is [ext[j][r], ext[j][r + 3]) = rows r-1 .. r+1.  Row stride 37 words: the producer's lanes (one per
+  // column) and the consumers' lanes (consecutive rows of a column) both access it without bank conflicts.
+  int ext[PG_MAX + 2][MAVI_TR + 5];
+  __device__ __forceinline__ int2 win(int j, int r) const { return make_int2(ext[j][r], ext[j][r + 3]); }
 };
 constexpr int PCH_BYTES = (sizeof(PChunk) + 15) / 16 * 16;
 constexpr int PBUF_BYTES = PCH_BYTES + PSPOS_CAP * (int)sizeof(real2) + POWN_CAP * (int)sizeof(unsigned int);
@@ -1431,14 +1433,16 @@ __device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restr
       ck->gbase[j] = st - base;
       const bool own = j >= 1 && j <= nc;
       unsigned int *lst = s_list + ownoff;
+      int *ext = ck->ext[j];
+      ext[0] = off;
 #pragma unroll 8
-      for (int r = 0; r < MAVI_TR; r++) {    // r = lr - 1
-        const int wa = r == 0 ? off : base + row[r - 1];                                        // start of cell row lr-1
-        const int wb = (r + 3 >= rows + 2) ? end : (r <= 29 ? base + row[r + 2] : base + lt);   // end of cell row lr+1
-        ck->cwin_t[r][j] = make_int2(wa, wb);
-        if (own) {  // own-particle list: the particles of cell row r (rows beyond the grid are empty)
+      for (int r = 0; r <= MAVI_TR + 1; r++) {
+        // start of cell row r: the tile's rows, then the row below (staged right after the tile), then the end of the column
+        const int rr = r <= MAVI_TR ? row[r] : lt;
+        ext[1 + r] = r > rows ? end : base + rr;
+        if (own && r < MAVI_TR) {  // own-particle list: the particles of cell row r (rows beyond the grid are empty)
           const unsigned int tag = ((unsigned int)j << 16) | ((unsigned int)(r + 1) << 24);
-          for (int i = row[r]; i < row[r + 1]; i++) lst[i] = (unsigned int)(base + i) | tag;
+          for (int i = rr; i < row[r + 1]; i++) lst[i] = (unsigned int)(base + i) | tag;
         }
       }
     }

@@ -45,10 +45,33 @@ struct OrSystem {
   int32_t *pn_count; /* [n] */
   int32_t *pn_list;  /* [n][15], pair-enumeration order like the reference */
   int32_t pn_overflow;
+  /* VarRingsIds (src/rings/states.jl:24-43) + sources / sinks (src/rings/sources.jl) */
+  int var_rings;           /* RingsState built with active_state */
+  uint8_t *ring_mask;      /* rings_ids.mask */
+  int64_t *ring_ids;       /* rings_ids.ids[1:num_active] as of the last calc_active_ids! (0-based) */
+  int64_t *ring_uids;
+  int64_t num_active;      /* rings_ids.num_active (add_ring! / remove_ring! change it at once) */
+  struct OrSource *src;
+  int32_t nsrc;
+  double *draws;
+  int64_t n_draws, draw_pos;
   int64_t num_steps;
   double time;
   char err[256];
 };
+
+/* one Source / Sink (src/rings/sources.jl:127-190, :232-251) */
+typedef struct OrSource {
+  int kind, nspawn, nsp;
+  double pad, spawn_pol;
+  double *bbox;       /* [nspawn][4]: bottom_left.x, .y, length, height */
+  double *spawn;      /* bbox_spawn_pos: [nspawn][nsp][2] */
+  uint8_t *is_empty;
+  int32_t **cells;    /* ChunksChecker.ids: per spawn area, linear cell ids (row-1) + rows*(col-1) in col-major scan order */
+  int32_t *ncells;
+  int sink_geom;
+  double sink[5];     /* rect: bl.x, bl.y, length, height | circle: c.x, c.y, radius */
+} OrSource;
 
 /* ------------------------------------------------------------------ helpers */
 
@@ -136,6 +159,10 @@ void mor_rtp_interaction(const double *par, const double *dr, double *f) {
 static inline int64_t ring_of(const OrSystem *s, int64_t idx0) { return idx0 / s->rp.n_max; }
 static inline int32_t ring_type(const OrSystem *s, int64_t ring0) { return s->rp.types ? s->rp.types[ring0] - 1 : 0; }
 static inline int32_t ring_np(const OrSystem *s, int64_t ring0) { return s->rp.num_particles[ring_type(s, ring0)]; }
+
+/* get_rings_ids(state): FixRingsIds -> every ring; VarRingsIds -> ids[1:num_active] (src/rings/states.jl:36-40) */
+static inline int64_t n_ring_ids(const OrSystem *s) { return s->var_rings ? s->num_active : s->rp.num_rings; }
+static inline int64_t ring_id_at(const OrSystem *s, int64_t q) { return s->var_rings ? s->ring_ids[q] : q; }
 
 /* Rings calc_interaction + calc_interaction_force, src/rings/integration.jl:32-77 */
 static void rings_interaction(const OrSystem *s, int64_t i, int64_t j, double *f) {
@@ -674,7 +701,8 @@ static void update_time(OrSystem *s) {
 static void update_continuos_pos(OrSystem *s) {
   if (s->p.spaces[0].wall != MAVI_WALL_PERIODIC) return;
   const int64_t nm = s->rp.n_max;
-  for (int64_t ring = 0; ring < s->rp.num_rings; ring++) {
+  for (int64_t rq = 0; rq < n_ring_ids(s); rq++) {  /* get_rings_ids(state) */
+    const int64_t ring = ring_id_at(s, rq);
     memcpy(s->cont_pos + 2 * ring * nm, s->pos + 2 * ring * nm, sizeof(double) * 2 * (size_t)nm);
     int32_t np = ring_np(s, ring);
     for (int32_t i = 1; i < np; i++) {
@@ -694,7 +722,8 @@ static const double *ring_points(const OrSystem *s, int64_t ring) {
 
 /* update_cms!, src/rings/integration.jl:366-372 */
 static void update_cms(OrSystem *s) {
-  for (int64_t ring = 0; ring < s->rp.num_rings; ring++) {
+  for (int64_t rq = 0; rq < n_ring_ids(s); rq++) {  /* get_rings_ids(state) */
+    const int64_t ring = ring_id_at(s, rq);
     const double *pts = ring_points(s, ring);
     int32_t np = ring_np(s, ring);
     double sx = pts[0], sy = pts[1];
@@ -721,7 +750,8 @@ static void rings_forces(OrSystem *s) {
   mor_pair_forces(s);
   double *forces = s->forces[0];
   const int64_t nm = s->rp.n_max;
-  for (int64_t ring = 0; ring < s->rp.num_rings; ring++) {
+  for (int64_t rq = 0; rq < n_ring_ids(s); rq++) {  /* get_rings_ids(state) */
+    const int64_t ring = ring_id_at(s, rq);
     int32_t np = ring_np(s, ring);
     int32_t t = ring_type(s, ring);
     double k = s->rp.k_spring[t], l = s->rp.l_spring[t];
@@ -737,7 +767,8 @@ static void rings_forces(OrSystem *s) {
       forces[2 * p2] -= f0; forces[2 * p2 + 1] -= f1;
     }
   }
-  for (int64_t ring = 0; ring < s->rp.num_rings; ring++) {
+  for (int64_t rq = 0; rq < n_ring_ids(s); rq++) {  /* get_rings_ids(state) */
+    const int64_t ring = ring_id_at(s, rq);
     int32_t np = ring_np(s, ring);
     int32_t t = ring_type(s, ring);
     double area = calc_area(ring_points(s, ring), np);
@@ -763,7 +794,8 @@ static void rings_update(OrSystem *s, const double *noise) {
   const double dt = s->p.dt;
   double *forces = s->forces[0], *pos = s->pos, *pol_a = s->second;
   const int64_t nm = s->rp.n_max;
-  for (int64_t ring = 0; ring < s->rp.num_rings; ring++) {
+  for (int64_t rq = 0; rq < n_ring_ids(s); rq++) {  /* get_rings_ids(state) */
+    const int64_t ring = ring_id_at(s, rq);
     int32_t np = ring_np(s, ring);
     int32_t t = ring_type(s, ring);
     double vo = s->rp.vo[t], relax_time = s->rp.relax_time[t], mu = s->rp.mobility[t], drot = s->rp.rot_diff[t];
@@ -791,6 +823,260 @@ static void rings_update(OrSystem *s, const double *noise) {
   }
 }
 
+
+/* ------------------------------------------------------------------ sources / sinks / variable ring count */
+
+/* calc_active_ids!, src/rings/states.jl:200-223 (update_ids!) */
+static void calc_active_ids(OrSystem *s) {
+  if (!s->var_rings) return;
+  int64_t pointer = 0, p_pointer = 0;
+  const int64_t nm = s->rp.n_max;
+  memset(s->mask, 0, (size_t)s->n);
+  for (int64_t ring = 0; ring < s->rp.num_rings; ring++) {
+    if (!s->ring_mask[ring]) continue;
+    s->ring_ids[pointer++] = ring;
+    int32_t np = ring_np(s, ring);
+    for (int32_t q = 0; q < np; q++) {
+      s->ids[p_pointer++] = ring * nm + q;
+      s->mask[ring * nm + q] = 1;
+    }
+  }
+  s->n_ids = p_pointer;
+  s->num_active = pointer;
+}
+
+/* is_inside, src/configs.jl:89-93 (RectangleCfg) */
+static int inside_rect(const double *pt, const double *r /* bl.x bl.y len h */, double pad) {
+  int is_x = r[0] - pad <= pt[0] && pt[0] <= r[0] + r[2] + pad;
+  int is_y = r[1] - pad <= pt[1] && pt[1] <= r[1] + r[3] + pad;
+  return is_x && is_y;
+}
+
+/* check_intersection(r1::RectangleCfg, r2::RectangleCfg), src/configs.jl:79-87 (only r1's edges are tested against r2) */
+static int rect_intersect(const double *r1, const double *r2) {
+  int x1 = r2[0] <= r1[0] && r1[0] <= r2[0] + r2[2];
+  int x2 = r2[0] <= r1[0] + r1[2] && r1[0] + r1[2] <= r2[0] + r2[2];
+  int y1 = r2[1] <= r1[1] && r1[1] <= r2[1] + r2[3];
+  int y2 = r2[1] <= r1[1] + r1[3] && r1[1] + r1[3] <= r2[1] + r2[3];
+  return (x1 || x2) && (y1 || y2);
+}
+
+/* Source ctor (src/rings/sources.jl:134-190) and, with chunks, ChunksChecker ctor (:52-119) */
+static int32_t build_source(OrSystem *s, OrSource *o, const MaviSourceSink *c) {
+  memset(o, 0, sizeof *o);
+  o->kind = c->kind;
+  if (c->kind == MAVI_SRC_SINK) {
+    o->sink_geom = c->sink_geom;
+    if (c->sink_geom == MAVI_GEOM_RECT) {
+      o->sink[0] = c->sink_rect_bl[0]; o->sink[1] = c->sink_rect_bl[1]; o->sink[2] = c->sink_rect_len; o->sink[3] = c->sink_rect_h;
+    } else {
+      o->sink[0] = c->sink_circ_center[0]; o->sink[1] = c->sink_circ_center[1]; o->sink[2] = c->sink_circ_radius;
+    }
+    return MAVI_OK;
+  }
+  if (c->num_spawn_pos != s->rp.n_max) {
+    snprintf(s->err, sizeof s->err, "SourceCfg.spawn_pos has %d points, rings_pos[:, ring] has %d", c->num_spawn_pos, s->rp.n_max);
+    return MAVI_ERR_BAD_PARAMS;
+  }
+  const int nsp = c->num_spawn_pos;
+  const double pad = c->pad;
+  o->nsp = nsp; o->pad = pad; o->spawn_pol = c->spawn_pol;
+  double min_x = c->spawn_pos[0], max_x = min_x, min_y = c->spawn_pos[1], max_y = min_y;
+  for (int i = 1; i < nsp; i++) {
+    double x = c->spawn_pos[2 * i], y = c->spawn_pos[2 * i + 1];
+    if (x < min_x) min_x = x;
+    if (x > max_x) max_x = x;
+    if (y < min_y) min_y = y;
+    if (y > max_y) max_y = y;
+  }
+  const double bl_len = max_x - min_x + 2 * pad, bl_h = max_y - min_y + 2 * pad;
+  const int ns = c->size[0] * c->size[1];
+  o->nspawn = ns;
+  o->bbox = (double *)calloc((size_t)ns * 4, sizeof(double));
+  double *bbox_pad = (double *)calloc((size_t)ns * 4, sizeof(double));
+  o->spawn = (double *)calloc((size_t)ns * nsp * 2, sizeof(double));
+  o->is_empty = (uint8_t *)calloc((size_t)ns, 1);
+  int idx = 0;
+  for (int i = 1; i <= c->size[0]; i++)
+    for (int j = 1; j <= c->size[1]; j++, idx++) {
+      double bx = c->bottom_left[0] + ((i - 1) * bl_len + i * c->offset[0]);
+      double by = c->bottom_left[1] + ((j - 1) * bl_h + j * c->offset[1]);
+      double *b = o->bbox + 4 * idx, *bp = bbox_pad + 4 * idx;
+      b[0] = bx; b[1] = by; b[2] = bl_len; b[3] = bl_h;
+      bp[0] = bx - pad; bp[1] = by - pad; bp[2] = bl_len + 2 * pad; bp[3] = bl_h + 2 * pad;
+      /* desloc = bbox.bottom_left - spawn_bbox.bottom_left + (pad, pad); spawn_pos .+ desloc */
+      double dx = bx - min_x + pad, dy = by - min_y + pad;
+      for (int q = 0; q < nsp; q++) {
+        o->spawn[2 * ((size_t)idx * nsp + q)] = c->spawn_pos[2 * q] + dx;
+        o->spawn[2 * ((size_t)idx * nsp + q) + 1] = c->spawn_pos[2 * q + 1] + dy;
+      }
+    }
+  if (s->has_chunks) { /* ChunksChecker(pos, chunks, bbox_pad_vec) */
+    double g[4] = {bbox_pad[0], bbox_pad[1], bbox_pad[2], bbox_pad[3]}; /* global_bbox = sum(bbox_vec), src/configs.jl:68-77 */
+    for (int k = 1; k < ns; k++) {
+      const double *b = bbox_pad + 4 * k;
+      double mx = fmax(g[0] + g[2], b[0] + b[2]), my = fmax(g[1] + g[3], b[1] + b[3]);
+      double mnx = fmin(g[0], b[0]), mny = fmin(g[1], b[1]);
+      g[0] = mnx; g[1] = mny; g[2] = mx - mnx; g[3] = my - mny;
+    }
+    const double tlx = s->p.grid_bl[0], tly = s->p.grid_bl[1] + s->p.grid_h; /* chunk_tl */
+    int found = 0;
+    int64_t sx = 0, ex = 0, sy = 0, ey = 0;
+    for (int64_t i = 1; i <= s->num_cols; i++) {
+      double x1 = tlx + (i - 1) * s->cl, x2 = x1 + s->cl;
+      if (!found && x1 <= g[0] && g[0] <= x2) { found = 1; sx = i; }
+      if (found && x1 >= g[0] + g[2]) { ex = i - 1; break; }
+    }
+    found = 0;
+    for (int64_t i = 1; i <= s->num_rows; i++) {
+      double y2 = tly - (i - 1) * s->ch, y1 = y2 - s->ch;
+      if (!found && y1 <= g[1] + g[3] && g[1] + g[3] <= y2) { found = 1; sy = i; }
+      if (found && y2 <= g[1]) { ey = i - 1; break; }
+    }
+    o->cells = (int32_t **)calloc((size_t)ns, sizeof(int32_t *));
+    o->ncells = (int32_t *)calloc((size_t)ns, sizeof(int32_t));
+    int64_t cap = (ex >= sx ? ex - sx + 1 : 0) * (ey >= sy ? ey - sy + 1 : 0);
+    for (int k = 0; k < ns; k++) o->cells[k] = (int32_t *)calloc((size_t)(cap > 0 ? cap : 1), sizeof(int32_t));
+    for (int64_t col = sx; col <= ex; col++)
+      for (int64_t row = sy; row <= ey; row++) {
+        /* get_chunk_rect, src/chunks.jl:50-59 */
+        double rect[4] = {tlx + (col - 1) * s->cl, tly - row * s->ch, s->cl, s->ch};
+        for (int k = 0; k < ns; k++)
+          if (rect_intersect(rect, bbox_pad + 4 * k)) o->cells[k][o->ncells[k]++] = (int32_t)((row - 1) + s->num_rows * (col - 1));
+      }
+  }
+  free(bbox_pad);
+  return MAVI_OK;
+}
+
+int32_t mor_rings_set_sources(OrSystem *s, const MaviSourceSink *list, int32_t n, const uint8_t *ring_active,
+                              const double *spawn_draws, int64_t n_draws) {
+  if (s->p.dynamics != MAVI_DYN_RINGS || n < 0 || (n > 0 && !list)) return MAVI_ERR_BAD_PARAMS;
+  const int64_t nr = s->rp.num_rings;
+  if (ring_active) {
+    s->var_rings = 1;
+    s->ring_mask = (uint8_t *)calloc((size_t)nr + 1, 1);
+    s->ring_ids = (int64_t *)calloc((size_t)nr + 1, sizeof(int64_t));
+    s->ring_uids = (int64_t *)calloc((size_t)nr + 1, sizeof(int64_t));
+    for (int64_t r = 0; r < nr; r++) {
+      s->ring_mask[r] = ring_active[r] != 0;
+      s->ring_ids[r] = r;
+      s->ring_uids[r] = r + 1; /* uids = Vector(1:num_rings) */
+    }
+  } else if (n > 0) {
+    snprintf(s->err, sizeof s->err, "sources / sinks need a RingsState with active_state (VarRingsIds)");
+    return MAVI_ERR_BAD_PARAMS;
+  }
+  s->nsrc = n;
+  s->src = (OrSource *)calloc((size_t)(n > 0 ? n : 1), sizeof(OrSource));
+  for (int k = 0; k < n; k++) {
+    int32_t st = build_source(s, &s->src[k], &list[k]);
+    if (st) return st;
+  }
+  if (spawn_draws && n_draws > 0) {
+    s->draws = dup_d(spawn_draws, n_draws);
+    s->n_draws = n_draws;
+  }
+  s->draw_pos = 0;
+  return MAVI_OK;
+}
+
+int32_t mor_rings_download_active(OrSystem *s, uint8_t *ring_active, int64_t *uids, int64_t *num_active) {
+  if (s->p.dynamics != MAVI_DYN_RINGS) return MAVI_ERR_BAD_PARAMS;
+  const int64_t nr = s->rp.num_rings;
+  for (int64_t r = 0; r < nr; r++) {
+    if (ring_active) ring_active[r] = s->var_rings ? s->ring_mask[r] : 1;
+    if (uids) uids[r] = s->var_rings ? s->ring_uids[r] : r + 1;
+  }
+  if (num_active) *num_active = s->var_rings ? s->num_active : nr;
+  return MAVI_OK;
+}
+
+/* update_area_empty!, src/rings/sources.jl:191-225 */
+static void update_area_empty(OrSystem *s, OrSource *o) {
+  for (int k = 0; k < o->nspawn; k++) {
+    o->is_empty[k] = 1;
+    const double *bbox = o->bbox + 4 * k;
+    if (s->has_chunks) { /* ChunksChecker: the chunk lists of the LAST update_chunks! (stale by one step), current positions */
+      for (int c = 0; c < o->ncells[k] && o->is_empty[k]; c++) {
+        int64_t cell = o->cells[k][c];
+        const int64_t *chunk = s->chunk_particles + cell * s->nc;
+        for (int64_t q = 0; q < s->num_in_chunk[cell]; q++)
+          if (inside_rect(s->pos + 2 * chunk[q], bbox, o->pad)) { o->is_empty[k] = 0; break; }
+      }
+    } else { /* PosChecker: get_ids(part_ids) as of the last update_ids! */
+      for (int64_t q = 0; q < s->n_ids; q++)
+        if (inside_rect(s->pos + 2 * s->ids[q], bbox, o->pad)) { o->is_empty[k] = 0; break; }
+    }
+  }
+}
+
+/* add_ring!, src/rings/states.jl:173-187 */
+static int64_t add_ring(OrSystem *s, const double *pts, double pol) {
+  const int64_t nm = s->rp.n_max;
+  for (int64_t i = 0; i < s->rp.num_rings; i++) {
+    if (s->ring_mask[i]) continue;
+    memcpy(s->pos + 2 * i * nm, pts, sizeof(double) * 2 * (size_t)nm);
+    s->second[i] = pol;
+    s->ring_mask[i] = 1;
+    int64_t mx = s->ring_uids[0];
+    for (int64_t r = 1; r < s->rp.num_rings; r++)
+      if (s->ring_uids[r] > mx) mx = s->ring_uids[r];
+    s->ring_uids[i] = mx + 1;
+    s->num_active += 1;
+    return i;
+  }
+  return -1;
+}
+
+/* update_sources!, src/rings/integration.jl:353-358; process_source! / process_sink!, src/rings/sources.jl:229-263 */
+static int32_t update_sources(OrSystem *s) {
+  for (int k = 0; k < s->nsrc; k++) {
+    OrSource *o = &s->src[k];
+    if (o->kind == MAVI_SRC_SINK) {
+      /* for ring_id in get_rings_ids(state): the view ids[1:num_active] is taken once, remove_ring! only lowers num_active */
+      const int64_t nview = s->num_active;
+      for (int64_t q = 0; q < nview; q++) {
+        const int64_t ring = s->ring_ids[q];
+        const double *cm = s->cms + 2 * ring;
+        int in;
+        if (o->sink_geom == MAVI_GEOM_RECT) in = inside_rect(cm, o->sink, 0.0);
+        else {
+          double ex = cm[0] - o->sink[0], ey = cm[1] - o->sink[1];
+          in = ex * ex + ey * ey <= o->sink[2] * o->sink[2];
+        }
+        if (in) { /* remove_ring!, src/rings/states.jl:189-193 */
+          s->ring_mask[ring] = 0;
+          s->num_active -= 1;
+        }
+      }
+      continue;
+    }
+    update_area_empty(s, o);
+    for (int a = 0; a < o->nspawn; a++) {
+      if (!o->is_empty[a]) continue;
+      double pol = o->spawn_pol;
+      if (isnan(pol)) { /* get_spawn_pol(::RandomPol): rand(rng, T) * 2 * pi — drawn BEFORE add_ring! looks for a slot */
+        if (s->draw_pos >= s->n_draws) {
+          snprintf(s->err, sizeof s->err, "spawn_draws exhausted after %lld draws", (long long)s->n_draws);
+          return MAVI_ERR_BAD_PARAMS;
+        }
+        pol = s->draws[s->draw_pos++] * 2 * M_PI;
+      }
+      int64_t ring = add_ring(s, o->spawn + 2 * (size_t)a * o->nsp, pol);
+      if (ring >= 0) { /* system.info.cms[ring_id] = sum(state.rings_pos[1:num_p, ring_id]) / num_p */
+        int32_t np = ring_np(s, ring);
+        const double *pts = s->pos + 2 * ring * s->rp.n_max;
+        double sx = pts[0], sy = pts[1];
+        for (int32_t i = 1; i < np; i++) { sx += pts[2 * i]; sy += pts[2 * i + 1]; }
+        s->cms[2 * ring] = sx / np;
+        s->cms[2 * ring + 1] = sy / np;
+      }
+    }
+  }
+  return MAVI_OK;
+}
+
 /* ------------------------------------------------------------------ steps */
 
 static int64_t noise_stride(const OrSystem *s) {
@@ -807,7 +1093,8 @@ static int32_t step_once(OrSystem *s, const double *noise) {
   int32_t st;
   if (s->p.dynamics == MAVI_DYN_RINGS) {
     update_cms(s);
-    /* update_sources! / update_ids!: fixed ring set here */
+    if ((st = update_sources(s))) return st;
+    calc_active_ids(s); /* update_ids! */
     if ((st = mor_update_chunks(s))) return st;
     update_continuos_pos(s);
     mor_clean_forces(s);
@@ -1013,6 +1300,14 @@ void mor_destroy(OrSystem *s) {
   free(s->chunk_particles); free(s->num_in_chunk); free(s->neigh); free(s->neigh_n);
   free(s->cont_pos); free(s->areas); free(s->cms);
   free(s->pn_count); free(s->pn_list);
+  free(s->ring_mask); free(s->ring_ids); free(s->ring_uids); free(s->draws);
+  for (int k = 0; k < s->nsrc; k++) {
+    OrSource *o = &s->src[k];
+    free(o->bbox); free(o->spawn); free(o->is_empty);
+    if (o->cells) for (int a = 0; a < o->nspawn; a++) free(o->cells[a]);
+    free(o->cells); free(o->ncells);
+  }
+  free(s->src);
   free(s);
 }
 
@@ -1052,12 +1347,16 @@ int32_t mor_upload_state(OrSystem *s, const double *pos, const double *second, c
   if (second) memcpy(s->second, second, sizeof(double) * (size_t)n_second);
   s->n_ids = 0;
   if (s->p.dynamics == MAVI_DYN_RINGS) {
-    /* FixRingsIds, src/rings/states.jl:45-61 */
-    for (int64_t ring = 0; ring < s->rp.num_rings; ring++) {
-      int32_t np = ring_np(s, ring);
-      for (int64_t q = 0; q < s->rp.n_max; q++) {
-        s->mask[ring * s->rp.n_max + q] = q < np;
-        if (q < np) s->ids[s->n_ids++] = ring * s->rp.n_max + q;
+    if (s->var_rings) {
+      calc_active_ids(s); /* RingsState ctor: update_ids!(state), src/rings/states.jl:121 */
+    } else {
+      /* FixRingsIds, src/rings/states.jl:45-61 */
+      for (int64_t ring = 0; ring < s->rp.num_rings; ring++) {
+        int32_t np = ring_np(s, ring);
+        for (int64_t q = 0; q < s->rp.n_max; q++) {
+          s->mask[ring * s->rp.n_max + q] = q < np;
+          if (q < np) s->ids[s->n_ids++] = ring * s->rp.n_max + q;
+        }
       }
     }
   } else {

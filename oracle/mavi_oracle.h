@@ -49,6 +49,10 @@ int32_t mor_energies(OrSystem *s, int32_t pe_mode, double *ke, double *pe);
 int32_t mor_rings_download_info(OrSystem *s, double *areas, double *cms, double *cont_pos);
 int32_t mor_rings_set_neighbors(OrSystem *s, int32_t mode, int32_t type_all, double tol);
 int32_t mor_rings_download_neighbors(OrSystem *s, int32_t *count, int32_t *list);
+/* sources / sinks / variable ring count (src/rings/sources.jl, src/rings/states.jl:173-227); before mor_upload_state */
+int32_t mor_rings_set_sources(OrSystem *s, const MaviSourceSink *list, int32_t n, const uint8_t *ring_active,
+                              const double *spawn_draws, int64_t n_draws);
+int32_t mor_rings_download_active(OrSystem *s, uint8_t *ring_active, int64_t *uids, int64_t *num_active);
 int32_t mor_get_time(OrSystem *s, int64_t *num_steps, double *time);
 
 /* fine-grained operators for unit tests (each is one reference function) */
