@@ -34,6 +34,7 @@ FLAG_SMALL_BLOCKS = 8
 FLAG_SLAB_SELF = 16
 FLAG_LEGACY_STAGING = 32  # A/B: round-1 force kernels (include/mavi.h)
 NEIGH_OFF, NEIGH_COUNT, NEIGH_LIST = range(3)
+SRC_SOURCE, SRC_SINK = range(2)
 NEIGH_MAX = 15
 
 
@@ -60,6 +61,16 @@ class MaviRingsParams(C.Structure):
         ("num_particles", C.POINTER(C.c_int32)),
         ("interaction", C.POINTER(C.c_double)),
         ("types", C.POINTER(C.c_int32)),
+    ]
+
+
+class MaviSourceSink(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("num_spawn_pos", C.c_int32), ("spawn_pos", C.POINTER(C.c_double)),
+        ("bottom_left", C.c_double * 2), ("spawn_pol", C.c_double), ("pad", C.c_double), ("offset", C.c_double * 2),
+        ("size", C.c_int32 * 2), ("sink_geom", C.c_int32), ("_pad", C.c_int32),
+        ("sink_rect_bl", C.c_double * 2), ("sink_rect_len", C.c_double), ("sink_rect_h", C.c_double),
+        ("sink_circ_center", C.c_double * 2), ("sink_circ_radius", C.c_double),
     ]
 
 
@@ -104,6 +115,8 @@ SIGNATURES = {
     "mavi_rings_download_info": (C.c_int32, [_H, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mavi_rings_set_neighbors": (C.c_int32, [_H, C.c_int32, C.c_int32, C.c_double]),
     "mavi_rings_download_neighbors": (C.c_int32, [_H, C.c_void_p, C.c_void_p]),
+    "mavi_rings_set_sources": (C.c_int32, [_H, C.POINTER(MaviSourceSink), C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]),
+    "mavi_rings_download_active": (C.c_int32, [_H, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
     "mavi_get_time": (C.c_int32, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "mavi_set_time": (C.c_int32, [_H, C.c_int64, C.c_double]),
     "mavi_sync": (C.c_int32, [_H]),

@@ -1256,8 +1256,8 @@ __device__ __forceinline__ void for_each_block_particle(const DevParams &p, cons
 // Float32 build: a float2 run is only 8-byte aligned, below the 16 bytes bulk copies need, so there the producer warp
 // copies the runs itself (plain loads / stores) before it arrives on `full`.
 // =========================================================================================================
-// consumer warps per CTA (template parameter CW): 8 -> 288 threads, 72 registers (a few spills in the particle loop),
-// 24 consumer warps per SM; 7 -> 256 threads, 80 registers, no spills, 21 consumer warps per SM.  MAVI_PIPE_CW picks.
+// warps per CTA: CW consumer warps + NP producer warps (template parameters; see pipe_cfg()).  7 + 2 = 288 threads, 72
+// registers, 21 consumer and 6 producer warps per SM (default); 8 + 1: 24 consumer warps, one producer per CTA.
 constexpr int PIPE_CTAS_PER_SM = 3;
 constexpr int PG_MAX = 30;                           // own columns per chunk (+ two side columns: one producer lane each)
 constexpr int PSPOS_CAP = 1280;                      // staged positions per chunk
@@ -1283,7 +1283,7 @@ struct PChunk {
 constexpr int PCH_BYTES = (sizeof(PChunk) + 15) / 16 * 16;
 constexpr int PBUF_BYTES = PCH_BYTES + PSPOS_CAP * (int)sizeof(real2) + POWN_CAP * (int)sizeof(unsigned int);
 constexpr int PTS_BYTES = 32 * (MAVI_TR + 1) * (int)sizeof(int);  // producer scratch: tstart rows of the staged columns
-constexpr int PIPE_SMEM = 64 + 2 * PBUF_BYTES + PTS_BYTES;       // [4 mbarriers | buffer 0 | buffer 1 | producer scratch]
+constexpr int PIPE_SMEM = 64 + 2 * PBUF_BYTES + 2 * PTS_BYTES;   // [4 mbarriers | buffer 0 | buffer 1 | scratch of producer 0, 1]
 
 __device__ __forceinline__ unsigned int smem_u32(const void *ptr) { return (unsigned int)__cvta_generic_to_shared(ptr); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
@@ -1454,11 +1454,11 @@ __device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restr
 
 // Drives a pipelined force kernel: pre(k) before and body(k, r, cell, active, F) after the pair force F of every
 // particle slot (F = 0 for the inactive tail).  work: device counter of the next tile block (see FLAG_WORK*).
-template <int DYN, bool PER, int PIPE_CW, typename Pre, typename Body>
+template <int DYN, bool PER, int PIPE_CW, int NPROD, typename Pre, typename Body>
 __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const int *__restrict__ tstart,
                                                        const real2 *__restrict__ pos, const int *__restrict__ cell,
                                                        bool exact_minimg, int *__restrict__ work, Pre &&pre, Body &&body) {
-  constexpr int PIPE_CT = PIPE_CW * 32;  // consumer threads; the producer is the LAST warp of the CTA
+  constexpr int PIPE_CT = PIPE_CW * 32;  // consumer threads; the producers are the LAST warp(s) of the CTA
   extern __shared__ __align__(16) unsigned char dsm[];
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(dsm);  // [0,1] full, [2,3] empty
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1474,9 +1474,14 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the async proxy (bulk copies) sees the initialised barriers
   }
   __syncthreads();  // the only CTA barrier of the kernel
-  if (w == PIPE_CW) {
-    // ================================ producer warp ================================
-    int k = 0;
+  if (w >= PIPE_CW) {
+    // ================================ producer warp(s) ================================
+    // One warp executes the staging code at ~12 cycles per instruction (short dependent chains), which is as long as the
+    // eight consumer warps need for a chunk (profiles/r02_ncu_newton_summary.md): with NPROD = 2 each producer owns ONE of
+    // the two buffers and the consumers alternate between them, so two chunks are staged concurrently.
+    const int pw = w - PIPE_CW;
+    int *s_ts = reinterpret_cast<int *>(dsm + 64 + 2 * (size_t)PBUF_BYTES + (size_t)pw * PTS_BYTES);
+    int k = 0;  // chunks staged by this producer
     for (;;) {
       int item = 0;
       if (lane == 0) item = atomicAdd(work, 1);
@@ -1489,20 +1494,24 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
       const int c_begin = p.ord_col0 + bcol * p.blk_cols;
       const int c_end = min(c_begin + p.blk_cols, p.ord_col0 + p.ord_cols);
       for (int cs = c_begin; cs < c_end; k++) {
-        const int b = k & 1;
-        if (k >= 2) mbar_wait(&bars[2 + b], (unsigned int)(((k >> 1) & 1) ^ 1));  // the consumers released this buffer
+        const int b = NPROD == 2 ? pw : (k & 1);
+        const int u = NPROD == 2 ? k : (k >> 1);  // how often this buffer has been filled before
+        if (u >= 1) mbar_wait(&bars[2 + b], (unsigned int)((u - 1) & 1));  // the consumers released its previous contents
         unsigned char *buf = dsm + 64 + (size_t)b * PBUF_BYTES;
         cs += pipe_stage<PER>(p, tstart, pos, tr, cs, c_end - cs, exact_minimg, reinterpret_cast<PChunk *>(buf),
                               reinterpret_cast<real2 *>(buf + PCH_BYTES),
-                              reinterpret_cast<unsigned int *>(buf + PCH_BYTES + PSPOS_CAP * sizeof(real2)), &bars[b],
-                              reinterpret_cast<int *>(dsm + 64 + 2 * (size_t)PBUF_BYTES));
+                              reinterpret_cast<unsigned int *>(buf + PCH_BYTES + PSPOS_CAP * sizeof(real2)), &bars[b], s_ts);
       }
     }
-    const int b = k & 1;  // end marker
-    if (k >= 2) mbar_wait(&bars[2 + b], (unsigned int)(((k >> 1) & 1) ^ 1));
-    if (lane == 0) {
-      reinterpret_cast<PChunk *>(dsm + 64 + (size_t)b * PBUF_BYTES)->state = 0;
-      mbar_arrive(&bars[b]);
+    // end marker(s): one per buffer this producer feeds
+    for (int e = 0; e < (NPROD == 2 ? 1 : 2); e++, k++) {
+      const int b = NPROD == 2 ? pw : (k & 1);
+      const int u = NPROD == 2 ? k : (k >> 1);
+      if (u >= 1) mbar_wait(&bars[2 + b], (unsigned int)((u - 1) & 1));
+      if (lane == 0) {
+        reinterpret_cast<PChunk *>(dsm + 64 + (size_t)b * PBUF_BYTES)->state = 0;
+        mbar_arrive(&bars[b]);
+      }
     }
     return;
   }
@@ -1515,14 +1524,20 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
       body(k, pos[k], 0, false, make_real2(0.0, 0.0), InCellNone{});
     }
   }
-  for (int kc = 0;; kc++) {
-    const int b = kc & 1;
+  // the two buffers are consumed alternately; uses = how often each was consumed (barrier phase), done = its end marker seen
+  int uses = 0;   // bits 0..15: buffer 0, bits 16..31: buffer 1
+  int done = 0;   // bit b
+  for (int b = 0; done != 3; b ^= 1) {
+    if (done & (1 << b)) continue;
     unsigned char *buf = dsm + 64 + (size_t)b * PBUF_BYTES;
     const PChunk *ck = reinterpret_cast<const PChunk *>(buf);
     const real2 *s_pos = reinterpret_cast<const real2 *>(buf + PCH_BYTES);
     const unsigned int *s_list = reinterpret_cast<const unsigned int *>(buf + PCH_BYTES + PSPOS_CAP * sizeof(real2));
-    mbar_wait(&bars[b], (unsigned int)((kc >> 1) & 1));
-    if (!ck->state) break;
+    mbar_wait(&bars[b], (unsigned int)((uses >> (16 * b)) & 1));
+    if (!ck->state) {
+      done |= 1 << b;
+      continue;
+    }
     const int cs = ck->cs, r0 = ck->tr * MAVI_TR;
     if (ck->ok) {
       const int nown = ck->nown;
@@ -1553,16 +1568,19 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&bars[2 + b]);  // this warp is done with the buffer
+    uses += 1 << (16 * b);
   }
 }
 
-// consumer warps per CTA of the pipelined kernels (A/B switch, see PIPE_CTAS_PER_SM)
-static inline int pipe_cw() {
-  static const int cw = [] {
-    const char *e = getenv("MAVI_PIPE_CW");
-    return (e && atoi(e) == 7) ? 7 : 8;
+// (consumer warps) * 10 + (producer warps) per CTA of the pipelined kernels: 72 (default), 82, 71, 81 — MAVI_PIPE_CFG is the
+// A/B switch of the measurements in profiles/r02_ncu_newton_summary.md
+static inline int pipe_cfg() {
+  static const int cfg = [] {
+    const char *e = getenv("MAVI_PIPE_CFG");
+    const int v = e ? atoi(e) : 72;
+    return (v == 81 || v == 71 || v == 82) ? v : 72;
   }();
-  return cw;
+  return cfg;
 }
 
 static inline int grid_pipe(const DevParams &p) {
@@ -1649,24 +1667,24 @@ __global__ void __launch_bounds__(TPB, MINB) k_newton_b2(const __grid_constant__
 }
 
 // the pipelined version of k_newton_b2 (default); work item counter: FLAG_WORK0 / FLAG_WORK1 (boundary-block launch)
-template <int DYN, bool PER, bool CARRY, int CW>
-__global__ void __launch_bounds__(CW * 32 + 32, PIPE_CTAS_PER_SM) k_newton_p(
+template <int DYN, bool PER, bool CARRY, int CW, int NP>
+__global__ void __launch_bounds__((CW + NP) * 32, PIPE_CTAS_PER_SM) k_newton_p(
     const __grid_constant__ DevParams p, const int *__restrict__ tstart, const real2 *__restrict__ pos_in,
     real2 *__restrict__ vel, const real2 *f1, real2 *f2, real2 *f1_next, real2 *__restrict__ pos_next,
     int *__restrict__ fix_idx, real2 *__restrict__ fix_pos, const __grid_constant__ MoverSink ms) {
   if (!ms.flags[FLAG_RAN]) return;
   const bool exact = ms.flags[FLAG_BIGMOVE] != 0 || (p.slab && p.blk_mode == 2);
-  pipe_for_each_particle<DYN, PER, CW>(p, tstart, pos_in, ms.cell, exact, ms.flags + (p.blk_mode == 2 ? FLAG_WORK1 : FLAG_WORK0),
+  pipe_for_each_particle<DYN, PER, CW, NP>(p, tstart, pos_in, ms.cell, exact, ms.flags + (p.blk_mode == 2 ? FLAG_WORK1 : FLAG_WORK0),
                                        MAVI_NEWTON_B_LAMBDAS);
 }
 
-template <int DYN, bool PER, int CW>
-__global__ void __launch_bounds__(CW * 32 + 32, PIPE_CTAS_PER_SM) k_self_propelled_p(
+template <int DYN, bool PER, int CW, int NP>
+__global__ void __launch_bounds__((CW + NP) * 32, PIPE_CTAS_PER_SM) k_self_propelled_p(
     const __grid_constant__ DevParams p, const int *__restrict__ tstart, const unsigned int *__restrict__ idflag,
     const real2 *__restrict__ pos_in, real *__restrict__ ang, real2 *__restrict__ pos_out, real2 *__restrict__ force,
     const real *__restrict__ noise, unsigned long long step, const __grid_constant__ MoverSink ms) {
   if (!ms.flags[FLAG_RAN]) return;
-  pipe_for_each_particle<DYN, PER, CW>(p, tstart, pos_in, ms.cell, false, ms.flags + FLAG_WORK0,
+  pipe_for_each_particle<DYN, PER, CW, NP>(p, tstart, pos_in, ms.cell, false, ms.flags + FLAG_WORK0,
     [&](int k) { prefetch_l1(ang + k); prefetch_l1(idflag + k); },
     [&](int k, real2 r, int c, bool active, real2 F, auto in_cell) {
       const unsigned int id = idflag[k] & ~MAVI_INACTIVE_BIT;
@@ -1771,17 +1789,21 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p_in, const DevArrays 
 #define CALL2(D, P) MAVI_LAUNCH(c, (k_newton_b2<D, P, false, 4>), grid2(p), TPB, PASS2_SMEM, ARGS2)
 #define CALL2C(D, P) MAVI_LAUNCH(c, (k_newton_b2<D, P, true, 4>), grid2(p), TPB, PASS2_SMEM, ARGS2)
     // pipelined persistent kernels (default); more than the 48 KB a kernel gets by default: opt in once per instantiation
-#define CALLP__(D, P, CARRYV, CWV)                                                                                  \
+#define CALLP__(D, P, CARRYV, CWV, NPV)                                                                             \
   do {                                                                                                              \
-    static const cudaError_t attr_ = cudaFuncSetAttribute((const void *)k_newton_p<D, P, CARRYV, CWV>,              \
+    static const cudaError_t attr_ = cudaFuncSetAttribute((const void *)k_newton_p<D, P, CARRYV, CWV, NPV>,         \
                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);  \
     (void)attr_;                                                                                                    \
-    MAVI_LAUNCH(c, (k_newton_p<D, P, CARRYV, CWV>), grid_pipe(p), CWV * 32 + 32, PIPE_SMEM, ARGS2);                 \
+    MAVI_LAUNCH(c, (k_newton_p<D, P, CARRYV, CWV, NPV>), grid_pipe(p), (CWV + NPV) * 32, PIPE_SMEM, ARGS2);         \
   } while (0)
-#define CALLP_(D, P, CARRYV)                         \
-  do {                                               \
-    if (pipe_cw() == 7) CALLP__(D, P, CARRYV, 7);    \
-    else CALLP__(D, P, CARRYV, 8);                   \
+#define CALLP_(D, P, CARRYV)                               \
+  do {                                                     \
+    switch (pipe_cfg()) {                                  \
+      case 81: CALLP__(D, P, CARRYV, 8, 1); break;         \
+      case 71: CALLP__(D, P, CARRYV, 7, 1); break;         \
+      case 82: CALLP__(D, P, CARRYV, 8, 2); break;         \
+      default: CALLP__(D, P, CARRYV, 7, 2); break;         \
+    }                                                      \
   } while (0)
 #define CALLP(D, P) CALLP_(D, P, false)
 #define CALLPC(D, P) CALLP_(D, P, true)
@@ -1858,17 +1880,21 @@ void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArra
   const MoverSink ms = mover_sink(a);
   if (!allp) {
 #define CALL2(D, P) MAVI_LAUNCH(c, (k_self_propelled2<D, P>), grid2(p), TPB, PASS2_SMEM, p, a.tstart, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms)
-#define CALLP_(D, P, CWV)                                                                                           \
+#define CALLP_(D, P, CWV, NPV)                                                                                      \
   do {                                                                                                              \
-    static const cudaError_t attr_ = cudaFuncSetAttribute((const void *)k_self_propelled_p<D, P, CWV>,              \
+    static const cudaError_t attr_ = cudaFuncSetAttribute((const void *)k_self_propelled_p<D, P, CWV, NPV>,         \
                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);  \
     (void)attr_;                                                                                                    \
-    MAVI_LAUNCH(c, (k_self_propelled_p<D, P, CWV>), grid_pipe(p), CWV * 32 + 32, PIPE_SMEM, p, a.tstart, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms); \
+    MAVI_LAUNCH(c, (k_self_propelled_p<D, P, CWV, NPV>), grid_pipe(p), (CWV + NPV) * 32, PIPE_SMEM, p, a.tstart, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms); \
   } while (0)
-#define CALLP(D, P)                        \
-  do {                                     \
-    if (pipe_cw() == 7) CALLP_(D, P, 7);   \
-    else CALLP_(D, P, 8);                  \
+#define CALLP(D, P)                                  \
+  do {                                               \
+    switch (pipe_cfg()) {                            \
+      case 81: CALLP_(D, P, 8, 1); break;            \
+      case 71: CALLP_(D, P, 7, 1); break;            \
+      case 82: CALLP_(D, P, 8, 2); break;            \
+      default: CALLP_(D, P, 7, 2); break;            \
+    }                                                \
   } while (0)
     if (!(c.flags & MAVI_FLAG_LEGACY_STAGING)) {
       if (p.dynamics == MAVI_DYN_SZABO) MAVI_DISPATCH2(MAVI_DYN_SZABO, p.periodic, CALLP);

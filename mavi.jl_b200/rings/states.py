@@ -11,8 +11,6 @@ import numpy as np
 
 class RingsState:
     def __init__(self, *, rings_pos, pol, num_particles=None, types=None, active_state=None):
-        if active_state is not None:
-            raise NotImplementedError("variable ring count (sources/sinks) is a 'next' row (SURVEY.md 8f #3)")
         rp = np.asarray(rings_pos)
         T = np.float32 if rp.dtype == np.float32 else np.float64  # element type of the state (Float32 mode keeps it)
         rp = rp.astype(T, copy=False)
@@ -27,6 +25,10 @@ class RingsState:
             raise ValueError("argument 'types' is empty!")
         self.num_particles = self.n_max if num_particles is None else num_particles
         self.types = None if types is None else np.ascontiguousarray(types, dtype=np.int32)  # 1-based like Julia
+        # VarRingsIds (src/rings/states.jl:24-43, :104-113): active_state = ActiveState(mask over rings) makes the number of
+        # rings variable (sources / sinks); None -> FixRingsIds (every ring active)
+        self.ring_mask = None if active_state is None else active_state.get_active_mask(self.num_rings)
+        self.uids = None if active_state is None else np.arange(1, self.num_rings + 1, dtype=np.int64)
 
     @property
     def second(self):

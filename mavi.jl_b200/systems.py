@@ -38,7 +38,7 @@ def _ptr(a):
 
 class System:
     def __init__(self, *, state, space_cfg: SpaceCfg, dynamic_cfg, int_cfg, info=None, debug_info=None,
-                 time_info=None, sys_type="standard", rng=None, p_neighbors_cfg=None):
+                 time_info=None, sys_type="standard", rng=None, p_neighbors_cfg=None, source_cfg=None, spawn_draws=None):
         self.state = state
         self.space_cfg = space_cfg
         self.dynamic_cfg = dynamic_cfg
@@ -66,6 +66,16 @@ class System:
             mode = capi.NEIGH_COUNT if p_neighbors_cfg.only_count else capi.NEIGH_LIST
             self._check(self._lib.mavi_rings_set_neighbors(self._h, mode, int(p_neighbors_cfg.type == "all"),
                                                            float(p_neighbors_cfg.tol)))
+        self.source_cfg = source_cfg
+        ring_mask = getattr(state, "ring_mask", None)
+        if source_cfg is not None or ring_mask is not None:
+            # RingsSystem(source_cfg=...) / RingsState(active_state=...): sources, sinks and the VarRingsIds mask go to the
+            # device before the upload (src/rings/rings.jl:162-185; the constructor's update_ids! sees the mask)
+            from .rings.sources import lower_sources
+            arr, n = lower_sources(source_cfg, self._lowered.keep) if source_cfg is not None else (None, 0)
+            draws = None if spawn_draws is None else np.ascontiguousarray(spawn_draws, dtype=np.float64)
+            self._check(self._lib.mavi_rings_set_sources(self._h, arr, n, _ptr(ring_mask), _ptr(draws),
+                                                         0 if draws is None else len(draws)))
         self._slab = int_cfg.device.world > 1 or bool(int_cfg.device.flags & capi.FLAG_SLAB_SELF)
         if self._slab:
             ids = getattr(state, "ids", None)
@@ -263,6 +273,19 @@ class System:
         lst = None if only else np.empty((self._n, capi.NEIGH_MAX), dtype=np.int32)
         self._check(self._lib.mavi_rings_download_neighbors(self._h, _ptr(count), _ptr(lst)))
         return count, (None if only else [lst[i, :count[i]].tolist() for i in range(self._n)])
+
+    def rings_active(self):
+        """(mask[num_rings], uids[num_rings], num_active): VarRingsIds after the last step (sources / sinks add and remove
+        rings on the device); also refreshes `state.ring_mask` / `state.uids`."""
+        nr = self.state.num_rings
+        mask = np.empty(nr, dtype=np.uint8)
+        uids = np.empty(nr, dtype=np.int64)
+        na = C.c_int64()
+        self._check(self._lib.mavi_rings_download_active(self._h, _ptr(mask), _ptr(uids), C.byref(na)))
+        if getattr(self.state, "ring_mask", None) is not None:
+            self.state.ring_mask[...] = mask
+            self.state.uids[...] = uids
+        return mask, uids, na.value
 
     def rings_info(self):
         nr = self.state.num_rings

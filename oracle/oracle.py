@@ -79,6 +79,7 @@ def load(fast=False):
         "mor_energies": (i32, [H, i32, C.POINTER(dbl), C.POINTER(dbl)]),
         "mor_rings_download_info": (i32, [H, vp, vp, vp]),
         "mor_rings_set_neighbors": (i32, [H, i32, i32, dbl]), "mor_rings_download_neighbors": (i32, [H, vp, vp]),
+        "mor_rings_set_sources": (i32, [H, vp, i32, vp, vp, i64]), "mor_rings_download_active": (i32, [H, vp, vp, C.POINTER(i64)]),
         "mor_get_time": (i32, [H, C.POINTER(i64), C.POINTER(dbl)]),
         "mor_clean_forces": (None, [H]), "mor_update_chunks": (i32, [H]), "mor_pair_forces": (None, [H]),
         "mor_walls_forces": (None, [H]), "mor_walls": (None, [H]), "mor_update_verlet": (None, [H]),
@@ -109,7 +110,8 @@ class OracleError(RuntimeError):
 class OracleSystem:
     """The oracle behind the same surface as the host mirror's `System` (built from the same configs)."""
 
-    def __init__(self, *, state, space_cfg, dynamic_cfg, int_cfg, lower, threads=1, p_neighbors_cfg=None, fast=False):
+    def __init__(self, *, state, space_cfg, dynamic_cfg, int_cfg, lower, threads=1, p_neighbors_cfg=None, fast=False,
+                 source_cfg=None, spawn_draws=None):
         self.lib = load(fast=fast)  # fast: the -O3 -march=native timing build (never used for parity checks)
         self.state = state
         self._lowered = lower(state, space_cfg, dynamic_cfg, int_cfg)
@@ -123,6 +125,15 @@ class OracleSystem:
         if p_neighbors_cfg is not None:  # RingsSystem(p_neighbors_cfg=...), src/rings/rings.jl:143-158
             self._check(self.lib.mor_rings_set_neighbors(self.h, 1 if p_neighbors_cfg.only_count else 2,
                                                          int(p_neighbors_cfg.type == "all"), float(p_neighbors_cfg.tol)))
+        ring_mask = getattr(state, "ring_mask", None)
+        if source_cfg is not None or ring_mask is not None:  # RingsSystem(source_cfg=...), RingsState(active_state=...)
+            import __graft_entry__ as entry
+            entry.load_package()
+            from mavi_jl_b200.rings.sources import lower_sources
+            arr, n = lower_sources(source_cfg, self._lowered.keep) if source_cfg is not None else (None, 0)
+            draws = None if spawn_draws is None else np.ascontiguousarray(spawn_draws, dtype=np.float64)
+            self._check(self.lib.mor_rings_set_sources(self.h, arr, n, _ptr(ring_mask), _ptr(draws),
+                                                       0 if draws is None else len(draws)))
         pos = np.ascontiguousarray(state.pos, dtype=np.float64)
         second = np.ascontiguousarray(state.second, dtype=np.float64)
         mask = state.active_mask()
@@ -204,6 +215,12 @@ class OracleSystem:
         areas, cms, cont = np.empty(nr), np.empty((nr, 2)), np.empty((self.n, 2))
         self._check(self.lib.mor_rings_download_info(self.h, _ptr(areas), _ptr(cms), _ptr(cont)))
         return areas, cms, cont
+
+    def rings_active(self):
+        nr = self.state.num_rings
+        mask, uids, na = np.empty(nr, dtype=np.uint8), np.empty(nr, dtype=np.int64), C.c_int64()
+        self._check(self.lib.mor_rings_download_active(self.h, _ptr(mask), _ptr(uids), C.byref(na)))
+        return mask, uids, na.value
 
     def particle_neighbors(self):
         """(count[n], lists) — lists[i] in the reference's append order (None with only_count)."""

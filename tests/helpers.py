@@ -120,3 +120,56 @@ def rings_case(kind="normal", num_cols=13, num_rows=13, use_chunks=True, seed=31
 def make_gpu_rings(case):
     from mavi_jl_b200.rings.rings import RingsSystem
     return RingsSystem(state=case["mk"](), space_cfg=case["space"], dynamic_cfg=case["dyn"], int_cfg=case["int_cfg"])
+
+
+def rings_source_case(use_chunks=True, spawn_pol="random", seed=24042001, num_slots=100):
+    """`create_system_source` (test/tests_rings/rings_utils.jl:101-191): an empty periodic box with 100 inactive ring slots, a
+    2 x 2 SourceCfg on the left and a SinkCfg rectangle on the right.  Spawn shape: a circle of the ring's target area
+    A0 = (n l0 / p0)^2 (the reference calls get_equilibrium_area, an NLsolve host helper; for these parameters A0 lies
+    below its limiting value and is returned as is)."""
+    import math
+    from mavi_jl_b200.rings import configs as rc
+    from mavi_jl_b200.rings import init_states as ri
+    from mavi_jl_b200.rings.sources import SinkCfg, SourceCfg
+    from mavi_jl_b200.rings.states import RingsState
+
+    n = 10
+    inter = rc.HarmTruncCfg(k_rep=30, k_atr=3, dist_eq=1, dist_max=1 * 1.5)
+    dyn = rc.RingsCfg(p0=3.545, relax_time=100, vo=1, mobility=1, rot_diff=0, k_area=3, k_spring=30,
+                      l_spring=inter.dist_eq * 0.8, num_particles=n, interaction_finder=inter)
+    ring_d = rc.get_ring_radius(dyn.particle_radius(), n) * 2
+    geom = pkg.RectangleCfg(length=18 * ring_d, height=10 * ring_d)
+    ring_area = (n * float(dyn.l_spring[0]) / float(dyn.p0[0])) ** 2
+    r = (ring_area / math.pi) ** .5
+    spawn_pos = ri.create_circle((0, 0), r, n)
+    rng = np.random.default_rng(seed)
+    pol = ri.random_pol(num_slots, rng=rng)
+    space = pkg.SpaceCfg(wall_type=pkg.PeriodicWalls(), geometry_cfg=geom)
+    max_size = inter.dist_max * 1.2
+    chunks = pkg.ChunksCfg(int(geom.length // max_size), int(geom.height // max_size)) if use_chunks else None
+    bl = np.asarray(geom.bottom_left, dtype=float)
+    source_cfg = [
+        SourceCfg(bottom_left=bl + np.array([2 * ring_d, geom.height / 2 - ring_d]), spawn_pos=spawn_pos, size=(2, 2),
+                  spawn_pol=spawn_pol, pad=dyn.particle_radius()),
+        SinkCfg(pkg.RectangleCfg(length=ring_d * 2, height=ring_d * 2,
+                                 bottom_left=bl + np.array([geom.length - 4 * ring_d, geom.height / 2 - ring_d]))),
+    ]
+    int_cfg = rc.RingsIntCfg(dt=0.01, p_chunks_cfg=chunks, device=pkg.CUDADevice(rng_mode="host_noise"))
+    rings_pos = np.zeros((num_slots, n, 2))
+    mk = lambda: RingsState(rings_pos=rings_pos.copy(), pol=pol.copy(),  # noqa: E731
+                            active_state=pkg.ActiveState(np.zeros(num_slots, dtype=bool)))
+    draws = np.random.default_rng(seed + 1).random(4096)   # stands for the rand(system.rng) of spawn_pol = :random
+    return dict(mk=mk, space=space, dyn=dyn, int_cfg=int_cfg, geom=geom, num_rings=num_slots, source_cfg=source_cfg,
+                spawn_draws=draws, ring_d=ring_d)
+
+
+def make_oracle_sources(case, threads=1):
+    oracle = entry.load_oracle()
+    return oracle.OracleSystem(state=case["mk"](), space_cfg=case["space"], dynamic_cfg=case["dyn"], int_cfg=case["int_cfg"],
+                               lower=lower, threads=threads, source_cfg=case["source_cfg"], spawn_draws=case["spawn_draws"])
+
+
+def make_gpu_rings_sources(case):
+    from mavi_jl_b200.rings.rings import RingsSystem
+    return RingsSystem(state=case["mk"](), space_cfg=case["space"], dynamic_cfg=case["dyn"], int_cfg=case["int_cfg"],
+                       source_cfg=case["source_cfg"], spawn_draws=case["spawn_draws"])
