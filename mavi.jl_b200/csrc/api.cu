@@ -1045,6 +1045,23 @@ int32_t api_rings_download_neighbors(void *hh, int32_t *count, int32_t *list) {
   return rings_download_neighbors(h, count, list);
 }
 
+int32_t api_rings_set_sources(void *hh, const MaviSourceSink *list, int32_t n, const uint8_t *ring_active, const double *spawn_draws,
+                              int64_t n_draws) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return MAVI_ERR_BAD_PARAMS;
+  cudaSetDevice(h->device);
+  return rings_set_sources(h, list, n, ring_active, spawn_draws, n_draws);
+}
+
+int32_t api_rings_download_active(void *hh, uint8_t *ring_active, int64_t *uids, int64_t *num_active) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return MAVI_ERR_BAD_PARAMS;
+  long long na = 0;
+  int st = rings_download_active(h, ring_active, reinterpret_cast<long long *>(uids), &na);
+  if (num_active) *num_active = na;
+  return st;
+}
+
 int32_t api_get_time(void *hh, int64_t *num_steps, double *time) {
   Handle *h = reinterpret_cast<Handle *>(hh);
   if (!h) return MAVI_ERR_BAD_PARAMS;

@@ -127,6 +127,13 @@ int32_t mavi_rings_set_neighbors(MaviHandle *h, int32_t mode, int32_t type_all, 
 int32_t mavi_rings_download_neighbors(MaviHandle *h, int32_t *count, int32_t *list) {
   MAVI_FWD_S(h, api_rings_download_neighbors(impl, count, list));
 }
+int32_t mavi_rings_set_sources(MaviHandle *h, const MaviSourceSink *list, int32_t n, const uint8_t *ring_active,
+                               const double *spawn_draws, int64_t n_draws) {
+  MAVI_FWD_S(h, api_rings_set_sources(impl, list, n, ring_active, spawn_draws, n_draws));
+}
+int32_t mavi_rings_download_active(MaviHandle *h, uint8_t *ring_active, int64_t *uids, int64_t *num_active) {
+  MAVI_FWD_S(h, api_rings_download_active(impl, ring_active, uids, num_active));
+}
 int32_t mavi_get_time(MaviHandle *h, int64_t *num_steps, double *time) {
   MAVI_FWD_M(h, get_time(impl, num_steps, time), api_get_time(impl, num_steps, time));
 }

@@ -20,6 +20,30 @@ struct RingsArrays {
   int neigh_mode = 0;           // MAVI_NEIGH_*
   int neigh_all = 0;            // 1: type = :all, 0: type = :rings (other rings only)
   double neigh_tol = 1.1;       // NeighborsCfg.tol
+  // VarRingsIds + sources / sinks (src/rings/states.jl:24-43,173-227, src/rings/sources.jl): the ring mask lives on the
+  // device (binning, pair and ring kernels honour it); add_ring! / remove_ring! / calc_active_ids! are sequential by
+  // definition (first free slot, uid = max + 1) and run on the host once per step from two tiny downloads
+  struct Source {
+    int kind = 0, nspawn = 0, nsp = 0, sink_geom = 0;
+    double pad = 0.0, spawn_pol = 0.0, sink[5] = {0, 0, 0, 0, 0};
+    std::vector<double> bbox;   // [nspawn][4]
+    std::vector<double> spawn;  // [nspawn][nsp][2]
+    int first_area = 0;         // index of its first spawn area in the device list
+  };
+  bool var_rings = false;
+  std::vector<int> np_h, types_h;      // host copies of num_particles[type] and the 0-based ring types (empty: one type)
+  std::vector<Source> sources;
+  std::vector<unsigned char> mask_h;   // rings_ids.mask
+  std::vector<long long> uids_h, ids_h;  // rings_ids.uids, rings_ids.ids[1:num_active] as of the last calc_active_ids!
+  long long num_active = 0;
+  std::vector<double> draws;           // rand(rng) stand-ins for spawn_pol = :random
+  size_t draw_pos = 0;
+  unsigned long long spawn_count = 0;  // production mode: counter of the host-side generator
+  unsigned char *mask_dev = nullptr;   // [num_rings]
+  double *areas_dev = nullptr;         // spawn areas: [n_areas][5] = bl.x, bl.y, length, height, pad
+  int *empty_dev = nullptr;            // [n_areas] 1 = no active particle inside
+  int n_areas = 0;
+  bool has_sinks = false;
 };
 
 // x-slab decomposition state (slab.cu)
@@ -103,5 +127,7 @@ int rings_bin(Handle *h);
 int rings_download_cells(Handle *h, int *cell_of_particle, int *counts, int *start, int *ids);
 int rings_set_neighbors(Handle *h, int mode, int type_all, double tol);
 int rings_download_neighbors(Handle *h, int *count, int *list);
+int rings_set_sources(Handle *h, const MaviSourceSink *list, int n, const unsigned char *ring_active, const double *draws, long long n_draws);
+int rings_download_active(Handle *h, unsigned char *mask, long long *uids, long long *num_active);
 
 }  // namespace MAVI_NS

@@ -41,12 +41,47 @@ __device__ __forceinline__ int ring_type(const DevRings &r, int ring) { return r
 __device__ __forceinline__ real cross_exact(real2 a, real2 b) { return add_rn(mul_rn(a.x, b.y), -mul_rn(a.y, b.x)); }
 
 // idflag for ring-ordered slots: padding slots of shorter ring types are inactive (FixRingsIds, src/rings/states.jl:45-61)
-__global__ void k_rings_ids(const __grid_constant__ DevParams p, unsigned int *__restrict__ idflag) {
+// ... and, with VarRingsIds, every slot of an inactive ring (calc_active_ids!, src/rings/states.jl:200-223)
+__global__ void k_rings_ids(const __grid_constant__ DevParams p, const unsigned char *__restrict__ ring_mask,
+                            unsigned int *__restrict__ idflag) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n) return;
   const int ring = i / p.rings.n_max, q = i - ring * p.rings.n_max;
   const int np = p.rings.num_particles[ring_type(p.rings, ring)];
-  idflag[i] = (unsigned int)i | (q < np ? 0u : MAVI_INACTIVE_BIT);
+  const bool on = q < np && (!ring_mask || ring_mask[ring]);
+  idflag[i] = (unsigned int)i | (on ? 0u : MAVI_INACTIVE_BIT);
+}
+
+// update_cms! (src/rings/integration.jl:366-372) on its own: with sources / sinks it must run BEFORE they are processed
+// (sinks test info.cms, spawned rings get their cms primed by process_source!), so the ring kernel skips it (prime_cms = -1)
+template <bool PER>
+__global__ void k_rings_cms(const __grid_constant__ DevParams p, const unsigned char *__restrict__ ring_mask,
+                            const real2 *__restrict__ pos, const real2 *__restrict__ cont_pos, real2 *__restrict__ cms) {
+  const DevRings &R = p.rings;
+  const int ring = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ring >= R.num_rings || (ring_mask && !ring_mask[ring])) return;
+  const int np = R.num_particles[ring_type(R, ring)];
+  const real2 *src = (PER ? cont_pos : pos) + (size_t)ring * R.n_max;
+  real sx = src[0].x, sy = src[0].y;
+  for (int i = 1; i < np; i++) { sx += src[i].x; sy += src[i].y; }
+  cms[ring] = make_real2(sx / np, sy / np);
+}
+
+// update_area_empty! (src/rings/sources.jl:191-225): an area is empty when no ACTIVE particle (ids as of the last
+// update_ids!: idflag has not been refreshed yet) lies inside its bounding box grown by pad (is_inside, src/configs.jl:89-93).
+// The reference's ChunksChecker walks the (one step old) chunk lists of the cells that intersect the padded box, which
+// finds the same particles unless one moved farther than pad + a cell in a single step.
+__global__ void k_rings_area_empty(const __grid_constant__ DevParams p, const unsigned int *__restrict__ idflag,
+                                   const real2 *__restrict__ pos, const double *__restrict__ areas, int n_areas,
+                                   int *__restrict__ empty) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n || (idflag[i] & MAVI_INACTIVE_BIT)) return;
+  const double x = pos[i].x, y = pos[i].y;
+  for (int a = 0; a < n_areas; a++) {
+    const double *b = areas + 5 * a;
+    const double pad = b[4];
+    if (b[0] - pad <= x && x <= b[0] + b[2] + pad && b[1] - pad <= y && y <= b[1] + b[3] + pad) empty[a] = 0;
+  }
 }
 
 // calc_interaction + calc_interaction_force (src/rings/integration.jl:32-77) summed over the stencil, + wall forces
@@ -162,7 +197,7 @@ __global__ void __launch_bounds__(RING_WARPS * 32) k_rings_ring(
     const __grid_constant__ DevParams p, real2 *__restrict__ pos, real *__restrict__ pol,
     const real2 *__restrict__ fpair, real2 *__restrict__ force, real2 *__restrict__ cont_pos,
     real *__restrict__ areas, real2 *__restrict__ cms, const real *__restrict__ noise, unsigned long long step,
-    int prime_cms, int *__restrict__ flags) {
+    int prime_cms, int *__restrict__ flags, const unsigned char *__restrict__ ring_mask) {
   __shared__ real2 s_pos[RING_WARPS][RING_NMAX];
   __shared__ real2 s_cont[RING_WARPS][RING_NMAX];
   __shared__ real2 s_vel[RING_WARPS][RING_NMAX];
@@ -171,6 +206,7 @@ __global__ void __launch_bounds__(RING_WARPS * 32) k_rings_ring(
   const int ring = blockIdx.x * RING_WARPS + w;
   if (ring >= R.num_rings || flags[FLAG_OVERFLOW]) return;
   if (MODE == 1 && ring == 0 && lane == 0) flags[FLAG_STEPS] += 1;  // steps that really ran (device-side step counter)
+  if (ring_mask && !ring_mask[ring]) return;  // get_rings_ids(state): active rings only
   const int t = ring_type(R, ring);
   const int np = R.num_particles[t];
   const int base = ring * R.n_max;
@@ -178,7 +214,7 @@ __global__ void __launch_bounds__(RING_WARPS * 32) k_rings_ring(
   for (int i = lane; i < R.n_max; i += 32) sp[i] = pos[base + i];
   __syncwarp();
   // ---- update_cms! (src/rings/integration.jl:366-372) runs FIRST in step!: it still sees last step's continuos_pos
-  if (MODE == 1 && lane == 0) {
+  if (MODE == 1 && prime_cms >= 0 && lane == 0) {
     real sx, sy;
     if (PER) { sx = cont_pos[base].x; sy = cont_pos[base].y; }
     else { sx = sp[0].x; sy = sp[0].y; }
@@ -214,7 +250,7 @@ __global__ void __launch_bounds__(RING_WARPS * 32) k_rings_ring(
     area = add_rn(area, cross_exact(sc[np - 1], sc[0]));
     area = area / 2.0;
     areas[ring] = area;
-    if (MODE == 0 && prime_cms) {  // constructor: update_cms! right after the first unwrap (src/rings/rings.jl:280-283)
+    if (MODE == 0 && prime_cms > 0) {  // constructor: update_cms! right after the first unwrap (src/rings/rings.jl:280-283)
       real sx = sc[0].x, sy = sc[0].y;
       for (int i = 1; i < np; i++) { sx += sc[i].x; sy += sc[i].y; }
       cms[ring] = make_real2(sx / np, sy / np);
@@ -300,16 +336,17 @@ __global__ void __launch_bounds__(RING_T_TPB) k_rings_ring_t(
     const __grid_constant__ DevParams p, real2 *__restrict__ pos, real *__restrict__ pol,
     const real2 *__restrict__ fpair, real2 *__restrict__ force, real2 *__restrict__ cont_pos,
     real *__restrict__ areas, real2 *__restrict__ cms, const real *__restrict__ noise, unsigned long long step,
-    int prime_cms, int *__restrict__ flags) {
+    int prime_cms, int *__restrict__ flags, const unsigned char *__restrict__ ring_mask) {
   const DevRings &R = p.rings;
   const int ring = blockIdx.x * blockDim.x + threadIdx.x;
   if (ring >= R.num_rings || flags[FLAG_OVERFLOW]) return;
   if (MODE == 1 && ring == 0) flags[FLAG_STEPS] += 1;  // steps that really ran (device-side step counter)
+  if (ring_mask && !ring_mask[ring]) return;  // get_rings_ids(state): active rings only
   const int t = ring_type(R, ring);
   const int np = R.num_particles[t];
   const int base = ring * R.n_max;
   // ---- update_cms! (src/rings/integration.jl:366-372) runs FIRST in step!: it still sees last step's continuos_pos
-  if (MODE == 1) {
+  if (MODE == 1 && prime_cms >= 0) {
     const real2 *src = PER ? cont_pos : pos;
     real sx = src[base].x, sy = src[base].y;
     for (int i = 1; i < np; i++) {
@@ -345,7 +382,7 @@ __global__ void __launch_bounds__(RING_T_TPB) k_rings_ring_t(
   area = add_rn(area, cross_exact(c_prev, c0));
   area = area / 2.0;
   areas[ring] = area;
-  if (MODE == 0 && prime_cms) cms[ring] = make_real2(sx / np, sy / np);  // src/rings/rings.jl:280-283
+  if (MODE == 0 && prime_cms > 0) cms[ring] = make_real2(sx / np, sy / np);  // src/rings/rings.jl:280-283
   // ---- forces! (:197-226): pair forces + springs (:79-97) + area_forces! (:140-195); update! (:300-351); walls!
   const real k_spring = R.k_spring[t], l_spring = R.l_spring[t];
   const real k_area = R.k_area[t], p0 = R.p0[t];
@@ -504,6 +541,8 @@ int rings_lower(Handle *h, const MaviParams *mp) {
       (st = up(h, &R.interaction, (const real *)inter.data(), inter.size())))
     return st;
   R.types = nullptr;
+  h->r.np_h.assign(r->num_particles, r->num_particles + nt);
+  h->r.types_h.clear();
   long long n_active = 0;
   if (r->types) {
     std::vector<int> t0((size_t)r->num_rings);
@@ -515,6 +554,7 @@ int rings_lower(Handle *h, const MaviParams *mp) {
       t0[i] = r->types[i] - 1;
       n_active += r->num_particles[t0[i]];
     }
+    h->r.types_h = t0;
     if ((st = up(h, &R.types, t0.data(), t0.size()))) return st;
   } else {
     n_active = r->num_rings * (long long)r->num_particles[0];
@@ -648,7 +688,7 @@ static void launch_ring(Handle *h, int mode, const real *noise, int prime_cms) {
   if (p.rings.n_max <= RING_T_NMAX && !warp_kernel) {
     const int gt = (p.rings.num_rings + RING_T_TPB - 1) / RING_T_TPB;
 #define RING_CALL_T(PER, MODE) \
-  RINGS_LAUNCH(h, (k_rings_ring_t<PER, MODE>), gt, RING_T_TPB, p, a.pos[0], r.pol, a.force_old, a.force, r.cont_pos, r.areas, r.cms, noise, step, prime_cms, a.flags)
+  RINGS_LAUNCH(h, (k_rings_ring_t<PER, MODE>), gt, RING_T_TPB, p, a.pos[0], r.pol, a.force_old, a.force, r.cont_pos, r.areas, r.cms, noise, step, prime_cms, a.flags, r.mask_dev)
     if (p.periodic) {
       if (mode) RING_CALL_T(true, 1); else RING_CALL_T(true, 0);
     } else {
@@ -658,13 +698,238 @@ static void launch_ring(Handle *h, int mode, const real *noise, int prime_cms) {
     return;
   }
 #define RING_CALL(PER, MODE) \
-  RINGS_LAUNCH(h, (k_rings_ring<PER, MODE>), grid, RING_WARPS * 32, p, a.pos[0], r.pol, a.force_old, a.force, r.cont_pos, r.areas, r.cms, noise, step, prime_cms, a.flags)
+  RINGS_LAUNCH(h, (k_rings_ring<PER, MODE>), grid, RING_WARPS * 32, p, a.pos[0], r.pol, a.force_old, a.force, r.cont_pos, r.areas, r.cms, noise, step, prime_cms, a.flags, r.mask_dev)
   if (p.periodic) {
     if (mode) RING_CALL(true, 1); else RING_CALL(true, 0);
   } else {
     if (mode) RING_CALL(false, 1); else RING_CALL(false, 0);
   }
 #undef RING_CALL
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// sources / sinks / variable ring count (src/rings/sources.jl, src/rings/states.jl:173-227)
+// ---------------------------------------------------------------------------------------------------------
+int rings_set_sources(Handle *h, const MaviSourceSink *list, int n, const unsigned char *ring_active, const double *draws,
+                      long long n_draws) {
+  if (h->p.dynamics != MAVI_DYN_RINGS || n < 0 || (n > 0 && !list)) {
+    h->set_error("sources / sinks are a Mavi.Rings feature (RingsSystem source_cfg)");
+    return MAVI_ERR_BAD_PARAMS;
+  }
+  RingsArrays &r = h->r;
+  const DevRings &R = h->p.rings;
+  const size_t nr = (size_t)R.num_rings;
+  if (!ring_active && n > 0) {
+    h->set_error("sources / sinks need a RingsState with active_state (VarRingsIds)");
+    return MAVI_ERR_BAD_PARAMS;
+  }
+  r.sources.clear();
+  r.var_rings = ring_active != nullptr;
+  r.has_sinks = false;
+  std::vector<double> areas;
+  for (int k = 0; k < n; k++) {
+    const MaviSourceSink &c = list[k];
+    RingsArrays::Source o;
+    o.kind = c.kind;
+    if (c.kind == MAVI_SRC_SINK) {
+      o.sink_geom = c.sink_geom;
+      if (c.sink_geom == MAVI_GEOM_RECT) {
+        o.sink[0] = c.sink_rect_bl[0]; o.sink[1] = c.sink_rect_bl[1]; o.sink[2] = c.sink_rect_len; o.sink[3] = c.sink_rect_h;
+      } else if (c.sink_geom == MAVI_GEOM_CIRCLE) {
+        o.sink[0] = c.sink_circ_center[0]; o.sink[1] = c.sink_circ_center[1]; o.sink[2] = c.sink_circ_radius;
+      } else {
+        h->set_error("SinkCfg geometry must be a rectangle or a circle (is_inside, src/configs.jl:89-93,165-168)");
+        return MAVI_ERR_UNSUPPORTED;
+      }
+      r.has_sinks = true;
+      r.sources.push_back(o);
+      continue;
+    }
+    if (c.kind != MAVI_SRC_SOURCE || !c.spawn_pos || c.num_spawn_pos != R.n_max || c.size[0] < 1 || c.size[1] < 1) {
+      h->set_error("SourceCfg: spawn_pos must hold n_max = %d points (add_ring! writes rings_pos[:, ring] .= pos) and size >= (1, 1)", R.n_max);
+      return MAVI_ERR_BAD_PARAMS;
+    }
+    // Source ctor, src/rings/sources.jl:134-190
+    const int nsp = c.num_spawn_pos;
+    const double pad = c.pad;
+    o.nsp = nsp; o.pad = pad; o.spawn_pol = c.spawn_pol;
+    double min_x = c.spawn_pos[0], max_x = min_x, min_y = c.spawn_pos[1], max_y = min_y;
+    for (int i = 1; i < nsp; i++) {
+      const double x = c.spawn_pos[2 * i], y = c.spawn_pos[2 * i + 1];
+      min_x = x < min_x ? x : min_x; max_x = x > max_x ? x : max_x;
+      min_y = y < min_y ? y : min_y; max_y = y > max_y ? y : max_y;
+    }
+    const double bl_len = max_x - min_x + 2 * pad, bl_h = max_y - min_y + 2 * pad;
+    o.nspawn = c.size[0] * c.size[1];
+    o.first_area = (int)(areas.size() / 5);
+    for (int i = 1; i <= c.size[0]; i++)
+      for (int j = 1; j <= c.size[1]; j++) {
+        const double bx = c.bottom_left[0] + ((i - 1) * bl_len + i * c.offset[0]);
+        const double by = c.bottom_left[1] + ((j - 1) * bl_h + j * c.offset[1]);
+        o.bbox.insert(o.bbox.end(), {bx, by, bl_len, bl_h});
+        areas.insert(areas.end(), {bx, by, bl_len, bl_h, pad});
+        const double dx = bx - min_x + pad, dy = by - min_y + pad;
+        for (int q = 0; q < nsp; q++) {
+          o.spawn.push_back(c.spawn_pos[2 * q] + dx);
+          o.spawn.push_back(c.spawn_pos[2 * q + 1] + dy);
+        }
+      }
+    r.sources.push_back(o);
+  }
+  r.mask_h.assign(nr, 1);
+  r.uids_h.resize(nr);
+  r.ids_h.resize(nr);
+  for (size_t i = 0; i < nr; i++) {
+    if (ring_active) r.mask_h[i] = ring_active[i] != 0;
+    r.uids_h[i] = (long long)i + 1;
+    r.ids_h[i] = (long long)i;
+  }
+  r.num_active = 0;
+  r.draws.assign(draws ? draws : nullptr, draws ? draws + (n_draws > 0 ? n_draws : 0) : nullptr);
+  r.draw_pos = 0;
+  r.spawn_count = 0;
+  r.n_areas = (int)(areas.size() / 5);
+  auto al = [&](void **ptr, size_t bytes) -> int {
+    if (*ptr) return MAVI_OK;
+    if (cudaMalloc(ptr, bytes ? bytes : 16) != cudaSuccess) {
+      h->set_error("cudaMalloc failed (sources)");
+      return MAVI_ERR_CUDA;
+    }
+    h->allocs.push_back(*ptr);
+    return MAVI_OK;
+  };
+  int st;
+  if (r.var_rings) {
+    if ((st = al((void **)&r.mask_dev, nr))) return st;
+    RINGS_TRY(h, cudaMemcpyAsync(r.mask_dev, r.mask_h.data(), nr, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (r.n_areas > 0) {
+    r.areas_dev = nullptr;
+    r.empty_dev = nullptr;
+    if ((st = al((void **)&r.areas_dev, areas.size() * sizeof(double))) || (st = al((void **)&r.empty_dev, (size_t)r.n_areas * sizeof(int))))
+      return st;
+    RINGS_TRY(h, cudaMemcpyAsync(r.areas_dev, areas.data(), areas.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  RINGS_TRY(h, cudaStreamSynchronize(h->stream));
+  return MAVI_OK;
+}
+
+// calc_active_ids!, src/rings/states.jl:200-223: ids[1:num_active] from the mask (the particle ids follow on the device)
+static void rings_calc_active_ids(RingsArrays &r) {
+  long long q = 0;
+  for (size_t i = 0; i < r.mask_h.size(); i++)
+    if (r.mask_h[i]) r.ids_h[(size_t)q++] = (long long)i;
+  r.num_active = q;
+}
+
+int rings_download_active(Handle *h, unsigned char *mask, long long *uids, long long *num_active) {
+  if (h->p.dynamics != MAVI_DYN_RINGS) return MAVI_ERR_BAD_PARAMS;
+  const RingsArrays &r = h->r;
+  const size_t nr = (size_t)h->p.rings.num_rings;
+  for (size_t i = 0; i < nr; i++) {
+    if (mask) mask[i] = r.var_rings ? r.mask_h[i] : 1;
+    if (uids) uids[i] = r.var_rings ? r.uids_h[i] : (long long)i + 1;
+  }
+  if (num_active) *num_active = r.var_rings ? r.num_active : (long long)nr;
+  return MAVI_OK;
+}
+
+// update_sources! + update_ids! of one step (src/rings/integration.jl:353-358,525-527).  info.cms is current (k_rings_cms ran).
+static int rings_process_sources(Handle *h) {
+  DevParams &p = h->p;
+  DevArrays &a = h->a;
+  RingsArrays &r = h->r;
+  const DevRings &R = p.rings;
+  const size_t nr = (size_t)R.num_rings;
+  std::vector<real2> cms;
+  std::vector<int> empty((size_t)r.n_areas, 1);
+  if (r.has_sinks) {
+    cms.resize(nr);
+    RINGS_TRY(h, cudaMemcpyAsync(cms.data(), r.cms, nr * sizeof(real2), cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (r.n_areas > 0) {
+    RINGS_TRY(h, cudaMemcpyAsync(r.empty_dev, empty.data(), empty.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    RINGS_LAUNCH(h, k_rings_area_empty, (p.n + TPB - 1) / TPB, TPB, p, a.idflag, a.pos[0], r.areas_dev, r.n_areas, r.empty_dev);
+    RINGS_TRY(h, cudaMemcpyAsync(empty.data(), r.empty_dev, empty.size() * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  }
+  RINGS_TRY(h, cudaStreamSynchronize(h->stream));
+  bool changed = false;
+  for (auto &o : r.sources) {
+    if (o.kind == MAVI_SRC_SINK) {
+      // process_sink! (src/rings/sources.jl:245-251): `for ring_id in get_rings_ids(state)` is the view ids[1:num_active]
+      // taken once; remove_ring! only clears the mask and lowers num_active (src/rings/states.jl:189-193)
+      const long long nview = r.num_active;
+      for (long long q = 0; q < nview; q++) {
+        const size_t ring = (size_t)r.ids_h[(size_t)q];
+        const double cx = cms[ring].x, cy = cms[ring].y;
+        bool in;
+        if (o.sink_geom == MAVI_GEOM_RECT)
+          in = o.sink[0] <= cx && cx <= o.sink[0] + o.sink[2] && o.sink[1] <= cy && cy <= o.sink[1] + o.sink[3];
+        else {
+          const double ex = cx - o.sink[0], ey = cy - o.sink[1];
+          in = ex * ex + ey * ey <= o.sink[2] * o.sink[2];
+        }
+        if (in) {
+          r.mask_h[ring] = 0;
+          r.num_active -= 1;
+          changed = true;
+        }
+      }
+      continue;
+    }
+    for (int k = 0; k < o.nspawn; k++) {
+      if (!empty[(size_t)(o.first_area + k)]) continue;
+      double pol = o.spawn_pol;
+      if (std::isnan(pol)) {  // get_spawn_pol(::RandomPol) = rand(rng) * 2 pi, drawn before add_ring! looks for a slot
+        double u;
+        if (!r.draws.empty()) {
+          if (r.draw_pos >= r.draws.size()) {
+            h->set_error("spawn_draws exhausted after %zu draws", r.draws.size());
+            return MAVI_ERR_BAD_PARAMS;
+          }
+          u = r.draws[r.draw_pos++];
+        } else {  // production mode: splitmix64 keyed (seed, spawn count)
+          unsigned long long z = p.seed + 0x9E3779B97F4A7C15ull * (++r.spawn_count);
+          z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+          z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+          z ^= z >> 31;
+          u = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+        }
+        pol = u * 2 * 3.141592653589793;
+      }
+      // add_ring! (src/rings/states.jl:173-187): first free slot
+      size_t slot = nr;
+      for (size_t i = 0; i < nr; i++)
+        if (!r.mask_h[i]) { slot = i; break; }
+      if (slot == nr) continue;  // "Space not found to add a new Ring!" — silently skipped by the reference
+      const int nm = R.n_max;
+      std::vector<real2> pts((size_t)nm);
+      const double *sp = o.spawn.data() + 2 * (size_t)k * o.nsp;
+      for (int q = 0; q < nm; q++) pts[(size_t)q] = make_real2((real)sp[2 * q], (real)sp[2 * q + 1]);
+      const real polr = (real)pol;
+      long long mx = r.uids_h[0];
+      for (size_t i = 1; i < nr; i++) mx = r.uids_h[i] > mx ? r.uids_h[i] : mx;
+      r.mask_h[slot] = 1;
+      r.uids_h[slot] = mx + 1;
+      r.num_active += 1;
+      changed = true;
+      // system.info.cms[ring_id] = sum(state.rings_pos[1:num_p, ring_id]) / num_p  (src/rings/sources.jl:240-243)
+      const int np = r.np_h[r.types_h.empty() ? 0 : (size_t)r.types_h[slot]];
+      real sx = pts[0].x, sy = pts[0].y;
+      for (int q = 1; q < np; q++) { sx += pts[(size_t)q].x; sy += pts[(size_t)q].y; }
+      const real2 cm = make_real2(sx / np, sy / np);
+      RINGS_TRY(h, cudaMemcpy(a.pos[0] + slot * (size_t)nm, pts.data(), (size_t)nm * sizeof(real2), cudaMemcpyHostToDevice));
+      RINGS_TRY(h, cudaMemcpy(r.pol + slot, &polr, sizeof(real), cudaMemcpyHostToDevice));
+      RINGS_TRY(h, cudaMemcpy(r.cms + slot, &cm, sizeof(real2), cudaMemcpyHostToDevice));
+    }
+  }
+  rings_calc_active_ids(r);  // update_ids!
+  if (changed) {
+    RINGS_TRY(h, cudaMemcpyAsync(r.mask_dev, r.mask_h.data(), nr, cudaMemcpyHostToDevice, h->stream));
+    RINGS_LAUNCH(h, k_rings_ids, (p.n + TPB - 1) / TPB, TPB, p, r.mask_dev, a.idflag);
+  }
+  return MAVI_OK;
 }
 
 // RingsSystem ctor tail (src/rings/rings.jl:280-288): ids, continuos_pos, cms, chunks, forces!
@@ -675,7 +940,8 @@ int rings_upload_finish(Handle *h) {
   const size_t n = (size_t)p.n;
   RINGS_TRY(h, cudaMemcpyAsync(a.pos[0], a.st_pos, n * sizeof(real2), cudaMemcpyDeviceToDevice, h->stream));
   RINGS_TRY(h, cudaMemcpyAsync(r.pol, a.st_ang, (size_t)p.rings.num_rings * sizeof(real), cudaMemcpyDeviceToDevice, h->stream));
-  RINGS_LAUNCH(h, k_rings_ids, (p.n + TPB - 1) / TPB, TPB, p, a.idflag);
+  if (r.var_rings) rings_calc_active_ids(r);  // RingsState ctor: update_ids!(state), src/rings/states.jl:121
+  RINGS_LAUNCH(h, k_rings_ids, (p.n + TPB - 1) / TPB, TPB, p, r.mask_dev, a.idflag);
   RINGS_TRY(h, cudaMemcpyAsync(a.st_id, a.idflag, n * sizeof(unsigned int), cudaMemcpyDeviceToDevice, h->stream));
   if (p.n_spaces == 1) launch_check_inside(h->ctx(), p, a);
   int st = h->check_device_flags();
@@ -700,6 +966,23 @@ int rings_calc_forces(Handle *h) {
 int rings_step(Handle *h, const real *noise_dev) {
   DevParams &p = h->p;
   DevArrays &a = h->a;
+  RingsArrays &r = h->r;
+  if (r.var_rings) {
+    // step! with a variable ring set (src/rings/integration.jl:522-527): update_cms!; update_sources!; update_ids! — one
+    // small host round trip (add_ring! / remove_ring! are sequential by definition) — then the usual step, binning
+    // synchronously (an index-tile overflow must not replay the sources)
+    const int gr = (p.rings.num_rings + TPB - 1) / TPB;
+    if (p.periodic) RINGS_LAUNCH(h, (k_rings_cms<true>), gr, TPB, p, r.mask_dev, a.pos[0], r.cont_pos, r.cms);
+    else RINGS_LAUNCH(h, (k_rings_cms<false>), gr, TPB, p, r.mask_dev, a.pos[0], r.cont_pos, r.cms);
+    int st = rings_process_sources(h);
+    if (st) return st;
+    if ((st = rings_bin(h))) return st;
+    launch_pair(h, true);
+    launch_ring(h, 1, noise_dev, -1);  // -1: update_cms! already done
+    h->num_steps += 1;
+    h->time += h->dt_host;
+    return MAVI_OK;
+  }
   if (p.num_cells > 0) {  // update_chunks_all! (after update_cms!, which only reads last step's continuos_pos)
     RINGS_TRY(h, cudaMemsetAsync(a.count, 0, ((size_t)p.num_cells + 2) * sizeof(int), h->stream));
     launch_build_index_tiles(h->ctx(), p, a.pos[0], a.idflag, a.cell, a.count, a.tstart, a.perm, a.flags);
