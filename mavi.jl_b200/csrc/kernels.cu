@@ -1256,8 +1256,9 @@ __device__ __forceinline__ void for_each_block_particle(const DevParams &p, cons
 // Float32 build: a float2 run is only 8-byte aligned, below the 16 bytes bulk copies need, so there the producer warp
 // copies the runs itself (plain loads / stores) before it arrives on `full`.
 // =========================================================================================================
-// warps per CTA: CW consumer warps + NP producer warps (template parameters; see pipe_cfg()).  7 + 2 = 288 threads, 72
-// registers, 21 consumer and 6 producer warps per SM (default); 8 + 1: 24 consumer warps, one producer per CTA.
+// warps per CTA: CW consumer warps + NP producer warps (template parameters; see pipe_cfg()).  7 + 1 = 256 threads, 80
+// registers, no spills, 21 consumer and 3 producer warps per SM (default, fastest measured); 8 + 1: 24 consumer warps at
+// 72 registers with a few spills; a second producer warp halves the consumers' waits but costs more issue slots than it wins.
 constexpr int PIPE_CTAS_PER_SM = 3;
 constexpr int PG_MAX = 30;                           // own columns per chunk (+ two side columns: one producer lane each)
 constexpr int PSPOS_CAP = 1280;                      // staged positions per chunk
@@ -1572,13 +1573,13 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
   }
 }
 
-// (consumer warps) * 10 + (producer warps) per CTA of the pipelined kernels: 72 (default), 82, 71, 81 — MAVI_PIPE_CFG is the
-// A/B switch of the measurements in profiles/r02_ncu_newton_summary.md
+// (consumer warps) * 10 + (producer warps) per CTA of the pipelined kernels: 71 (default), 81, 72, 82 — MAVI_PIPE_CFG is the
+// A/B switch of the measurements in profiles/r02_ncu_newton_summary.md (LJ 16 M: 71 0.551 ms, 81 0.562, 82 0.562, 72 0.598)
 static inline int pipe_cfg() {
   static const int cfg = [] {
     const char *e = getenv("MAVI_PIPE_CFG");
-    const int v = e ? atoi(e) : 72;
-    return (v == 81 || v == 71 || v == 82) ? v : 72;
+    const int v = e ? atoi(e) : 71;
+    return (v == 81 || v == 72 || v == 82) ? v : 71;
   }();
   return cfg;
 }
@@ -1800,9 +1801,9 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p_in, const DevArrays 
   do {                                                     \
     switch (pipe_cfg()) {                                  \
       case 81: CALLP__(D, P, CARRYV, 8, 1); break;         \
-      case 71: CALLP__(D, P, CARRYV, 7, 1); break;         \
+      case 72: CALLP__(D, P, CARRYV, 7, 2); break;         \
       case 82: CALLP__(D, P, CARRYV, 8, 2); break;         \
-      default: CALLP__(D, P, CARRYV, 7, 2); break;         \
+      default: CALLP__(D, P, CARRYV, 7, 1); break;         \
     }                                                      \
   } while (0)
 #define CALLP(D, P) CALLP_(D, P, false)
@@ -1891,9 +1892,9 @@ void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArra
   do {                                               \
     switch (pipe_cfg()) {                            \
       case 81: CALLP_(D, P, 8, 1); break;            \
-      case 71: CALLP_(D, P, 7, 1); break;            \
+      case 72: CALLP_(D, P, 7, 2); break;            \
       case 82: CALLP_(D, P, 8, 2); break;            \
-      default: CALLP_(D, P, 7, 2); break;            \
+      default: CALLP_(D, P, 7, 1); break;            \
     }                                                \
   } while (0)
     if (!(c.flags & MAVI_FLAG_LEGACY_STAGING)) {

@@ -55,6 +55,16 @@ struct OrSystem {
   int32_t nsrc;
   double *draws;
   int64_t n_draws, draw_pos;
+  /* invasions (src/rings/integration.jl:379-520): InvasionsCfg.steps_to_update, InvasionsInfo, ring-level Chunks on the cms */
+  int32_t inv_steps;         /* 0 = off */
+  int64_t inv_last_check;
+  int32_t *inv_list;         /* [n][3] = invasor ring, invaded ring, scalar particle id (0-based) */
+  int64_t inv_n, inv_cap;
+  int64_t r_cols, r_rows, r_nc; /* r_chunks (0 columns: check_invasions!(system, ::Nothing)) */
+  double r_cl, r_ch;
+  int64_t *r_particles, *r_num;
+  int32_t *r_neigh;
+  int8_t *r_neigh_n;
   int64_t num_steps;
   double time;
   char err[256];
@@ -240,8 +250,15 @@ static int64_t wrap_id(int64_t x, int64_t num_t) {
   return x;
 }
 
-static void build_neighbors(OrSystem *s) {
-  const int64_t nr = s->num_rows, ncl = s->num_cols;
+typedef struct NeighTab { int32_t *neigh; int8_t *neigh_n; } NeighTab;
+static void build_neighbors_tab(NeighTab *s, int64_t nr, int64_t ncl, int periodic);
+static void build_neighbors(OrSystem *sys) {
+  NeighTab t;
+  build_neighbors_tab(&t, sys->num_rows, sys->num_cols, sys->p.spaces[0].wall == MAVI_WALL_PERIODIC);
+  sys->neigh = t.neigh;
+  sys->neigh_n = t.neigh_n;
+}
+static void build_neighbors_tab(NeighTab *s, int64_t nr, int64_t ncl, int periodic) {
   s->neigh = (int32_t *)malloc(sizeof(int32_t) * 4 * (size_t)(nr * ncl));
   s->neigh_n = (int8_t *)calloc((size_t)(nr * ncl), 1);
 #define CELL(i, j) ((int32_t)(((i)-1) + nr * ((j)-1)))
@@ -251,7 +268,7 @@ static void build_neighbors(OrSystem *s) {
     s->neigh[4 * c_ + s->neigh_n[c_]] = CELL(ii, jj);               \
     s->neigh_n[c_]++;                                               \
   } while (0)
-  if (s->p.spaces[0].wall == MAVI_WALL_PERIODIC) {
+  if (periodic) {
     for (int64_t i = 1; i <= nr; i++)
       for (int64_t j = 1; j <= ncl; j++) {
         PUSH(i, j, wrap_id(i + 1, nr), wrap_id(j, ncl));
@@ -1077,6 +1094,148 @@ static int32_t update_sources(OrSystem *s) {
   return MAVI_OK;
 }
 
+
+/* ------------------------------------------------------------------ invasions */
+
+/* point_line_intersect, src/rings/integration.jl:379-420: does the ray from p towards +x cross the segment? */
+static int point_line_intersect(const double *p, const double *l1, const double *l2) {
+  const double dx = l2[0] - l1[0], dy = l2[1] - l1[1];
+  double x_inter;
+  if (dx == 0) {
+    x_inter = l1[0];
+    int check1 = x_inter > p[0];
+    const double *ya = dy < 0 ? l2 : l1, *yb = dy < 0 ? l1 : l2;
+    int check2 = ya[1] < p[1] && p[1] < yb[1];
+    return check1 & check2;
+  }
+  if (dy == 0) return 0;
+  const double c = dy * l1[0] - dx * l1[1];
+  x_inter = (c + dx * p[1]) / dy;
+  int check1 = x_inter > p[0];
+  const double *ya = dy < 0 ? l2 : l1, *yb = dy < 0 ? l1 : l2;
+  const double *xa = dx < 0 ? l2 : l1, *xb = dx < 0 ? l1 : l2;
+  int check2 = (xa[0] < x_inter && x_inter < xb[0]) & (ya[1] < p[1] && p[1] < yb[1]);
+  return check1 & check2;
+}
+
+static void inv_push(OrSystem *s, int64_t invasor, int64_t invaded, int64_t pid) {
+  if (s->inv_n == s->inv_cap) {
+    s->inv_cap = s->inv_cap ? 2 * s->inv_cap : 256;
+    s->inv_list = (int32_t *)realloc(s->inv_list, sizeof(int32_t) * 3 * (size_t)s->inv_cap);
+  }
+  int32_t *e = s->inv_list + 3 * s->inv_n++;
+  e[0] = (int32_t)invasor; e[1] = (int32_t)invaded; e[2] = (int32_t)pid;
+}
+
+/* polygons_intersect + find_invasions!, :422-469: the points of r1 inside r2 first, then the points of r2 inside r1 */
+static void find_invasions(OrSystem *s, int64_t r1, int64_t r2) {
+  const int64_t ring[2] = {r1, r2};
+  for (int d = 0; d < 2; d++) {
+    const int64_t a = ring[d], b = ring[1 - d];
+    const double *pa = ring_points(s, a), *pb = ring_points(s, b);
+    const int32_t na = ring_np(s, a), nb = ring_np(s, b);
+    for (int32_t i = 0; i < na; i++) {
+      int count = 0;
+      for (int32_t e = 0; e < nb; e++) {
+        const int32_t e2 = e == nb - 1 ? 0 : e + 1;
+        count += point_line_intersect(pa + 2 * i, pb + 2 * e, pb + 2 * e2);
+      }
+      if (count % 2 != 0) inv_push(s, a, b, a * s->rp.n_max + i);
+    }
+  }
+}
+
+/* update_chunks!(r_chunks) for RingsChunksInfo (src/rings/integration.jl:18-23): the cms of the active rings */
+static int32_t update_ring_chunks(OrSystem *s) {
+  if (s->r_cols <= 0) return MAVI_OK;
+  memset(s->r_num, 0, sizeof(int64_t) * (size_t)(s->r_rows * s->r_cols));
+  for (int64_t q = 0; q < n_ring_ids(s); q++) {
+    const int64_t ring = ring_id_at(s, q);
+    const double x = s->cms[2 * ring], y = s->cms[2 * ring + 1];
+    double rowf = mor_julia_div(-y + s->p.grid_bl[1] + s->p.grid_h, s->r_ch);
+    double colf = mor_julia_div(x - s->p.grid_bl[0], s->r_cl);
+    if (!(fabs(rowf) < 9.0e15) || !(fabs(colf) < 9.0e15)) return MAVI_ERR_OUT_OF_GRID;
+    int64_t row_id = (int64_t)rowf + 1, col_id = (int64_t)colf + 1;
+    row_id -= row_id == (s->r_rows + 1) ? 1 : 0;
+    col_id -= col_id == (s->r_cols + 1) ? 1 : 0;
+    if (row_id < 1 || row_id > s->r_rows || col_id < 1 || col_id > s->r_cols) {
+      snprintf(s->err, sizeof s->err, "ring %lld: centre of mass out of the ring chunks (BoundsError in the reference)", (long long)ring);
+      return MAVI_ERR_OUT_OF_GRID;
+    }
+    const int64_t cell = (row_id - 1) + s->r_rows * (col_id - 1);
+    if (s->r_num[cell] >= s->r_nc) {
+      snprintf(s->err, sizeof s->err, "ring cell %lld over capacity %lld (BoundsError in the reference)", (long long)cell, (long long)s->r_nc);
+      return MAVI_ERR_CAPACITY;
+    }
+    s->r_particles[cell * s->r_nc + s->r_num[cell]++] = ring;
+  }
+  return MAVI_OK;
+}
+
+/* update_invasions! + check_invasions!, :471-520 */
+static void update_invasions(OrSystem *s) {
+  if (s->inv_steps <= 0) return;
+  if (s->num_steps - s->inv_last_check < s->inv_steps) return;
+  s->inv_last_check = s->num_steps;
+  s->inv_n = 0;
+  if (s->r_cols > 0) {
+    for (int64_t col = 0; col < s->r_cols; col++)
+      for (int64_t row = 0; row < s->r_rows; row++) {
+        const int64_t cell = row + s->r_rows * col;
+        const int64_t np = s->r_num[cell];
+        const int64_t *chunk = s->r_particles + cell * s->r_nc;
+        for (int64_t i = 0; i < np; i++) {
+          for (int64_t j = i + 1; j < np; j++) find_invasions(s, chunk[i], chunk[j]);
+          for (int k = 0; k < s->r_neigh_n[cell]; k++) {
+            const int64_t nc = s->r_neigh[4 * cell + k];
+            const int64_t *nei = s->r_particles + nc * s->r_nc;
+            for (int64_t j = 0; j < s->r_num[nc]; j++) find_invasions(s, chunk[i], nei[j]);
+          }
+        }
+      }
+  } else {
+    /* check_invasions!(system, ::Nothing): ring ids 1:num_rings of the active COUNT (sic), every pair once */
+    const int64_t nr = n_ring_ids(s);
+    for (int64_t r1 = 0; r1 < nr; r1++)
+      for (int64_t r2 = r1 + 1; r2 < nr; r2++) find_invasions(s, r1, r2);
+  }
+}
+
+int32_t mor_rings_set_invasions(OrSystem *s, int32_t steps_to_update, int32_t r_cols, int32_t r_rows) {
+  if (s->p.dynamics != MAVI_DYN_RINGS || steps_to_update < 0 || r_cols < 0 || r_rows < 0) return MAVI_ERR_BAD_PARAMS;
+  s->inv_steps = steps_to_update;
+  s->inv_last_check = 0;
+  s->inv_n = 0;
+  s->r_cols = r_cols; s->r_rows = r_rows;
+  if (r_cols > 0) {
+    /* Chunks(num_cols, num_rows, bounding box, cms, minimum(get_ring_radius(dynamic_cfg))), src/rings/rings.jl:187-203 */
+    s->r_cl = s->p.grid_len / (double)r_cols;
+    s->r_ch = s->p.grid_h / (double)r_rows;
+    double rr = INFINITY;
+    for (int t = 0; t < s->rp.num_types; t++) {
+      const double pr = s->rp.interaction[4 * ((int64_t)t * s->rp.num_types + t) + 2] / 2.0;
+      const double ring_r = (pr * 2) / sqrt(2 * (1 - cos(2 * M_PI / s->rp.num_particles[t]))); /* src/rings/utils.jl:5-7 */
+      if (ring_r < rr) rr = ring_r;
+    }
+    const double ncf = (ceil(0.5 * s->r_cl / rr) + 1) * (ceil(0.5 * s->r_ch / rr) + 1);
+    s->r_nc = (int64_t)ceil(ncf * 2);
+    s->r_particles = (int64_t *)calloc((size_t)(s->r_nc * r_cols * r_rows) + 1, sizeof(int64_t));
+    s->r_num = (int64_t *)calloc((size_t)(r_cols * r_rows) + 1, sizeof(int64_t));
+    NeighTab t;
+    build_neighbors_tab(&t, r_rows, r_cols, s->p.spaces[0].wall == MAVI_WALL_PERIODIC);
+    s->r_neigh = t.neigh;
+    s->r_neigh_n = t.neigh_n;
+  }
+  return MAVI_OK;
+}
+
+/* info.invasions.list of the last check: triples (invasor ring, invaded ring, scalar particle id), 0-based */
+int32_t mor_rings_download_invasions(OrSystem *s, int64_t *n, int32_t *triples, int64_t cap) {
+  if (n) *n = s->inv_n;
+  if (triples) memcpy(triples, s->inv_list, sizeof(int32_t) * 3 * (size_t)(s->inv_n < cap ? s->inv_n : cap));
+  return MAVI_OK;
+}
+
 /* ------------------------------------------------------------------ steps */
 
 static int64_t noise_stride(const OrSystem *s) {
@@ -1095,8 +1254,10 @@ static int32_t step_once(OrSystem *s, const double *noise) {
     update_cms(s);
     if ((st = update_sources(s))) return st;
     calc_active_ids(s); /* update_ids! */
-    if ((st = mor_update_chunks(s))) return st;
+    if ((st = mor_update_chunks(s))) return st; /* update_chunks_all!: particles, then the ring chunks */
+    if ((st = update_ring_chunks(s))) return st;
     update_continuos_pos(s);
+    update_invasions(s);
     mor_clean_forces(s);
     rings_forces(s);
     mor_walls_forces(s);
@@ -1300,6 +1461,7 @@ void mor_destroy(OrSystem *s) {
   free(s->chunk_particles); free(s->num_in_chunk); free(s->neigh); free(s->neigh_n);
   free(s->cont_pos); free(s->areas); free(s->cms);
   free(s->pn_count); free(s->pn_list);
+  free(s->inv_list); free(s->r_particles); free(s->r_num); free(s->r_neigh); free(s->r_neigh_n);
   free(s->ring_mask); free(s->ring_ids); free(s->ring_uids); free(s->draws);
   for (int k = 0; k < s->nsrc; k++) {
     OrSource *o = &s->src[k];

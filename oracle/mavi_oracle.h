@@ -53,6 +53,9 @@ int32_t mor_rings_download_neighbors(OrSystem *s, int32_t *count, int32_t *list)
 int32_t mor_rings_set_sources(OrSystem *s, const MaviSourceSink *list, int32_t n, const uint8_t *ring_active,
                               const double *spawn_draws, int64_t n_draws);
 int32_t mor_rings_download_active(OrSystem *s, uint8_t *ring_active, int64_t *uids, int64_t *num_active);
+/* InvasionsCfg(steps_to_update) + RingsIntCfg(r_chunks_cfg) (src/rings/configs.jl:334-352); r_cols = 0: no ring chunks */
+int32_t mor_rings_set_invasions(OrSystem *s, int32_t steps_to_update, int32_t r_cols, int32_t r_rows);
+int32_t mor_rings_download_invasions(OrSystem *s, int64_t *n, int32_t *triples, int64_t cap);
 int32_t mor_get_time(OrSystem *s, int64_t *num_steps, double *time);
 
 /* fine-grained operators for unit tests (each is one reference function) */
