@@ -263,6 +263,17 @@ int32_t mavi_rings_set_sources(MaviHandle *h, const MaviSourceSink *list, int32_
 /* VarRingsIds after the last step: mask[num_rings], uids[num_rings] (either may be NULL), number of active rings */
 int32_t mavi_rings_download_active(MaviHandle *h, uint8_t *ring_active, int64_t *uids, int64_t *num_active);
 
+/* ---- ring invasions, src/rings/integration.jl:379-520 ----------------------------------------------------------------
+ * RingsIntCfg(invasions_cfg = InvasionsCfg(steps_to_update), r_chunks_cfg = ChunksCfg(r_cols, r_rows)).  Every steps_to_update
+ * steps (update_invasions!, :509-520; before the forces of that step) the rings are binned by centre of mass into the ring
+ * chunks (update_chunks!(r_chunks), :18-23) and, for every pair of rings in the same or adjacent ring chunks, the particles of
+ * one that lie inside the polygon of the other (polygons_intersect: ray casting with point_line_intersect on ring_points) are
+ * listed.  r_cols = r_rows = 0: no ring chunks, every pair of rings is tested (check_invasions!(system, ::Nothing)).
+ * mavi_rings_download_invasions: info.invasions.list of the last check as triples (invasor ring, invaded ring, scalar particle
+ * id), 0-based, sorted lexicographically (the reference lists them in pair-enumeration order); *n = their number. */
+int32_t mavi_rings_set_invasions(MaviHandle *h, int32_t steps_to_update, int32_t r_cols, int32_t r_rows);
+int32_t mavi_rings_download_invasions(MaviHandle *h, int64_t *n, int32_t *triples, int64_t cap);
+
 /* TimeInfo, src/systems.jl:30-33 (time += dt accumulated in Float64, src/integration.jl:500-503) */
 int32_t mavi_get_time(MaviHandle *h, int64_t *num_steps, double *time);
 int32_t mavi_set_time(MaviHandle *h, int64_t num_steps, double time);

@@ -117,6 +117,8 @@ SIGNATURES = {
     "mavi_rings_download_neighbors": (C.c_int32, [_H, C.c_void_p, C.c_void_p]),
     "mavi_rings_set_sources": (C.c_int32, [_H, C.POINTER(MaviSourceSink), C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]),
     "mavi_rings_download_active": (C.c_int32, [_H, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]),
+    "mavi_rings_set_invasions": (C.c_int32, [_H, C.c_int32, C.c_int32, C.c_int32]),
+    "mavi_rings_download_invasions": (C.c_int32, [_H, C.POINTER(C.c_int64), C.c_void_p, C.c_int64]),
     "mavi_get_time": (C.c_int32, [_H, C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "mavi_set_time": (C.c_int32, [_H, C.c_int64, C.c_double]),
     "mavi_sync": (C.c_int32, [_H]),

@@ -144,6 +144,10 @@ static int validate_and_lower(Handle *h, const MaviParams *mp) {
   p.wall_fast = (mp->n_spaces == 1 && p.periodic) ? 1 : 0;
   p.wall_ctr[0] = m0.rect_bl[0] + p.half[0]; p.wall_ctr[1] = m0.rect_bl[1] + p.half[1];
 
+  // bounding box of the geometry (get_chunks, src/systems.jl:14-28): also the frame of the ring-level chunks
+  p.grid_bl[0] = mp->grid_bl[0]; p.grid_bl[1] = mp->grid_bl[1];
+  p.grid_h = mp->grid_h;
+  h->grid_len_host = mp->grid_len;
   // Chunks ctor, src/chunks.jl:26-40
   if (mp->num_cols > 0) {
     if (mp->num_rows < 1) {
@@ -525,15 +529,17 @@ int Handle::run_steps(long long nsteps, const real *noise_dev, size_t stride) {
       // Rings: up to SYNC_EVERY steps enqueued back to back; an index-tile overflow latches, the device step counter
       // tells how many steps ran, the host clock is rolled back and the rest is re-run with larger tiles
       const int batch = (int)((nsteps - done_total) < SYNC_EVERY ? (nsteps - done_total) : SYNC_EVERY);
-      long long snap_steps[SYNC_EVERY + 1];
+      long long snap_steps[SYNC_EVERY + 1], snap_check[SYNC_EVERY + 1];
       double snap_time[SYNC_EVERY + 1];
       snap_steps[0] = num_steps;
       snap_time[0] = time;
+      snap_check[0] = r.inv_last_check;
       const int c0 = steps_seen;
       for (int s = 0; s < batch; s++) {
         if ((st = rings_step(this, noise_dev ? noise_dev + (size_t)(done_total + s) * stride : nullptr))) return st;
         snap_steps[s + 1] = num_steps;
         snap_time[s + 1] = time;
+        snap_check[s + 1] = r.inv_last_check;
       }
       st = check_device_flags();
       int done = flags_host[FLAG_STEPS] - c0;
@@ -541,6 +547,7 @@ int Handle::run_steps(long long nsteps, const real *noise_dev, size_t stride) {
       steps_seen = flags_host[FLAG_STEPS];
       num_steps = snap_steps[done];
       time = snap_time[done];
+      r.inv_last_check = snap_check[done];
       done_total += done;
       if (st) return st;
       if (flags_host[FLAG_OVERFLOW] && (st = rings_grow_tiles(this))) return st;
@@ -1059,6 +1066,23 @@ int32_t api_rings_download_active(void *hh, uint8_t *ring_active, int64_t *uids,
   long long na = 0;
   int st = rings_download_active(h, ring_active, reinterpret_cast<long long *>(uids), &na);
   if (num_active) *num_active = na;
+  return st;
+}
+
+int32_t api_rings_set_invasions(void *hh, int32_t steps_to_update, int32_t r_cols, int32_t r_rows) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return MAVI_ERR_BAD_PARAMS;
+  cudaSetDevice(h->device);
+  return rings_set_invasions(h, steps_to_update, r_cols, r_rows);
+}
+
+int32_t api_rings_download_invasions(void *hh, int64_t *n, int32_t *triples, int64_t cap) {
+  Handle *h = reinterpret_cast<Handle *>(hh);
+  if (!h) return MAVI_ERR_BAD_PARAMS;
+  cudaSetDevice(h->device);
+  long long cnt = 0;
+  int st = rings_download_invasions(h, &cnt, triples, cap);
+  if (n) *n = cnt;
   return st;
 }
 

@@ -134,6 +134,12 @@ int32_t mavi_rings_set_sources(MaviHandle *h, const MaviSourceSink *list, int32_
 int32_t mavi_rings_download_active(MaviHandle *h, uint8_t *ring_active, int64_t *uids, int64_t *num_active) {
   MAVI_FWD_S(h, api_rings_download_active(impl, ring_active, uids, num_active));
 }
+int32_t mavi_rings_set_invasions(MaviHandle *h, int32_t steps_to_update, int32_t r_cols, int32_t r_rows) {
+  MAVI_FWD_S(h, api_rings_set_invasions(impl, steps_to_update, r_cols, r_rows));
+}
+int32_t mavi_rings_download_invasions(MaviHandle *h, int64_t *n, int32_t *triples, int64_t cap) {
+  MAVI_FWD_S(h, api_rings_download_invasions(impl, n, triples, cap));
+}
 int32_t mavi_get_time(MaviHandle *h, int64_t *num_steps, double *time) {
   MAVI_FWD_M(h, get_time(impl, num_steps, time), api_get_time(impl, num_steps, time));
 }

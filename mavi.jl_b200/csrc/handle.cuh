@@ -44,6 +44,14 @@ struct RingsArrays {
   int *empty_dev = nullptr;            // [n_areas] 1 = no active particle inside
   int n_areas = 0;
   bool has_sinks = false;
+  // invasions (src/rings/integration.jl:379-520): InvasionsCfg.steps_to_update, ring-level chunks on the centres of mass
+  int inv_steps = 0;              // 0 = off
+  long long inv_last_check = 0;   // InvasionsInfo.last_check
+  int r_cols = 0, r_rows = 0;     // r_chunks_cfg (0: check every pair of rings)
+  int *rcell = nullptr, *rcount = nullptr, *rstart = nullptr, *rperm = nullptr, *rpart = nullptr;
+  int *inv_list = nullptr;        // [inv_cap][3] = invasor ring, invaded ring, scalar particle id
+  int *inv_n = nullptr;
+  int inv_cap = 0;
 };
 
 // x-slab decomposition state (slab.cu)
@@ -77,6 +85,7 @@ struct Handle {
   int steps_seen = 0;  // host mirror of the device-side step counter flags[FLAG_STEPS]
   long long num_steps = 0;
   double time = 0.0;
+  double grid_len_host = 0.0;  // length of the bounding box of the geometry (MaviParams.grid_len)
   double dt_host = 0.0;  // IntCfg.dt as the host passed it (Float64): TimeInfo accumulates it in Float64 in both builds
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_call[2] = {nullptr, nullptr};
@@ -129,5 +138,7 @@ int rings_set_neighbors(Handle *h, int mode, int type_all, double tol);
 int rings_download_neighbors(Handle *h, int *count, int *list);
 int rings_set_sources(Handle *h, const MaviSourceSink *list, int n, const unsigned char *ring_active, const double *draws, long long n_draws);
 int rings_download_active(Handle *h, unsigned char *mask, long long *uids, long long *num_active);
+int rings_set_invasions(Handle *h, int steps_to_update, int r_cols, int r_rows);
+int rings_download_invasions(Handle *h, long long *n, int *triples, long long cap);
 
 }  // namespace MAVI_NS

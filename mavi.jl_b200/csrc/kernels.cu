@@ -1573,6 +1573,19 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
   }
 }
 
+// more than the 48 KB of dynamic shared memory a kernel gets by default: opt in once per (kernel instantiation, DEVICE) — the
+// attribute belongs to the device's context, and a single-process multi-GPU handle launches from one thread per device
+#define MAVI_OPT_IN_SMEM(kernel, bytes)                                                                  \
+  do {                                                                                                   \
+    static bool done_[64] = {};                                                                          \
+    int dev_ = 0;                                                                                        \
+    cudaGetDevice(&dev_);                                                                                \
+    if (dev_ >= 0 && dev_ < 64 && !done_[dev_]) {                                                        \
+      cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)); \
+      done_[dev_] = true;                                                                                \
+    }                                                                                                    \
+  } while (0)
+
 // (consumer warps) * 10 + (producer warps) per CTA of the pipelined kernels: 71 (default), 81, 72, 82 — MAVI_PIPE_CFG is the
 // A/B switch of the measurements in profiles/r02_ncu_newton_summary.md (LJ 16 M: 71 0.551 ms, 81 0.562, 82 0.562, 72 0.598)
 static inline int pipe_cfg() {
@@ -1584,10 +1597,16 @@ static inline int pipe_cfg() {
   return cfg;
 }
 
+// Persistent grids.  In the two-stream slab step the boundary-block launch (blk_mode 2, side stream) has to run WHILE the
+// interior launch (blk_mode 1) occupies the device: the interior launch leaves PIPE_BND_CTAS CTA slots free and the boundary
+// launch is exactly that large (its ~2 blocks per tile row are 1-2 % of the work).
+constexpr int PIPE_BND_CTAS = 16;
 static inline int grid_pipe(const DevParams &p) {
   const int per_row = p.blk_mode == 0 ? p.blk_per_row : (p.blk_mode == 1 ? p.blk_per_row - 1 - p.blk_last : 1 + p.blk_last);
   const int items = per_row * p.tpc;
-  const int want = 148 * PIPE_CTAS_PER_SM;
+  int want = 148 * PIPE_CTAS_PER_SM;
+  if (p.blk_mode == 1) want -= PIPE_BND_CTAS;
+  else if (p.blk_mode == 2) want = PIPE_BND_CTAS;
   return items < want ? (items > 0 ? items : 1) : want;
 }
 
@@ -1792,9 +1811,7 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p_in, const DevArrays 
     // pipelined persistent kernels (default); more than the 48 KB a kernel gets by default: opt in once per instantiation
 #define CALLP__(D, P, CARRYV, CWV, NPV)                                                                             \
   do {                                                                                                              \
-    static const cudaError_t attr_ = cudaFuncSetAttribute((const void *)k_newton_p<D, P, CARRYV, CWV, NPV>,         \
-                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);  \
-    (void)attr_;                                                                                                    \
+    MAVI_OPT_IN_SMEM((k_newton_p<D, P, CARRYV, CWV, NPV>), PIPE_SMEM);                                              \
     MAVI_LAUNCH(c, (k_newton_p<D, P, CARRYV, CWV, NPV>), grid_pipe(p), (CWV + NPV) * 32, PIPE_SMEM, ARGS2);         \
   } while (0)
 #define CALLP_(D, P, CARRYV)                               \
@@ -1808,7 +1825,9 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p_in, const DevArrays 
   } while (0)
 #define CALLP(D, P) CALLP_(D, P, false)
 #define CALLPC(D, P) CALLP_(D, P, true)
-    if (!(c.flags & MAVI_FLAG_LEGACY_STAGING)) {
+    // A/B switch for the two-stream slab step: the split launches (interior / boundary blocks) with the non-persistent kernels
+    static const bool slab_legacy = getenv("MAVI_SLAB_LEGACY") != nullptr;
+    if (!(c.flags & MAVI_FLAG_LEGACY_STAGING) && !(slab_legacy && blk_mode != 0)) {
       if (carry) {
         ms.chg = a.chg;
         if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALLPC);
@@ -1883,9 +1902,7 @@ void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArra
 #define CALL2(D, P) MAVI_LAUNCH(c, (k_self_propelled2<D, P>), grid2(p), TPB, PASS2_SMEM, p, a.tstart, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms)
 #define CALLP_(D, P, CWV, NPV)                                                                                      \
   do {                                                                                                              \
-    static const cudaError_t attr_ = cudaFuncSetAttribute((const void *)k_self_propelled_p<D, P, CWV, NPV>,         \
-                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM);  \
-    (void)attr_;                                                                                                    \
+    MAVI_OPT_IN_SMEM((k_self_propelled_p<D, P, CWV, NPV>), PIPE_SMEM);                                              \
     MAVI_LAUNCH(c, (k_self_propelled_p<D, P, CWV, NPV>), grid_pipe(p), (CWV + NPV) * 32, PIPE_SMEM, p, a.tstart, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms); \
   } while (0)
 #define CALLP(D, P)                                  \

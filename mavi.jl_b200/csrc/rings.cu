@@ -5,6 +5,7 @@
 //   k_rings_pair : calc_forces! with the Rings pair law (:32-77) + calc_walls_forces!          (thread per particle)
 //   k_rings_ring : update_cms! -> update_continuos_pos! -> calc_area -> springs -> area_forces! -> update! -> walls!
 //                                                                                              (warp per ring)
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -708,6 +709,126 @@ static void launch_ring(Handle *h, int mode, const real *noise, int prime_cms) {
 }
 
 
+
+// ---------------------------------------------------------------------------------------------------------
+// invasions (src/rings/integration.jl:379-520): every InvasionsCfg.steps_to_update steps, the particles of a ring that lie
+// inside the polygon of another ring whose centre of mass sits in the same or an adjacent RING chunk
+// ---------------------------------------------------------------------------------------------------------
+// update_continuos_pos! on its own (the ring kernel redoes it): ring_points of THIS step for the polygon tests
+template <bool PER>
+__global__ void k_rings_unwrap(const __grid_constant__ DevParams p, const unsigned char *__restrict__ ring_mask,
+                               const real2 *__restrict__ pos, real2 *__restrict__ cont_pos) {
+  const DevRings &R = p.rings;
+  const int ring = blockIdx.x * blockDim.x + threadIdx.x;
+  if (!PER || ring >= R.num_rings || (ring_mask && !ring_mask[ring])) return;
+  const int np = R.num_particles[ring_type(R, ring)];
+  const size_t base = (size_t)ring * R.n_max;
+  real2 c_prev = pos[base], r_prev = c_prev;
+  cont_pos[base] = c_prev;
+  for (int i = 1; i < np; i++) {
+    const real2 ri = pos[base + i];
+    const real dx = min_image<true>(ri.x - r_prev.x, p.half[0], p.size[0]);
+    const real dy = min_image<true>(ri.y - r_prev.y, p.half[1], p.size[1]);
+    c_prev = make_real2(c_prev.x + dx, c_prev.y + dy);
+    cont_pos[base + i] = c_prev;
+    r_prev = ri;
+  }
+  for (int i = np; i < R.n_max; i++) cont_pos[base + i] = pos[base + i];
+}
+
+// update_chunks!(r_chunks) (src/rings/integration.jl:18-23): ring chunk of every active ring's centre of mass
+__global__ void k_ring_cells(const __grid_constant__ DevParams p, const unsigned char *__restrict__ ring_mask,
+                             const real2 *__restrict__ cms, int r_cols, int r_rows, double r_cl, double r_ch,
+                             int *__restrict__ rcell, int *__restrict__ rcount, int *__restrict__ flags) {
+  const int ring = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ring >= p.rings.num_rings) return;
+  int c = -1;
+  if (!ring_mask || ring_mask[ring]) {
+    const double rowf = julia_div_pos(-(double)cms[ring].y + p.grid_bl[1] + p.grid_h, r_ch);
+    const double colf = julia_div_pos((double)cms[ring].x - p.grid_bl[0], r_cl);
+    if (fabs(rowf) < 2.0e9 && fabs(colf) < 2.0e9) {
+      int row = (int)rowf + 1, col = (int)colf + 1;
+      row -= (row == r_rows + 1) ? 1 : 0;
+      col -= (col == r_cols + 1) ? 1 : 0;
+      if (row >= 1 && row <= r_rows && col >= 1 && col <= r_cols) c = (row - 1) + r_rows * (col - 1);
+    }
+    if (c < 0) atomicOr(&flags[FLAG_ERR], ERRBIT_OUT_OF_GRID);  // BoundsError in the reference
+    else atomicAdd(&rcount[c], 1);
+  }
+  rcell[ring] = c;
+}
+__global__ void k_ring_scatter(int num_rings, const int *__restrict__ rcell, const int *__restrict__ rstart,
+                               int *__restrict__ rcount, int *__restrict__ rperm) {
+  const int ring = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ring >= num_rings) return;
+  const int c = rcell[ring];
+  if (c >= 0) rperm[rstart[c] + atomicSub(&rcount[c], 1) - 1] = ring;
+}
+
+// point_line_intersect, src/rings/integration.jl:379-420 (ray from p towards +x against the segment l1-l2)
+__device__ __forceinline__ bool point_line_intersect(real2 p, real2 l1, real2 l2) {
+  const real dx = l2.x - l1.x, dy = l2.y - l1.y;
+  const real ylo = dy < 0 ? l2.y : l1.y, yhi = dy < 0 ? l1.y : l2.y;
+  if (dx == 0) return (l1.x > p.x) & (ylo < p.y && p.y < yhi);
+  if (dy == 0) return false;
+  const real c = dy * l1.x - dx * l1.y;
+  const real x_inter = (c + dx * p.y) / dy;
+  const real xlo = dx < 0 ? l2.x : l1.x, xhi = dx < 0 ? l1.x : l2.x;
+  return (x_inter > p.x) & ((xlo < x_inter && x_inter < xhi) & (ylo < p.y && p.y < yhi));
+}
+
+// find_invasions! for every (particle of ring r1, ring r2 of the same / an adjacent ring chunk): thread per particle
+__global__ void k_invasions(const __grid_constant__ DevParams p, const unsigned char *__restrict__ ring_mask,
+                            const unsigned int *__restrict__ idflag, const real2 *__restrict__ pts,
+                            const int *__restrict__ rcell, const int *__restrict__ rstart, const int *__restrict__ rperm,
+                            int r_cols, int r_rows, int wrap, int *__restrict__ inv_n, int *__restrict__ inv_list, int inv_cap) {
+  const DevRings &R = p.rings;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n || (idflag[i] & MAVI_INACTIVE_BIT)) return;
+  const int r1 = i / R.n_max;
+  const real2 pt = pts[i];
+  auto test_ring = [&](int r2) {
+    if (r2 == r1) return;
+    const int np2 = R.num_particles[ring_type(R, r2)];
+    const real2 *poly = pts + (size_t)r2 * R.n_max;
+    int count = 0;
+    real2 a = poly[0];
+    for (int e = 0; e < np2; e++) {
+      const real2 b = poly[e == np2 - 1 ? 0 : e + 1];
+      count += point_line_intersect(pt, a, b) ? 1 : 0;
+      a = b;
+    }
+    if (count & 1) {
+      const int k = atomicAdd(inv_n, 1);
+      if (k < inv_cap) {
+        inv_list[3 * k] = r1;
+        inv_list[3 * k + 1] = r2;
+        inv_list[3 * k + 2] = i;
+      }
+    }
+  };
+  if (r_cols <= 0) {  // check_invasions!(system, ::Nothing): every pair of rings
+    for (int r2 = 0; r2 < R.num_rings; r2++)
+      if (!ring_mask || ring_mask[r2]) test_ring(r2);
+    return;
+  }
+  const int c = rcell[r1];
+  if (c < 0) return;
+  const int col = c / r_rows, row = c - col * r_rows;
+  for (int dc = -1; dc <= 1; dc++) {
+    int c2 = col + dc;
+    if (c2 < 0) { if (!wrap) continue; c2 = r_cols - 1; }
+    else if (c2 >= r_cols) { if (!wrap) continue; c2 = 0; }
+    for (int dr = -1; dr <= 1; dr++) {
+      int r2 = row + dr;
+      if (r2 < 0) { if (!wrap) continue; r2 = r_rows - 1; }
+      else if (r2 >= r_rows) { if (!wrap) continue; r2 = 0; }
+      const int cell = r2 + r_rows * c2;
+      for (int q = rstart[cell]; q < rstart[cell + 1]; q++) test_ring(rperm[q]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // sources / sinks / variable ring count (src/rings/sources.jl, src/rings/states.jl:173-227)
 // ---------------------------------------------------------------------------------------------------------
@@ -932,6 +1053,92 @@ static int rings_process_sources(Handle *h) {
   return MAVI_OK;
 }
 
+// InvasionsCfg(steps_to_update) + RingsIntCfg(r_chunks_cfg), src/rings/configs.jl:334-352
+int rings_set_invasions(Handle *h, int steps_to_update, int r_cols, int r_rows) {
+  if (h->p.dynamics != MAVI_DYN_RINGS || steps_to_update < 0 || r_cols < 0 || r_rows < 0 || (r_cols > 0) != (r_rows > 0)) {
+    h->set_error("bad InvasionsCfg / r_chunks_cfg");
+    return MAVI_ERR_BAD_PARAMS;
+  }
+  RingsArrays &r = h->r;
+  const size_t nr = (size_t)h->p.rings.num_rings, ncell = (size_t)r_cols * r_rows;
+  r.inv_steps = steps_to_update;
+  r.inv_last_check = 0;
+  r.r_cols = r_cols;
+  r.r_rows = r_rows;
+  auto al = [&](int **ptr, size_t count) -> int {
+    *ptr = nullptr;
+    if (cudaMalloc((void **)ptr, (count ? count : 1) * sizeof(int)) != cudaSuccess) {
+      h->set_error("cudaMalloc failed (invasions)");
+      return MAVI_ERR_CUDA;
+    }
+    h->allocs.push_back((void *)*ptr);
+    return MAVI_OK;
+  };
+  int st;
+  r.inv_cap = (int)(2 * (size_t)h->p.n + 64);
+  if ((st = al(&r.rcell, nr)) || (st = al(&r.rcount, ncell + 2)) || (st = al(&r.rstart, ncell + 2)) || (st = al(&r.rperm, nr + 1)) ||
+      (st = al(&r.rpart, ncell / 4096 + 4)) || (st = al(&r.inv_list, 3 * (size_t)r.inv_cap)) || (st = al(&r.inv_n, 1)))
+    return st;
+  RINGS_TRY(h, cudaMemsetAsync(r.inv_n, 0, sizeof(int), h->stream));
+  return MAVI_OK;
+}
+
+// update_invasions! (src/rings/integration.jl:509-520) of the step about to run; info.cms must be current
+static int rings_check_invasions(Handle *h) {
+  DevParams &p = h->p;
+  DevArrays &a = h->a;
+  RingsArrays &r = h->r;
+  const int nr = p.rings.num_rings;
+  const int gr = (nr + TPB - 1) / TPB;
+  r.inv_last_check = h->num_steps;
+  if (p.periodic) RINGS_LAUNCH(h, (k_rings_unwrap<true>), gr, TPB, p, r.mask_dev, a.pos[0], r.cont_pos);
+  RINGS_TRY(h, cudaMemsetAsync(r.inv_n, 0, sizeof(int), h->stream));
+  if (r.r_cols > 0) {
+    const int ncell = r.r_cols * r.r_rows;
+    RINGS_TRY(h, cudaMemsetAsync(r.rcount, 0, ((size_t)ncell + 2) * sizeof(int), h->stream));
+    RINGS_LAUNCH(h, k_ring_cells, gr, TPB, p, r.mask_dev, r.cms, r.r_cols, r.r_rows, h->grid_len_host / (double)r.r_cols,
+                 (double)p.grid_h / r.r_rows, r.rcell, r.rcount, a.flags);
+    launch_exclusive_scan(h->ctx(), r.rcount, r.rstart, r.rpart, ncell + 1);
+    RINGS_LAUNCH(h, k_ring_scatter, gr, TPB, nr, r.rcell, r.rstart, r.rcount, r.rperm);
+  }
+  RINGS_LAUNCH(h, k_invasions, (p.n + TPB - 1) / TPB, TPB, p, r.mask_dev, a.idflag, p.periodic ? r.cont_pos : a.pos[0], r.rcell, r.rstart,
+               r.rperm, r.r_cols, r.r_rows, p.spaces[0].wall == MAVI_WALL_PERIODIC ? 1 : 0, r.inv_n, r.inv_list, r.inv_cap);
+  return MAVI_OK;
+}
+
+// info.invasions.list of the last check as (invasor ring, invaded ring, scalar particle id) triples, 0-based, sorted
+int rings_download_invasions(Handle *h, long long *n, int *triples, long long cap) {
+  RingsArrays &r = h->r;
+  if (h->p.dynamics != MAVI_DYN_RINGS || !r.inv_n) {
+    h->set_error("invasions are off (mavi_rings_set_invasions)");
+    return MAVI_ERR_BAD_PARAMS;
+  }
+  int cnt = 0;
+  RINGS_TRY(h, cudaMemcpyAsync(&cnt, r.inv_n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  int st = h->check_device_flags();
+  if (st) return st;
+  if (cnt > r.inv_cap) {
+    h->set_error("%d invasions exceed the list capacity %d", cnt, r.inv_cap);
+    return MAVI_ERR_CAPACITY;
+  }
+  if (n) *n = cnt;
+  if (triples && cnt > 0) {
+    std::vector<int> tmp(3 * (size_t)cnt);
+    RINGS_TRY(h, cudaMemcpy(tmp.data(), r.inv_list, tmp.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<size_t> order((size_t)cnt);
+    for (size_t i = 0; i < order.size(); i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](size_t x, size_t y) {
+      for (int q = 0; q < 3; q++)
+        if (tmp[3 * x + q] != tmp[3 * y + q]) return tmp[3 * x + q] < tmp[3 * y + q];
+      return false;
+    });
+    const long long m = cnt < cap ? cnt : cap;
+    for (long long i = 0; i < m; i++)
+      for (int q = 0; q < 3; q++) triples[3 * i + q] = tmp[3 * order[(size_t)i] + q];
+  }
+  return MAVI_OK;
+}
+
 // RingsSystem ctor tail (src/rings/rings.jl:280-288): ids, continuos_pos, cms, chunks, forces!
 int rings_upload_finish(Handle *h) {
   DevParams &p = h->p;
@@ -977,6 +1184,7 @@ int rings_step(Handle *h, const real *noise_dev) {
     int st = rings_process_sources(h);
     if (st) return st;
     if ((st = rings_bin(h))) return st;
+    if (r.inv_steps > 0 && h->num_steps - r.inv_last_check >= r.inv_steps && (st = rings_check_invasions(h))) return st;
     launch_pair(h, true);
     launch_ring(h, 1, noise_dev, -1);  // -1: update_cms! already done
     h->num_steps += 1;
@@ -987,8 +1195,18 @@ int rings_step(Handle *h, const real *noise_dev) {
     RINGS_TRY(h, cudaMemsetAsync(a.count, 0, ((size_t)p.num_cells + 2) * sizeof(int), h->stream));
     launch_build_index_tiles(h->ctx(), p, a.pos[0], a.idflag, a.cell, a.count, a.tstart, a.perm, a.flags);
   }
+  int prime = 0;
+  if (r.inv_steps > 0 && h->num_steps - r.inv_last_check >= r.inv_steps) {
+    // a check step: update_cms! on its own first (the ring chunks bin THIS step's cms), then the polygon tests
+    const int gr = (p.rings.num_rings + TPB - 1) / TPB;
+    if (p.periodic) RINGS_LAUNCH(h, (k_rings_cms<true>), gr, TPB, p, r.mask_dev, a.pos[0], r.cont_pos, r.cms);
+    else RINGS_LAUNCH(h, (k_rings_cms<false>), gr, TPB, p, r.mask_dev, a.pos[0], r.cont_pos, r.cms);
+    int st = rings_check_invasions(h);
+    if (st) return st;
+    prime = -1;
+  }
   launch_pair(h, true);
-  launch_ring(h, 1, noise_dev, 0);
+  launch_ring(h, 1, noise_dev, prime);
   h->num_steps += 1;  // src/rings/integration.jl:541-542
   h->time += h->dt_host;
   return MAVI_OK;

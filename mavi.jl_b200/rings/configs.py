@@ -110,8 +110,19 @@ class NeighborsCfg:
             raise ValueError("NeighborsCfg.type must be :rings or :all")
 
 
+@dataclass
+class InvasionsCfg:
+    """src/rings/configs.jl:334-336."""
+    steps_to_update: int
+
+
+@dataclass
+class IntCfgExtra:
+    """src/rings/configs.jl:338-341."""
+    r_chunks_cfg: Optional[ChunksCfg] = None
+    invasions_cfg: Optional[InvasionsCfg] = None
+
+
 def RingsIntCfg(*, dt, p_chunks_cfg=None, r_chunks_cfg=None, invasions_cfg=None, device=None):
-    """src/rings/configs.jl:343-351.  Ring-level chunks / invasions are "next" rows (SURVEY.md 8f #4)."""
-    if r_chunks_cfg is not None or invasions_cfg is not None:
-        raise NotImplementedError("ring-level chunks / invasions are outside the device hot path (SURVEY.md 8f)")
-    return IntCfg(dt=dt, chunks_cfg=p_chunks_cfg, device=device or CUDADevice())
+    """src/rings/configs.jl:343-351: an IntCfg whose `extra` carries the ring-level chunks and the invasions config."""
+    return IntCfg(dt=dt, chunks_cfg=p_chunks_cfg, device=device or CUDADevice(), extra=IntCfgExtra(r_chunks_cfg, invasions_cfg))

@@ -66,6 +66,12 @@ class System:
             mode = capi.NEIGH_COUNT if p_neighbors_cfg.only_count else capi.NEIGH_LIST
             self._check(self._lib.mavi_rings_set_neighbors(self._h, mode, int(p_neighbors_cfg.type == "all"),
                                                            float(p_neighbors_cfg.tol)))
+        extra = getattr(int_cfg, "extra", None)
+        inv = getattr(extra, "invasions_cfg", None)
+        if inv is not None:   # RingsIntCfg(invasions_cfg=..., r_chunks_cfg=...), src/rings/configs.jl:343-351
+            rc = getattr(extra, "r_chunks_cfg", None)
+            self._check(self._lib.mavi_rings_set_invasions(self._h, int(inv.steps_to_update), 0 if rc is None else int(rc.num_cols),
+                                                           0 if rc is None else int(rc.num_rows)))
         self.source_cfg = source_cfg
         ring_mask = getattr(state, "ring_mask", None)
         if source_cfg is not None or ring_mask is not None:
@@ -273,6 +279,16 @@ class System:
         lst = None if only else np.empty((self._n, capi.NEIGH_MAX), dtype=np.int32)
         self._check(self._lib.mavi_rings_download_neighbors(self._h, _ptr(count), _ptr(lst)))
         return count, (None if only else [lst[i, :count[i]].tolist() for i in range(self._n)])
+
+    def invasions(self):
+        """`system.info.invasions.list` of the last check (src/rings/integration.jl:509-520) as an (n, 3) int array of
+        (invasor ring, invaded ring, scalar particle id), 0-based, sorted."""
+        n = C.c_int64()
+        self._check(self._lib.mavi_rings_download_invasions(self._h, C.byref(n), None, 0))
+        out = np.empty((n.value, 3), dtype=np.int32)
+        if n.value:
+            self._check(self._lib.mavi_rings_download_invasions(self._h, C.byref(n), _ptr(out), n.value))
+        return out
 
     def rings_active(self):
         """(mask[num_rings], uids[num_rings], num_active): VarRingsIds after the last step (sources / sinks add and remove

@@ -80,6 +80,7 @@ def load(fast=False):
         "mor_rings_download_info": (i32, [H, vp, vp, vp]),
         "mor_rings_set_neighbors": (i32, [H, i32, i32, dbl]), "mor_rings_download_neighbors": (i32, [H, vp, vp]),
         "mor_rings_set_sources": (i32, [H, vp, i32, vp, vp, i64]), "mor_rings_download_active": (i32, [H, vp, vp, C.POINTER(i64)]),
+        "mor_rings_set_invasions": (i32, [H, i32, i32, i32]), "mor_rings_download_invasions": (i32, [H, C.POINTER(i64), vp, i64]),
         "mor_get_time": (i32, [H, C.POINTER(i64), C.POINTER(dbl)]),
         "mor_clean_forces": (None, [H]), "mor_update_chunks": (i32, [H]), "mor_pair_forces": (None, [H]),
         "mor_walls_forces": (None, [H]), "mor_walls": (None, [H]), "mor_update_verlet": (None, [H]),
@@ -125,6 +126,12 @@ class OracleSystem:
         if p_neighbors_cfg is not None:  # RingsSystem(p_neighbors_cfg=...), src/rings/rings.jl:143-158
             self._check(self.lib.mor_rings_set_neighbors(self.h, 1 if p_neighbors_cfg.only_count else 2,
                                                          int(p_neighbors_cfg.type == "all"), float(p_neighbors_cfg.tol)))
+        extra = getattr(int_cfg, "extra", None)
+        inv = getattr(extra, "invasions_cfg", None)
+        if inv is not None:
+            rc = getattr(extra, "r_chunks_cfg", None)
+            self._check(self.lib.mor_rings_set_invasions(self.h, int(inv.steps_to_update), 0 if rc is None else int(rc.num_cols),
+                                                         0 if rc is None else int(rc.num_rows)))
         ring_mask = getattr(state, "ring_mask", None)
         if source_cfg is not None or ring_mask is not None:  # RingsSystem(source_cfg=...), RingsState(active_state=...)
             import __graft_entry__ as entry
@@ -215,6 +222,15 @@ class OracleSystem:
         areas, cms, cont = np.empty(nr), np.empty((nr, 2)), np.empty((self.n, 2))
         self._check(self.lib.mor_rings_download_info(self.h, _ptr(areas), _ptr(cms), _ptr(cont)))
         return areas, cms, cont
+
+    def invasions(self):
+        """info.invasions.list of the last check as (n, 3) rows (invasor, invaded, particle id), sorted."""
+        n = C.c_int64()
+        self._check(self.lib.mor_rings_download_invasions(self.h, C.byref(n), None, 0))
+        out = np.empty((n.value, 3), dtype=np.int32)
+        if n.value:
+            self._check(self.lib.mor_rings_download_invasions(self.h, C.byref(n), _ptr(out), n.value))
+        return out[np.lexsort((out[:, 2], out[:, 1], out[:, 0]))] if n.value else out
 
     def rings_active(self):
         nr = self.state.num_rings
