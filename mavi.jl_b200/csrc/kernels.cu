@@ -1151,6 +1151,9 @@ __device__ __forceinline__ void chunk_stage(const DevParams &p, const int *__res
   __syncthreads();
 }
 
+#ifndef MAVI_WALK_UNROLL
+#define MAVI_WALK_UNROLL 4  // pairs per trip of the neighbour loop (build-time A/B)
+#endif
 // pair force on the staged particle (staged column jj, tile row lr, staged index self) from the staged positions
 template <int DYN, bool MINIMG, typename CK>
 __device__ __forceinline__ void chunk_walk(const DevParams &p, const CK *ck, const real2 *s_pos, int jj, int lr,
@@ -1166,7 +1169,8 @@ __device__ __forceinline__ void chunk_walk(const DevParams &p, const CK *ck, con
   const int o0 = w0.x * B;
   const int d1 = w1.x * B - c1 - o0, d3 = w2.x * B - c3 - (w1.x * B - c1) - B;
   const char *base = reinterpret_cast<const char *>(s_pos) + o0;
-#pragma unroll 4
+  constexpr int UNROLL = MAVI_WALK_UNROLL;
+#pragma unroll UNROLL
   for (int t = 0; t < total; t += B) {
     const int o = t + (t >= c1 ? d1 : 0) + (t >= c2 ? B : 0) + (t >= c3 ? d3 : 0);
     accumulate_pair<DYN, MINIMG>(p, ri, *reinterpret_cast<const real2 *>(base + o), fx, fy);
@@ -1192,8 +1196,8 @@ __device__ __forceinline__ void for_each_block_particle(const DevParams &p, cons
     const int i = ((int)blockIdx.x - nblk_tiles) * TPB + threadIdx.x;
     if (i < p.n - p.n_active) {
       const int k = p.tail_base + i;
-      pre(k);
-      body(k, pos[k], 0, false, make_real2(0.0, 0.0), InCellNone{});
+      auto pv = pre(k);
+      body(k, pos[k], 0, false, make_real2(0.0, 0.0), InCellNone{}, pv);
     }
     return;
   }
@@ -1215,24 +1219,24 @@ __device__ __forceinline__ void for_each_block_particle(const DevParams &p, cons
         const unsigned int u = s_list[q];
         const int self = u & 0xffffu, jj = (u >> 16) & 0xffu, lr = u >> 24;
         const int k = self + ck->gbase[jj];
-        pre(k);
+        auto pv = pre(k);
         const real2 r = s_pos[self];
         real fx = 0.0, fy = 0.0;
         if (mi) chunk_walk<DYN, true>(p, ck, s_pos, jj, lr, self, r, fx, fy);
         else chunk_walk<DYN, false>(p, ck, s_pos, jj, lr, self, r, fx, fy);
         const int cc = (cs - 1 + jj) * p.num_rows + r0 + lr - 1;
-        body(k, r, cc, true, make_real2(fx, fy), InCellExact{p, cc});
+        body(k, r, cc, true, make_real2(fx, fy), InCellExact{p, cc}, pv);
       }
     } else {
       // a single column too dense for the staging area: per-thread walk over the global arrays
       const int b = ck->src_t[1], e = b + ck->lt[1];
       for (int k = b + threadIdx.x; k < e; k += TPB) {
-        pre(k);
+        auto pv = pre(k);
         const real2 r = pos[k];
         const int c = cell[k];
         real fx = 0.0, fy = 0.0;
         for_each_neighbor(p, tstart, c, k, [&](int j) { accumulate_pair<DYN, PER>(p, r, __ldg(pos + j), fx, fy); });
-        body(k, r, c, true, make_real2(fx, fy), InCellExact{p, c});
+        body(k, r, c, true, make_real2(fx, fy), InCellExact{p, c}, pv);
       }
     }
     cs += nc;
@@ -1521,8 +1525,8 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
     const int ntail = p.n - p.n_active;
     for (int i = (int)blockIdx.x * PIPE_CT + (int)threadIdx.x; i < ntail; i += (int)gridDim.x * PIPE_CT) {
       const int k = p.tail_base + i;
-      pre(k);
-      body(k, pos[k], 0, false, make_real2(0.0, 0.0), InCellNone{});
+      auto pv = pre(k);
+      body(k, pos[k], 0, false, make_real2(0.0, 0.0), InCellNone{}, pv);
     }
   }
   // the two buffers are consumed alternately; uses = how often each was consumed (barrier phase), done = its end marker seen
@@ -1547,24 +1551,24 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
         const unsigned int u = s_list[q];
         const int self = u & 0xffffu, jj = (u >> 16) & 0xffu, lr = u >> 24;
         const int k = self + ck->gbase[jj];
-        pre(k);
+        auto pv = pre(k);
         const real2 r = s_pos[self];
         real fx = 0.0, fy = 0.0;
         if (mi) chunk_walk<DYN, true>(p, ck, s_pos, jj, lr, self, r, fx, fy);
         else chunk_walk<DYN, false>(p, ck, s_pos, jj, lr, self, r, fx, fy);
         const double2 xe = ck->xb[jj], ye = ck->yb[lr - 1];
-        body(k, r, (cs - 1 + jj) * p.num_rows + r0 + lr - 1, true, make_real2(fx, fy), InCellTab{p, xe.x, xe.y, ye.x, ye.y});
+        body(k, r, (cs - 1 + jj) * p.num_rows + r0 + lr - 1, true, make_real2(fx, fy), InCellTab{p, xe.x, xe.y, ye.x, ye.y}, pv);
       }
     } else {
       // a single column too dense for the staging area: per-thread walk over the global arrays
       const int b0 = ck->src_t1, e0 = b0 + ck->lt1;
       for (int k = b0 + (int)threadIdx.x; k < e0; k += PIPE_CT) {
-        pre(k);
+        auto pv = pre(k);
         const real2 r = pos[k];
         const int c = cell[k];
         real fx = 0.0, fy = 0.0;
         for_each_neighbor(p, tstart, c, k, [&](int jn) { accumulate_pair<DYN, PER>(p, r, __ldg(pos + jn), fx, fy); });
-        body(k, r, c, true, make_real2(fx, fy), InCellExact{p, c});
+        body(k, r, c, true, make_real2(fx, fy), InCellExact{p, c}, pv);
       }
     }
     __syncwarp();
@@ -1619,8 +1623,8 @@ template <int DYN, bool PER>
 __global__ void __launch_bounds__(TPB) k_force_only2(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
                               const int *__restrict__ cell, const real2 *__restrict__ pos,
                               real2 *__restrict__ force, int with_walls) {
-  for_each_block_particle<DYN, PER>(p, tstart, pos, cell, false, [](int) {},
-    [&](int k, real2 r, int, bool active, real2 F, auto) {
+  for_each_block_particle<DYN, PER>(p, tstart, pos, cell, false, [](int) { return 0; },
+    [&](int k, real2 r, int, bool active, real2 F, auto, auto) {
       if (active && with_walls && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
       force[k] = F;
     });
@@ -1632,8 +1636,8 @@ __global__ void __launch_bounds__(TPB) k_newton_a2(const __grid_constant__ DevPa
                             const real2 *__restrict__ vel, real2 *__restrict__ pos_out, real2 *__restrict__ f1,
                             int *__restrict__ flags) {
   if (!flags[FLAG_RAN]) return;
-  for_each_block_particle<DYN, PER>(p, tstart, pos_in, cell, false, [&](int k) { prefetch_l1(vel + k); },
-    [&](int k, real2 r, int, bool active, real2 F, auto) {
+  for_each_block_particle<DYN, PER>(p, tstart, pos_in, cell, false, [&](int k) { prefetch_l1(vel + k); return 0; },
+    [&](int k, real2 r, int, bool active, real2 F, auto, auto) {
       if (active && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
       bool big;
       pos_out[k] = verlet_drift(p, r, vel[k], F, big);
@@ -1643,11 +1647,19 @@ __global__ void __launch_bounds__(TPB) k_newton_a2(const __grid_constant__ DevPa
 }
 
 // pre(k) / body(k, r, cell, active, F) of the second Newton pass
+// MAVI_EARLY_LOAD (build-time A/B): vel / F1 are loaded into registers before the pair loop instead of being prefetched to L1
+struct VelF1 { real2 v, f; };
+#ifdef MAVI_EARLY_LOAD
+#define MAVI_NB_PRE [&](int k) { return VelF1{vel[k], f1[k]}; }
+#define MAVI_NB_GET real2 v = pv.v; const real2 Fo = pv.f;
+#else
+#define MAVI_NB_PRE [&](int k) { prefetch_l1(vel + k); prefetch_l1(f1 + k); return 0; }
+#define MAVI_NB_GET real2 v = vel[k]; const real2 Fo = f1[k];
+#endif
 #define MAVI_NEWTON_B_LAMBDAS \
-    [&](int k) { prefetch_l1(vel + k); prefetch_l1(f1 + k); }, \
-    [&](int k, real2 r, int c, bool active, real2 F, auto in_cell) { \
-      real2 v = vel[k]; \
-      const real2 Fo = f1[k]; \
+    MAVI_NB_PRE, \
+    [&](int k, real2 r, int c, bool active, real2 F, auto in_cell, auto pv) { \
+      MAVI_NB_GET \
       v.x = v.x + p.hdt * (F.x + Fo.x); \
       v.y = v.y + p.hdt * (F.y + Fo.y); \
       if (active) { \
@@ -1705,8 +1717,8 @@ __global__ void __launch_bounds__((CW + NP) * 32, PIPE_CTAS_PER_SM) k_self_prope
     const real *__restrict__ noise, unsigned long long step, const __grid_constant__ MoverSink ms) {
   if (!ms.flags[FLAG_RAN]) return;
   pipe_for_each_particle<DYN, PER, CW, NP>(p, tstart, pos_in, ms.cell, false, ms.flags + FLAG_WORK0,
-    [&](int k) { prefetch_l1(ang + k); prefetch_l1(idflag + k); },
-    [&](int k, real2 r, int c, bool active, real2 F, auto in_cell) {
+    [&](int k) { prefetch_l1(ang + k); prefetch_l1(idflag + k); return 0; },
+    [&](int k, real2 r, int c, bool active, real2 F, auto in_cell, auto) {
       const unsigned int id = idflag[k] & ~MAVI_INACTIVE_BIT;
       if (active && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
       force[k] = F;
@@ -1728,8 +1740,8 @@ __global__ void __launch_bounds__(TPB) k_self_propelled2(const __grid_constant__
                                   const __grid_constant__ MoverSink ms) {
   if (!ms.flags[FLAG_RAN]) return;
   for_each_block_particle<DYN, PER>(p, tstart, pos_in, ms.cell, false,
-    [&](int k) { prefetch_l1(ang + k); prefetch_l1(idflag + k); },
-    [&](int k, real2 r, int c, bool active, real2 F, auto in_cell) {
+    [&](int k) { prefetch_l1(ang + k); prefetch_l1(idflag + k); return 0; },
+    [&](int k, real2 r, int c, bool active, real2 F, auto in_cell, auto) {
       const unsigned int id = idflag[k] & ~MAVI_INACTIVE_BIT;
       if (active && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
       force[k] = F;
@@ -1825,9 +1837,13 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p_in, const DevArrays 
   } while (0)
 #define CALLP(D, P) CALLP_(D, P, false)
 #define CALLPC(D, P) CALLP_(D, P, true)
-    // A/B switch for the two-stream slab step: the split launches (interior / boundary blocks) with the non-persistent kernels
-    static const bool slab_legacy = getenv("MAVI_SLAB_LEGACY") != nullptr;
-    if (!(c.flags & MAVI_FLAG_LEGACY_STAGING) && !(slab_legacy && blk_mode != 0)) {
+    // The two-stream slab step splits the pass into an interior and a boundary launch that must overlap: the boundary blocks
+    // (side stream, high priority) slip into the slots the short-lived CTAs of the non-persistent kernels free all the time,
+    // but cannot get onto a device that persistent CTAs occupy for the whole pass (measured at 2 GPUs, profiles/
+    // r02_slab_timeline.md: 0.70 ms/step with the non-persistent kernels, 0.86 with persistent ones + 16 reserved slots).
+    // MAVI_SLAB_PIPELINED=1 is the A/B switch.
+    static const bool slab_pipelined = getenv("MAVI_SLAB_PIPELINED") != nullptr;
+    if (!(c.flags & MAVI_FLAG_LEGACY_STAGING) && (blk_mode == 0 || slab_pipelined)) {
       if (carry) {
         ms.chg = a.chg;
         if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALLPC);
