@@ -857,6 +857,7 @@ int32_t api_upload_local(void *hh, const int64_t *ids, const void *pos, const vo
   h->p.n = (int)n_local;
   int st = h->rebuild_from_staging((int)n_local);
   if (st) return st;
+  if ((st = slab_sync_counts(h))) return st;  // tiles that start out nearly full grow before the first step (collective)
   return h->check_device_flags();
 }
 

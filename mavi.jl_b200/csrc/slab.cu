@@ -355,6 +355,23 @@ int slab_sync_counts(Handle *h) {
   if (st) return st;
   st = slab_refresh_count(h);
   if (st) return st;
+  // Proactive tile growth.  A tile overflow in the middle of an un-synchronised run of slab steps cannot be rolled back (the
+  // other ranks have moved on), so it must not happen: at every synchronisation point (all ranks are at the same step here)
+  // the fullest tile seen so far is compared with the capacity and, if ANY rank is above 70 %, every rank rebuilds its
+  // layout with larger tiles — the slab-mode counterpart of the single-GPU overflow -> rebuild -> resume path.
+  if (!h->flags_host[FLAG_OVERFLOW]) {
+    int need = 0;
+    if (h->flags_host[FLAG_MAXCOUNT] * 10 > p.cap * 7) need = ((int)(h->flags_host[FLAG_MAXCOUNT] * 1.6) + 31) / 16 * 16;
+    if ((st = slab_allreduce_max(h, &need))) return st;
+    if (need > p.cap) {
+      h->n_rebuilds++;
+      launch_compact_to_staging(h->ctx(), h->p, h->a, h->second_kind == SECOND_VEL);  // with the current layout
+      const int n_owned = h->p.n;
+      if ((st = h->alloc_state(n_owned, need))) return st;          // every rank: the same, all-reduced capacity
+      if ((st = h->rebuild_from_staging(n_owned))) return st;       // collective (capacity agreement, first halo exchange)
+      return MAVI_OK;
+    }
+  }
   if (h->flags_host[FLAG_OVERFLOW]) {
     h->set_error("slab mode overflow (bits %d: 1 = tile capacity %d < %d, 2 = inbox capacity %d < %d at tile %d (column %d of %d), 4 = mover list %d, 8 = changed-cell list)",
                  h->flags_host[FLAG_OVERFLOW], p.cap, h->flags_host[FLAG_MAXCOUNT], p.inbox_cap, h->flags_host[FLAG_MAXINBOX],

@@ -36,9 +36,7 @@ def fast_lib_path():
 def build_fast(verbose=False):
     """The TIMING build of the same source (`-O3 -march=native -fopenmp`), a separate target from the
     parity oracle (`-O2 -ffp-contract=off`): used by bench.py's cpu_baseline / --impl reference legs only."""
-    path = fast_lib_path()
-    if os.path.exists(path):
-        return path
+    path = fast_lib_path()  # make rebuilds it when mavi_oracle.c is newer (a stale build lacks the newer entry points)
     res = subprocess.run(["make", "-C", _HERE, "fast", f"FAST_SO={os.path.basename(path)}"], capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout[-3000:], res.stderr[-3000:])

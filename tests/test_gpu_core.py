@@ -500,6 +500,26 @@ def test_c2_one_million_properties(cuda_lib):
     assert np.all(np.diff(cell[seg]) >= 0)
 
 
+def test_slab_mode_grows_tiles_proactively(cuda_lib):
+    """Slab mode cannot roll an overflowed step back (the other ranks have moved on), so tiles grow BEFORE they overflow: at
+    every synchronisation point a tile above 70 % of the capacity makes all ranks rebuild with larger tiles.  Forced here by
+    MAVI_FLAG_TIGHT_TILES (capacity = fullest tile at upload) in one-rank slab mode; results stay bit-identical."""
+    SELF, TIGHT = pkg.capi.FLAG_SLAB_SELF, pkg.capi.FLAG_TIGHT_TILES
+    case = H.newton_case(nx=64, ny=40, wall="periodic", jitter=0.3, vmax=3.0, dt=0.002)
+    a = H.make_gpu(_with_flags(case, 0))
+    b = H.make_gpu(_with_flags(case, SELF | TIGHT))
+    assert b.rebuild_count() >= 1           # grown right after the upload
+    cap0 = b.counters()["tile_cap"]
+    for steps in (40, 100):
+        a.step(steps)
+        b.step(steps)
+        a.sync_to_host()
+        ids, pos, vel, frc = b.download_local()
+        o = np.argsort(ids)
+        assert np.array_equal(pos[o], a.state.pos) and np.array_equal(vel[o], a.state.vel) and np.array_equal(frc[o], a.get_forces())
+    assert b.counters()["tile_cap"] >= cap0
+
+
 # ---------------------------------------------------------------- the x-slab machinery on ONE GPU (MAVI_FLAG_SLAB_SELF)
 @pytest.mark.parametrize("kind,flags", [("lj", 0), ("lj", 8), ("harm", 8), ("szabo", 0), ("szabo_noise", 0), ("rtp", 0)])
 def test_slab_self_mode_matches_plain(cuda_lib, kind, flags):

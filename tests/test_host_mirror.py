@@ -68,8 +68,8 @@ def test_rings_constructor_errors_mirror_the_reference():
     st.types = None
     with pytest.raises(ValueError, match="state.types is nothing"):
         RingsSystem(state=st, space_cfg=case["space"], dynamic_cfg=case["dyn"], int_cfg=case["int_cfg"])
-    # sources / sinks are a "next" row: refused loudly, not ignored
-    with pytest.raises(NotImplementedError):
+    # sources / sinks need the variable-ring-count state (src/rings/states.jl:173-227): refused loudly otherwise
+    with pytest.raises(ValueError, match="active_state"):
         RingsSystem(state=case["mk"](), space_cfg=case["space"], dynamic_cfg=case["dyn"], int_cfg=case["int_cfg"], source_cfg=object())
 
 
