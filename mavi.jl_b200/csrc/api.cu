@@ -267,6 +267,10 @@ static int allocate(Handle *h) {
   if ((st = dev_alloc(h, &a.fix_pos, n))) return st;
   if ((st = dev_alloc(h, &a.reduce_buf, 4096))) return st;
   if ((st = dev_alloc(h, &a.cta_first, n / RPB + 2))) return st;
+  if (p.num_cells > 0) {  // cell-edge tables (filled by alloc_state, once the tile geometry is known)
+    if ((st = dev_alloc(h, &a.edge_x, (size_t)p.num_cols + 2))) return st;
+    if ((st = dev_alloc(h, &a.edge_y, (size_t)((p.num_rows + MAVI_TR - 1) / MAVI_TR) * MAVI_TR))) return st;
+  }
   if (p.slab) {  // emigrant / immigrant records (slab.cu)
     a.em_cap = p.num_rows / 2 > 1024 ? p.num_rows / 2 : 1024;
     for (int d = 0; d < 2; d++) {
@@ -336,6 +340,7 @@ int Handle::alloc_state(int n_active, int cap) {
   }
   ns = (size_t)p.tail_base + (size_t)(p.slab ? 0 : (p.n - p.n_active));
   int st;
+  launch_cell_edges(ctx(), p, A);
   if (reuse) {
     carry_valid = false;
     CUDA_TRY(this, cudaMemsetAsync(A.force_old, 0, ns * sizeof(real2), stream));

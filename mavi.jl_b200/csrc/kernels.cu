@@ -584,6 +584,8 @@ struct MoverSink {
                      // struct into local memory, one copy per thread)
   int em_cap;
   const unsigned int *idflag;
+  // cell-edge tables of the grid (k_cell_edges); read by the pipelined kernels' producer warp
+  const double2 *edge_x, *edge_y;
 };
 
 __device__ __forceinline__ void mark_dirty(const MoverSink &ms, int t) {
@@ -1273,9 +1275,14 @@ struct PChunk {
   int state;        // 1: a staged chunk, 0: no more work for this CTA
   int nc, use_mi, nown, ok, tr, cs;
   int src_t1, lt1;  // !ok: the one column that does not fit the staging area (walked in global memory)
-  int gbase[PG_MAX + 2];
-  int pad_;
-  // edges of the cells as axis_in_cell() compares them (lo <= t < hi): staged column j / cell row lr-1 of the tile
+  int pad_[3];
+  // per staged column j.  Own particle q (0 <= q < nown, counted over the own columns 1 .. nc in order) of column j:
+  //   staged index self = q + col[j].x, global slot k = self + col[j].y, its cell = s_cell[q + col[j].z],
+  //   cell row inside the tile (1-based) lr = cell - col[j].w
+  int4 col[PG_MAX + 2];
+  int oend[32];     // oend[j]: end of the own-particle range of column j (oend[0] = 0; j > nc: INT_MAX)
+  // edges of the cells as axis_in_cell() compares them (lo <= t < hi): staged column j / cell row lr-1 of the tile;
+  // bulk copies of the handle's edge tables (DevArrays.edge_x / edge_y)
   double2 xb[PG_MAX + 2];
   double2 yb[MAVI_TR];
   // ext[j][k]: staged index where cell row k-1 of staged column j starts — k = 0 is the cell row ABOVE the tile, k = 1 ..
@@ -1286,9 +1293,11 @@ struct PChunk {
   __device__ __forceinline__ int2 win(int j, int r) const { return make_int2(ext[j][r], ext[j][r + 3]); }
 };
 constexpr int PCH_BYTES = (sizeof(PChunk) + 15) / 16 * 16;
-constexpr int PBUF_BYTES = PCH_BYTES + PSPOS_CAP * (int)sizeof(real2) + POWN_CAP * (int)sizeof(unsigned int);
-constexpr int PTS_BYTES = 32 * (MAVI_TR + 1) * (int)sizeof(int);  // producer scratch: tstart rows of the staged columns
-constexpr int PIPE_SMEM = 64 + 2 * PBUF_BYTES + 2 * PTS_BYTES;   // [4 mbarriers | buffer 0 | buffer 1 | scratch of producer 0, 1]
+// staged cells of the own particles: every own column's run of cell[] is copied from the 16-byte boundary below its first
+// slot to the one above its last (<= 6 extra entries), to a 16-byte aligned place -> 12 entries of slack per column
+constexpr int PCELL_CAP = (POWN_CAP + 4 + 12 * PG_MAX + 3) / 4 * 4;
+constexpr int PBUF_BYTES = PCH_BYTES + PSPOS_CAP * (int)sizeof(real2) + PCELL_CAP * (int)sizeof(int);
+constexpr int PIPE_SMEM = 64 + 2 * PBUF_BYTES;   // [4 mbarriers | buffer 0 | buffer 1]
 
 __device__ __forceinline__ unsigned int smem_u32(const void *ptr) { return (unsigned int)__cvta_generic_to_shared(ptr); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
@@ -1300,15 +1309,22 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.release.cta.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
-// The waiting warp is SUSPENDED by the hardware (suspend-time hint, woken as soon as the phase completes) instead of
-// spinning: the first version of this kernel spent 29 % of its issued instructions in this loop
-// (profiles/r02_ncu_newton_summary.md), slots taken from the very producer warp the consumers were waiting for.
+// try_wait suspends the warp for a while, but on this part it comes back every few hundred cycles: in the capture of
+// profiles/r02_ncu_newton_summary.md (r2n) the retry loop was 20 % of ALL issued instructions, taken from the warps the
+// waiters wait for.  A failed try is therefore followed by a short sleep (a hand-off costs at most that much; a chunk
+// takes ~15 us).
+#ifndef MAVI_WAIT_SLEEP_NS
+#define MAVI_WAIT_SLEEP_NS 96
+#endif
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned int parity) {
   asm volatile(
       "{\n\t.reg .pred ok;\n"
       "W%=:\n\t"
       "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 ok, [%0], %1, %2;\n\t"
-      "@!ok bra W%=;\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(100000u)
+      "@ok bra D%=;\n\t"
+      "nanosleep.u32 %3;\n\t"
+      "bra W%=;\n"
+      "D%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(100000u), "r"((unsigned int)MAVI_WAIT_SLEEP_NS)
       : "memory");
 }
 // one contiguous run global -> shared, completing `bytes` on the mbarrier (UBLKCP)
@@ -1320,10 +1336,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned in
 
 // PRODUCER WARP: stage the chunk of own columns starting at local column cs (at most `rem` columns) of tile row tr into
 // one buffer and arrive on its `full` barrier.  Returns the number of own columns taken.  Same layout as chunk_stage.
+// Lane j owns staged column j.  The warp is a serial resource (one chunk of the CTA per call), so it does as little as
+// possible: one round trip for the column's tstart row, a warp scan, bulk-async copies for everything that is a contiguous
+// run in global memory (positions, cells, cell edges), and the table of row starts straight from its registers.  The
+// consumers find a particle's column / cell row themselves (PChunk::oend, col, s_cell).
 template <bool PER>
 __device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restrict__ tstart, const real2 *__restrict__ pos,
-                                          int tr, int cs, int rem, bool exact_minimg, PChunk *ck, real2 *s_pos,
-                                          unsigned int *s_list, unsigned long long *full_bar, int *s_ts) {
+                                          const int *__restrict__ cell, const double2 *__restrict__ edge_x,
+                                          const double2 *__restrict__ edge_y, int tr, int cs, int rem, bool exact_minimg,
+                                          PChunk *ck, real2 *s_pos, int *s_cell, unsigned long long *full_bar) {
   const int lane = threadIdx.x & 31;
   const int R = p.num_rows, Cn = p.num_cols;
   const int r0 = tr * MAVI_TR;
@@ -1332,8 +1353,11 @@ __device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restr
   // ---- column descriptors: lane j describes staged column j (0 .. ncand+1); independent loads
   const int j = lane;
   const bool in = j < ncand + 2;
-  int la = 0, lt = 0, lb = 0, sa = 0, st = 0, sb = 0, cj = 0;
+  int la = 0, lt = 0, lb = 0, sa = 0, st = 0, sb = 0;
   bool wrapped = false;
+  int v[MAVI_TR + 1];  // the column's tstart row
+#pragma unroll
+  for (int r = 0; r <= MAVI_TR; r++) v[r] = 0;
   if (in) {
     int c = cs - 1 + j;
     bool exists = true;
@@ -1344,25 +1368,16 @@ __device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restr
     bool has_a = exists, has_b = exists;
     if (ra < 0) { if (p.wrap_rows) { ra = R - 1; wrapped = wrapped || exists; } else has_a = false; }
     if (rb >= R) { if (p.wrap_rows) { rb = 0; wrapped = wrapped || exists; } else has_b = false; }
-    cj = exists ? c : 0;
-    int *row = s_ts + j * (MAVI_TR + 1);
     if (exists) {
       const int *tt = tstart + (size_t)(c * p.tpc + tr) * (MAVI_TR + 1);
       const int qa = has_a ? tq_of(p, c, ra) : 0, qb = has_b ? tq_of(p, c, rb) : 0;
-      // the whole tstart row of the column in ONE round trip (33 independent loads per lane), kept in shared memory
-      // relative to the tile start for the window / list pass below (row stride 33 words: conflict-free across lanes)
-      int v[MAVI_TR + 1];
+      // the whole tstart row of the column in ONE round trip (33 + 4 independent loads per lane)
 #pragma unroll
       for (int r = 0; r <= MAVI_TR; r++) v[r] = __ldg(tt + r);
       const int a0 = has_a ? __ldg(tstart + qa) : 0, a1 = has_a ? __ldg(tstart + qa + 1) : 0;
       const int b0 = has_b ? __ldg(tstart + qb) : 0, b1 = has_b ? __ldg(tstart + qb + 1) : 0;
       st = v[0];
-#pragma unroll
-      for (int r = 0; r <= MAVI_TR; r++) row[r] = v[r] - st;
       lt = v[MAVI_TR] - st; sa = a0; la = a1 - a0; sb = b0; lb = b1 - b0;
-    } else {
-#pragma unroll
-      for (int r = 0; r <= MAVI_TR; r++) row[r] = 0;
     }
   }
   // ---- prefix sums over the lanes, greedy number of own columns that fit
@@ -1371,8 +1386,8 @@ __device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restr
   int incl = sz, oincl = own;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o), u = __shfl_up_sync(0xffffffffu, oincl, o);
-    if (lane >= o) { incl += v; oincl += u; }
+    const int vv = __shfl_up_sync(0xffffffffu, incl, o), u = __shfl_up_sync(0xffffffffu, oincl, o);
+    if (lane >= o) { incl += vv; oincl += u; }
   }
   const int incl_next = __shfl_down_sync(0xffffffffu, incl, 1);  // staged total if this lane were the last own column
   const bool fits = j >= 1 && j <= ncand && incl_next <= PSPOS_CAP && oincl <= POWN_CAP;
@@ -1380,9 +1395,19 @@ __device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restr
   const int nc = bal ? 31 - __clz(bal) : 1;  // fits is monotone in j
   const unsigned int wbal = __ballot_sync(0xffffffffu, in && j <= nc + 1 && wrapped);
   const int off = incl - sz, ownoff = oincl - own;
-  int tile_total = (in && j <= nc + 1) ? lt : 0;   // positions that arrive through bulk copies (the tile runs)
+  const bool staged = j <= nc + 1, is_own = j >= 1 && j <= nc;
+  // cells of the own particles: the run [st, st + lt) of cell[], widened to 16-byte boundaries
+  const int cg0 = st & ~3, cg1 = (st + lt + 3) & ~3;
+  const int coff = ((ownoff + 3) & ~3) + 12 * (j - 1);
+  // bytes that arrive through bulk copies
+  unsigned int tx = 0;
+  if (bal && staged) {
+    if (PIPE_BULK) tx += (unsigned int)lt * (unsigned int)sizeof(real2);
+    if (is_own && lt) tx += (unsigned int)(cg1 - cg0) * 4u;
+    if (lane == 0) tx += (unsigned int)(nc + 2 + MAVI_TR) * (unsigned int)sizeof(double2);
+  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) tile_total += __shfl_xor_sync(0xffffffffu, tile_total, o);
+  for (int o = 16; o > 0; o >>= 1) tx += __shfl_xor_sync(0xffffffffu, tx, o);
   const int nown = __shfl_sync(0xffffffffu, oincl, nc);
   const int st1 = __shfl_sync(0xffffffffu, st, 1), lt1 = __shfl_sync(0xffffffffu, lt, 1);
   if (lane == 0) {
@@ -1395,64 +1420,57 @@ __device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restr
     ck->cs = cs;
     ck->src_t1 = st1;
     ck->lt1 = lt1;
-    if (PIPE_BULK && bal && tile_total) mbar_expect_tx(full_bar, (unsigned int)tile_total * (unsigned int)sizeof(real2));
-  }
-  {  // ---- cell edges for the exact "still in its cell" test of the epilogue (see axis_in_cell / still_in_cell)
-    if (in) {
-      int g = cs - 1 + j;  // staged local column -> global column
-      if (g < 0) g += Cn;
-      else if (g >= Cn) g -= Cn;
-      if (p.slab) {
-        g = g + p.col_lo - 1;
-        if (g < 0) g += p.gcols;
-        else if (g >= p.gcols) g -= p.gcols;
-      }
-      const double lo = g == 0 ? nextafter(-p.cl, 1.0) : __dmul_ru((double)g, p.cl);  // t > -c  <=>  t >= nextafter(-c, +inf)
-      const double hi = __dmul_ru((double)((g == p.gcols - 1) ? p.gcols + 1 : g + 1), p.cl);
-      ck->xb[j] = make_double2(lo, hi);
-    }
-    const int row = r0 + lane;
-    const double lo = row == 0 ? nextafter(-p.ch, 1.0) : __dmul_ru((double)row, p.ch);
-    const double hi = __dmul_ru((double)((row == R - 1) ? R + 1 : row + 1), p.ch);
-    ck->yb[lane] = make_double2(lo, hi);
+    if (tx) mbar_expect_tx(full_bar, tx);
   }
   __syncwarp();
   if (bal) {
-    if (j <= nc + 1) {
-      // ---- positions.  The tile run of the column ([first .. last cell row of the tile], ~40 positions) is ONE bulk-async
-      // copy that completes on the buffer's `full` barrier; the one cell row above and below (a couple of positions each)
-      // are copied by the lane itself — three bulk copies per column cost more issue slots than they save
-      if (PIPE_BULK) {
-        if (lt) bulk_g2s(s_pos + off + la, pos + st, (unsigned int)lt * (unsigned int)sizeof(real2), full_bar);
-        for (int i = 0; i < la; i++) s_pos[off + i] = __ldg(pos + sa + i);
-        for (int i = 0; i < lb; i++) s_pos[off + la + lt + i] = __ldg(pos + sb + i);
-      } else {  // Float32 build: a float2 run is only 8-byte aligned
-        for (int i = 0; i < la; i++) s_pos[off + i] = __ldg(pos + sa + i);
-        for (int i = 0; i < lt; i++) s_pos[off + la + i] = __ldg(pos + st + i);
-        for (int i = 0; i < lb; i++) s_pos[off + la + lt + i] = __ldg(pos + sb + i);
+    const int base = off + la;             // staged index of the first particle of the tile
+    const int end = off + la + lt + lb;    // end of the staged column
+    real2 ea[2], eb[2];                    // the cell row above / below the tile: a couple of positions each
+    if (staged) {
+      // ---- the long-latency part first.  The tile run of the column ([first .. last cell row of the tile], ~40 positions)
+      // is ONE bulk-async copy that completes on the buffer's `full` barrier, and so are its cells; the cell row above and
+      // below are loaded by the lane itself (three bulk copies per column cost more issue slots than they save)
+      if (PIPE_BULK && lt) bulk_g2s(s_pos + base, pos + st, (unsigned int)lt * (unsigned int)sizeof(real2), full_bar);
+      if (is_own && lt) bulk_g2s(s_cell + coff, cell + cg0, (unsigned int)(cg1 - cg0) * 4u, full_bar);
+      if (lane == 0) {
+        bulk_g2s(ck->xb, edge_x + cs, (unsigned int)(nc + 2) * (unsigned int)sizeof(double2), full_bar);  // entry = column + 1
+        bulk_g2s(ck->yb, edge_y + r0, (unsigned int)MAVI_TR * (unsigned int)sizeof(double2), full_bar);
       }
-      // ---- cell-row windows and the own-particle list of the column, from its tstart row in shared memory
-      const int *row = s_ts + j * (MAVI_TR + 1);
-      const int base = off + la;             // staged index of the first particle of the tile
-      const int end = off + la + lt + lb;    // end of the staged column
-      ck->gbase[j] = st - base;
-      const bool own = j >= 1 && j <= nc;
-      unsigned int *lst = s_list + ownoff;
-      int *ext = ck->ext[j];
-      ext[0] = off;
-#pragma unroll 8
-      for (int r = 0; r <= MAVI_TR + 1; r++) {
-        // start of cell row r: the tile's rows, then the row below (staged right after the tile), then the end of the column
-        const int rr = r <= MAVI_TR ? row[r] : lt;
-        ext[1 + r] = r > rows ? end : base + rr;
-        if (own && r < MAVI_TR) {  // own-particle list: the particles of cell row r (rows beyond the grid are empty)
-          const unsigned int tag = ((unsigned int)j << 16) | ((unsigned int)(r + 1) << 24);
-          for (int i = rr; i < row[r + 1]; i++) lst[i] = (unsigned int)(base + i) | tag;
-        }
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        if (i < la) ea[i] = __ldg(pos + sa + i);
+        if (i < lb) eb[i] = __ldg(pos + sb + i);
       }
     }
+    // ---- per-column words and the row-start table, straight from the registers
+    ck->oend[j] = (j == 0) ? 0 : (is_own ? oincl : 0x7fffffff);
+    if (staged) {
+      ck->col[j] = make_int4(base - ownoff, st - base, coff + (st - cg0) - ownoff, (cs - 1 + j) * R + r0 - 1);
+      int *ext = ck->ext[j];
+      const int shift = base - st;  // global slot -> staged index (tile rows)
+      ext[0] = off;
+      if (rows == MAVI_TR) {
+#pragma unroll
+        for (int r = 0; r <= MAVI_TR; r++) ext[1 + r] = v[r] + shift;
+      } else {  // last tile row of the grid: rows beyond it are empty and the cell row "below" is the wrapped one
+#pragma unroll
+        for (int r = 0; r <= MAVI_TR; r++) ext[1 + r] = r > rows ? end : v[r] + shift;
+      }
+      ext[MAVI_TR + 2] = end;
+      // ---- positions the lane copies itself
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        if (i < la) s_pos[off + i] = ea[i];
+        if (i < lb) s_pos[base + lt + i] = eb[i];
+      }
+      for (int i = 2; i < la; i++) s_pos[off + i] = __ldg(pos + sa + i);
+      for (int i = 2; i < lb; i++) s_pos[base + lt + i] = __ldg(pos + sb + i);
+      if (!PIPE_BULK)  // Float32 build: a float2 run is only 8-byte aligned
+        for (int i = 0; i < lt; i++) s_pos[base + i] = __ldg(pos + st + i);
+    }
   }
-  __syncwarp();  // every lane's descriptor / list / position stores are ordered before the arrival below
+  __syncwarp();  // every lane's descriptor / table / position stores are ordered before the arrival below
   if (lane == 0) mbar_arrive(full_bar);
   return nc;
 }
@@ -1462,6 +1480,7 @@ __device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restr
 template <int DYN, bool PER, int PIPE_CW, int NPROD, typename Pre, typename Body>
 __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const int *__restrict__ tstart,
                                                        const real2 *__restrict__ pos, const int *__restrict__ cell,
+                                                       const double2 *__restrict__ edge_x, const double2 *__restrict__ edge_y,
                                                        bool exact_minimg, int *__restrict__ work, Pre &&pre, Body &&body) {
   constexpr int PIPE_CT = PIPE_CW * 32;  // consumer threads; the producers are the LAST warp(s) of the CTA
   extern __shared__ __align__(16) unsigned char dsm[];
@@ -1481,11 +1500,9 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
   __syncthreads();  // the only CTA barrier of the kernel
   if (w >= PIPE_CW) {
     // ================================ producer warp(s) ================================
-    // One warp executes the staging code at ~12 cycles per instruction (short dependent chains), which is as long as the
-    // eight consumer warps need for a chunk (profiles/r02_ncu_newton_summary.md): with NPROD = 2 each producer owns ONE of
-    // the two buffers and the consumers alternate between them, so two chunks are staged concurrently.
+    // With NPROD = 2 each producer owns ONE of the two buffers and the consumers alternate between them, so two chunks are
+    // staged concurrently (A/B switch MAVI_PIPE_CFG; one producer is enough since the staging became cheap).
     const int pw = w - PIPE_CW;
-    int *s_ts = reinterpret_cast<int *>(dsm + 64 + 2 * (size_t)PBUF_BYTES + (size_t)pw * PTS_BYTES);
     int k = 0;  // chunks staged by this producer
     for (;;) {
       int item = 0;
@@ -1503,9 +1520,9 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
         const int u = NPROD == 2 ? k : (k >> 1);  // how often this buffer has been filled before
         if (u >= 1) mbar_wait(&bars[2 + b], (unsigned int)((u - 1) & 1));  // the consumers released its previous contents
         unsigned char *buf = dsm + 64 + (size_t)b * PBUF_BYTES;
-        cs += pipe_stage<PER>(p, tstart, pos, tr, cs, c_end - cs, exact_minimg, reinterpret_cast<PChunk *>(buf),
-                              reinterpret_cast<real2 *>(buf + PCH_BYTES),
-                              reinterpret_cast<unsigned int *>(buf + PCH_BYTES + PSPOS_CAP * sizeof(real2)), &bars[b], s_ts);
+        cs += pipe_stage<PER>(p, tstart, pos, cell, edge_x, edge_y, tr, cs, c_end - cs, exact_minimg,
+                              reinterpret_cast<PChunk *>(buf), reinterpret_cast<real2 *>(buf + PCH_BYTES),
+                              reinterpret_cast<int *>(buf + PCH_BYTES + PSPOS_CAP * sizeof(real2)), &bars[b]);
       }
     }
     // end marker(s): one per buffer this producer feeds
@@ -1537,27 +1554,35 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
     unsigned char *buf = dsm + 64 + (size_t)b * PBUF_BYTES;
     const PChunk *ck = reinterpret_cast<const PChunk *>(buf);
     const real2 *s_pos = reinterpret_cast<const real2 *>(buf + PCH_BYTES);
-    const unsigned int *s_list = reinterpret_cast<const unsigned int *>(buf + PCH_BYTES + PSPOS_CAP * sizeof(real2));
+    const int *s_cell = reinterpret_cast<const int *>(buf + PCH_BYTES + PSPOS_CAP * sizeof(real2));
     mbar_wait(&bars[b], (unsigned int)((uses >> (16 * b)) & 1));
     if (!ck->state) {
       done |= 1 << b;
       continue;
     }
-    const int cs = ck->cs, r0 = ck->tr * MAVI_TR;
     if (ck->ok) {
       const int nown = ck->nown;
       const bool mi = PER && ck->use_mi;
-      for (int q = threadIdx.x; q < nown; q += PIPE_CT) {
-        const unsigned int u = s_list[q];
-        const int self = u & 0xffffu, jj = (u >> 16) & 0xffu, lr = u >> 24;
-        const int k = self + ck->gbase[jj];
-        auto pv = pre(k);
-        const real2 r = s_pos[self];
-        real fx = 0.0, fy = 0.0;
-        if (mi) chunk_walk<DYN, true>(p, ck, s_pos, jj, lr, self, r, fx, fy);
-        else chunk_walk<DYN, false>(p, ck, s_pos, jj, lr, self, r, fx, fy);
-        const double2 xe = ck->xb[jj], ye = ck->yb[lr - 1];
-        body(k, r, (cs - 1 + jj) * p.num_rows + r0 + lr - 1, true, make_real2(fx, fy), InCellTab{p, xe.x, xe.y, ye.x, ye.y}, pv);
+      const int oe = ck->oend[lane];
+      for (int q0 = w * 32; q0 < nown; q0 += PIPE_CT) {
+        // column of the warp's first particle (oend is non-decreasing), then a lane-local walk: 32 consecutive own
+        // particles rarely span more than two columns
+        int jj = __popc(__ballot_sync(0xffffffffu, oe <= q0));
+        const int q = q0 + lane;
+        if (q < nown) {
+          while (q >= ck->oend[jj]) jj++;
+          const int4 cd = ck->col[jj];
+          const int self = q + cd.x, k = self + cd.y;
+          auto pv = pre(k);
+          const int cc = s_cell[q + cd.z];
+          const int lr = cc - cd.w;
+          const real2 r = s_pos[self];
+          real fx = 0.0, fy = 0.0;
+          if (mi) chunk_walk<DYN, true>(p, ck, s_pos, jj, lr, self, r, fx, fy);
+          else chunk_walk<DYN, false>(p, ck, s_pos, jj, lr, self, r, fx, fy);
+          const double2 xe = ck->xb[jj], ye = ck->yb[lr - 1];
+          body(k, r, cc, true, make_real2(fx, fy), InCellTab{p, xe.x, xe.y, ye.x, ye.y}, pv);
+        }
       }
     } else {
       // a single column too dense for the staging area: per-thread walk over the global arrays
@@ -1599,6 +1624,14 @@ static inline int pipe_cfg() {
     return (v == 81 || v == 72 || v == 82) ? v : 71;
   }();
   return cfg;
+}
+
+// Float32 build: without bulk copies (8-byte aligned runs) the producer warp moves every position through its registers and
+// the pipelined kernels LOSE to the cp.async kernels (LJ 16 M, gpurun_out r2n: 0.684 vs 0.501 ms/step), so the Float32 build
+// keeps the latter; MAVI_F32_PIPELINED=1 is the A/B switch.
+static inline bool pipe_default() {
+  static const bool v = PIPE_BULK || getenv("MAVI_F32_PIPELINED") != nullptr;
+  return v;
 }
 
 // Persistent grids.  In the two-stream slab step the boundary-block launch (blk_mode 2, side stream) has to run WHILE the
@@ -1706,7 +1739,7 @@ __global__ void __launch_bounds__((CW + NP) * 32, PIPE_CTAS_PER_SM) k_newton_p(
     int *__restrict__ fix_idx, real2 *__restrict__ fix_pos, const __grid_constant__ MoverSink ms) {
   if (!ms.flags[FLAG_RAN]) return;
   const bool exact = ms.flags[FLAG_BIGMOVE] != 0 || (p.slab && p.blk_mode == 2);
-  pipe_for_each_particle<DYN, PER, CW, NP>(p, tstart, pos_in, ms.cell, exact, ms.flags + (p.blk_mode == 2 ? FLAG_WORK1 : FLAG_WORK0),
+  pipe_for_each_particle<DYN, PER, CW, NP>(p, tstart, pos_in, ms.cell, ms.edge_x, ms.edge_y, exact, ms.flags + (p.blk_mode == 2 ? FLAG_WORK1 : FLAG_WORK0),
                                        MAVI_NEWTON_B_LAMBDAS);
 }
 
@@ -1716,7 +1749,7 @@ __global__ void __launch_bounds__((CW + NP) * 32, PIPE_CTAS_PER_SM) k_self_prope
     const real2 *__restrict__ pos_in, real *__restrict__ ang, real2 *__restrict__ pos_out, real2 *__restrict__ force,
     const real *__restrict__ noise, unsigned long long step, const __grid_constant__ MoverSink ms) {
   if (!ms.flags[FLAG_RAN]) return;
-  pipe_for_each_particle<DYN, PER, CW, NP>(p, tstart, pos_in, ms.cell, false, ms.flags + FLAG_WORK0,
+  pipe_for_each_particle<DYN, PER, CW, NP>(p, tstart, pos_in, ms.cell, ms.edge_x, ms.edge_y, false, ms.flags + FLAG_WORK0,
     [&](int k) { prefetch_l1(ang + k); prefetch_l1(idflag + k); return 0; },
     [&](int k, real2 r, int c, bool active, real2 F, auto in_cell, auto) {
       const unsigned int id = idflag[k] & ~MAVI_INACTIVE_BIT;
@@ -1761,8 +1794,41 @@ __global__ void __launch_bounds__(TPB) k_self_propelled2(const __grid_constant__
     if (PERV) { CALL(DYNV, true); } else { CALL(DYNV, false); } \
   } while (0)
 
+// Edges of the cells exactly as axis_in_cell() / still_in_cell() compare them (lo <= t < hi with t = x - grid_bl[0] or
+// -y + grid_bl[1] + grid_h): edge_x[lc + 1] for the LOCAL column lc = -1 .. num_cols (the two extra entries are the columns
+// reached through the periodic wrap), edge_y[row] for row = 0 .. tpc * MAVI_TR - 1.  Depends on the grid only.
+__global__ void k_cell_edges(const __grid_constant__ DevParams p, double2 *__restrict__ edge_x, double2 *__restrict__ edge_y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Cn = p.num_cols, R = p.num_rows;
+  if (i < Cn + 2) {
+    int g = i - 1;  // local column -> global column
+    if (g < 0) g += Cn;
+    else if (g >= Cn) g -= Cn;
+    if (p.slab) {
+      g = g + p.col_lo - 1;
+      if (g < 0) g += p.gcols;
+      else if (g >= p.gcols) g -= p.gcols;
+    }
+    const double lo = g == 0 ? nextafter(-p.cl, 1.0) : __dmul_ru((double)g, p.cl);  // t > -c  <=>  t >= nextafter(-c, +inf)
+    const double hi = __dmul_ru((double)((g == p.gcols - 1) ? p.gcols + 1 : g + 1), p.cl);
+    edge_x[i] = make_double2(lo, hi);
+  }
+  if (i < p.tpc * MAVI_TR) {
+    const int row = i;
+    const double lo = row == 0 ? nextafter(-p.ch, 1.0) : __dmul_ru((double)row, p.ch);
+    const double hi = __dmul_ru((double)((row == R - 1) ? R + 1 : row + 1), p.ch);
+    edge_y[i] = make_double2(lo, hi);
+  }
+}
+
+void launch_cell_edges(const LaunchCtx &c, const DevParams &p, const DevArrays &a) {
+  if (p.num_cells == 0 || !a.edge_x) return;
+  const int n = max(p.num_cols + 2, p.tpc * MAVI_TR);
+  MAVI_LAUNCH(c, k_cell_edges, nblk(n), TPB, 0, p, a.edge_x, a.edge_y);
+}
+
 static MoverSink mover_sink(const DevArrays &a) {
-  return MoverSink{a.cell, a.tile_dirty, a.dirty_list, a.inbox_cnt, a.inbox, a.mv_src, a.flags, nullptr, a.em_send[0], a.em_send[1], a.em_cap, a.idflag};
+  return MoverSink{a.cell, a.tile_dirty, a.dirty_list, a.inbox_cnt, a.inbox, a.mv_src, a.flags, nullptr, a.em_send[0], a.em_send[1], a.em_cap, a.idflag, a.edge_x, a.edge_y};
 }
 
 void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool with_wall_forces) {
@@ -1843,7 +1909,7 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p_in, const DevArrays 
     // r02_slab_timeline.md: 0.70 ms/step with the non-persistent kernels, 0.86 with persistent ones + 16 reserved slots).
     // MAVI_SLAB_PIPELINED=1 is the A/B switch.
     static const bool slab_pipelined = getenv("MAVI_SLAB_PIPELINED") != nullptr;
-    if (!(c.flags & MAVI_FLAG_LEGACY_STAGING) && (blk_mode == 0 || slab_pipelined)) {
+    if (pipe_default() && !(c.flags & MAVI_FLAG_LEGACY_STAGING) && (blk_mode == 0 || slab_pipelined)) {
       if (carry) {
         ms.chg = a.chg;
         if (p.dynamics == MAVI_DYN_LJ) MAVI_DISPATCH2(MAVI_DYN_LJ, p.periodic, CALLPC);
@@ -1930,7 +1996,7 @@ void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArra
       default: CALLP_(D, P, 7, 1); break;            \
     }                                                \
   } while (0)
-    if (!(c.flags & MAVI_FLAG_LEGACY_STAGING)) {
+    if (pipe_default() && !(c.flags & MAVI_FLAG_LEGACY_STAGING)) {
       if (p.dynamics == MAVI_DYN_SZABO) MAVI_DISPATCH2(MAVI_DYN_SZABO, p.periodic, CALLP);
       else MAVI_DISPATCH2(MAVI_DYN_RTP, p.periodic, CALLP);
     } else {

@@ -54,6 +54,7 @@ struct DevArrays {
   int *fix_idx;         // sparse list of slots whose position walls! changed in pass B
   real2 *fix_pos;
   double *reduce_buf;
+  double2 *edge_x, *edge_y;  // cell edges of the grid (k_cell_edges): [num_cols + 2], [tpc * MAVI_TR]
 };
 
 struct LaunchCtx {
@@ -84,6 +85,7 @@ void ensure_rank_maps(const LaunchCtx &c, const DevParams &p, const DevArrays &a
 
 // force + integrate passes
 void launch_step_begin(const LaunchCtx &c, const DevArrays &a);
+void launch_cell_edges(const LaunchCtx &c, const DevParams &p, const DevArrays &a);  // after the grid / slab geometry is final
 void launch_force_only(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool with_wall_forces);
 void launch_newton_a(const LaunchCtx &c, const DevParams &p, const DevArrays &a);
 // blk_mode: 0 = every block, then the wall position fix-ups; 1 = blocks that read no halo column; 2 = the first / last
