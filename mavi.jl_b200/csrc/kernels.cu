@@ -962,8 +962,7 @@ __global__ void k_apply_pos_fixes(int *__restrict__ flags, const int *__restrict
 template <int DYN>
 __device__ __forceinline__ void self_propelled_update(const DevParams &p, real2 &r, const real2 F,
                                                       real *__restrict__ ang, int k, unsigned int id,
-                                                      const real *__restrict__ noise, unsigned long long step) {
-  real theta = ang[k];
+                                                      const real *__restrict__ noise, unsigned long long step, real theta) {
   real sn, cs;
   sincos(theta, &sn, &cs);
   if (DYN == MAVI_DYN_SZABO) {
@@ -1015,7 +1014,7 @@ __global__ void __launch_bounds__(TPB) k_self_propelled(const __grid_constant__ 
       if (p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
     }
     force[k] = F;
-    if ((int)id < p.n_count) self_propelled_update<DYN>(p, r, F, ang, k, id, noise, step);
+    if ((int)id < p.n_count) self_propelled_update<DYN>(p, r, F, ang, k, id, noise, step, ang[k]);
     if (active) {
       real vx = 0.0, vy = 0.0;
       apply_walls<false>(p, r.x, r.y, vx, vy, p.particle_radius);
@@ -1275,7 +1274,8 @@ struct PChunk {
   int state;        // 1: a staged chunk, 0: no more work for this CTA
   int nc, use_mi, nown, ok, tr, cs;
   int src_t1, lt1;  // !ok: the one column that does not fit the staging area (walked in global memory)
-  int pad_[3];
+  int next;         // consumers: first own particle of the next round of 32 (atomicAdd; reset by the producer)
+  int pad_[2];
   // per staged column j.  Own particle q (0 <= q < nown, counted over the own columns 1 .. nc in order) of column j:
   //   staged index self = q + col[j].x, global slot k = self + col[j].y, its cell = s_cell[q + col[j].z],
   //   cell row inside the tile (1-based) lr = cell - col[j].w
@@ -1420,6 +1420,7 @@ __device__ __forceinline__ int pipe_stage(const DevParams &p, const int *__restr
     ck->cs = cs;
     ck->src_t1 = st1;
     ck->lt1 = lt1;
+    ck->next = 0;
     if (tx) mbar_expect_tx(full_bar, tx);
   }
   __syncwarp();
@@ -1552,7 +1553,7 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
   for (int b = 0; done != 3; b ^= 1) {
     if (done & (1 << b)) continue;
     unsigned char *buf = dsm + 64 + (size_t)b * PBUF_BYTES;
-    const PChunk *ck = reinterpret_cast<const PChunk *>(buf);
+    PChunk *ck = reinterpret_cast<PChunk *>(buf);
     const real2 *s_pos = reinterpret_cast<const real2 *>(buf + PCH_BYTES);
     const int *s_cell = reinterpret_cast<const int *>(buf + PCH_BYTES + PSPOS_CAP * sizeof(real2));
     mbar_wait(&bars[b], (unsigned int)((uses >> (16 * b)) & 1));
@@ -1564,7 +1565,14 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
       const int nown = ck->nown;
       const bool mi = PER && ck->use_mi;
       const int oe = ck->oend[lane];
-      for (int q0 = w * 32; q0 < nown; q0 += PIPE_CT) {
+      // Rounds of 32 consecutive own particles are handed out dynamically: with a fixed round-robin the same warps get the
+      // extra round of every chunk, and with only two buffers the others cannot run ahead — in the capture r2p of
+      // profiles/r02_ncu_newton_summary.md the consumers slept ~40 % of the time on `full` although the producer was idle
+      for (;;) {
+        int q0 = 0;
+        if (lane == 0) q0 = atomicAdd(&ck->next, 32);
+        q0 = __shfl_sync(0xffffffffu, q0, 0);
+        if (q0 >= nown) break;
         // column of the warp's first particle (oend is non-decreasing), then a lane-local walk: 32 consecutive own
         // particles rarely span more than two columns
         int jj = __popc(__ballot_sync(0xffffffffu, oe <= q0));
@@ -1680,19 +1688,24 @@ __global__ void __launch_bounds__(TPB) k_newton_a2(const __grid_constant__ DevPa
 }
 
 // pre(k) / body(k, r, cell, active, F) of the second Newton pass
-// MAVI_EARLY_LOAD (build-time A/B): vel / F1 are loaded into registers before the pair loop instead of being prefetched to L1
+// vel / F1 are loaded into registers before the pair loop.  A prefetch to L1 (MAVI_LATE_LOAD, build-time A/B) leaves the loads
+// after the loop exposed: 16 % of the stall samples of capture r2q in profiles/r02_ncu_newton_summary.md, 0.544 -> 0.518 ms/step
 struct VelF1 { real2 v, f; };
-#ifdef MAVI_EARLY_LOAD
-#define MAVI_NB_PRE [&](int k) { return VelF1{vel[k], f1[k]}; }
-#define MAVI_NB_GET real2 v = pv.v; const real2 Fo = pv.f;
+#define MAVI_NB_PRE_EARLY [&](int k) { return VelF1{vel[k], f1[k]}; }
+#define MAVI_NB_GET_EARLY real2 v = pv.v; const real2 Fo = pv.f;
+#define MAVI_NB_PRE_LATE [&](int k) { prefetch_l1(vel + k); prefetch_l1(f1 + k); return 0; }
+#define MAVI_NB_GET_LATE real2 v = vel[k]; const real2 Fo = f1[k];
+// the cp.async kernels (64 registers, 4 CTAs per SM) keep the prefetch: no room for eight more live registers
+#define MAVI_NEWTON_B_LAMBDAS_LEGACY MAVI_NEWTON_B_LAMBDAS_(MAVI_NB_PRE_LATE, MAVI_NB_GET_LATE)
+#ifndef MAVI_LATE_LOAD
+#define MAVI_NEWTON_B_LAMBDAS MAVI_NEWTON_B_LAMBDAS_(MAVI_NB_PRE_EARLY, MAVI_NB_GET_EARLY)
 #else
-#define MAVI_NB_PRE [&](int k) { prefetch_l1(vel + k); prefetch_l1(f1 + k); return 0; }
-#define MAVI_NB_GET real2 v = vel[k]; const real2 Fo = f1[k];
+#define MAVI_NEWTON_B_LAMBDAS MAVI_NEWTON_B_LAMBDAS_(MAVI_NB_PRE_LATE, MAVI_NB_GET_LATE)
 #endif
-#define MAVI_NEWTON_B_LAMBDAS \
-    MAVI_NB_PRE, \
+#define MAVI_NEWTON_B_LAMBDAS_(PRE_, GET_) \
+    PRE_, \
     [&](int k, real2 r, int c, bool active, real2 F, auto in_cell, auto pv) { \
-      MAVI_NB_GET \
+      GET_ \
       v.x = v.x + p.hdt * (F.x + Fo.x); \
       v.y = v.y + p.hdt * (F.y + Fo.y); \
       if (active) { \
@@ -1728,7 +1741,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_newton_b2(const __grid_constant__
   // slab mode, blocks next to a halo column (blk_mode 2): their boundary particles are re-drifted on the side stream
   // without a big-drift report -> always the exact minimum-image path there
   const bool exact = ms.flags[FLAG_BIGMOVE] != 0 || (p.slab && p.blk_mode == 2);
-  for_each_block_particle<DYN, PER>(p, tstart, pos_in, ms.cell, exact, MAVI_NEWTON_B_LAMBDAS);
+  for_each_block_particle<DYN, PER>(p, tstart, pos_in, ms.cell, exact, MAVI_NEWTON_B_LAMBDAS_LEGACY);
 }
 
 // the pipelined version of k_newton_b2 (default); work item counter: FLAG_WORK0 / FLAG_WORK1 (boundary-block launch)
@@ -1743,6 +1756,7 @@ __global__ void __launch_bounds__((CW + NP) * 32, PIPE_CTAS_PER_SM) k_newton_p(
                                        MAVI_NEWTON_B_LAMBDAS);
 }
 
+struct AngId { real theta; unsigned int idf; };
 template <int DYN, bool PER, int CW, int NP>
 __global__ void __launch_bounds__((CW + NP) * 32, PIPE_CTAS_PER_SM) k_self_propelled_p(
     const __grid_constant__ DevParams p, const int *__restrict__ tstart, const unsigned int *__restrict__ idflag,
@@ -1750,12 +1764,13 @@ __global__ void __launch_bounds__((CW + NP) * 32, PIPE_CTAS_PER_SM) k_self_prope
     const real *__restrict__ noise, unsigned long long step, const __grid_constant__ MoverSink ms) {
   if (!ms.flags[FLAG_RAN]) return;
   pipe_for_each_particle<DYN, PER, CW, NP>(p, tstart, pos_in, ms.cell, ms.edge_x, ms.edge_y, false, ms.flags + FLAG_WORK0,
-    [&](int k) { prefetch_l1(ang + k); prefetch_l1(idflag + k); return 0; },
-    [&](int k, real2 r, int c, bool active, real2 F, auto in_cell, auto) {
-      const unsigned int id = idflag[k] & ~MAVI_INACTIVE_BIT;
+    // angle and id are loaded BEFORE the pair loop (3 registers): a prefetch to L1 left the loads exposed after it
+    [&](int k) { return AngId{ang[k], idflag[k]}; },
+    [&](int k, real2 r, int c, bool active, real2 F, auto in_cell, auto pv) {
+      const unsigned int id = pv.idf & ~MAVI_INACTIVE_BIT;
       if (active && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
       force[k] = F;
-      if ((int)id < p.n_count) self_propelled_update<DYN>(p, r, F, ang, k, id, noise, step);
+      if ((int)id < p.n_count) self_propelled_update<DYN>(p, r, F, ang, k, id, noise, step, pv.theta);
       if (active) {
         real vx = 0.0, vy = 0.0;
         apply_walls<false>(p, r.x, r.y, vx, vy, p.particle_radius);
@@ -1778,7 +1793,7 @@ __global__ void __launch_bounds__(TPB) k_self_propelled2(const __grid_constant__
       const unsigned int id = idflag[k] & ~MAVI_INACTIVE_BIT;
       if (active && p.has_force_walls) wall_forces(p, r.x, r.y, F.x, F.y);
       force[k] = F;
-      if ((int)id < p.n_count) self_propelled_update<DYN>(p, r, F, ang, k, id, noise, step);
+      if ((int)id < p.n_count) self_propelled_update<DYN>(p, r, F, ang, k, id, noise, step, ang[k]);
       if (active) {
         real vx = 0.0, vy = 0.0;
         apply_walls<false>(p, r.x, r.y, vx, vy, p.particle_radius);
