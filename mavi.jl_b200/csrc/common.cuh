@@ -53,6 +53,7 @@ struct DevParams {
   int mv_cap;     // capacity of the per-step inter-tile mover list
   int chg_cap;    // capacity of the per-step changed-cell list (force carry)
   int blk_cols, blk_per_row;  // tile-block force kernels: own tiles (columns) per CTA, CTAs per tile row
+  int pipe_items; // pipelined kernels: tile blocks a CTA takes before it exits (0: persistent, until the work counter runs out)
   int blk_mode;   // 0: all blocks; 1: all but the first and the last blk_last blocks of every tile row; 2: only those
   int blk_last;   // trailing blocks of a tile row that belong to the boundary group (2 when the last one is < 3 columns)
   // x-slab domain decomposition (one process per GPU): the local grid is [left halo | owned columns | right halo];

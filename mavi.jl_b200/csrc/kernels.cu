@@ -1505,7 +1505,7 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
     // staged concurrently (A/B switch MAVI_PIPE_CFG; one producer is enough since the staging became cheap).
     const int pw = w - PIPE_CW;
     int k = 0;  // chunks staged by this producer
-    for (;;) {
+    for (int taken = 0; p.pipe_items == 0 || taken < p.pipe_items; taken++) {
       int item = 0;
       if (lane == 0) item = atomicAdd(work, 1);
       item = __shfl_sync(0xffffffffu, item, 0);
@@ -1642,16 +1642,34 @@ static inline bool pipe_default() {
   return v;
 }
 
-// Persistent grids.  In the two-stream slab step the boundary-block launch (blk_mode 2, side stream) has to run WHILE the
-// interior launch (blk_mode 1) occupies the device: the interior launch leaves PIPE_BND_CTAS CTA slots free and the boundary
-// launch is exactly that large (its ~2 blocks per tile row are 1-2 % of the work).
-constexpr int PIPE_BND_CTAS = 16;
-static inline int grid_pipe(const DevParams &p) {
+// Grids of the pipelined kernels.  Single launches (blk_mode 0) are PERSISTENT: 3 CTAs per SM until the work counter runs out.
+// The two-stream slab step needs room on the device WHILE its interior launch runs — for the boundary launch and above all
+// for NCCL's send/recv kernel (96 registers x ~544 threads: it only fits an SM that holds none of these CTAs) — so there a
+// CTA exits after `pipe_items` tile blocks (MAVI_SLAB_PIPE_ITEMS, default 8, ~100 us; measured at 2 GPUs: 5 -> 0.615, 8 -> 0.601,
+// 12 -> 0.622, 16 -> 0.637 ms/step, cp.async kernels 0.696): the block scheduler drains an SM for
+// the high-priority side stream within one CTA lifetime.  With persistent CTAs the NCCL kernel of the migration exchange
+// started only when the interior launch had finished (2 GPUs: 0.86 ms/step, profiles/r02_slab_timeline.md).
+static inline int slab_pipe_items() {
+  static const int v = [] {
+    const char *e = getenv("MAVI_SLAB_PIPE_ITEMS");
+    const int k = e ? atoi(e) : 8;
+    return k < 0 ? 0 : k;
+  }();
+  return v;
+}
+static inline int grid_pipe(DevParams &p) {
   const int per_row = p.blk_mode == 0 ? p.blk_per_row : (p.blk_mode == 1 ? p.blk_per_row - 1 - p.blk_last : 1 + p.blk_last);
   const int items = per_row * p.tpc;
-  int want = 148 * PIPE_CTAS_PER_SM;
-  if (p.blk_mode == 1) want -= PIPE_BND_CTAS;
-  else if (p.blk_mode == 2) want = PIPE_BND_CTAS;
+  static const int items_all = getenv("MAVI_PIPE_ITEMS_ALL") ? atoi(getenv("MAVI_PIPE_ITEMS_ALL")) : 0;  // diagnosis: bounded CTAs everywhere
+  p.pipe_items = p.blk_mode == 0 ? items_all : slab_pipe_items();
+  const int want = 148 * PIPE_CTAS_PER_SM;
+  if (p.pipe_items > 0) {
+    // one device-full of CTAs more than items / pipe_items: the last wave is then as wide as the others and the work counter
+    // balances it (with exactly items / pipe_items CTAs the last, partial wave ran at a fraction of the device for a whole
+    // CTA lifetime: 16 items per CTA were SLOWER than 8); CTAs that find the counter exhausted exit at once
+    const int g = (items + p.pipe_items - 1) / p.pipe_items + want;
+    return items > 0 ? (g < items ? g : items) : 1;
+  }
   return items < want ? (items > 0 ? items : 1) : want;
 }
 
@@ -1905,7 +1923,8 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p_in, const DevArrays 
 #define CALLP__(D, P, CARRYV, CWV, NPV)                                                                             \
   do {                                                                                                              \
     MAVI_OPT_IN_SMEM((k_newton_p<D, P, CARRYV, CWV, NPV>), PIPE_SMEM);                                              \
-    MAVI_LAUNCH(c, (k_newton_p<D, P, CARRYV, CWV, NPV>), grid_pipe(p), (CWV + NPV) * 32, PIPE_SMEM, ARGS2);         \
+    const int grid_ = grid_pipe(p);                                                                                 \
+    MAVI_LAUNCH(c, (k_newton_p<D, P, CARRYV, CWV, NPV>), grid_, (CWV + NPV) * 32, PIPE_SMEM, ARGS2);                \
   } while (0)
 #define CALLP_(D, P, CARRYV)                               \
   do {                                                     \
@@ -1921,9 +1940,10 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p_in, const DevArrays 
     // The two-stream slab step splits the pass into an interior and a boundary launch that must overlap: the boundary blocks
     // (side stream, high priority) slip into the slots the short-lived CTAs of the non-persistent kernels free all the time,
     // but cannot get onto a device that persistent CTAs occupy for the whole pass (measured at 2 GPUs, profiles/
-    // r02_slab_timeline.md: 0.70 ms/step with the non-persistent kernels, 0.86 with persistent ones + 16 reserved slots).
-    // MAVI_SLAB_PIPELINED=1 is the A/B switch.
-    static const bool slab_pipelined = getenv("MAVI_SLAB_PIPELINED") != nullptr;
+    // r02_slab_timeline.md: 0.70 ms/step with the non-persistent kernels, 0.86 with persistent ones + 16 reserved slots):
+    // the split launches use the pipelined kernels with CTAs of bounded lifetime (grid_pipe).  MAVI_SLAB_LEGACY=1 is the
+    // A/B switch back to the cp.async kernels.
+    static const bool slab_pipelined = getenv("MAVI_SLAB_LEGACY") == nullptr;
     if (pipe_default() && !(c.flags & MAVI_FLAG_LEGACY_STAGING) && (blk_mode == 0 || slab_pipelined)) {
       if (carry) {
         ms.chg = a.chg;
@@ -1995,12 +2015,14 @@ void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArra
                            unsigned long long step) {
   const bool allp = p.num_cells == 0;
   const MoverSink ms = mover_sink(a);
+  DevParams pp = p;  // grid_pipe() sets pipe_items
   if (!allp) {
 #define CALL2(D, P) MAVI_LAUNCH(c, (k_self_propelled2<D, P>), grid2(p), TPB, PASS2_SMEM, p, a.tstart, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms)
 #define CALLP_(D, P, CWV, NPV)                                                                                      \
   do {                                                                                                              \
     MAVI_OPT_IN_SMEM((k_self_propelled_p<D, P, CWV, NPV>), PIPE_SMEM);                                              \
-    MAVI_LAUNCH(c, (k_self_propelled_p<D, P, CWV, NPV>), grid_pipe(p), (CWV + NPV) * 32, PIPE_SMEM, p, a.tstart, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms); \
+    const int grid_ = grid_pipe(pp);                                                                                \
+    MAVI_LAUNCH(c, (k_self_propelled_p<D, P, CWV, NPV>), grid_, (CWV + NPV) * 32, PIPE_SMEM, pp, a.tstart, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms); \
   } while (0)
 #define CALLP(D, P)                                  \
   do {                                               \

@@ -357,11 +357,12 @@ int slab_sync_counts(Handle *h) {
   if (st) return st;
   // Proactive tile growth.  A tile overflow in the middle of an un-synchronised run of slab steps cannot be rolled back (the
   // other ranks have moved on), so it must not happen: at every synchronisation point (all ranks are at the same step here)
-  // the fullest tile seen so far is compared with the capacity and, if ANY rank is above 70 %, every rank rebuilds its
+  // the fullest tile seen so far is compared with the capacity and, if ANY rank is above 85 %, every rank rebuilds its
   // layout with larger tiles — the slab-mode counterpart of the single-GPU overflow -> rebuild -> resume path.
   if (!h->flags_host[FLAG_OVERFLOW]) {
     int need = 0;
-    if (h->flags_host[FLAG_MAXCOUNT] * 10 > p.cap * 7) need = ((int)(h->flags_host[FLAG_MAXCOUNT] * 1.6) + 31) / 16 * 16;
+    // (a tile of the benchmark lattice holds up to 72 particles of the initial capacity 96: 75 % full is normal)
+    if (h->flags_host[FLAG_MAXCOUNT] * 100 > p.cap * 85) need = ((int)(h->flags_host[FLAG_MAXCOUNT] * 1.3) + 15) / 16 * 16;
     if ((st = slab_allreduce_max(h, &need))) return st;
     if (need > p.cap) {
       h->n_rebuilds++;

@@ -502,7 +502,7 @@ def test_c2_one_million_properties(cuda_lib):
 
 def test_slab_mode_grows_tiles_proactively(cuda_lib):
     """Slab mode cannot roll an overflowed step back (the other ranks have moved on), so tiles grow BEFORE they overflow: at
-    every synchronisation point a tile above 70 % of the capacity makes all ranks rebuild with larger tiles.  Forced here by
+    every synchronisation point a tile above 85 % of the capacity makes all ranks rebuild with larger tiles.  Forced here by
     MAVI_FLAG_TIGHT_TILES (capacity = fullest tile at upload) in one-rank slab mode; results stay bit-identical."""
     SELF, TIGHT = pkg.capi.FLAG_SLAB_SELF, pkg.capi.FLAG_TIGHT_TILES
     case = H.newton_case(nx=64, ny=40, wall="periodic", jitter=0.3, vmax=3.0, dt=0.002)
