@@ -116,6 +116,7 @@ enum {
   FLAG_NMOVED = 15,  // per step: particles whose cell changed (re-binned by the incremental repair)
   // persistent tile-block kernels: next work item of the launch on the main stream [0] / of the boundary-block launch [1]
   FLAG_WORK0 = 24, FLAG_WORK1 = 25,
+  FLAG_INBOX_STEP = 26,  // per step: largest inbox population (with FLAG_MAXCOUNT it tells whether a tile CAN overflow at all)
   FLAG_COUNT = 32
 };
 
@@ -124,6 +125,11 @@ enum {
 // at the control words only occasionally; FLAG_STEPS counts the steps that really ran.
 __device__ __forceinline__ bool step_poisoned(const int *flags) {
   return (flags[FLAG_OVERFLOW] != 0) || ((flags[FLAG_ERR] & ERRBIT_OOG_PENDING) != 0);
+}
+
+// raise a high-water mark without hammering one address with atomics: almost every caller sees a value that is already there
+__device__ __forceinline__ void raise_mark(int *word, int v) {
+  if (v > *reinterpret_cast<volatile int *>(word)) atomicMax(word, v);
 }
 
 #define MAVI_TR 32  // cell rows per tile

@@ -433,6 +433,10 @@ __global__ void __launch_bounds__(REPAIR_WARPS * 32) k_repair_tiles(
   const int ndirty = flags[FLAG_CHANGED];
   if (!flags[FLAG_RAN]) return;  // the step did not run (latched overflow / out-of-grid of an earlier step)
   if (WRITE && flags[FLAG_OVERFLOW]) return;
+  // CHECK pass: FLAG_MAXCOUNT is a high-water mark of every tile's population (full builds and the WRITE pass raise it) and
+  // FLAG_INBOX_STEP the largest inbox of this step — if even their sum fits, no tile can overflow and the pass has nothing
+  // to find (Szabo C3: 63 us of the 0.86 ms step)
+  if (!WRITE && flags[FLAG_MAXCOUNT] + flags[FLAG_INBOX_STEP] <= p.cap && flags[FLAG_INBOX_STEP] <= p.inbox_cap) return;
   for (int d = blockIdx.x * REPAIR_WARPS + w; d < ndirty; d += gridDim.x * REPAIR_WARPS) {
     const int t = dirty_list[d];
     const int base = t * p.cap;
@@ -476,6 +480,7 @@ __global__ void __launch_bounds__(REPAIR_WARPS * 32) k_repair_tiles(
       continue;
     }
     if (!WRITE) continue;  // (keeps the compiler from warning about the unreachable tail in the CHECK instantiation)
+    if (lane == 0) raise_mark(&flags[FLAG_MAXCOUNT], total);
     // ---- ... plus arrivals from other tiles
     for (int i = lane; i < nin; i += 32) {
       const int mi = inbox[(size_t)t * p.inbox_cap + i];
@@ -531,7 +536,7 @@ void launch_repair_tiles(const LaunchCtx &c, const DevParams &p, const DevArrays
   real *ang = second_is_vel ? nullptr : a.ang;
   const size_t smem = (size_t)REPAIR_WARPS * p.cap * sizeof(RepairRec);
   if (smem > 48 * 1024) cudaFuncSetAttribute(k_repair_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const int grid = 148 * 4;
+  const int grid = 148 * 8;  // one warp per dirty tile at a time: latency-bound, so as many warps as fit (8 CTAs of 4 warps per SM)
   MAVI_LAUNCH(c, (k_repair_tiles<false>), grid, REPAIR_WARPS * 32, 0, p, a.flags, a.dirty_list, a.tile_dirty, a.inbox_cnt,
               a.inbox, a.tstart, a.pos[0], vel, ang, a.force, a.idflag, a.cell, a.mv_pos, a.mv_second, a.mv_force, a.mv_id,
               a.mv_cell);
@@ -648,6 +653,7 @@ __device__ __noinline__ void note_moved_slow(const DevParams &p, const MoverSink
     mark_dirty(ms, t_new);
     const int m = atomicAdd(&ms.flags[FLAG_NMV], 1);
     const int i = atomicAdd(&ms.inbox_cnt[t_new], 1);
+    raise_mark(&ms.flags[FLAG_INBOX_STEP], i + 1);
     if (m < p.mv_cap && i < p.inbox_cap) {
       ms.mv_src[m] = k;
       ms.inbox[(size_t)t_new * p.inbox_cap + i] = m;
@@ -943,6 +949,7 @@ __global__ void k_step_begin(int *__restrict__ flags) {
     flags[FLAG_NMV] = 0;
     flags[FLAG_WORK0] = 0;
     flags[FLAG_WORK1] = 0;
+    flags[FLAG_INBOX_STEP] = 0;
     flags[FLAG_RAN] = run;
   }
 }
@@ -1547,18 +1554,23 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
       body(k, pos[k], 0, false, make_real2(0.0, 0.0), InCellNone{}, pv);
     }
   }
-  // the two buffers are consumed alternately; uses = how often each was consumed (barrier phase), done = its end marker seen
-  int uses = 0;   // bits 0..15: buffer 0, bits 16..31: buffer 1
-  int done = 0;   // bit b
-  for (int b = 0; done != 3; b ^= 1) {
-    if (done & (1 << b)) continue;
+  // The two buffers are consumed alternately.  Per warp: the barrier phase of each buffer (bits 0, 1) and whether its end
+  // marker was seen (bits 2, 3) — kept in shared memory: as registers the compiler spilled them to LOCAL memory, and the
+  // reload at every chunk boundary was 3.4 % of the stall samples (capture r2u of profiles/r02_ncu_newton_summary.md)
+  __shared__ int s_wstate[32];
+  volatile int *wst = s_wstate + w;
+  *wst = 0;
+  for (int b = 0;; b ^= 1) {
+    const int st = *wst;
+    if ((st >> 2) == 3) break;
+    if (st & (4 << b)) continue;
     unsigned char *buf = dsm + 64 + (size_t)b * PBUF_BYTES;
     PChunk *ck = reinterpret_cast<PChunk *>(buf);
     const real2 *s_pos = reinterpret_cast<const real2 *>(buf + PCH_BYTES);
     const int *s_cell = reinterpret_cast<const int *>(buf + PCH_BYTES + PSPOS_CAP * sizeof(real2));
-    mbar_wait(&bars[b], (unsigned int)((uses >> (16 * b)) & 1));
+    mbar_wait(&bars[b], (unsigned int)((st >> b) & 1));
     if (!ck->state) {
-      done |= 1 << b;
+      *wst = st | (4 << b);
       continue;
     }
     if (ck->ok) {
@@ -1606,7 +1618,7 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&bars[2 + b]);  // this warp is done with the buffer
-    uses += 1 << (16 * b);
+    *wst = *wst ^ (1 << b);
   }
 }
 

@@ -235,6 +235,7 @@ __global__ void k_ingest(const __grid_constant__ DevParams p, const EmRec *__res
     }
     const int m = atomicAdd(&flags[FLAG_NMV], 1);
     const int i = atomicAdd(&inbox_cnt[t], 1);
+    raise_mark(&flags[FLAG_INBOX_STEP], i + 1);
     if (m < p.mv_cap && i < p.inbox_cap) {
       mv_src[m] = -1;  // record already in place (k_repair_collect skips it)
       mv_pos[m] = e.pos;
