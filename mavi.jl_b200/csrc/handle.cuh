@@ -14,6 +14,7 @@ struct RingsArrays {
   real *areas = nullptr;
   real2 *cms = nullptr;       // info.cms (lags one step, src/rings/integration.jl:523)
   real *pol = nullptr;        // state.pol, one angle per ring
+  real2 *spos = nullptr;      // positions in index-tile slot order (spos[s] = pos[perm[s]]), rewritten by every binning
   // ParticleNeighbors (src/rings/neighbors.jl, src/rings/rings.jl:143-158): contact counts / lists of the last forces!
   int *neigh_count = nullptr;   // [n]
   int *neigh_list = nullptr;    // [n][MAVI_NEIGH_MAX], ascending ids, -1 padded (list mode only)

@@ -308,8 +308,10 @@ void launch_build_tiles(const LaunchCtx &c, const DevParams &p, const DevArrays 
 
 // ---- index-only tiles (Mavi.Rings): the state stays ring-ordered; only particle INDICES are binned -----------------
 // after the scatter every cell's slot range of perm[] is sorted ascending (= ascending ids, src/chunks.jl:153-155)
+// ... and spos[] (optional) receives the positions in slot order for the pair kernel
 __global__ void k_sort_perm_cells(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
-                                  int *__restrict__ perm, const int *__restrict__ flags) {
+                                  int *__restrict__ perm, const int *__restrict__ flags,
+                                  const real2 *__restrict__ pos, real2 *__restrict__ spos) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= p.num_cells || flags[FLAG_OVERFLOW]) return;
   const int col = div_rows(p, c), row = c - col * p.num_rows;
@@ -324,14 +326,16 @@ __global__ void k_sort_perm_cells(const __grid_constant__ DevParams p, const int
     }
     perm[j + 1] = v;
   }
+  if (spos)
+    for (int i = b; i < e; i++) spos[i] = pos[perm[i]];
 }
 
 void launch_build_index_tiles(const LaunchCtx &c, const DevParams &p, const real2 *pos, const unsigned int *idflag,
-                              int *cell_out, int *count, int *tstart, int *perm, int *flags) {
+                              int *cell_out, int *count, int *tstart, int *perm, int *flags, real2 *spos) {
   MAVI_LAUNCH(c, k_build_cell_index, nblk(p.n), TPB, 0, p, pos, idflag, cell_out, count, flags);
   MAVI_LAUNCH(c, k_build_layout, nblk(p.nt), TPB, 0, p, count, tstart, flags);
   MAVI_LAUNCH(c, k_build_scatter, nblk(p.n), TPB, 0, p, cell_out, tstart, count, perm, flags);
-  MAVI_LAUNCH(c, k_sort_perm_cells, nblk(p.num_cells), TPB, 0, p, tstart, perm, flags);
+  MAVI_LAUNCH(c, k_sort_perm_cells, nblk(p.num_cells), TPB, 0, p, tstart, perm, flags, pos, spos);
 }
 
 // dense copy of the current state into the staging arrays, in rank order

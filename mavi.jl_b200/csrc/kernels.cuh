@@ -69,7 +69,7 @@ void launch_check_inside(const LaunchCtx &c, const DevParams &p, const DevArrays
 void launch_build_tiles(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel);
 // Mavi.Rings: bin particle indices only (perm[slot] = particle index, ascending inside every cell)
 void launch_build_index_tiles(const LaunchCtx &c, const DevParams &p, const real2 *pos, const unsigned int *idflag,
-                              int *cell_out, int *count, int *tstart, int *perm, int *flags);
+                              int *cell_out, int *count, int *tstart, int *perm, int *flags, real2 *spos = nullptr);
 // dense copy of the current state into staging (rank order)
 void launch_compact_to_staging(const LaunchCtx &c, const DevParams &p, const DevArrays &a, bool second_is_vel);
 void launch_compact_cells(const LaunchCtx &c, const DevParams &p, const DevArrays &a, int *out);

@@ -85,10 +85,17 @@ __global__ void k_rings_area_empty(const __grid_constant__ DevParams p, const un
   }
 }
 
-// calc_interaction + calc_interaction_force (src/rings/integration.jl:32-77) summed over the stencil, + wall forces
+// calc_interaction + calc_interaction_force (src/rings/integration.jl:32-77) summed over the stencil, + wall forces.
+// Thread per particle in RING order (neighbouring threads are neighbours in space: their windows overlap in L1).  The
+// candidates come from the index tiles: spos[s] / perm[s] = position / particle index of slot s, so a candidate costs two
+// independent loads instead of the chain perm -> pos.  A particle whose cell rows r-1 .. r+1 lie inside one tile (30 of 32
+// rows) walks its three column runs in ONE flat loop (tstart[r-1] .. tstart[r+2] of each column, same visiting order as the
+// generic 9-cell walker, so the sums are bit-identical to it); the others take the generic walker.  In round 1 the nested
+// per-cell loops kept 12 of 32 lanes busy (profiles/r01_ncu_szabo_rings.md).
 template <bool PER>
 __global__ void __launch_bounds__(TPB) k_rings_pair(const __grid_constant__ DevParams p, const int *__restrict__ tstart,
-                                                    const int *__restrict__ perm, const int *__restrict__ cell,
+                                                    const int *__restrict__ perm, const real2 *__restrict__ spos,
+                                                    const int *__restrict__ cell,
                                                     const unsigned int *__restrict__ idflag,
                                                     const real2 *__restrict__ pos, real2 *__restrict__ fpair,
                                                     int with_walls, const int *__restrict__ flags) {
@@ -102,18 +109,19 @@ __global__ void __launch_bounds__(TPB) k_rings_pair(const __grid_constant__ DevP
   real fx = 0.0, fy = 0.0;
   if (!(idflag[i] & MAVI_INACTIVE_BIT)) {
     const int ring = i / R.n_max;
+    const int ring_lo = ring * R.n_max, ring_hi = ring_lo + R.n_max;
     const int ti = ring_type(R, ring);
     const int np = R.num_particles[ti];
+    const bool typed = R.num_types > 1;
+    const real *ic_row = s_inter + 7 * (ti * R.num_types);
     const real2 ri = pos[i];
-    auto visit = [&](int j) {
-      const real2 rj = __ldg(pos + j);
+    auto visit = [&](int j, real2 rj) {
       const real dx = min_image<PER>(ri.x - rj.x, p.half[0], p.size[0]);
       const real dy = min_image<PER>(ri.y - rj.y, p.half[1], p.size[1]);
       const real r2 = dist2_exact(dx, dy);
-      const int rj_ring = j / R.n_max;
-      const real *ic = s_inter + 7 * (ti * R.num_types + ring_type(R, rj_ring));
+      const bool same = j >= ring_lo && j < ring_hi;
+      const real *ic = typed ? ic_row + 7 * ring_type(R, j / R.n_max) : ic_row;
       if (r2 > ic[4]) return;  // dist > dist_max
-      const bool same = rj_ring == ring;
       if (same) {
         const int diff = i > j ? i - j : j - i;
         if (diff == 1 || diff == np - 1) return;  // bonded neighbours inside the ring
@@ -126,12 +134,41 @@ __global__ void __launch_bounds__(TPB) k_rings_pair(const __grid_constant__ DevP
     if (p.num_cells == 0) {
       // chunks === nothing: all pairs over the active ids (src/integration.jl:197-224)
       for (int j = 0; j < p.n; j++)
-        if (j != i && !(idflag[j] & MAVI_INACTIVE_BIT)) visit(j);
+        if (j != i && !(idflag[j] & MAVI_INACTIVE_BIT)) visit(j, __ldg(pos + j));
     } else {
-      for_each_neighbor(p, tstart, cell[i], -1, [&](int s) {
-        const int j = __ldg(perm + s);
-        if (j != i) visit(j);
-      });
+      const int c = cell[i];
+      const int col = div_rows(p, c), row = c - col * p.num_rows;
+      const int tr = row / MAVI_TR, lr = row - tr * MAVI_TR;
+      if (lr >= 1 && lr <= MAVI_TR - 2 && row + 1 < p.num_rows) {
+        int b[3], l[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          int c2 = col + d - 1;
+          bool ok = true;
+          if (c2 < 0) { ok = p.wrap_cols; c2 = p.num_cols - 1; }
+          else if (c2 >= p.num_cols) { ok = p.wrap_cols; c2 = 0; }
+          b[d] = 0; l[d] = 0;
+          if (ok) {
+            const int *tt = tstart + (size_t)(c2 * p.tpc + tr) * (MAVI_TR + 1) + lr - 1;
+            b[d] = __ldg(tt);
+            l[d] = __ldg(tt + 3) - b[d];
+          }
+        }
+        const int l01 = l[0] + l[1], total = l01 + l[2];
+        const int o1 = b[1] - l[0], o2 = b[2] - l01;
+#pragma unroll 2
+        for (int t = 0; t < total; t++) {
+          const int s = t + (t < l[0] ? b[0] : (t < l01 ? o1 : o2));
+          const int j = __ldg(perm + s);
+          const real2 rj = __ldg(spos + s);
+          if (j != i) visit(j, rj);
+        }
+      } else {
+        for_each_neighbor(p, tstart, c, -1, [&](int s) {
+          const int j = __ldg(perm + s);
+          if (j != i) visit(j, __ldg(spos + s));
+        });
+      }
     }
     if (with_walls && p.has_force_walls) wall_forces(p, ri.x, ri.y, fx, fy);
   }
@@ -600,7 +637,7 @@ int rings_allocate(Handle *h) {
 static int rings_alloc_tiles(Handle *h, int cap) {
   DevParams &p = h->p;
   DevArrays &a = h->a;
-  void *old[] = {a.tstart, a.perm};
+  void *old[] = {a.tstart, a.perm, h->r.spos};
   for (void *q : old)
     if (q) {
       for (auto &x : h->allocs)
@@ -626,13 +663,16 @@ static int rings_alloc_tiles(Handle *h, int cap) {
   }
   a.tstart = nullptr;
   a.perm = nullptr;
+  h->r.spos = nullptr;
   if (cudaMalloc((void **)&a.tstart, ((size_t)p.nt * (MAVI_TR + 1) + 1) * sizeof(int)) != cudaSuccess ||
-      cudaMalloc((void **)&a.perm, (slots + 2) * sizeof(int)) != cudaSuccess) {
+      cudaMalloc((void **)&a.perm, (slots + 2) * sizeof(int)) != cudaSuccess ||
+      cudaMalloc((void **)&h->r.spos, (slots + 2) * sizeof(real2)) != cudaSuccess) {
     h->set_error("cudaMalloc failed (index tiles)");
     return MAVI_ERR_CUDA;
   }
   h->allocs.push_back(a.tstart);
   h->allocs.push_back(a.perm);
+  h->allocs.push_back(h->r.spos);
   return MAVI_OK;
 }
 
@@ -645,7 +685,7 @@ int rings_bin(Handle *h) {
   for (int attempt = 0; attempt < 8; attempt++) {
     RINGS_TRY(h, cudaMemsetAsync(a.count, 0, ((size_t)p.num_cells + 2) * sizeof(int), h->stream));
     RINGS_TRY(h, cudaMemsetAsync(a.flags + 1, 0, (FLAG_STEPS - 1) * sizeof(int), h->stream));
-    launch_build_index_tiles(h->ctx(), p, a.pos[0], a.idflag, a.cell, a.count, a.tstart, a.perm, a.flags);
+    launch_build_index_tiles(h->ctx(), p, a.pos[0], a.idflag, a.cell, a.count, a.tstart, a.perm, a.flags, h->r.spos);
     int st = h->check_device_flags();
     if (st) return st;
     if (!h->flags_host[FLAG_OVERFLOW]) return MAVI_OK;
@@ -662,9 +702,9 @@ static void launch_pair(Handle *h, bool with_walls) {
   const size_t smem = (size_t)p.rings.num_types * p.rings.num_types * 7 * sizeof(real);
   const int grid = (p.n + TPB - 1) / TPB;
   if (p.periodic) {
-    k_rings_pair<true><<<grid, TPB, smem, h->stream>>>(p, a.tstart, a.perm, a.cell, a.idflag, a.pos[0], a.force_old, (int)with_walls, a.flags);
+    k_rings_pair<true><<<grid, TPB, smem, h->stream>>>(p, a.tstart, a.perm, h->r.spos, a.cell, a.idflag, a.pos[0], a.force_old, (int)with_walls, a.flags);
   } else {
-    k_rings_pair<false><<<grid, TPB, smem, h->stream>>>(p, a.tstart, a.perm, a.cell, a.idflag, a.pos[0], a.force_old, (int)with_walls, a.flags);
+    k_rings_pair<false><<<grid, TPB, smem, h->stream>>>(p, a.tstart, a.perm, h->r.spos, a.cell, a.idflag, a.pos[0], a.force_old, (int)with_walls, a.flags);
   }
   h->launches++;
   RingsArrays &r = h->r;
@@ -1193,7 +1233,7 @@ int rings_step(Handle *h, const real *noise_dev) {
   }
   if (p.num_cells > 0) {  // update_chunks_all! (after update_cms!, which only reads last step's continuos_pos)
     RINGS_TRY(h, cudaMemsetAsync(a.count, 0, ((size_t)p.num_cells + 2) * sizeof(int), h->stream));
-    launch_build_index_tiles(h->ctx(), p, a.pos[0], a.idflag, a.cell, a.count, a.tstart, a.perm, a.flags);
+    launch_build_index_tiles(h->ctx(), p, a.pos[0], a.idflag, a.cell, a.count, a.tstart, a.perm, a.flags, h->r.spos);
   }
   int prime = 0;
   if (r.inv_steps > 0 && h->num_steps - r.inv_last_check >= r.inv_steps) {

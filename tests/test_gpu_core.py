@@ -187,6 +187,37 @@ def test_philox_mode_statistics(cuda_lib):
     assert abs(g.state.pol_angle.mean()) < 0.05
 
 
+def test_philox_mode_statistics_rtp(cuda_lib):
+    """Device RNG mode of update_rtp! (src/integration.jl:467-498): a particle tumbles with probability tumble_rate * dt per
+    step and then gets a uniform angle in [0, 2 pi).  Free particles (no overlap, vo = 0), all starting at angle 10 (outside
+    the range a tumble can produce): after k steps the fraction still at 10 is (1 - p)^k, the others are uniform."""
+    dyn = pkg.RunTumbleCfg(vo=0.0, sigma=1.0, epsilon=1.0, tumble_rate=2.0)
+    pos, geom, rng = H.lattice(200, 200, dyn, offset=1.0)
+    n = len(pos)
+    st = pkg.SelfPropelledState(pos=pos, pol_angle=np.full(n, 10.0))
+    g = pkg.System(state=st, space_cfg=pkg.SpaceCfg(wall_type=pkg.PeriodicWalls(), geometry_cfg=geom), dynamic_cfg=dyn,
+                   int_cfg=pkg.IntCfg(dt=0.01, chunks_cfg=pkg.ChunksCfg(150, 150), device=pkg.CUDADevice(rng_mode="philox", seed=11)))
+    k = 40
+    g.step(k)
+    g.sync_to_host()
+    ang = g.state.pol_angle
+    untouched = ang == 10.0
+    expect = (1 - 2.0 * 0.01) ** k
+    assert abs(untouched.mean() - expect) < 4 * np.sqrt(expect * (1 - expect) / n)   # binomial, 4 sigma
+    t = ang[~untouched]
+    assert t.min() >= 0.0 and t.max() < 2 * np.pi
+    m = len(t)
+    assert abs(t.mean() - np.pi) < 4 * (2 * np.pi / np.sqrt(12)) / np.sqrt(m)
+    assert abs(t.var() - (2 * np.pi) ** 2 / 12) < 0.15
+    # the four quadrants are equally likely (chi-square with 3 degrees of freedom, p = 1e-4 at 21.1)
+    cnt = np.histogram(t, bins=4, range=(0, 2 * np.pi))[0]
+    assert ((cnt - m / 4) ** 2 / (m / 4)).sum() < 21.1
+    # different steps draw different numbers: the positions never moved, the tumbled set keeps growing
+    g.step(k)
+    g.sync_to_host()
+    assert (g.state.pol_angle == 10.0).mean() < untouched.mean()
+
+
 # ---------------------------------------------------------------- walls, force walls, composite spaces
 def test_rigid_circle_walls(cuda_lib):
     """examples/print_energy.jl geometry: LJ in a rigid circle, all pairs."""

@@ -157,6 +157,35 @@ def test_rings_gpu_philox_runs(cuda_lib):
 
 
 @pytest.mark.gpu
+def test_rings_gpu_philox_statistics(cuda_lib):
+    """Device RNG mode of the Rings update! (src/rings/integration.jl:345-346): with the alignment term switched off
+    (relax_time -> inf) a ring's polarisation is a random walk with variance 2 D_r t; rings are independent (no correlation
+    between neighbouring ring ids) and two seeds give different streams."""
+    from mavi_jl_b200.rings import configs as rc
+
+    def run(seed):
+        case = H.rings_case("normal", 40, 30, rot_diff=0.5)
+        case["dyn"].relax_time = np.full(case["dyn"].num_types, 1e30)
+        case["int_cfg"] = rc.RingsIntCfg(dt=0.01, p_chunks_cfg=case["int_cfg"].chunks_cfg, device=pkg.CUDADevice(rng_mode="philox", seed=seed))
+        g = H.make_gpu_rings(case)
+        pol0 = g.state.pol.copy()
+        g.step(100)
+        g.sync_to_host()
+        assert np.isfinite(g.state.pos).all()
+        return g.state.pol - pol0
+
+    d = run(5)
+    n = len(d)                                            # 1200 rings, t = 1: variance 2 * 0.5 * 1 = 1
+    assert abs(d.var() - 1.0) < 5 * np.sqrt(2.0 / n)      # variance of a normal sample: sigma^2 sqrt(2 / n)
+    assert abs(d.mean()) < 5 / np.sqrt(n)
+    assert abs(np.corrcoef(d[:-1], d[1:])[0, 1]) < 5 / np.sqrt(n)
+    kurt = ((d - d.mean()) ** 4).mean() / d.var() ** 2     # a sum of 100 normal increments is normal: kurtosis 3
+    assert abs(kurt - 3.0) < 0.8
+    d2 = run(6)
+    assert abs(np.corrcoef(d, d2)[0, 1]) < 5 / np.sqrt(n)
+
+
+@pytest.mark.gpu
 def test_rings_asymmetric_matrix_rejected(cuda_lib):
     from mavi_jl_b200.rings import configs as rc
     case = H.rings_case("types", 5, 5)
