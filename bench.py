@@ -81,6 +81,59 @@ def lj_workload(pkg, nx, ny, cuda_device=None, chunks=True, rank=0, world=1):
     return dict(pos=pos, vel=vel, space=space, dyn=dyn, int_cfg=int_cfg, geom=geom, ids=ids, n_global=nxt * ny)
 
 
+def szabo_slabs(pkg, dist, torch, nx, ny, rank, world, local_rank, stream, steps, warmup, peak):
+    """BASELINE config C3 at N > 1 (side measurement, never part of `value`): Szabo self-propelled particles, nx*world x ny
+    lattice (examples/szabo.jl parameters, offset 1), periodic, x-slabs over the ranks, Philox noise; weak scaling like the
+    headline.  All ranks call this collectively; returns the entry for `other_configs.szabo_c3`."""
+    from mavi_jl_b200 import slabs
+    box = [slabs.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    dyn = pkg.SzaboCfg(vo=1.0, mobility=1.0, relax_time=1.0, k_rep=10.0, k_adh=0.75, r_eq=1.0, r_max=1.1, rot_diff=0.01)
+    r = pkg.particle_radius(dyn)
+    nxt = nx * world
+    ncols, nrows = nxt - world, ny - 1
+    line, geom = pkg.rectangular_grid(nxt, 1, 1.0, r)
+    colm, g2 = pkg.rectangular_grid(1, ny, 1.0, r)
+    geom = pkg.RectangleCfg(length=geom.length, height=g2.height)
+    xs, ys = line[:, 0], colm[:, 1]
+    mine_x = np.flatnonzero(slabs.owner_of_column(slabs.column_of(xs, 0.0, geom.length, ncols), ncols, world) == rank)
+    pos = np.empty((ny, len(mine_x), 2))
+    pos[..., 0] = xs[mine_x][None, :]
+    pos[..., 1] = ys[:, None]
+    pos = pos.reshape(-1, 2)
+    ids = (np.arange(ny)[:, None] * nxt + mine_x[None, :]).reshape(-1)
+    ang = np.random.default_rng(SEED + rank).random(len(pos)) * 2 * np.pi
+    dev = pkg.CUDADevice(device=local_rank, stream=stream, rank=rank, world=world, nccl_unique_id=box[0], n_global=nxt * ny,
+                         rng_mode="philox")
+    st = pkg.SelfPropelledState(pos=pos, pol_angle=ang)
+    st.ids = ids
+    s = pkg.System(state=st, space_cfg=pkg.SpaceCfg(wall_type=pkg.PeriodicWalls(), geometry_cfg=geom), dynamic_cfg=dyn,
+                   int_cfg=pkg.IntCfg(dt=0.01, chunks_cfg=pkg.ChunksCfg(ncols, nrows), device=dev))
+    try:
+        s.step(warmup)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        s.step(steps)
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total = torch.tensor([float(s.local_count())], device="cuda", dtype=torch.float64)
+        dist.all_reduce(total, op=dist.ReduceOp.SUM)
+        ms = float(t.item()) / steps
+        n_all = nxt * ny
+        return {"ms_per_step": ms, "steps": steps, "value": n_all / (ms * 1e-3), "unit": "particle-steps/s", "n_gpus": world,
+                "roofline_step_frac": 88.0 * nx * ny / (ms * 1e-3) / 1e9 / peak, "bytes_per_particle_step": 88.0,
+                "count_conserved": bool(int(total.item()) == n_all),
+                "what": f"BASELINE config C3 on {world} GPUs: Szabo particles {nxt}x{ny} (16 M per GPU), periodic, f64, szabo_step!, "
+                        "Philox noise, x-slabs with NCCL halo + migration (max over ranks)"}
+    finally:
+        s.close()
+
+
 class ClockSampler(threading.Thread):
     """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  NVML (nvidia_ml_py) is
     polled every ~5 ms so that a 0.1 s timed region still gets tens of samples; `nvidia-smi` (one sample per ~0.1 s
@@ -481,12 +534,18 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / float(t.item())
 
+    peak, peak_kind = measured_peak_hbm()
+    szabo_multi = None
+    if world > 1 and not args.no_other_configs:   # collective: every rank takes part
+        try:
+            szabo_multi = szabo_slabs(pkg, dist, torch, nx, ny, rank, world, local_rank, stream, max(10, args.steps // 4), args.warmup, peak)
+        except Exception as exc:  # noqa: BLE001
+            szabo_multi = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peak, peak_kind = measured_peak_hbm()
     traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (same N only)
     try:
         with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
@@ -627,6 +686,8 @@ def run_ours(args):
     other = None
     if world == 1 and not args.no_other_configs and not slab_api_main:
         other = {"szabo_c3": side(m_szabo), "rings_c4": side(m_rings)}
+    elif szabo_multi is not None:
+        other = {"szabo_c3": szabo_multi}
     def m_cpu():
         # the C restatement built -O3 -march=native -fopenmp, all host cores, at 1M and (memory permitting) at
         # the metric's own 16M; `value` is the 16M figure when it ran.  Bounded: a few timed steps each.
