@@ -1562,8 +1562,9 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
   // marker was seen (bits 2, 3) — kept in shared memory: as registers the compiler spilled them to LOCAL memory, and the
   // reload at every chunk boundary was 3.4 % of the stall samples (capture r2u of profiles/r02_ncu_newton_summary.md)
   __shared__ int s_wstate[32];
-  volatile int *wst = s_wstate + w;
-  *wst = 0;
+  volatile int *wst = s_wstate + w;  // written by lane 0 only, read by the warp after a __syncwarp()
+  if (lane == 0) *wst = 0;
+  __syncwarp();
   for (int b = 0;; b ^= 1) {
     const int st = *wst;
     if ((st >> 2) == 3) break;
@@ -1574,7 +1575,9 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
     const int *s_cell = reinterpret_cast<const int *>(buf + PCH_BYTES + PSPOS_CAP * sizeof(real2));
     mbar_wait(&bars[b], (unsigned int)((st >> b) & 1));
     if (!ck->state) {
-      *wst = st | (4 << b);
+      __syncwarp();
+      if (lane == 0) *wst = st | (4 << b);
+      __syncwarp();
       continue;
     }
     if (ck->ok) {
@@ -1621,8 +1624,11 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&bars[2 + b]);  // this warp is done with the buffer
-    *wst = *wst ^ (1 << b);
+    if (lane == 0) {
+      mbar_arrive(&bars[2 + b]);  // this warp is done with the buffer
+      *wst = st ^ (1 << b);
+    }
+    __syncwarp();
   }
 }
 

@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(TPB) k_rings_pair(const __grid_constant__ DevP
                                                     const real2 *__restrict__ pos, real2 *__restrict__ fpair,
                                                     int with_walls, const int *__restrict__ flags) {
   extern __shared__ real s_inter[];  // [num_types^2][7]
+  __shared__ int s_rb[9][TPB], s_re[9][TPB];  // candidate runs of each thread
   const DevRings &R = p.rings;
   if (flags[FLAG_OVERFLOW]) return;  // the index tiles of this step overflowed: the step does not run (rings_run_steps re-runs it)
   for (int t = threadIdx.x; t < R.num_types * R.num_types * 7; t += blockDim.x) s_inter[t] = R.interaction[t];
@@ -115,19 +116,19 @@ __global__ void __launch_bounds__(TPB) k_rings_pair(const __grid_constant__ DevP
     const bool typed = R.num_types > 1;
     const real *ic_row = s_inter + 7 * (ti * R.num_types);
     const real2 ri = pos[i];
+    // branch-free: a candidate that does not interact (itself, out of range, bonded neighbour) contributes c = 0.  With
+    // early returns the warp ran the force branch for ~every candidate anyway and kept 13 of 32 lanes busy.
     auto visit = [&](int j, real2 rj) {
       const real dx = min_image<PER>(ri.x - rj.x, p.half[0], p.size[0]);
       const real dy = min_image<PER>(ri.y - rj.y, p.half[1], p.size[1]);
       const real r2 = dist2_exact(dx, dy);
       const bool same = j >= ring_lo && j < ring_hi;
       const real *ic = typed ? ic_row + 7 * ring_type(R, j / R.n_max) : ic_row;
-      if (r2 > ic[4]) return;  // dist > dist_max
-      if (same) {
-        const int diff = i > j ? i - j : j - i;
-        if (diff == 1 || diff == np - 1) return;  // bonded neighbours inside the ring
-      }
+      const int diff = i > j ? i - j : j - i;
+      // dist > dist_max | the particle itself | bonded neighbours inside the ring
+      const bool skip = (r2 > ic[4]) | (diff == 0) | (same & ((diff == 1) | (diff == np - 1)));
       const real k = (r2 < ic[5]) ? ic[0] : (same ? 0.0 : ic[1]);  // no intra-ring attraction
-      const real c = k * (rsqrt(r2) - ic[6]);
+      const real c = skip ? real(0.0) : k * (rsqrt(r2) - ic[6]);
       fx = fma(c, dx, fx);
       fy = fma(c, dy, fy);
     };
@@ -136,38 +137,54 @@ __global__ void __launch_bounds__(TPB) k_rings_pair(const __grid_constant__ DevP
       for (int j = 0; j < p.n; j++)
         if (j != i && !(idflag[j] & MAVI_INACTIVE_BIT)) visit(j, __ldg(pos + j));
     } else {
+      // Candidate RUNS of slots (start, end) in the visiting order of the generic 9-cell walker (columns col-1 .. col+1,
+      // rows row-1 .. row+1 inside each; cell rows that are adjacent in a tile merge into one run), kept in shared memory
+      // [run][thread], then ONE flat loop over all of them: every lane of the warp stays in the same loop whatever its cell
+      // (a separate generic path for rows at tile edges ran with 2-3 active lanes and dominated the kernel).
       const int c = cell[i];
       const int col = div_rows(p, c), row = c - col * p.num_rows;
       const int tr = row / MAVI_TR, lr = row - tr * MAVI_TR;
-      if (lr >= 1 && lr <= MAVI_TR - 2 && row + 1 < p.num_rows) {
-        int b[3], l[3];
+      const int tid = threadIdx.x;
+      int nruns = 0;
+      if (lr >= 1 && lr <= MAVI_TR - 2 && row + 1 < p.num_rows) {  // rows row-1 .. row+1 inside one tile: one run per column
 #pragma unroll
         for (int d = 0; d < 3; d++) {
           int c2 = col + d - 1;
           bool ok = true;
           if (c2 < 0) { ok = p.wrap_cols; c2 = p.num_cols - 1; }
           else if (c2 >= p.num_cols) { ok = p.wrap_cols; c2 = 0; }
-          b[d] = 0; l[d] = 0;
           if (ok) {
             const int *tt = tstart + (size_t)(c2 * p.tpc + tr) * (MAVI_TR + 1) + lr - 1;
-            b[d] = __ldg(tt);
-            l[d] = __ldg(tt + 3) - b[d];
+            s_rb[nruns][tid] = __ldg(tt);
+            s_re[nruns][tid] = __ldg(tt + 3);
+            nruns++;
           }
         }
-        const int l01 = l[0] + l[1], total = l01 + l[2];
-        const int o1 = b[1] - l[0], o2 = b[2] - l01;
-#pragma unroll 2
-        for (int t = 0; t < total; t++) {
-          const int s = t + (t < l[0] ? b[0] : (t < l01 ? o1 : o2));
-          const int j = __ldg(perm + s);
-          const real2 rj = __ldg(spos + s);
-          if (j != i) visit(j, rj);
-        }
       } else {
-        for_each_neighbor(p, tstart, c, -1, [&](int s) {
-          const int j = __ldg(perm + s);
-          if (j != i) visit(j, __ldg(spos + s));
-        });
+        for (int d = 0; d < 3; d++) {
+          int c2 = col + d - 1;
+          if (c2 < 0) { if (!p.wrap_cols) continue; c2 = p.num_cols - 1; }
+          else if (c2 >= p.num_cols) { if (!p.wrap_cols) continue; c2 = 0; }
+          int prev_end = -1;
+          for (int dr = -1; dr <= 1; dr++) {
+            int r2 = row + dr;
+            if (r2 < 0) { if (!p.wrap_rows) continue; r2 = p.num_rows - 1; }
+            else if (r2 >= p.num_rows) { if (!p.wrap_rows) continue; r2 = 0; }
+            const int q = tq_of(p, c2, r2);
+            const int jb = __ldg(tstart + q), je = __ldg(tstart + q + 1);
+            if (jb == prev_end) s_re[nruns - 1][tid] = je;
+            else { s_rb[nruns][tid] = jb; s_re[nruns][tid] = je; nruns++; }
+            prev_end = je;
+          }
+        }
+      }
+      int k = 0, cur = 0, end = 0;
+      if (nruns > 0) { cur = s_rb[0][tid]; end = s_re[0][tid]; }
+      for (;;) {
+        while (cur >= end && ++k < nruns) { cur = s_rb[k][tid]; end = s_re[k][tid]; }
+        if (cur >= end) break;
+        visit(__ldg(perm + cur), __ldg(spos + cur));
+        cur++;
       }
     }
     if (with_walls && p.has_force_walls) wall_forces(p, ri.x, ri.y, fx, fy);
