@@ -429,6 +429,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the library's default for its own communicator (csrc/slab.cu); NCCL reads it once per process, and torch
+        # initialises NCCL first here, so it has to be in the environment before that
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "2")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pkg = entry.load_package()
     pkg.load_library()

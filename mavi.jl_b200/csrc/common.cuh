@@ -37,6 +37,11 @@ struct DevRings {
 };
 
 // Kernel parameter block (passed by value as __grid_constant__).
+// Split launches of the slab step: the edge blocks (blk_mode 2) are the MAVI_EDGE_COLS owned columns next to each halo — the
+// only blocks that read a halo column, and the only ones an emigrant can come from unless it crosses >= MAVI_EDGE_COLS
+// columns in one step (reported loudly) — ~3 % of the particles of a 100-column slab, so the boundary launch is short.
+#define MAVI_EDGE_COLS 3
+
 struct DevParams {
   int n;               // particle slots held by this device
   int n_count;         // get_num_total_particles(state): number of active ids
@@ -54,8 +59,10 @@ struct DevParams {
   int chg_cap;    // capacity of the per-step changed-cell list (force carry)
   int blk_cols, blk_per_row;  // tile-block force kernels: own tiles (columns) per CTA, CTAs per tile row
   int pipe_items; // pipelined kernels: tile blocks a CTA takes before it exits (0: persistent, until the work counter runs out)
-  int blk_mode;   // 0: all blocks; 1: all but the first and the last blk_last blocks of every tile row; 2: only those
-  int blk_last;   // trailing blocks of a tile row that belong to the boundary group (2 when the last one is < 3 columns)
+  int pipe_reserved;  // pipelined kernels: CTAs that land on an SM with %smid < pipe_reserved exit at once (slab step, grid_pipe())
+  int blk_mode;   // 0: all blocks; 1: the interior of every tile row (all owned columns but MAVI_EDGE_COLS at each end, in blocks
+                  // of blk_cols); 2: the two edge blocks of every tile row (MAVI_EDGE_COLS columns each) — blk_items_per_row()
+  int blk_last;   // (unused)
   // x-slab domain decomposition (one process per GPU): the local grid is [left halo | owned columns | right halo];
   // cell arithmetic stays GLOBAL (bit-exact global cell ids), only the column index is shifted into the local frame.
   int slab;                   // 1 = slab mode
@@ -95,6 +102,27 @@ struct DevParams {
   DevRings rings;
 };
 
+// tile blocks of one tile row for the current blk_mode, and the owned columns [c_begin, c_end) of block `bcol`
+__host__ __device__ inline int blk_items_per_row(const DevParams &p) {
+  if (p.blk_mode == 0) return p.blk_per_row;
+  if (p.blk_mode == 1) return (p.ord_cols - 2 * MAVI_EDGE_COLS + p.blk_cols - 1) / p.blk_cols;
+  return 2;
+}
+__host__ __device__ inline void blk_columns(const DevParams &p, int bcol, int &c_begin, int &c_end) {
+  const int c0 = p.ord_col0, c1 = p.ord_col0 + p.ord_cols;
+  if (p.blk_mode == 0) {
+    c_begin = c0 + bcol * p.blk_cols;
+    c_end = c_begin + p.blk_cols < c1 ? c_begin + p.blk_cols : c1;
+  } else if (p.blk_mode == 1) {
+    c_begin = c0 + MAVI_EDGE_COLS + bcol * p.blk_cols;
+    c_end = c_begin + p.blk_cols < c1 - MAVI_EDGE_COLS ? c_begin + p.blk_cols : c1 - MAVI_EDGE_COLS;
+  } else {
+    c_begin = bcol ? c1 - MAVI_EDGE_COLS : c0;
+    c_end = c_begin + MAVI_EDGE_COLS;
+  }
+}
+
+
 enum { ERRBIT_OUT_OF_GRID = 1, ERRBIT_NAN = 2, ERRBIT_OUTSIDE_SPACE = 4, ERRBIT_OOG_PENDING = 8 };
 
 // flags[] layout (device control word, mirrored to pinned host memory once per step)
@@ -133,6 +161,7 @@ __device__ __forceinline__ void raise_mark(int *word, int v) {
 }
 
 #define MAVI_TR 32  // cell rows per tile
+
 
 // slab mode: record of a particle that leaves this rank's columns (written by the integrate kernel, shipped as is)
 struct EmRec {

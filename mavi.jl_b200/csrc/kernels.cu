@@ -1201,8 +1201,7 @@ __device__ __forceinline__ void for_each_block_particle(const DevParams &p, cons
   unsigned int *s_list = reinterpret_cast<unsigned int *>(dsm + C2_BYTES + SPOS2_CAP * sizeof(real2));
   // blk_mode 1 / 2 split a launch into the blocks that never read a halo column and the first / last block of every
   // tile row (slab mode: the halo exchange overlaps with the former)
-  const int bpr = p.blk_per_row;
-  const int per_row = p.blk_mode == 0 ? bpr : (p.blk_mode == 1 ? bpr - 1 - p.blk_last : 1 + p.blk_last);
+  const int per_row = blk_items_per_row(p);
   const int nblk_tiles = per_row * p.tpc;
   if ((int)blockIdx.x >= nblk_tiles) {  // inactive tail: no pair forces
     const int i = ((int)blockIdx.x - nblk_tiles) * TPB + threadIdx.x;
@@ -1214,11 +1213,8 @@ __device__ __forceinline__ void for_each_block_particle(const DevParams &p, cons
     return;
   }
   const int tr = (int)blockIdx.x / per_row;
-  int bcol = (int)blockIdx.x - tr * per_row;
-  if (p.blk_mode == 1) bcol += 1;
-  else if (p.blk_mode == 2) bcol = bcol ? bpr - bcol : 0;
-  const int c_begin = p.ord_col0 + bcol * p.blk_cols;
-  const int c_end = min(c_begin + p.blk_cols, p.ord_col0 + p.ord_cols);
+  int c_begin, c_end;
+  blk_columns(p, (int)blockIdx.x - tr * per_row, c_begin, c_end);
   const int r0 = tr * MAVI_TR;
   for (int cs = c_begin; cs < c_end;) {
     chunk_stage<PER>(p, tstart, pos, tr, cs, c_end - cs, exact_minimg, ck, s_pos, s_list);
@@ -1495,11 +1491,15 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
                                                        const double2 *__restrict__ edge_x, const double2 *__restrict__ edge_y,
                                                        bool exact_minimg, int *__restrict__ work, Pre &&pre, Body &&body) {
   constexpr int PIPE_CT = PIPE_CW * 32;  // consumer threads; the producers are the LAST warp(s) of the CTA
+  if (p.pipe_reserved > 0) {  // interior launch of the slab step: leave the reserved SMs to the side stream (grid_pipe())
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (smid < (unsigned int)p.pipe_reserved) return;
+  }
   extern __shared__ __align__(16) unsigned char dsm[];
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(dsm);  // [0,1] full, [2,3] empty
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int bpr = p.blk_per_row;
-  const int per_row = p.blk_mode == 0 ? bpr : (p.blk_mode == 1 ? bpr - 1 - p.blk_last : 1 + p.blk_last);
+  const int per_row = blk_items_per_row(p);
   const int nitems = per_row * p.tpc;
   if (threadIdx.x == 0) {
     mbar_init(&bars[0], 1);
@@ -1522,11 +1522,8 @@ __device__ __forceinline__ void pipe_for_each_particle(const DevParams &p, const
       item = __shfl_sync(0xffffffffu, item, 0);
       if (item >= nitems) break;
       const int tr = item / per_row;
-      int bcol = item - tr * per_row;
-      if (p.blk_mode == 1) bcol += 1;
-      else if (p.blk_mode == 2) bcol = bcol ? bpr - bcol : 0;
-      const int c_begin = p.ord_col0 + bcol * p.blk_cols;
-      const int c_end = min(c_begin + p.blk_cols, p.ord_col0 + p.ord_cols);
+      int c_begin, c_end;
+      blk_columns(p, item - tr * per_row, c_begin, c_end);
       for (int cs = c_begin; cs < c_end; k++) {
         const int b = NPROD == 2 ? pw : (k & 1);
         const int u = NPROD == 2 ? k : (k >> 1);  // how often this buffer has been filled before
@@ -1679,12 +1676,67 @@ static inline int slab_pipe_items() {
   }();
   return v;
 }
-static inline int grid_pipe(DevParams &p) {
-  const int per_row = p.blk_mode == 0 ? p.blk_per_row : (p.blk_mode == 1 ? p.blk_per_row - 1 - p.blk_last : 1 + p.blk_last);
-  const int items = per_row * p.tpc;
+
+// ... or, better (default), the interior launch stays persistent and LEAVES `reserved` SMs ALONE: it launches a few CTAs more
+// than the device holds, and every CTA that finds itself on an SM with %smid < reserved exits at once.  Those SMs then stay
+// empty for the whole pass (persistent CTAs never move), and the boundary launch (reserved * 3 persistent CTAs over the
+// narrow edge blocks, MAVI_EDGE_COLS), NCCL's kernels (<= 2 channels, slab.cu) and the small kernels of the side stream run
+// there without waiting for anything to drain.  MAVI_SLAB_RESERVED_SMS (default 4; 0 = CTAs of bounded lifetime instead).
+// Measured at 2 GPUs (LJ, 16 M per GPU, ms/step): bounded lifetime 0.592; reserved 2 / 3 / 4 SMs 0.633 / 0.574 / 0.564
+// (one GPU, no exchange: 0.538).  Checked once per device that the SM ids 0 .. reserved-1 exist.
+__global__ void k_smid_probe(int *__restrict__ seen) {
+  unsigned int smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+  if (threadIdx.x == 0 && smid < 64) seen[smid] = 1;
+}
+static inline int slab_reserved_sms(cudaStream_t stream) {
+  static int cache[64];
+  static bool done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 0;
+  if (!done[dev]) {
+    const char *e = getenv("MAVI_SLAB_RESERVED_SMS");
+    int want = e ? atoi(e) : 4;
+    if (want < 0) want = 0;
+    if (want > 32) want = 32;
+    int ok = 0;
+    if (want > 0) {
+      int *seen = nullptr;
+      int host[64] = {};
+      if (cudaMalloc((void **)&seen, 64 * sizeof(int)) == cudaSuccess) {
+        cudaMemsetAsync(seen, 0, 64 * sizeof(int), stream);
+        k_smid_probe<<<148 * 16, 64, 0, stream>>>(seen);  // far more CTAs than SMs: every SM gets some
+        cudaMemcpyAsync(host, seen, 64 * sizeof(int), cudaMemcpyDeviceToHost, stream);
+        cudaStreamSynchronize(stream);
+        cudaFree(seen);
+        ok = 1;
+        for (int i = 0; i < want; i++) ok = ok && host[i];
+      }
+    }
+    cache[dev] = ok ? want : 0;
+    done[dev] = true;
+  }
+  return cache[dev];
+}
+constexpr int PIPE_EXTRA_CTAS = 128;  // interior launch with reserved SMs: CTAs beyond one device-full (see above)
+
+static inline int grid_pipe(DevParams &p, cudaStream_t stream) {
+  const int items = blk_items_per_row(p) * p.tpc;
   static const int items_all = getenv("MAVI_PIPE_ITEMS_ALL") ? atoi(getenv("MAVI_PIPE_ITEMS_ALL")) : 0;  // diagnosis: bounded CTAs everywhere
-  p.pipe_items = p.blk_mode == 0 ? items_all : slab_pipe_items();
   const int want = 148 * PIPE_CTAS_PER_SM;
+  p.pipe_reserved = 0;
+  const int reserved = p.blk_mode == 0 ? 0 : slab_reserved_sms(stream);
+  if (reserved > 0) {
+    p.pipe_items = 0;
+    if (p.blk_mode == 1) {
+      p.pipe_reserved = reserved;
+      return want + PIPE_EXTRA_CTAS;
+    }
+    const int g = reserved * PIPE_CTAS_PER_SM;
+    return items < g ? (items > 0 ? items : 1) : g;
+  }
+  p.pipe_items = p.blk_mode == 0 ? items_all : slab_pipe_items();
   if (p.pipe_items > 0) {
     // one device-full of CTAs more than items / pipe_items: the last wave is then as wide as the others and the work counter
     // balances it (with exactly items / pipe_items CTAs the last, partial wave ran at a fraction of the device for a whole
@@ -1696,8 +1748,7 @@ static inline int grid_pipe(DevParams &p) {
 }
 
 static inline int grid2(const DevParams &p) {
-  const int per_row = p.blk_mode == 0 ? p.blk_per_row : (p.blk_mode == 1 ? p.blk_per_row - 1 - p.blk_last : 1 + p.blk_last);
-  return per_row * p.tpc + (p.blk_mode == 2 ? 0 : nblk(p.n - p.n_active));
+  return blk_items_per_row(p) * p.tpc + (p.blk_mode == 2 ? 0 : nblk(p.n - p.n_active));
 }
 
 template <int DYN, bool PER>
@@ -1945,7 +1996,7 @@ void launch_newton_b(const LaunchCtx &c, const DevParams &p_in, const DevArrays 
 #define CALLP__(D, P, CARRYV, CWV, NPV)                                                                             \
   do {                                                                                                              \
     MAVI_OPT_IN_SMEM((k_newton_p<D, P, CARRYV, CWV, NPV>), PIPE_SMEM);                                              \
-    const int grid_ = grid_pipe(p);                                                                                 \
+    const int grid_ = grid_pipe(p, c.stream);                                                                                \
     MAVI_LAUNCH(c, (k_newton_p<D, P, CARRYV, CWV, NPV>), grid_, (CWV + NPV) * 32, PIPE_SMEM, ARGS2);                \
   } while (0)
 #define CALLP_(D, P, CARRYV)                               \
@@ -2043,7 +2094,7 @@ void launch_self_propelled(const LaunchCtx &c, const DevParams &p, const DevArra
 #define CALLP_(D, P, CWV, NPV)                                                                                      \
   do {                                                                                                              \
     MAVI_OPT_IN_SMEM((k_self_propelled_p<D, P, CWV, NPV>), PIPE_SMEM);                                              \
-    const int grid_ = grid_pipe(pp);                                                                                \
+    const int grid_ = grid_pipe(pp, c.stream);                                                                                \
     MAVI_LAUNCH(c, (k_self_propelled_p<D, P, CWV, NPV>), grid_, (CWV + NPV) * 32, PIPE_SMEM, pp, a.tstart, a.idflag, a.pos[0], a.ang, a.pos[1], a.force, noise, step, ms); \
   } while (0)
 #define CALLP(D, P)                                  \

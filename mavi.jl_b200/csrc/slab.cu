@@ -11,6 +11,7 @@
 
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -151,6 +152,15 @@ int slab_configure(Handle *h, const MaviParams *mp) {
   if (!self) {
     ncclUniqueId id;
     memcpy(&id, mp->nccl_unique_id, sizeof id);
+    {
+      // The halo / migration messages are a few hundred KB: one or two channels carry them, and every channel is a CTA of
+      // NCCL's send/recv kernel that needs (almost) an SM to itself.  NCCL's default here is 32 channels, i.e. a kernel that
+      // wants 32 SMs next to a force pass that fills the device (2 GPUs: 0.671 ms/step with the default, 0.565 with <= 2
+      // channels and four reserved SMs, kernels.cu grid_pipe()).  Only a default: the caller's environment wins; NCCL
+      // reads the variable once per process, so a host that initialises NCCL itself first (bench.py under torchrun) sets it too.
+      static std::once_flag nccl_env_once;
+      std::call_once(nccl_env_once, [] { setenv("NCCL_MAX_P2P_NCHANNELS", "2", 0); });
+    }
     SLAB_NCCL(h, g_nccl.CommInitRank(&s.comm, s.world, id, s.rank));
   }
   {  // the side stream's small kernels must not queue behind the 16k blocks of the interior pass
@@ -457,7 +467,7 @@ int slab_step_once(Handle *h, const real *noise_dev) {
   // force carry (see k_newton_b): F1 and the drift of this step were produced by the previous one
   const bool carry = vel && !(h->flags_cfg & MAVI_FLAG_NO_FORCE_CARRY);
   static const bool nopipe = getenv("MAVI_SLAB_NOPIPE") != nullptr;  // debugging aid: everything on the main stream
-  const bool piped = carry && !nopipe && p.blk_per_row >= 4 && p.blk_cols >= 3 && s.m >= 8;
+  const bool piped = carry && !nopipe && s.m >= 2 * MAVI_EDGE_COLS + 2;
   if (h->prof) cudaEventRecord(h->ev[0], h->stream);
   launch_step_begin(c, a);
   tr.mark(1, h->stream);

@@ -15,6 +15,7 @@ nx = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 kind = sys.argv[3] if len(sys.argv) > 3 else "lj"
 flags = int(sys.argv[4]) if len(sys.argv) > 4 else 0   # MAVI_FLAG_* (32 = legacy staging kernels)
+pre = int(sys.argv[5]) if len(sys.argv) > 5 else 0     # steps before the timed region (2000: the thermalised lattice of bench.py's `hot`)
 if kind in ("lj", "ljself", "lj32"):
     # ljself: the x-slab machinery on one GPU (MAVI_FLAG_SLAB_SELF), for profiling the multi-GPU step on one rank
     w = bench.lj_workload(pkg, nx, nx, cuda_device=pkg.CUDADevice(flags=flags | (pkg.capi.FLAG_SLAB_SELF if kind == "ljself" else 0)))
@@ -37,7 +38,7 @@ else:
     case["int_cfg"] = rc.RingsIntCfg(dt=0.01, p_chunks_cfg=case["int_cfg"].chunks_cfg, device=pkg.CUDADevice(rng_mode="philox"))
     s = H.make_gpu_rings(case)
     n = case["num_rings"] * 10
-s.step(2)
+s.step(2 + pre)
 s.sync()
 t0 = time.perf_counter()
 s.step(steps)
