@@ -213,6 +213,10 @@ function attach!(system::System)
     if kind == 4 && !isnothing(system.info.p_neigh)      # RingsSystem(p_neighbors_cfg=...): before the upload, whose
         enable_particle_neighbors!(ds, system.info.p_neigh)   # forces! fills the lists like the reference's constructor
     end
+    if kind == 4                                           # sources / sinks / VarRingsIds and invasions: before the upload too
+        enable_sources!(ds, system, keep)
+        enable_invasions!(ds, system)
+    end
     upload_state!(system)
     finalizer(_ -> ccall((:mavi_destroy, LIB), Int32, (Ptr{Cvoid},), ds.h), ds)
     return ds
@@ -278,7 +282,11 @@ end
 # (src/rings/rings.jl:118-128; SURVEY.md A.2).  `noise` = one randn per ring and step in :host_noise mode.
 function Mavi.Rings.Integration.step!(system::CUDASystem; noise=nothing)
     device_step!(system, 1; noise=noise)
-    system.int_cfg.device.sync_every == 1 && sync_rings_info!(system)
+    if system.int_cfg.device.sync_every == 1
+        sync_rings_info!(system)
+        sync_rings_ids!(system)
+        sync_invasions!(system)
+    end
     return nothing
 end
 
@@ -345,6 +353,105 @@ function sync_particle_neighbors!(system)
     neigh.count[:, 1] .= count
     isnothing(neigh.list) || (neigh.list[:, :, 1] .= list .+ 1)            # back to 1-based ids (padding -1 -> 0)
     return neigh
+end
+
+"""
+Sources, sinks and a variable number of rings (src/rings/sources.jl, src/rings/states.jl:173-227): `RingsSystem(source_cfg=[...])`
+on a `RingsState(active_state=...)`.  The list goes to the device once (`mavi_rings_set_sources`, after `mavi_create`, before the
+upload); every `step!` then removes / spawns rings on the device side of the handle exactly where the reference does
+(src/rings/integration.jl:353-358,523-526).  `spawn_pol = :random` draws come from Philox on the device (`spawn_draws = NULL`);
+pass pre-drawn `rand(rng)` values instead for parity runs.  `sync_rings_ids!` brings `state.rings_ids` (mask, uids, ids,
+num_active) back where host code reads them.
+"""
+struct MaviSourceSink
+    kind::Int32; num_spawn_pos::Int32; spawn_pos::Ptr{Float64}
+    bottom_left::NTuple{2,Float64}; spawn_pol::Float64; pad::Float64; offset::NTuple{2,Float64}; size::NTuple{2,Int32}
+    sink_geom::Int32; _pad::Int32
+    sink_rect_bl::NTuple{2,Float64}; sink_rect_len::Float64; sink_rect_h::Float64
+    sink_circ_center::NTuple{2,Float64}; sink_circ_radius::Float64
+end
+
+function lower_source(src, keep)
+    cfg = src.cfg
+    if cfg isa Mavi.Rings.Sources.SourceCfg
+        sp = Float64[c for q in cfg.spawn_pos for c in q]
+        push!(keep, sp)
+        pol = cfg.spawn_pol isa Mavi.Rings.Sources.RandomPol ? NaN : Float64(cfg.spawn_pol)
+        return MaviSourceSink(0, length(cfg.spawn_pos), pointer(sp), Tuple(Float64.(cfg.bottom_left)), pol, cfg.pad,
+                              Float64.(cfg.offset), Int32.(cfg.size), 0, 0, (0.0, 0.0), 0.0, 0.0, (0.0, 0.0), 0.0)
+    end
+    g = cfg.geometry_cfg                                   # SinkCfg
+    if g isa RectangleCfg
+        return MaviSourceSink(1, 0, C_NULL, (0.0, 0.0), 0.0, 0.0, (0.0, 0.0), (Int32(0), Int32(0)), 0, 0,
+                              Tuple(Float64.(g.bottom_left)), g.length, g.height, (0.0, 0.0), 0.0)
+    elseif g isa CircleCfg
+        return MaviSourceSink(1, 0, C_NULL, (0.0, 0.0), 0.0, 0.0, (0.0, 0.0), (Int32(0), Int32(0)), 1, 0,
+                              (0.0, 0.0), 0.0, 0.0, Tuple(Float64.(g.center)), g.radius)
+    end
+    error("SinkCfg geometry $(typeof(g)) is not supported on the device")
+end
+
+function enable_sources!(ds::DeviceState, system, keep; spawn_draws=nothing)
+    ids = system.state.rings_ids
+    var = ids isa Mavi.Rings.States.VarRingsIds
+    srcs = system.info.sources
+    (var || !isnothing(srcs)) || return
+    list = isnothing(srcs) ? MaviSourceSink[] : [lower_source(s, keep) for s in srcs]
+    mask = var ? UInt8.(ids.mask) : UInt8[]
+    push!(keep, list); push!(keep, mask)
+    draws = isnothing(spawn_draws) ? Float64[] : Float64.(spawn_draws)
+    GC.@preserve list mask draws check(ds, ccall((:mavi_rings_set_sources, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{MaviSourceSink}, Int32, Ptr{UInt8}, Ptr{Float64}, Int64), ds.h,
+        isempty(list) ? C_NULL : pointer(list), length(list), isempty(mask) ? C_NULL : pointer(mask),
+        isempty(draws) ? C_NULL : pointer(draws), length(draws)))
+end
+
+function sync_rings_ids!(system)
+    ids = system.state.rings_ids
+    ids isa Mavi.Rings.States.VarRingsIds || return ids
+    ds = handle(system)
+    nr = length(ids.mask)
+    mask, uids, na = Vector{UInt8}(undef, nr), Vector{Int64}(undef, nr), Ref{Int64}(0)
+    GC.@preserve mask uids check(ds, ccall((:mavi_rings_download_active, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{UInt8}, Ptr{Int64}, Ref{Int64}), ds.h, pointer(mask), pointer(uids), na))
+    ids.mask .= mask .!= 0
+    ids.uids .= uids
+    Mavi.States.update_ids!(system.state)                 # calc_active_ids! on the host copy (ids, p_ids, counts)
+    return ids
+end
+
+"""
+Ring invasions (src/rings/integration.jl:379-520): `RingsIntCfg(invasions_cfg=InvasionsCfg(steps_to_update), r_chunks_cfg=...)`.
+The device checks every `steps_to_update` steps before the forces of that step; `sync_invasions!` refills
+`system.info.invasions.list` (1-based ids, sorted; the reference lists them in pair-enumeration order).
+"""
+function enable_invasions!(ds::DeviceState, system)
+    extra = system.int_cfg.extra
+    (isnothing(extra) || isnothing(extra.invasions_cfg)) && return
+    rc = extra.r_chunks_cfg
+    check(ds, ccall((:mavi_rings_set_invasions, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Int32), ds.h,
+        extra.invasions_cfg.steps_to_update, isnothing(rc) ? 0 : rc.num_cols, isnothing(rc) ? 0 : rc.num_rows))
+end
+
+function sync_invasions!(system)
+    inv = system.info.invasions
+    extra = system.int_cfg.extra
+    (isnothing(extra) || isnothing(extra.invasions_cfg)) && return inv     # invasions are off
+    ds = handle(system)
+    cap = 4096
+    while true
+        n, tri = Ref{Int64}(0), Matrix{Int32}(undef, 3, cap)
+        GC.@preserve tri check(ds, ccall((:mavi_rings_download_invasions, LIB), Int32,
+            (Ptr{Cvoid}, Ref{Int64}, Ptr{Int32}, Int64), ds.h, n, pointer(tri), cap))
+        if n[] <= cap
+            empty!(inv.list)
+            for k in 1:n[]
+                push!(inv.list, Mavi.Rings.Invasion(invasor=tri[1, k] + 1, invaded=tri[2, k] + 1, p_id=tri[3, k] + 1))
+            end
+            return inv
+        end
+        cap = n[]
+    end
 end
 
 end # module
