@@ -65,6 +65,7 @@ typedef struct MaviLine {
 
 /* One (wall_type, geometry_cfg) pair of a SpaceCfg (src/configs.jl:285-302).  spaces[0] is the
  * main wall/geometry (get_main_wall / get_main_geometry, src/configs.jl:304-312). */
+#define MAVI_MAX_POT_TYPES 4
 typedef struct MaviSpace {
   int32_t wall;          /* MAVI_WALL_* */
   int32_t geom;          /* MAVI_GEOM_* */
@@ -78,7 +79,9 @@ typedef struct MaviSpace {
   int32_t pot_kind;      /* PotentialWalls.potential: MAVI_POT_* */
   double pot[4];         /* HarmTrunc: k_rep,k_atr,dist_eq,dist_max; LJ: sigma,epsilon */
   int32_t pot_mode;      /* MAVI_WALLMODE_* */
-  int32_t _pad;
+  int32_t n_pot_types;   /* 0: `pot` for every particle; > 0: PotentialVector (src/configs.jl:454-463), pot_types[t] for particles
+                          * of type t + 1 (get_particle_type: the ring type — Mavi.Rings states only), all of kind pot_kind */
+  double pot_types[MAVI_MAX_POT_TYPES][4];
 } MaviSpace;
 
 /* RingsCfg + RingsState layout (src/rings/configs.jl:95-107, src/rings/states.jl:74-124).

@@ -42,13 +42,17 @@ class MaviLine(C.Structure):
     _fields_ = [("p1", C.c_double * 2), ("p2", C.c_double * 2)]
 
 
+MAVI_MAX_POT_TYPES = 4
+
+
 class MaviSpace(C.Structure):
     _fields_ = [
         ("wall", C.c_int32), ("geom", C.c_int32),
         ("rect_bl", C.c_double * 2), ("rect_len", C.c_double), ("rect_h", C.c_double),
         ("circ_center", C.c_double * 2), ("circ_radius", C.c_double),
         ("lines", C.POINTER(MaviLine)), ("n_lines", C.c_int32),
-        ("pot_kind", C.c_int32), ("pot", C.c_double * 4), ("pot_mode", C.c_int32), ("_pad", C.c_int32),
+        ("pot_kind", C.c_int32), ("pot", C.c_double * 4), ("pot_mode", C.c_int32), ("n_pot_types", C.c_int32),
+        ("pot_types", (C.c_double * 4) * MAVI_MAX_POT_TYPES),
     ]
 
 

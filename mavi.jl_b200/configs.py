@@ -126,6 +126,12 @@ class ForceWalls(WallType):
 
 
 @dataclass
+class PotentialVector:
+    """src/configs.jl:454-463: one wall potential per particle type (get_particle_type: the ring type of a Mavi.Rings state)."""
+    vector: list
+
+
+@dataclass
 class PotentialWalls(ForceWalls):
     """src/configs.jl:263-279.  mode in {'outside','inside','repulsion'} (process_dist :259-261)."""
     potential: object

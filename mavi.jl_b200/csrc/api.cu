@@ -109,6 +109,19 @@ static int validate_and_lower(Handle *h, const MaviParams *mp) {
     d.pot_kind = s.pot_kind;
     for (int i = 0; i < 4; i++) d.pot[i] = s.pot[i];
     d.pot_mode = s.pot_mode;
+    d.n_pot_types = 0;
+    if (s.wall == MAVI_WALL_POTENTIAL && s.n_pot_types != 0) {
+      // PotentialVector: get_particle_type exists for RingsState only (src/rings/states.jl:148); one entry per ring type
+      if (mp->dynamics != MAVI_DYN_RINGS || !mp->rings || s.n_pot_types != mp->rings->num_types ||
+          s.n_pot_types < 0 || s.n_pot_types > MAVI_MAX_POT_TYPES) {
+        h->set_error("PotentialVector needs a Mavi.Rings state with types and one potential per ring type (<= %d), got %d",
+                     MAVI_MAX_POT_TYPES, s.n_pot_types);
+        return MAVI_ERR_BAD_PARAMS;
+      }
+      d.n_pot_types = s.n_pot_types;
+      for (int t = 0; t < s.n_pot_types; t++)
+        for (int i = 0; i < 4; i++) d.pot_t[t][i] = (real)s.pot_types[t][i];
+    }
     d.n_lines = 0;
     d.lines = nullptr;
     if (s.wall == MAVI_WALL_POTENTIAL) {

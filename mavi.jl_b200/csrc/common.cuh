@@ -25,6 +25,8 @@ struct DevSpace {
   real pot[4];
   real pot_cut2;  // largest r2 with sqrt(r2) <= dist_max (exact cutoff test without sqrt)
   int pot_mode;
+  int n_pot_types;                      // PotentialVector: pot_t[type] instead of pot (Mavi.Rings: the ring type)
+  real pot_t[MAVI_MAX_POT_TYPES][4];
 };
 
 struct DevRings {

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(TPB) k_rings_pair(const __grid_constant__ DevP
         cur++;
       }
     }
-    if (with_walls && p.has_force_walls) wall_forces(p, ri.x, ri.y, fx, fy);
+    if (with_walls && p.has_force_walls) wall_forces(p, ri.x, ri.y, fx, fy, ti);
   }
   fpair[i] = make_real2(fx, fy);
 }

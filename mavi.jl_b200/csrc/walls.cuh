@@ -7,16 +7,16 @@ namespace MAVI_NS {
 
 // potential_force(dr, dist, potential) with an explicit (possibly signed) dist, as PotentialWalls uses it
 // (src/configs.jl:354-368, :389-397).  Per particle, not per pair: written like the reference.
-__device__ __forceinline__ void wall_potential_force(const DevSpace &sp, real drx, real dry, real dist, real &fx,
-                                                     real &fy) {
+__device__ __forceinline__ void wall_potential_force(const DevSpace &sp, const real *pot, real drx, real dry, real dist,
+                                                     real &fx, real &fy) {
   real c;
   if (sp.pot_kind == MAVI_POT_HARMTRUNC) {
-    if (dist > sp.pot[3]) return;
-    real k = (dist < sp.pot[2]) ? sp.pot[0] : sp.pot[1];
-    real fmod_ = -k * (dist / sp.pot[2] - 1.0);
+    if (dist > pot[3]) return;
+    real k = (dist < pot[2]) ? pot[0] : pot[1];
+    real fmod_ = -k * (dist / pot[2] - 1.0);
     c = fmod_ / dist;
   } else {
-    real sigma = sp.pot[0], eps = sp.pot[1];
+    real sigma = pot[0], eps = pot[1];
     real s6 = sigma * sigma * sigma * sigma * sigma * sigma;
     real d2 = dist * dist, d6 = d2 * d2 * d2, d7 = d6 * dist;
     real fmod_ = 4.0 * eps * (12.0 * s6 * s6 / (d6 * d7) - 6.0 * s6 / d7);
@@ -34,10 +34,12 @@ __device__ __forceinline__ real process_dist(int mode, real dist, real flag) {
 }
 
 // calc_walls_forces! for one particle: every PotentialWalls sub-space acts (ManyWalls loop, :258-264).
-__device__ __forceinline__ void wall_forces(const DevParams &p, real x, real y, real &fx, real &fy) {
+// ptype: get_particle_type(state, i) - 1 (the ring type; 0 for states without types), selects the PotentialVector entry.
+__device__ __forceinline__ void wall_forces(const DevParams &p, real x, real y, real &fx, real &fy, int ptype = 0) {
   for (int k = 0; k < p.n_spaces; k++) {
     const DevSpace &sp = p.spaces[k];
     if (sp.wall != MAVI_WALL_POTENTIAL) continue;
+    const real *pot = sp.n_pot_types > 0 ? sp.pot_t[ptype] : sp.pot;
     if (sp.geom == MAVI_GEOM_CIRCLE) {
       // signed_pos(point, ::CircleCfg), src/configs.jl:154-163
       real d0 = x - sp.cc[0], d1 = y - sp.cc[1];
@@ -45,7 +47,7 @@ __device__ __forceinline__ void wall_forces(const DevParams &p, real x, real y, 
       real drx = d0 - (d0 / dd) * sp.cr, dry = d1 - (d1 / dd) * sp.cr;
       real sd = dd - sp.cr;
       real dist = process_dist(sp.pot_mode, fabs(sd), sign_d(sd));
-      wall_potential_force(sp, drx, dry, dist, fx, fy);
+      wall_potential_force(sp, pot, drx, dry, dist, fx, fy);
     } else if (sp.geom == MAVI_GEOM_LINES) {
       for (int l = 0; l < sp.n_lines; l++) {
         // signed_pos(point, ::Line2D), src/configs.jl:119-135
@@ -62,7 +64,7 @@ __device__ __forceinline__ void wall_forces(const DevParams &p, real x, real y, 
           }
         }
         real dist = process_dist(sp.pot_mode, sqrt(drx * drx + dry * dry), 1.0);
-        wall_potential_force(sp, drx, dry, dist, fx, fy);
+        wall_potential_force(sp, pot, drx, dry, dist, fx, fy);
       }
     }
   }

@@ -59,7 +59,8 @@ struct MaviSpace
     pot_kind::Int32
     pot::NTuple{4,Float64}
     pot_mode::Int32
-    _pad::Int32
+    n_pot_types::Int32                  # PotentialVector (src/configs.jl:454-463): pot_types[t] for particles of type t
+    pot_types::NTuple{16,Float64}       # [MAVI_MAX_POT_TYPES = 4][4], row-major
 end
 
 struct MaviRingsParams
@@ -104,28 +105,38 @@ struct MaviParams
 end
 
 const WALL = Dict(RigidWalls => 0, PeriodicWalls => 1, SlipperyWalls => 2)
-zero_space() = MaviSpace(0, 0, (0.0, 0.0), 0.0, 0.0, (0.0, 0.0), 0.0, C_NULL, 0, 0, (0.0, 0.0, 0.0, 0.0), 0, 0)
+zero_space() = MaviSpace(0, 0, (0.0, 0.0), 0.0, 0.0, (0.0, 0.0), 0.0, C_NULL, 0, 0, (0.0, 0.0, 0.0, 0.0), 0, 0, ntuple(_ -> 0.0, 16))
 
 function lower_space(w, g, keep)
     wall = w isa PotentialWalls ? Int32(3) : Int32(WALL[typeof(w)])
     pot_kind, pot, mode = Int32(0), (0.0, 0.0, 0.0, 0.0), Int32(2)
+    npt, pts = Int32(0), zeros(Float64, 16)
+    pot_of(p) = p isa LenJonesCfg ? (Int32(1), (Float64(p.sigma), Float64(p.epsilon), 0.0, 0.0)) :
+                (Int32(0), (Float64(p.k_rep), Float64(p.k_atr), Float64(p.dist_eq), Float64(p.dist_max)))
     if w isa PotentialWalls
         p = w.potential
-        if p isa LenJonesCfg
-            pot_kind, pot = Int32(1), (Float64(p.sigma), Float64(p.epsilon), 0.0, 0.0)
+        if p isa Configs.PotentialVector                  # one potential per particle (ring) type, all of one kind
+            length(p.vector) <= 4 || error("PotentialVector: at most 4 types on the device")
+            npt = Int32(length(p.vector))
+            for (t, q) in enumerate(p.vector)
+                pot_kind, pq = pot_of(q)
+                pts[4t-3:4t] .= pq
+                t == 1 && (pot = pq)
+            end
         else
-            pot = (Float64(p.k_rep), Float64(p.k_atr), Float64(p.dist_eq), Float64(p.dist_max))
+            pot_kind, pot = pot_of(p)
         end
         mode = w.mode isa Configs.Outside ? Int32(0) : w.mode isa Configs.Inside ? Int32(1) : Int32(2)
     end
+    pts = Tuple(pts)
     if g isa RectangleCfg
-        return MaviSpace(wall, 0, Tuple(Float64.(g.bottom_left)), g.length, g.height, (0.0, 0.0), 0.0, C_NULL, 0, pot_kind, pot, mode, 0)
+        return MaviSpace(wall, 0, Tuple(Float64.(g.bottom_left)), g.length, g.height, (0.0, 0.0), 0.0, C_NULL, 0, pot_kind, pot, mode, npt, pts)
     elseif g isa CircleCfg
-        return MaviSpace(wall, 1, (0.0, 0.0), 0.0, 0.0, Tuple(Float64.(g.center)), g.radius, C_NULL, 0, pot_kind, pot, mode, 0)
+        return MaviSpace(wall, 1, (0.0, 0.0), 0.0, 0.0, Tuple(Float64.(g.center)), g.radius, C_NULL, 0, pot_kind, pot, mode, npt, pts)
     else
         lines = [MaviLine(Tuple(Float64.(l.p1)), Tuple(Float64.(l.p2))) for l in g.lines]
         push!(keep, lines)
-        return MaviSpace(wall, 2, (0.0, 0.0), 0.0, 0.0, (0.0, 0.0), 0.0, pointer(lines), length(lines), pot_kind, pot, mode, 0)
+        return MaviSpace(wall, 2, (0.0, 0.0), 0.0, 0.0, (0.0, 0.0), 0.0, pointer(lines), length(lines), pot_kind, pot, mode, npt, pts)
     end
 end
 

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import capi
 from .configs import (CircleCfg, CUDADevice, HarmTruncCfg, LenJonesCfg, LinesCfg, ManyGeometries, PeriodicWalls,
-                      PotentialWalls, RectangleCfg, RigidWalls, RunTumbleCfg, SlipperyWalls, SpaceCfg, SzaboCfg,
+                      PotentialVector, PotentialWalls, RectangleCfg, RigidWalls, RunTumbleCfg, SlipperyWalls, SpaceCfg, SzaboCfg,
                       get_bounding_box, particle_radius)
 
 _MODES = {"outside": capi.WALLMODE_OUTSIDE, "inside": capi.WALLMODE_INSIDE, "repulsion": capi.WALLMODE_REPULSION}
@@ -38,7 +38,7 @@ def _potential(pot):
         return capi.POT_LJ, [pot.sigma, pot.epsilon, 0.0, 0.0]
     if hasattr(pot, "k_rep") and hasattr(pot, "dist_max"):
         return capi.POT_HARMTRUNC, [pot.k_rep, pot.k_atr, pot.dist_eq, pot.dist_max]
-    raise TypeError(f"unsupported wall potential {type(pot).__name__} (PotentialVector is out of scope)")
+    raise TypeError(f"unsupported wall potential {type(pot).__name__}")
 
 
 def lower(state, space_cfg: SpaceCfg, dynamic_cfg, int_cfg) -> LoweredParams:
@@ -65,8 +65,24 @@ def lower(state, space_cfg: SpaceCfg, dynamic_cfg, int_cfg) -> LoweredParams:
             sp.wall = capi.WALL_SLIPPERY
         elif isinstance(w, PotentialWalls):
             sp.wall = capi.WALL_POTENTIAL
-            sp.pot_kind, pot = _potential(w.potential)
-            sp.pot[:] = pot
+            if isinstance(w.potential, PotentialVector):   # one entry per particle (ring) type, all of one kind
+                # get_particle_type(state, pid) has a method for RingsState only (src/rings/states.jl:148): with any other
+                # state the reference's calc_walls_forces! ends in a MethodError, and types index the vector
+                if not isinstance(dynamic_cfg, RingsCfg) or getattr(state, "types", None) is None:
+                    raise TypeError("PotentialVector needs a RingsState with types (get_particle_type)")
+                if len(w.potential.vector) != dynamic_cfg.num_types:
+                    raise ValueError(f"PotentialVector has {len(w.potential.vector)} entries for {dynamic_cfg.num_types} ring types")
+                kinds = [_potential(q) for q in w.potential.vector]
+                if not kinds or len(kinds) > capi.MAVI_MAX_POT_TYPES or len({k for k, _ in kinds}) != 1:
+                    raise ValueError(f"PotentialVector: 1..{capi.MAVI_MAX_POT_TYPES} potentials of one kind")
+                sp.pot_kind = kinds[0][0]
+                sp.pot[:] = kinds[0][1]
+                sp.n_pot_types = len(kinds)
+                for t, (_, pot) in enumerate(kinds):
+                    sp.pot_types[t][:] = pot
+            else:
+                sp.pot_kind, pot = _potential(w.potential)
+                sp.pot[:] = pot
             sp.pot_mode = _MODES[w.mode]
         else:
             raise TypeError(f"unsupported wall type {type(w).__name__}")

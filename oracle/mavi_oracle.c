@@ -494,16 +494,20 @@ void mor_walls_forces(OrSystem *s) {
       int64_t i = s->ids[q];
       const double *pt = s->pos + 2 * i;
       double dr[2], dist, flag, f[2];
+      /* get_potential_cfg(wall_pot.potential, state, i), src/integration.jl:237,248: PotentialVector picks the entry of the
+       * particle's type (src/configs.jl:454-463) = the type of its ring (src/rings/states.jl:148) */
+      const double *pot = sp->pot;
+      if (sp->n_pot_types > 0) pot = sp->pot_types[s->p.dynamics == MAVI_DYN_RINGS ? ring_type(s, i / s->rp.n_max) : 0];
       if (sp->geom == MAVI_GEOM_CIRCLE) {
         signed_pos_circle(pt, sp, dr, &dist, &flag);
         dist = process_dist(sp->pot_mode, dist, flag);
-        mor_potential_force(sp->pot_kind, sp->pot, dr, dist, f);
+        mor_potential_force(sp->pot_kind, pot, dr, dist, f);
         forces[2 * i] += f[0]; forces[2 * i + 1] += f[1];
       } else if (sp->geom == MAVI_GEOM_LINES) {
         for (int l = 0; l < sp->n_lines; l++) {
           signed_pos_line(pt, &s->lines[k][l], dr, &dist);
           dist = process_dist(sp->pot_mode, dist, 1.0);
-          mor_potential_force(sp->pot_kind, sp->pot, dr, dist, f);
+          mor_potential_force(sp->pot_kind, pot, dr, dist, f);
           forces[2 * i] += f[0]; forces[2 * i + 1] += f[1];
         }
       }

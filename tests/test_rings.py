@@ -296,3 +296,74 @@ def test_rings_gpu_contact_lists(cuda_lib, kind, chunks, ntype):
             if not only_count:
                 assert lg == [sorted(l) for l in lo]
         assert cg.sum() > 0
+
+
+# ---------------------------------------------------------------- PotentialVector: one wall potential per ring type
+def _potential_vector_case(potential):
+    """create_system_types rings (two ring types) in a periodic box with a PotentialWalls circle (mode outside) in the middle
+    and a PotentialWalls line: `potential` is a single HarmTruncCfg or a PotentialVector with one entry per ring type
+    (src/configs.jl:454-463; get_particle_type = the ring type, src/rings/states.jl:148)."""
+    case = H.rings_case("types", 8, 8)
+    geom = case["geom"]
+    bl = np.asarray(geom.bottom_left)
+    circle = pkg.CircleCfg(radius=1.3, center=[bl[0] + geom.length / 2, bl[1] + geom.height / 2])
+    line = pkg.LinesCfg([[(bl[0] + geom.length / 4, bl[1] + geom.height / 4), (bl[0] + geom.length / 4, bl[1] + 3 * geom.height / 4)]])
+    case["space"] = pkg.SpaceCfg([(pkg.PeriodicWalls(), geom), (pkg.PotentialWalls(potential=potential, mode="outside"), circle),
+                                  (pkg.PotentialWalls(potential=potential), line)])
+    return case
+
+
+def _wall_pots():
+    from mavi_jl_b200.rings import configs as rc
+    return (rc.HarmTruncCfg(k_rep=30, k_atr=0, dist_eq=0.6, dist_max=0.7), rc.HarmTruncCfg(k_rep=11, k_atr=2, dist_eq=0.9, dist_max=1.2))
+
+
+def test_oracle_potential_vector_selects_by_ring_type(oracle):
+    """The forces of a PotentialVector([A, B]) run are those of a PotentialWalls(A) run for the particles of type-1 rings and
+    those of a PotentialWalls(B) run for the particles of type-2 rings (same state; calc_forces! only)."""
+    pa, pb = _wall_pots()
+    outs = []
+    for pot in (pkg.PotentialVector([pa, pb]), pa, pb):
+        o = H.make_oracle(_potential_vector_case(pot))
+        o.calc_forces()
+        outs.append(o.get_forces().copy())
+    case = _potential_vector_case(pa)
+    st = case["mk"]()
+    n_max = st.rings_pos.shape[1]
+    ptype = np.repeat(np.asarray(st.types), n_max)          # type of every particle slot (1-based), ring-ordered
+    fv, fa, fb = outs
+    assert np.array_equal(fv[ptype == 1], fa[ptype == 1]) and np.array_equal(fv[ptype == 2], fb[ptype == 2])
+    assert not np.array_equal(fa, fb)                        # the two potentials do act differently on this state
+
+
+def test_potential_vector_rejected_without_ring_types(oracle):
+    """get_particle_type exists for RingsState only: a PotentialVector on a particle system is a constructor error; so is a
+    vector whose length is not the number of ring types."""
+    pa, pb = _wall_pots()
+    case = H.newton_case(nx=8, ny=8)
+    geom = case["geom"]
+    circle = pkg.CircleCfg(radius=1.0, center=[geom.length / 2, geom.height / 2])
+    case["space"] = pkg.SpaceCfg([(pkg.PeriodicWalls(), geom), (pkg.PotentialWalls(potential=pkg.PotentialVector([pa, pb]), mode="outside"), circle)])
+    with pytest.raises(TypeError, match="RingsState with types"):
+        H.make_oracle(case)
+    with pytest.raises(ValueError, match="3 entries for 2 ring types"):
+        H.make_oracle(_potential_vector_case(pkg.PotentialVector([pa, pb, pa])))
+
+
+@pytest.mark.gpu
+def test_gpu_potential_vector_matches_oracle(cuda_lib):
+    pa, pb = _wall_pots()
+    case = _potential_vector_case(pkg.PotentialVector([pa, pb]))
+    g, o = H.make_gpu_rings(case), H.make_oracle(case)
+    nr = case["num_rings"]
+    g.calc_forces()
+    o.calc_forces()
+    assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-12
+    rng = np.random.default_rng(12)
+    for _ in range(2):
+        noise = rng.standard_normal((40, nr))
+        g.step(40, noise)
+        o.step(40, noise)
+        g.sync_to_host()
+        assert np.abs(g.state.pos - o.pos()).max() / case["geom"].length < 1e-11
+        assert H.rel_err(g.get_forces(), o.get_forces()) < 1e-9
