@@ -341,7 +341,6 @@ int Handle::alloc_state(int n_active, int cap) {
       p.blk_cols = g < 1 ? 1 : (g > 30 ? 30 : g);
       if (flags_cfg & MAVI_FLAG_SMALL_BLOCKS) p.blk_cols = 3;
       p.blk_per_row = (p.ord_cols + p.blk_cols - 1) / p.blk_cols;
-      p.blk_last = (p.ord_cols - (p.blk_per_row - 1) * p.blk_cols) >= 3 ? 1 : 2;
       p.blk_mode = 0;
     }
   } else {
@@ -349,7 +348,6 @@ int Handle::alloc_state(int n_active, int cap) {
     p.tail_base = 0;
     p.inbox_cap = p.mv_cap = p.chg_cap = 0;
     p.blk_cols = p.blk_per_row = p.blk_mode = 0;
-    p.blk_last = 1;
   }
   ns = (size_t)p.tail_base + (size_t)(p.slab ? 0 : (p.n - p.n_active));
   int st;

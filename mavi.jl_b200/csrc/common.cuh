@@ -64,7 +64,6 @@ struct DevParams {
   int pipe_reserved;  // pipelined kernels: CTAs that land on an SM with %smid < pipe_reserved exit at once (slab step, grid_pipe())
   int blk_mode;   // 0: all blocks; 1: the interior of every tile row (all owned columns but MAVI_EDGE_COLS at each end, in blocks
                   // of blk_cols); 2: the two edge blocks of every tile row (MAVI_EDGE_COLS columns each) — blk_items_per_row()
-  int blk_last;   // (unused)
   // x-slab domain decomposition (one process per GPU): the local grid is [left halo | owned columns | right halo];
   // cell arithmetic stays GLOBAL (bit-exact global cell ids), only the column index is shifted into the local frame.
   int slab;                   // 1 = slab mode

@@ -415,10 +415,10 @@ struct SlabTrace {
     cudaStreamSynchronize(side);
     int f[FLAG_COUNT];
     cudaMemcpy(f, flags_dev, sizeof f, cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[slab trace rank %d] flags: err=%d dirty=%d bigmove=%d nfix=%d nmv=%d ran=%d overflow=%d nchg=%d bigmove_next=%d nem=%d,%d nemr=%d,%d | n=%d cap=%d blk_cols=%d bpr=%d blk_last=%d cols=%d fast_interior=%d\n",
+    fprintf(stderr, "[slab trace rank %d] flags: err=%d dirty=%d bigmove=%d nfix=%d nmv=%d ran=%d overflow=%d nchg=%d bigmove_next=%d nem=%d,%d nemr=%d,%d | n=%d cap=%d blk_cols=%d bpr=%d cols=%d fast_interior=%d\n",
             rank, f[FLAG_ERR], f[FLAG_CHANGED], f[FLAG_BIGMOVE], f[FLAG_NFIX], f[FLAG_NMV], f[FLAG_RAN], f[FLAG_OVERFLOW], f[FLAG_NCHG],
             f[FLAG_BIGMOVE_NEXT], f[FLAG_NEM0], f[FLAG_NEM1], f[FLAG_NEMR0], f[FLAG_NEMR1], p.n, p.cap, p.blk_cols, p.blk_per_row,
-            p.blk_last, p.num_cols, p.fast_interior);
+            p.num_cols, p.fast_interior);
     const char *names[N] = {"start", "step_begin", "K_int done", "fixes done (after side wait)", "migrate+ingest", "repair+redrift",
                             "side: C (halo X+layout) done", "interior recompute done", "side: K_bnd start", "side: bnd recompute + A(next) done", "side: K_bnd done", ""};
     for (int i = 1; i < 11; i++) {
