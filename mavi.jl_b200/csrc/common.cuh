@@ -383,17 +383,32 @@ __device__ __forceinline__ void philox_uniform2(unsigned long long seed, unsigne
   u1 = u01_from_bits(c[2], c[3]);
 }
 
+// Philox2x32-10 (Salmon et al., same construction with one multiplier): 64-bit counter, 32-bit key — half the multiplies of
+// the 4x32 generator for the draws that need only two words.
+__device__ __forceinline__ void philox2x32(unsigned int &c0, unsigned int &c1, unsigned int k) {
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    const unsigned int hi = __umulhi(0xD256D193u, c0), lo = 0xD256D193u * c0;
+    c0 = hi ^ k ^ c1;
+    c1 = lo;
+    k += 0x9E3779B9u;
+  }
+}
+
 // one standard normal (Box-Muller) for (id, step).  Production-mode noise only has to be N(0,1) to statistical accuracy
 // (the reference draws from Julia's ziggurat randn, which no device stream can reproduce), so the transform runs in single
-// precision: 24-bit uniforms, u0 in (0,1) -> |z| <= sqrt(2 ln 2^25) = 5.9; about 5x fewer instructions than the
-// double-precision log / cospi (the Szabo kernel spent 19 % of its instructions here, profiles/r01_ncu_szabo_rings.md).
+// precision with the hardware log / cos: 24-bit uniforms, u0 in (0,1) -> |z| <= sqrt(2 ln 2^25) = 5.9.  counter = (id, low
+// step word), key = seed and high step word folded into 32 bits.  (The Szabo kernel spent 19 % of its instructions in the
+// double-precision transform in round 1, profiles/r01_ncu_szabo_rings.md, and ~11 % in Philox4x32 + logf / cospif after that.)
 __device__ __forceinline__ double philox_normal(unsigned long long seed, unsigned int id, unsigned long long step) {
-  unsigned int c[4] = {id, (unsigned int)step, (unsigned int)(step >> 32), 0x4d415649u};
-  philox4x32(c, (unsigned int)seed, (unsigned int)(seed >> 32));
-  const float u0 = ((float)(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
-  const float u1 = (float)(c[2] >> 8) * (1.0f / 16777216.0f);           // [0,1)
-  const float r = sqrtf(-2.0f * logf(u0));
-  return (double)(r * cospif(2.0f * u1));
+  unsigned int c0 = id, c1 = (unsigned int)step;
+  const unsigned int key = (unsigned int)seed ^ ((unsigned int)(seed >> 32) * 0x9E3779B9u) ^
+                           ((unsigned int)(step >> 32) * 0x85EBCA6Bu) ^ 0x4d415649u;
+  philox2x32(c0, c1, key);
+  const float u0 = ((float)(c0 >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+  const float u1 = (float)(c1 >> 8) * (1.0f / 16777216.0f);           // [0,1)
+  const float r = sqrtf(-2.0f * __logf(u0));
+  return (double)(r * __cosf(6.2831853f * u1));
 }
 
 __device__ __forceinline__ real sign_d(real x) { return x > real(0) ? real(1) : (x < real(0) ? real(-1) : x); }
