@@ -275,6 +275,10 @@ def run_reference(args):
     # the metric's own workload (16M) when the host has the memory for the reference's cell table (1.9 GB) + state,
     # else a bounded 1M sample of the same lattice (same density and particles per cell)
     full = host_mem_available_gb() > 24.0 and not args.cpu_small
+    # ... and when `steps + warmup` passes over it end within a few minutes at the ~7e6 particle-steps/s the host cores reach
+    # (16 M x 20 steps = 45 s; 200 steps would be 7 minutes -> the 1 M sample, same lattice, rate-normalised)
+    if full and (args.steps + args.warmup) * args.nx * args.ny / 7.0e6 > 150.0:
+        full = False
     nx, ny = (args.nx, args.ny) if full else (args.cpu_sample, args.cpu_sample)
     rate, secs, threads, sample = cpu_reference_rate(pkg, args.steps, args.warmup, nx=nx, ny=ny)
     line = {
